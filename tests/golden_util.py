@@ -1,0 +1,47 @@
+"""Helpers shared by the golden-vector tests (CPU oracle tests and GPU parity tests)."""
+from __future__ import annotations
+
+import glob
+import os
+
+import numpy as np
+import torch
+
+from oracle import idee_oracle as O
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def load_case(name):
+    d = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    cfg = O.OracleConfig(in_vars=int(d["cfg_in_vars"]), in_chans=int(d["cfg_in_chans"]))
+    sd = {k[3:]: torch.from_numpy(d[k]) for k in d.files if k.startswith("sd/")}
+    grads = {k[5:]: torch.from_numpy(d[k]) for k in d.files if k.startswith("grad/")}
+    ins = {k[3:]: torch.from_numpy(d[k]) for k in d.files if k.startswith("in/")}
+    train = {k[6:]: torch.from_numpy(d[k]) for k in d.files if k.startswith("train/")}
+    ev = {k[5:]: torch.from_numpy(d[k]) for k in d.files if k.startswith("eval/")}
+    return cfg, sd, ins, train, ev, grads
+
+
+def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
+    """max-norm relative error ||a-b||_inf / max(||b||_inf, tiny)."""
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+
+def lfq_scalar(sd, z_enc: torch.Tensor) -> torch.Tensor:
+    """pre-quantiser scalar s per token from an encoder output [N,V,C,T,H,W] (LFQ.py:211)."""
+    w, b = sd["vq.project_in.weight"], sd["vq.project_in.bias"]
+    return torch.einsum("nvcthw,c->nvthw", z_enc.double().cpu(), w[0].double().cpu()) + b.double().cpu()
+
+
+def mask_agreement(anom_a, anom_b, s: torch.Tensor, tie_tol: float):
+    """fraction of equal mask elements, and whether every mismatch is a near-tie |s| < tie_tol."""
+    a = anom_a.cpu().long().reshape(-1)
+    b = anom_b.cpu().long().reshape(-1)
+    neq = a != b
+    frac = 1.0 - float(neq.float().mean())
+    ties_ok = bool((s.reshape(-1)[neq].abs() < tie_tol).all()) if neq.any() else True
+    return frac, ties_ok
