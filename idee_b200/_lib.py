@@ -1,0 +1,107 @@
+"""ctypes binding of libidee_b200.so (the C ABI declared in include/idee_b200.h).
+
+There is no fallback: if the library is missing and cannot be built, or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import torch
+
+from . import build as _build
+
+c_i64, c_int, c_f32, c_vp, c_sz = C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_size_t
+
+
+class SwinDesc(C.Structure):
+    _fields_ = [(n, c_int) for n in ("N", "V", "T", "H", "W", "C", "heads", "hidden", "wd", "wh", "ww", "st", "sh", "sw", "rpb_rows")] + \
+               [("scale", c_f32), ("param_stride", c_i64)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [(n, c_int) for n in ("N", "V", "Vw", "Cin", "Cout", "Ti", "Hi", "Wi", "To", "Ho", "Wo", "proj", "relu")] + \
+               [(n, c_i64) for n in ("x_sn", "x_sv", "x_st", "x_sh", "x_sw", "x_sg")] + [("in_cpg", c_int)] + \
+               [(n, c_i64) for n in ("y_sn", "y_sv", "y_st", "y_sh", "y_sw", "y_sg")] + [("out_cpg", c_int)]
+
+
+_SIGS = {
+    "idee_last_error": (C.c_char_p, []),
+    "idee_version": (c_int, []),
+    "idee_check_device": (c_int, []),
+    "idee_embed_ln_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp] + [c_int] * 7 + [c_vp]),
+    "idee_embed_ln_bwd_workspace_bytes": (c_sz, [c_int]),
+    "idee_embed_ln_bwd": (c_int, [c_vp] * 7 + [c_int] * 7 + [c_vp, c_sz, c_vp]),
+    "idee_swin_block_packed_floats": (c_int, [c_int]),
+    "idee_swin_block_fwd": (c_int, [C.POINTER(SwinDesc)] + [c_vp] * 6),
+    "idee_swin_block_bwd_workspace_bytes": (c_sz, [C.POINTER(SwinDesc)]),
+    "idee_swin_block_bwd": (c_int, [C.POINTER(SwinDesc)] + [c_vp] * 8 + [c_sz, c_vp]),
+    "idee_conv3d_fwd": (c_int, [C.POINTER(ConvDesc)] + [c_vp] * 5),
+    "idee_conv3d_dgrad": (c_int, [C.POINTER(ConvDesc)] + [c_vp] * 5),
+    "idee_conv3d_wgrad_workspace_bytes": (c_sz, [C.POINTER(ConvDesc)]),
+    "idee_conv3d_wgrad": (c_int, [C.POINTER(ConvDesc)] + [c_vp] * 5 + [c_sz, c_vp]),
+    "idee_lfq_workspace_bytes": (c_sz, [c_i64]),
+    "idee_lfq_fwd": (c_int, [c_vp] * 8 + [c_i64, c_int, c_int, c_int] + [c_f32] * 4 + [c_vp, c_sz, c_vp]),
+    "idee_lfq_bwd": (c_int, [c_vp] * 9 + [c_i64] + [c_f32] * 4 + [c_vp, c_sz, c_vp]),
+    "idee_bce_loss_fwd": (c_int, [c_vp, c_i64, c_i64, c_int, c_int, c_i64] + [c_vp] * 5),
+    "idee_anomaly_l1_workspace_bytes": (c_sz, [c_i64]),
+    "idee_anomaly_l1_fwd": (c_int, [c_vp] * 3 + [c_int] * 3 + [c_i64, c_int, c_vp, c_vp, c_sz, c_vp]),
+    "idee_anomaly_l1_bwd": (c_int, [c_vp] * 3 + [c_int] * 3 + [c_i64, c_int] + [c_vp] * 4),
+    "idee_adam_step": (c_int, [c_vp] * 4 + [c_i64] + [c_f32] * 5 + [c_int, c_vp]),
+}
+EXPORTS = tuple(_SIGS)
+
+_lock = threading.Lock()
+_lib = None
+
+
+def library_path() -> str:
+    return _build.LIB
+
+
+def load(build_if_missing: bool = True):
+    """Load (building in-tree with nvcc if needed) libidee_b200.so and declare every prototype."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = _build.LIB
+        if build_if_missing:
+            try:
+                path = _build.build()          # no-op when the in-tree library matches the sources (fingerprint stamp)
+            except Exception as e:
+                if not os.path.exists(path):
+                    raise RuntimeError(f"{path} is missing and could not be built ({e}); there is no fallback path") from e
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing: run `python -m idee_b200.build` (needs nvcc); there is no fallback path")
+        lib = C.CDLL(path)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)   # AttributeError if the symbol is not exported
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+        return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().idee_last_error().decode(errors="replace")
+        raise RuntimeError(f"idee_b200 {what} failed (rc={rc}): {msg}")
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("idee_b200 kernels run on CUDA tensors only (there is no CPU path); got a %s tensor" % t.device)
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)

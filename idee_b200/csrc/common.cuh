@@ -1,0 +1,104 @@
+// Shared device/host helpers for the idee_b200 CUDA kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "idee_b200 kernels are written for sm_100a (B200) only"
+#endif
+
+// ---- error reporting (C-ABI: every entry point returns int, message via idee_last_error) ----
+void idee_set_error(const char* fmt, ...);
+
+#define IDEE_REQUIRE(cond, ...)                                   \
+    do {                                                          \
+        if (!(cond)) {                                            \
+            idee_set_error(__VA_ARGS__);                          \
+            return 1;                                             \
+        }                                                         \
+    } while (0)
+
+#define IDEE_LAUNCH_CHECK(name)                                                            \
+    do {                                                                                   \
+        cudaError_t e__ = cudaGetLastError();                                              \
+        if (e__ != cudaSuccess) {                                                          \
+            idee_set_error("%s: kernel launch failed: %s", name, cudaGetErrorString(e__)); \
+            return 2;                                                                      \
+        }                                                                                  \
+    } while (0)
+
+#define IDEE_CUDA(call, name)                                                        \
+    do {                                                                             \
+        cudaError_t e__ = (call);                                                    \
+        if (e__ != cudaSuccess) {                                                    \
+            idee_set_error("%s: %s failed: %s", name, #call, cudaGetErrorString(e__)); \
+            return 2;                                                                \
+        }                                                                            \
+    } while (0)
+
+int idee_num_sms();  // cached SM count of the current device
+
+// ---- device helpers ----
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+__device__ __forceinline__ void load16(float* r, const float* p) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float4 v = ldg4(p + 4 * i);
+        r[4 * i + 0] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+    }
+}
+__device__ __forceinline__ void store16(float* p, const float* r) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) st4(p + 4 * i, make_float4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]));
+}
+__device__ __forceinline__ void zero16(float* r) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = 0.f;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// exact (erf) GELU and its derivative, as torch.nn.GELU() default (Swin_3D.py:27,32)
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+    const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+    return cdf + x * pdf;
+}
+
+// LayerNorm over 16 channels, eps 1e-5, no affine (Swin_3D.py:214,220,469): returns rstd, writes xn
+__device__ __forceinline__ float ln16(const float* x, float* xn) {
+    float mu = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) mu += x[i];
+    mu *= (1.f / 16.f);
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { const float d = x[i] - mu; xn[i] = d; var += d * d; }
+    const float rstd = 1.f / sqrtf(var * (1.f / 16.f) + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) xn[i] *= rstd;
+    return rstd;
+}
+// backward of the above: g_x = rstd * (g - mean(g) - xn * mean(g*xn))
+__device__ __forceinline__ void ln16_bwd(const float* g, const float* xn, float rstd, float* gx) {
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { m1 += g[i]; m2 += g[i] * xn[i]; }
+    m1 *= (1.f / 16.f); m2 *= (1.f / 16.f);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) gx[i] = rstd * (g[i] - m1 - xn[i] * m2);
+}

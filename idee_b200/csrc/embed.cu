@@ -1,0 +1,162 @@
+// PatchEmbed3D with patch (1,1,1): Conv3d(Cin->16, k=1, bias) + LayerNorm(16, no affine), written straight into the
+// channel-last token layout [N,V,T,H,W,16] that the Swin block kernels consume (sm_100a, fp32).
+// Replaces PatchEmbed3D.forward (Swin_3D.py:473-491) and the NCDHW->NDHWC rearrange of BasicLayer.forward (:434).
+#include "common.cuh"
+#include "idee_b200.h"
+
+namespace {
+
+constexpr int C = 16;
+constexpr int MAXCIN = 4;
+constexpr int EMB_THREADS = 256;
+
+struct EmbP {
+    const float* x; int64_t xs_n, xs_v, xs_c, xs_t, xs_h, xs_w;
+    const float* w; const float* b;   // [V][16][Cin], [V][16]
+    int N, V, Cin, T, H, W;
+};
+
+__device__ __forceinline__ int64_t x_offset(const EmbP& p, int64_t tok_v, int v, int& n_out) {
+    const int64_t thw = (int64_t)p.T * p.H * p.W;
+    const int n = (int)(tok_v / thw);
+    int64_t r = tok_v - n * thw;
+    const int t = (int)(r / ((int64_t)p.H * p.W));
+    r -= (int64_t)t * p.H * p.W;
+    const int h = (int)(r / p.W), w = (int)(r - (int64_t)h * p.W);
+    n_out = n;
+    return n * p.xs_n + v * p.xs_v + t * p.xs_t + h * p.xs_h + w * p.xs_w;
+}
+
+__global__ void __launch_bounds__(EMB_THREADS)
+embed_ln_fwd_kernel(EmbP p, float* __restrict__ y) {
+    const int v = blockIdx.y;
+    float wr[C][MAXCIN], br[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        br[c] = __ldg(p.b + v * C + c);
+#pragma unroll
+        for (int ci = 0; ci < MAXCIN; ++ci) wr[c][ci] = ci < p.Cin ? __ldg(p.w + (v * C + c) * p.Cin + ci) : 0.f;
+    }
+    const int64_t thw = (int64_t)p.T * p.H * p.W, ntok = (int64_t)p.N * thw;
+    for (int64_t tok = (int64_t)blockIdx.x * EMB_THREADS + threadIdx.x; tok < ntok; tok += (int64_t)gridDim.x * EMB_THREADS) {
+        int n;
+        const int64_t xo = x_offset(p, tok, v, n);
+        float xin[MAXCIN];
+#pragma unroll
+        for (int ci = 0; ci < MAXCIN; ++ci) xin[ci] = ci < p.Cin ? __ldg(p.x + xo + ci * p.xs_c) : 0.f;
+        float e[C], en[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            float a = br[c];
+#pragma unroll
+            for (int ci = 0; ci < MAXCIN; ++ci) a += wr[c][ci] * xin[ci];
+            e[c] = a;
+        }
+        ln16(e, en);
+        store16(y + (((int64_t)n * p.V + v) * thw + (tok - (int64_t)n * thw)) * C, en);
+    }
+}
+
+constexpr int EMB_NG = C * MAXCIN + C;
+
+__global__ void __launch_bounds__(EMB_THREADS)
+embed_ln_bwd_kernel(EmbP p, const float* __restrict__ gy, float* __restrict__ partials) {
+    const int v = blockIdx.y;
+    float wr[C][MAXCIN], br[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        br[c] = __ldg(p.b + v * C + c);
+#pragma unroll
+        for (int ci = 0; ci < MAXCIN; ++ci) wr[c][ci] = ci < p.Cin ? __ldg(p.w + (v * C + c) * p.Cin + ci) : 0.f;
+    }
+    float acc[EMB_NG];
+#pragma unroll
+    for (int k = 0; k < EMB_NG; ++k) acc[k] = 0.f;
+    const int64_t thw = (int64_t)p.T * p.H * p.W, ntok = (int64_t)p.N * thw;
+    for (int64_t tok = (int64_t)blockIdx.x * EMB_THREADS + threadIdx.x; tok < ntok; tok += (int64_t)gridDim.x * EMB_THREADS) {
+        int n;
+        const int64_t xo = x_offset(p, tok, v, n);
+        float xin[MAXCIN];
+#pragma unroll
+        for (int ci = 0; ci < MAXCIN; ++ci) xin[ci] = ci < p.Cin ? __ldg(p.x + xo + ci * p.xs_c) : 0.f;
+        float e[C], en[C], g[C], ge[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            float a = br[c];
+#pragma unroll
+            for (int ci = 0; ci < MAXCIN; ++ci) a += wr[c][ci] * xin[ci];
+            e[c] = a;
+        }
+        const float rstd = ln16(e, en);
+        load16(g, gy + (((int64_t)n * p.V + v) * thw + (tok - (int64_t)n * thw)) * C);
+        ln16_bwd(g, en, rstd, ge);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+#pragma unroll
+            for (int ci = 0; ci < MAXCIN; ++ci) acc[c * MAXCIN + ci] += ge[c] * xin[ci];
+            acc[C * MAXCIN + c] += ge[c];
+        }
+    }
+    __shared__ float red[EMB_THREADS / 32][EMB_NG];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < EMB_NG; ++k) {
+        const float s = warp_sum(acc[k]);
+        if (lane == 0) red[warp][k] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < EMB_NG) {
+        float s = 0.f;
+        for (int w = 0; w < EMB_THREADS / 32; ++w) s += red[w][threadIdx.x];
+        partials[((int64_t)v * gridDim.x + blockIdx.x) * EMB_NG + threadIdx.x] = s;
+    }
+}
+
+__global__ void embed_ln_bwd_finalize_kernel(const float* __restrict__ partials, int nblocks, int Cin, float* __restrict__ gw,
+                                             float* __restrict__ gb) {
+    const int v = blockIdx.x, k = threadIdx.x;
+    if (k >= EMB_NG) return;
+    double a = 0.0;
+    for (int b = 0; b < nblocks; ++b) a += partials[((int64_t)v * nblocks + b) * EMB_NG + k];
+    if (k < C * MAXCIN) {
+        const int c = k / MAXCIN, ci = k % MAXCIN;
+        if (ci < Cin) gw[(v * C + c) * Cin + ci] = (float)a;
+    } else gb[v * C + (k - C * MAXCIN)] = (float)a;
+}
+
+int emb_blocks(int V) { int b = (idee_num_sms() * 4 + V - 1) / V; return b < 1 ? 1 : b; }
+
+int fill(EmbP& p, const float* x, const int64_t* xs, const float* w, const float* b, int N, int V, int Cin, int T, int H, int W, int E) {
+    IDEE_REQUIRE(E == C, "embed_ln: only embed_dim=16 is built (got %d)", E);
+    IDEE_REQUIRE(Cin >= 1 && Cin <= MAXCIN, "embed_ln: in_chans must be in [1,%d] (got %d)", MAXCIN, Cin);
+    p.x = x; p.xs_n = xs[0]; p.xs_v = xs[1]; p.xs_c = xs[2]; p.xs_t = xs[3]; p.xs_h = xs[4]; p.xs_w = xs[5];
+    p.w = w; p.b = b; p.N = N; p.V = V; p.Cin = Cin; p.T = T; p.H = H; p.W = W;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" size_t idee_embed_ln_bwd_workspace_bytes(int V) { return sizeof(float) * (size_t)V * emb_blocks(V) * EMB_NG; }
+
+extern "C" int idee_embed_ln_fwd(const float* x, const int64_t* x_strides, const float* w, const float* b, float* y, int N, int V,
+                                 int Cin, int T, int H, int W, int E, void* stream) {
+    EmbP p;
+    if (fill(p, x, x_strides, w, b, N, V, Cin, T, H, W, E)) return 1;
+    embed_ln_fwd_kernel<<<dim3(emb_blocks(V), V), EMB_THREADS, 0, (cudaStream_t)stream>>>(p, y);
+    IDEE_LAUNCH_CHECK("embed_ln_fwd");
+    return 0;
+}
+
+extern "C" int idee_embed_ln_bwd(const float* x, const int64_t* x_strides, const float* w, const float* b, const float* gy, float* gw,
+                                 float* gb, int N, int V, int Cin, int T, int H, int W, int E, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+    EmbP p;
+    if (fill(p, x, x_strides, w, b, N, V, Cin, T, H, W, E)) return 1;
+    IDEE_REQUIRE(workspace_bytes >= idee_embed_ln_bwd_workspace_bytes(V), "embed_ln_bwd: workspace too small");
+    const int nb = emb_blocks(V);
+    embed_ln_bwd_kernel<<<dim3(nb, V), EMB_THREADS, 0, (cudaStream_t)stream>>>(p, gy, (float*)workspace);
+    IDEE_LAUNCH_CHECK("embed_ln_bwd");
+    embed_ln_bwd_finalize_kernel<<<V, 128, 0, (cudaStream_t)stream>>>((const float*)workspace, nb, Cin, gw, gb);
+    IDEE_LAUNCH_CHECK("embed_ln_bwd_finalize");
+    return 0;
+}

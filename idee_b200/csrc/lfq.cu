@@ -1,0 +1,207 @@
+// Lookup-free 1-bit quantiser ("binary driver codebook"), fused forward + aux losses + backward (sm_100a).
+//
+// Replaces LFQ.forward (models/codebook/LFQ.py:183-307) for dim=16, codebook_size=2 (-> codebook_dim 1,
+// project_in Linear(16,1), project_out Linear(1,16), codebook {-1,+1}); always fp32 like the reference
+// (LFQ.py:183,199).  Pure HBM-bound streaming kernel: 64 B/token in, 64 B (z_q) + 8 B (int64 index) out.
+//
+// forward (per token): s = w_in.z + b_in ; q = s>0 ? +1 : -1 (tie -> -1 -> index 0) ; x = s + (q - s) (train) | q (eval)
+//   index = x>0 ; z_q = x*w_out + b_out ; train: p = softmax([-200 s, +200 s]), sums of per-token entropy,
+//   of p (for the codebook entropy) and of (s-q)^2, reduced in double per CTA then by a 1-thread finalize.
+// backward: single pass, g_s = <w_out, g_zq> (straight-through) + g_aux * d(aux)/ds, using the saved mean prob.
+#include "common.cuh"
+#include "idee_b200.h"
+
+namespace {
+
+constexpr int C = 16;
+constexpr int LFQ_THREADS = 256;
+constexpr float LOG_EPS = 1e-5f;   // LFQ.py:52
+
+__device__ __forceinline__ void probs(float s, float inv_temp, float& p0, float& p1) {
+    // softmax over logits (-2*inv_temp*s*c) for codes c = {-1,+1}   (LFQ.py:239-240)
+    const float l1 = 2.f * inv_temp * s, l0 = -l1;
+    const float m = fmaxf(l0, l1);
+    const float e0 = expf(l0 - m), e1 = expf(l1 - m);
+    const float inv = 1.f / (e0 + e1);
+    p0 = e0 * inv; p1 = e1 * inv;
+}
+__device__ __forceinline__ float ent_term(float p) { return -p * logf(fmaxf(p, LOG_EPS)); }
+// d/dp [-p log(clamp(p, eps))]
+__device__ __forceinline__ float ent_grad(float p) { return -logf(fmaxf(p, LOG_EPS)) - (p >= LOG_EPS ? 1.f : 0.f); }
+
+template <int NACC>
+__device__ __forceinline__ void block_reduce_store(double* acc, double* out) {
+    __shared__ double red[LFQ_THREADS / 32][NACC];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) {
+        const double v = warp_sum_d(acc[a]);
+        if (lane == 0) red[warp][a] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NACC) {
+        double v = 0.0;
+        for (int w = 0; w < LFQ_THREADS / 32; ++w) v += red[w][threadIdx.x];
+        out[threadIdx.x] = v;
+    }
+}
+
+__global__ void __launch_bounds__(LFQ_THREADS)
+lfq_fwd_kernel(const float* __restrict__ z, const float* __restrict__ w_in, const float* __restrict__ b_in,
+               const float* __restrict__ w_out, const float* __restrict__ b_out, float* __restrict__ zq,
+               long long* __restrict__ indices, double* __restrict__ partials, int64_t ntok, int training, float inv_temp) {
+    float wi[C], wo[C], bo[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) { wi[c] = __ldg(w_in + c); wo[c] = __ldg(w_out + c); bo[c] = __ldg(b_out + c); }
+    const float bi = __ldg(b_in);
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};   // sum entropy, sum p0, sum p1, sum (s-q)^2
+    for (int64_t tok = (int64_t)blockIdx.x * LFQ_THREADS + threadIdx.x; tok < ntok; tok += (int64_t)gridDim.x * LFQ_THREADS) {
+        float zr[C];
+        load16(zr, z + tok * C);
+        float s = bi;
+#pragma unroll
+        for (int c = 0; c < C; ++c) s += wi[c] * zr[c];
+        const float q = s > 0.f ? 1.f : -1.f;
+        const float x = training ? s + (q - s) : q;
+        indices[tok] = x > 0.f ? 1 : 0;
+        float r[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) r[c] = x * wo[c] + bo[c];
+        store16(zq + tok * C, r);
+        if (training) {
+            float p0, p1;
+            probs(s, inv_temp, p0, p1);
+            acc[0] += (double)(ent_term(p0) + ent_term(p1));
+            acc[1] += (double)p0; acc[2] += (double)p1;
+            acc[3] += (double)((s - q) * (s - q));
+        }
+    }
+    if (training) block_reduce_store<4>(acc, partials + (int64_t)blockIdx.x * 4);
+}
+
+// stats (float[8]): aux, per_sample_entropy, codebook_entropy, commit, mean p0, mean p1, ntok, 0
+__global__ void lfq_finalize_kernel(const double* __restrict__ partials, int nblocks, int64_t ntok, float lam_commit,
+                                    float lam_ent, float gamma, float* __restrict__ stats) {
+    __shared__ double red[4][32];
+    double a[4] = {0, 0, 0, 0};
+    for (int b = threadIdx.x; b < nblocks; b += 32)
+        for (int k = 0; k < 4; ++k) a[k] += partials[(int64_t)b * 4 + k];
+    for (int k = 0; k < 4; ++k) a[k] = warp_sum_d(a[k]);
+    (void)red;
+    if (threadIdx.x == 0) {
+        const double n = (double)ntok;
+        const float h_tok = (float)(a[0] / n), p0 = (float)(a[1] / n), p1 = (float)(a[2] / n), commit = (float)(a[3] / n);
+        const float h_cb = ent_term(p0) + ent_term(p1);
+        stats[0] = commit * lam_commit + (lam_ent * h_tok - gamma * h_cb);   // LFQ.py:262,300
+        stats[1] = h_tok; stats[2] = h_cb; stats[3] = commit; stats[4] = p0; stats[5] = p1; stats[6] = (float)n; stats[7] = 0.f;
+    }
+}
+
+constexpr int LFQ_NG = 3 * C + 1;   // g_w_in[16], g_b_in, g_w_out[16], g_b_out[16]
+
+__global__ void __launch_bounds__(LFQ_THREADS)
+lfq_bwd_kernel(const float* __restrict__ z, const float* __restrict__ gzq, const float* __restrict__ g_aux,
+               const float* __restrict__ stats, const float* __restrict__ w_in, const float* __restrict__ b_in,
+               const float* __restrict__ w_out, float* __restrict__ gz, double* __restrict__ partials, int64_t ntok,
+               float lam_commit, float lam_ent, float gamma, float inv_temp) {
+    float wi[C], wo[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) { wi[c] = __ldg(w_in + c); wo[c] = __ldg(w_out + c); }
+    const float bi = __ldg(b_in);
+    const float ga = g_aux ? __ldg(g_aux) : 0.f;
+    const float invn = 1.f / (float)ntok;
+    const float cb_diff = ent_grad(__ldg(stats + 5)) - ent_grad(__ldg(stats + 4));   // f(pbar1) - f(pbar0)
+    float a_wi[C], a_wo[C], a_bo[C], a_bi = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { a_wi[c] = 0.f; a_wo[c] = 0.f; a_bo[c] = 0.f; }
+    double acc[LFQ_NG];
+#pragma unroll
+    for (int k = 0; k < LFQ_NG; ++k) acc[k] = 0.0;
+    int cnt = 0;
+    for (int64_t tok = (int64_t)blockIdx.x * LFQ_THREADS + threadIdx.x; tok < ntok; tok += (int64_t)gridDim.x * LFQ_THREADS) {
+        float zr[C], gr[C];
+        load16(zr, z + tok * C);
+        load16(gr, gzq + tok * C);
+        float s = bi;
+#pragma unroll
+        for (int c = 0; c < C; ++c) s += wi[c] * zr[c];
+        const float q = s > 0.f ? 1.f : -1.f;
+        const float x = s + (q - s);
+        float gs = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) { gs += wo[c] * gr[c]; a_wo[c] += x * gr[c]; a_bo[c] += gr[c]; }
+        float p0, p1;
+        probs(s, inv_temp, p0, p1);
+        const float dp1 = 2.f * inv_temp * 2.f * p0 * p1;     // d p1 / d s  (= 400 p0 p1 at inv_temp 100)
+        const float d_ent = dp1 * (ent_grad(p1) - ent_grad(p0));
+        gs += ga * invn * (lam_commit * 2.f * (s - q) + lam_ent * d_ent - gamma * dp1 * cb_diff);
+        float r[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) { r[c] = gs * wi[c]; a_wi[c] += gs * zr[c]; }
+        a_bi += gs;
+        store16(gz + tok * C, r);
+        if (++cnt == 64) {   // flush fp32 running sums into double
+#pragma unroll
+            for (int c = 0; c < C; ++c) { acc[c] += a_wi[c]; acc[C + 1 + c] += a_wo[c]; acc[2 * C + 1 + c] += a_bo[c]; a_wi[c] = a_wo[c] = a_bo[c] = 0.f; }
+            acc[C] += a_bi; a_bi = 0.f; cnt = 0;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) { acc[c] += a_wi[c]; acc[C + 1 + c] += a_wo[c]; acc[2 * C + 1 + c] += a_bo[c]; }
+    acc[C] += a_bi;
+    block_reduce_store<LFQ_NG>(acc, partials + (int64_t)blockIdx.x * LFQ_NG);
+}
+
+// grads (float[49]): g_w_in[16] | g_b_in | g_w_out[16] | g_b_out[16]
+__global__ void lfq_bwd_finalize_kernel(const double* __restrict__ partials, int nblocks, float* __restrict__ grads) {
+    const int k = threadIdx.x;
+    if (k >= LFQ_NG) return;
+    double a = 0.0;
+    for (int b = 0; b < nblocks; ++b) a += partials[(int64_t)b * LFQ_NG + k];
+    grads[k] = (float)a;
+}
+
+int lfq_blocks(int64_t ntok) {
+    int64_t nb = (ntok + LFQ_THREADS - 1) / LFQ_THREADS;
+    const int cap = idee_num_sms() * 8;
+    if (nb > cap) nb = cap;
+    if (nb < 1) nb = 1;
+    return (int)nb;
+}
+
+}  // namespace
+
+extern "C" size_t idee_lfq_workspace_bytes(int64_t ntok) { return sizeof(double) * (size_t)lfq_blocks(ntok) * LFQ_NG; }
+
+extern "C" int idee_lfq_fwd(const float* z, const float* w_in, const float* b_in, const float* w_out, const float* b_out,
+                            float* zq, int64_t* indices, float* stats, int64_t ntok, int dim, int codebook_size, int training,
+                            float inv_temperature, float lambda_commit, float lambda_entropy, float diversity_gamma,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+    IDEE_REQUIRE(dim == C && codebook_size == 2, "lfq_fwd: only dim=16, codebook_size=2 is built (got %d, %d)", dim, codebook_size);
+    IDEE_REQUIRE(workspace_bytes >= idee_lfq_workspace_bytes(ntok), "lfq_fwd: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nb = lfq_blocks(ntok);
+    lfq_fwd_kernel<<<nb, LFQ_THREADS, 0, st>>>(z, w_in, b_in, w_out, b_out, zq, (long long*)indices, (double*)workspace, ntok,
+                                                training, inv_temperature);
+    IDEE_LAUNCH_CHECK("lfq_fwd");
+    if (training) {
+        lfq_finalize_kernel<<<1, 32, 0, st>>>((const double*)workspace, nb, ntok, lambda_commit, lambda_entropy, diversity_gamma, stats);
+        IDEE_LAUNCH_CHECK("lfq_finalize");
+    }
+    return 0;
+}
+
+extern "C" int idee_lfq_bwd(const float* z, const float* gzq, const float* g_aux, const float* stats, const float* w_in,
+                            const float* b_in, const float* w_out, float* gz, float* grads, int64_t ntok, float inv_temperature,
+                            float lambda_commit, float lambda_entropy, float diversity_gamma, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+    IDEE_REQUIRE(workspace_bytes >= idee_lfq_workspace_bytes(ntok), "lfq_bwd: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nb = lfq_blocks(ntok);
+    lfq_bwd_kernel<<<nb, LFQ_THREADS, 0, st>>>(z, gzq, g_aux, stats, w_in, b_in, w_out, gz, (double*)workspace, ntok, lambda_commit,
+                                                lambda_entropy, diversity_gamma, inv_temperature);
+    IDEE_LAUNCH_CHECK("lfq_bwd");
+    lfq_bwd_finalize_kernel<<<1, 64, 0, st>>>((const double*)workspace, nb, grads);
+    IDEE_LAUNCH_CHECK("lfq_bwd_finalize");
+    return 0;
+}

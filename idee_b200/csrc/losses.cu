@@ -1,0 +1,211 @@
+// Fused loss kernels of the IDEE training step (sm_100a, fp32 with double block reductions).
+//   BCE_loss_synthetic        losses.py:105-124   class-frequency weighted BCE-with-logits, K logit maps per launch
+//   Anomaly_L1_loss_synthetic losses.py:147-168   masked L1 between z_q and the code of index 0, without the three
+//                                                 full-size broadcast temporaries the reference materialises
+#include "common.cuh"
+#include "idee_b200.h"
+
+namespace {
+
+constexpr int LT = 1024;
+
+__device__ __forceinline__ double block_sum_d(double v, double* red) {
+    v = warp_sum_d(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    double s = 0.0;
+    if (warp == 0) {
+        s = lane < (int)(blockDim.x >> 5) ? red[lane] : 0.0;
+        s = warp_sum_d(s);
+        if (lane == 0) red[0] = s;
+    }
+    __syncthreads();
+    s = red[0];
+    return s;
+}
+
+// class weights from torch.histc(target, bins=2) over [min,max] (losses.py:115-119): stats = {w0, w1}
+__global__ void __launch_bounds__(LT)
+bce_weights_kernel(const float* __restrict__ target, int64_t M, float* __restrict__ wts) {
+    __shared__ double red[32];
+    __shared__ float s_lo, s_hi;
+    float lo = INFINITY, hi = -INFINITY;
+    for (int64_t i = threadIdx.x; i < M; i += LT) { const float t = target[i]; lo = fminf(lo, t); hi = fmaxf(hi, t); }
+    for (int o = 16; o > 0; o >>= 1) { lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+    __shared__ float rl[32], rh[32];
+    if ((threadIdx.x & 31) == 0) { rl[threadIdx.x >> 5] = lo; rh[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < LT / 32; ++w) { lo = fminf(lo, rl[w]); hi = fmaxf(hi, rh[w]); }
+        if (lo == hi) { lo -= 1.f; hi += 1.f; }   // histc widens a degenerate range
+        s_lo = lo; s_hi = hi;
+    }
+    __syncthreads();
+    lo = s_lo; hi = s_hi;
+    double c1 = 0.0;
+    for (int64_t i = threadIdx.x; i < M; i += LT) {
+        const float t = target[i];
+        int bin = (int)((t - lo) / (hi - lo) * 2.f);
+        if (bin > 1) bin = 1;
+        c1 += bin;
+    }
+    c1 = block_sum_d(c1, red);
+    if (threadIdx.x == 0) {
+        const float n1 = (float)c1, n0 = (float)((double)M - c1), tot = n0 + n1;
+        wts[0] = logf(powf(n0 / tot, -0.5f) + 1.1f);
+        wts[1] = logf(powf(n1 / tot, -0.5f) + 1.1f);
+    }
+}
+
+// one CTA per logit map k: loss[k] = mean(w[target] * bce_with_logits(pred, target)); dpred = w*(sigmoid(x)-t)/M
+__global__ void __launch_bounds__(LT)
+bce_loss_kernel(const float* __restrict__ pred, int64_t sk, int64_t sn, int N, int64_t HW, const float* __restrict__ target,
+                const float* __restrict__ wts, float* __restrict__ loss, float* __restrict__ dpred) {
+    __shared__ double red[32];
+    const int k = blockIdx.x;
+    const float w0 = wts[0], w1 = wts[1];
+    const int64_t M = (int64_t)N * HW;
+    const float invM = 1.f / (float)M;
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < M; i += LT) {
+        const int64_t n = i / HW, r = i - n * HW;
+        const int64_t o = k * sk + n * sn + r;
+        const float x = pred[o], t = target[i];
+        const float w = ((int)t >= 1) ? w1 : w0;
+        const float l = fmaxf(x, 0.f) - x * t + log1pf(expf(-fabsf(x)));
+        acc += (double)(w * l);
+        if (dpred) dpred[o] = w * (1.f / (1.f + expf(-x)) - t) * invM;
+    }
+    acc = block_sum_d(acc, red);
+    if (threadIdx.x == 0) loss[k] = (float)(acc / (double)M);
+}
+
+// ---- anomaly L1 ----
+constexpr int AT = 256;
+struct AnomP { const float* zq; const float* mask; const float* vq0; int N, V, T; int64_t HW; };
+
+// partial sums: {sum |zq - vq0| * (1-m) over m != 1,  sum (1-m) over (n,h,w)}
+__global__ void __launch_bounds__(AT)
+anomaly_l1_fwd_kernel(AnomP p, double* __restrict__ partials) {
+    __shared__ double red[32];
+    float v0[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) v0[c] = __ldg(p.vq0 + c);
+    const int64_t per_n = (int64_t)p.V * p.T * p.HW, ntok = (int64_t)p.N * per_n;
+    double a = 0.0, wsum = 0.0;
+    for (int64_t tok = (int64_t)blockIdx.x * AT + threadIdx.x; tok < ntok; tok += (int64_t)gridDim.x * AT) {
+        const int64_t n = tok / per_n, r = tok - n * per_n, hw = r % p.HW;
+        const float m = __ldg(p.mask + n * p.HW + hw);
+        if (r < p.HW) wsum += (double)(1.f - m);      // v == 0 && t == 0: count each (n,h,w) once
+        if (m == 1.f) continue;
+        float z[16];
+        load16(z, p.zq + tok * 16);
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) s += fabsf(z[c] - v0[c]);
+        a += (double)(s * (1.f - m));
+    }
+    a = block_sum_d(a, red);
+    wsum = block_sum_d(wsum, red);
+    if (threadIdx.x == 0) { partials[2 * blockIdx.x] = a; partials[2 * blockIdx.x + 1] = wsum; }
+}
+// out: {loss, total weight = sum(1-m) * V*C*T}
+__global__ void anomaly_l1_finalize_kernel(const double* __restrict__ partials, int nblocks, int V, int T, float* __restrict__ out) {
+    double a = 0.0, w = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += 32) { a += partials[2 * b]; w += partials[2 * b + 1]; }
+    a = warp_sum_d(a); w = warp_sum_d(w);
+    if (threadIdx.x == 0) { const double tw = w * V * 16 * T; out[0] = (float)(a / tw); out[1] = (float)tw; }
+}
+// g_zq = g_loss * sign(zq - vq0) * (1-m) / total_weight  (0 where m == 1)
+__global__ void __launch_bounds__(AT)
+anomaly_l1_bwd_kernel(AnomP p, const float* __restrict__ out, const float* __restrict__ g_loss, float* __restrict__ gzq) {
+    float v0[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) v0[c] = __ldg(p.vq0 + c);
+    const float scale = __ldg(g_loss) / __ldg(out + 1);
+    const int64_t per_n = (int64_t)p.V * p.T * p.HW, ntok = (int64_t)p.N * per_n;
+    for (int64_t tok = (int64_t)blockIdx.x * AT + threadIdx.x; tok < ntok; tok += (int64_t)gridDim.x * AT) {
+        const int64_t n = tok / per_n, r = tok - n * per_n, hw = r % p.HW;
+        const float m = __ldg(p.mask + n * p.HW + hw);
+        float g[16];
+        if (m == 1.f) zero16(g);
+        else {
+            float z[16];
+            load16(z, p.zq + tok * 16);
+            const float sc = scale * (1.f - m);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) { const float d = z[c] - v0[c]; g[c] = d > 0.f ? sc : (d < 0.f ? -sc : 0.f); }
+        }
+        store16(gzq + tok * 16, g);
+    }
+}
+
+int anom_blocks(int64_t ntok) {
+    int64_t nb = (ntok + AT - 1) / AT;
+    const int cap = idee_num_sms() * 8;
+    return (int)(nb > cap ? cap : (nb < 1 ? 1 : nb));
+}
+
+// ---- Adam (torch.optim.Adam semantics: L2 weight decay folded into the gradient) ----
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
+                            float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float gi = g[i] + wd * p[i];
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        p[i] -= (lr / bc1) * mi / (sqrtf(vi) / bc2_sqrt + eps);
+    }
+}
+
+}  // namespace
+
+extern "C" int idee_bce_loss_fwd(const float* pred, int64_t stride_k, int64_t stride_n, int K, int N, int64_t HW, const float* target,
+                                 float* wts, float* loss, float* dpred, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    bce_weights_kernel<<<1, LT, 0, st>>>(target, (int64_t)N * HW, wts);
+    IDEE_LAUNCH_CHECK("bce_weights");
+    bce_loss_kernel<<<K, LT, 0, st>>>(pred, stride_k, stride_n, N, HW, target, wts, loss, dpred);
+    IDEE_LAUNCH_CHECK("bce_loss");
+    return 0;
+}
+
+extern "C" size_t idee_anomaly_l1_workspace_bytes(int64_t ntok) { return sizeof(double) * 2 * (size_t)anom_blocks(ntok); }
+
+extern "C" int idee_anomaly_l1_fwd(const float* zq, const float* mask, const float* vq0, int N, int V, int T, int64_t HW, int C, float* out,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+    IDEE_REQUIRE(C == 16, "anomaly_l1: only C=16 is built (got %d)", C);
+    const int64_t ntok = (int64_t)N * V * T * HW;
+    IDEE_REQUIRE(workspace_bytes >= idee_anomaly_l1_workspace_bytes(ntok), "anomaly_l1_fwd: workspace too small");
+    AnomP p{zq, mask, vq0, N, V, T, HW};
+    const int nb = anom_blocks(ntok);
+    anomaly_l1_fwd_kernel<<<nb, AT, 0, (cudaStream_t)stream>>>(p, (double*)workspace);
+    IDEE_LAUNCH_CHECK("anomaly_l1_fwd");
+    anomaly_l1_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const double*)workspace, nb, V, T, out);
+    IDEE_LAUNCH_CHECK("anomaly_l1_finalize");
+    return 0;
+}
+
+extern "C" int idee_anomaly_l1_bwd(const float* zq, const float* mask, const float* vq0, int N, int V, int T, int64_t HW, int C,
+                                   const float* out, const float* g_loss, float* gzq, void* stream) {
+    IDEE_REQUIRE(C == 16, "anomaly_l1: only C=16 is built (got %d)", C);
+    const int64_t ntok = (int64_t)N * V * T * HW;
+    AnomP p{zq, mask, vq0, N, V, T, HW};
+    anomaly_l1_bwd_kernel<<<anom_blocks(ntok), AT, 0, (cudaStream_t)stream>>>(p, out, g_loss, gzq);
+    IDEE_LAUNCH_CHECK("anomaly_l1_bwd");
+    return 0;
+}
+
+extern "C" int idee_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                              float weight_decay, int step, void* stream) {
+    IDEE_REQUIRE(step >= 1, "adam_step: step must be >= 1");
+    const float bc1 = 1.f - powf(beta1, (float)step), bc2 = sqrtf(1.f - powf(beta2, (float)step));
+    int nb = (int)((n + 255) / 256);
+    const int cap = idee_num_sms() * 8;
+    if (nb > cap) nb = cap;
+    adam_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2);
+    IDEE_LAUNCH_CHECK("adam_step");
+    return 0;
+}

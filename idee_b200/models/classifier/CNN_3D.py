@@ -1,0 +1,101 @@
+"""B200-native 3-D CNN extremes classifier: drop-in for the reference ``models/classifier/CNN_3D.py``.
+
+Same constructor, module tree and parameter names (``conv1..3`` joint head, ``layers[v].conv1..3`` per-variable heads) and
+the same ``forward(x[N,V,C,T,H,W]) -> (z[N,1,H,W], [y_v[N,1,H,W]]*V)`` contract (classifier/CNN_3D.py:63-139).  The six
+per-variable heads run as ONE batched launch per layer (weight set = variable), the joint head reads the V channel-last
+planes of z_q directly as a 16*V-channel image (no reshape copy), ReLU is fused into the conv epilogue.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ... import ops
+
+
+def _conv():
+    return dict(kernel_size=(2, 3, 3), stride=(2, 1, 1), padding=(0, 1, 1), bias=True)
+
+
+class Layer_v(nn.Module):
+    """Per-variable head (classifier/CNN_3D.py:17-58)."""
+
+    def __init__(self, embed_dim: int = 16, dim: int = 16, n_classes: int = 1, drop_rate: int = 0.1):
+        super().__init__()
+        self.embed_dim, self.dim, self.n_classes, self.drop_rate = embed_dim, dim, n_classes, drop_rate
+        self.conv1 = nn.Conv3d(embed_dim, dim, **_conv())
+        self.conv2 = nn.Conv3d(dim, dim, **_conv())
+        self.conv3 = nn.Conv3d(dim, n_classes, **_conv())
+        self.act = nn.ReLU()
+        self.drop = nn.Dropout(drop_rate, inplace=False)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """x [N,C,T,H,W] -> [N,n_classes,H,W]"""
+        tok = _channel_last(x.unsqueeze(1))
+        out = _head(tok, [(c.weight.unsqueeze(0), c.bias.unsqueeze(0)) for c in (self.conv1, self.conv2, self.conv3)],
+                    self.drop, groups=1)
+        return out[:, 0].permute(0, 4, 1, 2, 3).squeeze(2)
+
+
+def _channel_last(x: torch.Tensor) -> torch.Tensor:
+    """logical [N,V,C,T,H,W] -> token view [N,V,T,H,W,C] with C contiguous (copy only if the storage is not channel-last)."""
+    tok = x.permute(0, 1, 3, 4, 5, 2)
+    return tok if tok.stride(5) == 1 and ops._dense(tok) else tok.contiguous()
+
+
+def _head(tok, wb, drop, groups):
+    (w1, b1), (w2, b2), (w3, b3) = wb
+    h = ops.conv3d_cl(tok, w1, b1, proj=False, relu=True, groups=groups)
+    h = drop(h)
+    h = ops.conv3d_cl(h, w2, b2, proj=False, relu=True)
+    return ops.conv3d_cl(h, w3, b3, proj=False, relu=False)
+
+
+class CNN_3D(nn.Module):
+    def __init__(self, in_var: int = 6, embed_dim: int = 16, dim: int = 16, n_classes: int = 1, drop_rate: int = 0.2):
+        super().__init__()
+        if embed_dim != 16 or dim % 16 != 0 or n_classes != 1:
+            raise NotImplementedError("idee_b200: classifier kernels are built for embed_dim 16, dim multiple of 16, 1 class")
+        self.in_var = in_var
+        self.var_embed_dim, self.var_dim = embed_dim, dim
+        self.embed_dim = embed_dim * in_var
+        self.dim = dim * in_var
+        self.n_classes, self.drop_rate = n_classes, drop_rate
+        self.conv1 = nn.Conv3d(self.embed_dim, self.dim, **_conv())
+        self.conv2 = nn.Conv3d(self.dim, self.dim, **_conv())
+        self.conv3 = nn.Conv3d(self.dim, self.n_classes, **_conv())
+        self.layers = nn.ModuleList([Layer_v(embed_dim=embed_dim, dim=dim, n_classes=1, drop_rate=drop_rate) for _ in range(in_var)])
+        self.act = nn.ReLU()
+        self.drop = nn.Dropout(drop_rate, inplace=False)
+        self._packs = None
+
+    def init_weights(self):
+        """trunc_normal(.04) (classifier/CNN_3D.py:95-110; never called by the reference)."""
+        for m in self.modules():
+            if isinstance(m, (nn.Linear, nn.Conv2d, nn.Conv3d)):
+                nn.init.trunc_normal_(m.weight, std=.04)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+
+    def _head_params(self):
+        if self._packs is None:
+            V = self.in_var
+            self._packs = [(ops.ParamPack([[getattr(self.layers[v], n).weight] for v in range(V)]),
+                            ops.ParamPack([[getattr(self.layers[v], n).bias] for v in range(V)])) for n in ("conv1", "conv2", "conv3")]
+        V, e, d = self.in_var, self.var_embed_dim, self.var_dim
+        shapes = [(V, d, e, 2, 3, 3), (V, d, d, 2, 3, 3), (V, 1, d, 2, 3, 3)]
+        return [(ops.packed(pw, s), ops.packed(pb, (V, s[1]))) for (pw, pb), s in zip(self._packs, shapes)]
+
+    def forward(self, x):
+        """x [N,V,C,T,H,W] -> (z [N,n_classes,H,W], [y_v [N,1,H,W]] * V)"""
+        N, V, C, T, H, W = x.shape
+        tok = _channel_last(x)
+        # multi-head classifier: all V heads per launch
+        yh = _head(tok, self._head_params(), self.drop, groups=1)                 # [N,V,T',H,W,1]
+        y = [yh[:, i].permute(0, 4, 1, 2, 3).squeeze(2) for i in range(self.in_var)]
+        # joint head over the V*C channels
+        zj = _head(tok, [(c.weight.unsqueeze(0), c.bias.unsqueeze(0)) for c in (self.conv1, self.conv2, self.conv3)],
+                   self.drop, groups=V)                                           # [N,1,T',H,W,1]
+        z = zj[:, 0].permute(0, 4, 1, 2, 3).squeeze(2)
+        return z, y

@@ -1,0 +1,415 @@
+"""torch.autograd.Function wrappers over the C ABI (one per fused op) + parameter packing.
+
+Everything here is plumbing: pointer/stride extraction, workspace allocation through torch's caching allocator and
+autograd routing.  All arithmetic happens in libidee_b200.so; there is no PyTorch fallback for any op.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Sequence
+
+import torch
+
+from . import _lib as L
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# parameter packing: the kernels take per-variable weight blocks [V][P]; the modules keep the reference's individual
+# nn.Parameters (same state_dict).  A ParamPack owns one flat buffer and re-points each parameter's .data at a view
+# of it, so no per-step gather/scatter is needed and in-place optimiser updates / load_state_dict stay visible.
+# ----------------------------------------------------------------------------------------------------------------
+class ParamPack:
+    def __init__(self, groups: Sequence[Sequence[torch.nn.Parameter]]):
+        self.groups = [list(g) for g in groups]
+        self.sizes = [p.numel() for p in self.groups[0]]
+        self.shapes = [tuple(p.shape) for p in self.groups[0]]
+        for g in self.groups:
+            assert [tuple(p.shape) for p in g] == self.shapes, "all variables must share parameter shapes"
+        self.P = sum(self.sizes)
+        self.V = len(self.groups)
+        self.flat = None
+
+    def params(self) -> List[torch.nn.Parameter]:
+        return [p for g in self.groups for p in g]
+
+    def _aliased(self) -> bool:
+        base = self.flat.data_ptr()
+        for v, g in enumerate(self.groups):
+            off = 0
+            for p, n in zip(g, self.sizes):
+                if p.data_ptr() != base + 4 * (v * self.P + off) or not p.is_contiguous():
+                    return False
+                off += n
+        return True
+
+    @torch.no_grad()
+    def tensor(self) -> torch.Tensor:
+        p0 = self.groups[0][0]
+        if self.flat is not None and self.flat.device == p0.device and self._aliased():
+            return self.flat
+        if p0.dtype != torch.float32:
+            raise RuntimeError("idee_b200 keeps fp32 master parameters; got %s" % p0.dtype)
+        flat = torch.empty(self.V, self.P, device=p0.device, dtype=torch.float32)
+        for v, g in enumerate(self.groups):
+            off = 0
+            for p, n in zip(g, self.sizes):
+                view = flat[v, off:off + n].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                off += n
+        self.flat = flat
+        return flat
+
+    def split_grad(self, gflat: torch.Tensor):
+        out = []
+        for v in range(self.V):
+            off = 0
+            for n, shp in zip(self.sizes, self.shapes):
+                out.append(gflat[v, off:off + n].view(shp))
+                off += n
+        return out
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# PatchEmbed + LN
+# ----------------------------------------------------------------------------------------------------------------
+class EmbedLN(torch.autograd.Function):
+    """x [N,V,Cin,T,H,W] (any strides) -> tokens [N,V,T,H,W,16].  Swin_3D.py:473-491."""
+
+    @staticmethod
+    def forward(ctx, x, wpack: ParamPack, bpack: ParamPack, *params):
+        L.require_cuda(x)
+        lib = L.load()
+        x = x if x.dtype == torch.float32 else x.float()
+        N, V, Cin, T, H, W = x.shape
+        w, b = wpack.tensor(), bpack.tensor()
+        y = torch.empty(N, V, T, H, W, 16, device=x.device, dtype=torch.float32)
+        xs = (C.c_int64 * 6)(*x.stride())
+        L.check(lib.idee_embed_ln_fwd(x.data_ptr(), C.cast(xs, C.c_void_p), w.data_ptr(), b.data_ptr(), y.data_ptr(),
+                                      N, V, Cin, T, H, W, 16, L.stream()), "embed_ln_fwd")
+        ctx.save_for_backward(x)
+        ctx.packs = (wpack, bpack)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = L.load()
+        (x,) = ctx.saved_tensors
+        wpack, bpack = ctx.packs
+        N, V, Cin, T, H, W = x.shape
+        w, b = wpack.tensor(), bpack.tensor()
+        gy = _f32c(gy)
+        gw, gb = torch.empty_like(w), torch.empty_like(b)
+        nws = lib.idee_embed_ln_bwd_workspace_bytes(V)
+        ws = L.workspace(nws, x.device)
+        xs = (C.c_int64 * 6)(*x.stride())
+        L.check(lib.idee_embed_ln_bwd(x.data_ptr(), C.cast(xs, C.c_void_p), w.data_ptr(), b.data_ptr(), gy.data_ptr(),
+                                      gw.data_ptr(), gb.data_ptr(), N, V, Cin, T, H, W, 16, ws.data_ptr(), nws, L.stream()),
+                "embed_ln_bwd")
+        return (None, None, None, *wpack.split_grad(gw), *bpack.split_grad(gb))
+
+
+def embed_ln(x, wpack: ParamPack, bpack: ParamPack):
+    return EmbedLN.apply(x, wpack, bpack, *wpack.params(), *bpack.params())
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Swin block
+# ----------------------------------------------------------------------------------------------------------------
+def _swin_desc(x, window, shift, rpb_rows, scale, pack: ParamPack, heads, hidden):
+    N, V, T, H, W, Cc = x.shape
+    d = L.SwinDesc()
+    d.N, d.V, d.T, d.H, d.W, d.C, d.heads, d.hidden = N, V, T, H, W, Cc, heads, hidden
+    d.wd, d.wh, d.ww = window
+    d.st, d.sh, d.sw = shift
+    d.rpb_rows, d.scale, d.param_stride = rpb_rows, scale, pack.P
+    return d
+
+
+class SwinBlock(torch.autograd.Function):
+    """tokens [N,V,T,H,W,16] -> same; one launch for all V variables.  Swin_3D.py:224-287."""
+
+    @staticmethod
+    def forward(ctx, x, pack: ParamPack, rel_index, window, shift, rpb_rows, scale, heads, hidden, *params):
+        L.require_cuda(x)
+        lib = L.load()
+        x = _f32c(x)
+        flat = pack.tensor()
+        if lib.idee_swin_block_packed_floats(rpb_rows) != pack.P:
+            raise RuntimeError("swin_block: packed parameter size mismatch")
+        d = _swin_desc(x, window, shift, rpb_rows, scale, pack, heads, hidden)
+        out = torch.empty_like(x)
+        need_bwd = any(ctx.needs_input_grad)
+        ymid = torch.empty_like(x) if need_bwd else None
+        L.check(lib.idee_swin_block_fwd(C.byref(d), x.data_ptr(), out.data_ptr(), L.ptr(ymid), flat.data_ptr(),
+                                        rel_index.data_ptr(), L.stream()), "swin_block_fwd")
+        if need_bwd:
+            ctx.save_for_backward(x, ymid, rel_index)
+            ctx.pack, ctx.args = pack, (window, shift, rpb_rows, scale, heads, hidden)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        lib = L.load()
+        x, ymid, rel_index = ctx.saved_tensors
+        pack = ctx.pack
+        window, shift, rpb_rows, scale, heads, hidden = ctx.args
+        flat = pack.tensor()
+        d = _swin_desc(x, window, shift, rpb_rows, scale, pack, heads, hidden)
+        gout = _f32c(gout)
+        gx = torch.empty_like(x)
+        gflat = torch.empty_like(flat)
+        nws = lib.idee_swin_block_bwd_workspace_bytes(C.byref(d))
+        ws = L.workspace(nws, x.device)
+        L.check(lib.idee_swin_block_bwd(C.byref(d), x.data_ptr(), ymid.data_ptr(), gout.data_ptr(), gx.data_ptr(), flat.data_ptr(),
+                                        rel_index.data_ptr(), gflat.data_ptr(), ws.data_ptr(), nws, L.stream()), "swin_block_bwd")
+        return (gx, None, None, None, None, None, None, None, None, *pack.split_grad(gflat))
+
+
+def swin_block(x, pack: ParamPack, rel_index, window, shift, rpb_rows, scale, heads, hidden):
+    return SwinBlock.apply(x, pack, rel_index, tuple(window), tuple(shift), rpb_rows, float(scale), heads, hidden, *pack.params())
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# channel-last Conv3d (proj_var and classifier geometries)
+# ----------------------------------------------------------------------------------------------------------------
+def _conv_desc(x_dims, x_strides, y_strides, Vw, Cin, Cout, proj, relu, in_cpg, out_cpg, x_sg, y_sg):
+    """x_dims = (N, V, Ti, Hi, Wi); strides = (sn, sv, st, sh, sw) in elements."""
+    N, V, Ti, Hi, Wi = x_dims
+    d = L.ConvDesc()
+    d.N, d.V, d.Vw, d.Cin, d.Cout = N, V, Vw, Cin, Cout
+    d.Ti, d.Hi, d.Wi = Ti, Hi, Wi
+    d.To = Ti if proj else (Ti - 2) // 2 + 1
+    d.Ho, d.Wo = Hi, Wi
+    d.proj, d.relu = int(proj), int(relu)
+    d.x_sn, d.x_sv, d.x_st, d.x_sh, d.x_sw = x_strides
+    d.y_sn, d.y_sv, d.y_st, d.y_sh, d.y_sw = y_strides
+    d.x_sg, d.y_sg, d.in_cpg, d.out_cpg = x_sg, y_sg, in_cpg, out_cpg
+    return d
+
+
+class Conv3dCL(torch.autograd.Function):
+    """x: channel-last storage viewed as [N,V,Ti,Hi,Wi,Cg] (Cg contiguous); `groups` > 1 reads dim 1 as channel groups
+    (joint classifier head over the V planes of z_q).  Output [N,Vimg,To,Ho,Wo,Cout] contiguous."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, proj, relu, groups):
+        L.require_cuda(x, w)
+        lib = L.load()
+        if x.dtype != torch.float32:
+            x = x.float()
+        if x.stride(5) != 1 and x.shape[5] != 1:
+            x = x.contiguous()
+        N, V, Ti, Hi, Wi, Cg = x.shape
+        w = _f32c(w)
+        b = _f32c(b)
+        Vw = w.shape[0]                      # w: [Vw][Cout][Cin][kt][3][3]
+        Cout, Cin = w.shape[1], w.shape[2]
+        if groups > 1:
+            assert groups == V and Cin == V * Cg and Cg == 16 and Vw == 1
+            Vimg, x_sv, x_sg, in_cpg = 1, 0, x.stride(1), 1
+        else:
+            assert Cin == Cg
+            Vimg, x_sv, x_sg, in_cpg = V, x.stride(1), 0, max(Cg // 16, 1)
+        To = Ti if proj else (Ti - 2) // 2 + 1
+        y = torch.empty(N, Vimg, To, Hi, Wi, Cout, device=x.device, dtype=torch.float32)
+        d = _conv_desc((N, Vimg, Ti, Hi, Wi), (x.stride(0), x_sv, x.stride(2), x.stride(3), x.stride(4)),
+                       (y.stride(0), y.stride(1), y.stride(2), y.stride(3), y.stride(4)), Vw, Cin, Cout, proj, relu,
+                       in_cpg, max(Cout // 16, 1), x_sg, 0)
+        L.check(lib.idee_conv3d_fwd(C.byref(d), x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), L.stream()), "conv3d_fwd")
+        ctx.save_for_backward(x, w, y if relu else None)
+        ctx.desc, ctx.relu, ctx.groups = d, relu, groups
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = L.load()
+        x, w, y = ctx.saved_tensors
+        d = ctx.desc
+        gy = _f32c(gy)
+        if ctx.relu:
+            gy = torch.ops.aten.threshold_backward(gy, y, 0.0)
+        gw = torch.empty_like(w)
+        gb = torch.empty(w.shape[0], w.shape[1], device=w.device, dtype=torch.float32)
+        nws = lib.idee_conv3d_wgrad_workspace_bytes(C.byref(d))
+        ws = L.workspace(nws, x.device)
+        L.check(lib.idee_conv3d_wgrad(C.byref(d), x.data_ptr(), gy.data_ptr(), gw.data_ptr(), gb.data_ptr(), ws.data_ptr(), nws,
+                                      L.stream()), "conv3d_wgrad")
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_strided(x.shape, x.stride(), device=x.device, dtype=torch.float32) if _dense(x) else None
+            if gx is None:
+                raise RuntimeError("conv3d_dgrad: input must be a dense channel-last tensor")
+            L.check(lib.idee_conv3d_dgrad(C.byref(d), gy.data_ptr(), w.data_ptr(), None, gx.data_ptr(), L.stream()), "conv3d_dgrad")
+        return gx, gw, gb, None, None, None
+
+
+def _dense(t: torch.Tensor) -> bool:
+    """True if t's strides address every element of its storage span exactly once (a permuted contiguous tensor)."""
+    dims = sorted(((s, n) for s, n in zip(t.stride(), t.shape) if n > 1), key=lambda p: p[0])
+    expect = 1
+    for s, n in dims:
+        if s != expect:
+            return False
+        expect *= n
+    return True
+
+
+def conv3d_cl(x, w, b, proj: bool, relu: bool, groups: int = 1):
+    return Conv3dCL.apply(x, w, b, bool(proj), bool(relu), int(groups))
+
+
+class PackedWB(torch.autograd.Function):
+    """Identity view of a ParamPack's flat [V,P] buffer as a differentiable function of the individual parameters."""
+
+    @staticmethod
+    def forward(ctx, pack: ParamPack, shape, *params):
+        ctx.pack = pack
+        return pack.tensor().view(shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        pack = ctx.pack
+        return (None, None, *pack.split_grad(g.reshape(pack.V, pack.P)))
+
+
+def packed(pack: ParamPack, shape):
+    return PackedWB.apply(pack, tuple(shape), *pack.params())
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# LFQ
+# ----------------------------------------------------------------------------------------------------------------
+class LFQFn(torch.autograd.Function):
+    """z [..., 16] -> (z_q [..., 16], indices int64 [...], aux scalar).  LFQ.py:183-307."""
+
+    @staticmethod
+    def forward(ctx, z, w_in, b_in, w_out, b_out, training, inv_temp, lam_commit, lam_ent, gamma, codebook_size):
+        L.require_cuda(z)
+        lib = L.load()
+        z = _f32c(z)
+        w_in, b_in, w_out, b_out = _f32c(w_in), _f32c(b_in), _f32c(w_out), _f32c(b_out)
+        dim = z.shape[-1]
+        ntok = z.numel() // dim
+        zq = torch.empty_like(z)
+        idx = torch.empty(z.shape[:-1], device=z.device, dtype=torch.int64)
+        stats = torch.zeros(8, device=z.device, dtype=torch.float32)
+        nws = lib.idee_lfq_workspace_bytes(ntok)
+        ws = L.workspace(nws, z.device)
+        L.check(lib.idee_lfq_fwd(z.data_ptr(), w_in.data_ptr(), b_in.data_ptr(), w_out.data_ptr(), b_out.data_ptr(), zq.data_ptr(),
+                                 idx.data_ptr(), stats.data_ptr(), ntok, dim, codebook_size, int(training), inv_temp, lam_commit,
+                                 lam_ent, gamma, ws.data_ptr(), nws, L.stream()), "lfq_fwd")
+        ctx.save_for_backward(z, w_in, b_in, w_out, stats)
+        ctx.hyper = (inv_temp, lam_commit, lam_ent, gamma)
+        ctx.training = training
+        ctx.mark_non_differentiable(idx)
+        ctx.set_materialize_grads(False)
+        return zq, idx, stats[0]
+
+    @staticmethod
+    def backward(ctx, gzq, _gidx, gaux):
+        lib = L.load()
+        z, w_in, b_in, w_out, stats = ctx.saved_tensors
+        inv_temp, lam_commit, lam_ent, gamma = ctx.hyper
+        ntok = z.numel() // z.shape[-1]
+        gzq = torch.zeros_like(z) if gzq is None else _f32c(gzq)
+        if not ctx.training:
+            gaux = None   # eval mode: aux is a constant 0 and x = q has no gradient path to s
+        gaux_t = None if gaux is None else _f32c(gaux).reshape(1)
+        gz = torch.empty_like(z)
+        grads = torch.empty(49, device=z.device, dtype=torch.float32)
+        nws = lib.idee_lfq_workspace_bytes(ntok)
+        ws = L.workspace(nws, z.device)
+        L.check(lib.idee_lfq_bwd(z.data_ptr(), gzq.data_ptr(), L.ptr(gaux_t), stats.data_ptr(), w_in.data_ptr(), b_in.data_ptr(),
+                                 w_out.data_ptr(), gz.data_ptr(), grads.data_ptr(), ntok, inv_temp, lam_commit, lam_ent, gamma,
+                                 ws.data_ptr(), nws, L.stream()), "lfq_bwd")
+        if not ctx.training:
+            # x = q (LFQ.py:229-230): only project_out receives gradient
+            gz = torch.zeros_like(z)
+            grads[:17] = 0
+        return (gz, grads[0:16].view(1, 16), grads[16:17], grads[17:33].view(16, 1), grads[33:49],
+                None, None, None, None, None, None)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# losses
+# ----------------------------------------------------------------------------------------------------------------
+class BCEWeighted(torch.autograd.Function):
+    """K logit maps sharing one binary target -> losses [K].  losses.py:105-124.
+    pred: [K?, N, 1, H, W]-like storage addressed as k*sk + n*sn + i."""
+
+    @staticmethod
+    def forward(ctx, pred, target, K, sk, sn, N, HW):
+        L.require_cuda(pred, target)
+        lib = L.load()
+        target = _f32c(target)
+        loss = torch.empty(K, device=pred.device, dtype=torch.float32)
+        wts = torch.empty(2, device=pred.device, dtype=torch.float32)
+        dpred = torch.empty_strided(pred.shape, pred.stride(), device=pred.device, dtype=torch.float32)
+        L.check(lib.idee_bce_loss_fwd(pred.data_ptr(), sk, sn, K, N, HW, target.data_ptr(), wts.data_ptr(), loss.data_ptr(),
+                                      dpred.data_ptr(), L.stream()), "bce_loss_fwd")
+        ctx.save_for_backward(dpred)
+        ctx.K = K
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss):
+        (dpred,) = ctx.saved_tensors
+        if ctx.K == 1:
+            return dpred * gloss.reshape(()), None, None, None, None, None, None
+        shape = [ctx.K] + [1] * (dpred.dim() - 1)
+        return dpred * gloss.view(shape), None, None, None, None, None, None
+
+
+def bce_loss_map(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """single map, pred/target [N,1,H,W] (pred may be a strided view with contiguous H,W)."""
+    if pred.dtype != torch.float32:
+        pred = pred.float()
+    N = pred.shape[0]
+    HW = pred[0].numel()
+    inner_ok = pred[0].is_contiguous() if N > 0 else True
+    if not inner_ok:
+        pred = pred.contiguous()
+    return BCEWeighted.apply(pred, target, 1, 0, pred.stride(0), N, HW)[0]
+
+
+class AnomalyL1(torch.autograd.Function):
+    """z_q tokens [N,V,T,H,W,16], mask [N,H,W], vq0 [16] -> scalar.  losses.py:147-168."""
+
+    @staticmethod
+    def forward(ctx, zq, mask, vq0):
+        L.require_cuda(zq, mask, vq0)
+        lib = L.load()
+        zq, mask, vq0 = _f32c(zq), _f32c(mask), _f32c(vq0)
+        N, V, T, H, W, Cc = zq.shape
+        out = torch.empty(2, device=zq.device, dtype=torch.float32)
+        ntok = N * V * T * H * W
+        nws = lib.idee_anomaly_l1_workspace_bytes(ntok)
+        ws = L.workspace(nws, zq.device)
+        L.check(lib.idee_anomaly_l1_fwd(zq.data_ptr(), mask.data_ptr(), vq0.data_ptr(), N, V, T, H * W, Cc, out.data_ptr(),
+                                        ws.data_ptr(), nws, L.stream()), "anomaly_l1_fwd")
+        ctx.save_for_backward(zq, mask, vq0, out)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = L.load()
+        zq, mask, vq0, out = ctx.saved_tensors
+        N, V, T, H, W, Cc = zq.shape
+        g = _f32c(g).reshape(1)
+        gzq = torch.empty_like(zq)
+        L.check(lib.idee_anomaly_l1_bwd(zq.data_ptr(), mask.data_ptr(), vq0.data_ptr(), N, V, T, H * W, Cc, out.data_ptr(),
+                                        g.data_ptr(), gzq.data_ptr(), L.stream()), "anomaly_l1_bwd")
+        return gzq, None, None
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step):
+    lib = L.load()
+    L.check(lib.idee_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2, eps,
+                               weight_decay, step, L.stream()), "adam_step")

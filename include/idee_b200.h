@@ -1,0 +1,126 @@
+/* idee_b200 -- C ABI of the B200-native IDEE hot path (libidee_b200.so, sm_100a only).
+ *
+ * The reference (HakamShams/IDEE) ships no native code and no FFI: its hot path is plain PyTorch modules
+ * (SURVEY.md section 2).  These entry points are therefore what a binding for that path binds; each one names the
+ * reference code it replaces (paths relative to the reference repo root).  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; idee_last_error() returns the message (thread-local);
+ *   - all pointers are DEVICE pointers into caller-owned buffers (including workspaces, sized by the *_workspace_bytes
+ *     queries); the library never allocates, frees or synchronises; every launch goes to `stream` (a cudaStream_t);
+ *   - activations are fp32, channel-last: element (n,v,t,h,w,c) of a token tensor lives at ((((n*V+v)*T+t)*H+h)*W+w)*C+c
+ *     unless explicit strides (in elements) are passed;
+ *   - parameters keep the reference (PyTorch state_dict) layouts; gradients are written in the same layouts;
+ *   - there is no CPU fallback and no silent dispatch: an unsupported configuration is an error.
+ */
+#ifndef IDEE_B200_H
+#define IDEE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IDEE_B200_VERSION 100
+
+const char* idee_last_error(void);
+int idee_version(void);
+int idee_check_device(void);
+
+/* ---- PatchEmbed3D, patch (1,1,1): Conv3d(Cin->E,k=1,bias) + LayerNorm(E, no affine)   Swin_3D.py:449-491, :434 ----
+ * x: [N,V,Cin,T,H,W] with strides x_strides[6] = (n,v,c,t,h,w); w: [V][E][Cin]; b: [V][E]; y: [N,V,T,H,W,E]. */
+int idee_embed_ln_fwd(const float* x, const int64_t* x_strides, const float* w, const float* b, float* y,
+                      int N, int V, int Cin, int T, int H, int W, int E, void* stream);
+size_t idee_embed_ln_bwd_workspace_bytes(int V);
+int idee_embed_ln_bwd(const float* x, const int64_t* x_strides, const float* w, const float* b, const float* gy,
+                      float* gw, float* gb, int N, int V, int Cin, int T, int H, int W, int E,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- SwinTransformerBlock3D (LN1, cyclic shift, window partition, W-MSA/SW-MSA with relative position bias and shift
+ *      mask, proj, residual, LN2, MLP with erf-GELU, residual)                    Swin_3D.py:24-42, 45-74, 93-287, 340-352 ----
+ * One call runs the block of ALL V variables (V independent weight sets).
+ * params: [V][param_stride] floats; per variable, in the reference state_dict order of one block:
+ *   relative_position_bias_table[rpb_rows][heads] | qkv.weight[3C][C] | qkv.bias[3C] | proj.weight[C][C] | proj.bias[C] |
+ *   fc1.weight[hidden][C] | fc1.bias[hidden] | fc2.weight[C][hidden] | fc2.bias[C]      (idee_swin_block_packed_floats)
+ * rel_index: int32 [G][G], G = wd*wh*ww, the [:G,:G] slice of the module's relative_position_index buffer (Swin_3D.py:158-160).
+ * (wd,wh,ww) / (st,sh,sw) are the window and shift ALREADY clamped by get_window_size (Swin_3D.py:77-90). */
+typedef struct {
+    int N, V, T, H, W;      /* tokens [N,V,T,H,W,C] */
+    int C, heads, hidden;   /* built: 16, 2, 64 */
+    int wd, wh, ww;         /* window */
+    int st, sh, sw;         /* cyclic shift of this block (0,0,0 = W-MSA) */
+    int rpb_rows;           /* rows of the bias table, (2Wd-1)(2Wh-1)(2Ww-1) of the CONFIGURED window */
+    float scale;            /* qk scale, head_dim^-0.5 unless overridden */
+    int64_t param_stride;   /* floats between consecutive variables' packed parameter blocks */
+} idee_swin_desc;
+
+int idee_swin_block_packed_floats(int rpb_rows);
+/* ymid (optional, may be NULL): the mid-block residual x + attn(...) saved for the backward pass */
+int idee_swin_block_fwd(const idee_swin_desc* d, const float* x, float* out, float* ymid, const float* params,
+                        const int32_t* rel_index, void* stream);
+size_t idee_swin_block_bwd_workspace_bytes(const idee_swin_desc* d);
+/* gx may alias gout.  gparams: [V][param_stride], every packed element is overwritten. */
+int idee_swin_block_bwd(const idee_swin_desc* d, const float* x, const float* ymid, const float* gout, float* gx,
+                        const float* params, const int32_t* rel_index, float* gparams,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- channel-last Conv3d of the path ----
+ * proj=1: Conv3d(Cin,Cout,k=3,s=1,p=1,padding_mode='replicate')           Swin_3D.py:586-592   (encoder proj_var)
+ * proj=0: Conv3d(Cin,Cout,k=(2,3,3),s=(2,1,1),p=(0,1,1)), zero padding     classifier/CNN_3D.py:36-38, 83-85
+ * Images are indexed (n,v), n<N, v<V; image (n,v) uses weight set v when Vw==V, weight set 0 when Vw==1.
+ * Channels come in 16-wide chunks; chunk k of the input sits at (k / in_cpg) * x_sg + (k % in_cpg) * 16 from the pixel
+ * address (this lets the joint classifier head read the V per-variable planes of z_q as one 16*V-channel image);
+ * same for the output with out_cpg / y_sg.  w: [Vw][Cout][Cin][kt][3][3] (reference layout), b: [Vw][Cout]. */
+typedef struct {
+    int N, V, Vw;
+    int Cin, Cout;
+    int Ti, Hi, Wi, To, Ho, Wo;
+    int proj;               /* 1: 3x3x3 replicate, 0: (2,3,3)/(2,1,1) zero-pad */
+    int relu;               /* forward: fuse ReLU into the epilogue */
+    int64_t x_sn, x_sv, x_st, x_sh, x_sw, x_sg; int in_cpg;
+    int64_t y_sn, y_sv, y_st, y_sh, y_sw, y_sg; int out_cpg;
+} idee_conv_desc;
+
+int idee_conv3d_fwd(const idee_conv_desc* d, const float* x, const float* w, const float* b, float* y, void* stream);
+/* gx = conv^T(gy); when relu_src != NULL (same layout as gx) gx is multiplied by (relu_src > 0): the ReLU that
+ * produced this conv's input is folded into the data gradient */
+int idee_conv3d_dgrad(const idee_conv_desc* d, const float* gy, const float* w, const float* relu_src, float* gx, void* stream);
+size_t idee_conv3d_wgrad_workspace_bytes(const idee_conv_desc* d);
+int idee_conv3d_wgrad(const idee_conv_desc* d, const float* x, const float* gy, float* gw, float* gb,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- LFQ quantiser, dim=16, codebook_size=2                                      models/codebook/LFQ.py:183-307 ----
+ * z,zq,gz,gzq: [ntok][16]; indices: int64 [ntok]; stats: float[8] = {aux, per_sample_entropy, codebook_entropy,
+ * commit, mean p0, mean p1, ntok, 0} (written only when training); grads: float[49] = g_w_in[16] | g_b_in | g_w_out[16] | g_b_out[16] */
+size_t idee_lfq_workspace_bytes(int64_t ntok);
+int idee_lfq_fwd(const float* z, const float* w_in, const float* b_in, const float* w_out, const float* b_out,
+                 float* zq, int64_t* indices, float* stats, int64_t ntok, int dim, int codebook_size, int training,
+                 float inv_temperature, float lambda_commit, float lambda_entropy, float diversity_gamma,
+                 void* workspace, size_t workspace_bytes, void* stream);
+int idee_lfq_bwd(const float* z, const float* gzq, const float* g_aux, const float* stats, const float* w_in,
+                 const float* b_in, const float* w_out, float* gz, float* grads, int64_t ntok, float inv_temperature,
+                 float lambda_commit, float lambda_entropy, float diversity_gamma,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- losses                                                                         models/losses.py:98-168 ----
+ * BCE_loss_synthetic over K logit maps sharing one target: element (k,n,i) of pred at k*stride_k + n*stride_n + i, i<HW;
+ * target: [N][HW]; wts: float[2] scratch (class weights); loss: float[K]; dpred (optional, pred's layout): d loss[k] / d pred. */
+int idee_bce_loss_fwd(const float* pred, int64_t stride_k, int64_t stride_n, int K, int N, int64_t HW, const float* target,
+                      float* wts, float* loss, float* dpred, void* stream);
+/* Anomaly_L1_loss_synthetic: zq [N,V,T,HW,16], mask [N][HW], vq0 [16]; out: float[2] = {loss, total weight} */
+size_t idee_anomaly_l1_workspace_bytes(int64_t ntok);
+int idee_anomaly_l1_fwd(const float* zq, const float* mask, const float* vq0, int N, int V, int T, int64_t HW, int C, float* out,
+                        void* workspace, size_t workspace_bytes, void* stream);
+int idee_anomaly_l1_bwd(const float* zq, const float* mask, const float* vq0, int N, int V, int T, int64_t HW, int C,
+                        const float* out, const float* g_loss, float* gzq, void* stream);
+
+/* ---- optimiser: torch.optim.Adam(lr, betas, eps, weight_decay) on one flat buffer        train_synthetic.py:127-129 ---- */
+int idee_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, int step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IDEE_B200_H */

@@ -1,0 +1,117 @@
+"""CPU-side tests (-m "not gpu"): the C-ABI library loads and exports every declared symbol, the host-side mirror of the
+reference interface has the reference's parameter inventory / initialisation, and the product path refuses CPU tensors."""
+import os
+import re
+import sys
+
+import pytest
+import torch
+
+from oracle import idee_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "idee_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(idee_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from idee_b200 import _lib
+    lib = _lib.load()
+    syms = declared_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/idee_b200.h but not exported"
+    assert set(syms) == set(_lib.EXPORTS), set(syms) ^ set(_lib.EXPORTS)
+    assert lib.idee_version() == 100
+    assert lib.idee_swin_block_packed_floats(147) == 147 * 2 + 3216
+
+
+def test_state_dict_inventory_matches_reference_names():
+    from idee_b200.config import default_config
+    from idee_b200.models.build import VQ_model
+    for V, Cin in ((6, 1), (2, 2)):
+        model = VQ_model(default_config(in_channels_dynamic=V, in_channels=Cin))
+        got = {k: tuple(v.shape) for k, v in model.named_parameters()}
+        assert got == O.param_shapes(O.OracleConfig(in_vars=V, in_chans=Cin))
+        bufs = {k for k, _ in model.named_buffers()}
+        assert "vq.mask" in bufs and "encoder.layers_var.0.0.blocks.0.attn.relative_position_index" in bufs
+        sd = model.state_dict()
+        assert "vq.zero" not in sd and "vq.codebook" not in sd           # non-persistent (LFQ.py:135,143)
+    assert sum(p.numel() for p in VQ_model(default_config()).parameters()) == 535892
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (GPU box)")
+def test_initialisation_is_bit_identical_to_reference():
+    from tests.golden.make_golden import import_reference, reference_config
+    from idee_b200.config import default_config
+    from idee_b200.models.build import VQ_model
+    build, _, config_mod = import_reference()
+    torch.manual_seed(0)
+    ref = build.VQ_model(reference_config(config_mod, in_channels_dynamic=3, in_channels=1))
+    torch.manual_seed(0)
+    ours = VQ_model(default_config(in_channels_dynamic=3, in_channels=1))
+    rsd, osd = ref.state_dict(), ours.state_dict()
+    assert list(rsd.keys()) == list(osd.keys())
+    for k in rsd:
+        assert torch.equal(rsd[k], osd[k]), k
+    sys.modules.pop("models", None)
+
+
+def test_window_clamp_and_relative_index():
+    from idee_b200.models.encoder.Swin_3D import get_window_size, _relative_position_index
+    assert get_window_size((8, 200, 200), (8, 1, 1), (4, 0, 0)) == ((8, 1, 1), (0, 0, 0))
+    assert get_window_size((8, 200, 200), (2, 4, 4), (1, 2, 2)) == ((2, 4, 4), (1, 2, 2))
+    assert get_window_size((8, 3, 200), (2, 4, 4)) == (2, 3, 4)
+    for ws in ((2, 4, 4), (8, 1, 1), (2, 2, 2)):
+        assert torch.equal(_relative_position_index(ws), O.relative_position_index(ws))
+        assert get_window_size((5, 2, 9), ws, (1, 1, 1)) == O.get_window_size((5, 2, 9), ws, (1, 1, 1))
+
+
+def test_param_pack_aliases_and_survives_updates():
+    from idee_b200.ops import ParamPack
+    lins = [torch.nn.Linear(4, 3) for _ in range(3)]
+    pack = ParamPack([[l.weight, l.bias] for l in lins])
+    before = [l.weight.detach().clone() for l in lins]
+    flat = pack.tensor()
+    assert flat.shape == (3, 15) and pack.tensor() is flat
+    for v, l in enumerate(lins):
+        assert torch.equal(l.weight, before[v]) and torch.equal(flat[v, :12].view(3, 4), before[v])
+        with torch.no_grad():
+            l.weight.add_(1.0)                                      # optimiser-style in-place update
+        assert torch.equal(flat[v, :12].view(3, 4), before[v] + 1.0)
+    lins[1].weight.data = lins[1].weight.data.clone()               # storage replaced (e.g. module.to())
+    assert pack.tensor() is not flat                                # re-packed
+    g = torch.arange(45.).view(3, 15)
+    parts = pack.split_grad(g)
+    assert parts[2].shape == (3, 4) and torch.equal(parts[3], g[1, 12:])
+
+
+def test_product_path_has_no_cpu_fallback():
+    from idee_b200.models.encoder.Swin_3D import Swin_3D
+    from idee_b200.models.codebook.LFQ import LFQ
+    with pytest.raises(RuntimeError):
+        Swin_3D(in_vars=1, in_chans=1)(torch.randn(1, 1, 1, 8, 8, 8))
+    with pytest.raises(RuntimeError):
+        LFQ(dim=16, codebook_size=2)(torch.randn(1, 4, 16))
+
+
+def test_unsupported_configs_are_hard_errors():
+    from idee_b200.models.encoder.Swin_3D import Swin_3D
+    with pytest.raises(NotImplementedError):
+        Swin_3D(in_vars=1, embed_dim=[32, 32])
+    with pytest.raises(NotImplementedError):
+        Swin_3D(in_vars=1, drop_path_rate=0.1)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "idee_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle" not in src, f"{f} mentions the oracle"
