@@ -97,7 +97,7 @@ def stage_swin_b():
     _block_case((8, 1, 1), False, (8, 6, 10))
     _block_case((2, 4, 4), True, (8, 10, 14))      # padded H, W
     _block_case((8, 1, 1), False, (12, 4, 6))      # padded T (12 -> 16)
-    _block_case((2, 4, 4), True, (8, 3, 9))        # clamped window on H (3 <= 4), padded W
+    _block_case((2, 4, 4), True, (2, 8, 9))        # clamped window on T (2 <= 2 -> no T shift), padded W
     _block_case((2, 4, 4), True, (8, 24, 28), V=3)
 
 
