@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""Benchmark of the IDEE hot path (BASELINE.json metric: train samples/s of the Swin-3D IDEE model, 200x200 synthetic-CERRA).
+
+    python bench.py --gpus N --steps K --warmup W                  # this repo's CUDA path (one process per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W # the reference algorithm on the host CPU (oracle port)
+
+A step = forward + reference loss assembly + backward + (N>1: one flat NCCL gradient all-reduce) + fused Adam on one batch
+of B=8 samples per GPU of shape [6,1,8,200,200] (BASELINE.json configs[1]; weak scaling for N>1).  Prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch
+
+FLOP_FWD_BWD_PER_SAMPLE = 571.98e9      # SURVEY.md section 8d / BASELINE.md (matmul+conv FLOPs, 2*MAC, bwd = 2x fwd)
+METRIC = "train_samples_per_sec"
+UNIT = "samples/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="idee_b200", choices=["idee_b200", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="samples per GPU per step")
+    ap.add_argument("--hw", type=int, default=200)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, n_gpus):
+    return {"workload": f"IDEE VQ_model (Swin_3D encoder + LFQ + CNN_3D classifier) train step, synthetic-CERRA "
+                        f"[B={args.batch}/GPU, V=6, C=1, T=8, {args.hw}x{args.hw}] (BASELINE.json configs[1])",
+            "batch_per_gpu": args.batch, "global_batch": args.batch * n_gpus, "grid": [args.hw, args.hw], "T": 8, "V": 6,
+            "parallelism": f"dp{n_gpus}" if n_gpus > 1 else "single",
+            "step": "fwd + losses + bwd + flat grad all-reduce + fused Adam",
+            "l2": "working set >> L2: every activation tensor of a step is 0.98 GB (fp32), inputs 61 MB"}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference algorithm, timed on the host cores
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_oracle_samples_per_sec(hw, steps, warmup):
+    from oracle import idee_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    cfg = O.OracleConfig()
+    sd = {k: v.requires_grad_(True) for k, v in O.make_state_dict(cfg, seed=0, kind="reference").items()}
+    x, m_ext, m_loss = O.make_inputs(cfg, 1, 8, hw, hw, seed=0)
+    times = []
+    for it in range(warmup + steps):
+        for p in sd.values():
+            p.grad = None
+        t0 = time.perf_counter()
+        total, _ = O.train_step_loss(sd, x, m_ext, m_loss, cfg)
+        total.backward()
+        times.append(time.perf_counter() - t0)
+    sec = statistics.median(times[warmup:])
+    return 1.0 / sec, sec
+
+
+def cpu_model_name():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sps, sec = cpu_oracle_samples_per_sec(args.hw, args.steps, args.warmup)
+    sample = (f"B=1 sample per step of the same workload (forward + losses + backward, fp32, no optimiser), oracle port of the "
+              f"reference on {os.cpu_count()} host threads ({cpu_model_name()}), median of {args.steps} steps")
+    line = {"impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp32", "data": "synthetic", "config": workload_config(args, args.gpus),
+            "cpu_baseline": {"value": sps, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+            "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.idx, self.proc, self.lines = device_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for l in self.lines:
+            f = [t.strip() for t in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, val in zip(names, f[3:7]):
+                if val == "Active":
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# algorithmic work of the entry points (for the roofline of the dominant kernel)
+# ------------------------------------------------------------------------------------------------------------------
+def op_flops(name, B, V, T, H, W):
+    """Algorithmic FLOPs (2*MAC, no recompute / padding credit) of ONE call of an entry point; None if not FLOP-shaped."""
+    tok = B * V * T * H * W
+    if name.startswith("swin_block"):
+        per_tok = 8192 if "(2, 4, 4)" in name else 6656
+        return tok * per_tok * (2 if "bwd" in name else 1)
+    if name.startswith("conv3d"):
+        tag = name[name.index("[") + 1:-1]                        # e.g. "cls 96->96 T8"
+        kind, ch, tt = tag.split()
+        cin, cout = (int(c) for c in ch.split("->"))
+        ti = int(tt[1:])
+        imgs = B * (V if cin == 16 and cout <= 16 else 1)
+        if kind == "proj":
+            return 2 * 27 * cin * cout * imgs * ti * H * W
+        return 2 * 18 * cin * cout * imgs * ((ti - 2) // 2 + 1) * H * W
+    return None
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: the idee_b200 arm needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+
+    from idee_b200 import _lib
+    from idee_b200.config import default_config
+    from idee_b200.models.build import VQ_model
+    from idee_b200.trainer import Trainer
+    from oracle import idee_oracle as O            # only for the synthetic input factory and the cpu_baseline leg
+
+    _lib.check(_lib.load().idee_check_device(), "check_device")
+    cfg = default_config()
+    torch.manual_seed(0)
+    model = VQ_model(cfg).to(dev).train()
+    trainer = Trainer(model, lr=cfg.lr, betas=(cfg.beta1, cfg.beta2), weight_decay=cfg.weight_decay,
+                      lambda_anomaly=cfg.lambda_anomaly)
+    B, HW = args.batch, args.hw
+    ocfg = O.OracleConfig()
+    x_h, me_h, ml_h = O.make_inputs(ocfg, B, 8, HW, HW, seed=rank)
+    x_h, me_h, ml_h = x_h.pin_memory(), me_h.pin_memory(), ml_h.pin_memory()
+    x, me, ml = x_h.to(dev), me_h.to(dev), ml_h.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput ----
+    for _ in range(args.warmup):
+        trainer.step(x, me, ml)
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    _lib.Profile.reset(events=False)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss, _ = trainer.step(x, me, ml)
+    e1.record()
+    barrier()
+    clock_info = clocks.stop()
+    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    launches = _lib.Profile.launches
+    value = n_gpus * B / (ms_step / 1e3)
+    loss_val = float(loss)
+
+    # ---- end to end through the public API: pinned host inputs -> device, step, loss + logits back to the host ----
+    pred_h = torch.empty(B, 1, HW, HW, dtype=torch.float32).pin_memory()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        xd, med, mld = x_h.to(dev, non_blocking=True), me_h.to(dev, non_blocking=True), ml_h.to(dev, non_blocking=True)
+        loss, out = trainer.step(xd, med, mld)
+        pred_h.copy_(out["pred"].detach(), non_blocking=True)
+        _ = loss.item()
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    h2d = x_h.numel() * 4 + me_h.numel() * 4 + ml_h.numel() * 4
+    d2h = pred_h.numel() * 4 + 4
+
+    # ---- per-entry-point CUDA-event profile (same workload, same stream) for the roofline of the dominant kernel ----
+    roofline, breakdown = None, None
+    if not args.no_profile:
+        prof_steps = max(2, min(args.steps, 5))
+        barrier()
+        _lib.Profile.reset(events=True)
+        for _ in range(prof_steps):
+            trainer.step(x, me, ml)
+        torch.cuda.synchronize()
+        summ = _lib.Profile.summary()
+        _lib.Profile.reset(events=False)
+        tot = sum(t for _, t in summ.values())
+        top = sorted(summ.items(), key=lambda kv: -kv[1][1])
+        breakdown = [{"op": k, "calls_per_step": c / prof_steps, "ms_per_step": t / prof_steps, "share": t / tot} for k, (c, t) in top[:12]]
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+        for k, (c, t) in top:
+            fl = op_flops(k, B, 6, 8, HW, HW)
+            if fl is not None:
+                avg_ms = t / c
+                ach = fl / (avg_ms * 1e-3) / 1e12
+                roofline = {"kernel": k, "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                            "traffic": None, "avg_ms_per_launch": avg_ms, "flops_per_launch": fl, "share_of_step": t / tot,
+                            "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s (of fallback)",
+                            "note": "fp32 CUDA-core kernel measured against the dense bf16 tensor-core peak"}
+                break
+
+    if rank == 0:
+        cpu_baseline = None
+        if n_gpus == 1 and not args.no_cpu_baseline:
+            sps, sec = cpu_oracle_samples_per_sec(HW, 2, 1)
+            cpu_baseline = {"value": sps, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                            "sample": f"B=1 sample of the same workload, fwd+losses+bwd fp32, median of 2 steps after 1 warm-up "
+                                      f"({sec:.2f} s/step), {cpu_model_name()}"}
+        whole_model_tf = value / n_gpus * FLOP_FWD_BWD_PER_SAMPLE / 1e12
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32",
+                "data": "synthetic", "config": workload_config(args, n_gpus), "impl": "idee_b200",
+                "e2e": {"value": n_gpus * B / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e},
+                "gpu_launches": launches, "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "model_tflops_per_gpu": whole_model_tf, "loss": loss_val, "breakdown": breakdown}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -89,6 +89,47 @@ def check(rc: int, what: str = ""):
         raise RuntimeError(f"idee_b200 {what} failed (rc={rc}): {msg}")
 
 
+# kernels launched by each C-ABI entry point (used for the gpu_launches figure of bench.py)
+LAUNCHES = {"embed_ln_fwd": 1, "embed_ln_bwd": 2, "swin_block_fwd": 1, "swin_block_bwd": 3, "conv3d_fwd": 1, "conv3d_dgrad": 1,
+            "conv3d_wgrad": 2, "lfq_fwd": 2, "lfq_fwd_eval": 1, "lfq_bwd": 2, "bce_loss_fwd": 2, "anomaly_l1_fwd": 2,
+            "anomaly_l1_bwd": 1, "adam_step": 1}
+
+
+class Profile:
+    """Opt-in per-entry-point accounting: launch counts always, CUDA-event timing when ``events`` is on."""
+    launches = 0
+    events = False
+    records = []      # (name, tag, start_event, end_event)
+
+    @classmethod
+    def reset(cls, events: bool = False):
+        cls.launches, cls.events, cls.records = 0, events, []
+
+    @classmethod
+    def summary(cls):
+        """{name: (calls, total_ms)} -- call after torch.cuda.synchronize()."""
+        out = {}
+        for name, tag, e0, e1 in cls.records:
+            key = name if tag is None else f"{name}[{tag}]"
+            c, t = out.get(key, (0, 0.0))
+            out[key] = (c + 1, t + e0.elapsed_time(e1))
+        return out
+
+
+def run(what: str, fn, *args, tag=None):
+    """Call one C-ABI entry point on the current stream; raise on a non-zero return code."""
+    Profile.launches += LAUNCHES[what]
+    if Profile.events:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        Profile.records.append((what, tag, e0, e1))
+    else:
+        rc = fn(*args)
+    check(rc, what)
+
+
 def stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 

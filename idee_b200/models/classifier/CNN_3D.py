@@ -78,11 +78,16 @@ class CNN_3D(nn.Module):
                 if m.bias is not None:
                     nn.init.constant_(m.bias, 0)
 
-    def _head_params(self):
+    def packs(self):
+        """ParamPacks of the per-variable heads (the joint head's parameters are used in place)."""
         if self._packs is None:
             V = self.in_var
             self._packs = [(ops.ParamPack([[getattr(self.layers[v], n).weight] for v in range(V)]),
                             ops.ParamPack([[getattr(self.layers[v], n).bias] for v in range(V)])) for n in ("conv1", "conv2", "conv3")]
+        return [p for pair in self._packs for p in pair]
+
+    def _head_params(self):
+        self.packs()
         V, e, d = self.in_var, self.var_embed_dim, self.var_dim
         shapes = [(V, d, e, 2, 3, 3), (V, d, d, 2, 3, 3), (V, 1, d, 2, 3, 3)]
         return [(ops.packed(pw, s), ops.packed(pb, (V, s[1]))) for (pw, pb), s in zip(self._packs, shapes)]

@@ -235,6 +235,14 @@ class Swin_3D(nn.Module):
             packs[f"proj{i}_b"] = ops.ParamPack([[self.proj_var[v][i].bias] for v in range(V)])
         self._packs = packs
 
+    def packs(self):
+        """Every ParamPack of the variable-batched path (for model-wide flat parameter / gradient buffers)."""
+        if self._packs is None:
+            self._build_packs()
+        pk = self._packs
+        return [pk["embed_w"], pk["embed_b"]] + [p for _, _, p in pk["blocks"]] + \
+            [pk["proj0_w"], pk["proj0_b"], pk["proj2_w"], pk["proj2_b"]]
+
     def forward_tokens(self, x: torch.Tensor) -> torch.Tensor:
         """x [N,V,C,D,H,W] -> channel-last encoder output [N,V,D,H,W,E] (contiguous)."""
         if x.dim() == 5 and self.in_chans == 1:

@@ -47,9 +47,15 @@ class ParamPack:
         p0 = self.groups[0][0]
         if self.flat is not None and self.flat.device == p0.device and self._aliased():
             return self.flat
+        return self.bind(torch.empty(self.V, self.P, device=p0.device, dtype=torch.float32))
+
+    @torch.no_grad()
+    def bind(self, flat: torch.Tensor) -> torch.Tensor:
+        """Move the parameters into ``flat`` ([V,P] fp32, possibly a slice of a model-wide buffer) and alias them to it."""
+        p0 = self.groups[0][0]
         if p0.dtype != torch.float32:
             raise RuntimeError("idee_b200 keeps fp32 master parameters; got %s" % p0.dtype)
-        flat = torch.empty(self.V, self.P, device=p0.device, dtype=torch.float32)
+        assert tuple(flat.shape) == (self.V, self.P) and flat.is_contiguous() and flat.dtype == torch.float32
         for v, g in enumerate(self.groups):
             off = 0
             for p, n in zip(g, self.sizes):
@@ -91,8 +97,8 @@ class EmbedLN(torch.autograd.Function):
         w, b = wpack.tensor(), bpack.tensor()
         y = torch.empty(N, V, T, H, W, 16, device=x.device, dtype=torch.float32)
         xs = (C.c_int64 * 6)(*x.stride())
-        L.check(lib.idee_embed_ln_fwd(x.data_ptr(), C.cast(xs, C.c_void_p), w.data_ptr(), b.data_ptr(), y.data_ptr(),
-                                      N, V, Cin, T, H, W, 16, L.stream()), "embed_ln_fwd")
+        L.run("embed_ln_fwd", lib.idee_embed_ln_fwd, x.data_ptr(), C.cast(xs, C.c_void_p), w.data_ptr(), b.data_ptr(), y.data_ptr(),
+                                      N, V, Cin, T, H, W, 16, L.stream())
         ctx.save_for_backward(x)
         ctx.packs = (wpack, bpack)
         return y
@@ -109,9 +115,8 @@ class EmbedLN(torch.autograd.Function):
         nws = lib.idee_embed_ln_bwd_workspace_bytes(V)
         ws = L.workspace(nws, x.device)
         xs = (C.c_int64 * 6)(*x.stride())
-        L.check(lib.idee_embed_ln_bwd(x.data_ptr(), C.cast(xs, C.c_void_p), w.data_ptr(), b.data_ptr(), gy.data_ptr(),
-                                      gw.data_ptr(), gb.data_ptr(), N, V, Cin, T, H, W, 16, ws.data_ptr(), nws, L.stream()),
-                "embed_ln_bwd")
+        L.run("embed_ln_bwd", lib.idee_embed_ln_bwd, x.data_ptr(), C.cast(xs, C.c_void_p), w.data_ptr(), b.data_ptr(), gy.data_ptr(),
+                                      gw.data_ptr(), gb.data_ptr(), N, V, Cin, T, H, W, 16, ws.data_ptr(), nws, L.stream())
         return (None, None, None, *wpack.split_grad(gw), *bpack.split_grad(gb))
 
 
@@ -147,8 +152,8 @@ class SwinBlock(torch.autograd.Function):
         out = torch.empty_like(x)
         need_bwd = any(ctx.needs_input_grad)
         ymid = torch.empty_like(x) if need_bwd else None
-        L.check(lib.idee_swin_block_fwd(C.byref(d), x.data_ptr(), out.data_ptr(), L.ptr(ymid), flat.data_ptr(),
-                                        rel_index.data_ptr(), L.stream()), "swin_block_fwd")
+        L.run("swin_block_fwd", lib.idee_swin_block_fwd, C.byref(d), x.data_ptr(), out.data_ptr(), L.ptr(ymid), flat.data_ptr(),
+              rel_index.data_ptr(), L.stream(), tag=f"w{window} s{shift}")
         if need_bwd:
             ctx.save_for_backward(x, ymid, rel_index)
             ctx.pack, ctx.args = pack, (window, shift, rpb_rows, scale, heads, hidden)
@@ -167,8 +172,8 @@ class SwinBlock(torch.autograd.Function):
         gflat = torch.empty_like(flat)
         nws = lib.idee_swin_block_bwd_workspace_bytes(C.byref(d))
         ws = L.workspace(nws, x.device)
-        L.check(lib.idee_swin_block_bwd(C.byref(d), x.data_ptr(), ymid.data_ptr(), gout.data_ptr(), gx.data_ptr(), flat.data_ptr(),
-                                        rel_index.data_ptr(), gflat.data_ptr(), ws.data_ptr(), nws, L.stream()), "swin_block_bwd")
+        L.run("swin_block_bwd", lib.idee_swin_block_bwd, C.byref(d), x.data_ptr(), ymid.data_ptr(), gout.data_ptr(), gx.data_ptr(), flat.data_ptr(),
+                                        rel_index.data_ptr(), gflat.data_ptr(), ws.data_ptr(), nws, L.stream(), tag=f"w{window} s{shift}")
         return (gx, None, None, None, None, None, None, None, None, *pack.split_grad(gflat))
 
 
@@ -222,7 +227,8 @@ class Conv3dCL(torch.autograd.Function):
         d = _conv_desc((N, Vimg, Ti, Hi, Wi), (x.stride(0), x_sv, x.stride(2), x.stride(3), x.stride(4)),
                        (y.stride(0), y.stride(1), y.stride(2), y.stride(3), y.stride(4)), Vw, Cin, Cout, proj, relu,
                        in_cpg, max(Cout // 16, 1), x_sg, 0)
-        L.check(lib.idee_conv3d_fwd(C.byref(d), x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), L.stream()), "conv3d_fwd")
+        L.run("conv3d_fwd", lib.idee_conv3d_fwd, C.byref(d), x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), L.stream(),
+              tag=_conv_tag(d))
         ctx.save_for_backward(x, w, y if relu else None)
         ctx.desc, ctx.relu, ctx.groups = d, relu, groups
         return y
@@ -239,15 +245,20 @@ class Conv3dCL(torch.autograd.Function):
         gb = torch.empty(w.shape[0], w.shape[1], device=w.device, dtype=torch.float32)
         nws = lib.idee_conv3d_wgrad_workspace_bytes(C.byref(d))
         ws = L.workspace(nws, x.device)
-        L.check(lib.idee_conv3d_wgrad(C.byref(d), x.data_ptr(), gy.data_ptr(), gw.data_ptr(), gb.data_ptr(), ws.data_ptr(), nws,
-                                      L.stream()), "conv3d_wgrad")
+        L.run("conv3d_wgrad", lib.idee_conv3d_wgrad, C.byref(d), x.data_ptr(), gy.data_ptr(), gw.data_ptr(), gb.data_ptr(), ws.data_ptr(), nws,
+                                      L.stream(), tag=_conv_tag(d))
         gx = None
         if ctx.needs_input_grad[0]:
             gx = torch.empty_strided(x.shape, x.stride(), device=x.device, dtype=torch.float32) if _dense(x) else None
             if gx is None:
                 raise RuntimeError("conv3d_dgrad: input must be a dense channel-last tensor")
-            L.check(lib.idee_conv3d_dgrad(C.byref(d), gy.data_ptr(), w.data_ptr(), None, gx.data_ptr(), L.stream()), "conv3d_dgrad")
+            L.run("conv3d_dgrad", lib.idee_conv3d_dgrad, C.byref(d), gy.data_ptr(), w.data_ptr(), None, gx.data_ptr(), L.stream(),
+                  tag=_conv_tag(d))
         return gx, gw, gb, None, None, None
+
+
+def _conv_tag(d) -> str:
+    return f"{'proj' if d.proj else 'cls'} {d.Cin}->{d.Cout} T{d.Ti}"
 
 
 def _dense(t: torch.Tensor) -> bool:
@@ -302,9 +313,9 @@ class LFQFn(torch.autograd.Function):
         stats = torch.zeros(8, device=z.device, dtype=torch.float32)
         nws = lib.idee_lfq_workspace_bytes(ntok)
         ws = L.workspace(nws, z.device)
-        L.check(lib.idee_lfq_fwd(z.data_ptr(), w_in.data_ptr(), b_in.data_ptr(), w_out.data_ptr(), b_out.data_ptr(), zq.data_ptr(),
+        L.run("lfq_fwd" if training else "lfq_fwd_eval", lib.idee_lfq_fwd, z.data_ptr(), w_in.data_ptr(), b_in.data_ptr(), w_out.data_ptr(), b_out.data_ptr(), zq.data_ptr(),
                                  idx.data_ptr(), stats.data_ptr(), ntok, dim, codebook_size, int(training), inv_temp, lam_commit,
-                                 lam_ent, gamma, ws.data_ptr(), nws, L.stream()), "lfq_fwd")
+                                 lam_ent, gamma, ws.data_ptr(), nws, L.stream())
         ctx.save_for_backward(z, w_in, b_in, w_out, stats)
         ctx.hyper = (inv_temp, lam_commit, lam_ent, gamma)
         ctx.training = training
@@ -326,9 +337,9 @@ class LFQFn(torch.autograd.Function):
         grads = torch.empty(49, device=z.device, dtype=torch.float32)
         nws = lib.idee_lfq_workspace_bytes(ntok)
         ws = L.workspace(nws, z.device)
-        L.check(lib.idee_lfq_bwd(z.data_ptr(), gzq.data_ptr(), L.ptr(gaux_t), stats.data_ptr(), w_in.data_ptr(), b_in.data_ptr(),
+        L.run("lfq_bwd", lib.idee_lfq_bwd, z.data_ptr(), gzq.data_ptr(), L.ptr(gaux_t), stats.data_ptr(), w_in.data_ptr(), b_in.data_ptr(),
                                  w_out.data_ptr(), gz.data_ptr(), grads.data_ptr(), ntok, inv_temp, lam_commit, lam_ent, gamma,
-                                 ws.data_ptr(), nws, L.stream()), "lfq_bwd")
+                                 ws.data_ptr(), nws, L.stream())
         if not ctx.training:
             # x = q (LFQ.py:229-230): only project_out receives gradient
             gz = torch.zeros_like(z)
@@ -352,8 +363,8 @@ class BCEWeighted(torch.autograd.Function):
         loss = torch.empty(K, device=pred.device, dtype=torch.float32)
         wts = torch.empty(2, device=pred.device, dtype=torch.float32)
         dpred = torch.empty_strided(pred.shape, pred.stride(), device=pred.device, dtype=torch.float32)
-        L.check(lib.idee_bce_loss_fwd(pred.data_ptr(), sk, sn, K, N, HW, target.data_ptr(), wts.data_ptr(), loss.data_ptr(),
-                                      dpred.data_ptr(), L.stream()), "bce_loss_fwd")
+        L.run("bce_loss_fwd", lib.idee_bce_loss_fwd, pred.data_ptr(), sk, sn, K, N, HW, target.data_ptr(), wts.data_ptr(), loss.data_ptr(),
+                                      dpred.data_ptr(), L.stream())
         ctx.save_for_backward(dpred)
         ctx.K = K
         return loss
@@ -392,8 +403,8 @@ class AnomalyL1(torch.autograd.Function):
         ntok = N * V * T * H * W
         nws = lib.idee_anomaly_l1_workspace_bytes(ntok)
         ws = L.workspace(nws, zq.device)
-        L.check(lib.idee_anomaly_l1_fwd(zq.data_ptr(), mask.data_ptr(), vq0.data_ptr(), N, V, T, H * W, Cc, out.data_ptr(),
-                                        ws.data_ptr(), nws, L.stream()), "anomaly_l1_fwd")
+        L.run("anomaly_l1_fwd", lib.idee_anomaly_l1_fwd, zq.data_ptr(), mask.data_ptr(), vq0.data_ptr(), N, V, T, H * W, Cc, out.data_ptr(),
+                                        ws.data_ptr(), nws, L.stream())
         ctx.save_for_backward(zq, mask, vq0, out)
         return out[0]
 
@@ -404,12 +415,12 @@ class AnomalyL1(torch.autograd.Function):
         N, V, T, H, W, Cc = zq.shape
         g = _f32c(g).reshape(1)
         gzq = torch.empty_like(zq)
-        L.check(lib.idee_anomaly_l1_bwd(zq.data_ptr(), mask.data_ptr(), vq0.data_ptr(), N, V, T, H * W, Cc, out.data_ptr(),
-                                        g.data_ptr(), gzq.data_ptr(), L.stream()), "anomaly_l1_bwd")
+        L.run("anomaly_l1_bwd", lib.idee_anomaly_l1_bwd, zq.data_ptr(), mask.data_ptr(), vq0.data_ptr(), N, V, T, H * W, Cc, out.data_ptr(),
+                                        g.data_ptr(), gzq.data_ptr(), L.stream())
         return gzq, None, None
 
 
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step):
     lib = L.load()
-    L.check(lib.idee_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2, eps,
-                               weight_decay, step, L.stream()), "adam_step")
+    L.run("adam_step", lib.idee_adam_step, p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2, eps,
+                               weight_decay, step, L.stream())

@@ -1,0 +1,89 @@
+"""One-process-per-GPU training step for the IDEE hot path (replaces nn.DataParallel, train_synthetic.py:134-135,175-205).
+
+All 535 892 parameters live in ONE flat fp32 buffer (the modules' nn.Parameters are views of it, so state_dict /
+checkpoints are unchanged) and all gradients in a second flat buffer, so a step is
+
+    zero flat grad -> forward -> losses -> backward -> ONE NCCL all-reduce (average) of the flat gradient -> ONE fused Adam
+
+The batch is sharded over ranks; each rank evaluates the reference loss on its local shard and gradients are averaged,
+i.e. the result equals the mean of per-shard reference steps.  Batch statistics inside the
+loss (LFQ codebook entropy, BCE class weights, anomaly normaliser) are per-shard, as they are per-replica in the reference.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .models.losses import train_step_loss
+
+
+class Trainer:
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.003, lambda_anomaly=100.0,
+                 process_group=None, distributed=None):
+        self.model = model
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.lambda_anomaly = lambda_anomaly
+        self.group = process_group
+        self.distributed = dist.is_available() and dist.is_initialized() if distributed is None else distributed
+        self.world = dist.get_world_size(process_group) if self.distributed else 1
+        self.step_count = 0
+        self._flatten()
+        self.exp_avg = torch.zeros_like(self.flat_params)
+        self.exp_avg_sq = torch.zeros_like(self.flat_params)
+        if self.distributed and self.world > 1:
+            dist.broadcast(self.flat_params, src=0, group=self.group)   # same weights on every rank
+
+    @torch.no_grad()
+    def _flatten(self):
+        model = self.model
+        packs = list(model.encoder.packs()) + list(model.cls.packs())
+        in_pack = {id(p) for pk in packs for p in pk.params()}
+        rest = [p for p in model.parameters() if id(p) not in in_pack]
+        total = sum(pk.V * pk.P for pk in packs) + sum(p.numel() for p in rest)
+        dev = next(model.parameters()).device
+        flat = torch.empty(total, device=dev, dtype=torch.float32)
+        off = 0
+        for pk in packs:
+            n = pk.V * pk.P
+            pk.bind(flat[off:off + n].view(pk.V, pk.P))
+            off += n
+        for p in rest:
+            n = p.numel()
+            view = flat[off:off + n].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+            off += n
+        assert off == total == sum(p.numel() for p in model.parameters())
+        self.flat_params = flat
+        self.flat_grads = torch.zeros_like(flat)
+        base = flat.data_ptr()
+        for p in model.parameters():
+            o = (p.data_ptr() - base) // 4
+            p.grad = self.flat_grads[o:o + p.numel()].view(p.shape)
+
+    def _check_flat(self):
+        base, end = self.flat_params.data_ptr(), self.flat_params.data_ptr() + 4 * self.flat_params.numel()
+        for p in self.model.parameters():
+            if not (base <= p.data_ptr() < end) or p.grad is None:
+                raise RuntimeError("Trainer: a parameter left the flat buffer (module.to()/zero_grad(set_to_none=True) after "
+                                   "Trainer creation?); build the Trainer after moving the model")
+
+    def forward_backward(self, x, mask_extreme, mask_extreme_loss):
+        self.flat_grads.zero_()
+        total, out = train_step_loss(self.model, x, mask_extreme, mask_extreme_loss, self.lambda_anomaly)
+        total.backward()
+        return total, out
+
+    def optimizer_step(self):
+        if self.distributed and self.world > 1:
+            dist.all_reduce(self.flat_grads, op=dist.ReduceOp.AVG, group=self.group)
+        self.step_count += 1
+        ops.adam_step(self.flat_params, self.flat_grads, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1],
+                      self.eps, self.weight_decay, self.step_count)
+
+    def step(self, x, mask_extreme, mask_extreme_loss):
+        """forward + losses + backward + gradient all-reduce + Adam; returns (loss[1] tensor on device, outputs)."""
+        total, out = self.forward_backward(x, mask_extreme, mask_extreme_loss)
+        self.optimizer_step()
+        return total.detach(), out
