@@ -36,6 +36,8 @@ def parse_args():
     ap.add_argument("--impl", default="idee_b200", choices=["idee_b200", "reference"])
     ap.add_argument("--batch", type=int, default=8, help="samples per GPU per step")
     ap.add_argument("--hw", type=int, default=200)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
+                    help="bf16: tensor-core operands + fp32 accumulate for the GEMM-shaped kernels; fp32: exact CUDA-core path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     return ap.parse_args()
@@ -154,6 +156,8 @@ def op_flops(name, B, V, T, H, W):
         per_tok = 8192 if "(2, 4, 4)" in name else 6656
         return tok * per_tok * (2 if "bwd" in name else 1)
     if name.startswith("conv3d"):
+        if "[" not in name:
+            return None
         tag = name[name.index("[") + 1:-1]                        # e.g. "cls 96->96 T8"
         kind, ch, tt = tag.split()
         cin, cout = (int(c) for c in ch.split("->"))
@@ -190,6 +194,7 @@ def main():
     from oracle import idee_oracle as O            # only for the synthetic input factory and the cpu_baseline leg
 
     _lib.check(_lib.load().idee_check_device(), "check_device")
+    _lib.set_precision(args.precision)
     cfg = default_config()
     torch.manual_seed(0)
     model = VQ_model(cfg).to(dev).train()
@@ -276,7 +281,7 @@ def main():
                 roofline = {"kernel": k, "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                             "traffic": None, "avg_ms_per_launch": avg_ms, "flops_per_launch": fl, "share_of_step": t / tot,
                             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s (of fallback)",
-                            "note": "fp32 CUDA-core kernel measured against the dense bf16 tensor-core peak"}
+                            "note": "algorithmic FLOPs (2*MAC, no recompute/padding credit) against the dense bf16 tensor-core peak"}
                 break
 
     if rank == 0:
@@ -288,7 +293,7 @@ def main():
                                       f"({sec:.2f} s/step), {cpu_model_name()}"}
         whole_model_tf = value / n_gpus * FLOP_FWD_BWD_PER_SAMPLE / 1e12
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32",
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision,
                 "data": "synthetic", "config": workload_config(args, n_gpus), "impl": "idee_b200",
                 "e2e": {"value": n_gpus * B / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e},

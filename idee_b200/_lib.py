@@ -21,7 +21,7 @@ class SwinDesc(C.Structure):
 
 
 class ConvDesc(C.Structure):
-    _fields_ = [(n, c_int) for n in ("N", "V", "Vw", "Cin", "Cout", "Ti", "Hi", "Wi", "To", "Ho", "Wo", "proj", "relu")] + \
+    _fields_ = [(n, c_int) for n in ("N", "V", "Vw", "Cin", "Cout", "Ti", "Hi", "Wi", "To", "Ho", "Wo", "proj", "relu", "precision")] + \
                [(n, c_i64) for n in ("x_sn", "x_sv", "x_st", "x_sh", "x_sw", "x_sg")] + [("in_cpg", c_int)] + \
                [(n, c_i64) for n in ("y_sn", "y_sv", "y_st", "y_sh", "y_sw", "y_sg")] + [("out_cpg", c_int)]
 
@@ -37,8 +37,10 @@ _SIGS = {
     "idee_swin_block_fwd": (c_int, [C.POINTER(SwinDesc)] + [c_vp] * 6),
     "idee_swin_block_bwd_workspace_bytes": (c_sz, [C.POINTER(SwinDesc)]),
     "idee_swin_block_bwd": (c_int, [C.POINTER(SwinDesc)] + [c_vp] * 8 + [c_sz, c_vp]),
-    "idee_conv3d_fwd": (c_int, [C.POINTER(ConvDesc)] + [c_vp] * 5),
-    "idee_conv3d_dgrad": (c_int, [C.POINTER(ConvDesc)] + [c_vp] * 5),
+    "idee_conv3d_fwd_workspace_bytes": (c_sz, [C.POINTER(ConvDesc)]),
+    "idee_conv3d_fwd": (c_int, [C.POINTER(ConvDesc)] + [c_vp] * 5 + [c_sz, c_vp]),
+    "idee_conv3d_dgrad_workspace_bytes": (c_sz, [C.POINTER(ConvDesc)]),
+    "idee_conv3d_dgrad": (c_int, [C.POINTER(ConvDesc)] + [c_vp] * 5 + [c_sz, c_vp]),
     "idee_conv3d_wgrad_workspace_bytes": (c_sz, [C.POINTER(ConvDesc)]),
     "idee_conv3d_wgrad": (c_int, [C.POINTER(ConvDesc)] + [c_vp] * 5 + [c_sz, c_vp]),
     "idee_lfq_workspace_bytes": (c_sz, [c_i64]),
@@ -90,8 +92,22 @@ def check(rc: int, what: str = ""):
 
 
 # kernels launched by each C-ABI entry point (used for the gpu_launches figure of bench.py)
+# numeric policy of the GEMM-shaped kernels: "fp32" = exact CUDA-core path, "bf16" = bf16 tensor-core operands with fp32
+# accumulation (activations stay fp32 in HBM, the LFQ quantiser and all losses are always fp32)
+PRECISION = os.environ.get("IDEE_B200_PRECISION", "fp32")
+if PRECISION not in ("fp32", "bf16"):
+    raise ValueError("IDEE_B200_PRECISION must be fp32 or bf16")
+
+
+def set_precision(mode: str) -> None:
+    global PRECISION
+    if mode not in ("fp32", "bf16"):
+        raise ValueError("precision must be 'fp32' or 'bf16'")
+    PRECISION = mode
+
+
 LAUNCHES = {"embed_ln_fwd": 1, "embed_ln_bwd": 2, "swin_block_fwd": 1, "swin_block_bwd": 3, "conv3d_fwd": 1, "conv3d_dgrad": 1,
-            "conv3d_wgrad": 2, "lfq_fwd": 2, "lfq_fwd_eval": 1, "lfq_bwd": 2, "bce_loss_fwd": 2, "anomaly_l1_fwd": 2,
+            "conv3d_wgrad": 2, "conv3d_fwd_bf16": 2, "conv3d_dgrad_bf16": 3, "conv3d_wgrad_bf16": 2, "lfq_fwd": 2, "lfq_fwd_eval": 1, "lfq_bwd": 2, "bce_loss_fwd": 2, "anomaly_l1_fwd": 2,
             "anomaly_l1_bwd": 1, "adam_step": 1}
 
 

@@ -14,6 +14,15 @@
 #include "common.cuh"
 #include "idee_b200.h"
 
+// bf16 tensor-core path (conv_tc.cu)
+size_t conv_tc_fwd_workspace_bytes(const idee_conv_desc* d);
+size_t conv_tc_dgrad_workspace_bytes(const idee_conv_desc* d);
+size_t conv_tc_wgrad_workspace_bytes(const idee_conv_desc* d);
+int conv_tc_wgrad_splits(const idee_conv_desc* d);
+int conv_tc_fwd(const idee_conv_desc* d, const float* x, const float* w, const float* b, float* y, void* ws, cudaStream_t st);
+int conv_tc_dgrad(const idee_conv_desc* d, const float* gy, const float* w, const float* relu_src, float* gx, void* ws, cudaStream_t st);
+int conv_tc_wgrad_partials(const idee_conv_desc* d, const float* x, const float* gy, float* partials, cudaStream_t st);
+
 namespace {
 
 enum { CLS_FWD = 0, PROJ_FWD = 1, CLS_DGRAD = 2, PROJ_DGRAD = 3 };
@@ -338,8 +347,14 @@ int launch_gather(const ConvP& p, cudaStream_t st, const char* who) {
 
 }  // namespace
 
-extern "C" int idee_conv3d_fwd(const idee_conv_desc* d, const float* x, const float* w, const float* b, float* y, void* stream) {
+extern "C" size_t idee_conv3d_fwd_workspace_bytes(const idee_conv_desc* d) { return d->precision == 1 ? conv_tc_fwd_workspace_bytes(d) : 0; }
+extern "C" size_t idee_conv3d_dgrad_workspace_bytes(const idee_conv_desc* d) { return d->precision == 1 ? conv_tc_dgrad_workspace_bytes(d) : 0; }
+
+extern "C" int idee_conv3d_fwd(const idee_conv_desc* d, const float* x, const float* w, const float* b, float* y,
+                               void* workspace, size_t workspace_bytes, void* stream) {
     if (check_desc(d, "conv3d_fwd")) return 1;
+    IDEE_REQUIRE(workspace_bytes >= idee_conv3d_fwd_workspace_bytes(d), "conv3d_fwd: workspace too small");
+    if (d->precision == 1) return conv_tc_fwd(d, x, w, b, y, workspace, (cudaStream_t)stream);
     ConvP p{};
     fill_common(p, d);
     p.in = x; p.out = y; p.w = w; p.bias = b; p.relu_src = nullptr; p.relu = d->relu;
@@ -354,8 +369,11 @@ extern "C" int idee_conv3d_fwd(const idee_conv_desc* d, const float* x, const fl
 }
 
 // gx = conv^T(gy); if relu_src != NULL the result is multiplied by (relu_src > 0) (relu_src has gx's layout)
-extern "C" int idee_conv3d_dgrad(const idee_conv_desc* d, const float* gy, const float* w, const float* relu_src, float* gx, void* stream) {
+extern "C" int idee_conv3d_dgrad(const idee_conv_desc* d, const float* gy, const float* w, const float* relu_src, float* gx,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
     if (check_desc(d, "conv3d_dgrad")) return 1;
+    IDEE_REQUIRE(workspace_bytes >= idee_conv3d_dgrad_workspace_bytes(d), "conv3d_dgrad: workspace too small");
+    if (d->precision == 1) return conv_tc_dgrad(d, gy, w, relu_src, gx, workspace, (cudaStream_t)stream);
     ConvP p{};
     fill_common(p, d);
     p.in = gy; p.out = gx; p.w = w; p.bias = nullptr; p.relu_src = relu_src; p.relu = relu_src != nullptr;
@@ -370,6 +388,7 @@ extern "C" int idee_conv3d_dgrad(const idee_conv_desc* d, const float* gy, const
 }
 
 extern "C" size_t idee_conv3d_wgrad_workspace_bytes(const idee_conv_desc* d) {
+    if (d->precision == 1) return conv_tc_wgrad_workspace_bytes(d);
     const int n_ic = (d->Cin + 15) / 16, n_oc = (d->Cout + 15) / 16, NT = (d->proj ? 3 : 2) * 9;
     return sizeof(float) * (size_t)d->Vw * n_ic * n_oc * wgrad_splits(d) * (NT * 256 + 16);
 }
@@ -378,13 +397,24 @@ extern "C" int idee_conv3d_wgrad(const idee_conv_desc* d, const float* x, const 
                                  void* workspace, size_t workspace_bytes, void* stream) {
     if (check_desc(d, "conv3d_wgrad")) return 1;
     IDEE_REQUIRE(workspace_bytes >= idee_conv3d_wgrad_workspace_bytes(d), "conv3d_wgrad: workspace too small");
+    IDEE_REQUIRE(d->out_cpg * 16 >= d->Cout || d->Cout == 1, "conv3d_wgrad: grouped output layout is not supported");
+    if (d->precision == 1) {
+        cudaStream_t st = (cudaStream_t)stream;
+        if (conv_tc_wgrad_partials(d, x, gy, (float*)workspace, st)) return 2;
+        const int NT = (d->proj ? 3 : 2) * 9;
+        const int64_t nel = (int64_t)d->Cout * d->Cin * NT + d->Cout;
+        conv_wgrad_reduce_kernel<<<dim3((unsigned)((nel + 255) / 256), d->Vw), 256, 0, st>>>(
+            (const float*)workspace, gw, gb, d->Vw, d->Cin, d->Cout, NT, (d->Cin + 15) / 16, (d->Cout + 15) / 16, conv_tc_wgrad_splits(d),
+            (int64_t)d->Cin * d->Cout * NT, d->Cout);
+        IDEE_LAUNCH_CHECK("conv3d_wgrad_reduce");
+        return 0;
+    }
     WgradP p{};
     p.in = x; p.gout = gy; p.partials = (float*)workspace;
     p.N = d->N; p.V = d->V; p.Vw = d->Vw;
     p.Ti = d->Ti; p.Hi = d->Hi; p.Wi = d->Wi; p.To = d->To; p.Ho = d->Ho; p.Wo = d->Wo;
     p.in_sn = d->x_sn; p.in_sv = d->x_sv; p.in_st = d->x_st; p.in_sh = d->x_sh; p.in_sw = d->x_sw; p.in_sg = d->x_sg; p.in_cpg = d->in_cpg;
     p.go_sn = d->y_sn; p.go_sv = d->y_sv; p.go_st = d->y_st; p.go_sh = d->y_sh; p.go_sw = d->y_sw;
-    IDEE_REQUIRE(d->out_cpg * 16 >= d->Cout || d->Cout == 1, "conv3d_wgrad: grouped output layout is not supported");
     p.FCI = d->Cin; p.FCO = d->Cout; p.KT = d->proj ? 3 : 2; p.proj = d->proj;
     p.n_ic = (d->Cin + 15) / 16; p.n_oc = (d->Cout + 15) / 16; p.S = wgrad_splits(d);
     p.rows_per_set = (int64_t)d->N * (d->Vw == 1 ? d->V : 1) * d->To * d->Ho;

@@ -196,6 +196,7 @@ def _conv_desc(x_dims, x_strides, y_strides, Vw, Cin, Cout, proj, relu, in_cpg, 
     d.x_sn, d.x_sv, d.x_st, d.x_sh, d.x_sw = x_strides
     d.y_sn, d.y_sv, d.y_st, d.y_sh, d.y_sw = y_strides
     d.x_sg, d.y_sg, d.in_cpg, d.out_cpg = x_sg, y_sg, in_cpg, out_cpg
+    d.precision = 1 if L.PRECISION == "bf16" else 0
     return d
 
 
@@ -227,8 +228,10 @@ class Conv3dCL(torch.autograd.Function):
         d = _conv_desc((N, Vimg, Ti, Hi, Wi), (x.stride(0), x_sv, x.stride(2), x.stride(3), x.stride(4)),
                        (y.stride(0), y.stride(1), y.stride(2), y.stride(3), y.stride(4)), Vw, Cin, Cout, proj, relu,
                        in_cpg, max(Cout // 16, 1), x_sg, 0)
-        L.run("conv3d_fwd", lib.idee_conv3d_fwd, C.byref(d), x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), L.stream(),
-              tag=_conv_tag(d))
+        nws = lib.idee_conv3d_fwd_workspace_bytes(C.byref(d))
+        ws = L.workspace(nws, x.device)
+        L.run("conv3d_fwd_bf16" if d.precision else "conv3d_fwd", lib.idee_conv3d_fwd, C.byref(d), x.data_ptr(), w.data_ptr(),
+              b.data_ptr(), y.data_ptr(), ws.data_ptr(), nws, L.stream(), tag=_conv_tag(d))
         ctx.save_for_backward(x, w, y if relu else None)
         ctx.desc, ctx.relu, ctx.groups = d, relu, groups
         return y
@@ -245,15 +248,17 @@ class Conv3dCL(torch.autograd.Function):
         gb = torch.empty(w.shape[0], w.shape[1], device=w.device, dtype=torch.float32)
         nws = lib.idee_conv3d_wgrad_workspace_bytes(C.byref(d))
         ws = L.workspace(nws, x.device)
-        L.run("conv3d_wgrad", lib.idee_conv3d_wgrad, C.byref(d), x.data_ptr(), gy.data_ptr(), gw.data_ptr(), gb.data_ptr(), ws.data_ptr(), nws,
+        L.run("conv3d_wgrad_bf16" if d.precision else "conv3d_wgrad", lib.idee_conv3d_wgrad, C.byref(d), x.data_ptr(), gy.data_ptr(), gw.data_ptr(), gb.data_ptr(), ws.data_ptr(), nws,
                                       L.stream(), tag=_conv_tag(d))
         gx = None
         if ctx.needs_input_grad[0]:
             gx = torch.empty_strided(x.shape, x.stride(), device=x.device, dtype=torch.float32) if _dense(x) else None
             if gx is None:
                 raise RuntimeError("conv3d_dgrad: input must be a dense channel-last tensor")
-            L.run("conv3d_dgrad", lib.idee_conv3d_dgrad, C.byref(d), gy.data_ptr(), w.data_ptr(), None, gx.data_ptr(), L.stream(),
-                  tag=_conv_tag(d))
+            nws = lib.idee_conv3d_dgrad_workspace_bytes(C.byref(d))
+            ws = L.workspace(nws, x.device)
+            L.run("conv3d_dgrad_bf16" if d.precision else "conv3d_dgrad", lib.idee_conv3d_dgrad, C.byref(d), gy.data_ptr(),
+                  w.data_ptr(), None, gx.data_ptr(), ws.data_ptr(), nws, L.stream(), tag=_conv_tag(d))
         return gx, gw, gb, None, None, None
 
 

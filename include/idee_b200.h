@@ -79,14 +79,19 @@ typedef struct {
     int Ti, Hi, Wi, To, Ho, Wo;
     int proj;               /* 1: 3x3x3 replicate, 0: (2,3,3)/(2,1,1) zero-pad */
     int relu;               /* forward: fuse ReLU into the epilogue */
+    int precision;          /* 0: fp32 CUDA-core exact path; 1: bf16 tensor-core operands, fp32 accumulate (fp32 I/O either way) */
     int64_t x_sn, x_sv, x_st, x_sh, x_sw, x_sg; int in_cpg;
     int64_t y_sn, y_sv, y_st, y_sh, y_sw, y_sg; int out_cpg;
 } idee_conv_desc;
 
-int idee_conv3d_fwd(const idee_conv_desc* d, const float* x, const float* w, const float* b, float* y, void* stream);
+size_t idee_conv3d_fwd_workspace_bytes(const idee_conv_desc* d);
+int idee_conv3d_fwd(const idee_conv_desc* d, const float* x, const float* w, const float* b, float* y,
+                    void* workspace, size_t workspace_bytes, void* stream);
 /* gx = conv^T(gy); when relu_src != NULL (same layout as gx) gx is multiplied by (relu_src > 0): the ReLU that
  * produced this conv's input is folded into the data gradient */
-int idee_conv3d_dgrad(const idee_conv_desc* d, const float* gy, const float* w, const float* relu_src, float* gx, void* stream);
+size_t idee_conv3d_dgrad_workspace_bytes(const idee_conv_desc* d);
+int idee_conv3d_dgrad(const idee_conv_desc* d, const float* gy, const float* w, const float* relu_src, float* gx,
+                      void* workspace, size_t workspace_bytes, void* stream);
 size_t idee_conv3d_wgrad_workspace_bytes(const idee_conv_desc* d);
 int idee_conv3d_wgrad(const idee_conv_desc* d, const float* x, const float* gy, float* gw, float* gb,
                       void* workspace, size_t workspace_bytes, void* stream);

@@ -22,7 +22,12 @@ def rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
 
 
+BF16 = os.environ.get("IDEE_B200_PRECISION", "fp32") == "bf16"
+
+
 def report(name, err, tol=1e-4):
+    if BF16:
+        tol = 2e-2
     print(f"  {'OK  ' if err < tol else 'FAIL'} {name:58s} rel_err={err:.3e}", flush=True)
 
 
@@ -131,6 +136,10 @@ def _conv_case(proj, Cin, Cout, V, Vw, dims, relu, groups=1, N=2, seed=0):
     got = ops.conv3d_cl(xc, wc, bc, proj, relu, groups)
     tag = f"conv proj={int(proj)} {Cin}->{Cout} V={V} Vw={Vw} g={groups} dims={dims} relu={int(relu)}"
     report(tag + " fwd", rel(got, want))
+    if BF16 and relu:
+        # bf16 rounding flips the ReLU mask of near-zero pre-activations, which is not a kernel error: check the
+        # backward kernels on the linear conv instead
+        return _conv_case(proj, Cin, Cout, V, Vw, dims, False, groups, N, seed)
     (got * g.cuda()).sum().backward()
     report(tag + " dgrad", rel(xc.grad, x.grad), 5e-4)
     report(tag + " wgrad", rel(wc.grad, w.grad), 5e-4)
@@ -212,8 +221,12 @@ def stage_model():
         model = build_model(cfg, sd)
         total, out = train_step_loss(model, ins["x"].cuda(), ins["mask_extreme"].cuda(), ins["mask_extreme_loss"].cuda())
         total.backward()
-        frac, ties = mask_agreement(out["anomaly"], train["anomaly"], lfq_scalar(sd, train["z_enc"]), 1e-4)
-        print(f" [{name}] mask agreement {frac:.5f} ties_ok={ties}")
+        s_ref = lfq_scalar(sd, train["z_enc"])
+        tie = 2e-2 * float(s_ref.abs().max()) if BF16 else 1e-4
+        frac, ties = mask_agreement(out["anomaly"], train["anomaly"], s_ref, tie)
+        print(f" [{name}] mask agreement {frac:.5f} ties_ok={ties} (tie threshold {tie:.2e})")
+        with torch.no_grad():
+            report(f"{name} z_enc", rel(model.encoder(ins["x"].cuda()), train["z_enc"]))
         report(f"{name} pred", rel(out["pred"], train["pred"]))
         report(f"{name} pred_y", rel(torch.stack(list(out["pred_y"])), train["pred_y"]))
         report(f"{name} z_q", rel(out["z_q"], train["z_q"]))
