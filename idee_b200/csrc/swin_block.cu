@@ -15,6 +15,8 @@
 //   swin_attn_bwd : (x, g_y)    -> g_x,  d{qkv,proj,rpb}
 // Weight gradients are accumulated in registers across the CTA's persistent loop via a shared-memory
 // transposed outer-product phase, written as per-CTA partials and summed by a deterministic second stage.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "idee_b200.h"
 
@@ -601,6 +603,8 @@ __global__ void swin_grad_finalize_kernel(const float* __restrict__ part_attn, c
     gparams[(int64_t)v * pstride + e] = acc;
 }
 
+#include "swin_tc.cuh"
+
 // ---- host side -----------------------------------------------------------------------------------------
 int make_geom(Geom& g, const idee_swin_desc* d, const char* who) {
     IDEE_REQUIRE(d->C == C && d->heads == NH && d->hidden == HID,
@@ -635,6 +639,16 @@ template <int WD, int WH, int WW>
 int launch_fwd(const idee_swin_desc* d, const Geom& g, const float* x, float* out, float* ymid, const float* params,
                const int* rel_index, cudaStream_t st) {
     constexpr int G = WD * WH * WW;
+    if (d->precision == 1) {
+        if (G < 8) { idee_set_error("swin_block_fwd(bf16): windows with fewer than 8 tokens are only built for the fp32 path"); return 1; }
+        int per_v = (g.n_wg + TCW - 1) / TCW;
+        const int cap = (idee_num_sms() * 6 + d->V - 1) / d->V;
+        if (per_v > cap) per_v = cap;
+        if (per_v < 1) per_v = 1;
+        swin_fwd_tc_kernel<WD, WH, WW><<<dim3(per_v, d->V), TCW * 32, 0, st>>>(x, out, ymid, params, d->param_stride, rel_index, g);
+        IDEE_LAUNCH_CHECK("swin_block_fwd(bf16)");
+        return 0;
+    }
     auto kern = swin_block_fwd_kernel<WD, WH, WW, FWD_WARPS>;
     const size_t smem = fwd_smem_bytes<G>(FWD_WARPS);
     IDEE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "swin_block_fwd");
@@ -648,7 +662,7 @@ int launch_fwd(const idee_swin_desc* d, const Geom& g, const float* x, float* ou
 }
 
 int bwd_ctas_per_var(int V) {
-    int per_v = (idee_num_sms() * 2 + V - 1) / V;
+    int per_v = (idee_num_sms() * 3 + V - 1) / V;
     return per_v < 1 ? 1 : per_v;
 }
 
@@ -663,6 +677,18 @@ int launch_bwd(const idee_swin_desc* d, const Geom& g, const float* x, const flo
     float* part_attn = ws;
     float* part_mlp = ws + (size_t)d->V * per_v * APS;
     const int64_t thw = (int64_t)d->T * d->H * d->W;
+    if (d->precision == 1) {
+        if (G < 8) { idee_set_error("swin_block_bwd(bf16): windows with fewer than 8 tokens are only built for the fp32 path"); return 1; }
+        swin_mlp_bwd_tc_kernel<<<dim3(per_v, d->V), TCW * 32, 0, st>>>(ymid, gout, gx, params, d->param_stride, g.tbl, part_mlp, d->N, d->V, thw);
+        IDEE_LAUNCH_CHECK("swin_mlp_bwd(bf16)");
+        swin_attn_bwd_tc_kernel<WD, WH, WW><<<dim3(per_v, d->V), TCW * 32, 0, st>>>(x, gx, gx, params, d->param_stride, rel_index, part_attn, g);
+        IDEE_LAUNCH_CHECK("swin_attn_bwd(bf16)");
+        const POff po2(g.tbl);
+        swin_grad_finalize_kernel<G><<<dim3((po2.total + 127) / 128, d->V), 128, 0, st>>>(part_attn, part_mlp, per_v, per_v, rel_index,
+                                                                                        gparams, d->param_stride, g.tbl);
+        IDEE_LAUNCH_CHECK("swin_grad_finalize");
+        return 0;
+    }
     IDEE_CUDA(cudaFuncSetAttribute(swin_mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MlpSmem)), "swin_mlp_bwd");
     // g_y is written into gx, then the attention half updates it in place
     swin_mlp_bwd_kernel<<<dim3(per_v, d->V), MLP_TOK, sizeof(MlpSmem), st>>>(ymid, gout, gx, params, d->param_stride, g.tbl,

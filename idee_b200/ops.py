@@ -134,6 +134,7 @@ def _swin_desc(x, window, shift, rpb_rows, scale, pack: ParamPack, heads, hidden
     d.wd, d.wh, d.ww = window
     d.st, d.sh, d.sw = shift
     d.rpb_rows, d.scale, d.param_stride = rpb_rows, scale, pack.P
+    d.precision = 1 if L.PRECISION == "bf16" else 0
     return d
 
 

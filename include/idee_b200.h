@@ -54,6 +54,7 @@ typedef struct {
     int rpb_rows;           /* rows of the bias table, (2Wd-1)(2Wh-1)(2Ww-1) of the CONFIGURED window */
     float scale;            /* qk scale, head_dim^-0.5 unless overridden */
     int64_t param_stride;   /* floats between consecutive variables' packed parameter blocks */
+    int precision;          /* 0: fp32 CUDA-core exact path; 1: bf16 tensor-core operands, fp32 accumulate / softmax / LayerNorm */
 } idee_swin_desc;
 
 int idee_swin_block_packed_floats(int rpb_rows);
