@@ -79,6 +79,18 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
     return cdf + x * pdf;
 }
 
+// bf16 path: Phi(x) and phi(x) from ONE exp and ONE reciprocal; erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7),
+// exp(-z^2) with z = x/sqrt(2) is also the Gaussian density factor, so GELU and its derivative share everything.
+__device__ __forceinline__ void gelu_fast(float x, float& y, float& dy) {
+    const float az = fabsf(x) * 0.70710678118654752440f;
+    const float t = __fdividef(1.f, 1.f + 0.3275911f * az);
+    const float E = __expf(-az * az);
+    const float poly = ((((1.061405429f * t - 1.453152027f) * t + 1.421413741f) * t - 0.284496736f) * t + 0.254829592f) * t;
+    const float cdf = 0.5f * (1.f + copysignf(1.f - poly * E, x));
+    y = x * cdf;
+    dy = cdf + x * E * 0.39894228040143267794f;
+}
+
 // LayerNorm over 16 channels, eps 1e-5, no affine (Swin_3D.py:214,220,469): returns rstd, writes xn
 __device__ __forceinline__ float ln16(const float* x, float* xn) {
     float mu = 0.f;

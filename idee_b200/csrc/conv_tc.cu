@@ -130,30 +130,49 @@ conv_tc_kernel(P p) {
     // ---- halo: fp32 HBM -> bf16 smem (zero / clamp handled here, so the MMA loop is branch-free) ----
     const float* in_img = p.in + n * p.in_sn + v * p.in_sv;
     const int V4 = CI / 4;
-    for (int e = tid; e < KTIN * HH * HW_ * V4; e += 128) {
-        const int c4 = e % V4;
-        int r = e / V4;
-        const int ww = r % HW_; r /= HW_;
-        const int hh = r % HH, kt = r / HH;
-        int ti, hi = h0 + hh - 1, wi = w0 + ww - 1;
-        bool ok = true;
-        if (MODE == CLS_FWD) { ti = 2 * t + kt; ok = hi >= 0 && hi < p.Hi && wi >= 0 && wi < p.Wi; }
-        else if (MODE == PROJ_FWD) { ti = min(max(t + kt - 1, 0), p.Ti - 1); hi = min(max(hi, 0), p.Hi - 1); wi = min(max(wi, 0), p.Wi - 1); }
-        else if (MODE == CLS_DGRAD) { ti = t >> 1; ok = ti < p.Ti && hi >= 0 && hi < p.Hi && wi >= 0 && wi < p.Wi; }
-        else { ti = t + kt - 2; hi -= 1; wi -= 1; ok = ti >= 0 && ti < p.Ti && hi >= 0 && hi < p.Hi && wi >= 0 && wi < p.Wi; }
-        float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok) {
-            const int ch = c4 * 4, chunk = ch / 16;
-            const float* src = in_img + ti * p.in_st + hi * p.in_sh + wi * p.in_sw + (chunk / p.in_cpg) * p.in_sg + (chunk % p.in_cpg) * 16 + (ch % 16);
-            if (p.CIr >= CI) f = ldg4(src);
-            else {
-                if (ch < p.CIr) f.x = __ldg(src);
-                if (ch + 1 < p.CIr) f.y = __ldg(src + 1);
-                if (ch + 2 < p.CIr) f.z = __ldg(src + 2);
-                if (ch + 3 < p.CIr) f.w = __ldg(src + 3);
+    const int halo_total = KTIN * HH * HW_ * V4;
+    // 4 independent loads in flight per thread before any conversion/store (the loop is latency-bound otherwise)
+    for (int e0 = tid; e0 < halo_total; e0 += 4 * 128) {
+        const float* src[4];
+        int dst[4], chs[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * 128;
+            src[u] = nullptr; dst[u] = -1; chs[u] = 0;
+            if (e < halo_total) {
+                const int c4 = e % V4;
+                int r = e / V4;
+                const int ww = r % HW_; r /= HW_;
+                const int hh = r % HH, kt = r / HH;
+                int ti, hi = h0 + hh - 1, wi = w0 + ww - 1;
+                bool ok = true;
+                if (MODE == CLS_FWD) { ti = 2 * t + kt; ok = hi >= 0 && hi < p.Hi && wi >= 0 && wi < p.Wi; }
+                else if (MODE == PROJ_FWD) { ti = min(max(t + kt - 1, 0), p.Ti - 1); hi = min(max(hi, 0), p.Hi - 1); wi = min(max(wi, 0), p.Wi - 1); }
+                else if (MODE == CLS_DGRAD) { ti = t >> 1; ok = ti < p.Ti && hi >= 0 && hi < p.Hi && wi >= 0 && wi < p.Wi; }
+                else { ti = t + kt - 2; hi -= 1; wi -= 1; ok = ti >= 0 && ti < p.Ti && hi >= 0 && hi < p.Hi && wi >= 0 && wi < p.Wi; }
+                const int ch = c4 * 4, chunk = ch / 16;
+                dst[u] = ((kt * HH + hh) * HW_ + ww) * CP + ch;
+                chs[u] = ch;
+                if (ok) src[u] = in_img + ti * p.in_st + hi * p.in_sh + wi * p.in_sw + (chunk / p.in_cpg) * p.in_sg + (chunk % p.in_cpg) * 16 + (ch % 16);
             }
         }
-        *reinterpret_cast<uint2*>(halo + ((size_t)(kt * HH + hh) * HW_ + ww) * CP + c4 * 4) = make_uint2(pack_bf16(f.x, f.y), pack_bf16(f.z, f.w));
+        float4 f[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            f[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (src[u]) {
+                if (p.CIr >= CI) f[u] = ldg4(src[u]);
+                else {
+                    if (chs[u] < p.CIr) f[u].x = __ldg(src[u]);
+                    if (chs[u] + 1 < p.CIr) f[u].y = __ldg(src[u] + 1);
+                    if (chs[u] + 2 < p.CIr) f[u].z = __ldg(src[u] + 2);
+                    if (chs[u] + 3 < p.CIr) f[u].w = __ldg(src[u] + 3);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (dst[u] >= 0) *reinterpret_cast<uint2*>(halo + dst[u]) = make_uint2(pack_bf16(f[u].x, f[u].y), pack_bf16(f[u].z, f[u].w));
     }
     float acc[2][NTL][4];
 #pragma unroll
@@ -306,40 +325,67 @@ wgrad_tc_kernel(WP p) {
     const int b_pix = (lane & 7) + ((lane >> 3) & 1) * 8, b_coff = (lane >> 4) * 8;     // B (trans) lane address
     const int64_t coff = (ic / p.in_cpg) * p.in_sg + (ic % p.in_cpg) * 16;
     for (int64_t tile = t_begin; tile < t_end; ++tile) {
-        int64_t r = tile;
+        int64_t r = tile;                          // t fastest: consecutive tiles of a CTA share input t-slices (L1/L2 hits)
+        const int t = (int)(r % p.To); r /= p.To;
         const int tw_ = (int)(r % p.tiles_w); r /= p.tiles_w;
-        const int th_ = (int)(r % p.tiles_h); r /= p.tiles_h;
-        const int t = (int)(r % p.To);
-        const int64_t img = r / p.To;
+        const int th_ = (int)(r % p.tiles_h);
+        const int64_t img = r / p.tiles_h;
         const int n = (int)(img / imgs_per_n), v = p.Vw == 1 ? (int)(img % imgs_per_n) : wset;
         const int h0 = th_ * TH, w0 = tw_ * TW;
         __syncthreads();
         const float* in_img = p.in + n * p.in_sn + v * p.in_sv + coff;
-        for (int e = tid; e < KTIN * HH * HW_ * 4; e += 128) {
-            const int c4 = e & 3;
-            int q = e >> 2;
-            const int ww = q % HW_; q /= HW_;
-            const int hh = q % HH, kt = q / HH;
-            int ti, hi = h0 + hh - 1, wi = w0 + ww - 1;
-            bool ok = true;
-            if (p.proj) { ti = min(max(t + kt - 1, 0), p.Ti - 1); hi = min(max(hi, 0), p.Hi - 1); wi = min(max(wi, 0), p.Wi - 1); }
-            else { ti = 2 * t + kt; ok = hi >= 0 && hi < p.Hi && wi >= 0 && wi < p.Wi; }
-            float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok) f = ldg4(in_img + ti * p.in_st + hi * p.in_sh + wi * p.in_sw + c4 * 4);
-            *reinterpret_cast<uint2*>(tileA + ((size_t)(kt * HH + hh) * HW_ + ww) * CPA + c4 * 4) = make_uint2(pack_bf16(f.x, f.y), pack_bf16(f.z, f.w));
+        constexpr int A_TOTAL = KTIN * HH * HW_ * 4;
+        for (int e0 = tid; e0 < A_TOTAL; e0 += 4 * 128) {
+            const float* src[4];
+            int dst[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * 128;
+                src[u] = nullptr; dst[u] = -1;
+                if (e < A_TOTAL) {
+                    const int c4 = e & 3;
+                    int q = e >> 2;
+                    const int ww = q % HW_; q /= HW_;
+                    const int hh = q % HH, kt = q / HH;
+                    int ti, hi = h0 + hh - 1, wi = w0 + ww - 1;
+                    bool ok = true;
+                    if (p.proj) { ti = min(max(t + kt - 1, 0), p.Ti - 1); hi = min(max(hi, 0), p.Hi - 1); wi = min(max(wi, 0), p.Wi - 1); }
+                    else { ti = 2 * t + kt; ok = hi >= 0 && hi < p.Hi && wi >= 0 && wi < p.Wi; }
+                    dst[u] = ((kt * HH + hh) * HW_ + ww) * CPA + c4 * 4;
+                    if (ok) src[u] = in_img + ti * p.in_st + hi * p.in_sh + wi * p.in_sw + c4 * 4;
+                }
+            }
+            float4 f[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) f[u] = src[u] ? ldg4(src[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (dst[u] >= 0) *reinterpret_cast<uint2*>(tileA + dst[u]) = make_uint2(pack_bf16(f[u].x, f[u].y), pack_bf16(f[u].z, f[u].w));
         }
         const float* go_img = p.gout + n * p.go_sn + v * p.go_sv + t * p.go_st;
-        for (int e = tid; e < TH * TW * (NC / 4); e += 128) {
-            const int c4 = e % (NC / 4), pix = e / (NC / 4);
-            const int h = h0 + pix / TW, w = w0 + pix % TW;
-            const int co = occ * NC + c4 * 4;
-            float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (h < p.Ho && w < p.Wo) {
-                const float* g = go_img + h * p.go_sh + w * p.go_sw + co;
-                if (co + 3 < p.FCO) f = ldg4(g);
-                else { if (co < p.FCO) f.x = __ldg(g); if (co + 1 < p.FCO) f.y = __ldg(g + 1); if (co + 2 < p.FCO) f.z = __ldg(g + 2); }
+        constexpr int G_TOTAL = TH * TW * (NC / 4);
+        for (int e0 = tid; e0 < G_TOTAL; e0 += 4 * 128) {
+            float4 f[4];
+            int dst[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * 128;
+                f[u] = make_float4(0.f, 0.f, 0.f, 0.f); dst[u] = -1;
+                if (e < G_TOTAL) {
+                    const int c4 = e % (NC / 4), pix = e / (NC / 4);
+                    const int h = h0 + pix / TW, w = w0 + pix % TW;
+                    const int co = occ * NC + c4 * 4;
+                    dst[u] = pix * CPG + c4 * 4;
+                    if (h < p.Ho && w < p.Wo) {
+                        const float* g = go_img + h * p.go_sh + w * p.go_sw + co;
+                        if (co + 3 < p.FCO) f[u] = ldg4(g);
+                        else { if (co < p.FCO) f[u].x = __ldg(g); if (co + 1 < p.FCO) f[u].y = __ldg(g + 1); if (co + 2 < p.FCO) f[u].z = __ldg(g + 2); }
+                    }
+                }
             }
-            *reinterpret_cast<uint2*>(tileG + (size_t)pix * CPG + c4 * 4) = make_uint2(pack_bf16(f.x, f.y), pack_bf16(f.z, f.w));
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (dst[u] >= 0) *reinterpret_cast<uint2*>(tileG + dst[u]) = make_uint2(pack_bf16(f[u].x, f[u].y), pack_bf16(f[u].z, f[u].w));
         }
         __syncthreads();
 #pragma unroll

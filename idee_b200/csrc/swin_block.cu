@@ -681,7 +681,9 @@ int launch_bwd(const idee_swin_desc* d, const Geom& g, const float* x, const flo
         if (G < 8) { idee_set_error("swin_block_bwd(bf16): windows with fewer than 8 tokens are only built for the fp32 path"); return 1; }
         swin_mlp_bwd_tc_kernel<<<dim3(per_v, d->V), TCW * 32, 0, st>>>(ymid, gout, gx, params, d->param_stride, g.tbl, part_mlp, d->N, d->V, thw);
         IDEE_LAUNCH_CHECK("swin_mlp_bwd(bf16)");
-        swin_attn_bwd_tc_kernel<WD, WH, WW><<<dim3(per_v, d->V), TCW * 32, 0, st>>>(x, gx, gx, params, d->param_stride, rel_index, part_attn, g);
+        const size_t dyn = sizeof(float) * TCW * NH * G * dbs(G);
+        IDEE_CUDA(cudaFuncSetAttribute(swin_attn_bwd_tc_kernel<WD, WH, WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn), "swin_attn_bwd(bf16)");
+        swin_attn_bwd_tc_kernel<WD, WH, WW><<<dim3(per_v, d->V), TCW * 32, dyn, st>>>(x, gx, gx, params, d->param_stride, rel_index, part_attn, g);
         IDEE_LAUNCH_CHECK("swin_attn_bwd(bf16)");
         const POff po2(g.tbl);
         swin_grad_finalize_kernel<G><<<dim3((po2.total + 127) / 128, d->V), 128, 0, st>>>(part_attn, part_mlp, per_v, per_v, rel_index,

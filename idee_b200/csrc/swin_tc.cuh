@@ -191,7 +191,7 @@ struct AttnTC {
 #pragma unroll
             for (int nj = 0; nj < 4; ++nj) {
                 if (tile_needed(r, nj)) {
-                    const float e0 = expf(p[mi][nj][2 * hf] - mx), e1 = expf(p[mi][nj][2 * hf + 1] - mx);
+                    const float e0 = __expf(p[mi][nj][2 * hf] - mx), e1 = __expf(p[mi][nj][2 * hf + 1] - mx);
                     p[mi][nj][2 * hf] = e0; p[mi][nj][2 * hf + 1] = e1; sum += e0 + e1;
                 } else { p[mi][nj][2 * hf] = 0.f; p[mi][nj][2 * hf + 1] = 0.f; }
             }
@@ -325,7 +325,7 @@ swin_fwd_tc_kernel(const float* __restrict__ x, float* __restrict__ out, float* 
 #pragma unroll
             for (int r = 0; r < 4; ++r)
 #pragma unroll
-                for (int qd = 0; qd < 4; ++qd) h[r][qd] = gelu_erf(h[r][qd]);
+                for (int qd = 0; qd < 4; ++qd) { float dy; gelu_fast(h[r][qd], h[r][qd], dy); }
             gemm16(acc, h, wf + (16 + 2 * kk) * 32, lane);
         }
         store_tile(out, acc, tr, c0);
@@ -410,8 +410,10 @@ swin_mlp_bwd_tc_kernel(const float* __restrict__ y, const float* __restrict__ go
             for (int r = 0; r < 4; ++r)
 #pragma unroll
                 for (int qd = 0; qd < 4; ++qd) {
-                    hid[r][qd] = tr.valid[r] ? gelu_erf(pre[r][qd]) : 0.f;
-                    dh[r][qd] = tr.valid[r] ? dh[r][qd] * gelu_erf_grad(pre[r][qd]) : 0.f;   // dPre
+                    float hv, dg;
+                    gelu_fast(pre[r][qd], hv, dg);
+                    hid[r][qd] = tr.valid[r] ? hv : 0.f;
+                    dh[r][qd] = tr.valid[r] ? dh[r][qd] * dg : 0.f;   // dPre
                     ab1[kk][qd] += dh[r][qd];
                 }
             gemm16(dyn, dh, wf + (16 + 2 * kk) * 32, lane);      // dYn += dPre W1[chunk]
@@ -467,6 +469,8 @@ swin_mlp_bwd_tc_kernel(const float* __restrict__ y, const float* __restrict__ go
 // =====================================================================================================
 // fragment table: qkv^T 6 | proj "N" (k = c, n = e) 2 | qkv "N" (k = o in 3 k-steps, n = c 2 n-tiles) 6
 constexpr int AB_FRAGS = 14;
+// row stride of the warp-private bias-gradient table: conflict-free 8-byte read-modify-write per half warp
+__host__ __device__ constexpr int dbs(int G) { return G == 8 ? 8 : G + 8; }
 
 template <int WD, int WH, int WW>
 __global__ void __launch_bounds__(TCW * 32)
@@ -475,10 +479,12 @@ swin_attn_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ g
                         float* __restrict__ partials, Geom g) {
     constexpr int G = WD * WH * WW;
     constexpr int PART = ATT_PART_W + NH * G * G;
+    constexpr int DBS = dbs(G), DBW = NH * G * DBS;           // per-warp bias-gradient table
     __shared__ __align__(16) uint2 wf[AB_FRAGS * 32];
     __shared__ __align__(16) float bq_s[3 * C];
     __shared__ __align__(16) float Bn[bsz(G)];
-    __shared__ float red[PART];
+    __shared__ float red[ATT_PART_W];
+    extern __shared__ __align__(16) float dBw_all[];          // [TCW][DBW]
     const int v = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* P = params + (int64_t)v * pstride;
     const POff po(g.tbl);
@@ -488,12 +494,13 @@ swin_attn_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ g
         else pack_fragN(wf + f * 32, P + po.qkv_w, C, 16 * ((f - 8) / 2), 8 * ((f - 8) % 2), lane);
     }
     for (int e = tid; e < 3 * C; e += blockDim.x) bq_s[e] = P[po.qkv_b + e];
-    for (int e = tid; e < PART; e += blockDim.x) red[e] = 0.f;
+    for (int e = tid; e < ATT_PART_W; e += blockDim.x) red[e] = 0.f;
+    for (int e = tid; e < TCW * DBW; e += blockDim.x) dBw_all[e] = 0.f;
     stage_bias_n<G>(Bn, P, rel_index);
     __syncthreads();
     const int gq = lane / 4, c0 = 2 * (lane % 4);
     const bool masked = g.masked != 0;
-    float* dB = red + ATT_PART_W;
+    float* dB = dBw_all + warp * DBW;
 
     // persistent accumulators: dWqkv[o][c] 3 m-tiles x 2 n-tiles ; dWproj[c][e] 1 x 2 ; biases per-lane column sums
     float aWq[3][2][4], aWp[2][4], abq[3][4], abp[4];
@@ -553,15 +560,18 @@ swin_attn_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ g
                             for (int b = 0; b < 2; ++b) ds[mi][nj][2 * hf + b] = p[mi][nj][2 * hf + b] * (ds[mi][nj][2 * hf + b] - Dr[2 * mi + hf]);
                     }
                 }
-            // relative-position-bias gradient: dB[h][i_local][j_local] += dS (warp-shared smem, atomics)
+            // relative-position-bias gradient: dB[h][i_local][j_local] += dS.  The table is private to the warp and every
+            // (i_local, j_local) pair is owned by exactly one lane, so a plain 8-byte read-modify-write is race-free.
 #pragma unroll
             for (int r = 0; r < 4; ++r)
 #pragma unroll
                 for (int nj = 0; nj < 4; ++nj)
                     if (AttnTC<G>::tile_needed(r, nj)) {
                         const int il = (gq + 8 * r) % G, jl = (8 * nj + c0) % G;
-                        atomicAdd(&dB[(h * G + il) * G + jl], ds[r / 2][nj][2 * (r % 2)]);
-                        atomicAdd(&dB[(h * G + il) * G + jl + 1], ds[r / 2][nj][2 * (r % 2) + 1]);
+                        float2* pd = reinterpret_cast<float2*>(&dB[(h * G + il) * DBS + jl]);
+                        float2 acc2 = *pd;
+                        acc2.x += ds[r / 2][nj][2 * (r % 2)]; acc2.y += ds[r / 2][nj][2 * (r % 2) + 1];
+                        *pd = acc2;
                     }
             // packed 8x8 blocks of dS and P: blk[ib][jb]
             uint32_t dsb[4][4], pb[4][4];
@@ -663,5 +673,12 @@ swin_attn_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ g
     }
     __syncthreads();
     float* part = partials + ((int64_t)v * gridDim.x + blockIdx.x) * PART;
-    for (int e = tid; e < PART; e += blockDim.x) part[e] = red[e];
+    for (int e = tid; e < ATT_PART_W; e += blockDim.x) part[e] = red[e];
+    for (int e = tid; e < NH * G * G; e += blockDim.x) {
+        const int hi = e / G, jl = e % G;     // hi = h * G + i_local
+        float sum = 0.f;
+#pragma unroll
+        for (int w = 0; w < TCW; ++w) sum += dBw_all[w * DBW + hi * DBS + jl];
+        part[ATT_PART_W + e] = sum;
+    }
 }
