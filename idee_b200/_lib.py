@@ -46,7 +46,8 @@ _SIGS = {
     "idee_lfq_workspace_bytes": (c_sz, [c_i64]),
     "idee_lfq_fwd": (c_int, [c_vp] * 8 + [c_i64, c_int, c_int, c_int] + [c_f32] * 4 + [c_vp, c_sz, c_vp]),
     "idee_lfq_bwd": (c_int, [c_vp] * 9 + [c_i64] + [c_f32] * 4 + [c_vp, c_sz, c_vp]),
-    "idee_bce_loss_fwd": (c_int, [c_vp, c_i64, c_i64, c_int, c_int, c_i64] + [c_vp] * 5),
+    "idee_bce_loss_workspace_bytes": (c_sz, [c_int]),
+    "idee_bce_loss_fwd": (c_int, [c_vp, c_i64, c_i64, c_int, c_int, c_i64] + [c_vp] * 5 + [c_sz, c_vp]),
     "idee_anomaly_l1_workspace_bytes": (c_sz, [c_i64]),
     "idee_anomaly_l1_fwd": (c_int, [c_vp] * 3 + [c_int] * 3 + [c_i64, c_int, c_vp, c_vp, c_sz, c_vp]),
     "idee_anomaly_l1_bwd": (c_int, [c_vp] * 3 + [c_int] * 3 + [c_i64, c_int] + [c_vp] * 4),
@@ -107,7 +108,7 @@ def set_precision(mode: str) -> None:
 
 
 LAUNCHES = {"embed_ln_fwd": 1, "embed_ln_bwd": 2, "swin_block_fwd": 1, "swin_block_bwd": 3, "conv3d_fwd": 1, "conv3d_dgrad": 1,
-            "conv3d_wgrad": 2, "conv3d_fwd_bf16": 2, "conv3d_dgrad_bf16": 3, "conv3d_wgrad_bf16": 2, "lfq_fwd": 2, "lfq_fwd_eval": 1, "lfq_bwd": 2, "bce_loss_fwd": 2, "anomaly_l1_fwd": 2,
+            "conv3d_wgrad": 2, "conv3d_fwd_bf16": 2, "conv3d_dgrad_bf16": 3, "conv3d_wgrad_bf16": 2, "lfq_fwd": 2, "lfq_fwd_eval": 1, "lfq_bwd": 2, "bce_loss_fwd": 4, "anomaly_l1_fwd": 2,
             "anomaly_l1_bwd": 1, "adam_step": 1}
 
 

@@ -7,7 +7,6 @@
 
 namespace {
 
-constexpr int LT = 1024;
 
 __device__ __forceinline__ double block_sum_d(double v, double* red) {
     v = warp_sum_d(v);
@@ -26,50 +25,62 @@ __device__ __forceinline__ double block_sum_d(double v, double* red) {
     return s;
 }
 
-// class weights from torch.histc(target, bins=2) over [min,max] (losses.py:115-119): stats = {w0, w1}
-__global__ void __launch_bounds__(LT)
-bce_weights_kernel(const float* __restrict__ target, int64_t M, float* __restrict__ wts) {
-    __shared__ double red[32];
-    __shared__ float s_lo, s_hi;
+// ---- BCE_loss_synthetic: 4 small multi-block launches (range, counts, weighted loss + gradient, finalize) ----
+constexpr int BNB = 64;      // blocks per pass
+constexpr int BT = 256;
+// workspace (doubles): [0,BNB) min | [BNB,2BNB) max | [2BNB,3BNB) count of bin 1 | [3BNB, 3BNB + K*BNB) loss partials
+__global__ void __launch_bounds__(BT)
+bce_range_kernel(const float* __restrict__ target, int64_t M, double* __restrict__ ws) {
+    __shared__ float rl[BT / 32], rh[BT / 32];
     float lo = INFINITY, hi = -INFINITY;
-    for (int64_t i = threadIdx.x; i < M; i += LT) { const float t = target[i]; lo = fminf(lo, t); hi = fmaxf(hi, t); }
+    for (int64_t i = (int64_t)blockIdx.x * BT + threadIdx.x; i < M; i += (int64_t)BNB * BT) { const float t = target[i]; lo = fminf(lo, t); hi = fmaxf(hi, t); }
     for (int o = 16; o > 0; o >>= 1) { lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
-    __shared__ float rl[32], rh[32];
     if ((threadIdx.x & 31) == 0) { rl[threadIdx.x >> 5] = lo; rh[threadIdx.x >> 5] = hi; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int w = 1; w < LT / 32; ++w) { lo = fminf(lo, rl[w]); hi = fmaxf(hi, rh[w]); }
-        if (lo == hi) { lo -= 1.f; hi += 1.f; }   // histc widens a degenerate range
-        s_lo = lo; s_hi = hi;
-    }
-    __syncthreads();
-    lo = s_lo; hi = s_hi;
-    double c1 = 0.0;
-    for (int64_t i = threadIdx.x; i < M; i += LT) {
-        const float t = target[i];
-        int bin = (int)((t - lo) / (hi - lo) * 2.f);
-        if (bin > 1) bin = 1;
-        c1 += bin;
-    }
-    c1 = block_sum_d(c1, red);
-    if (threadIdx.x == 0) {
-        const float n1 = (float)c1, n0 = (float)((double)M - c1), tot = n0 + n1;
-        wts[0] = logf(powf(n0 / tot, -0.5f) + 1.1f);
-        wts[1] = logf(powf(n1 / tot, -0.5f) + 1.1f);
+        for (int w = 1; w < BT / 32; ++w) { lo = fminf(lo, rl[w]); hi = fmaxf(hi, rh[w]); }
+        ws[blockIdx.x] = lo; ws[BNB + blockIdx.x] = hi;
     }
 }
-
-// one CTA per logit map k: loss[k] = mean(w[target] * bce_with_logits(pred, target)); dpred = w*(sigmoid(x)-t)/M
-__global__ void __launch_bounds__(LT)
-bce_loss_kernel(const float* __restrict__ pred, int64_t sk, int64_t sn, int N, int64_t HW, const float* __restrict__ target,
-                const float* __restrict__ wts, float* __restrict__ loss, float* __restrict__ dpred) {
+__device__ __forceinline__ void bce_range(const double* ws, float& lo, float& hi) {
+    lo = INFINITY; hi = -INFINITY;
+    for (int b = 0; b < BNB; ++b) { lo = fminf(lo, (float)ws[b]); hi = fmaxf(hi, (float)ws[BNB + b]); }
+    if (lo == hi) { lo -= 1.f; hi += 1.f; }     // torch.histc widens a degenerate range
+}
+// class counts of torch.histc(target, bins=2) over [min,max] (losses.py:115)
+__global__ void __launch_bounds__(BT)
+bce_count_kernel(const float* __restrict__ target, int64_t M, double* __restrict__ ws) {
     __shared__ double red[32];
-    const int k = blockIdx.x;
-    const float w0 = wts[0], w1 = wts[1];
+    float lo, hi;
+    bce_range(ws, lo, hi);
+    double c1 = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * BT + threadIdx.x; i < M; i += (int64_t)BNB * BT) {
+        int bin = (int)((target[i] - lo) / (hi - lo) * 2.f);
+        c1 += bin > 1 ? 1 : bin;
+    }
+    c1 = block_sum_d(c1, red);
+    if (threadIdx.x == 0) ws[2 * BNB + blockIdx.x] = c1;
+}
+// w_k = log((cnt_k / total)^-0.5 + 1.1)  (losses.py:117-119)
+__device__ __forceinline__ void bce_class_weights(const double* ws, int64_t M, float& w0, float& w1) {
+    double c1 = 0.0;
+    for (int b = 0; b < BNB; ++b) c1 += ws[2 * BNB + b];
+    const float n1 = (float)c1, n0 = (float)((double)M - c1), tot = n0 + n1;
+    w0 = logf(powf(n0 / tot, -0.5f) + 1.1f);
+    w1 = logf(powf(n1 / tot, -0.5f) + 1.1f);
+}
+// grid (BNB, K): partial sums of w[target] * bce_with_logits(pred, target); dpred = w * (sigmoid(x) - t) / M
+__global__ void __launch_bounds__(BT)
+bce_loss_kernel(const float* __restrict__ pred, int64_t sk, int64_t sn, int N, int64_t HW, const float* __restrict__ target,
+                double* __restrict__ ws, float* __restrict__ dpred) {
+    __shared__ double red[32];
+    const int k = blockIdx.y;
     const int64_t M = (int64_t)N * HW;
+    float w0, w1;
+    bce_class_weights(ws, M, w0, w1);
     const float invM = 1.f / (float)M;
     double acc = 0.0;
-    for (int64_t i = threadIdx.x; i < M; i += LT) {
+    for (int64_t i = (int64_t)blockIdx.x * BT + threadIdx.x; i < M; i += (int64_t)BNB * BT) {
         const int64_t n = i / HW, r = i - n * HW;
         const int64_t o = k * sk + n * sn + r;
         const float x = pred[o], t = target[i];
@@ -79,7 +90,16 @@ bce_loss_kernel(const float* __restrict__ pred, int64_t sk, int64_t sn, int N, i
         if (dpred) dpred[o] = w * (1.f / (1.f + expf(-x)) - t) * invM;
     }
     acc = block_sum_d(acc, red);
-    if (threadIdx.x == 0) loss[k] = (float)(acc / (double)M);
+    if (threadIdx.x == 0) ws[3 * BNB + k * BNB + blockIdx.x] = acc;
+}
+__global__ void bce_finalize_kernel(const double* __restrict__ ws, int K, int64_t M, float* __restrict__ wts, float* __restrict__ loss) {
+    const int k = threadIdx.x;
+    if (k == 0) { float w0, w1; bce_class_weights(ws, M, w0, w1); wts[0] = w0; wts[1] = w1; }
+    if (k < K) {
+        double a = 0.0;
+        for (int b = 0; b < BNB; ++b) a += ws[3 * BNB + k * BNB + b];
+        loss[k] = (float)(a / (double)M);
+    }
 }
 
 // ---- anomaly L1 ----
@@ -162,13 +182,23 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 
 }  // namespace
 
+extern "C" size_t idee_bce_loss_workspace_bytes(int K) { return sizeof(double) * (size_t)(3 + K) * BNB; }
+
 extern "C" int idee_bce_loss_fwd(const float* pred, int64_t stride_k, int64_t stride_n, int K, int N, int64_t HW, const float* target,
-                                 float* wts, float* loss, float* dpred, void* stream) {
+                                 float* wts, float* loss, float* dpred, void* workspace, size_t workspace_bytes, void* stream) {
+    IDEE_REQUIRE(K >= 1 && K <= 1024, "bce_loss_fwd: K must be in [1,1024]");
+    IDEE_REQUIRE(workspace_bytes >= idee_bce_loss_workspace_bytes(K), "bce_loss_fwd: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
-    bce_weights_kernel<<<1, LT, 0, st>>>(target, (int64_t)N * HW, wts);
-    IDEE_LAUNCH_CHECK("bce_weights");
-    bce_loss_kernel<<<K, LT, 0, st>>>(pred, stride_k, stride_n, N, HW, target, wts, loss, dpred);
+    double* ws = (double*)workspace;
+    const int64_t M = (int64_t)N * HW;
+    bce_range_kernel<<<BNB, BT, 0, st>>>(target, M, ws);
+    IDEE_LAUNCH_CHECK("bce_range");
+    bce_count_kernel<<<BNB, BT, 0, st>>>(target, M, ws);
+    IDEE_LAUNCH_CHECK("bce_count");
+    bce_loss_kernel<<<dim3(BNB, K), BT, 0, st>>>(pred, stride_k, stride_n, N, HW, target, ws, dpred);
     IDEE_LAUNCH_CHECK("bce_loss");
+    bce_finalize_kernel<<<1, K < 32 ? 32 : K, 0, st>>>(ws, K, M, wts, loss);
+    IDEE_LAUNCH_CHECK("bce_finalize");
     return 0;
 }
 

@@ -369,8 +369,10 @@ class BCEWeighted(torch.autograd.Function):
         loss = torch.empty(K, device=pred.device, dtype=torch.float32)
         wts = torch.empty(2, device=pred.device, dtype=torch.float32)
         dpred = torch.empty_strided(pred.shape, pred.stride(), device=pred.device, dtype=torch.float32)
+        nws = lib.idee_bce_loss_workspace_bytes(K)
+        ws = L.workspace(nws, pred.device)
         L.run("bce_loss_fwd", lib.idee_bce_loss_fwd, pred.data_ptr(), sk, sn, K, N, HW, target.data_ptr(), wts.data_ptr(), loss.data_ptr(),
-                                      dpred.data_ptr(), L.stream())
+              dpred.data_ptr(), ws.data_ptr(), nws, L.stream())
         ctx.save_for_backward(dpred)
         ctx.K = K
         return loss

@@ -18,6 +18,15 @@ from . import ops
 from .models.losses import train_step_loss
 
 
+def shard_batch(t: torch.Tensor, rank: int, world: int) -> torch.Tensor:
+    """Contiguous batch shard of rank `rank` (samples are independent through the whole path)."""
+    n = t.shape[0]
+    if n % world:
+        raise ValueError(f"global batch {n} is not divisible by world size {world}")
+    per = n // world
+    return t[rank * per:(rank + 1) * per]
+
+
 class Trainer:
     def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.003, lambda_anomaly=100.0,
                  process_group=None, distributed=None):
@@ -75,9 +84,14 @@ class Trainer:
         total.backward()
         return total, out
 
-    def optimizer_step(self):
+    def reduce_gradients(self):
+        """ONE collective per step: sum the flat gradient over ranks, then average (SUM + scale works on NCCL and gloo)."""
         if self.distributed and self.world > 1:
-            dist.all_reduce(self.flat_grads, op=dist.ReduceOp.AVG, group=self.group)
+            dist.all_reduce(self.flat_grads, op=dist.ReduceOp.SUM, group=self.group)
+            self.flat_grads.mul_(1.0 / self.world)
+
+    def optimizer_step(self):
+        self.reduce_gradients()
         self.step_count += 1
         ops.adam_step(self.flat_params, self.flat_grads, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1],
                       self.eps, self.weight_decay, self.step_count)

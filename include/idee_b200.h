@@ -112,9 +112,10 @@ int idee_lfq_bwd(const float* z, const float* gzq, const float* g_aux, const flo
 
 /* ---- losses                                                                         models/losses.py:98-168 ----
  * BCE_loss_synthetic over K logit maps sharing one target: element (k,n,i) of pred at k*stride_k + n*stride_n + i, i<HW;
- * target: [N][HW]; wts: float[2] scratch (class weights); loss: float[K]; dpred (optional, pred's layout): d loss[k] / d pred. */
+ * target: [N][HW]; wts: float[2] out (class weights); loss: float[K]; dpred (optional, pred's layout): d loss[k] / d pred. */
+size_t idee_bce_loss_workspace_bytes(int K);
 int idee_bce_loss_fwd(const float* pred, int64_t stride_k, int64_t stride_n, int K, int N, int64_t HW, const float* target,
-                      float* wts, float* loss, float* dpred, void* stream);
+                      float* wts, float* loss, float* dpred, void* workspace, size_t workspace_bytes, void* stream);
 /* Anomaly_L1_loss_synthetic: zq [N,V,T,HW,16], mask [N][HW], vq0 [16]; out: float[2] = {loss, total weight} */
 size_t idee_anomaly_l1_workspace_bytes(int64_t ntok);
 int idee_anomaly_l1_fwd(const float* zq, const float* mask, const float* vq0, int N, int V, int T, int64_t HW, int C, float* out,
