@@ -21,8 +21,9 @@ LIB = os.path.join(LIBDIR, "libidee_b200.so")
 INCLUDE = os.path.join(ROOT, "include")
 
 SOURCES = ["api.cu", "embed.cu", "swin_block.cu", "conv.cu", "conv_tc.cu", "lfq.cu", "losses.cu"]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-              "--expt-relaxed-constexpr", "-I", INCLUDE, "-I", CSRC]
+BASE_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
+              "--expt-relaxed-constexpr"]
+NVCC_FLAGS = BASE_FLAGS + ["-I", INCLUDE, "-I", CSRC]
 
 
 def _nvcc() -> str:
@@ -33,22 +34,37 @@ def _nvcc() -> str:
 
 
 def _fingerprint() -> str:
+    """Hash of the sources and flags; independent of where the tree is checked out (the GPU box uses another path)."""
     h = hashlib.sha256()
     files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(INCLUDE, "idee_b200.h")]
     for f in files:
         with open(f, "rb") as fh:
-            h.update(f.encode())
+            h.update(os.path.basename(f).encode())
             h.update(fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(BASE_FLAGS + SOURCES).encode())
     return h.hexdigest()
+
+
+def _up_to_date(fp: str) -> bool:
+    stamp = os.path.join(LIBDIR, "build.stamp")
+    return os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == fp
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
-    stamp = os.path.join(LIBDIR, "build.stamp")
     fp = _fingerprint()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == fp:
+    if not force and _up_to_date(fp):
         return LIB
+    import fcntl
+    with open(os.path.join(LIBDIR, "build.lock"), "w") as lock:      # one builder at a time (ranks of a torchrun job)
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and _up_to_date(fp):
+            return LIB
+        return _build_locked(fp, verbose)
+
+
+def _build_locked(fp: str, verbose: bool) -> str:
+    stamp = os.path.join(LIBDIR, "build.stamp")
     nvcc = _nvcc()
     objdir = os.path.join(LIBDIR, "obj")
     os.makedirs(objdir, exist_ok=True)
@@ -67,10 +83,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    tmp = LIB + ".tmp"
+    cmd = [nvcc, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    if os.path.exists(stamp):
+        os.remove(stamp)
+    os.replace(tmp, LIB)                                             # atomic: a concurrent loader never sees a partial file
     with open(stamp, "w") as fh:
         fh.write(fp)
     return LIB
