@@ -44,6 +44,10 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem));
 }
+// 16-byte async copy; src_bytes == 0 writes zeros (the source address must still be valid)
+__device__ __forceinline__ void cp_async16_zfill(void* smem, const void* gmem, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem)), "l"(gmem), "r"(src_bytes));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
@@ -130,49 +134,54 @@ conv_tc_kernel(P p) {
     // ---- halo: fp32 HBM -> bf16 smem (zero / clamp handled here, so the MMA loop is branch-free) ----
     const float* in_img = p.in + n * p.in_sn + v * p.in_sv;
     const int V4 = CI / 4;
-    const int halo_total = KTIN * HH * HW_ * V4;
-    // 4 independent loads in flight per thread before any conversion/store (the loop is latency-bound otherwise)
-    for (int e0 = tid; e0 < halo_total; e0 += 4 * 128) {
-        const float* src[4];
-        int dst[4], chs[4];
+    // Halo staging: element e = row * NCOL + col (row = (kt, hh) halo row, col = (pixel column, float4 channel group)).
+    // All 128 threads stride through e with an incrementally updated (row, col) pair (no per-element division by the
+    // halo extents) and keep 4 independent 16-byte loads in flight before converting/storing.
+    {
+        const int NCOL = HW_ * V4, NROW = KTIN * HH;
+        int row = tid / NCOL, col = tid - row * NCOL;
+        const int drow = 128 / NCOL, dcol = 128 - drow * NCOL;
+        while (row < NROW) {
+            const float* src[4];
+            int dst[4], chs[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int e = e0 + u * 128;
-            src[u] = nullptr; dst[u] = -1; chs[u] = 0;
-            if (e < halo_total) {
-                const int c4 = e % V4;
-                int r = e / V4;
-                const int ww = r % HW_; r /= HW_;
-                const int hh = r % HH, kt = r / HH;
-                int ti, hi = h0 + hh - 1, wi = w0 + ww - 1;
-                bool ok = true;
-                if (MODE == CLS_FWD) { ti = 2 * t + kt; ok = hi >= 0 && hi < p.Hi && wi >= 0 && wi < p.Wi; }
-                else if (MODE == PROJ_FWD) { ti = min(max(t + kt - 1, 0), p.Ti - 1); hi = min(max(hi, 0), p.Hi - 1); wi = min(max(wi, 0), p.Wi - 1); }
-                else if (MODE == CLS_DGRAD) { ti = t >> 1; ok = ti < p.Ti && hi >= 0 && hi < p.Hi && wi >= 0 && wi < p.Wi; }
-                else { ti = t + kt - 2; hi -= 1; wi -= 1; ok = ti >= 0 && ti < p.Ti && hi >= 0 && hi < p.Hi && wi >= 0 && wi < p.Wi; }
-                const int ch = c4 * 4, chunk = ch / 16;
-                dst[u] = ((kt * HH + hh) * HW_ + ww) * CP + ch;
-                chs[u] = ch;
-                if (ok) src[u] = in_img + ti * p.in_st + hi * p.in_sh + wi * p.in_sw + (chunk / p.in_cpg) * p.in_sg + (chunk % p.in_cpg) * 16 + (ch % 16);
-            }
-        }
-        float4 f[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            f[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (src[u]) {
-                if (p.CIr >= CI) f[u] = ldg4(src[u]);
-                else {
-                    if (chs[u] < p.CIr) f[u].x = __ldg(src[u]);
-                    if (chs[u] + 1 < p.CIr) f[u].y = __ldg(src[u] + 1);
-                    if (chs[u] + 2 < p.CIr) f[u].z = __ldg(src[u] + 2);
-                    if (chs[u] + 3 < p.CIr) f[u].w = __ldg(src[u] + 3);
+            for (int u = 0; u < 4; ++u) {
+                src[u] = nullptr; dst[u] = -1; chs[u] = 0;
+                if (row < NROW) {
+                    const int kt = row / HH, hh = row - kt * HH;
+                    const int ww = col / V4, c4 = col - ww * V4;
+                    int ti, hi = h0 + hh - 1, wi = w0 + ww - 1;
+                    bool ok = true;
+                    if (MODE == CLS_FWD) { ti = 2 * t + kt; ok = hi >= 0 && hi < p.Hi && wi >= 0 && wi < p.Wi; }
+                    else if (MODE == PROJ_FWD) { ti = min(max(t + kt - 1, 0), p.Ti - 1); hi = min(max(hi, 0), p.Hi - 1); wi = min(max(wi, 0), p.Wi - 1); }
+                    else if (MODE == CLS_DGRAD) { ti = t >> 1; ok = ti < p.Ti && hi >= 0 && hi < p.Hi && wi >= 0 && wi < p.Wi; }
+                    else { ti = t + kt - 2; hi -= 1; wi -= 1; ok = ti >= 0 && ti < p.Ti && hi >= 0 && hi < p.Hi && wi >= 0 && wi < p.Wi; }
+                    const int ch = c4 * 4, chunk = ch >> 4;
+                    dst[u] = (row * HW_ + ww) * CP + ch;
+                    chs[u] = ch;
+                    if (ok) src[u] = in_img + ti * p.in_st + hi * p.in_sh + wi * p.in_sw + (chunk / p.in_cpg) * p.in_sg + (chunk % p.in_cpg) * 16 + (ch & 15);
+                    row += drow; col += dcol;
+                    if (col >= NCOL) { col -= NCOL; ++row; }
                 }
             }
-        }
+            float4 f[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (dst[u] >= 0) *reinterpret_cast<uint2*>(halo + dst[u]) = make_uint2(pack_bf16(f[u].x, f[u].y), pack_bf16(f[u].z, f[u].w));
+            for (int u = 0; u < 4; ++u) {
+                f[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (src[u]) {
+                    if (p.CIr >= CI) f[u] = ldg4(src[u]);
+                    else {
+                        if (chs[u] < p.CIr) f[u].x = __ldg(src[u]);
+                        if (chs[u] + 1 < p.CIr) f[u].y = __ldg(src[u] + 1);
+                        if (chs[u] + 2 < p.CIr) f[u].z = __ldg(src[u] + 2);
+                        if (chs[u] + 3 < p.CIr) f[u].w = __ldg(src[u] + 3);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (dst[u] >= 0) *reinterpret_cast<uint2*>(halo + dst[u]) = make_uint2(pack_bf16(f[u].x, f[u].y), pack_bf16(f[u].z, f[u].w));
+        }
     }
     float acc[2][NTL][4];
 #pragma unroll
@@ -247,6 +256,131 @@ conv_tc_kernel(P p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// 16-input-channel convs (proj_var, per-variable classifier heads, and their data gradients): persistent, pipelined.
+// A CTA loads the weights once, then walks tiles:  wait(stage i) -> convert fp32 stage -> bf16 halo -> issue cp.async for
+// tile i+1 (zero-fill for padding, clamped addresses for replicate) -> MMA + epilogue of tile i.  The global-memory latency
+// of the next tile is hidden behind the tensor-core phase of the current one; taps are fully unrolled.
+// ------------------------------------------------------------------------------------------------------------------
+template <int MODE, int NTL>
+__global__ void __launch_bounds__(128)
+conv_tc16_kernel(P p, int64_t total_tiles, int tiles_h) {
+    constexpr int CP = 24;
+    constexpr int KTIN = (MODE == CLS_FWD) ? 2 : (MODE == CLS_DGRAD ? 1 : 3);
+    constexpr int NJ = (MODE == CLS_FWD) ? 18 : (MODE == CLS_DGRAD ? 9 : 27);
+    constexpr int NTF = (MODE == CLS_FWD || MODE == CLS_DGRAD) ? 18 : 27;
+    constexpr int WTAP = NTL * 32, NPIX = KTIN * HH * HW_;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint2* wsm = reinterpret_cast<uint2*>(smem_raw);                                     // [NTF][WTAP]
+    float* stage = reinterpret_cast<float*>(smem_raw + sizeof(uint2) * NTF * WTAP);      // [NPIX][16] fp32
+    __nv_bfloat16* halo = reinterpret_cast<__nv_bfloat16*>(stage + NPIX * 16);           // [NPIX][CP] bf16
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    auto decode = [&](int64_t tile, int& n, int& v, int& t, int& h0, int& w0) {
+        int64_t r = tile;
+        w0 = (int)(r % p.tiles_w) * TW; r /= p.tiles_w;
+        h0 = (int)(r % tiles_h) * TH; r /= tiles_h;
+        t = (int)(r % p.To); r /= p.To;
+        v = (int)(r % p.V); n = (int)(r / p.V);
+    };
+    auto issue = [&](int64_t tile) {
+        int n, v, t, h0, w0;
+        decode(tile, n, v, t, h0, w0);
+        const float* in_img = p.in + n * p.in_sn + v * p.in_sv;
+        constexpr int NCOL = HW_ * 4, NROW = KTIN * HH, DROW = 128 / NCOL, DCOL = 128 - DROW * NCOL;
+        int row = tid / NCOL, col = tid - row * NCOL;
+        while (row < NROW) {
+            const int kt = row / HH, hh = row - kt * HH;
+            const int ww = col >> 2, c4 = col & 3;
+            int ti, hi = h0 + hh - 1, wi = w0 + ww - 1;
+            bool ok = true;
+            if (MODE == CLS_FWD) { ti = 2 * t + kt; ok = hi >= 0 && hi < p.Hi && wi >= 0 && wi < p.Wi; }
+            else if (MODE == PROJ_FWD) { ti = min(max(t + kt - 1, 0), p.Ti - 1); hi = min(max(hi, 0), p.Hi - 1); wi = min(max(wi, 0), p.Wi - 1); }
+            else if (MODE == CLS_DGRAD) { ti = t >> 1; ok = ti < p.Ti && hi >= 0 && hi < p.Hi && wi >= 0 && wi < p.Wi; }
+            else { ti = t + kt - 2; hi -= 1; wi -= 1; ok = ti >= 0 && ti < p.Ti && hi >= 0 && hi < p.Hi && wi >= 0 && wi < p.Wi; }
+            const float* src = ok ? in_img + ti * p.in_st + hi * p.in_sh + wi * p.in_sw + c4 * 4 : p.in;
+            cp_async16_zfill(stage + (row * HW_ + ww) * 16 + c4 * 4, src, ok ? 16 : 0);
+            row += DROW; col += DCOL;
+            if (col >= NCOL) { col -= NCOL; ++row; }
+        }
+        cp_async_commit();
+    };
+
+    const int64_t first = blockIdx.x;
+    if (first < total_tiles) issue(first);
+    // weights of this CTA's weight set(s): with Vw > 1 the set changes with v, so reload when v changes (rare: tiles are v-major)
+    int cur_wset = -1;
+    const int a_pix = (lane & 7) + ((lane >> 3) & 1) * 8, a_koff = (lane >> 4) * 8;
+    for (int64_t tile = first; tile < total_tiles; tile += gridDim.x) {
+        int n, v, t, h0, w0;
+        decode(tile, n, v, t, h0, w0);
+        const int wset = p.Vw == 1 ? 0 : v;
+        cp_async_wait<0>();
+        __syncthreads();                                   // stage(tile) landed; every warp is done with the previous halo/weights
+        if (wset != cur_wset) {
+            const uint2* wf = p.wfrag + (int64_t)wset * NTF * WTAP;
+            for (int e = tid; e < NTF * WTAP; e += 128) wsm[e] = wf[e];
+            cur_wset = wset;
+        }
+        for (int e = tid; e < NPIX * 4; e += 128) {        // fp32 stage -> bf16 halo (padded pixel stride)
+            const float4 f = ld4(stage + e * 4);
+            *reinterpret_cast<uint2*>(halo + (e >> 2) * CP + (e & 3) * 4) = make_uint2(pack_bf16(f.x, f.y), pack_bf16(f.z, f.w));
+        }
+        __syncthreads();
+        if (tile + gridDim.x < total_tiles) issue(tile + gridDim.x);
+
+        float acc[2][NTL][4];
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int nt = 0; nt < NTL; ++nt) acc[m][nt][0] = acc[m][nt][1] = acc[m][nt][2] = acc[m][nt][3] = 0.f;
+        const __nv_bfloat16* abase = halo + ((warp * 2) * HW_ + a_pix) * CP + a_koff;
+        const uint2* wpar = wsm + ((MODE == CLS_DGRAD) ? (t & 1) * 9 * WTAP : 0) + lane;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            constexpr int dummy = 0; (void)dummy;
+            const int kt = (MODE == CLS_DGRAD) ? 0 : j / 9, kh = (MODE == CLS_DGRAD) ? j / 3 : (j / 3) % 3, kw = j % 3;
+            const int ft = (MODE == CLS_FWD || MODE == PROJ_FWD) ? j
+                         : (MODE == CLS_DGRAD ? (2 - kh) * 3 + (2 - kw) : (2 - kt) * 9 + (2 - kh) * 3 + (2 - kw));
+            uint32_t a0[4], a1[4];
+            ldsm_x4(a0, abase + ((kt * HH + kh) * HW_ + kw) * CP);
+            ldsm_x4(a1, abase + ((kt * HH + kh + 1) * HW_ + kw) * CP);
+#pragma unroll
+            for (int nt = 0; nt < NTL; ++nt) {
+                const uint2 b = wpar[ft * WTAP + nt * 32];
+                mma_bf16(acc[0][nt], a0, b.x, b.y);
+                mma_bf16(acc[1][nt], a1, b.x, b.y);
+            }
+        }
+        // epilogue
+        const float* B = p.bias ? p.bias + (int64_t)wset * p.CO : nullptr;
+        float* out_img = p.out + n * p.out_sn + v * p.out_sv + t * p.out_st;
+        const float* rs_img = p.relu_src ? p.relu_src + n * p.out_sn + v * p.out_sv + t * p.out_st : nullptr;
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            const int h = h0 + warp * 2 + m;
+            if (h >= p.Ho) continue;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int w = w0 + lane / 4 + half * 8;
+                if (w >= p.Wo) continue;
+#pragma unroll
+                for (int nt = 0; nt < NTL; ++nt) {
+                    const int co = nt * 8 + (lane % 4) * 2;
+                    if (co >= p.CO) continue;
+                    const int64_t o = h * p.out_sh + w * p.out_sw + co;
+                    float v0 = acc[m][nt][half * 2], v1 = acc[m][nt][half * 2 + 1];
+                    if (B) { v0 += B[co]; if (co + 1 < p.CO) v1 += B[co + 1]; }
+                    if (p.relu && MODE <= PROJ_FWD) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+                    if (rs_img) { if (!(rs_img[o] > 0.f)) v0 = 0.f; if (co + 1 < p.CO && !(rs_img[o + 1] > 0.f)) v1 = 0.f; }
+                    if (co + 1 < p.CO) *reinterpret_cast<float2*>(out_img + o) = make_float2(v0, v1);
+                    else out_img[o] = v0;
+                }
+            }
+        }
+    }
+}
+
 // gin[r] = sum of gpad over the padded positions that clamp to r (adjoint of replicate padding), optional ReLU mask
 __global__ void fold_pad_kernel(const float* __restrict__ gpad, float* __restrict__ gin, const float* __restrict__ relu_src,
                                 int NV, int T, int H, int W) {
@@ -296,9 +430,12 @@ struct WP {
 template <int NT, int NTL>
 __global__ void __launch_bounds__(128)
 wgrad_tc_kernel(WP p) {
-    constexpr int KTIN = NT / 9, CPA = 24, NC = NTL * 8, CPG = NC + 8, TPW = (NT + 3) / 4;
-    __shared__ __align__(16) __nv_bfloat16 tileA[KTIN * HH * HW_ * CPA];
-    __shared__ __align__(16) __nv_bfloat16 tileG[TH * TW * CPG];
+    constexpr int KTIN = NT / 9, CPA = 24, NC = NTL * 8, CPG = NC + 8, TPW = (NT + 3) / 4, NPIX = KTIN * HH * HW_;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* stageA = reinterpret_cast<float*>(smem_raw);                                  // [NPIX][16] fp32
+    float* stageG = stageA + NPIX * 16;                                                  // [128][NC] fp32
+    __nv_bfloat16* tileA = reinterpret_cast<__nv_bfloat16*>(stageG + TH * TW * NC);      // [NPIX][CPA]
+    __nv_bfloat16* tileG = tileA + NPIX * CPA;                                           // [128][CPG]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int s = blockIdx.x, wset = blockIdx.y;
     const int n_occ = (p.n_oc16 * 16 + NC - 1) / NC;          // output chunks of NC channels
@@ -324,70 +461,86 @@ wgrad_tc_kernel(WP p) {
     const int a_pix = (lane & 7) + (lane >> 4) * 8, a_coff = ((lane >> 3) & 1) * 8;     // A (trans) lane address
     const int b_pix = (lane & 7) + ((lane >> 3) & 1) * 8, b_coff = (lane >> 4) * 8;     // B (trans) lane address
     const int64_t coff = (ic / p.in_cpg) * p.in_sg + (ic % p.in_cpg) * 16;
-    for (int64_t tile = t_begin; tile < t_end; ++tile) {
+    const bool g_vec = (p.FCO % 4) == 0;                      // gout rows can be fetched in 16-byte pieces
+    // smem offsets (halves) of this warp's taps inside the halo tile
+    int a_off[TPW];
+#pragma unroll
+    for (int i = 0; i < TPW; ++i) {
+        const int ft = warp + 4 * i, kt = ft / 9, kh = (ft / 3) % 3, kw = ft % 3;
+        a_off[i] = (((kt * HH + kh) * HW_ + kw) + a_pix) * CPA + a_coff;
+    }
+    auto decode = [&](int64_t tile, int& n, int& v, int& t, int& h0, int& w0) {
         int64_t r = tile;                          // t fastest: consecutive tiles of a CTA share input t-slices (L1/L2 hits)
-        const int t = (int)(r % p.To); r /= p.To;
-        const int tw_ = (int)(r % p.tiles_w); r /= p.tiles_w;
-        const int th_ = (int)(r % p.tiles_h);
+        t = (int)(r % p.To); r /= p.To;
+        w0 = (int)(r % p.tiles_w) * TW; r /= p.tiles_w;
+        h0 = (int)(r % p.tiles_h) * TH;
         const int64_t img = r / p.tiles_h;
-        const int n = (int)(img / imgs_per_n), v = p.Vw == 1 ? (int)(img % imgs_per_n) : wset;
-        const int h0 = th_ * TH, w0 = tw_ * TW;
-        __syncthreads();
+        n = (int)(img / imgs_per_n); v = p.Vw == 1 ? (int)(img % imgs_per_n) : wset;
+    };
+    auto issue = [&](int64_t tile) {
+        int n, v, t, h0, w0;
+        decode(tile, n, v, t, h0, w0);
         const float* in_img = p.in + n * p.in_sn + v * p.in_sv + coff;
-        constexpr int A_TOTAL = KTIN * HH * HW_ * 4;
-        for (int e0 = tid; e0 < A_TOTAL; e0 += 4 * 128) {
-            const float* src[4];
-            int dst[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int e = e0 + u * 128;
-                src[u] = nullptr; dst[u] = -1;
-                if (e < A_TOTAL) {
-                    const int c4 = e & 3;
-                    int q = e >> 2;
-                    const int ww = q % HW_; q /= HW_;
-                    const int hh = q % HH, kt = q / HH;
-                    int ti, hi = h0 + hh - 1, wi = w0 + ww - 1;
-                    bool ok = true;
-                    if (p.proj) { ti = min(max(t + kt - 1, 0), p.Ti - 1); hi = min(max(hi, 0), p.Hi - 1); wi = min(max(wi, 0), p.Wi - 1); }
-                    else { ti = 2 * t + kt; ok = hi >= 0 && hi < p.Hi && wi >= 0 && wi < p.Wi; }
-                    dst[u] = ((kt * HH + hh) * HW_ + ww) * CPA + c4 * 4;
-                    if (ok) src[u] = in_img + ti * p.in_st + hi * p.in_sh + wi * p.in_sw + c4 * 4;
-                }
-            }
-            float4 f[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) f[u] = src[u] ? ldg4(src[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (dst[u] >= 0) *reinterpret_cast<uint2*>(tileA + dst[u]) = make_uint2(pack_bf16(f[u].x, f[u].y), pack_bf16(f[u].z, f[u].w));
+        constexpr int NCOL = HW_ * 4, NROW = KTIN * HH, DROW = 128 / NCOL, DCOL = 128 - DROW * NCOL;
+        int row = tid / NCOL, col = tid - row * NCOL;
+        while (row < NROW) {
+            const int kt = row / HH, hh = row - kt * HH;
+            const int ww = col >> 2, c4 = col & 3;
+            int ti, hi = h0 + hh - 1, wi = w0 + ww - 1;
+            bool ok = true;
+            if (p.proj) { ti = min(max(t + kt - 1, 0), p.Ti - 1); hi = min(max(hi, 0), p.Hi - 1); wi = min(max(wi, 0), p.Wi - 1); }
+            else { ti = 2 * t + kt; ok = hi >= 0 && hi < p.Hi && wi >= 0 && wi < p.Wi; }
+            const float* src = ok ? in_img + ti * p.in_st + hi * p.in_sh + wi * p.in_sw + c4 * 4 : p.in;
+            cp_async16_zfill(stageA + (row * HW_ + ww) * 16 + c4 * 4, src, ok ? 16 : 0);
+            row += DROW; col += DCOL;
+            if (col >= NCOL) { col -= NCOL; ++row; }
         }
-        const float* go_img = p.gout + n * p.go_sn + v * p.go_sv + t * p.go_st;
-        constexpr int G_TOTAL = TH * TW * (NC / 4);
-        for (int e0 = tid; e0 < G_TOTAL; e0 += 4 * 128) {
-            float4 f[4];
-            int dst[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int e = e0 + u * 128;
-                f[u] = make_float4(0.f, 0.f, 0.f, 0.f); dst[u] = -1;
-                if (e < G_TOTAL) {
-                    const int c4 = e % (NC / 4), pix = e / (NC / 4);
-                    const int h = h0 + pix / TW, w = w0 + pix % TW;
-                    const int co = occ * NC + c4 * 4;
-                    dst[u] = pix * CPG + c4 * 4;
-                    if (h < p.Ho && w < p.Wo) {
-                        const float* g = go_img + h * p.go_sh + w * p.go_sw + co;
-                        if (co + 3 < p.FCO) f[u] = ldg4(g);
-                        else { if (co < p.FCO) f[u].x = __ldg(g); if (co + 1 < p.FCO) f[u].y = __ldg(g + 1); if (co + 2 < p.FCO) f[u].z = __ldg(g + 2); }
-                    }
-                }
+        if (g_vec) {
+            const float* go_img = p.gout + n * p.go_sn + v * p.go_sv + t * p.go_st;
+            for (int e = tid; e < TH * TW * (NC / 4); e += 128) {
+                const int c4 = e % (NC / 4), pix = e / (NC / 4);
+                const int h = h0 + pix / TW, w = w0 + pix % TW;
+                const int co = occ * NC + c4 * 4;
+                const bool ok = h < p.Ho && w < p.Wo && co + 3 < p.FCO;
+                const float* src = ok ? go_img + h * p.go_sh + w * p.go_sw + co : p.gout;
+                cp_async16_zfill(stageG + pix * NC + c4 * 4, src, ok ? 16 : 0);
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (dst[u] >= 0) *reinterpret_cast<uint2*>(tileG + dst[u]) = make_uint2(pack_bf16(f[u].x, f[u].y), pack_bf16(f[u].z, f[u].w));
+        }
+        cp_async_commit();
+    };
+    if (t_begin < t_end) issue(t_begin);
+    for (int64_t tile = t_begin; tile < t_end; ++tile) {
+        cp_async_wait<0>();
+        __syncthreads();
+        for (int e = tid; e < NPIX * 4; e += 128) {
+            const float4 f = ld4(stageA + e * 4);
+            *reinterpret_cast<uint2*>(tileA + (e >> 2) * CPA + (e & 3) * 4) = make_uint2(pack_bf16(f.x, f.y), pack_bf16(f.z, f.w));
+        }
+        if (g_vec) {
+            for (int e = tid; e < TH * TW * (NC / 4); e += 128) {
+                const int c4 = e % (NC / 4), pix = e / (NC / 4);
+                const float4 f = ld4(stageG + e * 4);
+                *reinterpret_cast<uint2*>(tileG + pix * CPG + c4 * 4) = make_uint2(pack_bf16(f.x, f.y), pack_bf16(f.z, f.w));
+            }
+        } else {                                   // Cout not a multiple of 4 (the 1-channel logit convs): scalar fetch
+            int n, v, t, h0, w0;
+            decode(tile, n, v, t, h0, w0);
+            const float* go_img = p.gout + n * p.go_sn + v * p.go_sv + t * p.go_st;
+            for (int e = tid; e < TH * TW * (NC / 4); e += 128) {
+                const int c4 = e % (NC / 4), pix = e / (NC / 4);
+                const int h = h0 + pix / TW, w = w0 + pix % TW;
+                const int co = occ * NC + c4 * 4;
+                float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (h < p.Ho && w < p.Wo) {
+                    const float* g = go_img + h * p.go_sh + w * p.go_sw + co;
+                    if (co < p.FCO) f.x = __ldg(g); if (co + 1 < p.FCO) f.y = __ldg(g + 1);
+                    if (co + 2 < p.FCO) f.z = __ldg(g + 2); if (co + 3 < p.FCO) f.w = __ldg(g + 3);
+                }
+                *reinterpret_cast<uint2*>(tileG + pix * CPG + c4 * 4) = make_uint2(pack_bf16(f.x, f.y), pack_bf16(f.z, f.w));
+            }
         }
         __syncthreads();
+        if (tile + 1 < t_end) issue(tile + 1);      // next tile's loads fly while this tile's MMAs run
 #pragma unroll
         for (int ks = 0; ks < TH; ++ks) {            // k-step = one tile row of 16 pixels
             uint32_t b[NTL / 2 > 0 ? NTL / 2 : 1][4];
@@ -399,11 +552,9 @@ wgrad_tc_kernel(WP p) {
             }
 #pragma unroll
             for (int i = 0; i < TPW; ++i) {
-                const int ft = warp + 4 * i;
-                if (ft < NT) {
-                    const int kt = ft / 9, kh = (ft / 3) % 3, kw = ft % 3;
+                if (warp + 4 * i < NT) {
                     uint32_t a[4];
-                    ldsm_x4_t(a, tileA + ((size_t)(kt * HH + ks + kh) * HW_ + kw + a_pix) * CPA + a_coff);
+                    ldsm_x4_t(a, tileA + a_off[i] + ks * HW_ * CPA);
 #pragma unroll
                     for (int nt = 0; nt < NTL; ++nt) mma_bf16(acc[i][nt], a, b[nt / 2][(nt & 1) * 2], b[nt / 2][(nt & 1) * 2 + 1]);
                 }
@@ -474,8 +625,29 @@ int launch_tc(P p, const Plan& pl, int n_img_t, cudaStream_t st, const char* who
     return 0;
 }
 
+template <int MODE, int NTL>
+int launch_tc16(const P& p, int n_img_t, cudaStream_t st, const char* who) {
+    constexpr int KTIN = (MODE == CLS_FWD) ? 2 : (MODE == CLS_DGRAD ? 1 : 3);
+    constexpr int NTF = (MODE == CLS_FWD || MODE == CLS_DGRAD) ? 18 : 27;
+    const size_t smem = sizeof(uint2) * NTF * NTL * 32 + (size_t)KTIN * HH * HW_ * (16 * 4 + 24 * 2);
+    auto kern = conv_tc16_kernel<MODE, NTL>;
+    IDEE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), who);
+    const int tiles_h = (p.Ho + TH - 1) / TH;
+    const int64_t total = (int64_t)n_img_t * tiles_h * p.tiles_w;
+    int per_sm = 1;
+    IDEE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem), who);
+    if (per_sm < 1) per_sm = 1;
+    int64_t grid = (int64_t)idee_num_sms() * per_sm;
+    if (grid > total) grid = total;
+    kern<<<(unsigned)grid, 128, smem, st>>>(p, total, tiles_h);
+    IDEE_LAUNCH_CHECK(who);
+    return 0;
+}
+
 template <int MODE>
 int dispatch_tc(const P& p, const Plan& pl, int n_img_t, cudaStream_t st, const char* who) {
+    if (pl.KS == 1 && p.CIr == 16 && pl.n_oc == 1 && pl.NTL == 2) return launch_tc16<MODE, 2>(p, n_img_t, st, who);
+    if (pl.KS == 1 && p.CIr == 16 && pl.n_oc == 1 && pl.NTL == 1) return launch_tc16<MODE, 1>(p, n_img_t, st, who);
     if (pl.KS == 1 && pl.NTL == 2) return launch_tc<MODE, 1, 2, false>(p, pl, n_img_t, st, who);
     if (pl.KS == 1 && pl.NTL == 1) return launch_tc<MODE, 1, 1, false>(p, pl, n_img_t, st, who);
     if (pl.KS == 1 && pl.NTL == 12) return launch_tc<MODE, 1, 12, false>(p, pl, n_img_t, st, who);
@@ -597,10 +769,18 @@ int conv_tc_wgrad_partials(const idee_conv_desc* d, const float* x, const float*
     // the partial buffer is only partly written when Cout is not a multiple of 16 (Cout == 1): clear it first
     if (d->Cout % 16) IDEE_CUDA(cudaMemsetAsync(partials, 0, conv_tc_wgrad_workspace_bytes(d), st), "conv3d_wgrad(bf16)");
     dim3 grid(p.S, d->Vw, p.n_ic * n_occ);
-    if (d->proj) { if (NC == 16) wgrad_tc_kernel<27, 2><<<grid, 128, 0, st>>>(p); else { idee_set_error("conv3d_wgrad(proj,bf16): Cout must be 16"); return 1; } }
-    else if (NC == 32) wgrad_tc_kernel<18, 4><<<grid, 128, 0, st>>>(p);
-    else if (NC == 16) wgrad_tc_kernel<18, 2><<<grid, 128, 0, st>>>(p);
-    else wgrad_tc_kernel<18, 1><<<grid, 128, 0, st>>>(p);
+    const int KTIN = d->proj ? 3 : 2;
+    const size_t smem = (size_t)KTIN * HH * HW_ * (16 * 4 + 24 * 2) + (size_t)TH * TW * (NC * 4 + (NC + 8) * 2);
+#define IDEE_WGRAD_LAUNCH(NT_, NTL_)                                                                                       \
+    do {                                                                                                                   \
+        IDEE_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<NT_, NTL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "conv3d_wgrad(bf16)"); \
+        wgrad_tc_kernel<NT_, NTL_><<<grid, 128, smem, st>>>(p);                                                            \
+    } while (0)
+    if (d->proj) { if (NC == 16) IDEE_WGRAD_LAUNCH(27, 2); else { idee_set_error("conv3d_wgrad(proj,bf16): Cout must be 16"); return 1; } }
+    else if (NC == 32) IDEE_WGRAD_LAUNCH(18, 4);
+    else if (NC == 16) IDEE_WGRAD_LAUNCH(18, 2);
+    else IDEE_WGRAD_LAUNCH(18, 1);
+#undef IDEE_WGRAD_LAUNCH
     IDEE_LAUNCH_CHECK("conv3d_wgrad(bf16)");
     return 0;
 }

@@ -66,12 +66,36 @@ struct TokRows {
     int64_t off[4];
     int code[4];
 };
+// Token coordinates of the 4 rows (tokens g + 8r) of this lane.  The window index is decoded ONCE per warp iteration (three
+// integer divisions) and advanced incrementally for the following windows of the warp; the in-window part uses compile-time
+// divisors.  Same mapping as TokenMap (cyclic shift, padding, region codes).
 template <int WD, int WH, int WW>
 __device__ __forceinline__ void map_rows(TokRows& tr, const Geom& g, int v, int wg, bool wg_ok, int lane) {
+    constexpr int G = WD * WH * WW;
+    const int gq = lane / 4;
+    const int win0 = wg * (32 / G);
+    int n = win0 / g.nwin_img;
+    int rem = win0 - n * g.nwin_img;
+    int dw = rem / (g.nwh * g.nww);
+    rem -= dw * g.nwh * g.nww;
+    int hw = rem / g.nww, ww = rem - hw * g.nww;
+    int cur = 0;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        const TokenMap<WD, WH, WW> tm(g, v, wg, lane / 4 + 8 * r);
-        tr.valid[r] = tm.valid && wg_ok; tr.off[r] = tm.off; tr.code[r] = tm.code;
+        const int wl = (8 * r) / G;                  // window of this row inside the warp (compile time)
+        while (cur < wl) {                           // advance to the next window (row-major over ww, hw, dw, n)
+            ++cur;
+            if (++ww == g.nww) { ww = 0; if (++hw == g.nwh) { hw = 0; if (++dw == g.nwt) { dw = 0; ++n; } } }
+        }
+        const int i = (8 * r) % G + gq;
+        const int dl = i / (WH * WW), hl = (i / WW) % WH, wl_ = i % WW;
+        const int pt = dw * WD + dl, ph = hw * WH + hl, pw = ww * WW + wl_;
+        int s_t = pt + g.st; if (s_t >= g.Tp) s_t -= g.Tp;
+        int s_h = ph + g.sh; if (s_h >= g.Hp) s_h -= g.Hp;
+        int s_w = pw + g.sw; if (s_w >= g.Wp) s_w -= g.Wp;
+        tr.valid[r] = wg_ok && n < g.N && s_t < g.T && s_h < g.H && s_w < g.W;
+        tr.off[r] = ((((int64_t)(n * g.V + v) * g.T + s_t) * g.H + s_h) * g.W + s_w) * C;
+        tr.code[r] = g.masked ? (region_id(pt, g.Tp, WD, g.st) * 9 + region_id(ph, g.Hp, WH, g.sh) * 3 + region_id(pw, g.Wp, WW, g.sw)) : 0;
     }
 }
 __device__ __forceinline__ void load_tile(float (&t)[4][4], const float* base, const TokRows& tr, int c0) {

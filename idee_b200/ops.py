@@ -28,6 +28,13 @@ class ParamPack:
         self.P = sum(self.sizes)
         self.V = len(self.groups)
         self.flat = None
+        self.grad_flat = None     # optional [V,P] destination for the op's weight gradient (a slice of a model-wide buffer)
+
+    def grad_out(self, like: torch.Tensor) -> torch.Tensor:
+        """Where the backward kernel writes this pack's gradient: the bound destination if any, else a fresh buffer."""
+        if self.grad_flat is not None and self.grad_flat.device == like.device:
+            return self.grad_flat
+        return torch.empty(self.V, self.P, device=like.device, dtype=torch.float32)
 
     def params(self) -> List[torch.nn.Parameter]:
         return [p for g in self.groups for p in g]
@@ -111,7 +118,7 @@ class EmbedLN(torch.autograd.Function):
         N, V, Cin, T, H, W = x.shape
         w, b = wpack.tensor(), bpack.tensor()
         gy = _f32c(gy)
-        gw, gb = torch.empty_like(w), torch.empty_like(b)
+        gw, gb = wpack.grad_out(w), bpack.grad_out(b)
         nws = lib.idee_embed_ln_bwd_workspace_bytes(V)
         ws = L.workspace(nws, x.device)
         xs = (C.c_int64 * 6)(*x.stride())
@@ -170,7 +177,7 @@ class SwinBlock(torch.autograd.Function):
         d = _swin_desc(x, window, shift, rpb_rows, scale, pack, heads, hidden)
         gout = _f32c(gout)
         gx = torch.empty_like(x)
-        gflat = torch.empty_like(flat)
+        gflat = pack.grad_out(flat)
         nws = lib.idee_swin_block_bwd_workspace_bytes(C.byref(d))
         ws = L.workspace(nws, x.device)
         L.run("swin_block_bwd", lib.idee_swin_block_bwd, C.byref(d), x.data_ptr(), ymid.data_ptr(), gout.data_ptr(), gx.data_ptr(), flat.data_ptr(),
@@ -235,6 +242,7 @@ class Conv3dCL(torch.autograd.Function):
               b.data_ptr(), y.data_ptr(), ws.data_ptr(), nws, L.stream(), tag=_conv_tag(d))
         ctx.save_for_backward(x, w, y if relu else None)
         ctx.desc, ctx.relu, ctx.groups = d, relu, groups
+        ctx.grad_dst = (getattr(w, "_idee_grad_dst", None), getattr(b, "_idee_grad_dst", None))
         return y
 
     @staticmethod
@@ -245,8 +253,10 @@ class Conv3dCL(torch.autograd.Function):
         gy = _f32c(gy)
         if ctx.relu:
             gy = torch.ops.aten.threshold_backward(gy, y, 0.0)
-        gw = torch.empty_like(w)
-        gb = torch.empty(w.shape[0], w.shape[1], device=w.device, dtype=torch.float32)
+        gw_dst, gb_dst = ctx.grad_dst
+        gw = gw_dst if gw_dst is not None and gw_dst.shape == w.shape else torch.empty_like(w)
+        gb = gb_dst if gb_dst is not None and gb_dst.shape == (w.shape[0], w.shape[1]) else \
+            torch.empty(w.shape[0], w.shape[1], device=w.device, dtype=torch.float32)
         nws = lib.idee_conv3d_wgrad_workspace_bytes(C.byref(d))
         ws = L.workspace(nws, x.device)
         L.run("conv3d_wgrad_bf16" if d.precision else "conv3d_wgrad", lib.idee_conv3d_wgrad, C.byref(d), x.data_ptr(), gy.data_ptr(), gw.data_ptr(), gb.data_ptr(), ws.data_ptr(), nws,
@@ -288,7 +298,10 @@ class PackedWB(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pack: ParamPack, shape, *params):
         ctx.pack = pack
-        return pack.tensor().view(shape)
+        out = pack.tensor().view(shape)
+        if pack.grad_flat is not None:
+            out._idee_grad_dst = pack.grad_flat.view(shape)      # lets the consumer's wgrad kernel write in place
+        return out
 
     @staticmethod
     def backward(ctx, g):

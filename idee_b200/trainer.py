@@ -67,21 +67,40 @@ class Trainer:
         self.flat_params = flat
         self.flat_grads = torch.zeros_like(flat)
         base = flat.data_ptr()
+        self._grad_view = {}
         for p in model.parameters():
             o = (p.data_ptr() - base) // 4
-            p.grad = self.flat_grads[o:o + p.numel()].view(p.shape)
+            self._grad_view[id(p)] = self.flat_grads[o:o + p.numel()].view(p.shape)
+            p.grad = self._grad_view[id(p)]
+        # the kernels write each pack's gradient block straight into the flat buffer (no per-parameter accumulate launches)
+        off = 0
+        self._pack_params = []
+        for pk in packs:
+            n = pk.V * pk.P
+            pk.grad_flat = self.flat_grads[off:off + n].view(pk.V, pk.P)
+            self._pack_params.extend(pk.params())
+            off += n
 
     def _check_flat(self):
         base, end = self.flat_params.data_ptr(), self.flat_params.data_ptr() + 4 * self.flat_params.numel()
         for p in self.model.parameters():
-            if not (base <= p.data_ptr() < end) or p.grad is None:
+            if not (base <= p.data_ptr() < end):
                 raise RuntimeError("Trainer: a parameter left the flat buffer (module.to()/zero_grad(set_to_none=True) after "
                                    "Trainer creation?); build the Trainer after moving the model")
 
     def forward_backward(self, x, mask_extreme, mask_extreme_loss):
         self.flat_grads.zero_()
+        for p in self._pack_params:
+            p.grad = None                      # autograd then adopts the gradient views the kernels wrote in place
         total, out = train_step_loss(self.model, x, mask_extreme, mask_extreme_loss, self.lambda_anomaly)
         total.backward()
+        for p in self._pack_params:            # safety net: anything autograd cloned instead of adopting is copied back
+            view = self._grad_view[id(p)]
+            if p.grad is None:
+                continue
+            if p.grad.data_ptr() != view.data_ptr():
+                view.copy_(p.grad)
+            p.grad = view
         return total, out
 
     def reduce_gradients(self):
