@@ -13,6 +13,8 @@
 // Backward is recompute-based and split like the fp32 path (MLP half / attention half around the saved mid residual);
 // weight-gradient accumulators stay in registers across the CTA's persistent loop and are reduced once per CTA.
 
+constexpr float LOG2E = 1.4426950408889634f;   // attention scores are kept in the log2 domain (one ex2 per probability)
+
 __device__ __forceinline__ uint32_t pk(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
@@ -124,7 +126,7 @@ __device__ __forceinline__ void ln_tile(const float (&x)[4][4], float (&xn)[4][4
         float d[4], s = 0.f;
 #pragma unroll
         for (int q = 0; q < 4; ++q) { d[q] = x[r][q] - mu; s += d[q] * d[q]; }
-        const float rs = 1.f / sqrtf(quad_sum(s) * (1.f / 16.f) + 1e-5f);
+        const float rs = rsqrtf(quad_sum(s) * (1.f / 16.f) + 1e-5f);
         rstd[r] = rs;
 #pragma unroll
         for (int q = 0; q < 4; ++q) xn[r][q] = (valid == nullptr || valid[r]) ? d[q] * rs : 0.f;
@@ -176,8 +178,11 @@ struct AttnTC {
             }
         }
     }
-    // scores + bias + mask + softmax for head h: p[mi][nj][4] (probabilities, 0 outside the window)
-    __device__ __forceinline__ void probs(int h, float (&p)[2][4][4], const float* Bn, const TokRows& tr, bool masked, int lane) {
+    // scores + bias + mask + softmax for head h: p[mi][nj][4] (probabilities, 0 outside the window).  Everything is in
+    // the log2 domain (q, the bias table and the mask constant carry a factor log2(e)), so the exponential is one ex2.
+    // NORMALISE=false leaves p unnormalised and returns 1/rowsum in rinv (the forward pass scales O instead of P).
+    template <bool NORMALISE>
+    __device__ __forceinline__ void probs(int h, float (&p)[2][4][4], float (&rinv)[4], const float* Bn, const TokRows& tr, bool masked, int lane) {
         const int g = lane / 4, c0 = 2 * (lane % 4);
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi)
@@ -205,7 +210,7 @@ struct AttnTC {
                     const int jl = (8 * nj + c0) % G;
                     const float2 b = *reinterpret_cast<const float2*>(Bn + (h * G + il) * G + jl);
                     float s0 = p[mi][nj][2 * hf] + b.x, s1 = p[mi][nj][2 * hf + 1] + b.y;
-                    if (masked) { if (cj[nj][0] != tr.code[r]) s0 += -100.0f; if (cj[nj][1] != tr.code[r]) s1 += -100.0f; }
+                    if (masked) { if (cj[nj][0] != tr.code[r]) s0 += -100.0f * LOG2E; if (cj[nj][1] != tr.code[r]) s1 += -100.0f * LOG2E; }
                     p[mi][nj][2 * hf] = s0; p[mi][nj][2 * hf + 1] = s1;
                     mx = fmaxf(mx, fmaxf(s0, s1));
                 }
@@ -215,13 +220,16 @@ struct AttnTC {
 #pragma unroll
             for (int nj = 0; nj < 4; ++nj) {
                 if (tile_needed(r, nj)) {
-                    const float e0 = __expf(p[mi][nj][2 * hf] - mx), e1 = __expf(p[mi][nj][2 * hf + 1] - mx);
+                    const float e0 = ex2_approx(p[mi][nj][2 * hf] - mx), e1 = ex2_approx(p[mi][nj][2 * hf + 1] - mx);
                     p[mi][nj][2 * hf] = e0; p[mi][nj][2 * hf + 1] = e1; sum += e0 + e1;
                 } else { p[mi][nj][2 * hf] = 0.f; p[mi][nj][2 * hf + 1] = 0.f; }
             }
-            const float inv = 1.f / quad_sum(sum);
+            const float inv = __fdividef(1.f, quad_sum(sum));
+            if (NORMALISE) {
 #pragma unroll
-            for (int nj = 0; nj < 4; ++nj) { p[mi][nj][2 * hf] *= inv; p[mi][nj][2 * hf + 1] *= inv; }
+                for (int nj = 0; nj < 4; ++nj) { p[mi][nj][2 * hf] *= inv; p[mi][nj][2 * hf + 1] *= inv; }
+            }
+            rinv[r] = inv;
         }
     }
     // o (+)= P V_h into columns of head h of the O tile
@@ -251,7 +259,7 @@ template <int G>
 __device__ __forceinline__ void stage_bias_n(float* Bn, const float* tbl, const int* __restrict__ rel_index) {
     for (int e = threadIdx.x; e < NH * G * G; e += blockDim.x) {
         const int h = e / (G * G), ij = e % (G * G);
-        Bn[e] = tbl[rel_index[ij] * NH + h];
+        Bn[e] = tbl[rel_index[ij] * NH + h] * 1.4426950408889634f;      // log2 domain
     }
 }
 
@@ -312,16 +320,18 @@ swin_fwd_tc_kernel(const float* __restrict__ x, float* __restrict__ out, float* 
         {
             float xn[4][4], rstd[4], q[4][4], k[4][4], vv[4][4], o[4][4];
             ln_tile(xt, xn, rstd, tr.valid);
-            qkv_tiles(xn, wf, bias_s, g.scale, q, k, vv, lane);
+            qkv_tiles(xn, wf, bias_s, g.scale * LOG2E, q, k, vv, lane);
             AttnTC<G> at;
             at.pack(q, k, vv);
 #pragma unroll
             for (int r = 0; r < 4; ++r) o[r][0] = o[r][1] = o[r][2] = o[r][3] = 0.f;
 #pragma unroll
             for (int h = 0; h < NH; ++h) {
-                float p[2][4][4];
-                at.probs(h, p, Bn, tr, masked, lane);
+                float p[2][4][4], rinv[4];
+                at.template probs<false>(h, p, rinv, Bn, tr, masked, lane);
                 at.pv(h, p, o);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) { o[r][2 * h] *= rinv[r]; o[r][2 * h + 1] *= rinv[r]; }
             }
 #pragma unroll
             for (int r = 0; r < 4; ++r)
@@ -349,7 +359,7 @@ swin_fwd_tc_kernel(const float* __restrict__ x, float* __restrict__ out, float* 
 #pragma unroll
             for (int r = 0; r < 4; ++r)
 #pragma unroll
-                for (int qd = 0; qd < 4; ++qd) { float dy; gelu_fast(h[r][qd], h[r][qd], dy); }
+                for (int qd = 0; qd < 4; ++qd) h[r][qd] = gelu_fast(h[r][qd]);
             gemm16(acc, h, wf + (16 + 2 * kk) * 32, lane);
         }
         store_tile(out, acc, tr, c0);
@@ -362,7 +372,7 @@ swin_fwd_tc_kernel(const float* __restrict__ x, float* __restrict__ out, float* 
 // fragment table: fc1^T 8 | fc2 "N" (k = c, n = hidden) 8 | fc1 "N" (k = hidden 4 k-steps, n = c 2 n-tiles) 8
 constexpr int MB_FRAGS = 24;
 
-__global__ void __launch_bounds__(TCW * 32)
+__global__ void __launch_bounds__(TCW * 32, 3)
 swin_mlp_bwd_tc_kernel(const float* __restrict__ y, const float* __restrict__ gout, float* __restrict__ gy,
                        const float* __restrict__ params, int64_t pstride, int tbl, float* __restrict__ partials,
                        int N, int V, int64_t thw) {
@@ -435,7 +445,7 @@ swin_mlp_bwd_tc_kernel(const float* __restrict__ y, const float* __restrict__ go
 #pragma unroll
                 for (int qd = 0; qd < 4; ++qd) {
                     float hv, dg;
-                    gelu_fast(pre[r][qd], hv, dg);
+                    gelu_fast_grad(pre[r][qd], hv, dg);
                     hid[r][qd] = tr.valid[r] ? hv : 0.f;
                     dh[r][qd] = tr.valid[r] ? dh[r][qd] * dg : 0.f;   // dPre
                     ab1[kk][qd] += dh[r][qd];
@@ -497,7 +507,7 @@ constexpr int AB_FRAGS = 14;
 __host__ __device__ constexpr int dbs(int G) { return G == 8 ? 8 : G + 8; }
 
 template <int WD, int WH, int WW>
-__global__ void __launch_bounds__(TCW * 32)
+__global__ void __launch_bounds__(TCW * 32, 3)
 swin_attn_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gx,
                         const float* __restrict__ params, int64_t pstride, const int* __restrict__ rel_index,
                         float* __restrict__ partials, Geom g) {
@@ -548,7 +558,7 @@ swin_attn_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ g
         load_tile(ga, gy, tr, c0);
         ln_tile(xt, xn, rstd, tr.valid);
         float q[4][4], k[4][4], vv[4][4];
-        qkv_tiles(xn, wf, bq_s, g.scale, q, k, vv, lane);
+        qkv_tiles(xn, wf, bq_s, g.scale * LOG2E, q, k, vv, lane);
         AttnTC<G> at;
         at.pack(q, k, vv);
         float dot[4][4];                                  // dO = dY Wproj
@@ -562,8 +572,8 @@ swin_attn_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ g
             for (int qd = 0; qd < 4; ++qd) { o[r][qd] = 0.f; dq[r][qd] = 0.f; dk[r][qd] = 0.f; dv[r][qd] = 0.f; }
 #pragma unroll
         for (int h = 0; h < NH; ++h) {
-            float p[2][4][4];
-            at.probs(h, p, Bn, tr, masked, lane);
+            float p[2][4][4], rinv[4];
+            at.template probs<true>(h, p, rinv, Bn, tr, masked, lane);
             at.pv(h, p, o);
             // D_r = <dO_r, O_r> over the 8 dims of head h
             float Dr[4];
@@ -637,7 +647,7 @@ swin_attn_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ g
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
-            for (int qd = 0; qd < 4; ++qd) dq[r][qd] *= g.scale;
+            for (int qd = 0; qd < 4; ++qd) { dq[r][qd] *= g.scale; dk[r][qd] *= (1.f / LOG2E); }   // dK was formed with q * scale * log2(e)
         // dXn = dQ Wq + dK Wk + dV Wv ; dX = dY + LN_bwd
         float dxn[4][4], gxt[4][4];
 #pragma unroll
