@@ -59,32 +59,34 @@ embed_ln_fwd_kernel(EmbP p, float* __restrict__ y) {
 
 constexpr int EMB_NG = C * MAXCIN + C;
 
+template <int CIN>
 __global__ void __launch_bounds__(EMB_THREADS)
 embed_ln_bwd_kernel(EmbP p, const float* __restrict__ gy, float* __restrict__ partials) {
     const int v = blockIdx.y;
-    float wr[C][MAXCIN], br[C];
+    float wr[C][CIN], br[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) {
         br[c] = __ldg(p.b + v * C + c);
 #pragma unroll
-        for (int ci = 0; ci < MAXCIN; ++ci) wr[c][ci] = ci < p.Cin ? __ldg(p.w + (v * C + c) * p.Cin + ci) : 0.f;
+        for (int ci = 0; ci < CIN; ++ci) wr[c][ci] = __ldg(p.w + (v * C + c) * CIN + ci);
     }
-    float acc[EMB_NG];
+    constexpr int NG = C * CIN + C;
+    float acc[NG];
 #pragma unroll
-    for (int k = 0; k < EMB_NG; ++k) acc[k] = 0.f;
+    for (int k = 0; k < NG; ++k) acc[k] = 0.f;
     const int64_t thw = (int64_t)p.T * p.H * p.W, ntok = (int64_t)p.N * thw;
     for (int64_t tok = (int64_t)blockIdx.x * EMB_THREADS + threadIdx.x; tok < ntok; tok += (int64_t)gridDim.x * EMB_THREADS) {
         int n;
         const int64_t xo = x_offset(p, tok, v, n);
-        float xin[MAXCIN];
+        float xin[CIN];
 #pragma unroll
-        for (int ci = 0; ci < MAXCIN; ++ci) xin[ci] = ci < p.Cin ? __ldg(p.x + xo + ci * p.xs_c) : 0.f;
+        for (int ci = 0; ci < CIN; ++ci) xin[ci] = __ldg(p.x + xo + ci * p.xs_c);
         float e[C], en[C], g[C], ge[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             float a = br[c];
 #pragma unroll
-            for (int ci = 0; ci < MAXCIN; ++ci) a += wr[c][ci] * xin[ci];
+            for (int ci = 0; ci < CIN; ++ci) a += wr[c][ci] * xin[ci];
             e[c] = a;
         }
         const float rstd = ln16(e, en);
@@ -93,22 +95,25 @@ embed_ln_bwd_kernel(EmbP p, const float* __restrict__ gy, float* __restrict__ pa
 #pragma unroll
         for (int c = 0; c < C; ++c) {
 #pragma unroll
-            for (int ci = 0; ci < MAXCIN; ++ci) acc[c * MAXCIN + ci] += ge[c] * xin[ci];
-            acc[C * MAXCIN + c] += ge[c];
+            for (int ci = 0; ci < CIN; ++ci) acc[c * CIN + ci] += ge[c] * xin[ci];
+            acc[C * CIN + c] += ge[c];
         }
     }
-    __shared__ float red[EMB_THREADS / 32][EMB_NG];
+    __shared__ float red[EMB_THREADS / 32][NG];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int k = 0; k < EMB_NG; ++k) {
+    for (int k = 0; k < NG; ++k) {
         const float s = warp_sum(acc[k]);
         if (lane == 0) red[warp][k] = s;
     }
     __syncthreads();
-    if (threadIdx.x < EMB_NG) {
+    if (threadIdx.x < NG) {
         float s = 0.f;
         for (int w = 0; w < EMB_THREADS / 32; ++w) s += red[w][threadIdx.x];
-        partials[((int64_t)v * gridDim.x + blockIdx.x) * EMB_NG + threadIdx.x] = s;
+        // partial layout is the MAXCIN one: weight (c, ci) at c*MAXCIN + ci, bias c at C*MAXCIN + c
+        const int k = threadIdx.x;
+        const int dst = k < C * CIN ? (k / CIN) * MAXCIN + (k % CIN) : C * MAXCIN + (k - C * CIN);
+        partials[((int64_t)v * gridDim.x + blockIdx.x) * EMB_NG + dst] = s;
     }
 }
 
@@ -116,11 +121,12 @@ __global__ void embed_ln_bwd_finalize_kernel(const float* __restrict__ partials,
                                              float* __restrict__ gb) {
     const int v = blockIdx.x, k = threadIdx.x;
     if (k >= EMB_NG) return;
+    if (k < C * MAXCIN && (k % MAXCIN) >= Cin) return;      // slot not produced for this Cin
     double a = 0.0;
     for (int b = 0; b < nblocks; ++b) a += partials[((int64_t)v * nblocks + b) * EMB_NG + k];
     if (k < C * MAXCIN) {
         const int c = k / MAXCIN, ci = k % MAXCIN;
-        if (ci < Cin) gw[(v * C + c) * Cin + ci] = (float)a;
+        gw[(v * C + c) * Cin + ci] = (float)a;
     } else gb[v * C + (k - C * MAXCIN)] = (float)a;
 }
 
@@ -154,7 +160,10 @@ extern "C" int idee_embed_ln_bwd(const float* x, const int64_t* x_strides, const
     if (fill(p, x, x_strides, w, b, N, V, Cin, T, H, W, E)) return 1;
     IDEE_REQUIRE(workspace_bytes >= idee_embed_ln_bwd_workspace_bytes(V), "embed_ln_bwd: workspace too small");
     const int nb = emb_blocks(V);
-    embed_ln_bwd_kernel<<<dim3(nb, V), EMB_THREADS, 0, (cudaStream_t)stream>>>(p, gy, (float*)workspace);
+    if (Cin == 1) embed_ln_bwd_kernel<1><<<dim3(nb, V), EMB_THREADS, 0, (cudaStream_t)stream>>>(p, gy, (float*)workspace);
+    else if (Cin == 2) embed_ln_bwd_kernel<2><<<dim3(nb, V), EMB_THREADS, 0, (cudaStream_t)stream>>>(p, gy, (float*)workspace);
+    else if (Cin == 3) embed_ln_bwd_kernel<3><<<dim3(nb, V), EMB_THREADS, 0, (cudaStream_t)stream>>>(p, gy, (float*)workspace);
+    else embed_ln_bwd_kernel<4><<<dim3(nb, V), EMB_THREADS, 0, (cudaStream_t)stream>>>(p, gy, (float*)workspace);
     IDEE_LAUNCH_CHECK("embed_ln_bwd");
     embed_ln_bwd_finalize_kernel<<<V, 128, 0, (cudaStream_t)stream>>>((const float*)workspace, nb, Cin, gw, gb);
     IDEE_LAUNCH_CHECK("embed_ln_bwd_finalize");

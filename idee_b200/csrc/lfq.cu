@@ -49,7 +49,8 @@ __device__ __forceinline__ void block_reduce_store(double* acc, double* out) {
 __global__ void __launch_bounds__(LFQ_THREADS)
 lfq_fwd_kernel(const float* __restrict__ z, const float* __restrict__ w_in, const float* __restrict__ b_in,
                const float* __restrict__ w_out, const float* __restrict__ b_out, float* __restrict__ zq,
-               long long* __restrict__ indices, double* __restrict__ partials, int64_t ntok, int training, float inv_temp) {
+               long long* __restrict__ indices, float* __restrict__ xq, double* __restrict__ partials, int64_t ntok, int training,
+               float inv_temp) {
     float wi[C], wo[C], bo[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) { wi[c] = __ldg(w_in + c); wo[c] = __ldg(w_out + c); bo[c] = __ldg(b_out + c); }
@@ -64,6 +65,7 @@ lfq_fwd_kernel(const float* __restrict__ z, const float* __restrict__ w_in, cons
         const float q = s > 0.f ? 1.f : -1.f;
         const float x = training ? s + (q - s) : q;
         indices[tok] = x > 0.f ? 1 : 0;
+        if (xq) xq[tok] = x;
         float r[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) r[c] = x * wo[c] + bo[c];
@@ -100,7 +102,7 @@ __global__ void lfq_finalize_kernel(const double* __restrict__ partials, int nbl
 constexpr int LFQ_NG = 3 * C + 1;   // g_w_in[16], g_b_in, g_w_out[16], g_b_out[16]
 
 __global__ void __launch_bounds__(LFQ_THREADS)
-lfq_bwd_kernel(const float* __restrict__ z, const float* __restrict__ gzq, const float* __restrict__ g_aux,
+lfq_bwd_kernel(const float* __restrict__ z, const float* __restrict__ gzq, const float* __restrict__ gxq, const float* __restrict__ g_aux,
                const float* __restrict__ stats, const float* __restrict__ w_in, const float* __restrict__ b_in,
                const float* __restrict__ w_out, float* __restrict__ gz, double* __restrict__ partials, int64_t ntok,
                float lam_commit, float lam_ent, float gamma, float inv_temp) {
@@ -130,6 +132,7 @@ lfq_bwd_kernel(const float* __restrict__ z, const float* __restrict__ gzq, const
         float gs = 0.f;
 #pragma unroll
         for (int c = 0; c < C; ++c) { gs += wo[c] * gr[c]; a_wo[c] += x * gr[c]; a_bo[c] += gr[c]; }
+        if (gxq) gs += __ldg(gxq + tok);        // gradient that reached the quantised scalar x directly (rank-1 consumers of z_q)
         float p0, p1;
         probs(s, inv_temp, p0, p1);
         const float dp1 = 2.f * inv_temp * 2.f * p0 * p1;     // d p1 / d s  (= 400 p0 p1 at inv_temp 100)
@@ -174,14 +177,14 @@ int lfq_blocks(int64_t ntok) {
 extern "C" size_t idee_lfq_workspace_bytes(int64_t ntok) { return sizeof(double) * (size_t)lfq_blocks(ntok) * LFQ_NG; }
 
 extern "C" int idee_lfq_fwd(const float* z, const float* w_in, const float* b_in, const float* w_out, const float* b_out,
-                            float* zq, int64_t* indices, float* stats, int64_t ntok, int dim, int codebook_size, int training,
+                            float* zq, int64_t* indices, float* xq, float* stats, int64_t ntok, int dim, int codebook_size, int training,
                             float inv_temperature, float lambda_commit, float lambda_entropy, float diversity_gamma,
                             void* workspace, size_t workspace_bytes, void* stream) {
     IDEE_REQUIRE(dim == C && codebook_size == 2, "lfq_fwd: only dim=16, codebook_size=2 is built (got %d, %d)", dim, codebook_size);
     IDEE_REQUIRE(workspace_bytes >= idee_lfq_workspace_bytes(ntok), "lfq_fwd: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     const int nb = lfq_blocks(ntok);
-    lfq_fwd_kernel<<<nb, LFQ_THREADS, 0, st>>>(z, w_in, b_in, w_out, b_out, zq, (long long*)indices, (double*)workspace, ntok,
+    lfq_fwd_kernel<<<nb, LFQ_THREADS, 0, st>>>(z, w_in, b_in, w_out, b_out, zq, (long long*)indices, xq, (double*)workspace, ntok,
                                                 training, inv_temperature);
     IDEE_LAUNCH_CHECK("lfq_fwd");
     if (training) {
@@ -191,14 +194,14 @@ extern "C" int idee_lfq_fwd(const float* z, const float* w_in, const float* b_in
     return 0;
 }
 
-extern "C" int idee_lfq_bwd(const float* z, const float* gzq, const float* g_aux, const float* stats, const float* w_in,
+extern "C" int idee_lfq_bwd(const float* z, const float* gzq, const float* gxq, const float* g_aux, const float* stats, const float* w_in,
                             const float* b_in, const float* w_out, float* gz, float* grads, int64_t ntok, float inv_temperature,
                             float lambda_commit, float lambda_entropy, float diversity_gamma, void* workspace,
                             size_t workspace_bytes, void* stream) {
     IDEE_REQUIRE(workspace_bytes >= idee_lfq_workspace_bytes(ntok), "lfq_bwd: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     const int nb = lfq_blocks(ntok);
-    lfq_bwd_kernel<<<nb, LFQ_THREADS, 0, st>>>(z, gzq, g_aux, stats, w_in, b_in, w_out, gz, (double*)workspace, ntok, lambda_commit,
+    lfq_bwd_kernel<<<nb, LFQ_THREADS, 0, st>>>(z, gzq, gxq, g_aux, stats, w_in, b_in, w_out, gz, (double*)workspace, ntok, lambda_commit,
                                                 lambda_entropy, diversity_gamma, inv_temperature);
     IDEE_LAUNCH_CHECK("lfq_bwd");
     lfq_bwd_finalize_kernel<<<1, 64, 0, st>>>((const double*)workspace, nb, grads);

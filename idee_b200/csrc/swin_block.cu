@@ -573,34 +573,43 @@ swin_attn_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gy, 
 }
 
 // ---- second stage: deterministic sum of per-CTA partials into the packed gradient block -------------
-// gparams[v][...] (same packing as params).  One thread per packed element.
+// One CTA per variable: phase 1 sums every partial element over the CTAs (coalesced), phase 2 writes the packed gradient
+// and gathers the bias-table rows from the summed [h][i][j] gradient through rel_index.
 template <int G>
-__global__ void swin_grad_finalize_kernel(const float* __restrict__ part_attn, const float* __restrict__ part_mlp,
-                                          int ncta_attn, int ncta_mlp, const int* __restrict__ rel_index,
-                                          float* __restrict__ gparams, int64_t pstride, int tbl) {
-    const int v = blockIdx.y;
+__global__ void __launch_bounds__(1024)
+swin_grad_finalize_kernel(const float* __restrict__ part_attn, const float* __restrict__ part_mlp,
+                          int ncta_attn, int ncta_mlp, const int* __restrict__ rel_index,
+                          float* __restrict__ gparams, int64_t pstride, int tbl) {
+    constexpr int APS = ATT_PART_W + NH * G * G;
+    __shared__ float sum_attn[APS];
+    __shared__ float sum_mlp[MLP_PART];
+    const int v = blockIdx.x;
     const POff po(tbl);
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= po.total) return;
-    float acc = 0.f;
-    if (e < po.qkv_w) {
-        // rpb table entry (row = e / NH, head = e % NH): gather all (i,j) that index it
-        const int row = e / NH, h = e % NH;
-        const int APS = ATT_PART_W + NH * G * G;
-        for (int ij = 0; ij < G * G; ++ij) {
-            if (rel_index[ij] != row) continue;
-            const float* p = part_attn + (int64_t)v * ncta_attn * APS + ATT_PART_W + h * G * G + ij;
-            for (int c = 0; c < ncta_attn; ++c) acc += p[(int64_t)c * APS];
-        }
-    } else if (e < po.fc1_w) {
-        const int APS = ATT_PART_W + NH * G * G;
-        const float* p = part_attn + (int64_t)v * ncta_attn * APS + (e - po.qkv_w);
+    for (int e = threadIdx.x; e < APS; e += blockDim.x) {
+        const float* p = part_attn + (int64_t)v * ncta_attn * APS + e;
+        float acc = 0.f;
         for (int c = 0; c < ncta_attn; ++c) acc += p[(int64_t)c * APS];
-    } else {
-        const float* p = part_mlp + (int64_t)v * ncta_mlp * MLP_PART + (e - po.fc1_w);
-        for (int c = 0; c < ncta_mlp; ++c) acc += p[(int64_t)c * MLP_PART];
+        sum_attn[e] = acc;
     }
-    gparams[(int64_t)v * pstride + e] = acc;
+    for (int e = threadIdx.x; e < MLP_PART; e += blockDim.x) {
+        const float* p = part_mlp + (int64_t)v * ncta_mlp * MLP_PART + e;
+        float acc = 0.f;
+        for (int c = 0; c < ncta_mlp; ++c) acc += p[(int64_t)c * MLP_PART];
+        sum_mlp[e] = acc;
+    }
+    __syncthreads();
+    float* gp = gparams + (int64_t)v * pstride;
+    for (int e = threadIdx.x; e < po.total; e += blockDim.x) {
+        float val;
+        if (e < po.qkv_w) {                       // table entry (row, head): every (i,j) that indexes it
+            const int row = e / NH, h = e % NH;
+            val = 0.f;
+            for (int ij = 0; ij < G * G; ++ij)
+                if (rel_index[ij] == row) val += sum_attn[ATT_PART_W + h * G * G + ij];
+        } else if (e < po.fc1_w) val = sum_attn[e - po.qkv_w];
+        else val = sum_mlp[e - po.fc1_w];
+        gp[e] = val;
+    }
 }
 
 #include "swin_tc.cuh"
@@ -685,9 +694,7 @@ int launch_bwd(const idee_swin_desc* d, const Geom& g, const float* x, const flo
         IDEE_CUDA(cudaFuncSetAttribute(swin_attn_bwd_tc_kernel<WD, WH, WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn), "swin_attn_bwd(bf16)");
         swin_attn_bwd_tc_kernel<WD, WH, WW><<<dim3(per_v, d->V), TCW * 32, dyn, st>>>(x, gx, gx, params, d->param_stride, rel_index, part_attn, g);
         IDEE_LAUNCH_CHECK("swin_attn_bwd(bf16)");
-        const POff po2(g.tbl);
-        swin_grad_finalize_kernel<G><<<dim3((po2.total + 127) / 128, d->V), 128, 0, st>>>(part_attn, part_mlp, per_v, per_v, rel_index,
-                                                                                        gparams, d->param_stride, g.tbl);
+        swin_grad_finalize_kernel<G><<<d->V, 1024, 0, st>>>(part_attn, part_mlp, per_v, per_v, rel_index, gparams, d->param_stride, g.tbl);
         IDEE_LAUNCH_CHECK("swin_grad_finalize");
         return 0;
     }
@@ -701,9 +708,7 @@ int launch_bwd(const idee_swin_desc* d, const Geom& g, const float* x, const flo
     IDEE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "swin_attn_bwd");
     kern<<<dim3(per_v, d->V), AB_WARPS * 32, smem, st>>>(x, gx, gx, params, d->param_stride, rel_index, part_attn, g);
     IDEE_LAUNCH_CHECK("swin_attn_bwd");
-    const POff po(g.tbl);
-    swin_grad_finalize_kernel<G><<<dim3((po.total + 127) / 128, d->V), 128, 0, st>>>(part_attn, part_mlp, per_v, per_v, rel_index,
-                                                                                   gparams, d->param_stride, g.tbl);
+    swin_grad_finalize_kernel<G><<<d->V, 1024, 0, st>>>(part_attn, part_mlp, per_v, per_v, rel_index, gparams, d->param_stride, g.tbl);
     IDEE_LAUNCH_CHECK("swin_grad_finalize");
     return 0;
 }

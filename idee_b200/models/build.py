@@ -71,5 +71,7 @@ class VQ_model(nn.Module):
         z_q, anomaly, loss_z_q = self.vq(tok.view(N, V * T * H * W, C))  # token order (v,t,h,w) as build.py:150
         z_q = z_q.view(N, V, T, H, W, C).permute(0, 1, 5, 2, 3, 4)      # logical [N,V,C,T,H,W]
         anomaly = anomaly.view(N, V, T, H, W)
-        z, y = self.cls(z_q)
+        # the joint head consumes the rank-1 form of z_q (x * w_out + b_out): identical result, 1/6 of the conv1 work
+        rank1 = (self.vq.last_scalar.view(N, V, T, H, W), self.vq.project_out.weight, self.vq.project_out.bias)
+        z, y = self.cls(z_q, rank1=rank1)
         return z, y, anomaly, z_q, loss_z_q.unsqueeze(0)

@@ -44,9 +44,9 @@ def _channel_last(x: torch.Tensor) -> torch.Tensor:
     return tok if tok.stride(5) == 1 and ops._dense(tok) else tok.contiguous()
 
 
-def _head(tok, wb, drop, groups):
+def _head(tok, wb, drop, groups, first=None):
     (w1, b1), (w2, b2), (w3, b3) = wb
-    h = ops.conv3d_cl(tok, w1, b1, proj=False, relu=True, groups=groups)
+    h = first if first is not None else ops.conv3d_cl(tok, w1, b1, proj=False, relu=True, groups=groups)
     h = drop(h)
     h = ops.conv3d_cl(h, w2, b2, proj=False, relu=True)
     return ops.conv3d_cl(h, w3, b3, proj=False, relu=False)
@@ -92,15 +92,36 @@ class CNN_3D(nn.Module):
         shapes = [(V, d, e, 2, 3, 3), (V, d, d, 2, 3, 3), (V, 1, d, 2, 3, 3)]
         return [(ops.packed(pw, s), ops.packed(pb, (V, s[1]))) for (pw, pb), s in zip(self._packs, shapes)]
 
-    def forward(self, x):
-        """x [N,V,C,T,H,W] -> (z [N,n_classes,H,W], [y_v [N,1,H,W]] * V)"""
+    def _joint_conv1_rank1(self, xq, w_out, b_out):
+        """First conv of the joint head on the rank-1 form of z_q.
+
+        z_q[n,v,c,t,h,w] = x[n,v,t,h,w] * w_out[c] + b_out[c] (LFQ.py:284), so Conv3d(V*C -> dim) over z_q equals a conv over
+        V+1 planes -- the V scalar planes x_v with weights sum_c W[o, v*C+c] w_out[c] and a plane of ones with weights
+        sum_{v,c} W[o, v*C+c] b_out[c] (the ones plane reproduces the zero-padding border exactly).  Same result (fp32
+        rounding aside), 1/6 of the multiply-adds, and +-1 / 1 / 0 inputs are exact in bf16.  The folded weights are built with
+        differentiable torch ops, so gradients reach conv1.weight, project_out.weight and project_out.bias through autograd."""
+        N, V, T, H, W = xq.shape
+        Co, C = self.dim, self.var_embed_dim
+        planes = torch.cat([xq.permute(0, 2, 3, 4, 1), xq.new_ones(N, T, H, W, 1), xq.new_zeros(N, T, H, W, 15 - V)], dim=-1)
+        W5 = self.conv1.weight.view(Co, V, C, 2, 3, 3)
+        Wq = torch.einsum('ovcthw,c->ovthw', W5, w_out.reshape(-1))
+        Wb = torch.einsum('ovcthw,c->othw', W5, b_out.reshape(-1))
+        W16 = torch.cat([Wq, Wb.unsqueeze(1), Wq.new_zeros(Co, 15 - V, 2, 3, 3)], dim=1)
+        return ops.conv3d_cl(planes.unsqueeze(1), W16.unsqueeze(0), self.conv1.bias.unsqueeze(0), proj=False, relu=True)
+
+    def forward(self, x, rank1=None):
+        """x [N,V,C,T,H,W] -> (z [N,n_classes,H,W], [y_v [N,1,H,W]] * V).
+        rank1 (optional): (xq [N,V,T,H,W], w_out [C,1], b_out [C]) with x == xq * w_out + b_out, as produced by LFQ."""
         N, V, C, T, H, W = x.shape
         tok = _channel_last(x)
         # multi-head classifier: all V heads per launch
         yh = _head(tok, self._head_params(), self.drop, groups=1)                 # [N,V,T',H,W,1]
         y = [yh[:, i].permute(0, 4, 1, 2, 3).squeeze(2) for i in range(self.in_var)]
         # joint head over the V*C channels
+        first = None
+        if rank1 is not None and V + 1 <= 16 and C == self.var_embed_dim:
+            first = self._joint_conv1_rank1(*rank1)
         zj = _head(tok, [(c.weight.unsqueeze(0), c.bias.unsqueeze(0)) for c in (self.conv1, self.conv2, self.conv3)],
-                   self.drop, groups=V)                                           # [N,1,T',H,W,1]
+                   self.drop, groups=V, first=first)                              # [N,1,T',H,W,1]
         z = zj[:, 0].permute(0, 4, 1, 2, 3).squeeze(2)
         return z, y

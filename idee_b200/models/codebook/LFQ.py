@@ -82,10 +82,12 @@ class LFQ(nn.Module):
         if is_img_or_video:
             x = x.movedim(1, -1)
         assert x.shape[-1] == self.dim, f'expected dimension of {self.dim} but received {x.shape[-1]}'
-        zq, idx, aux = ops.LFQFn.apply(x, self.project_in.weight, self.project_in.bias, self.project_out.weight,
-                                       self.project_out.bias, self.training, float(inv_temperature),
-                                       float(self.commitment_loss_weight), float(self.entropy_loss_weight),
-                                       float(self.diversity_gamma), self.codebook_size)
+        zq, idx, aux, xq = ops.LFQFn.apply(x, self.project_in.weight, self.project_in.bias, self.project_out.weight,
+                                           self.project_out.bias, self.training, float(inv_temperature),
+                                           float(self.commitment_loss_weight), float(self.entropy_loss_weight),
+                                           float(self.diversity_gamma), self.codebook_size)
+        # the quantised scalar x of the last call (z_q = x * w_out + b_out): lets a consumer use the rank-1 form of z_q
+        self.last_scalar = xq
         if not self.training:
             aux = self.zero
         if is_img_or_video:

@@ -317,7 +317,8 @@ def packed(pack: ParamPack, shape):
 # LFQ
 # ----------------------------------------------------------------------------------------------------------------
 class LFQFn(torch.autograd.Function):
-    """z [..., 16] -> (z_q [..., 16], indices int64 [...], aux scalar).  LFQ.py:183-307."""
+    """z [..., 16] -> (z_q [..., 16], indices int64 [...], aux scalar, xq [...]).  LFQ.py:183-307.
+    xq is the quantised scalar x (+-1, with the straight-through gradient) such that z_q = x * w_out + b_out."""
 
     @staticmethod
     def forward(ctx, z, w_in, b_in, w_out, b_out, training, inv_temp, lam_commit, lam_ent, gamma, codebook_size):
@@ -329,36 +330,38 @@ class LFQFn(torch.autograd.Function):
         ntok = z.numel() // dim
         zq = torch.empty_like(z)
         idx = torch.empty(z.shape[:-1], device=z.device, dtype=torch.int64)
+        xq = torch.empty(z.shape[:-1], device=z.device, dtype=torch.float32)
         stats = torch.zeros(8, device=z.device, dtype=torch.float32)
         nws = lib.idee_lfq_workspace_bytes(ntok)
         ws = L.workspace(nws, z.device)
-        L.run("lfq_fwd" if training else "lfq_fwd_eval", lib.idee_lfq_fwd, z.data_ptr(), w_in.data_ptr(), b_in.data_ptr(), w_out.data_ptr(), b_out.data_ptr(), zq.data_ptr(),
-                                 idx.data_ptr(), stats.data_ptr(), ntok, dim, codebook_size, int(training), inv_temp, lam_commit,
-                                 lam_ent, gamma, ws.data_ptr(), nws, L.stream())
+        L.run("lfq_fwd" if training else "lfq_fwd_eval", lib.idee_lfq_fwd, z.data_ptr(), w_in.data_ptr(), b_in.data_ptr(),
+              w_out.data_ptr(), b_out.data_ptr(), zq.data_ptr(), idx.data_ptr(), xq.data_ptr(), stats.data_ptr(), ntok, dim,
+              codebook_size, int(training), inv_temp, lam_commit, lam_ent, gamma, ws.data_ptr(), nws, L.stream())
         ctx.save_for_backward(z, w_in, b_in, w_out, stats)
         ctx.hyper = (inv_temp, lam_commit, lam_ent, gamma)
         ctx.training = training
         ctx.mark_non_differentiable(idx)
         ctx.set_materialize_grads(False)
-        return zq, idx, stats[0]
+        return zq, idx, stats[0], xq
 
     @staticmethod
-    def backward(ctx, gzq, _gidx, gaux):
+    def backward(ctx, gzq, _gidx, gaux, gxq):
         lib = L.load()
         z, w_in, b_in, w_out, stats = ctx.saved_tensors
         inv_temp, lam_commit, lam_ent, gamma = ctx.hyper
         ntok = z.numel() // z.shape[-1]
         gzq = torch.zeros_like(z) if gzq is None else _f32c(gzq)
         if not ctx.training:
-            gaux = None   # eval mode: aux is a constant 0 and x = q has no gradient path to s
+            gaux, gxq = None, None   # eval mode: aux is a constant 0 and x = q has no gradient path to s
         gaux_t = None if gaux is None else _f32c(gaux).reshape(1)
+        gxq_t = None if gxq is None else _f32c(gxq)
         gz = torch.empty_like(z)
         grads = torch.empty(49, device=z.device, dtype=torch.float32)
         nws = lib.idee_lfq_workspace_bytes(ntok)
         ws = L.workspace(nws, z.device)
-        L.run("lfq_bwd", lib.idee_lfq_bwd, z.data_ptr(), gzq.data_ptr(), L.ptr(gaux_t), stats.data_ptr(), w_in.data_ptr(), b_in.data_ptr(),
-                                 w_out.data_ptr(), gz.data_ptr(), grads.data_ptr(), ntok, inv_temp, lam_commit, lam_ent, gamma,
-                                 ws.data_ptr(), nws, L.stream())
+        L.run("lfq_bwd", lib.idee_lfq_bwd, z.data_ptr(), gzq.data_ptr(), L.ptr(gxq_t), L.ptr(gaux_t), stats.data_ptr(), w_in.data_ptr(),
+              b_in.data_ptr(), w_out.data_ptr(), gz.data_ptr(), grads.data_ptr(), ntok, inv_temp, lam_commit, lam_ent, gamma,
+              ws.data_ptr(), nws, L.stream())
         if not ctx.training:
             # x = q (LFQ.py:229-230): only project_out receives gradient
             gz = torch.zeros_like(z)
