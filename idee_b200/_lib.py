@@ -100,6 +100,15 @@ if PRECISION not in ("fp32", "bf16"):
     raise ValueError("IDEE_B200_PRECISION must be fp32 or bf16")
 
 
+# route the dense 96->96 classifier convs through the tcgen05/TMEM kernel (bf16 mode only)
+UMMA = os.environ.get("IDEE_B200_UMMA", "0") == "1"
+
+
+def set_umma(on: bool) -> None:
+    global UMMA
+    UMMA = bool(on)
+
+
 def set_precision(mode: str) -> None:
     global PRECISION
     if mode not in ("fp32", "bf16"):

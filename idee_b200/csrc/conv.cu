@@ -347,14 +347,14 @@ int launch_gather(const ConvP& p, cudaStream_t st, const char* who) {
 
 }  // namespace
 
-extern "C" size_t idee_conv3d_fwd_workspace_bytes(const idee_conv_desc* d) { return d->precision == 1 ? conv_tc_fwd_workspace_bytes(d) : 0; }
-extern "C" size_t idee_conv3d_dgrad_workspace_bytes(const idee_conv_desc* d) { return d->precision == 1 ? conv_tc_dgrad_workspace_bytes(d) : 0; }
+extern "C" size_t idee_conv3d_fwd_workspace_bytes(const idee_conv_desc* d) { return d->precision >= 1 ? conv_tc_fwd_workspace_bytes(d) : 0; }
+extern "C" size_t idee_conv3d_dgrad_workspace_bytes(const idee_conv_desc* d) { return d->precision >= 1 ? conv_tc_dgrad_workspace_bytes(d) : 0; }
 
 extern "C" int idee_conv3d_fwd(const idee_conv_desc* d, const float* x, const float* w, const float* b, float* y,
                                void* workspace, size_t workspace_bytes, void* stream) {
     if (check_desc(d, "conv3d_fwd")) return 1;
     IDEE_REQUIRE(workspace_bytes >= idee_conv3d_fwd_workspace_bytes(d), "conv3d_fwd: workspace too small");
-    if (d->precision == 1) return conv_tc_fwd(d, x, w, b, y, workspace, (cudaStream_t)stream);
+    if (d->precision >= 1) return conv_tc_fwd(d, x, w, b, y, workspace, (cudaStream_t)stream);
     ConvP p{};
     fill_common(p, d);
     p.in = x; p.out = y; p.w = w; p.bias = b; p.relu_src = nullptr; p.relu = d->relu;
@@ -373,7 +373,7 @@ extern "C" int idee_conv3d_dgrad(const idee_conv_desc* d, const float* gy, const
                                  void* workspace, size_t workspace_bytes, void* stream) {
     if (check_desc(d, "conv3d_dgrad")) return 1;
     IDEE_REQUIRE(workspace_bytes >= idee_conv3d_dgrad_workspace_bytes(d), "conv3d_dgrad: workspace too small");
-    if (d->precision == 1) return conv_tc_dgrad(d, gy, w, relu_src, gx, workspace, (cudaStream_t)stream);
+    if (d->precision >= 1) return conv_tc_dgrad(d, gy, w, relu_src, gx, workspace, (cudaStream_t)stream);
     ConvP p{};
     fill_common(p, d);
     p.in = gy; p.out = gx; p.w = w; p.bias = nullptr; p.relu_src = relu_src; p.relu = relu_src != nullptr;
@@ -388,7 +388,7 @@ extern "C" int idee_conv3d_dgrad(const idee_conv_desc* d, const float* gy, const
 }
 
 extern "C" size_t idee_conv3d_wgrad_workspace_bytes(const idee_conv_desc* d) {
-    if (d->precision == 1) return conv_tc_wgrad_workspace_bytes(d);
+    if (d->precision >= 1) return conv_tc_wgrad_workspace_bytes(d);
     const int n_ic = (d->Cin + 15) / 16, n_oc = (d->Cout + 15) / 16, NT = (d->proj ? 3 : 2) * 9;
     return sizeof(float) * (size_t)d->Vw * n_ic * n_oc * wgrad_splits(d) * (NT * 256 + 16);
 }
@@ -398,7 +398,7 @@ extern "C" int idee_conv3d_wgrad(const idee_conv_desc* d, const float* x, const 
     if (check_desc(d, "conv3d_wgrad")) return 1;
     IDEE_REQUIRE(workspace_bytes >= idee_conv3d_wgrad_workspace_bytes(d), "conv3d_wgrad: workspace too small");
     IDEE_REQUIRE(d->out_cpg * 16 >= d->Cout || d->Cout == 1, "conv3d_wgrad: grouped output layout is not supported");
-    if (d->precision == 1) {
+    if (d->precision >= 1) {
         cudaStream_t st = (cudaStream_t)stream;
         if (conv_tc_wgrad_partials(d, x, gy, (float*)workspace, st)) return 2;
         const int NT = (d->proj ? 3 : 2) * 9;

@@ -672,11 +672,19 @@ int prep(const idee_conv_desc* d, const float* w, uint2* wfrag, const Plan& pl, 
 
 }  // namespace
 
+// tcgen05 / TMEM path for the 96 -> 96 classifier conv (conv_umma.cu)
+bool conv_umma_eligible(const idee_conv_desc* d);
+size_t conv_umma_workspace_bytes();
+int conv_umma_run(const idee_conv_desc* d, int dgrad, const float* in, const float* w, const float* bias, const float* relu_src,
+                  float* out, void* ws, cudaStream_t st);
+
 size_t conv_tc_fwd_workspace_bytes(const idee_conv_desc* d) {
+    if (conv_umma_eligible(d)) return conv_umma_workspace_bytes();
     return make_plan(d->proj ? PROJ_FWD : CLS_FWD, d->Cin, d->Cout, d->Vw).wfrag_bytes;
 }
 
 size_t conv_tc_dgrad_workspace_bytes(const idee_conv_desc* d) {
+    if (conv_umma_eligible(d)) return conv_umma_workspace_bytes();
     size_t b = make_plan(d->proj ? PROJ_DGRAD_PAD : CLS_DGRAD, d->Cout, d->Cin, d->Vw).wfrag_bytes;
     b = (b + 255) / 256 * 256;
     if (d->proj) b += sizeof(float) * (size_t)d->N * d->V * (d->Ti + 2) * (d->Hi + 2) * (d->Wi + 2) * 16;
@@ -684,6 +692,7 @@ size_t conv_tc_dgrad_workspace_bytes(const idee_conv_desc* d) {
 }
 
 int conv_tc_fwd(const idee_conv_desc* d, const float* x, const float* w, const float* b, float* y, void* ws, cudaStream_t st) {
+    if (conv_umma_eligible(d)) return conv_umma_run(d, 0, x, w, b, nullptr, y, ws, st);
     const int mode = d->proj ? PROJ_FWD : CLS_FWD;
     const Plan pl = make_plan(mode, d->Cin, d->Cout, d->Vw);
     if (prep(d, w, (uint2*)ws, pl, 0, st)) return 2;
@@ -699,6 +708,7 @@ int conv_tc_fwd(const idee_conv_desc* d, const float* x, const float* w, const f
 }
 
 int conv_tc_dgrad(const idee_conv_desc* d, const float* gy, const float* w, const float* relu_src, float* gx, void* ws, cudaStream_t st) {
+    if (conv_umma_eligible(d)) return conv_umma_run(d, 1, gy, w, nullptr, relu_src, gx, ws, st);
     const int mode = d->proj ? PROJ_DGRAD_PAD : CLS_DGRAD;
     const Plan pl = make_plan(mode, d->Cout, d->Cin, d->Vw);
     if (prep(d, w, (uint2*)ws, pl, 1, st)) return 2;

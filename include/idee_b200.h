@@ -80,7 +80,8 @@ typedef struct {
     int Ti, Hi, Wi, To, Ho, Wo;
     int proj;               /* 1: 3x3x3 replicate, 0: (2,3,3)/(2,1,1) zero-pad */
     int relu;               /* forward: fuse ReLU into the epilogue */
-    int precision;          /* 0: fp32 CUDA-core exact path; 1: bf16 tensor-core operands, fp32 accumulate (fp32 I/O either way) */
+    int precision;          /* 0: fp32 CUDA-core exact path; 1: bf16 tensor-core operands, fp32 accumulate (fp32 I/O either way);
+                               2: as 1, and the 96->96 classifier conv (forward / data gradient) runs on tcgen05 + TMEM */
     int64_t x_sn, x_sv, x_st, x_sh, x_sw, x_sg; int in_cpg;
     int64_t y_sn, y_sv, y_st, y_sh, y_sw, y_sg; int out_cpg;
 } idee_conv_desc;

@@ -160,6 +160,18 @@ def stage_conv_b():
     _conv_case(True, 16, 16, 2, 2, (8, 40, 52), True, N=1)
 
 
+def stage_conv_umma():
+    """96 -> 96 classifier conv on the tcgen05 / TMEM kernel (bf16 operands) against the oracle."""
+    from idee_b200 import _lib
+    _lib.set_precision("bf16")
+    _lib.set_umma(True)
+    global BF16
+    BF16 = True
+    _conv_case(False, 96, 96, 1, 1, (4, 9, 7), True)
+    _conv_case(False, 96, 96, 1, 1, (4, 40, 52), True, N=2)
+    _conv_case(False, 96, 96, 1, 1, (8, 24, 20), False, N=1)
+
+
 def stage_lfq():
     from idee_b200.models.codebook.LFQ import LFQ
     cfg = O.OracleConfig()
