@@ -51,10 +51,13 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
-    do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    while (!ok) {
+        __nanosleep(64);                      // idle warps must not steal issue slots from the MMA / copy warp
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    } while (!ok);
+    }
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
@@ -94,33 +97,44 @@ __global__ void prep_umma_weights_kernel(const float* __restrict__ w, __nv_bfloa
     }
 }
 
+// Zero-copy operand layout.  The halo of a tile is stored as 3 column-shifted copies ("planes"), one per kw, each with a row
+// pitch of exactly 16 pixels and split into 8-channel (16-byte) chunks:
+//     plane[kw][kt][kc][hh][px]  (16 B each)  =  channels kc*8..kc*8+7 of halo pixel (kt, hh, px + kw)
+// Output pixel m = r*16 + c of the tile reads, for tap (kt,kh,kw), plane[kw][kt][kc][r+kh][c] = linear row kh*16 + m of that
+// plane: exactly the canonical K-major SWIZZLE_NONE layout (8 rows x 16 B core matrices, SBO = 128 B, LBO = HH*16*16 B), so a
+// tap is nothing but a descriptor start address.  No per-tap copies, no CTA-wide barriers inside the K loop.
 template <int MODE>
 __global__ void __launch_bounds__(128, 1)
 conv_umma_kernel(UP p) {
-    constexpr int KTIN = MODE == U_FWD ? 2 : 1;
-    constexpr int NJ = MODE == U_FWD ? 18 : 9;
+    constexpr int NPH = MODE == U_FWD ? 2 : 1;                      // phases = forward kt taps (one input time slice each)
+    constexpr int NB = 6;                                           // weight-tap ring depth
+    constexpr int P_LBO = HH * 16 * 16 + 16;                        // bytes between 8-channel chunks of a plane (+16: the 12
+                                                                    // chunks of a pixel fall into different banks when stored)
+    constexpr int P_BYTES = (CI / 8) * P_LBO;                       // one kw plane
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __nv_bfloat16* halo = reinterpret_cast<__nv_bfloat16*>(smem_raw);                          // [KTIN*HH*HWp][CPH]
-    unsigned char* Abuf = smem_raw + ((KTIN * HH * HWp * CPH * 2 + 1023) / 1024) * 1024;       // 2 x A_BYTES
-    unsigned char* Bbuf = Abuf + 2 * A_BYTES;                                                  // 2 x B_BYTES
-    uint64_t* bars = reinterpret_cast<uint64_t*>(Bbuf + 2 * B_BYTES);                          // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+    unsigned char* planes = smem_raw;                                                          // [3 kw] planes
+    unsigned char* Bbuf = planes + 3 * P_BYTES;                                                // NB x B_BYTES
+    uint64_t* bars = reinterpret_cast<uint64_t*>(Bbuf + NB * B_BYTES);                         // [NB] slot free, [NB] = phase done
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NB + 1);
+    __shared__ __align__(16) float bias_s[CO];           // parameters are only 4-byte aligned (views of a flat buffer)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < CO) bias_s[tid] = p.bias ? p.bias[tid] : 0.f;
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        mbar_init(smem_u32(&bars[0]), 1);
-        mbar_init(smem_u32(&bars[1]), 1);
+#pragma unroll
+        for (int i = 0; i <= NB; ++i) mbar_init(smem_u32(&bars[i]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
-    uint32_t par0 = 0u, par1 = 0u;     // mbarrier phase parity of the two A/B slots
+    uint32_t slot_par = 0u;            // bit i = phase parity of slot barrier i (warp 0 only)
+    uint32_t done_par = 0u;
 
     for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int64_t rr = tile;
@@ -128,85 +142,119 @@ conv_umma_kernel(UP p) {
         const int h0 = (int)(rr % p.tiles_h) * TH; rr /= p.tiles_h;
         const int t = (int)(rr % p.To);
         const int n = (int)(rr / p.To);
-        // ---- halo: fp32 HBM -> bf16 smem, zero padding ----
-        {
-            const float* in_img = p.in + n * p.in_sn;
-            constexpr int V4 = CI / 4, NCOL = HWp * V4, NROW = KTIN * HH, DROW = 128 / NCOL, DCOL = 128 - DROW * NCOL;
-            int row = tid / NCOL, col = tid - row * NCOL;
-            while (row < NROW) {
-                const float* src[4];
-                int dst[4];
+#pragma unroll 1
+        for (int ph = 0; ph < NPH; ++ph) {
+            // ---- halo slice: fp32 HBM -> bf16, written into the three shifted planes (zero padding) ----
+            {
+                const int ti = MODE == U_FWD ? 2 * t + ph : (t >> 1);
+                const float* in_img = p.in + n * p.in_sn + ti * p.in_st;
+                const bool tok = ti < p.Ti;
+                constexpr int V4 = CI / 4, NCOL = HWp * V4, DROW = 128 / NCOL, DCOL = 128 - DROW * NCOL;
+                int row = tid / NCOL, col = tid - row * NCOL;
+                constexpr int DEPTH = 16;          // independent 16-byte loads in flight per thread (1 CTA/SM: registers are free)
+                while (row < HH) {
+                    const float* src[DEPTH];
+                    int dsts[DEPTH];               // packed (row, ww, c4); -1 = none
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    src[u] = nullptr; dst[u] = -1;
-                    if (row < NROW) {
-                        const int kt = row / HH, hh = row - kt * HH;
-                        const int ww = col / V4, c4 = col - ww * V4;
-                        const int ti = MODE == U_FWD ? 2 * t + kt : (t >> 1);
-                        const int hi = h0 + hh - 1, wi = w0 + ww - 1;
-                        const bool ok = ti < p.Ti && hi >= 0 && hi < p.Hi && wi >= 0 && wi < p.Wi;
-                        dst[u] = (row * HWp + ww) * CPH + c4 * 4;
-                        if (ok) src[u] = in_img + ti * p.in_st + hi * p.in_sh + wi * p.in_sw + c4 * 4;
-                        row += DROW; col += DCOL;
-                        if (col >= NCOL) { col -= NCOL; ++row; }
+                    for (int u = 0; u < DEPTH; ++u) {
+                        src[u] = nullptr; dsts[u] = -1;
+                        if (row < HH) {
+                            const int ww = col / V4, c4 = col - ww * V4;
+                            const int hi = h0 + row - 1, wi = w0 + ww - 1;
+                            const bool ok = tok && hi >= 0 && hi < p.Hi && wi >= 0 && wi < p.Wi;
+                            dsts[u] = (row << 16) | (ww << 8) | c4;
+                            if (ok) src[u] = in_img + hi * p.in_sh + wi * p.in_sw + c4 * 4;
+                            row += DROW; col += DCOL;
+                            if (col >= NCOL) { col -= NCOL; ++row; }
+                        }
+                    }
+                    float4 f[DEPTH];
+#pragma unroll
+                    for (int u = 0; u < DEPTH; ++u) f[u] = src[u] ? ldg4(src[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int u = 0; u < DEPTH; ++u) {
+                        if (dsts[u] < 0) continue;
+                        const uint2 v = make_uint2(pack_bf16(f[u].x, f[u].y), pack_bf16(f[u].z, f[u].w));
+                        const int rw = dsts[u] >> 16, ww = (dsts[u] >> 8) & 0xFF, c4 = dsts[u] & 0xFF;
+                        const int kc = c4 >> 1, half = c4 & 1;                  // 8-channel chunk and which 8-byte half of it
+#pragma unroll
+                        for (int kw = 0; kw < 3; ++kw) {
+                            const int px = ww - kw;
+                            if (px >= 0 && px < 16)
+                                *reinterpret_cast<uint2*>(planes + kw * P_BYTES + kc * P_LBO + (rw * 16 + px) * 16 + half * 8) = v;
+                        }
                     }
                 }
-                float4 f[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) f[u] = src[u] ? ldg4(src[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (dst[u] >= 0) *reinterpret_cast<uint2*>(halo + dst[u]) = make_uint2(pack_bf16(f[u].x, f[u].y), pack_bf16(f[u].z, f[u].w));
-            }
-        }
-        __syncthreads();
-        // ---- K loop over taps ----
-        const int pr = tid >> 4, pc = tid & 15;              // this thread's pixel (row, col) inside the tile = TMEM lane tid
-#pragma unroll 1
-        for (int j = 0; j < NJ; ++j) {
-            const int b = j & 1;
-            if (j >= 2) {                                   // MMAs of tap j-2 released slot b
-                mbar_wait(smem_u32(&bars[b]), b ? par1 : par0);
-                if (b) par1 ^= 1u; else par0 ^= 1u;
-            }
-            int kt, kh, kw, ft;
-            if (MODE == U_FWD) { kt = j / 9; kh = (j / 3) % 3; kw = j % 3; ft = j; }
-            else { kt = 0; kh = j / 3; kw = j % 3; ft = (t & 1) * 9 + (2 - kh) * 3 + (2 - kw); }
-            // B tap (18 KB, L2 resident) -> slot b
-            {
-                const uint4* src = reinterpret_cast<const uint4*>(p.wB + (size_t)ft * CO * CI);
-                uint4* dst = reinterpret_cast<uint4*>(Bbuf + b * B_BYTES);
-#pragma unroll
-                for (int i = 0; i < B_BYTES / 16 / 128; ++i) dst[tid + i * 128] = __ldg(src + tid + i * 128);
-            }
-            // A tap: this thread's pixel row (96 channels = 12 x 16 B) -> canonical layout
-            {
-                const uint4* src = reinterpret_cast<const uint4*>(halo + ((kt * HH + pr + kh) * HWp + pc + kw) * CPH);
-                unsigned char* dst = Abuf + b * A_BYTES + (tid >> 3) * SBO + (tid & 7) * 16;
-#pragma unroll
-                for (int kc = 0; kc < CI / 8; ++kc) *reinterpret_cast<uint4*>(dst + kc * A_LBO) = src[kc];
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core
             __syncthreads();
-            if (tid == 0) {
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a0 = smem_u32(Abuf + b * A_BYTES), b0 = smem_u32(Bbuf + b * B_BYTES);
+            // ---- 9 taps: warp 0 streams the weight taps (cp.async ring) and issues the MMAs; no CTA-wide barriers ----
+            if (warp == 0) {
+                auto ftap_of = [&](int j) -> int {
+                    if (MODE == U_FWD) return ph * 9 + j;
+                    return (t & 1) * 9 + (2 - j / 3) * 3 + (2 - j % 3);
+                };
+                auto load_B = [&](int j) {
+                    const uint4* src = reinterpret_cast<const uint4*>(p.wB + (size_t)ftap_of(j) * CO * CI);
+                    unsigned char* dst = Bbuf + (j % NB) * B_BYTES;
+#pragma unroll 4
+                    for (int i = lane; i < B_BYTES / 16; i += 32)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + i * 16)), "l"(src + i) : "memory");
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                };
 #pragma unroll
-                for (int ks = 0; ks < CI / 16; ++ks)
-                    umma_bf16(tmem_base, make_desc(a0 + ks * 2 * A_LBO, A_LBO, SBO), make_desc(b0 + ks * 2 * B_LBO, B_LBO, SBO),
-                              (j > 0 || ks > 0) ? 1u : 0u);
-                umma_commit(smem_u32(&bars[b]));
+                for (int j = 0; j < NB; ++j) load_B(j);                    // every slot is free: the previous phase was drained
+#pragma unroll 1
+                for (int j = 0; j < 9; ++j) {
+                    const int b = j % NB;
+                    // B(j) has landed once at most the younger groups are still pending.  Issued so far: taps 0..NB-1 up front plus
+                    // one refill at the end of each earlier iteration >= 1, i.e. up to tap min(8, max(NB-1, j+NB-2)).
+                    const int newest = min(8, max(NB - 1, j + NB - 2));
+                    const int younger = newest - j;
+                    if (younger >= 5) asm volatile("cp.async.wait_group 5;" ::: "memory");
+                    else if (younger == 4) asm volatile("cp.async.wait_group 4;" ::: "memory");
+                    else if (younger == 3) asm volatile("cp.async.wait_group 3;" ::: "memory");
+                    else if (younger == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
+                    else if (younger == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+                    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const int kh = j / 3, kw = j % 3;
+                        const uint32_t a0 = smem_u32(planes + kw * P_BYTES + kh * 16 * 16);
+                        const uint32_t b0 = smem_u32(Bbuf + b * B_BYTES);
+#pragma unroll
+                        for (int ks = 0; ks < CI / 16; ++ks)
+                            umma_bf16(tmem_base, make_desc(a0 + ks * 2 * P_LBO, P_LBO, SBO), make_desc(b0 + ks * 2 * B_LBO, B_LBO, SBO),
+                                      (ph > 0 || j > 0 || ks > 0) ? 1u : 0u);
+                        umma_commit(smem_u32(&bars[b]));                    // slot b is free when these MMAs have read it
+                        if (j == 8) umma_commit(smem_u32(&bars[NB]));       // ... and this phase's MMAs are complete
+                    }
+                    __syncwarp();
+                    if (j >= 1 && j - 1 + NB < 9) {                         // refill the slot released by tap j-1 (overlaps MMA j)
+                        const int bb = (j - 1) % NB;
+                        mbar_wait(smem_u32(&bars[bb]), (slot_par >> bb) & 1u);
+                        slot_par ^= 1u << bb;
+                        load_B(j - 1 + NB);
+                    }
+                }
+                // consume the slot-barrier phases not waited on inside the loop (taps whose slot was not refilled)
+#pragma unroll 1
+                for (int j = 0; j < 9; ++j) {
+                    if (j + NB < 9) continue;
+                    const int bb = j % NB;
+                    mbar_wait(smem_u32(&bars[bb]), (slot_par >> bb) & 1u);
+                    slot_par ^= 1u << bb;
+                }
             }
+            mbar_wait(smem_u32(&bars[NB]), done_par);                       // every thread: this phase's MMAs are complete
+            done_par ^= 1u;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (ph + 1 < NPH) __syncthreads();                              // planes may be refilled for the next time slice
         }
-        // drain: the last two taps' commits
-#pragma unroll
-        for (int jj = NJ - 2; jj < NJ; ++jj) {
-            const int b = jj & 1;
-            mbar_wait(smem_u32(&bars[b]), b ? par1 : par0);
-            if (b) par1 ^= 1u; else par0 ^= 1u;
-        }
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // ---- epilogue: TMEM lane = pixel, 96 columns = output channels ----
+        const int pr = tid >> 4, pc = tid & 15;
         const int h = h0 + pr, w = w0 + pc;
         const bool pix_ok = h < p.Ho && w < p.Wo;
         float* orow = p.out + n * p.out_sn + t * p.out_st + h * p.out_sh + w * p.out_sw;
@@ -219,7 +267,7 @@ conv_umma_kernel(UP p) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
                     float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                    if (p.bias) { const float4 bb = ldg4(p.bias + c0 + i); o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w; }
+                    { const float4 bb = ld4(bias_s + c0 + i); o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w; }
                     if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
                     if (rrow) {
                         const float4 a = ldg4(rrow + c0 + i);
@@ -230,7 +278,7 @@ conv_umma_kernel(UP p) {
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();                                  // every warp has drained the accumulator and the halo
+        __syncthreads();                                  // every warp has drained the accumulator; planes may be overwritten
     }
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
 }
@@ -267,8 +315,7 @@ int conv_umma_run(const idee_conv_desc* d, int dgrad, const float* in, const flo
     }
     p.tiles_w = (p.Wo + TW - 1) / TW; p.tiles_h = (p.Ho + TH - 1) / TH;
     p.total_tiles = (int64_t)d->N * p.To * p.tiles_h * p.tiles_w;
-    const int KTIN = dgrad ? 1 : 2;
-    const size_t smem = ((size_t)(KTIN * HH * HWp * CPH * 2 + 1023) / 1024) * 1024 + 2 * A_BYTES + 2 * B_BYTES + 64;
+    const size_t smem = (size_t)3 * (CI / 8) * (HH * 16 * 16 + 16) + (size_t)6 * B_BYTES + 128;
     int64_t grid = idee_num_sms();
     if (grid > p.total_tiles) grid = p.total_tiles;
     if (!dgrad) {

@@ -107,3 +107,32 @@ def test_bf16_medium_mask_flips_are_near_ties():
     assert 0.2 < float(want[2].float().mean()) < 0.8
     assert band < TOL * float(z_enc.abs().max()) * float(sd["vq.project_in.weight"].abs().sum())
     assert ties_ok and frac >= 0.98, frac
+
+
+def test_tcgen05_classifier_conv_matches_mma_sync_and_oracle():
+    """The opt-in tcgen05 / TMEM kernel for the 96->96 classifier conv (forward + data gradient) against the mma.sync kernel
+    and the fp32 oracle (torch conv3d on CPU)."""
+    import torch.nn.functional as F
+    from idee_b200 import _lib, ops
+    torch.manual_seed(0)
+    x = torch.randn(2, 1, 4, 20, 28, 96)
+    w = torch.randn(1, 96, 96, 2, 3, 3) * 0.05
+    b = torch.randn(1, 96)
+    g = torch.randn(2, 1, 2, 20, 28, 96)
+    xr = x.clone().requires_grad_(True)
+    want = F.conv3d(xr[:, 0].permute(0, 4, 1, 2, 3), w[0], b[0], stride=(2, 1, 1), padding=(0, 1, 1)).permute(0, 2, 3, 4, 1).unsqueeze(1)
+    (want * g).sum().backward()
+    outs = {}
+    try:
+        for umma in (False, True):
+            _lib.set_umma(umma)
+            xc = x.cuda().requires_grad_(True)
+            y = ops.conv3d_cl(xc, w.cuda(), b.cuda(), False, False)
+            (y * g.cuda()).sum().backward()
+            outs[umma] = (y.detach().cpu(), xc.grad.cpu())
+    finally:
+        _lib.set_umma(False)
+    for umma in (False, True):
+        assert rel_err(outs[umma][0], want) < TOL
+        assert rel_err(outs[umma][1], xr.grad) < TOL
+    assert rel_err(outs[True][0], outs[False][0]) < 2e-3          # same bf16 operands, different accumulation order
