@@ -34,7 +34,7 @@ class Layer_v(nn.Module):
         """x [N,C,T,H,W] -> [N,n_classes,H,W]"""
         tok = _channel_last(x.unsqueeze(1))
         out = _head(tok, [(c.weight.unsqueeze(0), c.bias.unsqueeze(0)) for c in (self.conv1, self.conv2, self.conv3)],
-                    self.drop, groups=1)
+                    self.drop, groups=1, fuse1=self.drop_rate == 0 or not self.training)
         return out[:, 0].permute(0, 4, 1, 2, 3).squeeze(2)
 
 
@@ -44,12 +44,14 @@ def _channel_last(x: torch.Tensor) -> torch.Tensor:
     return tok if tok.stride(5) == 1 and ops._dense(tok) else tok.contiguous()
 
 
-def _head(tok, wb, drop, groups, first=None):
+def _head(tok, wb, drop, groups, first=None, fuse1=True):
+    """conv1 -> ReLU -> Dropout -> conv2 -> ReLU -> conv3.  Each ReLU output has exactly one consumer, so the ReLU backward
+    masks are applied in the consumers' data-gradient epilogues (fuse1 is False when an active Dropout sits in between)."""
     (w1, b1), (w2, b2), (w3, b3) = wb
-    h = first if first is not None else ops.conv3d_cl(tok, w1, b1, proj=False, relu=True, groups=groups)
+    h = first if first is not None else ops.conv3d_cl(tok, w1, b1, proj=False, relu=True, groups=groups, consumer_masks=fuse1)
     h = drop(h)
-    h = ops.conv3d_cl(h, w2, b2, proj=False, relu=True)
-    return ops.conv3d_cl(h, w3, b3, proj=False, relu=False)
+    h = ops.conv3d_cl(h, w2, b2, proj=False, relu=True, input_is_relu=fuse1, consumer_masks=True)
+    return ops.conv3d_cl(h, w3, b3, proj=False, relu=False, input_is_relu=True)
 
 
 class CNN_3D(nn.Module):
@@ -107,7 +109,12 @@ class CNN_3D(nn.Module):
         Wq = torch.einsum('ovcthw,c->ovthw', W5, w_out.reshape(-1))
         Wb = torch.einsum('ovcthw,c->othw', W5, b_out.reshape(-1))
         W16 = torch.cat([Wq, Wb.unsqueeze(1), Wq.new_zeros(Co, 15 - V, 2, 3, 3)], dim=1)
-        return ops.conv3d_cl(planes.unsqueeze(1), W16.unsqueeze(0), self.conv1.bias.unsqueeze(0), proj=False, relu=True)
+        return ops.conv3d_cl(planes.unsqueeze(1), W16.unsqueeze(0), self.conv1.bias.unsqueeze(0), proj=False, relu=True,
+                             consumer_masks=self._fuse1())
+
+    def _fuse1(self) -> bool:
+        """conv2 may apply conv1's ReLU mask only when the Dropout between them is the identity."""
+        return self.drop_rate == 0 or not self.training
 
     def forward(self, x, rank1=None):
         """x [N,V,C,T,H,W] -> (z [N,n_classes,H,W], [y_v [N,1,H,W]] * V).
@@ -115,13 +122,13 @@ class CNN_3D(nn.Module):
         N, V, C, T, H, W = x.shape
         tok = _channel_last(x)
         # multi-head classifier: all V heads per launch
-        yh = _head(tok, self._head_params(), self.drop, groups=1)                 # [N,V,T',H,W,1]
+        yh = _head(tok, self._head_params(), self.drop, groups=1, fuse1=self._fuse1())   # [N,V,T',H,W,1]
         y = [yh[:, i].permute(0, 4, 1, 2, 3).squeeze(2) for i in range(self.in_var)]
         # joint head over the V*C channels
         first = None
         if rank1 is not None and V + 1 <= 16 and C == self.var_embed_dim:
             first = self._joint_conv1_rank1(*rank1)
         zj = _head(tok, [(c.weight.unsqueeze(0), c.bias.unsqueeze(0)) for c in (self.conv1, self.conv2, self.conv3)],
-                   self.drop, groups=V, first=first)                              # [N,1,T',H,W,1]
+                   self.drop, groups=V, first=first, fuse1=self._fuse1())         # [N,1,T',H,W,1]
         z = zj[:, 0].permute(0, 4, 1, 2, 3).squeeze(2)
         return z, y

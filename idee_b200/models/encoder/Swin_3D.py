@@ -260,8 +260,10 @@ class Swin_3D(nn.Module):
             tok = ops.swin_block(tok, pack, idx, ws, ss, rows, scale, heads, hidden)
         w0, b0 = ops.packed(pk["proj0_w"], (V, E, E, 3, 3, 3)), ops.packed(pk["proj0_b"], (V, E))
         w2, b2 = ops.packed(pk["proj2_w"], (V, E, E, 3, 3, 3)), ops.packed(pk["proj2_b"], (V, E))
-        tok = ops.conv3d_cl(tok, w0, b0, proj=True, relu=True)
-        tok = ops.conv3d_cl(tok, w2, b2, proj=True, relu=False)
+        # conv -> ReLU -> conv: the second conv is the only consumer of the ReLU output, so its data-gradient epilogue applies
+        # the ReLU backward mask and the first conv skips the separate pass
+        tok = ops.conv3d_cl(tok, w0, b0, proj=True, relu=True, consumer_masks=True)
+        tok = ops.conv3d_cl(tok, w2, b2, proj=True, relu=False, input_is_relu=True)
         return tok
 
     def forward(self, x):

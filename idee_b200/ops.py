@@ -213,7 +213,10 @@ class Conv3dCL(torch.autograd.Function):
     (joint classifier head over the V planes of z_q).  Output [N,Vimg,To,Ho,Wo,Cout] contiguous."""
 
     @staticmethod
-    def forward(ctx, x, w, b, proj, relu, groups):
+    def forward(ctx, x, w, b, proj, relu, groups, input_is_relu=False, consumer_masks=False):
+        """input_is_relu: x is the fused-ReLU output of a conv whose ONLY consumer is this op -> this op's data gradient is
+        multiplied by (x > 0) in the kernel epilogue.  consumer_masks: the (only) consumer of this op's ReLU output does
+        exactly that, so the incoming gradient is already masked and no separate ReLU-backward pass is needed."""
         L.require_cuda(x, w)
         lib = L.load()
         if x.dtype != torch.float32:
@@ -242,6 +245,7 @@ class Conv3dCL(torch.autograd.Function):
               b.data_ptr(), y.data_ptr(), ws.data_ptr(), nws, L.stream(), tag=_conv_tag(d))
         ctx.save_for_backward(x, w, y if relu else None)
         ctx.desc, ctx.relu, ctx.groups = d, relu, groups
+        ctx.input_is_relu, ctx.consumer_masks = bool(input_is_relu), bool(consumer_masks)
         ctx.grad_dst = (getattr(w, "_idee_grad_dst", None), getattr(b, "_idee_grad_dst", None))
         return y
 
@@ -251,7 +255,7 @@ class Conv3dCL(torch.autograd.Function):
         x, w, y = ctx.saved_tensors
         d = ctx.desc
         gy = _f32c(gy)
-        if ctx.relu:
+        if ctx.relu and not ctx.consumer_masks:
             gy = torch.ops.aten.threshold_backward(gy, y, 0.0)
         gw_dst, gb_dst = ctx.grad_dst
         gw = gw_dst if gw_dst is not None and gw_dst.shape == w.shape else torch.empty_like(w)
@@ -268,9 +272,10 @@ class Conv3dCL(torch.autograd.Function):
                 raise RuntimeError("conv3d_dgrad: input must be a dense channel-last tensor")
             nws = lib.idee_conv3d_dgrad_workspace_bytes(C.byref(d))
             ws = L.workspace(nws, x.device)
+            relu_src = x.data_ptr() if ctx.input_is_relu else None       # dL/d(pre-activation) = dL/dx * (x > 0), fused
             L.run("conv3d_dgrad_bf16" if d.precision else "conv3d_dgrad", lib.idee_conv3d_dgrad, C.byref(d), gy.data_ptr(),
-                  w.data_ptr(), None, gx.data_ptr(), ws.data_ptr(), nws, L.stream(), tag=_conv_tag(d))
-        return gx, gw, gb, None, None, None
+                  w.data_ptr(), relu_src, gx.data_ptr(), ws.data_ptr(), nws, L.stream(), tag=_conv_tag(d))
+        return gx, gw, gb, None, None, None, None, None
 
 
 def _conv_tag(d) -> str:
@@ -288,8 +293,8 @@ def _dense(t: torch.Tensor) -> bool:
     return True
 
 
-def conv3d_cl(x, w, b, proj: bool, relu: bool, groups: int = 1):
-    return Conv3dCL.apply(x, w, b, bool(proj), bool(relu), int(groups))
+def conv3d_cl(x, w, b, proj: bool, relu: bool, groups: int = 1, input_is_relu: bool = False, consumer_masks: bool = False):
+    return Conv3dCL.apply(x, w, b, bool(proj), bool(relu), int(groups), bool(input_is_relu), bool(consumer_masks))
 
 
 class PackedWB(torch.autograd.Function):
