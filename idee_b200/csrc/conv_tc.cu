@@ -256,6 +256,8 @@ conv_tc_kernel(P p) {
     }
 }
 
+constexpr int C16_THREADS = 128;     // 4 warps per CTA, two tile rows (m-tiles) per warp (8 warps measured slower)
+
 // ------------------------------------------------------------------------------------------------------------------
 // 16-input-channel convs (proj_var, per-variable classifier heads, and their data gradients): persistent, pipelined.
 // A CTA loads the weights once, then walks tiles:  wait(stage i) -> convert fp32 stage -> bf16 halo -> issue cp.async for
@@ -263,55 +265,81 @@ conv_tc_kernel(P p) {
 // of the next tile is hidden behind the tensor-core phase of the current one; taps are fully unrolled.
 // ------------------------------------------------------------------------------------------------------------------
 template <int MODE, int NTL>
-__global__ void __launch_bounds__(128)
-conv_tc16_kernel(P p, int64_t total_tiles, int tiles_h) {
-    constexpr int CP = 24;
+__global__ void __launch_bounds__(C16_THREADS)
+conv_tc16_kernel(P p, int64_t total_tiles64, int tiles_h) {
+    constexpr int CP = 24, NTH = C16_THREADS, MT = 8 / (NTH / 32);   // m-tiles (tile rows of 16 pixels) per warp
     constexpr int KTIN = (MODE == CLS_FWD) ? 2 : (MODE == CLS_DGRAD ? 1 : 3);
     constexpr int NJ = (MODE == CLS_FWD) ? 18 : (MODE == CLS_DGRAD ? 9 : 27);
     constexpr int NTF = (MODE == CLS_FWD || MODE == CLS_DGRAD) ? 18 : 27;
     constexpr int WTAP = NTL * 32, NPIX = KTIN * HH * HW_;
+    constexpr int NCOL = HW_ * 4, TOTAL = KTIN * HH * NCOL, NEL = (TOTAL + NTH - 1) / NTH;   // 16-byte halo elements
+    constexpr int OT = (MODE == PROJ_FWD) ? -1 : (MODE == PROJ_DGRAD_PAD ? -2 : 0);          // halo origin relative to the tile
+    constexpr int OHW = (MODE == PROJ_DGRAD_PAD) ? -2 : -1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint2* wsm = reinterpret_cast<uint2*>(smem_raw);                                     // [NTF][WTAP]
     float* stage = reinterpret_cast<float*>(smem_raw + sizeof(uint2) * NTF * WTAP);      // [NPIX][16] fp32
     __nv_bfloat16* halo = reinterpret_cast<__nv_bfloat16*>(stage + NPIX * 16);           // [NPIX][CP] bf16
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t total_tiles = (uint32_t)total_tiles64;
 
-    auto decode = [&](int64_t tile, int& n, int& v, int& t, int& h0, int& w0) {
-        int64_t r = tile;
-        w0 = (int)(r % p.tiles_w) * TW; r /= p.tiles_w;
-        h0 = (int)(r % tiles_h) * TH; r /= tiles_h;
-        t = (int)(r % p.To); r /= p.To;
-        v = (int)(r % p.V); n = (int)(r / p.V);
+    // Per-thread constants: the halo elements a thread fetches are the same for every tile, so their source offsets
+    // relative to the halo origin are computed once (32-bit), leaving one 64-bit add per element on interior tiles.
+    int rel_src[NEL];
+#pragma unroll
+    for (int i = 0; i < NEL; ++i) {
+        const int e = tid + i * NTH, row = e / NCOL, col = e - row * NCOL;
+        const int kt = row / HH, hh = row - kt * HH, ww = col >> 2, c4 = col & 3;
+        rel_src[i] = (int)(kt * p.in_st + hh * p.in_sh + ww * p.in_sw) + c4 * 4;
+    }
+    // epilogue offsets of this thread's 2*MT (row, half) output pixels relative to the tile origin
+    int rel_out[MT][2];
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) rel_out[m][hf] = (int)((warp * MT + m) * p.out_sh + (lane / 4 + hf * 8) * p.out_sw) + (lane % 4) * 2;
+
+    auto decode = [&](uint32_t tile, int& n, int& v, int& t, int& h0, int& w0) {
+        uint32_t r = tile;                                       // 32-bit: tw fastest, then th, t, v, n
+        uint32_t q = r / (uint32_t)p.tiles_w; w0 = (int)(r - q * p.tiles_w) * TW; r = q;
+        q = r / (uint32_t)tiles_h; h0 = (int)(r - q * tiles_h) * TH; r = q;
+        q = r / (uint32_t)p.To; t = (int)(r - q * p.To); r = q;
+        q = r / (uint32_t)p.V; v = (int)(r - q * p.V); n = (int)q;
     };
-    auto issue = [&](int64_t tile) {
+    auto issue = [&](uint32_t tile) {
         int n, v, t, h0, w0;
         decode(tile, n, v, t, h0, w0);
         const float* in_img = p.in + n * p.in_sn + v * p.in_sv;
-        constexpr int NCOL = HW_ * 4, NROW = KTIN * HH, DROW = 128 / NCOL, DCOL = 128 - DROW * NCOL;
-        int row = tid / NCOL, col = tid - row * NCOL;
-        while (row < NROW) {
-            const int kt = row / HH, hh = row - kt * HH;
-            const int ww = col >> 2, c4 = col & 3;
-            int ti, hi = h0 + hh - 1, wi = w0 + ww - 1;
-            bool ok = true;
-            if (MODE == CLS_FWD) { ti = 2 * t + kt; ok = hi >= 0 && hi < p.Hi && wi >= 0 && wi < p.Wi; }
-            else if (MODE == PROJ_FWD) { ti = min(max(t + kt - 1, 0), p.Ti - 1); hi = min(max(hi, 0), p.Hi - 1); wi = min(max(wi, 0), p.Wi - 1); }
-            else if (MODE == CLS_DGRAD) { ti = t >> 1; ok = ti < p.Ti && hi >= 0 && hi < p.Hi && wi >= 0 && wi < p.Wi; }
-            else { ti = t + kt - 2; hi -= 1; wi -= 1; ok = ti >= 0 && ti < p.Ti && hi >= 0 && hi < p.Hi && wi >= 0 && wi < p.Wi; }
-            const float* src = ok ? in_img + ti * p.in_st + hi * p.in_sh + wi * p.in_sw + c4 * 4 : p.in;
-            cp_async16_zfill(stage + (row * HW_ + ww) * 16 + c4 * 4, src, ok ? 16 : 0);
-            row += DROW; col += DCOL;
-            if (col >= NCOL) { col -= NCOL; ++row; }
+        const int tb = (MODE == CLS_FWD) ? 2 * t : (MODE == CLS_DGRAD ? (t >> 1) : t);
+        const int t_lo = tb + OT, h_lo = h0 + OHW, w_lo = w0 + OHW;      // halo origin
+        const bool interior = t_lo >= 0 && t_lo + KTIN - 1 < p.Ti && h_lo >= 0 && h_lo + HH - 1 < p.Hi && w_lo >= 0 && w_lo + HW_ - 1 < p.Wi;
+        if (interior) {
+            const float* base = in_img + t_lo * p.in_st + h_lo * p.in_sh + w_lo * p.in_sw;
+#pragma unroll
+            for (int i = 0; i < NEL; ++i) {
+                const int e = tid + i * NTH;
+                if (e < TOTAL) cp_async16_zfill(stage + e * 4, base + rel_src[i], 16);
+            }
+        } else {
+#pragma unroll 1
+            for (int e = tid; e < TOTAL; e += NTH) {
+                const int row = e / NCOL, col = e - row * NCOL;
+                const int kt = row / HH, hh = row - kt * HH, ww = col >> 2, c4 = col & 3;
+                int ti = t_lo + kt, hi = h_lo + hh, wi = w_lo + ww;
+                bool ok = true;
+                if (MODE == PROJ_FWD) { ti = min(max(ti, 0), p.Ti - 1); hi = min(max(hi, 0), p.Hi - 1); wi = min(max(wi, 0), p.Wi - 1); }
+                else ok = ti >= 0 && ti < p.Ti && hi >= 0 && hi < p.Hi && wi >= 0 && wi < p.Wi;
+                const float* src = ok ? in_img + ti * p.in_st + hi * p.in_sh + wi * p.in_sw + c4 * 4 : p.in;
+                cp_async16_zfill(stage + e * 4, src, ok ? 16 : 0);
+            }
         }
         cp_async_commit();
     };
 
-    const int64_t first = blockIdx.x;
+    const uint32_t first = blockIdx.x;
     if (first < total_tiles) issue(first);
-    // weights of this CTA's weight set(s): with Vw > 1 the set changes with v, so reload when v changes (rare: tiles are v-major)
     int cur_wset = -1;
     const int a_pix = (lane & 7) + ((lane >> 3) & 1) * 8, a_koff = (lane >> 4) * 8;
-    for (int64_t tile = first; tile < total_tiles; tile += gridDim.x) {
+    for (uint32_t tile = first; tile < total_tiles; tile += gridDim.x) {
         int n, v, t, h0, w0;
         decode(tile, n, v, t, h0, w0);
         const int wset = p.Vw == 1 ? 0 : v;
@@ -319,62 +347,70 @@ conv_tc16_kernel(P p, int64_t total_tiles, int tiles_h) {
         __syncthreads();                                   // stage(tile) landed; every warp is done with the previous halo/weights
         if (wset != cur_wset) {
             const uint2* wf = p.wfrag + (int64_t)wset * NTF * WTAP;
-            for (int e = tid; e < NTF * WTAP; e += 128) wsm[e] = wf[e];
+            for (int e = tid; e < NTF * WTAP; e += NTH) wsm[e] = wf[e];
             cur_wset = wset;
         }
-        for (int e = tid; e < NPIX * 4; e += 128) {        // fp32 stage -> bf16 halo (padded pixel stride)
-            const float4 f = ld4(stage + e * 4);
-            *reinterpret_cast<uint2*>(halo + (e >> 2) * CP + (e & 3) * 4) = make_uint2(pack_bf16(f.x, f.y), pack_bf16(f.z, f.w));
+#pragma unroll
+        for (int i = 0; i < (NPIX * 4 + NTH - 1) / NTH; ++i) {   // fp32 stage -> bf16 halo (padded pixel stride)
+            const int e = tid + i * NTH;
+            if (e < NPIX * 4) {
+                const float4 f = ld4(stage + e * 4);
+                *reinterpret_cast<uint2*>(halo + (e >> 2) * CP + (e & 3) * 4) = make_uint2(pack_bf16(f.x, f.y), pack_bf16(f.z, f.w));
+            }
         }
         __syncthreads();
         if (tile + gridDim.x < total_tiles) issue(tile + gridDim.x);
 
-        float acc[2][NTL][4];
+        float acc[MT][NTL][4];
 #pragma unroll
-        for (int m = 0; m < 2; ++m)
+        for (int m = 0; m < MT; ++m)
 #pragma unroll
             for (int nt = 0; nt < NTL; ++nt) acc[m][nt][0] = acc[m][nt][1] = acc[m][nt][2] = acc[m][nt][3] = 0.f;
-        const __nv_bfloat16* abase = halo + ((warp * 2) * HW_ + a_pix) * CP + a_koff;
+        const __nv_bfloat16* abase = halo + ((warp * MT) * HW_ + a_pix) * CP + a_koff;
         const uint2* wpar = wsm + ((MODE == CLS_DGRAD) ? (t & 1) * 9 * WTAP : 0) + lane;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
-            constexpr int dummy = 0; (void)dummy;
             const int kt = (MODE == CLS_DGRAD) ? 0 : j / 9, kh = (MODE == CLS_DGRAD) ? j / 3 : (j / 3) % 3, kw = j % 3;
             const int ft = (MODE == CLS_FWD || MODE == PROJ_FWD) ? j
                          : (MODE == CLS_DGRAD ? (2 - kh) * 3 + (2 - kw) : (2 - kt) * 9 + (2 - kh) * 3 + (2 - kw));
-            uint32_t a0[4], a1[4];
-            ldsm_x4(a0, abase + ((kt * HH + kh) * HW_ + kw) * CP);
-            ldsm_x4(a1, abase + ((kt * HH + kh + 1) * HW_ + kw) * CP);
+            uint32_t af[MT][4];
+#pragma unroll
+            for (int m = 0; m < MT; ++m) ldsm_x4(af[m], abase + ((kt * HH + kh + m) * HW_ + kw) * CP);
 #pragma unroll
             for (int nt = 0; nt < NTL; ++nt) {
                 const uint2 b = wpar[ft * WTAP + nt * 32];
-                mma_bf16(acc[0][nt], a0, b.x, b.y);
-                mma_bf16(acc[1][nt], a1, b.x, b.y);
+#pragma unroll
+                for (int m = 0; m < MT; ++m) mma_bf16(acc[m][nt], af[m], b.x, b.y);
             }
         }
         // epilogue
         const float* B = p.bias ? p.bias + (int64_t)wset * p.CO : nullptr;
-        float* out_img = p.out + n * p.out_sn + v * p.out_sv + t * p.out_st;
-        const float* rs_img = p.relu_src ? p.relu_src + n * p.out_sn + v * p.out_sv + t * p.out_st : nullptr;
+        const int64_t tile_off = n * p.out_sn + v * p.out_sv + t * p.out_st + h0 * p.out_sh + w0 * p.out_sw;
+        float* out_tile = p.out + tile_off;
+        const float* rs_tile = p.relu_src ? p.relu_src + tile_off : nullptr;
+        float bias0[NTL], bias1[NTL];
 #pragma unroll
-        for (int m = 0; m < 2; ++m) {
-            const int h = h0 + warp * 2 + m;
-            if (h >= p.Ho) continue;
+        for (int nt = 0; nt < NTL; ++nt) {
+            const int co = nt * 8 + (lane % 4) * 2;
+            bias0[nt] = (B && co < p.CO) ? B[co] : 0.f;
+            bias1[nt] = (B && co + 1 < p.CO) ? B[co + 1] : 0.f;
+        }
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+            if (h0 + warp * MT + m >= p.Ho) continue;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-                const int w = w0 + lane / 4 + half * 8;
-                if (w >= p.Wo) continue;
+                if (w0 + lane / 4 + half * 8 >= p.Wo) continue;
 #pragma unroll
                 for (int nt = 0; nt < NTL; ++nt) {
                     const int co = nt * 8 + (lane % 4) * 2;
                     if (co >= p.CO) continue;
-                    const int64_t o = h * p.out_sh + w * p.out_sw + co;
-                    float v0 = acc[m][nt][half * 2], v1 = acc[m][nt][half * 2 + 1];
-                    if (B) { v0 += B[co]; if (co + 1 < p.CO) v1 += B[co + 1]; }
+                    const int o = rel_out[m][half] + nt * 8;
+                    float v0 = acc[m][nt][half * 2] + bias0[nt], v1 = acc[m][nt][half * 2 + 1] + bias1[nt];
                     if (p.relu && MODE <= PROJ_FWD) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-                    if (rs_img) { if (!(rs_img[o] > 0.f)) v0 = 0.f; if (co + 1 < p.CO && !(rs_img[o + 1] > 0.f)) v1 = 0.f; }
-                    if (co + 1 < p.CO) *reinterpret_cast<float2*>(out_img + o) = make_float2(v0, v1);
-                    else out_img[o] = v0;
+                    if (rs_tile) { if (!(rs_tile[o] > 0.f)) v0 = 0.f; if (co + 1 < p.CO && !(rs_tile[o + 1] > 0.f)) v1 = 0.f; }
+                    if (co + 1 < p.CO) *reinterpret_cast<float2*>(out_tile + o) = make_float2(v0, v1);
+                    else out_tile[o] = v0;
                 }
             }
         }
@@ -469,41 +505,74 @@ wgrad_tc_kernel(WP p) {
         const int ft = warp + 4 * i, kt = ft / 9, kh = (ft / 3) % 3, kw = ft % 3;
         a_off[i] = (((kt * HH + kh) * HW_ + kw) + a_pix) * CPA + a_coff;
     }
-    auto decode = [&](int64_t tile, int& n, int& v, int& t, int& h0, int& w0) {
-        int64_t r = tile;                          // t fastest: consecutive tiles of a CTA share input t-slices (L1/L2 hits)
-        t = (int)(r % p.To); r /= p.To;
-        w0 = (int)(r % p.tiles_w) * TW; r /= p.tiles_w;
-        h0 = (int)(r % p.tiles_h) * TH;
-        const int64_t img = r / p.tiles_h;
-        n = (int)(img / imgs_per_n); v = p.Vw == 1 ? (int)(img % imgs_per_n) : wset;
+    constexpr int NCOLA = HW_ * 4, TOTALA = KTIN * HH * NCOLA, NELA = (TOTALA + 127) / 128;
+    constexpr int TOTALG = TH * TW * (NC / 4), NELG = (TOTALG + 127) / 128;
+    // tile-independent relative offsets of the elements this thread fetches (32-bit), see conv_tc16_kernel
+    int rel_a[NELA], rel_g[NELG];
+#pragma unroll
+    for (int i = 0; i < NELA; ++i) {
+        const int e = tid + i * 128, row = e / NCOLA, col = e - row * NCOLA;
+        const int kt = row / HH, hh = row - kt * HH, ww = col >> 2, c4 = col & 3;
+        rel_a[i] = (int)(kt * p.in_st + hh * p.in_sh + ww * p.in_sw) + c4 * 4;
+    }
+#pragma unroll
+    for (int i = 0; i < NELG; ++i) {
+        const int e = tid + i * 128, c4 = e % (NC / 4), pix = e / (NC / 4);
+        rel_g[i] = (int)((pix / TW) * p.go_sh + (pix % TW) * p.go_sw) + occ * NC + c4 * 4;
+    }
+    const bool g_full = occ * NC + NC <= p.FCO;             // every channel of this output chunk exists
+    auto decode = [&](int64_t tile64, int& n, int& v, int& t, int& h0, int& w0) {
+        uint32_t r = (uint32_t)tile64;             // t fastest: consecutive tiles of a CTA share input t-slices (L1/L2 hits)
+        uint32_t q = r / (uint32_t)p.To; t = (int)(r - q * p.To); r = q;
+        q = r / (uint32_t)p.tiles_w; w0 = (int)(r - q * p.tiles_w) * TW; r = q;
+        q = r / (uint32_t)p.tiles_h; h0 = (int)(r - q * p.tiles_h) * TH;
+        const uint32_t img = q;
+        n = (int)(img / (uint32_t)imgs_per_n); v = p.Vw == 1 ? (int)(img % (uint32_t)imgs_per_n) : wset;
     };
     auto issue = [&](int64_t tile) {
         int n, v, t, h0, w0;
         decode(tile, n, v, t, h0, w0);
         const float* in_img = p.in + n * p.in_sn + v * p.in_sv + coff;
-        constexpr int NCOL = HW_ * 4, NROW = KTIN * HH, DROW = 128 / NCOL, DCOL = 128 - DROW * NCOL;
-        int row = tid / NCOL, col = tid - row * NCOL;
-        while (row < NROW) {
-            const int kt = row / HH, hh = row - kt * HH;
-            const int ww = col >> 2, c4 = col & 3;
-            int ti, hi = h0 + hh - 1, wi = w0 + ww - 1;
-            bool ok = true;
-            if (p.proj) { ti = min(max(t + kt - 1, 0), p.Ti - 1); hi = min(max(hi, 0), p.Hi - 1); wi = min(max(wi, 0), p.Wi - 1); }
-            else { ti = 2 * t + kt; ok = hi >= 0 && hi < p.Hi && wi >= 0 && wi < p.Wi; }
-            const float* src = ok ? in_img + ti * p.in_st + hi * p.in_sh + wi * p.in_sw + c4 * 4 : p.in;
-            cp_async16_zfill(stageA + (row * HW_ + ww) * 16 + c4 * 4, src, ok ? 16 : 0);
-            row += DROW; col += DCOL;
-            if (col >= NCOL) { col -= NCOL; ++row; }
+        const int t_lo = p.proj ? t - 1 : 2 * t, h_lo = h0 - 1, w_lo = w0 - 1;
+        const bool interior = t_lo >= 0 && t_lo + KTIN - 1 < p.Ti && h_lo >= 0 && h_lo + HH - 1 < p.Hi && w_lo >= 0 && w_lo + HW_ - 1 < p.Wi;
+        if (interior) {
+            const float* base = in_img + t_lo * p.in_st + h_lo * p.in_sh + w_lo * p.in_sw;
+#pragma unroll
+            for (int i = 0; i < NELA; ++i) {
+                const int e = tid + i * 128;
+                if (e < TOTALA) cp_async16_zfill(stageA + e * 4, base + rel_a[i], 16);
+            }
+        } else {
+#pragma unroll 1
+            for (int e = tid; e < TOTALA; e += 128) {
+                const int row = e / NCOLA, col = e - row * NCOLA;
+                const int kt = row / HH, hh = row - kt * HH, ww = col >> 2, c4 = col & 3;
+                int ti = t_lo + kt, hi = h_lo + hh, wi = w_lo + ww;
+                bool ok = true;
+                if (p.proj) { ti = min(max(ti, 0), p.Ti - 1); hi = min(max(hi, 0), p.Hi - 1); wi = min(max(wi, 0), p.Wi - 1); }
+                else ok = hi >= 0 && hi < p.Hi && wi >= 0 && wi < p.Wi;
+                const float* src = ok ? in_img + ti * p.in_st + hi * p.in_sh + wi * p.in_sw + c4 * 4 : p.in;
+                cp_async16_zfill(stageA + e * 4, src, ok ? 16 : 0);
+            }
         }
         if (g_vec) {
-            const float* go_img = p.gout + n * p.go_sn + v * p.go_sv + t * p.go_st;
-            for (int e = tid; e < TH * TW * (NC / 4); e += 128) {
-                const int c4 = e % (NC / 4), pix = e / (NC / 4);
-                const int h = h0 + pix / TW, w = w0 + pix % TW;
-                const int co = occ * NC + c4 * 4;
-                const bool ok = h < p.Ho && w < p.Wo && co + 3 < p.FCO;
-                const float* src = ok ? go_img + h * p.go_sh + w * p.go_sw + co : p.gout;
-                cp_async16_zfill(stageG + pix * NC + c4 * 4, src, ok ? 16 : 0);
+            const float* go_tile = p.gout + n * p.go_sn + v * p.go_sv + t * p.go_st + h0 * p.go_sh + w0 * p.go_sw;
+            if (g_full && h0 + TH <= p.Ho && w0 + TW <= p.Wo) {
+#pragma unroll
+                for (int i = 0; i < NELG; ++i) {
+                    const int e = tid + i * 128;
+                    if (e < TOTALG) cp_async16_zfill(stageG + e * 4, go_tile + rel_g[i], 16);
+                }
+            } else {
+#pragma unroll 1
+                for (int e = tid; e < TOTALG; e += 128) {
+                    const int c4 = e % (NC / 4), pix = e / (NC / 4);
+                    const int h = h0 + pix / TW, w = w0 + pix % TW;
+                    const int co = occ * NC + c4 * 4;
+                    const bool ok = h < p.Ho && w < p.Wo && co + 3 < p.FCO;
+                    const float* src = ok ? go_tile + (pix / TW) * p.go_sh + (pix % TW) * p.go_sw + co : p.gout;
+                    cp_async16_zfill(stageG + e * 4, src, ok ? 16 : 0);
+                }
             }
         }
         cp_async_commit();
@@ -634,12 +703,14 @@ int launch_tc16(const P& p, int n_img_t, cudaStream_t st, const char* who) {
     IDEE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), who);
     const int tiles_h = (p.Ho + TH - 1) / TH;
     const int64_t total = (int64_t)n_img_t * tiles_h * p.tiles_w;
+    IDEE_REQUIRE(total < (1ll << 31) && 3 * p.in_st + HH * p.in_sh + HW_ * p.in_sw < (1ll << 31) &&
+                 TH * p.out_sh + TW * p.out_sw < (1ll << 31), "%s: tensor too large for 32-bit tile-relative offsets", who);
     int per_sm = 1;
-    IDEE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem), who);
+    IDEE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C16_THREADS, smem), who);
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)idee_num_sms() * per_sm;
     if (grid > total) grid = total;
-    kern<<<(unsigned)grid, 128, smem, st>>>(p, total, tiles_h);
+    kern<<<(unsigned)grid, C16_THREADS, smem, st>>>(p, total, tiles_h);
     IDEE_LAUNCH_CHECK(who);
     return 0;
 }
