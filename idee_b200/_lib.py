@@ -23,7 +23,8 @@ class SwinDesc(C.Structure):
 class ConvDesc(C.Structure):
     _fields_ = [(n, c_int) for n in ("N", "V", "Vw", "Cin", "Cout", "Ti", "Hi", "Wi", "To", "Ho", "Wo", "proj", "relu", "precision")] + \
                [(n, c_i64) for n in ("x_sn", "x_sv", "x_st", "x_sh", "x_sw", "x_sg")] + [("in_cpg", c_int)] + \
-               [(n, c_i64) for n in ("y_sn", "y_sv", "y_st", "y_sh", "y_sw", "y_sg")] + [("out_cpg", c_int)]
+               [(n, c_i64) for n in ("y_sn", "y_sv", "y_st", "y_sh", "y_sw", "y_sg")] + [("out_cpg", c_int)] + \
+               [(n, c_int) for n in ("x_dtype", "y_dtype", "gx_dtype")]
 
 
 _SIGS = {
@@ -34,7 +35,7 @@ _SIGS = {
     "idee_embed_ln_bwd_workspace_bytes": (c_sz, [c_int]),
     "idee_embed_ln_bwd": (c_int, [c_vp] * 7 + [c_int] * 7 + [c_vp, c_sz, c_vp]),
     "idee_swin_block_packed_floats": (c_int, [c_int]),
-    "idee_swin_block_fwd": (c_int, [C.POINTER(SwinDesc)] + [c_vp] * 6),
+    "idee_swin_block_fwd": (c_int, [C.POINTER(SwinDesc)] + [c_vp] * 7),
     "idee_swin_block_bwd_workspace_bytes": (c_sz, [C.POINTER(SwinDesc)]),
     "idee_swin_block_bwd": (c_int, [C.POINTER(SwinDesc)] + [c_vp] * 8 + [c_sz, c_vp]),
     "idee_conv3d_fwd_workspace_bytes": (c_sz, [C.POINTER(ConvDesc)]),

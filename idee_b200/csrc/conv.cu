@@ -19,9 +19,9 @@ size_t conv_tc_fwd_workspace_bytes(const idee_conv_desc* d);
 size_t conv_tc_dgrad_workspace_bytes(const idee_conv_desc* d);
 size_t conv_tc_wgrad_workspace_bytes(const idee_conv_desc* d);
 int conv_tc_wgrad_splits(const idee_conv_desc* d);
-int conv_tc_fwd(const idee_conv_desc* d, const float* x, const float* w, const float* b, float* y, void* ws, cudaStream_t st);
-int conv_tc_dgrad(const idee_conv_desc* d, const float* gy, const float* w, const float* relu_src, float* gx, void* ws, cudaStream_t st);
-int conv_tc_wgrad_partials(const idee_conv_desc* d, const float* x, const float* gy, float* partials, cudaStream_t st);
+int conv_tc_fwd(const idee_conv_desc* d, const void* x, const float* w, const float* b, void* y, void* ws, cudaStream_t st);
+int conv_tc_dgrad(const idee_conv_desc* d, const void* gy, const float* w, const void* relu_src, void* gx, void* ws, cudaStream_t st);
+int conv_tc_wgrad_partials(const idee_conv_desc* d, const void* x, const void* gy, float* partials, cudaStream_t st);
 
 namespace {
 
@@ -330,6 +330,10 @@ int check_desc(const idee_conv_desc* d, const char* who) {
     IDEE_REQUIRE(d->in_cpg >= 1 && d->out_cpg >= 1, "%s: chunks-per-group must be >= 1", who);
     if (d->proj) IDEE_REQUIRE(d->To == d->Ti && d->Ho == d->Hi && d->Wo == d->Wi, "%s: proj conv keeps the shape", who);
     else IDEE_REQUIRE(d->To == (d->Ti - 2) / 2 + 1 && d->Ti >= 2 && d->Ho == d->Hi && d->Wo == d->Wi, "%s: cls conv output shape mismatch", who);
+    IDEE_REQUIRE((unsigned)d->x_dtype <= 1u && (unsigned)d->y_dtype <= 1u && (unsigned)d->gx_dtype <= 1u, "%s: dtype fields must be 0 (float) or 1 (bf16)", who);
+    if (d->x_dtype || d->y_dtype || d->gx_dtype)
+        IDEE_REQUIRE(d->precision >= 1 && d->proj && d->Cin == 16 && d->Cout == 16 && d->in_cpg == 1 && d->out_cpg == 1,
+                     "%s: bf16 activation storage is only built for the precision >= 1 16 -> 16 proj conv", who);
     return 0;
 }
 
@@ -350,14 +354,14 @@ int launch_gather(const ConvP& p, cudaStream_t st, const char* who) {
 extern "C" size_t idee_conv3d_fwd_workspace_bytes(const idee_conv_desc* d) { return d->precision >= 1 ? conv_tc_fwd_workspace_bytes(d) : 0; }
 extern "C" size_t idee_conv3d_dgrad_workspace_bytes(const idee_conv_desc* d) { return d->precision >= 1 ? conv_tc_dgrad_workspace_bytes(d) : 0; }
 
-extern "C" int idee_conv3d_fwd(const idee_conv_desc* d, const float* x, const float* w, const float* b, float* y,
+extern "C" int idee_conv3d_fwd(const idee_conv_desc* d, const void* x, const float* w, const float* b, void* y,
                                void* workspace, size_t workspace_bytes, void* stream) {
     if (check_desc(d, "conv3d_fwd")) return 1;
     IDEE_REQUIRE(workspace_bytes >= idee_conv3d_fwd_workspace_bytes(d), "conv3d_fwd: workspace too small");
     if (d->precision >= 1) return conv_tc_fwd(d, x, w, b, y, workspace, (cudaStream_t)stream);
     ConvP p{};
     fill_common(p, d);
-    p.in = x; p.out = y; p.w = w; p.bias = b; p.relu_src = nullptr; p.relu = d->relu;
+    p.in = (const float*)x; p.out = (float*)y; p.w = w; p.bias = b; p.relu_src = nullptr; p.relu = d->relu;
     p.Ti = d->Ti; p.Hi = d->Hi; p.Wi = d->Wi; p.To = d->To; p.Ho = d->Ho; p.Wo = d->Wo;
     p.in_sn = d->x_sn; p.in_sv = d->x_sv; p.in_st = d->x_st; p.in_sh = d->x_sh; p.in_sw = d->x_sw; p.in_sg = d->x_sg; p.in_cpg = d->in_cpg;
     p.out_sn = d->y_sn; p.out_sv = d->y_sv; p.out_st = d->y_st; p.out_sh = d->y_sh; p.out_sw = d->y_sw; p.out_sg = d->y_sg; p.out_cpg = d->out_cpg;
@@ -369,14 +373,14 @@ extern "C" int idee_conv3d_fwd(const idee_conv_desc* d, const float* x, const fl
 }
 
 // gx = conv^T(gy); if relu_src != NULL the result is multiplied by (relu_src > 0) (relu_src has gx's layout)
-extern "C" int idee_conv3d_dgrad(const idee_conv_desc* d, const float* gy, const float* w, const float* relu_src, float* gx,
+extern "C" int idee_conv3d_dgrad(const idee_conv_desc* d, const void* gy, const float* w, const void* relu_src, void* gx,
                                  void* workspace, size_t workspace_bytes, void* stream) {
     if (check_desc(d, "conv3d_dgrad")) return 1;
     IDEE_REQUIRE(workspace_bytes >= idee_conv3d_dgrad_workspace_bytes(d), "conv3d_dgrad: workspace too small");
     if (d->precision >= 1) return conv_tc_dgrad(d, gy, w, relu_src, gx, workspace, (cudaStream_t)stream);
     ConvP p{};
     fill_common(p, d);
-    p.in = gy; p.out = gx; p.w = w; p.bias = nullptr; p.relu_src = relu_src; p.relu = relu_src != nullptr;
+    p.in = (const float*)gy; p.out = (float*)gx; p.w = w; p.bias = nullptr; p.relu_src = (const float*)relu_src; p.relu = relu_src != nullptr;
     // gather-input = gradient wrt the forward output, output = gradient wrt the forward input
     p.Ti = d->To; p.Hi = d->Ho; p.Wi = d->Wo; p.To = d->Ti; p.Ho = d->Hi; p.Wo = d->Wi;
     p.in_sn = d->y_sn; p.in_sv = d->y_sv; p.in_st = d->y_st; p.in_sh = d->y_sh; p.in_sw = d->y_sw; p.in_sg = d->y_sg; p.in_cpg = d->out_cpg;
@@ -393,7 +397,7 @@ extern "C" size_t idee_conv3d_wgrad_workspace_bytes(const idee_conv_desc* d) {
     return sizeof(float) * (size_t)d->Vw * n_ic * n_oc * wgrad_splits(d) * (NT * 256 + 16);
 }
 
-extern "C" int idee_conv3d_wgrad(const idee_conv_desc* d, const float* x, const float* gy, float* gw, float* gb,
+extern "C" int idee_conv3d_wgrad(const idee_conv_desc* d, const void* x, const void* gy, float* gw, float* gb,
                                  void* workspace, size_t workspace_bytes, void* stream) {
     if (check_desc(d, "conv3d_wgrad")) return 1;
     IDEE_REQUIRE(workspace_bytes >= idee_conv3d_wgrad_workspace_bytes(d), "conv3d_wgrad: workspace too small");
@@ -410,7 +414,7 @@ extern "C" int idee_conv3d_wgrad(const idee_conv_desc* d, const float* x, const 
         return 0;
     }
     WgradP p{};
-    p.in = x; p.gout = gy; p.partials = (float*)workspace;
+    p.in = (const float*)x; p.gout = (const float*)gy; p.partials = (float*)workspace;
     p.N = d->N; p.V = d->V; p.Vw = d->Vw;
     p.Ti = d->Ti; p.Hi = d->Hi; p.Wi = d->Wi; p.To = d->To; p.Ho = d->Ho; p.Wo = d->Wo;
     p.in_sn = d->x_sn; p.in_sv = d->x_sv; p.in_st = d->x_st; p.in_sh = d->x_sh; p.in_sw = d->x_sw; p.in_sg = d->x_sg; p.in_cpg = d->in_cpg;

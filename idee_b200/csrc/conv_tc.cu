@@ -15,6 +15,8 @@
 //     gradient rides along as one extra mma against a ones row; per-CTA partials are reduced by conv.cu's second stage.
 #include <cuda_bf16.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "idee_b200.h"
 
@@ -48,8 +50,29 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async16_zfill(void* smem, const void* gmem, int src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem)), "l"(gmem), "r"(src_bytes));
 }
+__device__ __forceinline__ void cp_async16_u32(uint32_t smem, const void* gmem, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem), "l"(gmem), "r"(src_bytes));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+// n / d and n % d for n < 2^31 by multiply-high with m = ceil(2^32 / d) (0xFFFFFFFF for d == 1) and one correction step
+struct FastDiv {
+    uint32_t d, m;
+    __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const {
+        uint32_t qq = __umulhi(n, m);
+        int rr = (int)(n - qq * d);
+        if (rr < 0) { --qq; rr += (int)d; }
+        if (rr >= (int)d) { ++qq; rr -= (int)d; }
+        q = qq; r = (uint32_t)rr;
+    }
+};
+inline FastDiv make_fastdiv(int d) {
+    FastDiv f;
+    f.d = (uint32_t)d;
+    f.m = d > 1 ? (uint32_t)(((1ull << 32) + (uint64_t)d - 1) / (uint64_t)d) : 0xFFFFFFFFu;
+    return f;
+}
 
 struct P {
     const float* in; float* out; const float* bias; const float* relu_src;
@@ -65,6 +88,7 @@ struct P {
     int relu;
     int tiles_w;
     int KS;                      // k-steps (gather-in channels / 16) for the generic (template KS == 0) kernels
+    int in16, out16;             // input / output tensors hold bf16 instead of fp32 (16-channel proj kernels only)
 };
 
 // fp32 PyTorch weights [FCO][FCI][NTf] -> bf16 mma B fragments.  B(k, n) = W[o=n][c=k] (forward) or W[o=k][c=n] (dgrad).
@@ -260,37 +284,53 @@ constexpr int C16_THREADS = 128;     // 4 warps per CTA, two tile rows (m-tiles)
 
 // ------------------------------------------------------------------------------------------------------------------
 // 16-input-channel convs (proj_var, per-variable classifier heads, and their data gradients): persistent, pipelined.
-// A CTA loads the weights once, then walks tiles:  wait(stage i) -> convert fp32 stage -> bf16 halo -> issue cp.async for
-// tile i+1 (zero-fill for padding, clamped addresses for replicate) -> MMA + epilogue of tile i.  The global-memory latency
-// of the next tile is hidden behind the tensor-core phase of the current one; taps are fully unrolled.
+// A CTA loads the weights once, then walks tiles with the next tile's halo in flight behind the current tile's MMAs:
+//   fp32 input (IN16 = false):  wait(stage i) -> convert fp32 stage -> bf16 halo -> issue cp.async(stage i+1) -> MMA + epilogue
+//   bf16 input (IN16 = true):   wait(halo[b] i) -> issue cp.async(halo[b^1] i+1) -> MMA + epilogue     (no staging, no convert)
+// Padding is resolved by the loader (zero-fill for zero padding, clamped addresses for replicate); taps are fully unrolled.
+// OUT16 stores the result as bf16 (same value the next conv would round to when it loads an fp32 copy).
 // ------------------------------------------------------------------------------------------------------------------
-template <int MODE, int NTL>
+template <int MODE, int NTL, bool IN16, bool OUT16>
 __global__ void __launch_bounds__(C16_THREADS)
-conv_tc16_kernel(P p, int64_t total_tiles64, int tiles_h) {
+conv_tc16_kernel(P p, int64_t total_tiles64, FastDiv fd_tw, FastDiv fd_th, FastDiv fd_to, FastDiv fd_v) {
     constexpr int CP = 24, NTH = C16_THREADS, MT = 8 / (NTH / 32);   // m-tiles (tile rows of 16 pixels) per warp
     constexpr int KTIN = (MODE == CLS_FWD) ? 2 : (MODE == CLS_DGRAD ? 1 : 3);
-    constexpr int NJ = (MODE == CLS_FWD) ? 18 : (MODE == CLS_DGRAD ? 9 : 27);
+    constexpr int NKH = (MODE == CLS_DGRAD) ? 3 : 3, NKT = (MODE == CLS_DGRAD) ? 1 : KTIN;
     constexpr int NTF = (MODE == CLS_FWD || MODE == CLS_DGRAD) ? 18 : 27;
     constexpr int WTAP = NTL * 32, NPIX = KTIN * HH * HW_;
-    constexpr int NCOL = HW_ * 4, TOTAL = KTIN * HH * NCOL, NEL = (TOTAL + NTH - 1) / NTH;   // 16-byte halo elements
+    constexpr int EPP = IN16 ? 2 : 4, ESC = IN16 ? 8 : 4;            // 16-byte elements per halo pixel, scalars per element
+    constexpr int NCOL = HW_ * EPP, PLANE = HH * NCOL, TOTAL = KTIN * PLANE, NEL = (TOTAL + NTH - 1) / NTH;
     constexpr int OT = (MODE == PROJ_FWD) ? -1 : (MODE == PROJ_DGRAD_PAD ? -2 : 0);          // halo origin relative to the tile
     constexpr int OHW = (MODE == PROJ_DGRAD_PAD) ? -2 : -1;
+    static_assert(NTH <= PLANE, "a thread's element i must span at most two halo planes");
+    using in_t = typename std::conditional<IN16, __nv_bfloat16, float>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint2* wsm = reinterpret_cast<uint2*>(smem_raw);                                     // [NTF][WTAP]
-    float* stage = reinterpret_cast<float*>(smem_raw + sizeof(uint2) * NTF * WTAP);      // [NPIX][16] fp32
-    __nv_bfloat16* halo = reinterpret_cast<__nv_bfloat16*>(stage + NPIX * 16);           // [NPIX][CP] bf16
+    uint2* wsm = reinterpret_cast<uint2*>(smem_raw);                                     // [NTF][32 lanes][NTL] (lane-major)
+    unsigned char* dyn = smem_raw + sizeof(uint2) * NTF * WTAP;
+    // fp32 input: [NPIX][16] fp32 stage | [NPIX][CP] bf16 halo;   bf16 input: [2][NPIX][CP] bf16 halo (double buffer)
+    float* stage = reinterpret_cast<float*>(dyn);
+    __nv_bfloat16* halo = reinterpret_cast<__nv_bfloat16*>(IN16 ? dyn : dyn + sizeof(float) * NPIX * 16);
+    const in_t* in = reinterpret_cast<const in_t*>(p.in);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t total_tiles = (uint32_t)total_tiles64;
+    const int ist = (int)p.in_st, ish = (int)p.in_sh, isw = (int)p.in_sw;
 
     // Per-thread constants: the halo elements a thread fetches are the same for every tile, so their source offsets
-    // relative to the halo origin are computed once (32-bit), leaving one 64-bit add per element on interior tiles.
-    int rel_src[NEL];
+    // relative to the halo origin (32-bit) are computed once, leaving one 64-bit add per element on tiles whose halo stays
+    // inside the image in h and w (a t-border only shifts / blanks whole planes).  hw[i] packs the in-plane halo coordinates
+    // (hh | ww << 4) for the tiles that touch an h / w border.
+    int rel_src[NEL], hw[NEL];
 #pragma unroll
     for (int i = 0; i < NEL; ++i) {
         const int e = tid + i * NTH, row = e / NCOL, col = e - row * NCOL;
-        const int kt = row / HH, hh = row - kt * HH, ww = col >> 2, c4 = col & 3;
-        rel_src[i] = (int)(kt * p.in_st + hh * p.in_sh + ww * p.in_sw) + c4 * 4;
+        const int kt = row / HH, hh = row - kt * HH, ww = col / EPP, c = col % EPP;
+        rel_src[i] = kt * ist + hh * ish + ww * isw + c * ESC;
+        hw[i] = hh | (ww << 4);
     }
+    const int csub = (tid % EPP) * ESC;                  // NTH is a multiple of EPP: the channel part is per-thread constant
+    // shared-memory destination of element (tid + i * NTH): base + i * DSTEP bytes
+    constexpr int DSTEP = IN16 ? (NTH / 2) * CP * 2 : NTH * 16;
+    const uint32_t dst_base = smem_u32(dyn) + (IN16 ? (tid >> 1) * CP * 2 + (tid & 1) * 16 : tid * 16);
     // epilogue offsets of this thread's 2*MT (row, half) output pixels relative to the tile origin
     int rel_out[MT][2];
 #pragma unroll
@@ -298,96 +338,161 @@ conv_tc16_kernel(P p, int64_t total_tiles64, int tiles_h) {
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) rel_out[m][hf] = (int)((warp * MT + m) * p.out_sh + (lane / 4 + hf * 8) * p.out_sw) + (lane % 4) * 2;
 
-    auto decode = [&](uint32_t tile, int& n, int& v, int& t, int& h0, int& w0) {
-        uint32_t r = tile;                                       // 32-bit: tw fastest, then th, t, v, n
-        uint32_t q = r / (uint32_t)p.tiles_w; w0 = (int)(r - q * p.tiles_w) * TW; r = q;
-        q = r / (uint32_t)tiles_h; h0 = (int)(r - q * tiles_h) * TH; r = q;
-        q = r / (uint32_t)p.To; t = (int)(r - q * p.To); r = q;
-        q = r / (uint32_t)p.V; v = (int)(r - q * p.V); n = (int)q;
+    struct Tile { int n, v, t, h0, w0; };
+    auto decode = [&](uint32_t tile) {                           // tw fastest, then th, t, v, n (multiply-high divisions)
+        Tile c;
+        uint32_t q, r;
+        fd_tw.divmod(tile, q, r); c.w0 = (int)r * TW;
+        fd_th.divmod(q, q, r); c.h0 = (int)r * TH;
+        fd_to.divmod(q, q, r); c.t = (int)r;
+        fd_v.divmod(q, q, r); c.v = (int)r; c.n = (int)q;
+        return c;
     };
-    auto issue = [&](uint32_t tile) {
-        int n, v, t, h0, w0;
-        decode(tile, n, v, t, h0, w0);
-        const float* in_img = p.in + n * p.in_sn + v * p.in_sv;
-        const int tb = (MODE == CLS_FWD) ? 2 * t : (MODE == CLS_DGRAD ? (t >> 1) : t);
-        const int t_lo = tb + OT, h_lo = h0 + OHW, w_lo = w0 + OHW;      // halo origin
-        const bool interior = t_lo >= 0 && t_lo + KTIN - 1 < p.Ti && h_lo >= 0 && h_lo + HH - 1 < p.Hi && w_lo >= 0 && w_lo + HW_ - 1 < p.Wi;
-        if (interior) {
-            const float* base = in_img + t_lo * p.in_st + h_lo * p.in_sh + w_lo * p.in_sw;
+    auto issue = [&](const Tile& c, int buf) {
+        const in_t* in_img = in + c.n * p.in_sn + c.v * p.in_sv;
+        const int tb = (MODE == CLS_FWD) ? 2 * c.t : (MODE == CLS_DGRAD ? (c.t >> 1) : c.t);
+        const int t_lo = tb + OT, h_lo = c.h0 + OHW, w_lo = c.w0 + OHW;      // halo origin
+        const uint32_t dst0 = dst_base + (IN16 ? buf * NPIX * CP * 2 : 0);
+        // per-plane resolution of the t border: replicate shifts the plane, zero padding blanks it
+        int dT[KTIN]; bool okT[KTIN];
+#pragma unroll
+        for (int k = 0; k < KTIN; ++k) {
+            const int ti = t_lo + k;
+            if (MODE == PROJ_FWD) { dT[k] = (min(max(ti, 0), p.Ti - 1) - ti) * ist; okT[k] = true; }
+            else { okT[k] = (unsigned)ti < (unsigned)p.Ti; dT[k] = okT[k] ? 0 : -(t_lo * ist + k * ist); }
+        }
+        if (h_lo >= 0 && h_lo + HH - 1 < p.Hi && w_lo >= 0 && w_lo + HW_ - 1 < p.Wi) {
+            // blanked planes read (and discard) the first plane-0 element row of the image: dT moves them to t = 0
+            const in_t* base = in_img + (int64_t)t_lo * p.in_st + h_lo * ish + w_lo * isw;
 #pragma unroll
             for (int i = 0; i < NEL; ++i) {
-                const int e = tid + i * NTH;
-                if (e < TOTAL) cp_async16_zfill(stage + e * 4, base + rel_src[i], 16);
+                const int k0 = (i * NTH) / PLANE, k1 = (i * NTH + NTH - 1) / PLANE;       // planes this i can touch
+                if (tid + i * NTH < TOTAL) {
+                    int d; bool ok;
+                    if (k0 == k1 || k1 >= KTIN) { d = dT[k0]; ok = okT[k0]; }
+                    else { const bool up = tid >= k1 * PLANE - i * NTH; d = up ? dT[k1 < KTIN ? k1 : k0] : dT[k0]; ok = up ? okT[k1 < KTIN ? k1 : k0] : okT[k0]; }
+                    cp_async16_u32(dst0 + i * DSTEP, base + (rel_src[i] + d), ok ? 16 : 0);
+                }
+            }
+        } else if (IN16) {
+#pragma unroll
+            for (int i = 0; i < NEL; ++i) {
+                const int k0 = (i * NTH) / PLANE, k1 = (i * NTH + NTH - 1) / PLANE;
+                if (tid + i * NTH < TOTAL) {
+                    int kt = k0;
+                    if (k0 != k1 && k1 < KTIN) kt = tid >= k1 * PLANE - i * NTH ? k1 : k0;
+                    int ti = t_lo + kt, hi = h_lo + (hw[i] & 15), wi = w_lo + (hw[i] >> 4);
+                    bool ok = true;
+                    if (MODE == PROJ_FWD) { ti = min(max(ti, 0), p.Ti - 1); hi = min(max(hi, 0), p.Hi - 1); wi = min(max(wi, 0), p.Wi - 1); }
+                    else ok = (unsigned)ti < (unsigned)p.Ti && (unsigned)hi < (unsigned)p.Hi && (unsigned)wi < (unsigned)p.Wi;
+                    const int off = ok ? ti * ist + hi * ish + wi * isw + csub : 0;
+                    cp_async16_u32(dst0 + i * DSTEP, in_img + off, ok ? 16 : 0);
+                }
             }
         } else {
 #pragma unroll 1
-            for (int e = tid; e < TOTAL; e += NTH) {
-                const int row = e / NCOL, col = e - row * NCOL;
-                const int kt = row / HH, hh = row - kt * HH, ww = col >> 2, c4 = col & 3;
-                int ti = t_lo + kt, hi = h_lo + hh, wi = w_lo + ww;
+            for (int e = tid, d = 0; e < TOTAL; e += NTH, d += DSTEP) {
+                const int row = e / NCOL, col = e - row * NCOL, kt = row / HH;
+                int ti = t_lo + kt, hi = h_lo + row - kt * HH, wi = w_lo + col / EPP;
                 bool ok = true;
                 if (MODE == PROJ_FWD) { ti = min(max(ti, 0), p.Ti - 1); hi = min(max(hi, 0), p.Hi - 1); wi = min(max(wi, 0), p.Wi - 1); }
-                else ok = ti >= 0 && ti < p.Ti && hi >= 0 && hi < p.Hi && wi >= 0 && wi < p.Wi;
-                const float* src = ok ? in_img + ti * p.in_st + hi * p.in_sh + wi * p.in_sw + c4 * 4 : p.in;
-                cp_async16_zfill(stage + e * 4, src, ok ? 16 : 0);
+                else ok = (unsigned)ti < (unsigned)p.Ti && (unsigned)hi < (unsigned)p.Hi && (unsigned)wi < (unsigned)p.Wi;
+                const int off = ok ? ti * ist + hi * ish + wi * isw + csub : 0;
+                cp_async16_u32(dst0 + d, in_img + off, ok ? 16 : 0);
             }
         }
         cp_async_commit();
     };
 
     const uint32_t first = blockIdx.x;
-    if (first < total_tiles) issue(first);
-    int cur_wset = -1;
+    Tile nxt{};
+    if (first < total_tiles) { nxt = decode(first); issue(nxt, 0); }
+    int cur_wset = -1, buf = 0;
     const int a_pix = (lane & 7) + ((lane >> 3) & 1) * 8, a_koff = (lane >> 4) * 8;
-    for (uint32_t tile = first; tile < total_tiles; tile += gridDim.x) {
-        int n, v, t, h0, w0;
-        decode(tile, n, v, t, h0, w0);
-        const int wset = p.Vw == 1 ? 0 : v;
+    for (uint32_t tile = first; tile < total_tiles; tile += gridDim.x, buf ^= 1) {
+        const Tile c = nxt;
+        const int wset = p.Vw == 1 ? 0 : c.v;
         cp_async_wait<0>();
-        __syncthreads();                                   // stage(tile) landed; every warp is done with the previous halo/weights
+        __syncthreads();                                   // tile's data landed; every warp is done with the previous halo/weights
         if (wset != cur_wset) {
-            const uint2* wf = p.wfrag + (int64_t)wset * NTF * WTAP;
-            for (int e = tid; e < NTF * WTAP; e += NTH) wsm[e] = wf[e];
+            const uint2* wf = p.wfrag + (int64_t)wset * NTF * WTAP;      // global: [ftap][ntile][lane] -> smem [ftap][lane][ntile]
+            for (int e = tid; e < NTF * WTAP; e += NTH) {
+                const int ft = e / WTAP, r = e - ft * WTAP;
+                wsm[ft * WTAP + (r & 31) * NTL + (r >> 5)] = wf[e];
+            }
             cur_wset = wset;
+            if (IN16) __syncthreads();
         }
+        const bool more = tile + gridDim.x < total_tiles;
+        const __nv_bfloat16* hb = halo;
+        if (IN16) {
+            hb = halo + buf * NPIX * CP;
+            if (more) { nxt = decode(tile + gridDim.x); issue(nxt, buf ^ 1); }
+        } else {
 #pragma unroll
-        for (int i = 0; i < (NPIX * 4 + NTH - 1) / NTH; ++i) {   // fp32 stage -> bf16 halo (padded pixel stride)
-            const int e = tid + i * NTH;
-            if (e < NPIX * 4) {
-                const float4 f = ld4(stage + e * 4);
-                *reinterpret_cast<uint2*>(halo + (e >> 2) * CP + (e & 3) * 4) = make_uint2(pack_bf16(f.x, f.y), pack_bf16(f.z, f.w));
+            for (int i = 0; i < (NPIX * 4 + NTH - 1) / NTH; ++i) {   // fp32 stage -> bf16 halo (padded pixel stride)
+                const int e = tid + i * NTH;
+                if (e < NPIX * 4) {
+                    const float4 f = ld4(stage + e * 4);
+                    *reinterpret_cast<uint2*>(halo + (e >> 2) * CP + (e & 3) * 4) = make_uint2(pack_bf16(f.x, f.y), pack_bf16(f.z, f.w));
+                }
+            }
+            __syncthreads();
+            if (more) { nxt = decode(tile + gridDim.x); issue(nxt, 0); }
+        }
+
+        // Two accumulator sets (taps alternate between them, summed at the end): 2 * MT * NTL independent HMMA chains per warp
+        // instead of MT * NTL, which is what hides the HMMA latency at 3 resident warps per scheduler.
+        float acc2[2][MT][NTL][4];
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2)
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+#pragma unroll
+                for (int nt = 0; nt < NTL; ++nt) acc2[s2][m][nt][0] = acc2[s2][m][nt][1] = acc2[s2][m][nt][2] = acc2[s2][m][nt][3] = 0.f;
+        const __nv_bfloat16* abase = hb + ((warp * MT) * HW_ + a_pix) * CP + a_koff;
+        const uint2* wpar = wsm + ((MODE == CLS_DGRAD) ? (c.t & 1) * 9 * WTAP : 0) + lane * NTL;
+        // taps ordered (kt, kw, kh): the MT + 2 halo rows of one (kt, kw) column feed all three kh taps of every m-tile
+#pragma unroll
+        for (int kt = 0; kt < NKT; ++kt) {
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                uint32_t af[MT + NKH - 1][4];
+#pragma unroll
+                for (int r = 0; r < MT + NKH - 1; ++r) ldsm_x4(af[r], abase + ((kt * HH + r) * HW_ + kw) * CP);
+#pragma unroll
+                for (int kh = 0; kh < NKH; ++kh) {
+                    const int ft = (MODE == CLS_FWD || MODE == PROJ_FWD) ? kt * 9 + kh * 3 + kw
+                                 : (MODE == CLS_DGRAD ? (2 - kh) * 3 + (2 - kw) : (2 - kt) * 9 + (2 - kh) * 3 + (2 - kw));
+                    const int set = ((kt * 3 + kw) * NKH + kh) & 1;
+                    uint2 b[NTL];
+                    if (NTL == 2) {
+                        const uint4 bb = *reinterpret_cast<const uint4*>(wpar + ft * WTAP);
+                        b[0] = make_uint2(bb.x, bb.y); b[NTL - 1] = make_uint2(bb.z, bb.w);
+                    } else {
+#pragma unroll
+                        for (int nt = 0; nt < NTL; ++nt) b[nt] = wpar[ft * WTAP + nt];
+                    }
+#pragma unroll
+                    for (int nt = 0; nt < NTL; ++nt)
+#pragma unroll
+                        for (int m = 0; m < MT; ++m) mma_bf16(acc2[set][m][nt], af[m + kh], b[nt].x, b[nt].y);
+                }
             }
         }
-        __syncthreads();
-        if (tile + gridDim.x < total_tiles) issue(tile + gridDim.x);
-
         float acc[MT][NTL][4];
 #pragma unroll
         for (int m = 0; m < MT; ++m)
 #pragma unroll
-            for (int nt = 0; nt < NTL; ++nt) acc[m][nt][0] = acc[m][nt][1] = acc[m][nt][2] = acc[m][nt][3] = 0.f;
-        const __nv_bfloat16* abase = halo + ((warp * MT) * HW_ + a_pix) * CP + a_koff;
-        const uint2* wpar = wsm + ((MODE == CLS_DGRAD) ? (t & 1) * 9 * WTAP : 0) + lane;
+            for (int nt = 0; nt < NTL; ++nt)
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            const int kt = (MODE == CLS_DGRAD) ? 0 : j / 9, kh = (MODE == CLS_DGRAD) ? j / 3 : (j / 3) % 3, kw = j % 3;
-            const int ft = (MODE == CLS_FWD || MODE == PROJ_FWD) ? j
-                         : (MODE == CLS_DGRAD ? (2 - kh) * 3 + (2 - kw) : (2 - kt) * 9 + (2 - kh) * 3 + (2 - kw));
-            uint32_t af[MT][4];
-#pragma unroll
-            for (int m = 0; m < MT; ++m) ldsm_x4(af[m], abase + ((kt * HH + kh + m) * HW_ + kw) * CP);
-#pragma unroll
-            for (int nt = 0; nt < NTL; ++nt) {
-                const uint2 b = wpar[ft * WTAP + nt * 32];
-#pragma unroll
-                for (int m = 0; m < MT; ++m) mma_bf16(acc[m][nt], af[m], b.x, b.y);
-            }
-        }
+                for (int q = 0; q < 4; ++q) acc[m][nt][q] = acc2[0][m][nt][q] + acc2[1][m][nt][q];
         // epilogue
         const float* B = p.bias ? p.bias + (int64_t)wset * p.CO : nullptr;
-        const int64_t tile_off = n * p.out_sn + v * p.out_sv + t * p.out_st + h0 * p.out_sh + w0 * p.out_sw;
+        const int64_t tile_off = c.n * p.out_sn + c.v * p.out_sv + (int64_t)(c.t * (int)p.out_st + c.h0 * (int)p.out_sh + c.w0 * (int)p.out_sw);
         float* out_tile = p.out + tile_off;
-        const float* rs_tile = p.relu_src ? p.relu_src + tile_off : nullptr;
+        __nv_bfloat16* out_tile16 = reinterpret_cast<__nv_bfloat16*>(p.out) + tile_off;
+        const float* rs_tile = (!OUT16 && p.relu_src) ? p.relu_src + tile_off : nullptr;
         float bias0[NTL], bias1[NTL];
 #pragma unroll
         for (int nt = 0; nt < NTL; ++nt) {
@@ -397,10 +502,10 @@ conv_tc16_kernel(P p, int64_t total_tiles64, int tiles_h) {
         }
 #pragma unroll
         for (int m = 0; m < MT; ++m) {
-            if (h0 + warp * MT + m >= p.Ho) continue;
+            if (c.h0 + warp * MT + m >= p.Ho) continue;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-                if (w0 + lane / 4 + half * 8 >= p.Wo) continue;
+                if (c.w0 + lane / 4 + half * 8 >= p.Wo) continue;
 #pragma unroll
                 for (int nt = 0; nt < NTL; ++nt) {
                     const int co = nt * 8 + (lane % 4) * 2;
@@ -408,42 +513,61 @@ conv_tc16_kernel(P p, int64_t total_tiles64, int tiles_h) {
                     const int o = rel_out[m][half] + nt * 8;
                     float v0 = acc[m][nt][half * 2] + bias0[nt], v1 = acc[m][nt][half * 2 + 1] + bias1[nt];
                     if (p.relu && MODE <= PROJ_FWD) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-                    if (rs_tile) { if (!(rs_tile[o] > 0.f)) v0 = 0.f; if (co + 1 < p.CO && !(rs_tile[o + 1] > 0.f)) v1 = 0.f; }
-                    if (co + 1 < p.CO) *reinterpret_cast<float2*>(out_tile + o) = make_float2(v0, v1);
-                    else out_tile[o] = v0;
+                    if (OUT16) {                           // host guarantees an even channel count
+                        *reinterpret_cast<__nv_bfloat162*>(out_tile16 + o) = __floats2bfloat162_rn(v0, v1);
+                    } else {
+                        if (rs_tile) { if (!(rs_tile[o] > 0.f)) v0 = 0.f; if (co + 1 < p.CO && !(rs_tile[o + 1] > 0.f)) v1 = 0.f; }
+                        if (co + 1 < p.CO) *reinterpret_cast<float2*>(out_tile + o) = make_float2(v0, v1);
+                        else out_tile[o] = v0;
+                    }
                 }
             }
         }
     }
 }
 
-// gin[r] = sum of gpad over the padded positions that clamp to r (adjoint of replicate padding), optional ReLU mask
-__global__ void fold_pad_kernel(const float* __restrict__ gpad, float* __restrict__ gin, const float* __restrict__ relu_src,
-                                int NV, int T, int H, int W) {
-    const int64_t total = (int64_t)NV * T * H * W * 4;   // float4 units of the 16 channels
-    const int64_t Wp = W + 2, Hp = H + 2, Tp = T + 2;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-        const int c4 = (int)(e & 3);
-        int64_t r = e >> 2;
-        const int w = (int)(r % W); r /= W;
-        const int h = (int)(r % H); r /= H;
-        const int t = (int)(r % T);
-        const int64_t img = r / T;
+// gin[r] = sum of gpad over the padded positions that clamp to r (adjoint of replicate padding), optional ReLU mask.
+// OUT16 / RS16: gin / relu_src hold bf16 (the sum is formed in fp32 and rounded once).
+// One CTA walks whole rows (img, t, h): the row coordinates and the t / h ranges are CTA-uniform, threads cover (w, channel
+// quarter), so the only per-element integer work is the w range.
+template <bool OUT16, bool RS16>
+__global__ void __launch_bounds__(256)
+fold_pad_kernel(const float* __restrict__ gpad, void* __restrict__ gin_, const void* __restrict__ relu_src_,
+                int rows, int T, int H, int W, FastDiv fd_h, FastDiv fd_t) {
+    const int Wp = W + 2, Hp = H + 2, Tp = T + 2;
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        uint32_t q, r;
+        fd_h.divmod((uint32_t)row, q, r); const int h = (int)r;
+        fd_t.divmod(q, q, r); const int t = (int)r;
+        const int64_t img = q;
         const int t0 = t == 0 ? 0 : t + 1, t1 = t == T - 1 ? T + 1 : t + 1;
         const int h0 = h == 0 ? 0 : h + 1, h1 = h == H - 1 ? H + 1 : h + 1;
-        const int w0 = w == 0 ? 0 : w + 1, w1 = w == W - 1 ? W + 1 : w + 1;
-        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int tt = t0; tt <= t1; ++tt)
-            for (int hh = h0; hh <= h1; ++hh)
-                for (int ww = w0; ww <= w1; ++ww) {
-                    const float4 g = ldg4(gpad + ((((img * Tp + tt) * Hp + hh) * Wp + ww) * 16 + c4 * 4));
-                    s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
+        const int64_t row_out = (int64_t)row * W * 16;
+        for (int e = threadIdx.x; e < W * 4; e += 256) {
+            const int w = e >> 2, c4 = e & 3;
+            const int w0 = w == 0 ? 0 : w + 1, w1 = w == W - 1 ? W + 1 : w + 1;
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int tt = t0; tt <= t1; ++tt)
+                for (int hh = h0; hh <= h1; ++hh) {
+                    const float* prow = gpad + (((img * Tp + tt) * Hp + hh) * Wp) * 16 + c4 * 4;
+                    for (int ww = w0; ww <= w1; ++ww) {
+                        const float4 g = ldg4(prow + ww * 16);
+                        s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
+                    }
                 }
-        if (relu_src) {
-            const float4 a = ldg4(relu_src + e * 4);
-            if (!(a.x > 0.f)) s.x = 0.f; if (!(a.y > 0.f)) s.y = 0.f; if (!(a.z > 0.f)) s.z = 0.f; if (!(a.w > 0.f)) s.w = 0.f;
+            const int64_t o = row_out + e * 4;
+            if (relu_src_) {
+                float4 a;
+                if (RS16) {
+                    const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(relu_src_) + o));
+                    a = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u), __uint_as_float(u.y << 16),
+                                    __uint_as_float(u.y & 0xFFFF0000u));
+                } else a = ldg4(reinterpret_cast<const float*>(relu_src_) + o);
+                if (!(a.x > 0.f)) s.x = 0.f; if (!(a.y > 0.f)) s.y = 0.f; if (!(a.z > 0.f)) s.z = 0.f; if (!(a.w > 0.f)) s.w = 0.f;
+            }
+            if (OUT16) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(gin_) + o) = make_uint2(pack_bf16(s.x, s.y), pack_bf16(s.z, s.w));
+            else st4(reinterpret_cast<float*>(gin_) + o, s);
         }
-        st4(gin + e * 4, s);
     }
 }
 
@@ -451,7 +575,7 @@ __global__ void fold_pad_kernel(const float* __restrict__ gpad, float* __restric
 // weight gradient
 // ------------------------------------------------------------------------------------------------------------------
 struct WP {
-    const float* in; const float* gout; float* partials;
+    const void* in; const void* gout; float* partials;   // in / gout: fp32, or bf16 when a16 / g16
     int N, V, Vw;
     int Ti, Hi, Wi, To, Ho, Wo;
     int64_t in_sn, in_sv, in_st, in_sh, in_sw, in_sg;
@@ -460,18 +584,30 @@ struct WP {
     int n_ic, n_oc16, S;        // n_oc16: 16-wide output chunks in total (partials layout of conv.cu)
     int tiles_h, tiles_w;
     int64_t tiles_per_set;      // imgs_per_set * To * tiles_h * tiles_w
+    int a16, g16;
+    FastDiv fd_to, fd_tw, fd_th, fd_ipn;
 };
 
-// NT taps, NTL n-tiles (8 output channels each) per CTA; cin chunk 16
-template <int NT, int NTL>
+// NT taps, NTL n-tiles (8 output channels each) per CTA; cin chunk 16.  A16 / G16: the input / output-gradient tensors hold
+// bf16: their tiles are then copied by cp.async straight into the (double-buffered) MMA layout, no staging and no convert.
+template <int NT, int NTL, bool A16, bool G16>
 __global__ void __launch_bounds__(128)
 wgrad_tc_kernel(WP p) {
     constexpr int KTIN = NT / 9, CPA = 24, NC = NTL * 8, CPG = NC + 8, TPW = (NT + 3) / 4, NPIX = KTIN * HH * HW_;
+    constexpr int A_TILE = NPIX * CPA * 2, G_TILE = TH * TW * CPG * 2;                    // bytes of one bf16 tile
+    constexpr int A_STAGE = NPIX * 64, G_STAGE = TH * TW * NC * 4;                        // bytes of the fp32 stages
+    constexpr int A_BYTES = A16 ? 2 * A_TILE : A_STAGE + A_TILE;
+    using a_t = typename std::conditional<A16, __nv_bfloat16, float>::type;
+    using g_t = typename std::conditional<G16, __nv_bfloat16, float>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* stageA = reinterpret_cast<float*>(smem_raw);                                  // [NPIX][16] fp32
-    float* stageG = stageA + NPIX * 16;                                                  // [128][NC] fp32
-    __nv_bfloat16* tileA = reinterpret_cast<__nv_bfloat16*>(stageG + TH * TW * NC);      // [NPIX][CPA]
-    __nv_bfloat16* tileG = tileA + NPIX * CPA;                                           // [128][CPG]
+    unsigned char* regA = smem_raw;
+    unsigned char* regG = smem_raw + A_BYTES;
+    float* stageA = reinterpret_cast<float*>(regA);                                       // [NPIX][16] fp32      (!A16)
+    float* stageG = reinterpret_cast<float*>(regG);                                       // [128][NC] fp32       (!G16)
+    __nv_bfloat16* tileA0 = reinterpret_cast<__nv_bfloat16*>(A16 ? regA : regA + A_STAGE);    // [NPIX][CPA] (x2 if A16)
+    __nv_bfloat16* tileG0 = reinterpret_cast<__nv_bfloat16*>(G16 ? regG : regG + G_STAGE);    // [128][CPG]  (x2 if G16)
+    const a_t* in = reinterpret_cast<const a_t*>(p.in);
+    const g_t* gout = reinterpret_cast<const g_t*>(p.gout);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int s = blockIdx.x, wset = blockIdx.y;
     const int n_occ = (p.n_oc16 * 16 + NC - 1) / NC;          // output chunks of NC channels
@@ -497,7 +633,7 @@ wgrad_tc_kernel(WP p) {
     const int a_pix = (lane & 7) + (lane >> 4) * 8, a_coff = ((lane >> 3) & 1) * 8;     // A (trans) lane address
     const int b_pix = (lane & 7) + ((lane >> 3) & 1) * 8, b_coff = (lane >> 4) * 8;     // B (trans) lane address
     const int64_t coff = (ic / p.in_cpg) * p.in_sg + (ic % p.in_cpg) * 16;
-    const bool g_vec = (p.FCO % 4) == 0;                      // gout rows can be fetched in 16-byte pieces
+    const bool g_vec = G16 || (p.FCO % 4) == 0;               // gout rows can be fetched in 16-byte pieces
     // smem offsets (halves) of this warp's taps inside the halo tile
     int a_off[TPW];
 #pragma unroll
@@ -505,111 +641,151 @@ wgrad_tc_kernel(WP p) {
         const int ft = warp + 4 * i, kt = ft / 9, kh = (ft / 3) % 3, kw = ft % 3;
         a_off[i] = (((kt * HH + kh) * HW_ + kw) + a_pix) * CPA + a_coff;
     }
-    constexpr int NCOLA = HW_ * 4, TOTALA = KTIN * HH * NCOLA, NELA = (TOTALA + 127) / 128;
-    constexpr int TOTALG = TH * TW * (NC / 4), NELG = (TOTALG + 127) / 128;
+    constexpr int EPPA = A16 ? 2 : 4, ESCA = A16 ? 8 : 4;     // 16-byte elements per halo pixel, scalars per element
+    constexpr int NCOLA = HW_ * EPPA, PLANE = HH * NCOLA, TOTALA = KTIN * PLANE, NELA = (TOTALA + 127) / 128;
+    constexpr int GE = G16 ? NC / 8 : NC / 4, ESCG = G16 ? 8 : 4;
+    constexpr int TOTALG = TH * TW * GE, NELG = (TOTALG + 127) / 128;
+    static_assert(!G16 || (128 % GE == 0), "bf16 gout tiles need a power-of-two element count per pixel");
+    const int ist = (int)p.in_st, ish = (int)p.in_sh, isw = (int)p.in_sw;
     // tile-independent relative offsets of the elements this thread fetches (32-bit), see conv_tc16_kernel
-    int rel_a[NELA], rel_g[NELG];
+    int rel_a[NELA], rel_g[NELG], hw[NELA];
 #pragma unroll
     for (int i = 0; i < NELA; ++i) {
         const int e = tid + i * 128, row = e / NCOLA, col = e - row * NCOLA;
-        const int kt = row / HH, hh = row - kt * HH, ww = col >> 2, c4 = col & 3;
-        rel_a[i] = (int)(kt * p.in_st + hh * p.in_sh + ww * p.in_sw) + c4 * 4;
+        const int kt = row / HH, hh = row - kt * HH, ww = col / EPPA, c = col % EPPA;
+        rel_a[i] = kt * ist + hh * ish + ww * isw + c * ESCA;
+        hw[i] = hh | (ww << 4);
     }
 #pragma unroll
     for (int i = 0; i < NELG; ++i) {
-        const int e = tid + i * 128, c4 = e % (NC / 4), pix = e / (NC / 4);
-        rel_g[i] = (int)((pix / TW) * p.go_sh + (pix % TW) * p.go_sw) + occ * NC + c4 * 4;
+        const int e = tid + i * 128, c = e % GE, pix = e / GE;
+        rel_g[i] = (int)((pix / TW) * p.go_sh + (pix % TW) * p.go_sw) + occ * NC + c * ESCG;
     }
+    constexpr int DSTEPA = A16 ? 64 * CPA * 2 : 128 * 16;
+    constexpr int DSTEPG = G16 ? (128 / GE) * CPG * 2 : 128 * 16;
+    const uint32_t dstA_base = smem_u32(regA) + (A16 ? (tid >> 1) * CPA * 2 + (tid & 1) * 16 : tid * 16);
+    const uint32_t dstG_base = smem_u32(regG) + (G16 ? (tid / GE) * CPG * 2 + (tid % GE) * 16 : tid * 16);
+    const int csub = (tid % EPPA) * ESCA;
     const bool g_full = occ * NC + NC <= p.FCO;             // every channel of this output chunk exists
-    auto decode = [&](int64_t tile64, int& n, int& v, int& t, int& h0, int& w0) {
-        uint32_t r = (uint32_t)tile64;             // t fastest: consecutive tiles of a CTA share input t-slices (L1/L2 hits)
-        uint32_t q = r / (uint32_t)p.To; t = (int)(r - q * p.To); r = q;
-        q = r / (uint32_t)p.tiles_w; w0 = (int)(r - q * p.tiles_w) * TW; r = q;
-        q = r / (uint32_t)p.tiles_h; h0 = (int)(r - q * p.tiles_h) * TH;
-        const uint32_t img = q;
-        n = (int)(img / (uint32_t)imgs_per_n); v = p.Vw == 1 ? (int)(img % (uint32_t)imgs_per_n) : wset;
+    struct Tile { int n, v, t, h0, w0; };
+    auto decode = [&](int64_t tile64) {            // t fastest: consecutive tiles of a CTA share input t-slices (L1/L2 hits)
+        Tile c;
+        uint32_t q, r;
+        p.fd_to.divmod((uint32_t)tile64, q, r); c.t = (int)r;
+        p.fd_tw.divmod(q, q, r); c.w0 = (int)r * TW;
+        p.fd_th.divmod(q, q, r); c.h0 = (int)r * TH;
+        if (p.Vw == 1) { p.fd_ipn.divmod(q, q, r); c.n = (int)q; c.v = (int)r; }
+        else { c.n = (int)q; c.v = wset; }
+        return c;
     };
-    auto issue = [&](int64_t tile) {
-        int n, v, t, h0, w0;
-        decode(tile, n, v, t, h0, w0);
-        const float* in_img = p.in + n * p.in_sn + v * p.in_sv + coff;
-        const int t_lo = p.proj ? t - 1 : 2 * t, h_lo = h0 - 1, w_lo = w0 - 1;
-        const bool interior = t_lo >= 0 && t_lo + KTIN - 1 < p.Ti && h_lo >= 0 && h_lo + HH - 1 < p.Hi && w_lo >= 0 && w_lo + HW_ - 1 < p.Wi;
-        if (interior) {
-            const float* base = in_img + t_lo * p.in_st + h_lo * p.in_sh + w_lo * p.in_sw;
+    auto issue = [&](const Tile& c, int buf) {
+        const a_t* in_img = in + c.n * p.in_sn + c.v * p.in_sv + coff;
+        const int t_lo = p.proj ? c.t - 1 : 2 * c.t, h_lo = c.h0 - 1, w_lo = c.w0 - 1;
+        const uint32_t dstA = dstA_base + (A16 ? buf * A_TILE : 0), dstG = dstG_base + (G16 ? buf * G_TILE : 0);
+        if (h_lo >= 0 && h_lo + HH - 1 < p.Hi && w_lo >= 0 && w_lo + HW_ - 1 < p.Wi) {
+            // a t border (replicate conv only; the strided classifier conv never leaves the image in t) shifts whole planes
+            int dT[KTIN];
+#pragma unroll
+            for (int k = 0; k < KTIN; ++k) dT[k] = p.proj ? (min(max(t_lo + k, 0), p.Ti - 1) - (t_lo + k)) * ist : 0;
+            const a_t* base = in_img + (int64_t)t_lo * p.in_st + h_lo * ish + w_lo * isw;
 #pragma unroll
             for (int i = 0; i < NELA; ++i) {
-                const int e = tid + i * 128;
-                if (e < TOTALA) cp_async16_zfill(stageA + e * 4, base + rel_a[i], 16);
+                const int k0 = (i * 128) / PLANE, k1 = (i * 128 + 127) / PLANE;
+                if (tid + i * 128 < TOTALA) {
+                    int d = dT[k0];
+                    if (k0 != k1 && k1 < KTIN) d = tid >= k1 * PLANE - i * 128 ? dT[k1 < KTIN ? k1 : k0] : dT[k0];
+                    cp_async16_u32(dstA + i * DSTEPA, base + (rel_a[i] + d), 16);
+                }
+            }
+        } else if (A16) {
+#pragma unroll
+            for (int i = 0; i < NELA; ++i) {
+                const int k0 = (i * 128) / PLANE, k1 = (i * 128 + 127) / PLANE;
+                if (tid + i * 128 < TOTALA) {
+                    int kt = k0;
+                    if (k0 != k1 && k1 < KTIN) kt = tid >= k1 * PLANE - i * 128 ? k1 : k0;
+                    int ti = t_lo + kt, hi = h_lo + (hw[i] & 15), wi = w_lo + (hw[i] >> 4);
+                    bool ok = true;
+                    if (p.proj) { ti = min(max(ti, 0), p.Ti - 1); hi = min(max(hi, 0), p.Hi - 1); wi = min(max(wi, 0), p.Wi - 1); }
+                    else ok = (unsigned)hi < (unsigned)p.Hi && (unsigned)wi < (unsigned)p.Wi;
+                    const int off = ok ? ti * ist + hi * ish + wi * isw + csub : 0;
+                    cp_async16_u32(dstA + i * DSTEPA, in_img + off, ok ? 16 : 0);
+                }
             }
         } else {
 #pragma unroll 1
-            for (int e = tid; e < TOTALA; e += 128) {
-                const int row = e / NCOLA, col = e - row * NCOLA;
-                const int kt = row / HH, hh = row - kt * HH, ww = col >> 2, c4 = col & 3;
-                int ti = t_lo + kt, hi = h_lo + hh, wi = w_lo + ww;
+            for (int e = tid, d = 0; e < TOTALA; e += 128, d += DSTEPA) {
+                const int row = e / NCOLA, col = e - row * NCOLA, kt = row / HH;
+                int ti = t_lo + kt, hi = h_lo + row - kt * HH, wi = w_lo + col / EPPA;
                 bool ok = true;
                 if (p.proj) { ti = min(max(ti, 0), p.Ti - 1); hi = min(max(hi, 0), p.Hi - 1); wi = min(max(wi, 0), p.Wi - 1); }
-                else ok = hi >= 0 && hi < p.Hi && wi >= 0 && wi < p.Wi;
-                const float* src = ok ? in_img + ti * p.in_st + hi * p.in_sh + wi * p.in_sw + c4 * 4 : p.in;
-                cp_async16_zfill(stageA + e * 4, src, ok ? 16 : 0);
+                else ok = (unsigned)hi < (unsigned)p.Hi && (unsigned)wi < (unsigned)p.Wi;
+                const int off = ok ? ti * ist + hi * ish + wi * isw + csub : 0;
+                cp_async16_u32(dstA + d, in_img + off, ok ? 16 : 0);
             }
         }
         if (g_vec) {
-            const float* go_tile = p.gout + n * p.go_sn + v * p.go_sv + t * p.go_st + h0 * p.go_sh + w0 * p.go_sw;
-            if (g_full && h0 + TH <= p.Ho && w0 + TW <= p.Wo) {
+            const g_t* go_tile = gout + c.n * p.go_sn + c.v * p.go_sv + (int64_t)(c.t * (int)p.go_st + c.h0 * (int)p.go_sh + c.w0 * (int)p.go_sw);
+            if (g_full && c.h0 + TH <= p.Ho && c.w0 + TW <= p.Wo) {
+#pragma unroll
+                for (int i = 0; i < NELG; ++i)
+                    if (tid + i * 128 < TOTALG) cp_async16_u32(dstG + i * DSTEPG, go_tile + rel_g[i], 16);
+            } else {
 #pragma unroll
                 for (int i = 0; i < NELG; ++i) {
                     const int e = tid + i * 128;
-                    if (e < TOTALG) cp_async16_zfill(stageG + e * 4, go_tile + rel_g[i], 16);
-                }
-            } else {
-#pragma unroll 1
-                for (int e = tid; e < TOTALG; e += 128) {
-                    const int c4 = e % (NC / 4), pix = e / (NC / 4);
-                    const int h = h0 + pix / TW, w = w0 + pix % TW;
-                    const int co = occ * NC + c4 * 4;
-                    const bool ok = h < p.Ho && w < p.Wo && co + 3 < p.FCO;
-                    const float* src = ok ? go_tile + (pix / TW) * p.go_sh + (pix % TW) * p.go_sw + co : p.gout;
-                    cp_async16_zfill(stageG + e * 4, src, ok ? 16 : 0);
+                    if (e < TOTALG) {
+                        const int cc = e % GE, pix = e / GE;
+                        const int co = occ * NC + cc * ESCG;
+                        const bool ok = c.h0 + pix / TW < p.Ho && c.w0 + pix % TW < p.Wo && co + ESCG - 1 < p.FCO;
+                        cp_async16_u32(dstG + i * DSTEPG, ok ? go_tile + rel_g[i] : gout, ok ? 16 : 0);
+                    }
                 }
             }
         }
         cp_async_commit();
     };
-    if (t_begin < t_end) issue(t_begin);
-    for (int64_t tile = t_begin; tile < t_end; ++tile) {
+    Tile nxt{};
+    if (t_begin < t_end) { nxt = decode(t_begin); issue(nxt, 0); }
+    int buf = 0;
+    for (int64_t tile = t_begin; tile < t_end; ++tile, buf ^= 1) {
+        const Tile c = nxt;
         cp_async_wait<0>();
         __syncthreads();
-        for (int e = tid; e < NPIX * 4; e += 128) {
-            const float4 f = ld4(stageA + e * 4);
-            *reinterpret_cast<uint2*>(tileA + (e >> 2) * CPA + (e & 3) * 4) = make_uint2(pack_bf16(f.x, f.y), pack_bf16(f.z, f.w));
-        }
-        if (g_vec) {
-            for (int e = tid; e < TH * TW * (NC / 4); e += 128) {
-                const int c4 = e % (NC / 4), pix = e / (NC / 4);
-                const float4 f = ld4(stageG + e * 4);
-                *reinterpret_cast<uint2*>(tileG + pix * CPG + c4 * 4) = make_uint2(pack_bf16(f.x, f.y), pack_bf16(f.z, f.w));
+        const __nv_bfloat16* tileA = tileA0 + (A16 ? buf * (A_TILE / 2) : 0);
+        const __nv_bfloat16* tileG = tileG0 + (G16 ? buf * (G_TILE / 2) : 0);
+        if (!A16) {
+            for (int e = tid; e < NPIX * 4; e += 128) {
+                const float4 f = ld4(stageA + e * 4);
+                *reinterpret_cast<uint2*>(tileA0 + (e >> 2) * CPA + (e & 3) * 4) = make_uint2(pack_bf16(f.x, f.y), pack_bf16(f.z, f.w));
             }
-        } else {                                   // Cout not a multiple of 4 (the 1-channel logit convs): scalar fetch
-            int n, v, t, h0, w0;
-            decode(tile, n, v, t, h0, w0);
-            const float* go_img = p.gout + n * p.go_sn + v * p.go_sv + t * p.go_st;
-            for (int e = tid; e < TH * TW * (NC / 4); e += 128) {
-                const int c4 = e % (NC / 4), pix = e / (NC / 4);
-                const int h = h0 + pix / TW, w = w0 + pix % TW;
-                const int co = occ * NC + c4 * 4;
-                float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (h < p.Ho && w < p.Wo) {
-                    const float* g = go_img + h * p.go_sh + w * p.go_sw + co;
-                    if (co < p.FCO) f.x = __ldg(g); if (co + 1 < p.FCO) f.y = __ldg(g + 1);
-                    if (co + 2 < p.FCO) f.z = __ldg(g + 2); if (co + 3 < p.FCO) f.w = __ldg(g + 3);
+        }
+        if (!G16) {
+            if (g_vec) {
+                for (int e = tid; e < TH * TW * (NC / 4); e += 128) {
+                    const int c4 = e % (NC / 4), pix = e / (NC / 4);
+                    const float4 f = ld4(stageG + e * 4);
+                    *reinterpret_cast<uint2*>(tileG0 + pix * CPG + c4 * 4) = make_uint2(pack_bf16(f.x, f.y), pack_bf16(f.z, f.w));
                 }
-                *reinterpret_cast<uint2*>(tileG + pix * CPG + c4 * 4) = make_uint2(pack_bf16(f.x, f.y), pack_bf16(f.z, f.w));
+            } else {                                   // Cout not a multiple of 4 (the 1-channel logit convs): scalar fetch
+                const int h0 = c.h0, w0 = c.w0;
+                const float* go_img = reinterpret_cast<const float*>(p.gout) + c.n * p.go_sn + c.v * p.go_sv + c.t * p.go_st;
+                for (int e = tid; e < TH * TW * (NC / 4); e += 128) {
+                    const int c4 = e % (NC / 4), pix = e / (NC / 4);
+                    const int h = h0 + pix / TW, w = w0 + pix % TW;
+                    const int co = occ * NC + c4 * 4;
+                    float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (h < p.Ho && w < p.Wo) {
+                        const float* g = go_img + h * p.go_sh + w * p.go_sw + co;
+                        if (co < p.FCO) f.x = __ldg(g); if (co + 1 < p.FCO) f.y = __ldg(g + 1);
+                        if (co + 2 < p.FCO) f.z = __ldg(g + 2); if (co + 3 < p.FCO) f.w = __ldg(g + 3);
+                    }
+                    *reinterpret_cast<uint2*>(tileG0 + pix * CPG + c4 * 4) = make_uint2(pack_bf16(f.x, f.y), pack_bf16(f.z, f.w));
+                }
             }
         }
-        __syncthreads();
-        if (tile + 1 < t_end) issue(tile + 1);      // next tile's loads fly while this tile's MMAs run
+        if (!A16 || !G16) __syncthreads();
+        if (tile + 1 < t_end) { nxt = decode(tile + 1); issue(nxt, buf ^ 1); }   // next tile's loads fly while this tile's MMAs run
 #pragma unroll
         for (int ks = 0; ks < TH; ++ks) {            // k-step = one tile row of 16 pixels
             uint32_t b[NTL / 2 > 0 ? NTL / 2 : 1][4];
@@ -694,31 +870,47 @@ int launch_tc(P p, const Plan& pl, int n_img_t, cudaStream_t st, const char* who
     return 0;
 }
 
-template <int MODE, int NTL>
+template <int MODE, int NTL, bool IN16, bool OUT16>
 int launch_tc16(const P& p, int n_img_t, cudaStream_t st, const char* who) {
     constexpr int KTIN = (MODE == CLS_FWD) ? 2 : (MODE == CLS_DGRAD ? 1 : 3);
     constexpr int NTF = (MODE == CLS_FWD || MODE == CLS_DGRAD) ? 18 : 27;
-    const size_t smem = sizeof(uint2) * NTF * NTL * 32 + (size_t)KTIN * HH * HW_ * (16 * 4 + 24 * 2);
-    auto kern = conv_tc16_kernel<MODE, NTL>;
+    const size_t smem = sizeof(uint2) * NTF * NTL * 32 + (size_t)KTIN * HH * HW_ * (IN16 ? 2 * 24 * 2 : 16 * 4 + 24 * 2);
+    auto kern = conv_tc16_kernel<MODE, NTL, IN16, OUT16>;
     IDEE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), who);
     const int tiles_h = (p.Ho + TH - 1) / TH;
     const int64_t total = (int64_t)n_img_t * tiles_h * p.tiles_w;
-    IDEE_REQUIRE(total < (1ll << 31) && 3 * p.in_st + HH * p.in_sh + HW_ * p.in_sw < (1ll << 31) &&
-                 TH * p.out_sh + TW * p.out_sw < (1ll << 31), "%s: tensor too large for 32-bit tile-relative offsets", who);
+    IDEE_REQUIRE(total < (1ll << 31) && (p.Ti + 3) * p.in_st + (p.Hi + HH) * p.in_sh + (p.Wi + HW_) * p.in_sw < (1ll << 31) &&
+                 (p.To + 1) * p.out_st + (p.Ho + TH) * p.out_sh + (p.Wo + TW) * p.out_sw < (1ll << 31),
+                 "%s: tensor too large for 32-bit image-relative offsets", who);
+    IDEE_REQUIRE(!OUT16 || (p.CO % 2 == 0 && p.relu_src == nullptr), "%s: bf16 output needs an even channel count and no mask", who);
     int per_sm = 1;
     IDEE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C16_THREADS, smem), who);
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)idee_num_sms() * per_sm;
     if (grid > total) grid = total;
-    kern<<<(unsigned)grid, C16_THREADS, smem, st>>>(p, total, tiles_h);
+    kern<<<(unsigned)grid, C16_THREADS, smem, st>>>(p, total, make_fastdiv(p.tiles_w), make_fastdiv(tiles_h), make_fastdiv(p.To),
+                                                    make_fastdiv(p.V));
     IDEE_LAUNCH_CHECK(who);
     return 0;
 }
 
 template <int MODE>
 int dispatch_tc(const P& p, const Plan& pl, int n_img_t, cudaStream_t st, const char* who) {
-    if (pl.KS == 1 && p.CIr == 16 && pl.n_oc == 1 && pl.NTL == 2) return launch_tc16<MODE, 2>(p, n_img_t, st, who);
-    if (pl.KS == 1 && p.CIr == 16 && pl.n_oc == 1 && pl.NTL == 1) return launch_tc16<MODE, 1>(p, n_img_t, st, who);
+    if (p.in16 || p.out16) {       // bf16 activation storage: 16 -> 16 proj conv (forward: any mix, data gradient: bf16 input)
+        if (pl.KS == 1 && p.CIr == 16 && pl.n_oc == 1 && pl.NTL == 2) {
+            if constexpr (MODE == PROJ_FWD) {
+                if (p.in16 && p.out16) return launch_tc16<MODE, 2, true, true>(p, n_img_t, st, who);
+                if (p.in16) return launch_tc16<MODE, 2, true, false>(p, n_img_t, st, who);
+                return launch_tc16<MODE, 2, false, true>(p, n_img_t, st, who);
+            } else if constexpr (MODE == PROJ_DGRAD_PAD) {
+                if (p.in16 && !p.out16) return launch_tc16<MODE, 2, true, false>(p, n_img_t, st, who);
+            }
+        }
+        idee_set_error("%s: bf16 activation storage is not built for this configuration", who);
+        return 1;
+    }
+    if (pl.KS == 1 && p.CIr == 16 && pl.n_oc == 1 && pl.NTL == 2) return launch_tc16<MODE, 2, false, false>(p, n_img_t, st, who);
+    if (pl.KS == 1 && p.CIr == 16 && pl.n_oc == 1 && pl.NTL == 1) return launch_tc16<MODE, 1, false, false>(p, n_img_t, st, who);
     if (pl.KS == 1 && pl.NTL == 2) return launch_tc<MODE, 1, 2, false>(p, pl, n_img_t, st, who);
     if (pl.KS == 1 && pl.NTL == 1) return launch_tc<MODE, 1, 1, false>(p, pl, n_img_t, st, who);
     if (pl.KS == 1 && pl.NTL == 12) return launch_tc<MODE, 1, 12, false>(p, pl, n_img_t, st, who);
@@ -762,13 +954,14 @@ size_t conv_tc_dgrad_workspace_bytes(const idee_conv_desc* d) {
     return b;
 }
 
-int conv_tc_fwd(const idee_conv_desc* d, const float* x, const float* w, const float* b, float* y, void* ws, cudaStream_t st) {
-    if (conv_umma_eligible(d)) return conv_umma_run(d, 0, x, w, b, nullptr, y, ws, st);
+int conv_tc_fwd(const idee_conv_desc* d, const void* x, const float* w, const float* b, void* y, void* ws, cudaStream_t st) {
+    if (conv_umma_eligible(d)) return conv_umma_run(d, 0, (const float*)x, w, b, nullptr, (float*)y, ws, st);
     const int mode = d->proj ? PROJ_FWD : CLS_FWD;
     const Plan pl = make_plan(mode, d->Cin, d->Cout, d->Vw);
     if (prep(d, w, (uint2*)ws, pl, 0, st)) return 2;
     P p{};
-    p.in = x; p.out = y; p.bias = b; p.relu_src = nullptr; p.wfrag = (const uint2*)ws;
+    p.in = (const float*)x; p.out = (float*)y; p.bias = b; p.relu_src = nullptr; p.wfrag = (const uint2*)ws;
+    p.in16 = d->x_dtype; p.out16 = d->y_dtype;
     p.N = d->N; p.V = d->V; p.Vw = d->Vw;
     p.Ti = d->Ti; p.Hi = d->Hi; p.Wi = d->Wi; p.To = d->To; p.Ho = d->Ho; p.Wo = d->Wo;
     p.in_sn = d->x_sn; p.in_sv = d->x_sv; p.in_st = d->x_st; p.in_sh = d->x_sh; p.in_sw = d->x_sw; p.in_sg = d->x_sg; p.in_cpg = d->in_cpg;
@@ -778,19 +971,20 @@ int conv_tc_fwd(const idee_conv_desc* d, const float* x, const float* w, const f
     return d->proj ? dispatch_tc<PROJ_FWD>(p, pl, nit, st, "conv3d_fwd(proj,bf16)") : dispatch_tc<CLS_FWD>(p, pl, nit, st, "conv3d_fwd(cls,bf16)");
 }
 
-int conv_tc_dgrad(const idee_conv_desc* d, const float* gy, const float* w, const float* relu_src, float* gx, void* ws, cudaStream_t st) {
-    if (conv_umma_eligible(d)) return conv_umma_run(d, 1, gy, w, nullptr, relu_src, gx, ws, st);
+int conv_tc_dgrad(const idee_conv_desc* d, const void* gy, const float* w, const void* relu_src, void* gx, void* ws, cudaStream_t st) {
+    if (conv_umma_eligible(d)) return conv_umma_run(d, 1, (const float*)gy, w, nullptr, (const float*)relu_src, (float*)gx, ws, st);
     const int mode = d->proj ? PROJ_DGRAD_PAD : CLS_DGRAD;
     const Plan pl = make_plan(mode, d->Cout, d->Cin, d->Vw);
     if (prep(d, w, (uint2*)ws, pl, 1, st)) return 2;
     P p{};
-    p.in = gy; p.bias = nullptr; p.wfrag = (const uint2*)ws;
+    p.in = (const float*)gy; p.bias = nullptr; p.wfrag = (const uint2*)ws;
+    p.in16 = d->y_dtype; p.out16 = 0;
     p.N = d->N; p.V = d->V; p.Vw = d->Vw;
     p.Ti = d->To; p.Hi = d->Ho; p.Wi = d->Wo;
     p.in_sn = d->y_sn; p.in_sv = d->y_sv; p.in_st = d->y_st; p.in_sh = d->y_sh; p.in_sw = d->y_sw; p.in_sg = d->y_sg; p.in_cpg = d->out_cpg;
     p.CO = d->Cin; p.CIr = d->Cout; p.NTf = pl.NTf; p.relu = 0;
     if (!d->proj) {
-        p.out = gx; p.relu_src = relu_src;
+        p.out = (float*)gx; p.relu_src = (const float*)relu_src;
         p.To = d->Ti; p.Ho = d->Hi; p.Wo = d->Wi;
         p.out_sn = d->x_sn; p.out_sv = d->x_sv; p.out_st = d->x_st; p.out_sh = d->x_sh; p.out_sw = d->x_sw; p.out_sg = d->x_sg; p.out_cpg = d->in_cpg;
         p.tiles_w = (p.Wo + TW - 1) / TW;
@@ -808,11 +1002,17 @@ int conv_tc_dgrad(const idee_conv_desc* d, const float* gy, const float* w, cons
     p.out_sn = p.out_sv * d->V; p.out_sg = 0; p.out_cpg = 1;
     p.tiles_w = (p.Wo + TW - 1) / TW;
     if (dispatch_tc<PROJ_DGRAD_PAD>(p, pl, d->N * d->V * Tp, st, "conv3d_dgrad(proj,bf16)")) return 2;
-    const int64_t total = (int64_t)d->N * d->V * d->Ti * d->Hi * d->Wi * 4;
-    int nb = (int)((total + 255) / 256);
-    const int cap = idee_num_sms() * 16;
+    const int64_t rows64 = (int64_t)d->N * d->V * d->Ti * d->Hi;
+    IDEE_REQUIRE(rows64 < (1ll << 31), "conv3d_dgrad(proj,bf16): too many rows for the fold stage");
+    const int rows = (int)rows64;
+    int nb = rows;
+    const int cap = idee_num_sms() * 8;
     if (nb > cap) nb = cap;
-    fold_pad_kernel<<<nb, 256, 0, st>>>(gpad, gx, relu_src, d->N * d->V, d->Ti, d->Hi, d->Wi);
+    const FastDiv fh = make_fastdiv(d->Hi), ft = make_fastdiv(d->Ti);
+    if (d->gx_dtype && d->x_dtype) fold_pad_kernel<true, true><<<nb, 256, 0, st>>>(gpad, gx, relu_src, rows, d->Ti, d->Hi, d->Wi, fh, ft);
+    else if (d->gx_dtype) fold_pad_kernel<true, false><<<nb, 256, 0, st>>>(gpad, gx, relu_src, rows, d->Ti, d->Hi, d->Wi, fh, ft);
+    else if (d->x_dtype) fold_pad_kernel<false, true><<<nb, 256, 0, st>>>(gpad, gx, relu_src, rows, d->Ti, d->Hi, d->Wi, fh, ft);
+    else fold_pad_kernel<false, false><<<nb, 256, 0, st>>>(gpad, gx, relu_src, rows, d->Ti, d->Hi, d->Wi, fh, ft);
     IDEE_LAUNCH_CHECK("conv3d_dgrad fold");
     return 0;
 }
@@ -834,9 +1034,10 @@ size_t conv_tc_wgrad_workspace_bytes(const idee_conv_desc* d) {
 }
 
 // launches the tensor-core partial kernel; the caller (conv.cu) runs the shared reduce stage with S = conv_tc_wgrad_splits
-int conv_tc_wgrad_partials(const idee_conv_desc* d, const float* x, const float* gy, float* partials, cudaStream_t st) {
+int conv_tc_wgrad_partials(const idee_conv_desc* d, const void* x, const void* gy, float* partials, cudaStream_t st) {
     WP p{};
     p.in = x; p.gout = gy; p.partials = partials;
+    p.a16 = d->x_dtype; p.g16 = d->y_dtype;
     p.N = d->N; p.V = d->V; p.Vw = d->Vw;
     p.Ti = d->Ti; p.Hi = d->Hi; p.Wi = d->Wi; p.To = d->To; p.Ho = d->Ho; p.Wo = d->Wo;
     p.in_sn = d->x_sn; p.in_sv = d->x_sv; p.in_st = d->x_st; p.in_sh = d->x_sh; p.in_sw = d->x_sw; p.in_sg = d->x_sg; p.in_cpg = d->in_cpg;
@@ -845,22 +1046,36 @@ int conv_tc_wgrad_partials(const idee_conv_desc* d, const float* x, const float*
     p.n_ic = (d->Cin + 15) / 16; p.n_oc16 = (d->Cout + 15) / 16; p.S = conv_tc_wgrad_splits(d);
     p.tiles_h = (d->Ho + TH - 1) / TH; p.tiles_w = (d->Wo + TW - 1) / TW;
     p.tiles_per_set = (int64_t)d->N * (d->Vw == 1 ? d->V : 1) * d->To * p.tiles_h * p.tiles_w;
+    p.fd_to = make_fastdiv(d->To); p.fd_tw = make_fastdiv(p.tiles_w); p.fd_th = make_fastdiv(p.tiles_h);
+    p.fd_ipn = make_fastdiv(d->Vw == 1 ? d->V : 1);
+    IDEE_REQUIRE(p.tiles_per_set < (1ll << 31), "conv3d_wgrad(bf16): too many tiles for 32-bit tile indices");
     const int NC = conv_tc_wgrad_ncout(d);
     const int n_occ = (p.n_oc16 * 16 + NC - 1) / NC;
     // the partial buffer is only partly written when Cout is not a multiple of 16 (Cout == 1): clear it first
     if (d->Cout % 16) IDEE_CUDA(cudaMemsetAsync(partials, 0, conv_tc_wgrad_workspace_bytes(d), st), "conv3d_wgrad(bf16)");
     dim3 grid(p.S, d->Vw, p.n_ic * n_occ);
     const int KTIN = d->proj ? 3 : 2;
-    const size_t smem = (size_t)KTIN * HH * HW_ * (16 * 4 + 24 * 2) + (size_t)TH * TW * (NC * 4 + (NC + 8) * 2);
-#define IDEE_WGRAD_LAUNCH(NT_, NTL_)                                                                                       \
+    const size_t smem = (size_t)KTIN * HH * HW_ * (p.a16 ? 2 * 24 * 2 : 16 * 4 + 24 * 2) +
+                        (size_t)TH * TW * (p.g16 ? 2 * (NC + 8) * 2 : NC * 4 + (NC + 8) * 2);
+    IDEE_REQUIRE((int64_t)(d->Ti + 3) * d->x_st + (int64_t)(d->Hi + HH) * d->x_sh + (int64_t)(d->Wi + HW_) * d->x_sw < (1ll << 31) &&
+                 (int64_t)(d->To + 1) * d->y_st + (int64_t)(d->Ho + TH) * d->y_sh + (int64_t)(d->Wo + TW) * d->y_sw < (1ll << 31),
+                 "conv3d_wgrad(bf16): tensor too large for 32-bit image-relative offsets");
+#define IDEE_WGRAD_LAUNCH(NT_, NTL_, A_, G_)                                                                               \
     do {                                                                                                                   \
-        IDEE_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<NT_, NTL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "conv3d_wgrad(bf16)"); \
-        wgrad_tc_kernel<NT_, NTL_><<<grid, 128, smem, st>>>(p);                                                            \
+        IDEE_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<NT_, NTL_, A_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "conv3d_wgrad(bf16)"); \
+        wgrad_tc_kernel<NT_, NTL_, A_, G_><<<grid, 128, smem, st>>>(p);                                                    \
     } while (0)
-    if (d->proj) { if (NC == 16) IDEE_WGRAD_LAUNCH(27, 2); else { idee_set_error("conv3d_wgrad(proj,bf16): Cout must be 16"); return 1; } }
-    else if (NC == 32) IDEE_WGRAD_LAUNCH(18, 4);
-    else if (NC == 16) IDEE_WGRAD_LAUNCH(18, 2);
-    else IDEE_WGRAD_LAUNCH(18, 1);
+    if (d->proj) {
+        if (NC != 16) { idee_set_error("conv3d_wgrad(proj,bf16): Cout must be 16"); return 1; }
+        if (p.a16 && p.g16) IDEE_WGRAD_LAUNCH(27, 2, true, true);
+        else if (p.a16) IDEE_WGRAD_LAUNCH(27, 2, true, false);
+        else if (p.g16) IDEE_WGRAD_LAUNCH(27, 2, false, true);
+        else IDEE_WGRAD_LAUNCH(27, 2, false, false);
+    }
+    else if (p.a16 || p.g16) { idee_set_error("conv3d_wgrad(cls,bf16): bf16 activation storage is not built"); return 1; }
+    else if (NC == 32) IDEE_WGRAD_LAUNCH(18, 4, false, false);
+    else if (NC == 16) IDEE_WGRAD_LAUNCH(18, 2, false, false);
+    else IDEE_WGRAD_LAUNCH(18, 1, false, false);
 #undef IDEE_WGRAD_LAUNCH
     IDEE_LAUNCH_CHECK("conv3d_wgrad(bf16)");
     return 0;

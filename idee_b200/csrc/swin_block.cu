@@ -45,6 +45,7 @@ struct Geom {
     int n_wg;     // window groups (warps' worth of windows) per variable
     int tbl;      // rows of the rpb table
     float scale;
+    void* out16;  // forward, bf16 path: optional bf16 copy of the block output (for the proj conv that consumes it)
 };
 
 __device__ __forceinline__ int region_id(int p, int S, int ws, int ss) {
@@ -731,10 +732,12 @@ extern "C" size_t idee_swin_block_bwd_workspace_bytes(const idee_swin_desc* d) {
     return sizeof(float) * (size_t)d->V * per_v * (ATT_PART_W + NH * Gt * Gt + MLP_PART);
 }
 
-extern "C" int idee_swin_block_fwd(const idee_swin_desc* d, const float* x, float* out, float* ymid, const float* params,
-                                   const int32_t* rel_index, void* stream) {
+extern "C" int idee_swin_block_fwd(const idee_swin_desc* d, const float* x, float* out, float* ymid, void* out_bf16,
+                                   const float* params, const int32_t* rel_index, void* stream) {
     Geom g;
     if (make_geom(g, d, "swin_block_fwd")) return 1;
+    IDEE_REQUIRE(out_bf16 == nullptr || d->precision == 1, "swin_block_fwd: the bf16 output copy is only produced by the bf16 path");
+    g.out16 = out_bf16;
     cudaStream_t st = (cudaStream_t)stream;
     SWIN_DISPATCH(launch_fwd, d, g, x, out, ymid, params, rel_index, st)
 }

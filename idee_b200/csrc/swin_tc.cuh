@@ -118,6 +118,14 @@ __device__ __forceinline__ void store_tile(float* base, const float (&t)[4][4], 
             *reinterpret_cast<float2*>(base + tr.off[r] + c0 + 8) = make_float2(t[r][2], t[r][3]);
         }
 }
+__device__ __forceinline__ void store_tile_bf16(__nv_bfloat16* base, const float (&t)[4][4], const TokRows& tr, int c0) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+        if (tr.valid[r]) {
+            *reinterpret_cast<__nv_bfloat162*>(base + tr.off[r] + c0) = __floats2bfloat162_rn(t[r][0], t[r][1]);
+            *reinterpret_cast<__nv_bfloat162*>(base + tr.off[r] + c0 + 8) = __floats2bfloat162_rn(t[r][2], t[r][3]);
+        }
+}
 // LayerNorm(16, eps 1e-5, no affine) of every row; rows flagged invalid become exact zeros (padding after LN1)
 __device__ __forceinline__ void ln_tile(const float (&x)[4][4], float (&xn)[4][4], float (&rstd)[4], const bool* valid) {
 #pragma unroll
@@ -363,6 +371,7 @@ swin_fwd_tc_kernel(const float* __restrict__ x, float* __restrict__ out, float* 
             gemm16(acc, h, wf + (16 + 2 * kk) * 32, lane);
         }
         store_tile(out, acc, tr, c0);
+        if (g.out16) store_tile_bf16(reinterpret_cast<__nv_bfloat16*>(g.out16), acc, tr, c0);
     }
 }
 

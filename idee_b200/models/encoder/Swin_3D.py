@@ -16,7 +16,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from ... import ops
+from ... import _lib, ops
 
 
 def get_window_size(x_size, window_size, shift_size=None):
@@ -254,15 +254,23 @@ class Swin_3D(nn.Module):
         pk = self._packs
         E = self.embed_dim[-1]
         tok = ops.embed_ln(x, pk["embed_w"], pk["embed_b"])
-        for l, b, pack in pk["blocks"]:
+        # bf16 mode: the tensor-core proj convs round their operands to bf16 when they load them, so the tensors only they
+        # consume (the last block's output and the hidden ReLU activation, plus the hidden gradient in backward) are kept in
+        # HBM as bf16 -- bit-identical results, half the traffic, and no conversion pass in the conv kernels.
+        bf16_io = _lib.PRECISION == "bf16" and E == 16
+        tok16 = None
+        for i, (l, b, pack) in enumerate(pk["blocks"]):
             blk = self.layers_var[0][l].blocks[b]
             ws, ss, idx, rows, scale, heads, hidden = blk.kernel_args(D, H, W)
-            tok = ops.swin_block(tok, pack, idx, ws, ss, rows, scale, heads, hidden)
+            if bf16_io and i == len(pk["blocks"]) - 1:
+                tok, tok16 = ops.swin_block(tok, pack, idx, ws, ss, rows, scale, heads, hidden, want_bf16=True)
+            else:
+                tok = ops.swin_block(tok, pack, idx, ws, ss, rows, scale, heads, hidden)
         w0, b0 = ops.packed(pk["proj0_w"], (V, E, E, 3, 3, 3)), ops.packed(pk["proj0_b"], (V, E))
         w2, b2 = ops.packed(pk["proj2_w"], (V, E, E, 3, 3, 3)), ops.packed(pk["proj2_b"], (V, E))
         # conv -> ReLU -> conv: the second conv is the only consumer of the ReLU output, so its data-gradient epilogue applies
         # the ReLU backward mask and the first conv skips the separate pass
-        tok = ops.conv3d_cl(tok, w0, b0, proj=True, relu=True, consumer_masks=True)
+        tok = ops.conv3d_cl(tok, w0, b0, proj=True, relu=True, consumer_masks=True, x16=tok16, out_bf16=bf16_io)
         tok = ops.conv3d_cl(tok, w2, b2, proj=True, relu=False, input_is_relu=True)
         return tok
 

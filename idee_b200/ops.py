@@ -149,7 +149,8 @@ class SwinBlock(torch.autograd.Function):
     """tokens [N,V,T,H,W,16] -> same; one launch for all V variables.  Swin_3D.py:224-287."""
 
     @staticmethod
-    def forward(ctx, x, pack: ParamPack, rel_index, window, shift, rpb_rows, scale, heads, hidden, *params):
+    def forward(ctx, x, pack: ParamPack, rel_index, window, shift, rpb_rows, scale, heads, hidden, want_bf16, *params):
+        """want_bf16 (bf16 mode only): also return a non-differentiable bf16 copy of the output, written by the same kernel."""
         L.require_cuda(x)
         lib = L.load()
         x = _f32c(x)
@@ -160,15 +161,19 @@ class SwinBlock(torch.autograd.Function):
         out = torch.empty_like(x)
         need_bwd = any(ctx.needs_input_grad)
         ymid = torch.empty_like(x) if need_bwd else None
-        L.run("swin_block_fwd", lib.idee_swin_block_fwd, C.byref(d), x.data_ptr(), out.data_ptr(), L.ptr(ymid), flat.data_ptr(),
-              rel_index.data_ptr(), L.stream(), tag=f"w{window} s{shift}")
+        out16 = torch.empty_like(x, dtype=torch.bfloat16) if want_bf16 else None
+        L.run("swin_block_fwd", lib.idee_swin_block_fwd, C.byref(d), x.data_ptr(), out.data_ptr(), L.ptr(ymid), L.ptr(out16),
+              flat.data_ptr(), rel_index.data_ptr(), L.stream(), tag=f"w{window} s{shift}")
         if need_bwd:
             ctx.save_for_backward(x, ymid, rel_index)
             ctx.pack, ctx.args = pack, (window, shift, rpb_rows, scale, heads, hidden)
+        if want_bf16:
+            ctx.mark_non_differentiable(out16)
+            return out, out16
         return out
 
     @staticmethod
-    def backward(ctx, gout):
+    def backward(ctx, gout, *_unused):
         lib = L.load()
         x, ymid, rel_index = ctx.saved_tensors
         pack = ctx.pack
@@ -182,11 +187,13 @@ class SwinBlock(torch.autograd.Function):
         ws = L.workspace(nws, x.device)
         L.run("swin_block_bwd", lib.idee_swin_block_bwd, C.byref(d), x.data_ptr(), ymid.data_ptr(), gout.data_ptr(), gx.data_ptr(), flat.data_ptr(),
                                         rel_index.data_ptr(), gflat.data_ptr(), ws.data_ptr(), nws, L.stream(), tag=f"w{window} s{shift}")
-        return (gx, None, None, None, None, None, None, None, None, *pack.split_grad(gflat))
+        return (gx, None, None, None, None, None, None, None, None, None, *pack.split_grad(gflat))
 
 
-def swin_block(x, pack: ParamPack, rel_index, window, shift, rpb_rows, scale, heads, hidden):
-    return SwinBlock.apply(x, pack, rel_index, tuple(window), tuple(shift), rpb_rows, float(scale), heads, hidden, *pack.params())
+def swin_block(x, pack: ParamPack, rel_index, window, shift, rpb_rows, scale, heads, hidden, want_bf16: bool = False):
+    """-> out, or (out, out_bf16) when want_bf16 (bf16 mode; the copy feeds a bf16-storage conv, see Conv3dCL)."""
+    return SwinBlock.apply(x, pack, rel_index, tuple(window), tuple(shift), rpb_rows, float(scale), heads, hidden,
+                           bool(want_bf16), *pack.params())
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -210,41 +217,53 @@ def _conv_desc(x_dims, x_strides, y_strides, Vw, Cin, Cout, proj, relu, in_cpg, 
 
 class Conv3dCL(torch.autograd.Function):
     """x: channel-last storage viewed as [N,V,Ti,Hi,Wi,Cg] (Cg contiguous); `groups` > 1 reads dim 1 as channel groups
-    (joint classifier head over the V planes of z_q).  Output [N,Vimg,To,Ho,Wo,Cout] contiguous."""
+    (joint classifier head over the V planes of z_q).  Output [N,Vimg,To,Ho,Wo,Cout] contiguous.
+
+    bf16 activation storage (bf16 mode, 16 -> 16 proj conv only): the tensor-core kernels round their operands to bf16 as they
+    load them, so an activation that only such kernels consume can live in HBM as bf16 with bit-identical results:
+      * ``x`` itself may be a bf16 tensor (then its gradient is produced in bf16 too);
+      * ``x16`` is a bf16 copy of an fp32 ``x`` made by the producer; it replaces ``x`` as the kernels' input (the gradient
+        w.r.t. ``x`` stays fp32);
+      * ``out_bf16`` stores the output as bf16 (and its incoming gradient is then bf16)."""
 
     @staticmethod
-    def forward(ctx, x, w, b, proj, relu, groups, input_is_relu=False, consumer_masks=False):
+    def forward(ctx, x, w, b, proj, relu, groups, input_is_relu=False, consumer_masks=False, x16=None, out_bf16=False):
         """input_is_relu: x is the fused-ReLU output of a conv whose ONLY consumer is this op -> this op's data gradient is
         multiplied by (x > 0) in the kernel epilogue.  consumer_masks: the (only) consumer of this op's ReLU output does
         exactly that, so the incoming gradient is already masked and no separate ReLU-backward pass is needed."""
         L.require_cuda(x, w)
         lib = L.load()
-        if x.dtype != torch.float32:
-            x = x.float()
-        if x.stride(5) != 1 and x.shape[5] != 1:
-            x = x.contiguous()
-        N, V, Ti, Hi, Wi, Cg = x.shape
+        gx_dtype = torch.bfloat16 if (x.dtype == torch.bfloat16 and x16 is None) else torch.float32
+        xin = x16 if x16 is not None else x
+        if x16 is not None:
+            assert x16.dtype == torch.bfloat16 and x16.shape == x.shape and x16.stride() == x.stride()
+        elif xin.dtype not in (torch.float32, torch.bfloat16):
+            xin = xin.float()
+        if xin.stride(5) != 1 and xin.shape[5] != 1:
+            xin = xin.contiguous()
+        N, V, Ti, Hi, Wi, Cg = xin.shape
         w = _f32c(w)
         b = _f32c(b)
         Vw = w.shape[0]                      # w: [Vw][Cout][Cin][kt][3][3]
         Cout, Cin = w.shape[1], w.shape[2]
         if groups > 1:
             assert groups == V and Cin == V * Cg and Cg == 16 and Vw == 1
-            Vimg, x_sv, x_sg, in_cpg = 1, 0, x.stride(1), 1
+            Vimg, x_sv, x_sg, in_cpg = 1, 0, xin.stride(1), 1
         else:
             assert Cin == Cg
-            Vimg, x_sv, x_sg, in_cpg = V, x.stride(1), 0, max(Cg // 16, 1)
+            Vimg, x_sv, x_sg, in_cpg = V, xin.stride(1), 0, max(Cg // 16, 1)
         To = Ti if proj else (Ti - 2) // 2 + 1
-        y = torch.empty(N, Vimg, To, Hi, Wi, Cout, device=x.device, dtype=torch.float32)
-        d = _conv_desc((N, Vimg, Ti, Hi, Wi), (x.stride(0), x_sv, x.stride(2), x.stride(3), x.stride(4)),
+        y = torch.empty(N, Vimg, To, Hi, Wi, Cout, device=xin.device, dtype=torch.bfloat16 if out_bf16 else torch.float32)
+        d = _conv_desc((N, Vimg, Ti, Hi, Wi), (xin.stride(0), x_sv, xin.stride(2), xin.stride(3), xin.stride(4)),
                        (y.stride(0), y.stride(1), y.stride(2), y.stride(3), y.stride(4)), Vw, Cin, Cout, proj, relu,
                        in_cpg, max(Cout // 16, 1), x_sg, 0)
+        d.x_dtype, d.y_dtype, d.gx_dtype = int(xin.dtype == torch.bfloat16), int(out_bf16), int(gx_dtype == torch.bfloat16)
         nws = lib.idee_conv3d_fwd_workspace_bytes(C.byref(d))
-        ws = L.workspace(nws, x.device)
-        L.run("conv3d_fwd_bf16" if d.precision else "conv3d_fwd", lib.idee_conv3d_fwd, C.byref(d), x.data_ptr(), w.data_ptr(),
+        ws = L.workspace(nws, xin.device)
+        L.run("conv3d_fwd_bf16" if d.precision else "conv3d_fwd", lib.idee_conv3d_fwd, C.byref(d), xin.data_ptr(), w.data_ptr(),
               b.data_ptr(), y.data_ptr(), ws.data_ptr(), nws, L.stream(), tag=_conv_tag(d))
-        ctx.save_for_backward(x, w, y if relu else None)
-        ctx.desc, ctx.relu, ctx.groups = d, relu, groups
+        ctx.save_for_backward(xin, w, y if relu else None)
+        ctx.desc, ctx.relu, ctx.groups, ctx.gx_dtype = d, relu, groups, gx_dtype
         ctx.input_is_relu, ctx.consumer_masks = bool(input_is_relu), bool(consumer_masks)
         ctx.grad_dst = (getattr(w, "_idee_grad_dst", None), getattr(b, "_idee_grad_dst", None))
         return y
@@ -254,7 +273,7 @@ class Conv3dCL(torch.autograd.Function):
         lib = L.load()
         x, w, y = ctx.saved_tensors
         d = ctx.desc
-        gy = _f32c(gy)
+        gy = gy.contiguous() if (d.y_dtype and gy.dtype == torch.bfloat16) else (gy.to(torch.bfloat16).contiguous() if d.y_dtype else _f32c(gy))
         if ctx.relu and not ctx.consumer_masks:
             gy = torch.ops.aten.threshold_backward(gy, y, 0.0)
         gw_dst, gb_dst = ctx.grad_dst
@@ -267,7 +286,7 @@ class Conv3dCL(torch.autograd.Function):
                                       L.stream(), tag=_conv_tag(d))
         gx = None
         if ctx.needs_input_grad[0]:
-            gx = torch.empty_strided(x.shape, x.stride(), device=x.device, dtype=torch.float32) if _dense(x) else None
+            gx = torch.empty_strided(x.shape, x.stride(), device=x.device, dtype=ctx.gx_dtype) if _dense(x) else None
             if gx is None:
                 raise RuntimeError("conv3d_dgrad: input must be a dense channel-last tensor")
             nws = lib.idee_conv3d_dgrad_workspace_bytes(C.byref(d))
@@ -275,7 +294,7 @@ class Conv3dCL(torch.autograd.Function):
             relu_src = x.data_ptr() if ctx.input_is_relu else None       # dL/d(pre-activation) = dL/dx * (x > 0), fused
             L.run("conv3d_dgrad_bf16" if d.precision else "conv3d_dgrad", lib.idee_conv3d_dgrad, C.byref(d), gy.data_ptr(),
                   w.data_ptr(), relu_src, gx.data_ptr(), ws.data_ptr(), nws, L.stream(), tag=_conv_tag(d))
-        return gx, gw, gb, None, None, None, None, None
+        return gx, gw, gb, None, None, None, None, None, None, None
 
 
 def _conv_tag(d) -> str:
@@ -293,8 +312,10 @@ def _dense(t: torch.Tensor) -> bool:
     return True
 
 
-def conv3d_cl(x, w, b, proj: bool, relu: bool, groups: int = 1, input_is_relu: bool = False, consumer_masks: bool = False):
-    return Conv3dCL.apply(x, w, b, bool(proj), bool(relu), int(groups), bool(input_is_relu), bool(consumer_masks))
+def conv3d_cl(x, w, b, proj: bool, relu: bool, groups: int = 1, input_is_relu: bool = False, consumer_masks: bool = False,
+              x16=None, out_bf16: bool = False):
+    return Conv3dCL.apply(x, w, b, bool(proj), bool(relu), int(groups), bool(input_is_relu), bool(consumer_masks), x16,
+                          bool(out_bf16))
 
 
 class PackedWB(torch.autograd.Function):

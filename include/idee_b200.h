@@ -58,8 +58,10 @@ typedef struct {
 } idee_swin_desc;
 
 int idee_swin_block_packed_floats(int rpb_rows);
-/* ymid (optional, may be NULL): the mid-block residual x + attn(...) saved for the backward pass */
-int idee_swin_block_fwd(const idee_swin_desc* d, const float* x, float* out, float* ymid, const float* params,
+/* ymid (optional, may be NULL): the mid-block residual x + attn(...) saved for the backward pass.
+ * out_bf16 (optional, may be NULL; precision 1 only): a bf16 copy of `out` in the same layout, written by the same kernel for a
+ * consumer that rounds its input to bf16 anyway (the proj_var conv, see idee_conv_desc.x_dtype) */
+int idee_swin_block_fwd(const idee_swin_desc* d, const float* x, float* out, float* ymid, void* out_bf16, const float* params,
                         const int32_t* rel_index, void* stream);
 size_t idee_swin_block_bwd_workspace_bytes(const idee_swin_desc* d);
 /* gx may alias gout.  gparams: [V][param_stride], every packed element is overwritten. */
@@ -80,22 +82,27 @@ typedef struct {
     int Ti, Hi, Wi, To, Ho, Wo;
     int proj;               /* 1: 3x3x3 replicate, 0: (2,3,3)/(2,1,1) zero-pad */
     int relu;               /* forward: fuse ReLU into the epilogue */
-    int precision;          /* 0: fp32 CUDA-core exact path; 1: bf16 tensor-core operands, fp32 accumulate (fp32 I/O either way);
+    int precision;          /* 0: fp32 CUDA-core exact path; 1: bf16 tensor-core operands, fp32 accumulate;
                                2: as 1, and the 96->96 classifier conv (forward / data gradient) runs on tcgen05 + TMEM */
     int64_t x_sn, x_sv, x_st, x_sh, x_sw, x_sg; int in_cpg;
     int64_t y_sn, y_sv, y_st, y_sh, y_sw, y_sg; int out_cpg;
+    /* element type of the activation tensors, 0: float (default), 1: bf16.  bf16 storage is accepted by the precision >= 1
+     * 16 -> 16 proj conv only: those kernels round their operands to bf16 when they load them, so keeping the bf16 copy in
+     * HBM gives bit-identical results with half the traffic and no conversion pass.  Strides stay in elements.
+     *   x_dtype: x (forward / weight gradient) and relu_src (data gradient);  y_dtype: y and gy;  gx_dtype: gx */
+    int x_dtype, y_dtype, gx_dtype;
 } idee_conv_desc;
 
 size_t idee_conv3d_fwd_workspace_bytes(const idee_conv_desc* d);
-int idee_conv3d_fwd(const idee_conv_desc* d, const float* x, const float* w, const float* b, float* y,
+int idee_conv3d_fwd(const idee_conv_desc* d, const void* x, const float* w, const float* b, void* y,
                     void* workspace, size_t workspace_bytes, void* stream);
 /* gx = conv^T(gy); when relu_src != NULL (same layout as gx) gx is multiplied by (relu_src > 0): the ReLU that
  * produced this conv's input is folded into the data gradient */
 size_t idee_conv3d_dgrad_workspace_bytes(const idee_conv_desc* d);
-int idee_conv3d_dgrad(const idee_conv_desc* d, const float* gy, const float* w, const float* relu_src, float* gx,
+int idee_conv3d_dgrad(const idee_conv_desc* d, const void* gy, const float* w, const void* relu_src, void* gx,
                       void* workspace, size_t workspace_bytes, void* stream);
 size_t idee_conv3d_wgrad_workspace_bytes(const idee_conv_desc* d);
-int idee_conv3d_wgrad(const idee_conv_desc* d, const float* x, const float* gy, float* gw, float* gb,
+int idee_conv3d_wgrad(const idee_conv_desc* d, const void* x, const void* gy, float* gw, float* gb,
                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- LFQ quantiser, dim=16, codebook_size=2                                      models/codebook/LFQ.py:183-307 ----

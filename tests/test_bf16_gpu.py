@@ -136,3 +136,50 @@ def test_tcgen05_classifier_conv_matches_mma_sync_and_oracle():
         assert rel_err(outs[umma][0], want) < TOL
         assert rel_err(outs[umma][1], xr.grad) < TOL
     assert rel_err(outs[True][0], outs[False][0]) < 2e-3          # same bf16 operands, different accumulation order
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 4, 21, 37), (1, 6, 8, 40, 48)])
+def test_bf16_activation_storage_is_bit_identical(shape):
+    """proj conv -> ReLU -> proj conv with the intermediate tensors stored as bf16 (Conv3dCL x16 / out_bf16 / bf16 input,
+    idee_conv_desc.x_dtype / y_dtype / gx_dtype) against the same kernels on fp32 storage: the tensor-core kernels round their
+    operands to bf16 when they load them, so every output and gradient must agree bit for bit."""
+    from idee_b200 import ops
+    N, V, T, H, W = shape
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn(N, V, T, H, W, 16, device="cuda", generator=g)
+    w0 = torch.randn(V, 16, 16, 3, 3, 3, device="cuda", generator=g) * 0.08
+    w1 = torch.randn(V, 16, 16, 3, 3, 3, device="cuda", generator=g) * 0.08
+    b0 = torch.randn(V, 16, device="cuda", generator=g) * 0.1
+    b1 = torch.randn(V, 16, device="cuda", generator=g) * 0.1
+    gz = torch.randn(N, V, T, H, W, 16, device="cuda", generator=g)
+
+    def run(bf16_io):
+        leaves = [t.clone().requires_grad_(True) for t in (x, w0, b0, w1, b1)]
+        xx, a0, c0, a1, c1 = leaves
+        x16 = xx.detach().to(torch.bfloat16) if bf16_io else None
+        h = ops.conv3d_cl(xx, a0, c0, proj=True, relu=True, consumer_masks=True, x16=x16, out_bf16=bf16_io)
+        z = ops.conv3d_cl(h, a1, c1, proj=True, relu=False, input_is_relu=True)
+        z.backward(gz)
+        return h.detach(), z.detach(), [t.grad for t in leaves]
+
+    h32, z32, g32 = run(False)
+    h16, z16, g16 = run(True)
+    assert h16.dtype == torch.bfloat16 and h32.dtype == torch.float32
+    assert torch.equal(h16, h32.to(torch.bfloat16))
+    assert torch.equal(z16, z32)
+    for a, b in zip(g16, g32):
+        assert a.dtype == torch.float32 and torch.equal(a, b)
+
+
+def test_bf16_swin_block_side_output_matches():
+    """The bf16 copy written by the last Swin block's forward kernel is the rounded fp32 output."""
+    from idee_b200 import ops
+    from idee_b200.models.encoder.Swin_3D import SwinTransformerBlock3D
+    torch.manual_seed(3)
+    blocks = [SwinTransformerBlock3D(16, 2, (2, 4, 4), (1, 2, 2), 4., True).cuda() for _ in range(3)]
+    pack = ops.ParamPack([b.packed_parameters() for b in blocks])
+    ws, ss, idx, rows, scale, heads, hidden = blocks[0].kernel_args(4, 18, 22)
+    x = torch.randn(2, 3, 4, 18, 22, 16, device="cuda")
+    y = ops.swin_block(x, pack, idx, ws, ss, rows, scale, heads, hidden)
+    y2, y16 = ops.swin_block(x, pack, idx, ws, ss, rows, scale, heads, hidden, want_bf16=True)
+    assert torch.equal(y, y2) and y16.dtype == torch.bfloat16 and torch.equal(y16, y.to(torch.bfloat16))
