@@ -281,7 +281,7 @@ def main():
         _lib.Profile.reset(events=False)
         tot = sum(t for _, t in summ.values())
         top = sorted(summ.items(), key=lambda kv: -kv[1][1])
-        breakdown = [{"op": k, "calls_per_step": c / prof_steps, "ms_per_step": t / prof_steps, "share": t / tot} for k, (c, t) in top[:12]]
+        breakdown = [{"op": k, "calls_per_step": c / prof_steps, "ms_per_step": t / prof_steps, "share": t / tot} for k, (c, t) in top[:40]]
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

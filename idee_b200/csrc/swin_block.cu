@@ -45,6 +45,7 @@ struct Geom {
     int n_wg;     // window groups (warps' worth of windows) per variable
     int tbl;      // rows of the rpb table
     float scale;
+    int thwc;     // T*H*W*C (elements of one (n, v) image; < 2^31)
     void* out16;  // forward, bf16 path: optional bf16 copy of the block output (for the proj conv that consumes it)
 };
 
@@ -633,6 +634,9 @@ int make_geom(Geom& g, const idee_swin_desc* d, const char* who) {
     g.n_wg = (int)((nwin + (32 / Gt) - 1) / (32 / Gt));
     g.tbl = d->rpb_rows;
     g.scale = d->scale;
+    IDEE_REQUIRE((int64_t)d->T * d->H * d->W * C < (1ll << 31), "%s: one (n, v) volume must hold fewer than 2^31 elements", who);
+    g.thwc = d->T * d->H * d->W * C;
+    g.out16 = nullptr;
     return 0;
 }
 
@@ -651,8 +655,12 @@ int launch_fwd(const idee_swin_desc* d, const Geom& g, const float* x, float* ou
     constexpr int G = WD * WH * WW;
     if (d->precision == 1) {
         if (G < 8) { idee_set_error("swin_block_fwd(bf16): windows with fewer than 8 tokens are only built for the fp32 path"); return 1; }
+        // persistent grid of exactly one resident wave (a partial second wave would run at a fraction of the occupancy)
+        int per_sm = 1;
+        IDEE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, swin_fwd_tc_kernel<WD, WH, WW>, TCW * 32, 0), "swin_block_fwd(bf16)");
+        if (per_sm < 1) per_sm = 1;
         int per_v = (g.n_wg + TCW - 1) / TCW;
-        const int cap = (idee_num_sms() * 6 + d->V - 1) / d->V;
+        const int cap = idee_num_sms() * per_sm / d->V;
         if (per_v > cap) per_v = cap;
         if (per_v < 1) per_v = 1;
         swin_fwd_tc_kernel<WD, WH, WW><<<dim3(per_v, d->V), TCW * 32, 0, st>>>(x, out, ymid, params, d->param_stride, rel_index, g);

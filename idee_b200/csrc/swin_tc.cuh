@@ -67,6 +67,7 @@ struct TokRows {
     bool valid[4];
     int64_t off[4];
     int code[4];
+    bool masked;      // warp-uniform: some window of this warp touches the shifted border (its region codes differ)
 };
 // Token coordinates of the 4 rows (tokens g + 8r) of this lane.  The window index is decoded ONCE per warp iteration (three
 // integer divisions) and advanced incrementally for the following windows of the warp; the in-window part uses compile-time
@@ -82,6 +83,7 @@ __device__ __forceinline__ void map_rows(TokRows& tr, const Geom& g, int v, int 
     rem -= dw * g.nwh * g.nww;
     int hw = rem / g.nww, ww = rem - hw * g.nww;
     int cur = 0;
+    bool any_border = false;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const int wl = (8 * r) / G;                  // window of this row inside the warp (compile time)
@@ -96,9 +98,18 @@ __device__ __forceinline__ void map_rows(TokRows& tr, const Geom& g, int v, int 
         int s_h = ph + g.sh; if (s_h >= g.Hp) s_h -= g.Hp;
         int s_w = pw + g.sw; if (s_w >= g.Wp) s_w -= g.Wp;
         tr.valid[r] = wg_ok && n < g.N && s_t < g.T && s_h < g.H && s_w < g.W;
-        tr.off[r] = ((((int64_t)(n * g.V + v) * g.T + s_t) * g.H + s_h) * g.W + s_w) * C;
-        tr.code[r] = g.masked ? (region_id(pt, g.Tp, WD, g.st) * 9 + region_id(ph, g.Hp, WH, g.sh) * 3 + region_id(pw, g.Wp, WW, g.sw)) : 0;
+        // host guarantees T*H*W*C < 2^31: one widening multiply for the image base, 32-bit math inside the image
+        tr.off[r] = (int64_t)(n * g.V + v) * g.thwc + (((s_t * g.H + s_h) * g.W + s_w) * C);
+        // Only the last window along a shifted axis mixes regions; everywhere else every token has region code 0, which is
+        // also what the formula gives, so the codes (and the mask pass of the softmax) are skipped for interior windows.
+        const bool border = g.masked && ((g.st && dw == g.nwt - 1) || (g.sh && hw == g.nwh - 1) || (g.sw && ww == g.nww - 1));
+        tr.code[r] = 0;
+        if (border) {
+            tr.code[r] = region_id(pt, g.Tp, WD, g.st) * 9 + region_id(ph, g.Hp, WH, g.sh) * 3 + region_id(pw, g.Wp, WW, g.sw);
+            any_border = true;
+        }
     }
+    tr.masked = any_border;
 }
 __device__ __forceinline__ void load_tile(float (&t)[4][4], const float* base, const TokRows& tr, int c0) {
 #pragma unroll
@@ -217,12 +228,21 @@ struct AttnTC {
                 if (tile_needed(r, nj)) {
                     const int jl = (8 * nj + c0) % G;
                     const float2 b = *reinterpret_cast<const float2*>(Bn + (h * G + il) * G + jl);
-                    float s0 = p[mi][nj][2 * hf] + b.x, s1 = p[mi][nj][2 * hf + 1] + b.y;
-                    if (masked) { if (cj[nj][0] != tr.code[r]) s0 += -100.0f * LOG2E; if (cj[nj][1] != tr.code[r]) s1 += -100.0f * LOG2E; }
-                    p[mi][nj][2 * hf] = s0; p[mi][nj][2 * hf + 1] = s1;
-                    mx = fmaxf(mx, fmaxf(s0, s1));
+                    p[mi][nj][2 * hf] += b.x; p[mi][nj][2 * hf + 1] += b.y;
                 }
             }
+            if (masked) {                                  // warp-uniform: only warps holding a border window take this
+#pragma unroll
+                for (int nj = 0; nj < 4; ++nj) {
+                    if (tile_needed(r, nj)) {
+                        if (cj[nj][0] != tr.code[r]) p[mi][nj][2 * hf] += -100.0f * LOG2E;
+                        if (cj[nj][1] != tr.code[r]) p[mi][nj][2 * hf + 1] += -100.0f * LOG2E;
+                    }
+                }
+            }
+#pragma unroll
+            for (int nj = 0; nj < 4; ++nj)
+                if (tile_needed(r, nj)) mx = fmaxf(mx, fmaxf(p[mi][nj][2 * hf], p[mi][nj][2 * hf + 1]));
             mx = quad_max(mx);
             float sum = 0.f;
 #pragma unroll
@@ -257,6 +277,12 @@ struct AttnTC {
     }
 };
 
+// t = bias broadcast over rows (accumulator initialisation: the following gemm16 adds the product onto it)
+__device__ __forceinline__ void init_bias_tile(float (&t)[4][4], const float* b, int c0) {
+    const float b0 = b[c0], b1 = b[c0 + 1], b2 = b[c0 + 8], b3 = b[c0 + 9];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) { t[r][0] = b0; t[r][1] = b1; t[r][2] = b2; t[r][3] = b3; }
+}
 __device__ __forceinline__ void add_bias_tile(float (&t)[4][4], const float* b, int c0) {
     const float b0 = b[c0], b1 = b[c0 + 1], b2 = b[c0 + 8], b3 = b[c0 + 9];
 #pragma unroll
@@ -275,13 +301,9 @@ __device__ __forceinline__ void stage_bias_n(float* Bn, const float* tbl, const 
 __device__ __forceinline__ void qkv_tiles(const float (&xn)[4][4], const uint2* wq, const float* bq, float scale,
                                           float (&q)[4][4], float (&k)[4][4], float (&v)[4][4], int lane) {
     const int c0 = 2 * (lane % 4);
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int x = 0; x < 4; ++x) { q[r][x] = 0.f; k[r][x] = 0.f; v[r][x] = 0.f; }
-    gemm16(q, xn, wq, lane);      add_bias_tile(q, bq, c0);
-    gemm16(k, xn, wq + 64, lane); add_bias_tile(k, bq + 16, c0);
-    gemm16(v, xn, wq + 128, lane); add_bias_tile(v, bq + 32, c0);
+    init_bias_tile(q, bq, c0);      gemm16(q, xn, wq, lane);
+    init_bias_tile(k, bq + 16, c0); gemm16(k, xn, wq + 64, lane);
+    init_bias_tile(v, bq + 32, c0); gemm16(v, xn, wq + 128, lane);
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -318,7 +340,6 @@ swin_fwd_tc_kernel(const float* __restrict__ x, float* __restrict__ out, float* 
     stage_bias_n<G>(Bn, P, rel_index);
     __syncthreads();
     const int c0 = 2 * (lane % 4);
-    const bool masked = g.masked != 0;
 
     for (int wg = blockIdx.x * TCW + warp; wg < g.n_wg; wg += gridDim.x * TCW) {
         TokRows tr;
@@ -336,7 +357,7 @@ swin_fwd_tc_kernel(const float* __restrict__ x, float* __restrict__ out, float* 
 #pragma unroll
             for (int h = 0; h < NH; ++h) {
                 float p[2][4][4], rinv[4];
-                at.template probs<false>(h, p, rinv, Bn, tr, masked, lane);
+                at.template probs<false>(h, p, rinv, Bn, tr, tr.masked, lane);
                 at.pv(h, p, o);
 #pragma unroll
                 for (int r = 0; r < 4; ++r) { o[r][2 * h] *= rinv[r]; o[r][2 * h + 1] *= rinv[r]; }
@@ -360,10 +381,8 @@ swin_fwd_tc_kernel(const float* __restrict__ x, float* __restrict__ out, float* 
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
             float h[4][4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) h[r][0] = h[r][1] = h[r][2] = h[r][3] = 0.f;
+            init_bias_tile(h, bias_s + 4 * C + 16 * kk, c0);
             gemm16(h, yn, wf + (8 + 2 * kk) * 32, lane);
-            add_bias_tile(h, bias_s + 4 * C + 16 * kk, c0);
 #pragma unroll
             for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -414,16 +433,23 @@ swin_mlp_bwd_tc_kernel(const float* __restrict__ y, const float* __restrict__ go
     }
     const int64_t ntok = (int64_t)N * thw;
     const int64_t n_grp = (ntok + 31) / 32;
-    for (int64_t grp = (int64_t)blockIdx.x * TCW + warp; grp < n_grp; grp += (int64_t)gridDim.x * TCW) {
+    // (sample, in-sample token) of the warp's first token, advanced incrementally: no division inside the loop
+    const int64_t grp0 = (int64_t)blockIdx.x * TCW + warp, gstep = (int64_t)gridDim.x * TCW;
+    int64_t n0 = (grp0 * 32) / thw, rem0 = grp0 * 32 - n0 * thw;
+    for (int64_t grp = grp0; grp < n_grp; grp += gstep) {
         TokRows tr;
+        tr.masked = false;
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const int64_t tok = grp * 32 + g + 8 * r;
             tr.valid[r] = tok < ntok;
-            const int64_t tc = tr.valid[r] ? tok : 0, n = tc / thw;
-            tr.off[r] = ((n * V + v) * thw + (tc - n * thw)) * C;
+            int64_t n = n0, rem = rem0 + g + 8 * r;
+            while (rem >= thw) { rem -= thw; ++n; }
+            tr.off[r] = tr.valid[r] ? ((n * V + v) * thw + rem) * C : 0;
             tr.code[r] = 0;
         }
+        rem0 += gstep * 32;
+        while (rem0 >= thw) { rem0 -= thw; ++n0; }
         float yt[4][4], go[4][4], yn[4][4], rstd[4], dyn[4][4];
         load_tile(yt, y, tr, c0);
         load_tile(go, gout, tr, c0);
@@ -444,19 +470,19 @@ swin_mlp_bwd_tc_kernel(const float* __restrict__ y, const float* __restrict__ go
         for (int kk = 0; kk < 4; ++kk) {          // 16 hidden units per chunk
             float pre[4][4], dh[4][4];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) { pre[r][0] = pre[r][1] = pre[r][2] = pre[r][3] = 0.f; dh[r][0] = dh[r][1] = dh[r][2] = dh[r][3] = 0.f; }
+            for (int r = 0; r < 4; ++r) dh[r][0] = dh[r][1] = dh[r][2] = dh[r][3] = 0.f;
+            init_bias_tile(pre, b1_s + 16 * kk, c0);
             gemm16(pre, yn, wf + (2 * kk) * 32, lane);
-            add_bias_tile(pre, b1_s + 16 * kk, c0);
             gemm16(dh, go, wf + (8 + 2 * kk) * 32, lane);        // dHid = dOut W2
             float hid[4][4];
 #pragma unroll
             for (int r = 0; r < 4; ++r)
 #pragma unroll
                 for (int qd = 0; qd < 4; ++qd) {
-                    float hv, dg;
-                    gelu_fast_grad(pre[r][qd], hv, dg);
-                    hid[r][qd] = tr.valid[r] ? hv : 0.f;
-                    dh[r][qd] = tr.valid[r] ? dh[r][qd] * dg : 0.f;   // dPre
+                    // rows past the end load go = 0, so dHid, dPre and their weight-gradient terms vanish without a mask
+                    float dg;
+                    gelu_fast_grad(pre[r][qd], hid[r][qd], dg);
+                    dh[r][qd] *= dg;                                  // dPre
                     ab1[kk][qd] += dh[r][qd];
                 }
             gemm16(dyn, dh, wf + (16 + 2 * kk) * 32, lane);      // dYn += dPre W1[chunk]
@@ -542,7 +568,6 @@ swin_attn_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ g
     stage_bias_n<G>(Bn, P, rel_index);
     __syncthreads();
     const int gq = lane / 4, c0 = 2 * (lane % 4);
-    const bool masked = g.masked != 0;
     float* dB = dBw_all + warp * DBW;
 
     // persistent accumulators: dWqkv[o][c] 3 m-tiles x 2 n-tiles ; dWproj[c][e] 1 x 2 ; biases per-lane column sums
@@ -582,7 +607,7 @@ swin_attn_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ g
 #pragma unroll
         for (int h = 0; h < NH; ++h) {
             float p[2][4][4], rinv[4];
-            at.template probs<true>(h, p, rinv, Bn, tr, masked, lane);
+            at.template probs<true>(h, p, rinv, Bn, tr, tr.masked, lane);
             at.pv(h, p, o);
             // D_r = <dO_r, O_r> over the 8 dims of head h
             float Dr[4];
