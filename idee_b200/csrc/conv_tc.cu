@@ -280,15 +280,27 @@ conv_tc_kernel(P p) {
     }
 }
 
+#ifndef IDEE_C16_DB
+#define IDEE_C16_DB 0
+#endif
+constexpr bool C16_DB = IDEE_C16_DB != 0;   // bf16-input halo double buffering (experiment switch)
+#ifndef IDEE_C16_WSMEM
+#define IDEE_C16_WSMEM 1
+#endif
+constexpr bool C16_WSMEM = IDEE_C16_WSMEM != 0;   // weights in shared memory (else read through L1 from the fragment table)
 constexpr int C16_THREADS = 128;     // 4 warps per CTA, two tile rows (m-tiles) per warp (8 warps measured slower)
 
 // ------------------------------------------------------------------------------------------------------------------
-// 16-input-channel convs (proj_var, per-variable classifier heads, and their data gradients): persistent, pipelined.
-// A CTA loads the weights once, then walks tiles with the next tile's halo in flight behind the current tile's MMAs:
+// 16-input-channel convs (proj_var, per-variable classifier heads, and their data gradients): persistent CTAs walking tiles.
 //   fp32 input (IN16 = false):  wait(stage i) -> convert fp32 stage -> bf16 halo -> issue cp.async(stage i+1) -> MMA + epilogue
-//   bf16 input (IN16 = true):   wait(halo[b] i) -> issue cp.async(halo[b^1] i+1) -> MMA + epilogue     (no staging, no convert)
+//   bf16 input (IN16 = true):   cp.async lands straight in the MMA layout (no staging, no convert).  Measured on B200 at the
+//                               benchmark shape: one halo buffer and 5 resident CTAs per SM (other CTAs cover the load
+//                               latency) beats a double-buffered halo at 3 CTAs per SM by 10 %; reading the weights through
+//                               L1 instead of shared memory to fit 8 CTAs is slower again.  Both remain as compile switches.
 // Padding is resolved by the loader (zero-fill for zero padding, clamped addresses for replicate); taps are fully unrolled.
 // OUT16 stores the result as bf16 (same value the next conv would round to when it loads an fp32 copy).
+// Tile coordinates come from multiply-high divisions, once per tile; the 32-bit integer work per element is one add on tiles
+// whose halo stays inside the image in h and w (ncu: address arithmetic was 68 % of the executed instructions before).
 // ------------------------------------------------------------------------------------------------------------------
 template <int MODE, int NTL, bool IN16, bool OUT16>
 __global__ void __launch_bounds__(C16_THREADS)
@@ -306,7 +318,7 @@ conv_tc16_kernel(P p, int64_t total_tiles64, FastDiv fd_tw, FastDiv fd_th, FastD
     using in_t = typename std::conditional<IN16, __nv_bfloat16, float>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint2* wsm = reinterpret_cast<uint2*>(smem_raw);                                     // [NTF][32 lanes][NTL] (lane-major)
-    unsigned char* dyn = smem_raw + sizeof(uint2) * NTF * WTAP;
+    unsigned char* dyn = smem_raw + (C16_WSMEM ? sizeof(uint2) * NTF * WTAP : 0);
     // fp32 input: [NPIX][16] fp32 stage | [NPIX][CP] bf16 halo;   bf16 input: [2][NPIX][CP] bf16 halo (double buffer)
     float* stage = reinterpret_cast<float*>(dyn);
     __nv_bfloat16* halo = reinterpret_cast<__nv_bfloat16*>(IN16 ? dyn : dyn + sizeof(float) * NPIX * 16);
@@ -352,7 +364,7 @@ conv_tc16_kernel(P p, int64_t total_tiles64, FastDiv fd_tw, FastDiv fd_th, FastD
         const in_t* in_img = in + c.n * p.in_sn + c.v * p.in_sv;
         const int tb = (MODE == CLS_FWD) ? 2 * c.t : (MODE == CLS_DGRAD ? (c.t >> 1) : c.t);
         const int t_lo = tb + OT, h_lo = c.h0 + OHW, w_lo = c.w0 + OHW;      // halo origin
-        const uint32_t dst0 = dst_base + (IN16 ? buf * NPIX * CP * 2 : 0);
+        const uint32_t dst0 = dst_base + ((IN16 && C16_DB) ? buf * NPIX * CP * 2 : 0);
         // per-plane resolution of the t border: replicate shifts the plane, zero padding blanks it
         int dT[KTIN]; bool okT[KTIN];
 #pragma unroll
@@ -414,7 +426,7 @@ conv_tc16_kernel(P p, int64_t total_tiles64, FastDiv fd_tw, FastDiv fd_th, FastD
         const int wset = p.Vw == 1 ? 0 : c.v;
         cp_async_wait<0>();
         __syncthreads();                                   // tile's data landed; every warp is done with the previous halo/weights
-        if (wset != cur_wset) {
+        if (C16_WSMEM && wset != cur_wset) {
             const uint2* wf = p.wfrag + (int64_t)wset * NTF * WTAP;      // global: [ftap][ntile][lane] -> smem [ftap][lane][ntile]
             for (int e = tid; e < NTF * WTAP; e += NTH) {
                 const int ft = e / WTAP, r = e - ft * WTAP;
@@ -425,9 +437,11 @@ conv_tc16_kernel(P p, int64_t total_tiles64, FastDiv fd_tw, FastDiv fd_th, FastD
         }
         const bool more = tile + gridDim.x < total_tiles;
         const __nv_bfloat16* hb = halo;
-        if (IN16) {
+        if (IN16 && C16_DB) {
             hb = halo + buf * NPIX * CP;
             if (more) { nxt = decode(tile + gridDim.x); issue(nxt, buf ^ 1); }
+        } else if (IN16) {
+            // single buffer: the next tile is requested after this tile's MMAs (other resident CTAs cover the latency)
         } else {
 #pragma unroll
             for (int i = 0; i < (NPIX * 4 + NTH - 1) / NTH; ++i) {   // fp32 stage -> bf16 halo (padded pixel stride)
@@ -452,6 +466,7 @@ conv_tc16_kernel(P p, int64_t total_tiles64, FastDiv fd_tw, FastDiv fd_th, FastD
                 for (int nt = 0; nt < NTL; ++nt) acc2[s2][m][nt][0] = acc2[s2][m][nt][1] = acc2[s2][m][nt][2] = acc2[s2][m][nt][3] = 0.f;
         const __nv_bfloat16* abase = hb + ((warp * MT) * HW_ + a_pix) * CP + a_koff;
         const uint2* wpar = wsm + ((MODE == CLS_DGRAD) ? (c.t & 1) * 9 * WTAP : 0) + lane * NTL;
+        const uint2* wglb = p.wfrag + (int64_t)wset * NTF * WTAP + ((MODE == CLS_DGRAD) ? (c.t & 1) * 9 * WTAP : 0) + lane;
         // taps ordered (kt, kw, kh): the MT + 2 halo rows of one (kt, kw) column feed all three kh taps of every m-tile
 #pragma unroll
         for (int kt = 0; kt < NKT; ++kt) {
@@ -466,7 +481,10 @@ conv_tc16_kernel(P p, int64_t total_tiles64, FastDiv fd_tw, FastDiv fd_th, FastD
                                  : (MODE == CLS_DGRAD ? (2 - kh) * 3 + (2 - kw) : (2 - kt) * 9 + (2 - kh) * 3 + (2 - kw));
                     const int set = ((kt * 3 + kw) * NKH + kh) & 1;
                     uint2 b[NTL];
-                    if (NTL == 2) {
+                    if (!C16_WSMEM) {
+#pragma unroll
+                        for (int nt = 0; nt < NTL; ++nt) b[nt] = __ldg(wglb + ft * WTAP + nt * 32);
+                    } else if (NTL == 2) {
                         const uint4 bb = *reinterpret_cast<const uint4*>(wpar + ft * WTAP);
                         b[0] = make_uint2(bb.x, bb.y); b[NTL - 1] = make_uint2(bb.z, bb.w);
                     } else {
@@ -487,6 +505,10 @@ conv_tc16_kernel(P p, int64_t total_tiles64, FastDiv fd_tw, FastDiv fd_th, FastD
             for (int nt = 0; nt < NTL; ++nt)
 #pragma unroll
                 for (int q = 0; q < 4; ++q) acc[m][nt][q] = acc2[0][m][nt][q] + acc2[1][m][nt][q];
+        if (IN16 && !C16_DB) {
+            __syncthreads();
+            if (more) { nxt = decode(tile + gridDim.x); issue(nxt, 0); }
+        }
         // epilogue
         const float* B = p.bias ? p.bias + (int64_t)wset * p.CO : nullptr;
         const int64_t tile_off = c.n * p.out_sn + c.v * p.out_sv + (int64_t)(c.t * (int)p.out_st + c.h0 * (int)p.out_sh + c.w0 * (int)p.out_sw);
@@ -874,7 +896,7 @@ template <int MODE, int NTL, bool IN16, bool OUT16>
 int launch_tc16(const P& p, int n_img_t, cudaStream_t st, const char* who) {
     constexpr int KTIN = (MODE == CLS_FWD) ? 2 : (MODE == CLS_DGRAD ? 1 : 3);
     constexpr int NTF = (MODE == CLS_FWD || MODE == CLS_DGRAD) ? 18 : 27;
-    const size_t smem = sizeof(uint2) * NTF * NTL * 32 + (size_t)KTIN * HH * HW_ * (IN16 ? 2 * 24 * 2 : 16 * 4 + 24 * 2);
+    const size_t smem = (C16_WSMEM ? sizeof(uint2) * NTF * NTL * 32 : 0) + (size_t)KTIN * HH * HW_ * (IN16 ? (C16_DB ? 2 : 1) * 24 * 2 : 16 * 4 + 24 * 2);
     auto kern = conv_tc16_kernel<MODE, NTL, IN16, OUT16>;
     IDEE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), who);
     const int tiles_h = (p.Ho + TH - 1) / TH;
