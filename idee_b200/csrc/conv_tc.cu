@@ -416,12 +416,15 @@ conv_tc16_kernel(P p, int64_t total_tiles64, FastDiv fd_tw, FastDiv fd_th, FastD
         cp_async_commit();
     };
 
-    const uint32_t first = blockIdx.x;
+    // Each CTA walks one contiguous range of tiles: it stays inside one or two (n, v) images, so the weight set is (re)loaded
+    // once or twice per CTA instead of every few tiles, and neighbouring tiles find their shared halo rows in L2.
+    const uint32_t per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
+    const uint32_t first = blockIdx.x * per_cta, last = min(total_tiles, first + per_cta);
     Tile nxt{};
-    if (first < total_tiles) { nxt = decode(first); issue(nxt, 0); }
+    if (first < last) { nxt = decode(first); issue(nxt, 0); }
     int cur_wset = -1, buf = 0;
     const int a_pix = (lane & 7) + ((lane >> 3) & 1) * 8, a_koff = (lane >> 4) * 8;
-    for (uint32_t tile = first; tile < total_tiles; tile += gridDim.x, buf ^= 1) {
+    for (uint32_t tile = first; tile < last; ++tile, buf ^= 1) {
         const Tile c = nxt;
         const int wset = p.Vw == 1 ? 0 : c.v;
         cp_async_wait<0>();
@@ -435,11 +438,11 @@ conv_tc16_kernel(P p, int64_t total_tiles64, FastDiv fd_tw, FastDiv fd_th, FastD
             cur_wset = wset;
             if (IN16) __syncthreads();
         }
-        const bool more = tile + gridDim.x < total_tiles;
+        const bool more = tile + 1 < last;
         const __nv_bfloat16* hb = halo;
         if (IN16 && C16_DB) {
             hb = halo + buf * NPIX * CP;
-            if (more) { nxt = decode(tile + gridDim.x); issue(nxt, buf ^ 1); }
+            if (more) { nxt = decode(tile + 1); issue(nxt, buf ^ 1); }
         } else if (IN16) {
             // single buffer: the next tile is requested after this tile's MMAs (other resident CTAs cover the latency)
         } else {
@@ -452,7 +455,7 @@ conv_tc16_kernel(P p, int64_t total_tiles64, FastDiv fd_tw, FastDiv fd_th, FastD
                 }
             }
             __syncthreads();
-            if (more) { nxt = decode(tile + gridDim.x); issue(nxt, 0); }
+            if (more) { nxt = decode(tile + 1); issue(nxt, 0); }
         }
 
         // Two accumulator sets (taps alternate between them, summed at the end): 2 * MT * NTL independent HMMA chains per warp
@@ -507,7 +510,7 @@ conv_tc16_kernel(P p, int64_t total_tiles64, FastDiv fd_tw, FastDiv fd_th, FastD
                 for (int q = 0; q < 4; ++q) acc[m][nt][q] = acc2[0][m][nt][q] + acc2[1][m][nt][q];
         if (IN16 && !C16_DB) {
             __syncthreads();
-            if (more) { nxt = decode(tile + gridDim.x); issue(nxt, 0); }
+            if (more) { nxt = decode(tile + 1); issue(nxt, 0); }
         }
         // epilogue
         const float* B = p.bias ? p.bias + (int64_t)wset * p.CO : nullptr;
@@ -963,14 +966,30 @@ size_t conv_umma_workspace_bytes();
 int conv_umma_run(const idee_conv_desc* d, int dgrad, const float* in, const float* w, const float* bias, const float* relu_src,
                   float* out, void* ws, cudaStream_t st);
 
+// tcgen05 / TMEM path for the bf16-input 16 -> 16 proj conv (conv16_umma.cu)
+size_t conv16_umma_workspace_bytes(int Vw);
+int conv16_umma_run(int mode, int out16, const void* in, const float* w, const float* bias, void* out, void* ws, int N, int V, int Vw,
+                    int Ti, int Hi, int Wi, int To, int Ho, int Wo, const int64_t* in_s, const int64_t* out_s, int relu,
+                    cudaStream_t st);
+static bool umma16_fwd_eligible(const idee_conv_desc* d) {
+    return d->umma16 && d->precision >= 1 && d->proj && d->Cin == 16 && d->Cout == 16 && d->x_dtype == 1 && d->x_sw == 16 && d->y_sw == 16;
+}
+static bool umma16_dgrad_eligible(const idee_conv_desc* d) {
+    return d->umma16 && d->precision >= 1 && d->proj && d->Cin == 16 && d->Cout == 16 && d->y_dtype == 1 && d->y_sw == 16;
+}
+static size_t max_sz(size_t a, size_t b) { return a > b ? a : b; }
+
 size_t conv_tc_fwd_workspace_bytes(const idee_conv_desc* d) {
     if (conv_umma_eligible(d)) return conv_umma_workspace_bytes();
-    return make_plan(d->proj ? PROJ_FWD : CLS_FWD, d->Cin, d->Cout, d->Vw).wfrag_bytes;
+    size_t b = make_plan(d->proj ? PROJ_FWD : CLS_FWD, d->Cin, d->Cout, d->Vw).wfrag_bytes;
+    if (umma16_fwd_eligible(d)) b = max_sz(b, conv16_umma_workspace_bytes(d->Vw));
+    return b;
 }
 
 size_t conv_tc_dgrad_workspace_bytes(const idee_conv_desc* d) {
     if (conv_umma_eligible(d)) return conv_umma_workspace_bytes();
     size_t b = make_plan(d->proj ? PROJ_DGRAD_PAD : CLS_DGRAD, d->Cout, d->Cin, d->Vw).wfrag_bytes;
+    if (umma16_dgrad_eligible(d)) b = max_sz(b, conv16_umma_workspace_bytes(d->Vw));
     b = (b + 255) / 256 * 256;
     if (d->proj) b += sizeof(float) * (size_t)d->N * d->V * (d->Ti + 2) * (d->Hi + 2) * (d->Wi + 2) * 16;
     return b;
@@ -978,6 +997,11 @@ size_t conv_tc_dgrad_workspace_bytes(const idee_conv_desc* d) {
 
 int conv_tc_fwd(const idee_conv_desc* d, const void* x, const float* w, const float* b, void* y, void* ws, cudaStream_t st) {
     if (conv_umma_eligible(d)) return conv_umma_run(d, 0, (const float*)x, w, b, nullptr, (float*)y, ws, st);
+    if (umma16_fwd_eligible(d)) {
+        const int64_t is[5] = {d->x_sn, d->x_sv, d->x_st, d->x_sh, d->x_sw}, os[5] = {d->y_sn, d->y_sv, d->y_st, d->y_sh, d->y_sw};
+        return conv16_umma_run(0, d->y_dtype, x, w, b, y, ws, d->N, d->V, d->Vw, d->Ti, d->Hi, d->Wi, d->To, d->Ho, d->Wo, is, os,
+                               d->relu, st);
+    }
     const int mode = d->proj ? PROJ_FWD : CLS_FWD;
     const Plan pl = make_plan(mode, d->Cin, d->Cout, d->Vw);
     if (prep(d, w, (uint2*)ws, pl, 0, st)) return 2;
@@ -1016,14 +1040,19 @@ int conv_tc_dgrad(const idee_conv_desc* d, const void* gy, const float* w, const
     IDEE_REQUIRE(d->x_sw == 16 && d->x_sh == (int64_t)d->Wi * 16 && d->x_st == (int64_t)d->Hi * d->Wi * 16 &&
                  d->x_sv == (int64_t)d->Ti * d->Hi * d->Wi * 16 && d->x_sn == d->x_sv * d->V,
                  "conv3d_dgrad(proj,bf16): the input gradient must be a contiguous [N,V,T,H,W,16] tensor");
-    float* gpad = (float*)((char*)ws + (pl.wfrag_bytes + 255) / 256 * 256);
+    const bool u16 = umma16_dgrad_eligible(d);
+    const size_t wbytes = u16 ? max_sz(pl.wfrag_bytes, conv16_umma_workspace_bytes(d->Vw)) : pl.wfrag_bytes;
+    float* gpad = (float*)((char*)ws + (wbytes + 255) / 256 * 256);
     const int Tp = d->Ti + 2, Hp = d->Hi + 2, Wp = d->Wi + 2;
     p.out = gpad; p.relu_src = nullptr;
     p.To = Tp; p.Ho = Hp; p.Wo = Wp;
     p.out_sw = 16; p.out_sh = (int64_t)Wp * 16; p.out_st = (int64_t)Hp * Wp * 16; p.out_sv = (int64_t)Tp * Hp * Wp * 16;
     p.out_sn = p.out_sv * d->V; p.out_sg = 0; p.out_cpg = 1;
     p.tiles_w = (p.Wo + TW - 1) / TW;
-    if (dispatch_tc<PROJ_DGRAD_PAD>(p, pl, d->N * d->V * Tp, st, "conv3d_dgrad(proj,bf16)")) return 2;
+    if (u16) {
+        const int64_t is[5] = {d->y_sn, d->y_sv, d->y_st, d->y_sh, d->y_sw}, os[5] = {p.out_sn, p.out_sv, p.out_st, p.out_sh, p.out_sw};
+        if (conv16_umma_run(1, 0, gy, w, nullptr, gpad, ws, d->N, d->V, d->Vw, d->To, d->Ho, d->Wo, Tp, Hp, Wp, is, os, 0, st)) return 2;
+    } else if (dispatch_tc<PROJ_DGRAD_PAD>(p, pl, d->N * d->V * Tp, st, "conv3d_dgrad(proj,bf16)")) return 2;
     const int64_t rows64 = (int64_t)d->N * d->V * d->Ti * d->Hi;
     IDEE_REQUIRE(rows64 < (1ll << 31), "conv3d_dgrad(proj,bf16): too many rows for the fold stage");
     const int rows = (int)rows64;

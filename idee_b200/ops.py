@@ -212,6 +212,7 @@ def _conv_desc(x_dims, x_strides, y_strides, Vw, Cin, Cout, proj, relu, in_cpg, 
     d.y_sn, d.y_sv, d.y_st, d.y_sh, d.y_sw = y_strides
     d.x_sg, d.y_sg, d.in_cpg, d.out_cpg = x_sg, y_sg, in_cpg, out_cpg
     d.precision = (2 if L.UMMA else 1) if L.PRECISION == "bf16" else 0
+    d.umma16 = int(L.UMMA16 and L.PRECISION == "bf16")
     return d
 
 

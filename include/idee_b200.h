@@ -91,6 +91,9 @@ typedef struct {
      * HBM gives bit-identical results with half the traffic and no conversion pass.  Strides stay in elements.
      *   x_dtype: x (forward / weight gradient) and relu_src (data gradient);  y_dtype: y and gy;  gx_dtype: gx */
     int x_dtype, y_dtype, gx_dtype;
+    /* 1: run the bf16-input 16 -> 16 proj conv (forward and data gradient) on tcgen05 + TMEM (conv16_umma.cu) instead of
+     * mma.sync; same operands and rounding points, different accumulation order */
+    int umma16;
 } idee_conv_desc;
 
 size_t idee_conv3d_fwd_workspace_bytes(const idee_conv_desc* d);
