@@ -241,10 +241,18 @@ def main():
     pred_h = torch.empty(B, 1, HW, HW, dtype=torch.float32).pin_memory()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # every step's inputs are copied from pinned host memory inside the timed region; the copy of step i+1 runs on a side
+    # stream while step i computes (idee_b200.trainer.HostPrefetcher), the logits and the loss come back every step
+    from idee_b200.trainer import HostPrefetcher
+    pf = HostPrefetcher(dev, (x_h, me_h, ml_h))
     e0.record()
-    for _ in range(args.steps):
-        xd, med, mld = x_h.to(dev, non_blocking=True), me_h.to(dev, non_blocking=True), ml_h.to(dev, non_blocking=True)
+    pf.stage(0, (x_h, me_h, ml_h))
+    for i in range(args.steps):
+        xd, med, mld = pf.take(i & 1)
+        if i + 1 < args.steps:
+            pf.stage((i + 1) & 1, (x_h, me_h, ml_h))
         loss, out = trainer.step(xd, med, mld)
+        pf.release(i & 1)
         pred_h.copy_(out["pred"].detach(), non_blocking=True)
         _ = loss.item()
     e1.record()

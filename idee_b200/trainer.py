@@ -120,3 +120,39 @@ class Trainer:
         total, out = self.forward_backward(x, mask_extreme, mask_extreme_loss)
         self.optimizer_step()
         return total.detach(), out
+
+
+class HostPrefetcher:
+    """Double-buffered host -> device staging of a step's inputs on a side stream.
+
+    The reference feeds the model from a DataLoader (train_synthetic.py:156-176) and copies each batch with ``.to(device)`` on
+    the compute stream, so the copy sits in front of every step.  Here batch i+1 is copied from pinned host memory into one of
+    two preallocated device slots while step i computes; ``take`` makes the compute stream wait for the copy, ``release`` tells
+    the copy stream when the slot may be overwritten.  Every batch still crosses PCIe once per step."""
+
+    def __init__(self, device, example_batch):
+        self.device = torch.device(device)
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self.slots = [[torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in example_batch] for _ in range(2)]
+        self.copied = [torch.cuda.Event(), torch.cuda.Event()]
+        self.free = [None, None]
+
+    def stage(self, slot: int, host_batch):
+        """Start copying ``host_batch`` (pinned tensors) into ``slot``; returns immediately."""
+        with torch.cuda.stream(self.copy_stream):
+            if self.free[slot] is not None:
+                self.copy_stream.wait_event(self.free[slot])          # the step that read this slot has finished
+            for dst, src in zip(self.slots[slot], host_batch):
+                dst.copy_(src, non_blocking=True)
+            self.copied[slot].record(self.copy_stream)
+
+    def take(self, slot: int):
+        """Device tensors of ``slot``; the current stream waits for the copy."""
+        torch.cuda.current_stream(self.device).wait_event(self.copied[slot])
+        return self.slots[slot]
+
+    def release(self, slot: int):
+        """Call after the step that consumed ``slot`` has been enqueued."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self.free[slot] = ev
