@@ -162,6 +162,69 @@ anomaly_l1_bwd_kernel(AnomP p, const float* __restrict__ out, const float* __res
     }
 }
 
+// ---- anomaly L1 on the rank-1 form of z_q (z_q[c] = x * w_out[c] + b_out[c], x = +-1): the per-token loss takes one of two
+// values A(+1), A(-1), so the forward pass is a mask-weighted count of the two signs over the scalar plane x (1/16 of z_q) ----
+// partials per block: {sum (1-m) [x > 0], sum (1-m) [x <= 0] over tokens with m != 1, sum (1-m) over (n,h,w)}
+__global__ void __launch_bounds__(AT)
+anomaly_rank1_fwd_kernel(const float* __restrict__ xq, const float* __restrict__ mask, int N, int V, int T, int64_t HW,
+                         double* __restrict__ partials) {
+    __shared__ double red[32];
+    const int64_t per_n = (int64_t)V * T * HW, ntok = (int64_t)N * per_n;
+    double cp = 0.0, cm = 0.0, wsum = 0.0;
+    for (int64_t tok = (int64_t)blockIdx.x * AT + threadIdx.x; tok < ntok; tok += (int64_t)gridDim.x * AT) {
+        const int64_t n = tok / per_n, r = tok - n * per_n, hw = r % HW;
+        const float m = __ldg(mask + n * HW + hw);
+        if (r < HW) wsum += (double)(1.f - m);
+        if (m == 1.f) continue;
+        if (__ldg(xq + tok) > 0.f) cp += (double)(1.f - m); else cm += (double)(1.f - m);
+    }
+    cp = block_sum_d(cp, red); cm = block_sum_d(cm, red); wsum = block_sum_d(wsum, red);
+    if (threadIdx.x == 0) { partials[3 * blockIdx.x] = cp; partials[3 * blockIdx.x + 1] = cm; partials[3 * blockIdx.x + 2] = wsum; }
+}
+// out: {loss, total weight = sum(1-m) * V*C*T, count(+1), count(-1)}
+__global__ void anomaly_rank1_finalize_kernel(const double* __restrict__ partials, int nblocks, int V, int T, const float* __restrict__ w_out,
+                                              const float* __restrict__ b_out, const float* __restrict__ vq0, float* __restrict__ out) {
+    double cp = 0.0, cm = 0.0, w = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += 32) { cp += partials[3 * b]; cm += partials[3 * b + 1]; w += partials[3 * b + 2]; }
+    cp = warp_sum_d(cp); cm = warp_sum_d(cm); w = warp_sum_d(w);
+    if (threadIdx.x == 0) {
+        float ap = 0.f, am = 0.f;                       // same fp32 arithmetic as z_q = fma(x, w, b) followed by |z_q - vq0|
+        for (int c = 0; c < 16; ++c) { ap += fabsf((w_out[c] + b_out[c]) - vq0[c]); am += fabsf((-w_out[c] + b_out[c]) - vq0[c]); }
+        const double tw = w * V * 16 * T;
+        out[0] = (float)((cp * (double)ap + cm * (double)am) / tw); out[1] = (float)tw; out[2] = (float)cp; out[3] = (float)cm;
+    }
+}
+// g_x = g_loss * (1-m) / total_weight * sum_c sign(x w_c + b_c - v_c) w_c;  block 0 also writes g_w_out[16], g_b_out[16]
+__global__ void __launch_bounds__(AT)
+anomaly_rank1_bwd_kernel(const float* __restrict__ xq, const float* __restrict__ mask, int N, int V, int T, int64_t HW,
+                         const float* __restrict__ w_out, const float* __restrict__ b_out, const float* __restrict__ vq0,
+                         const float* __restrict__ out, const float* __restrict__ g_loss, float* __restrict__ gxq,
+                         float* __restrict__ gw, float* __restrict__ gb) {
+    const float scale = __ldg(g_loss) / __ldg(out + 1);
+    float gp = 0.f, gm = 0.f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+        const float w = __ldg(w_out + c), b = __ldg(b_out + c), v = __ldg(vq0 + c);
+        const float dp = (w + b) - v, dm = (-w + b) - v;
+        gp += dp > 0.f ? w : (dp < 0.f ? -w : 0.f);
+        gm += dm > 0.f ? w : (dm < 0.f ? -w : 0.f);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 16) {
+        const int c = threadIdx.x;
+        const float w = w_out[c], b = b_out[c], v = vq0[c], cp = out[2], cm = out[3];
+        const float dp = (w + b) - v, dm = (-w + b) - v;
+        const float sp = dp > 0.f ? 1.f : (dp < 0.f ? -1.f : 0.f), sm = dm > 0.f ? 1.f : (dm < 0.f ? -1.f : 0.f);
+        gw[c] = scale * (cp * sp - cm * sm);            // d z_q[c] / d w_out[c] = x
+        gb[c] = scale * (cp * sp + cm * sm);
+    }
+    const int64_t per_n = (int64_t)V * T * HW, ntok = (int64_t)N * per_n;
+    for (int64_t tok = (int64_t)blockIdx.x * AT + threadIdx.x; tok < ntok; tok += (int64_t)gridDim.x * AT) {
+        const int64_t n = tok / per_n, r = tok - n * per_n, hw = r % HW;
+        const float m = __ldg(mask + n * HW + hw);
+        gxq[tok] = m == 1.f ? 0.f : scale * (1.f - m) * (__ldg(xq + tok) > 0.f ? gp : gm);
+    }
+}
+
 int anom_blocks(int64_t ntok) {
     int64_t nb = (ntok + AT - 1) / AT;
     const int cap = idee_num_sms() * 8;
@@ -225,6 +288,32 @@ extern "C" int idee_anomaly_l1_bwd(const float* zq, const float* mask, const flo
     AnomP p{zq, mask, vq0, N, V, T, HW};
     anomaly_l1_bwd_kernel<<<anom_blocks(ntok), AT, 0, (cudaStream_t)stream>>>(p, out, g_loss, gzq);
     IDEE_LAUNCH_CHECK("anomaly_l1_bwd");
+    return 0;
+}
+
+extern "C" size_t idee_anomaly_rank1_workspace_bytes(int64_t ntok) { return sizeof(double) * 3 * (size_t)anom_blocks(ntok); }
+
+extern "C" int idee_anomaly_rank1_fwd(const float* xq, const float* mask, const float* w_out, const float* b_out, const float* vq0, int N,
+                                      int V, int T, int64_t HW, int C, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+    IDEE_REQUIRE(C == 16, "anomaly_rank1: only C=16 is built (got %d)", C);
+    const int64_t ntok = (int64_t)N * V * T * HW;
+    IDEE_REQUIRE(workspace_bytes >= idee_anomaly_rank1_workspace_bytes(ntok), "anomaly_rank1_fwd: workspace too small");
+    const int nb = anom_blocks(ntok);
+    anomaly_rank1_fwd_kernel<<<nb, AT, 0, (cudaStream_t)stream>>>(xq, mask, N, V, T, HW, (double*)workspace);
+    IDEE_LAUNCH_CHECK("anomaly_rank1_fwd");
+    anomaly_rank1_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const double*)workspace, nb, V, T, w_out, b_out, vq0, out);
+    IDEE_LAUNCH_CHECK("anomaly_rank1_finalize");
+    return 0;
+}
+
+extern "C" int idee_anomaly_rank1_bwd(const float* xq, const float* mask, const float* w_out, const float* b_out, const float* vq0, int N,
+                                      int V, int T, int64_t HW, int C, const float* out, const float* g_loss, float* gxq, float* gw,
+                                      float* gb, void* stream) {
+    IDEE_REQUIRE(C == 16, "anomaly_rank1: only C=16 is built (got %d)", C);
+    const int64_t ntok = (int64_t)N * V * T * HW;
+    anomaly_rank1_bwd_kernel<<<anom_blocks(ntok), AT, 0, (cudaStream_t)stream>>>(xq, mask, N, V, T, HW, w_out, b_out, vq0, out, g_loss, gxq,
+                                                                              gw, gb);
+    IDEE_LAUNCH_CHECK("anomaly_rank1_bwd");
     return 0;
 }
 

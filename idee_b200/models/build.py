@@ -74,4 +74,5 @@ class VQ_model(nn.Module):
         # the joint head consumes the rank-1 form of z_q (x * w_out + b_out): identical result, 1/6 of the conv1 work
         rank1 = (self.vq.last_scalar.view(N, V, T, H, W), self.vq.project_out.weight, self.vq.project_out.bias)
         z, y = self.cls(z_q, rank1=rank1)
+        z_q._idee_rank1 = rank1            # lets Anomaly_L1_loss_synthetic evaluate the same loss on the scalar plane
         return z, y, anomaly, z_q, loss_z_q.unsqueeze(0)

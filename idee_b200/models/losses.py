@@ -24,6 +24,11 @@ class Anomaly_L1_loss_synthetic(nn.Module):
 
     def forward(self, pred, mask_extreme, vq_0):
         """pred z_q [N,V,C,T,H,W], mask_extreme [N,H,W], vq_0 [1,C] -> scalar"""
+        rank1 = getattr(pred, "_idee_rank1", None)
+        if rank1 is not None and pred.shape[2] == 16:
+            # z_q as returned by idee_b200's VQ_model carries its rank-1 factors (x, w_out, b_out): same loss, 1/16 of the bytes
+            xq, w_out, b_out = rank1
+            return ops.AnomalyRank1.apply(xq, w_out, b_out, mask_extreme, vq_0.reshape(-1))
         tok = pred.permute(0, 1, 3, 4, 5, 2)                          # [N,V,T,H,W,C]; a view when pred is channel-last
         return ops.AnomalyL1.apply(tok, mask_extreme, vq_0.reshape(-1))
 

@@ -471,6 +471,41 @@ class AnomalyL1(torch.autograd.Function):
         return gzq, None, None
 
 
+class AnomalyRank1(torch.autograd.Function):
+    """The same loss evaluated on the rank-1 form of z_q: xq [N,V,T,H,W] (+-1), w_out [16,1] / [16], b_out [16], mask [N,H,W],
+    vq0 [16] -> scalar.  z_q[c] = xq * w_out[c] + b_out[c] (LFQ.py:284), so the per-token L1 takes one of two values and the pass
+    reads 1/16 of the bytes; the gradient reaches the encoder through xq (straight-through, idee_lfq_bwd's gxq input)."""
+
+    @staticmethod
+    def forward(ctx, xq, w_out, b_out, mask, vq0):
+        L.require_cuda(xq, mask, vq0)
+        lib = L.load()
+        xq, mask, vq0 = _f32c(xq), _f32c(mask), _f32c(vq0)
+        w, b = _f32c(w_out.reshape(-1)), _f32c(b_out.reshape(-1))
+        N, V, T, H, W = xq.shape
+        out = torch.empty(4, device=xq.device, dtype=torch.float32)
+        ntok = N * V * T * H * W
+        nws = lib.idee_anomaly_rank1_workspace_bytes(ntok)
+        ws = L.workspace(nws, xq.device)
+        L.run("anomaly_rank1_fwd", lib.idee_anomaly_rank1_fwd, xq.data_ptr(), mask.data_ptr(), w.data_ptr(), b.data_ptr(), vq0.data_ptr(),
+              N, V, T, H * W, 16, out.data_ptr(), ws.data_ptr(), nws, L.stream())
+        ctx.save_for_backward(xq, mask, w, b, vq0, out)
+        ctx.shapes = (w_out.shape, b_out.shape)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = L.load()
+        xq, mask, w, b, vq0, out = ctx.saved_tensors
+        N, V, T, H, W = xq.shape
+        g = _f32c(g).reshape(1)
+        gxq = torch.empty_like(xq)
+        gw, gb = torch.empty_like(w), torch.empty_like(b)
+        L.run("anomaly_rank1_bwd", lib.idee_anomaly_rank1_bwd, xq.data_ptr(), mask.data_ptr(), w.data_ptr(), b.data_ptr(), vq0.data_ptr(),
+              N, V, T, H * W, 16, out.data_ptr(), g.data_ptr(), gxq.data_ptr(), gw.data_ptr(), gb.data_ptr(), L.stream())
+        return gxq, gw.view(ctx.shapes[0]), gb.view(ctx.shapes[1]), None, None
+
+
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step):
     lib = L.load()
     L.run("adam_step", lib.idee_adam_step, p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2, eps,

@@ -135,6 +135,16 @@ int idee_anomaly_l1_fwd(const float* zq, const float* mask, const float* vq0, in
 int idee_anomaly_l1_bwd(const float* zq, const float* mask, const float* vq0, int N, int V, int T, int64_t HW, int C,
                         const float* out, const float* g_loss, float* gzq, void* stream);
 
+/* The same loss on the rank-1 form of z_q (z_q[c] = x * w_out[c] + b_out[c], x = +-1 the quantised scalar of idee_lfq_fwd):
+ * reads the scalar plane xq [N,V,T,HW] instead of the 16-channel z_q; out: float[4] = {loss, total weight, count(+1), count(-1)};
+ * backward writes gxq [N,V,T,HW] (gradient w.r.t. x, fed to idee_lfq_bwd) and g_w_out[16], g_b_out[16] */
+size_t idee_anomaly_rank1_workspace_bytes(int64_t ntok);
+int idee_anomaly_rank1_fwd(const float* xq, const float* mask, const float* w_out, const float* b_out, const float* vq0, int N, int V,
+                           int T, int64_t HW, int C, float* out, void* workspace, size_t workspace_bytes, void* stream);
+int idee_anomaly_rank1_bwd(const float* xq, const float* mask, const float* w_out, const float* b_out, const float* vq0, int N, int V,
+                           int T, int64_t HW, int C, const float* out, const float* g_loss, float* gxq, float* gw, float* gb,
+                           void* stream);
+
 /* ---- optimiser: torch.optim.Adam(lr, betas, eps, weight_decay) on one flat buffer        train_synthetic.py:127-129 ---- */
 int idee_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                    float weight_decay, int step, void* stream);

@@ -107,3 +107,29 @@ def test_full_step_matches_oracle_medium():
         named = dict(model.named_parameters())
         worst = max((rel_err(named[k].grad, sdg[k].grad), k) for k in sd)
         assert worst[0] < TOL_GRAD, worst
+
+
+def test_anomaly_rank1_matches_full_loss():
+    """Anomaly_L1 on the rank-1 factors (xq, w_out, b_out) of z_q against the 16-channel kernel and the oracle: same loss, and the
+    gradients agree after the chain rule z_q = xq * w_out + b_out."""
+    from idee_b200 import ops
+    from oracle import idee_oracle as O
+    g = torch.Generator(device="cuda").manual_seed(5)
+    N, V, T, H, W = 2, 3, 4, 9, 13
+    xq = torch.where(torch.rand(N, V, T, H, W, device="cuda", generator=g) > 0.4, 1.0, -1.0).requires_grad_(True)
+    w_out = (torch.randn(16, 1, device="cuda", generator=g) * 0.5).requires_grad_(True)
+    b_out = (torch.randn(16, device="cuda", generator=g) * 0.5).requires_grad_(True)
+    mask = (torch.rand(N, H, W, device="cuda", generator=g) > 0.7).float()
+    vq0 = (-w_out.detach().reshape(-1) + b_out.detach()).clone()            # code of index 0
+    loss1 = ops.AnomalyRank1.apply(xq, w_out, b_out, mask, vq0)
+    loss1.backward()
+    g1 = (xq.grad.clone(), w_out.grad.clone(), b_out.grad.clone())
+    for t in (xq, w_out, b_out):
+        t.grad = None
+    zq = xq.unsqueeze(-1) * w_out.reshape(-1) + b_out                       # [N,V,T,H,W,16]
+    loss2 = ops.AnomalyL1.apply(zq, mask, vq0)
+    loss2.backward()
+    want = O.anomaly_l1_loss_synthetic(zq.detach().permute(0, 1, 5, 2, 3, 4).cpu(), mask.cpu(), vq0.cpu())
+    assert abs(float(loss1) - float(want)) <= 1e-6 * abs(float(want)) and abs(float(loss1) - float(loss2)) <= 1e-6 * abs(float(loss2))
+    for a, b in zip(g1, (xq.grad, w_out.grad, b_out.grad)):
+        assert rel_err(a, b) < 1e-5
