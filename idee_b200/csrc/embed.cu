@@ -16,16 +16,14 @@ struct EmbP {
     int N, V, Cin, T, H, W;
 };
 
-__device__ __forceinline__ int64_t x_offset(const EmbP& p, int64_t tok_v, int v, int& n_out) {
-    const int64_t thw = (int64_t)p.T * p.H * p.W;
-    const int n = (int)(tok_v / thw);
-    int64_t r = tok_v - n * thw;
-    const int t = (int)(r / ((int64_t)p.H * p.W));
-    r -= (int64_t)t * p.H * p.W;
-    const int h = (int)(r / p.W), w = (int)(r - (int64_t)h * p.W);
-    n_out = n;
-    return n * p.xs_n + v * p.xs_v + t * p.xs_t + h * p.xs_h + w * p.xs_w;
+// Offset of in-image token r (< T*H*W, 32-bit) inside image (n, v) of x.  Dense (t,h,w) strides need no division at all.
+__device__ __forceinline__ int64_t x_offset(const EmbP& p, uint32_t r, bool dense) {
+    if (dense) return (int64_t)r * p.xs_w;
+    const uint32_t hw = (uint32_t)(p.H * p.W);
+    const uint32_t t = r / hw, r2 = r - t * hw, h = r2 / (uint32_t)p.W, w = r2 - h * (uint32_t)p.W;
+    return t * p.xs_t + h * p.xs_h + w * p.xs_w;
 }
+__device__ __forceinline__ bool x_dense(const EmbP& p) { return p.xs_h == p.W * p.xs_w && p.xs_t == (int64_t)p.H * p.W * p.xs_w; }
 
 __global__ void __launch_bounds__(EMB_THREADS)
 embed_ln_fwd_kernel(EmbP p, float* __restrict__ y) {
@@ -37,13 +35,17 @@ embed_ln_fwd_kernel(EmbP p, float* __restrict__ y) {
 #pragma unroll
         for (int ci = 0; ci < MAXCIN; ++ci) wr[c][ci] = ci < p.Cin ? __ldg(p.w + (v * C + c) * p.Cin + ci) : 0.f;
     }
-    const int64_t thw = (int64_t)p.T * p.H * p.W, ntok = (int64_t)p.N * thw;
-    for (int64_t tok = (int64_t)blockIdx.x * EMB_THREADS + threadIdx.x; tok < ntok; tok += (int64_t)gridDim.x * EMB_THREADS) {
-        int n;
-        const int64_t xo = x_offset(p, tok, v, n);
+    // grid = (blocks, V, N): a block strides over the T*H*W tokens of one (n, v) image with 32-bit indices
+    const int n = blockIdx.z;
+    const uint32_t thw = (uint32_t)(p.T * p.H * p.W);
+    const bool dense = x_dense(p);
+    const float* ximg = p.x + n * p.xs_n + v * p.xs_v;
+    float* yimg = y + ((int64_t)n * p.V + v) * thw * C;
+    for (uint32_t r = blockIdx.x * EMB_THREADS + threadIdx.x; r < thw; r += gridDim.x * EMB_THREADS) {
+        const int64_t xo = x_offset(p, r, dense);
         float xin[MAXCIN];
 #pragma unroll
-        for (int ci = 0; ci < MAXCIN; ++ci) xin[ci] = ci < p.Cin ? __ldg(p.x + xo + ci * p.xs_c) : 0.f;
+        for (int ci = 0; ci < MAXCIN; ++ci) xin[ci] = ci < p.Cin ? __ldg(ximg + xo + ci * p.xs_c) : 0.f;
         float e[C], en[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) {
@@ -53,7 +55,7 @@ embed_ln_fwd_kernel(EmbP p, float* __restrict__ y) {
             e[c] = a;
         }
         ln16(e, en);
-        store16(y + (((int64_t)n * p.V + v) * thw + (tok - (int64_t)n * thw)) * C, en);
+        store16(yimg + (int64_t)r * C, en);
     }
 }
 
@@ -74,13 +76,18 @@ embed_ln_bwd_kernel(EmbP p, const float* __restrict__ gy, float* __restrict__ pa
     float acc[NG];
 #pragma unroll
     for (int k = 0; k < NG; ++k) acc[k] = 0.f;
-    const int64_t thw = (int64_t)p.T * p.H * p.W, ntok = (int64_t)p.N * thw;
-    for (int64_t tok = (int64_t)blockIdx.x * EMB_THREADS + threadIdx.x; tok < ntok; tok += (int64_t)gridDim.x * EMB_THREADS) {
-        int n;
-        const int64_t xo = x_offset(p, tok, v, n);
+    // blocks of one variable stride over the (n, in-image token) pairs: n advances only when a block wraps an image
+    const uint32_t thw = (uint32_t)(p.T * p.H * p.W);
+    const bool dense = x_dense(p);
+    const uint32_t per_img = (thw + EMB_THREADS - 1) / EMB_THREADS;            // chunks of EMB_THREADS tokens per image
+    for (uint32_t chunk = blockIdx.x; chunk < per_img * (uint32_t)p.N; chunk += gridDim.x) {
+        const uint32_t n = chunk / per_img, r = (chunk - n * per_img) * EMB_THREADS + threadIdx.x;
+        if (r >= thw) continue;
+        const float* ximg = p.x + n * p.xs_n + v * p.xs_v;
+        const int64_t xo = x_offset(p, r, dense);
         float xin[CIN];
 #pragma unroll
-        for (int ci = 0; ci < CIN; ++ci) xin[ci] = __ldg(p.x + xo + ci * p.xs_c);
+        for (int ci = 0; ci < CIN; ++ci) xin[ci] = __ldg(ximg + xo + ci * p.xs_c);
         float e[C], en[C], g[C], ge[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) {
@@ -90,7 +97,7 @@ embed_ln_bwd_kernel(EmbP p, const float* __restrict__ gy, float* __restrict__ pa
             e[c] = a;
         }
         const float rstd = ln16(e, en);
-        load16(g, gy + (((int64_t)n * p.V + v) * thw + (tok - (int64_t)n * thw)) * C);
+        load16(g, gy + (((int64_t)n * p.V + v) * thw + r) * C);
         ln16_bwd(g, en, rstd, ge);
 #pragma unroll
         for (int c = 0; c < C; ++c) {
@@ -148,7 +155,12 @@ extern "C" int idee_embed_ln_fwd(const float* x, const int64_t* x_strides, const
                                  int Cin, int T, int H, int W, int E, void* stream) {
     EmbP p;
     if (fill(p, x, x_strides, w, b, N, V, Cin, T, H, W, E)) return 1;
-    embed_ln_fwd_kernel<<<dim3(emb_blocks(V), V), EMB_THREADS, 0, (cudaStream_t)stream>>>(p, y);
+    IDEE_REQUIRE((int64_t)T * H * W < (1ll << 31) / C && N <= 65535, "embed_ln: image too large for 32-bit token indices");
+    int bx = (emb_blocks(V) + N - 1) / N;
+    const int need = (int)(((int64_t)T * H * W + EMB_THREADS - 1) / EMB_THREADS);
+    if (bx > need) bx = need;
+    if (bx < 1) bx = 1;
+    embed_ln_fwd_kernel<<<dim3(bx, V, N), EMB_THREADS, 0, (cudaStream_t)stream>>>(p, y);
     IDEE_LAUNCH_CHECK("embed_ln_fwd");
     return 0;
 }
@@ -159,6 +171,7 @@ extern "C" int idee_embed_ln_bwd(const float* x, const int64_t* x_strides, const
     EmbP p;
     if (fill(p, x, x_strides, w, b, N, V, Cin, T, H, W, E)) return 1;
     IDEE_REQUIRE(workspace_bytes >= idee_embed_ln_bwd_workspace_bytes(V), "embed_ln_bwd: workspace too small");
+    IDEE_REQUIRE((int64_t)T * H * W < (1ll << 31) / C, "embed_ln: image too large for 32-bit token indices");
     const int nb = emb_blocks(V);
     if (Cin == 1) embed_ln_bwd_kernel<1><<<dim3(nb, V), EMB_THREADS, 0, (cudaStream_t)stream>>>(p, gy, (float*)workspace);
     else if (Cin == 2) embed_ln_bwd_kernel<2><<<dim3(nb, V), EMB_THREADS, 0, (cudaStream_t)stream>>>(p, gy, (float*)workspace);
