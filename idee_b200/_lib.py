@@ -24,7 +24,7 @@ class ConvDesc(C.Structure):
     _fields_ = [(n, c_int) for n in ("N", "V", "Vw", "Cin", "Cout", "Ti", "Hi", "Wi", "To", "Ho", "Wo", "proj", "relu", "precision")] + \
                [(n, c_i64) for n in ("x_sn", "x_sv", "x_st", "x_sh", "x_sw", "x_sg")] + [("in_cpg", c_int)] + \
                [(n, c_i64) for n in ("y_sn", "y_sv", "y_st", "y_sh", "y_sw", "y_sg")] + [("out_cpg", c_int)] + \
-               [(n, c_int) for n in ("x_dtype", "y_dtype", "gx_dtype", "umma16")]
+               [(n, c_int) for n in ("x_dtype", "y_dtype", "gx_dtype", "umma16", "umma96")]
 
 
 _SIGS = {
@@ -114,6 +114,16 @@ UMMA16 = os.environ.get("IDEE_B200_UMMA16", "1") == "1"
 def set_umma(on: bool) -> None:
     global UMMA
     UMMA = bool(on)
+
+
+# warp-specialised tcgen05 + TMEM kernel for the dense 96 -> 96 classifier conv (forward + data gradient), bf16 mode only;
+# on by default (measured 1.9x / 1.5x faster than the mma.sync kernel), IDEE_B200_UMMA96=0 selects the mma.sync kernel
+UMMA96 = os.environ.get("IDEE_B200_UMMA96", "1") == "1"
+
+
+def set_umma96(on: bool) -> None:
+    global UMMA96
+    UMMA96 = bool(on)
 
 
 def set_umma16(on: bool) -> None:

@@ -1,0 +1,375 @@
+// Warp-specialised tcgen05 / TMEM implicit-GEMM kernel for the one dense contraction of the path: the 96 -> 96 classifier
+// convolution Conv3d(96, 96, (2,3,3), stride (2,1,1), pad (0,1,1)) (classifier/CNN_3D.py:84), forward and data gradient.
+//
+// Roles (288 threads):  warps 0-7 load the halo of tile i+1 (fp32 HBM -> bf16 shared memory) and then drain the accumulator of
+// tile i (tcgen05.ld -> bias / ReLU / mask -> fp32 stores; warp w owns TMEM lanes 32 (w & 3).. and columns 48 (w >> 2)..);
+// warp 8 streams the per-tap weight matrices through a cp.async ring and issues the tcgen05.mma of tile i.
+// Two halo buffers and two TMEM accumulators (2 x 96 columns) let the three stages run concurrently; all hand-offs are mbarriers (halo full, accumulator done via tcgen05.commit, accumulator drained, weight slot
+// free) -- there is no CTA-wide barrier in the steady state.
+//
+// Zero-copy operands (same construction as conv16_umma.cu): a tile is 16 rows x 8 columns of output pixels = 128 TMEM lanes,
+// the halo [kt][18][10] is stored as twelve 8-channel chunk planes with 16 bytes per pixel, so a tile row is one 8 x 16-byte
+// core matrix of the canonical K-major SWIZZLE_NONE layout and tap (kt,kh,kw), k-step ks is the descriptor
+// {start = plane(2 ks) + ((kt*18+kh)*10+kw)*16, LBO = plane stride, SBO = 160 B}.  K = taps x 96 = 1728 (forward) or 864 (data
+// gradient, taps of the output time parity) is accumulated in TMEM by 108 / 54 MMAs of shape M=128, N=96, K=16.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "idee_b200.h"
+
+namespace conv96u {
+
+constexpr int TR = 16, TC = 8, HR = TR + 2, HC = TC + 2;
+constexpr int CI = 96, CO = 96, KC = CI / 8;
+constexpr int NB = 4;                                  // weight-tap ring depth
+constexpr int B_TAP = CO * CI * 2;                     // 18432 bytes per tap, canonical [kc][ng][8][16 B]
+constexpr int B_LBO = (CO / 8) * 128, B_SBO = 128;
+constexpr int TMEM_COLS = 256;
+constexpr int NLOAD = 256;                             // loader / epilogue threads (warps 0-7); warp 8 = weights + MMA issue
+constexpr int MMA_WARP = NLOAD / 32, NTHREADS = NLOAD + 32;
+enum { U_FWD = 0, U_DGRAD = 1 };
+
+struct UP {
+    const float* in; float* out; const float* bias; const float* relu_src; const __nv_bfloat16* wB;
+    int N, Ti, Hi, Wi, To, Ho, Wo;
+    int64_t in_sn, out_sn;
+    int in_st, in_sh, in_sw, out_st, out_sh, out_sw;
+    int relu, tiles_w, tiles_h;
+    uint32_t total_tiles;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// instruction descriptor: D = F32, A = B = BF16, both K-major, N = 96, M = 128
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CO >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    while (!ok) {
+        __nanosleep(32);
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// fp32 reference-layout weights [Co][Ci][18] -> bf16 canonical K-major tiles, one per forward tap:
+//   wB[ft][kc][ng][r][e] = B(n = ng*8 + r, k = kc*8 + e);  forward: B(n,k) = W[n][k][ft];  dgrad: B(n,k) = W[k][n][ft]
+__global__ void prep96_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wB, int dgrad) {
+    const int total = 18 * CO * CI;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int el = e & 7, r = (e >> 3) & 7;
+        int q = e >> 6;
+        const int ng = q % (CO / 8); q /= (CO / 8);
+        const int kc = q % KC;
+        const int ft = q / KC;
+        const int n = ng * 8 + r, k = kc * 8 + el;
+        const int fo = dgrad ? k : n, fc = dgrad ? n : k;
+        wB[e] = __float2bfloat16(w[((int64_t)fo * CI + fc) * 18 + ft]);
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv96_umma_kernel(UP p) {
+    constexpr int KTIN = MODE == U_FWD ? 2 : 1, NT = MODE == U_FWD ? 18 : 9;
+    constexpr int NPX = KTIN * HR * HC;                   // halo pixels
+    constexpr int CHUNK = NPX * 16 + 16;                  // plane stride (+16: a pixel's 12 chunks land in different banks)
+    constexpr int HALO = KC * CHUNK;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* halo = smem_raw;                                        // [2][KC][NPX][16 B]
+    unsigned char* Bring = smem_raw + 2 * ((HALO + 127) / 128 * 128);      // [NB][B_TAP]
+    float* bias_s = reinterpret_cast<float*>(Bring + NB * B_TAP);          // [96]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + CO);             // full[2] | accdone[2] | accfree[2] | bslot[NB]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + NB);
+    constexpr int HALO_PAD = (HALO + 127) / 128 * 128;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t bar_full = smem_u32(&bars[0]), bar_done = smem_u32(&bars[2]), bar_free = smem_u32(&bars[4]), bar_slot = smem_u32(&bars[6]);
+
+    if (tid < CO) bias_s[tid] = p.bias ? p.bias[tid] : 0.f;
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_full + 8 * i, NLOAD); mbar_init(bar_done + 8 * i, 1); mbar_init(bar_free + 8 * i, NLOAD); }
+        for (int i = 0; i < NB; ++i) mbar_init(bar_slot + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    // contiguous tile range of this CTA
+    const uint32_t per_cta = (p.total_tiles + gridDim.x - 1) / gridDim.x;
+    const uint32_t first = blockIdx.x * per_cta, last = min(p.total_tiles, first + per_cta);
+    const uint32_t ntile = last > first ? last - first : 0;
+    struct Tile { int n, t, h0, w0; };
+    auto decode = [&](uint32_t tile) {
+        Tile c;
+        uint32_t r = tile;
+        c.w0 = (int)(r % (uint32_t)p.tiles_w) * TC; r /= (uint32_t)p.tiles_w;
+        c.h0 = (int)(r % (uint32_t)p.tiles_h) * TR; r /= (uint32_t)p.tiles_h;
+        c.t = (int)(r % (uint32_t)p.To); c.n = (int)(r / (uint32_t)p.To);
+        return c;
+    };
+
+    if (warp == MMA_WARP) {
+        // ================= weight ring + MMA issue =================
+        const uint32_t total_taps = ntile * NT;
+        auto tap_ft = [&](uint32_t g) -> int {                          // forward-tap index of global tap g
+            const uint32_t it = g / NT; const int j = (int)(g - it * NT);
+            if (MODE == U_FWD) return j;
+            const Tile c = decode(first + it);
+            return (c.t & 1) * 9 + (2 - j / 3) * 3 + (2 - j % 3);
+        };
+        auto load_B = [&](uint32_t g) {
+            const uint4* src = reinterpret_cast<const uint4*>(p.wB + (size_t)tap_ft(g) * CO * CI);
+            const uint32_t dst = smem_u32(Bring) + (g % NB) * B_TAP;
+#pragma unroll 4
+            for (int i = lane; i < B_TAP / 16; i += 32)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 16), "l"(src + i) : "memory");
+        };
+        for (uint32_t g = 0; g < NB; ++g) {                              // fill the ring (empty groups keep the count uniform)
+            if (g < total_taps) load_B(g);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        uint32_t g = 0;
+        for (uint32_t it = 0; it < ntile; ++it) {
+            const uint32_t b = it & 1;
+            mbar_wait(bar_full + 8 * b, (it >> 1) & 1u);                                   // halo of this tile is in shared memory
+            if (it >= 2) mbar_wait(bar_free + 8 * b, ((it >> 1) - 1) & 1u);                // accumulator b has been drained
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t adesc0 = make_desc(smem_u32(halo) + b * HALO_PAD, CHUNK, HC * 16);
+            const uint32_t dcol = tmem_base + b * CO;
+#pragma unroll 1
+            for (int j = 0; j < NT; ++j, ++g) {
+                // tap g has landed once at most NB-2 younger groups are pending (group index == tap index)
+                asm volatile("cp.async.wait_group %0;" ::"n"(NB - 2) : "memory");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    const int kt = MODE == U_FWD ? j / 9 : 0, kh = (j / 3) % 3, kw = j % 3;
+                    const uint64_t ad = adesc0 + (uint64_t)((kt * HR + kh) * HC + kw);
+                    const uint64_t bd = make_desc(smem_u32(Bring) + (g % NB) * B_TAP, B_LBO, B_SBO);
+#pragma unroll
+                    for (int ks = 0; ks < CI / 16; ++ks)
+                        umma_bf16(dcol, ad + (uint64_t)(ks * 2 * (CHUNK / 16)), bd + (uint64_t)(ks * 2 * (B_LBO / 16)), (j > 0 || ks > 0) ? 1u : 0u);
+                    umma_commit(bar_slot + 8 * (g % NB));                                   // slot is free when these MMAs have read it
+                    if (j == NT - 1) umma_commit(bar_done + 8 * b);                         // ... and the accumulator is complete
+                }
+                __syncwarp();
+                // refill the slot released by tap g-1 (its MMAs precede tap g's in the pipe, so this wait overlaps tap g)
+                if (g >= 1) {
+                    const uint32_t gp = g - 1;
+                    if (gp + NB < total_taps) {
+                        mbar_wait(bar_slot + 8 * (gp % NB), (gp / NB) & 1u);
+                        load_B(gp + NB);
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                }
+            }
+        }
+    } else {
+        // ================= halo loads (one tile ahead) + epilogue =================
+        auto load_halo = [&](const Tile& c, int buf) {
+            unsigned char* dst = halo + buf * HALO_PAD;
+            const float* in_n = p.in + c.n * p.in_sn;
+            constexpr int V4 = CI / 4, TOTAL = NPX * V4;                   // float4 units: (pixel, c4), c4 fastest
+            constexpr int DQ = NLOAD / V4, DC = NLOAD - DQ * V4;
+            int q = tid / V4, c4 = tid - q * V4;
+            constexpr int DEPTH = 12;
+            for (int e0 = tid; e0 < TOTAL; e0 += NLOAD * DEPTH) {
+                const float* src[DEPTH]; int dsto[DEPTH];
+#pragma unroll
+                for (int u = 0; u < DEPTH; ++u) {
+                    src[u] = nullptr; dsto[u] = -1;
+                    if (e0 + u * NLOAD < TOTAL) {
+                        const int kt = q / (HR * HC), rem = q - kt * (HR * HC), hh = rem / HC, ww = rem - hh * HC;
+                        const int ti = MODE == U_FWD ? 2 * c.t + kt : (c.t >> 1);
+                        const int hi = c.h0 + hh - 1, wi = c.w0 + ww - 1;
+                        const bool ok = ti < p.Ti && (unsigned)hi < (unsigned)p.Hi && (unsigned)wi < (unsigned)p.Wi;
+                        dsto[u] = (c4 >> 1) * CHUNK + q * 16 + (c4 & 1) * 8;
+                        if (ok) src[u] = in_n + (int64_t)(ti * p.in_st + hi * p.in_sh + wi * p.in_sw) + c4 * 4;
+                        q += DQ; c4 += DC;
+                        if (c4 >= V4) { c4 -= V4; ++q; }
+                    }
+                }
+                float4 f[DEPTH];
+#pragma unroll
+                for (int u = 0; u < DEPTH; ++u) f[u] = src[u] ? ldg4(src[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < DEPTH; ++u)
+                    if (dsto[u] >= 0) *reinterpret_cast<uint2*>(dst + dsto[u]) = make_uint2(pack_bf16(f[u].x, f[u].y), pack_bf16(f[u].z, f[u].w));
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core
+            mbar_arrive(bar_full + 8 * buf);
+        };
+        // warp w drains TMEM lanes 32 (w & 3).. (its 4 tile rows) x columns 48 (w >> 2)..  For the data gradient the ReLU mask
+        // of the 48 channels is fetched as a bit mask BEFORE waiting for the accumulator, so its latency hides behind the MMAs.
+        const int quad = warp & 3, chalf = warp >> 2;
+        auto out_offset = [&](const Tile& c, bool& pix_ok) -> int64_t {
+            const int r = quad * 4 + (lane >> 3), cc = lane & 7;
+            const int h = c.h0 + r, w = c.w0 + cc;
+            pix_ok = h < p.Ho && w < p.Wo;
+            return c.n * p.out_sn + (int64_t)(c.t * p.out_st + h * p.out_sh + w * p.out_sw) + chalf * 48;
+        };
+        auto relu_bits = [&](const Tile& c, uint32_t (&bits)[2]) {
+            bits[0] = bits[1] = 0xFFFFFFFFu;
+            if (!p.relu_src) return;
+            bool pix_ok;
+            const int64_t o = out_offset(c, pix_ok);
+            if (!pix_ok) return;
+            float4 a[12];
+#pragma unroll
+            for (int i = 0; i < 12; ++i) a[i] = ldg4(p.relu_src + o + 4 * i);
+            uint32_t b0 = 0u, b1 = 0u;
+#pragma unroll
+            for (int i = 0; i < 12; ++i) {
+                const uint32_t m = (a[i].x > 0.f ? 1u : 0u) | (a[i].y > 0.f ? 2u : 0u) | (a[i].z > 0.f ? 4u : 0u) | (a[i].w > 0.f ? 8u : 0u);
+                if (i < 8) b0 |= m << (4 * i); else b1 |= m << (4 * (i - 8));
+            }
+            bits[0] = b0; bits[1] = b1;
+        };
+        auto epilogue = [&](const Tile& c, int acc, const uint32_t (&bits)[2]) {
+            bool pix_ok;
+            const int64_t o = out_offset(c, pix_ok);
+            float* orow = p.out + o;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                float v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * CO + chalf * 48 + 16 * k, v);
+                if (pix_ok) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        float4 ov = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        { const float4 bb = ld4(bias_s + chalf * 48 + 16 * k + i); ov.x += bb.x; ov.y += bb.y; ov.z += bb.z; ov.w += bb.w; }
+                        if (p.relu) { ov.x = fmaxf(ov.x, 0.f); ov.y = fmaxf(ov.y, 0.f); ov.z = fmaxf(ov.z, 0.f); ov.w = fmaxf(ov.w, 0.f); }
+                        const int ch = 16 * k + i;                               // channel inside this warp's 48
+                        const uint32_t m = (ch < 32 ? bits[0] >> ch : bits[1] >> (ch - 32)) & 15u;
+                        if (!(m & 1u)) ov.x = 0.f; if (!(m & 2u)) ov.y = 0.f; if (!(m & 4u)) ov.z = 0.f; if (!(m & 8u)) ov.w = 0.f;
+                        st4(orow + ch, ov);
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(bar_free + 8 * acc);
+        };
+        Tile cur{}, nxt{};
+        if (ntile > 0) { nxt = decode(first); load_halo(nxt, 0); }
+        for (uint32_t it = 0; it < ntile; ++it) {
+            cur = nxt;
+            // buffer (it+1)&1 was read by tile it-1, whose completion these warps waited for before its epilogue
+            if (it + 1 < ntile) { nxt = decode(first + it + 1); load_halo(nxt, (it + 1) & 1); }
+            uint32_t bits[2];
+            relu_bits(cur, bits);
+            mbar_wait(bar_done + 8 * (it & 1), (it >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            epilogue(cur, it & 1, bits);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+}
+
+}  // namespace conv96u
+
+using namespace conv96u;
+
+bool conv96_umma_eligible(const idee_conv_desc* d) {
+    return d->umma96 && d->precision >= 1 && !d->proj && d->Cin == 96 && d->Cout == 96 && d->V == 1 && d->Vw == 1 && d->in_cpg == 6 &&
+           d->out_cpg == 6 && d->x_sw == 96 && d->y_sw == 96 && !d->x_dtype && !d->y_dtype && !d->gx_dtype;
+}
+
+size_t conv96_umma_workspace_bytes() { return sizeof(__nv_bfloat16) * 18 * CO * CI; }
+
+// dgrad == 0: y = conv(x) (+bias, ReLU);  dgrad == 1: gx = conv^T(gy) (optional ReLU mask)
+int conv96_umma_run(const idee_conv_desc* d, int dgrad, const float* in, const float* w, const float* bias, const float* relu_src,
+                    float* out, void* ws, cudaStream_t st) {
+    __nv_bfloat16* wB = (__nv_bfloat16*)ws;
+    prep96_weights_kernel<<<256, 256, 0, st>>>(w, wB, dgrad);
+    IDEE_LAUNCH_CHECK("conv3d(umma96) prep");
+    UP p{};
+    p.in = in; p.out = out; p.bias = bias; p.relu_src = relu_src; p.wB = wB; p.N = d->N;
+    int64_t is[4], os[4];
+    if (!dgrad) {
+        p.Ti = d->Ti; p.Hi = d->Hi; p.Wi = d->Wi; p.To = d->To; p.Ho = d->Ho; p.Wo = d->Wo;
+        is[0] = d->x_sn; is[1] = d->x_st; is[2] = d->x_sh; is[3] = d->x_sw; os[0] = d->y_sn; os[1] = d->y_st; os[2] = d->y_sh; os[3] = d->y_sw;
+        p.relu = d->relu;
+    } else {
+        p.Ti = d->To; p.Hi = d->Ho; p.Wi = d->Wo; p.To = d->Ti; p.Ho = d->Hi; p.Wo = d->Wi;
+        is[0] = d->y_sn; is[1] = d->y_st; is[2] = d->y_sh; is[3] = d->y_sw; os[0] = d->x_sn; os[1] = d->x_st; os[2] = d->x_sh; os[3] = d->x_sw;
+        p.relu = 0;
+    }
+    IDEE_REQUIRE((int64_t)(p.Ti + 1) * is[1] + (int64_t)(p.Hi + HR) * is[2] + (int64_t)(p.Wi + HC) * is[3] < (1ll << 31) &&
+                 (int64_t)(p.To + 1) * os[1] + (int64_t)(p.Ho + TR) * os[2] + (int64_t)(p.Wo + TC) * os[3] < (1ll << 31),
+                 "conv3d(umma96): tensor too large for 32-bit image-relative offsets");
+    p.in_sn = is[0]; p.in_st = (int)is[1]; p.in_sh = (int)is[2]; p.in_sw = (int)is[3];
+    p.out_sn = os[0]; p.out_st = (int)os[1]; p.out_sh = (int)os[2]; p.out_sw = (int)os[3];
+    p.tiles_w = (p.Wo + TC - 1) / TC; p.tiles_h = (p.Ho + TR - 1) / TR;
+    const int64_t total = (int64_t)d->N * p.To * p.tiles_h * p.tiles_w;
+    IDEE_REQUIRE(total < (1ll << 31), "conv3d(umma96): too many tiles");
+    p.total_tiles = (uint32_t)total;
+    const int ktin = dgrad ? 1 : 2;
+    const size_t halo_pad = ((size_t)KC * (ktin * HR * HC * 16 + 16) + 127) / 128 * 128;
+    const size_t smem = 2 * halo_pad + (size_t)NB * B_TAP + CO * 4 + (6 + NB) * 8 + 16;
+    int64_t grid = idee_num_sms();
+    if (grid > total) grid = total;
+    if (!dgrad) {
+        IDEE_CUDA(cudaFuncSetAttribute(conv96_umma_kernel<U_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "conv3d(umma96)");
+        conv96_umma_kernel<U_FWD><<<(unsigned)grid, NTHREADS, smem, st>>>(p);
+    } else {
+        IDEE_CUDA(cudaFuncSetAttribute(conv96_umma_kernel<U_DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "conv3d(umma96)");
+        conv96_umma_kernel<U_DGRAD><<<(unsigned)grid, NTHREADS, smem, st>>>(p);
+    }
+    IDEE_LAUNCH_CHECK("conv3d(umma96)");
+    return 0;
+}

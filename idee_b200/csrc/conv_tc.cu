@@ -966,6 +966,11 @@ size_t conv_umma_workspace_bytes();
 int conv_umma_run(const idee_conv_desc* d, int dgrad, const float* in, const float* w, const float* bias, const float* relu_src,
                   float* out, void* ws, cudaStream_t st);
 
+// warp-specialised tcgen05 / TMEM path for the 96 -> 96 classifier conv (conv96_umma.cu)
+bool conv96_umma_eligible(const idee_conv_desc* d);
+size_t conv96_umma_workspace_bytes();
+int conv96_umma_run(const idee_conv_desc* d, int dgrad, const float* in, const float* w, const float* bias, const float* relu_src,
+                    float* out, void* ws, cudaStream_t st);
 // tcgen05 / TMEM path for the bf16-input 16 -> 16 proj conv (conv16_umma.cu)
 size_t conv16_umma_workspace_bytes(int Vw);
 int conv16_umma_run(int mode, int out16, const void* in, const float* w, const float* bias, void* out, void* ws, int N, int V, int Vw,
@@ -980,6 +985,7 @@ static bool umma16_dgrad_eligible(const idee_conv_desc* d) {
 static size_t max_sz(size_t a, size_t b) { return a > b ? a : b; }
 
 size_t conv_tc_fwd_workspace_bytes(const idee_conv_desc* d) {
+    if (conv96_umma_eligible(d)) return conv96_umma_workspace_bytes();
     if (conv_umma_eligible(d)) return conv_umma_workspace_bytes();
     size_t b = make_plan(d->proj ? PROJ_FWD : CLS_FWD, d->Cin, d->Cout, d->Vw).wfrag_bytes;
     if (umma16_fwd_eligible(d)) b = max_sz(b, conv16_umma_workspace_bytes(d->Vw));
@@ -987,6 +993,7 @@ size_t conv_tc_fwd_workspace_bytes(const idee_conv_desc* d) {
 }
 
 size_t conv_tc_dgrad_workspace_bytes(const idee_conv_desc* d) {
+    if (conv96_umma_eligible(d)) return conv96_umma_workspace_bytes();
     if (conv_umma_eligible(d)) return conv_umma_workspace_bytes();
     size_t b = make_plan(d->proj ? PROJ_DGRAD_PAD : CLS_DGRAD, d->Cout, d->Cin, d->Vw).wfrag_bytes;
     if (umma16_dgrad_eligible(d)) b = max_sz(b, conv16_umma_workspace_bytes(d->Vw));
@@ -996,6 +1003,7 @@ size_t conv_tc_dgrad_workspace_bytes(const idee_conv_desc* d) {
 }
 
 int conv_tc_fwd(const idee_conv_desc* d, const void* x, const float* w, const float* b, void* y, void* ws, cudaStream_t st) {
+    if (conv96_umma_eligible(d)) return conv96_umma_run(d, 0, (const float*)x, w, b, nullptr, (float*)y, ws, st);
     if (conv_umma_eligible(d)) return conv_umma_run(d, 0, (const float*)x, w, b, nullptr, (float*)y, ws, st);
     if (umma16_fwd_eligible(d)) {
         const int64_t is[5] = {d->x_sn, d->x_sv, d->x_st, d->x_sh, d->x_sw}, os[5] = {d->y_sn, d->y_sv, d->y_st, d->y_sh, d->y_sw};
@@ -1018,6 +1026,7 @@ int conv_tc_fwd(const idee_conv_desc* d, const void* x, const float* w, const fl
 }
 
 int conv_tc_dgrad(const idee_conv_desc* d, const void* gy, const float* w, const void* relu_src, void* gx, void* ws, cudaStream_t st) {
+    if (conv96_umma_eligible(d)) return conv96_umma_run(d, 1, (const float*)gy, w, nullptr, (const float*)relu_src, (float*)gx, ws, st);
     if (conv_umma_eligible(d)) return conv_umma_run(d, 1, (const float*)gy, w, nullptr, (const float*)relu_src, (float*)gx, ws, st);
     const int mode = d->proj ? PROJ_DGRAD_PAD : CLS_DGRAD;
     const Plan pl = make_plan(mode, d->Cout, d->Cin, d->Vw);

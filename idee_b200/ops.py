@@ -213,6 +213,7 @@ def _conv_desc(x_dims, x_strides, y_strides, Vw, Cin, Cout, proj, relu, in_cpg, 
     d.x_sg, d.y_sg, d.in_cpg, d.out_cpg = x_sg, y_sg, in_cpg, out_cpg
     d.precision = (2 if L.UMMA else 1) if L.PRECISION == "bf16" else 0
     d.umma16 = int(L.UMMA16 and L.PRECISION == "bf16")
+    d.umma96 = int(L.UMMA96 and L.PRECISION == "bf16")
     return d
 
 

@@ -94,6 +94,9 @@ typedef struct {
     /* 1: run the bf16-input 16 -> 16 proj conv (forward and data gradient) on tcgen05 + TMEM (conv16_umma.cu) instead of
      * mma.sync; same operands and rounding points, different accumulation order */
     int umma16;
+    /* 1: run the 96 -> 96 classifier conv (forward and data gradient, fp32 I/O) on the warp-specialised tcgen05 + TMEM kernel
+     * (conv96_umma.cu) instead of mma.sync */
+    int umma96;
 } idee_conv_desc;
 
 size_t idee_conv3d_fwd_workspace_bytes(const idee_conv_desc* d);
