@@ -53,6 +53,9 @@ __device__ __forceinline__ void cp_async16_zfill(void* smem, const void* gmem, i
 __device__ __forceinline__ void cp_async16_u32(uint32_t smem, const void* gmem, int src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem), "l"(gmem), "r"(src_bytes));
 }
+__device__ __forceinline__ void cp_async4_u32(uint32_t smem, const void* gmem, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem), "l"(gmem), "r"(src_bytes));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
@@ -597,6 +600,116 @@ fold_pad_kernel(const float* __restrict__ gpad, void* __restrict__ gin_, const v
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Data gradient of the 16 -> 1 proj conv (the encoder's last conv folded with the quantiser's project_in): the incoming
+// gradient is ONE scalar per pixel, so gx[r][c] = sum over the (<= 27) pairs (p, tap) with clamp(p + tap - 1) == r of
+// W[c][tap] * gs[p] is a 27-point scalar stencil with 16 outputs -- 432 fp32 FMAs per pixel on the CUDA cores, no padded
+// domain and no fold pass (each axis contributes at most three (p, tap) pairs, also on the replicate border).
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int axis_pairs(int r, int S, int (&pp)[4], int (&kk)[4]) {
+    int n = 0;
+#pragma unroll
+    for (int off = -1; off <= 1; ++off) {
+        const int q = r - off;                                   // p + off == r
+        if (q >= 0 && q < S) { pp[n] = q; kk[n] = off + 1; ++n; }
+    }
+    if (r == 0) { pp[n] = 0; kk[n] = 0; ++n; }                   // p + off == -1 clamps to 0
+    if (r == S - 1) { pp[n] = S - 1; kk[n] = 2; ++n; }           // p + off == S clamps to S - 1
+    return n;
+}
+
+template <bool OUT16, bool RS16>
+__global__ void __launch_bounds__(256)
+proj_dgrad_scalar_kernel(const float* __restrict__ gs, const float* __restrict__ w, const void* __restrict__ relu_src_,
+                         void* __restrict__ gx_, int V, int Vw, int T, int H, int W, int64_t gs_sn, int64_t gs_sv, int gs_st, int gs_sh,
+                         int gs_sw, int rows_per_v, FastDiv fd_h, FastDiv fd_t) {
+    __shared__ __align__(16) float Ws[27][16];                    // [tap][c] of this variable's weight set
+    const int v = blockIdx.y;
+    const float* wv = w + (int64_t)(Vw == 1 ? 0 : v) * 16 * 27;   // [1][16][27]
+    for (int e = threadIdx.x; e < 27 * 16; e += 256) Ws[e / 16][e % 16] = wv[(e % 16) * 27 + e / 16];
+    __syncthreads();
+    for (int row = blockIdx.x; row < rows_per_v; row += gridDim.x) {       // row = (n, t, h) of variable v
+        uint32_t q, r;
+        fd_h.divmod((uint32_t)row, q, r); const int h = (int)r;
+        fd_t.divmod(q, q, r); const int t = (int)r;
+        const int n = (int)q;
+        int pt[4], kt[4], ph[4], kh[4];
+        const int nt = axis_pairs(t, T, pt, kt), nh = axis_pairs(h, H, ph, kh);
+        const float* gimg = gs + n * gs_sn + v * gs_sv;
+        const int64_t orow = ((((int64_t)n * V + v) * T + t) * H + h) * (int64_t)W * 16;
+        for (int x = threadIdx.x; x < W; x += 256) {
+            int pw[4], kw[4];
+            const int nw = axis_pairs(x, W, pw, kw);
+            float acc[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+            if (t > 0 && t < T - 1 && h > 0 && h < H - 1 && x > 0 && x < W - 1) {
+                // interior pixel: exactly the 27 pairs (p = r + 1 - k, k); all loads are issued before the FMAs
+                float g[27];
+                const float* g0 = gimg + (t + 1) * gs_st + (h + 1) * gs_sh + (x + 1) * gs_sw;
+#pragma unroll
+                for (int k = 0; k < 27; ++k) g[k] = __ldg(g0 - (k / 9) * gs_st - ((k / 3) % 3) * gs_sh - (k % 3) * gs_sw);
+#pragma unroll
+                for (int k = 0; k < 27; ++k) {
+                    const float4* wr = reinterpret_cast<const float4*>(Ws[k]);
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        const float4 ww = wr[c4];
+                        acc[4 * c4] += ww.x * g[k]; acc[4 * c4 + 1] += ww.y * g[k]; acc[4 * c4 + 2] += ww.z * g[k]; acc[4 * c4 + 3] += ww.w * g[k];
+                    }
+                }
+            } else
+            for (int a = 0; a < nt; ++a)
+                for (int b = 0; b < nh; ++b) {
+                    const float* grow = gimg + pt[a] * gs_st + ph[b] * gs_sh;
+                    const int tap0 = (kt[a] * 3 + kh[b]) * 3;
+                    for (int cidx = 0; cidx < nw; ++cidx) {
+                        const float g = __ldg(grow + pw[cidx] * gs_sw);
+                        const float4* wr = reinterpret_cast<const float4*>(Ws[tap0 + kw[cidx]]);
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; ++c4) {
+                            const float4 ww = wr[c4];
+                            acc[4 * c4] += ww.x * g; acc[4 * c4 + 1] += ww.y * g; acc[4 * c4 + 2] += ww.z * g; acc[4 * c4 + 3] += ww.w * g;
+                        }
+                    }
+                }
+            const int64_t o = orow + (int64_t)x * 16;
+            if (relu_src_) {
+                if (RS16) {
+                    const uint4* rs = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(relu_src_) + o);
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        const uint4 u = __ldg(rs + hf);
+                        const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (!(__uint_as_float(uu[k] << 16) > 0.f)) acc[8 * hf + 2 * k] = 0.f;
+                            if (!(__uint_as_float(uu[k] & 0xFFFF0000u) > 0.f)) acc[8 * hf + 2 * k + 1] = 0.f;
+                        }
+                    }
+                } else {
+                    const float* rs = reinterpret_cast<const float*>(relu_src_) + o;
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        const float4 a4 = ldg4(rs + 4 * c4);
+                        if (!(a4.x > 0.f)) acc[4 * c4] = 0.f; if (!(a4.y > 0.f)) acc[4 * c4 + 1] = 0.f;
+                        if (!(a4.z > 0.f)) acc[4 * c4 + 2] = 0.f; if (!(a4.w > 0.f)) acc[4 * c4 + 3] = 0.f;
+                    }
+                }
+            }
+            if (OUT16) {
+                uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(gx_) + o);
+                dst[0] = make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]), pack_bf16(acc[6], acc[7]));
+                dst[1] = make_uint4(pack_bf16(acc[8], acc[9]), pack_bf16(acc[10], acc[11]), pack_bf16(acc[12], acc[13]), pack_bf16(acc[14], acc[15]));
+            } else {
+                float* dst = reinterpret_cast<float*>(gx_) + o;
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) st4(dst + 4 * c4, make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]));
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // weight gradient
 // ------------------------------------------------------------------------------------------------------------------
 struct WP {
@@ -612,6 +725,138 @@ struct WP {
     int a16, g16;
     FastDiv fd_to, fd_tw, fd_th, fd_ipn;
 };
+
+// ------------------------------------------------------------------------------------------------------------------
+// Weight gradient of the 16 -> 1 proj conv as ONE small GEMM per tile:  dW[c][tap] = sum_q h[q][c] * G[q][tap], where
+// G[q][tap] = sum of gs[p] over the pixels p with clamp(p + tap - 1) == q is the im2col of the SCALAR gradient plane (27 values
+// per pixel from a 3 x 10 x 18 halo of floats; the replicate border adds at most one extra term per axis).  Every h pixel is
+// read once (no shifted re-reads of the 16-channel halo): per 16 pixels one ldmatrix for h, two for G and four HMMAs.
+// Partials use conv.cu's layout so the shared second-stage reduction applies (entry (tap, c, o = 0) at tap*256 + c*16).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+proj_wgrad_scalar_kernel(WP p) {
+    constexpr int CPA = 24, CPG = 40, NHALO = 3 * HH * HW_;            // pixel strides (halves) of the h / G tiles
+    __shared__ __align__(16) __nv_bfloat16 tileA[2][TH * TW * CPA];    // h tile, double buffered (cp.async)
+    __shared__ __align__(16) float gsh[2][NHALO];                      // scalar-gradient halo, double buffered
+    __shared__ __align__(16) __nv_bfloat16 tileG[TH * TW * CPG];       // im2col of the scalar plane, 32 columns (27 taps + 5 zeros)
+    __shared__ float red[27 * 16 + 1];
+    const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(p.in);
+    const float* gout = reinterpret_cast<const float*>(p.gout);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int s = blockIdx.x, wset = blockIdx.y;
+    for (int e = tid; e < 27 * 16 + 1; e += 128) red[e] = 0.f;
+    float acc[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+    float gsum = 0.f;
+    const int imgs_per_n = p.Vw == 1 ? p.V : 1;
+    (void)imgs_per_n;
+    const int64_t t_begin = p.tiles_per_set * s / p.S, t_end = p.tiles_per_set * (s + 1) / p.S;
+    const int a_pix = (lane & 7) + (lane >> 4) * 8, a_coff = ((lane >> 3) & 1) * 8;     // A (trans) lane address
+    const int b_pix = (lane & 7) + ((lane >> 3) & 1) * 8, b_coff = (lane >> 4) * 8;     // B (trans) lane address
+    const int pr = tid / TW, pc = tid % TW;                                              // this thread's tile pixel
+    struct Tile { int n, v, t, h0, w0; };
+    auto decode = [&](int64_t tile64) {
+        Tile c;
+        uint32_t q, r;
+        p.fd_to.divmod((uint32_t)tile64, q, r); c.t = (int)r;
+        p.fd_tw.divmod(q, q, r); c.w0 = (int)r * TW;
+        p.fd_th.divmod(q, q, r); c.h0 = (int)r * TH;
+        if (p.Vw == 1) { p.fd_ipn.divmod(q, q, r); c.n = (int)q; c.v = (int)r; }
+        else { c.n = (int)q; c.v = wset; }
+        return c;
+    };
+    auto issue = [&](const Tile& c, int buf) {
+        // h tile: 128 pixels x 2 chunks of 16 bytes (zero-fill outside the image: those pixels contribute nothing)
+        const __nv_bfloat16* in_img = in + c.n * p.in_sn + c.v * p.in_sv;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int e = tid + i * 128, pix = e >> 1, ch = e & 1;
+            const int h = c.h0 + pix / TW, w = c.w0 + pix % TW;
+            const bool ok = h < p.Hi && w < p.Wi;
+            const __nv_bfloat16* src = ok ? in_img + (int64_t)(c.t * (int)p.in_st + h * (int)p.in_sh + w * (int)p.in_sw) + ch * 8 : in;
+            cp_async16_u32(smem_u32(&tileA[buf][pix * CPA + ch * 8]), src, ok ? 16 : 0);
+        }
+        // scalar halo [3][10][18], zero outside the image
+        const float* g_img = gout + c.n * p.go_sn + c.v * p.go_sv;
+        for (int e = tid; e < NHALO; e += 128) {
+            const int a = e / (HH * HW_), rem = e - a * (HH * HW_), b = rem / HW_, cc = rem - b * HW_;
+            const int pt = c.t - 1 + a, ph = c.h0 - 1 + b, pw = c.w0 - 1 + cc;
+            const bool ok = (unsigned)pt < (unsigned)p.To && (unsigned)ph < (unsigned)p.Ho && (unsigned)pw < (unsigned)p.Wo;
+            const float* src = ok ? g_img + (int64_t)(pt * (int)p.go_st + ph * (int)p.go_sh + pw * (int)p.go_sw) : gout;
+            cp_async4_u32(smem_u32(&gsh[buf][e]), src, ok ? 4 : 0);
+        }
+        cp_async_commit();
+    };
+    Tile nxt{};
+    if (t_begin < t_end) { nxt = decode(t_begin); issue(nxt, 0); }
+    int buf = 0;
+    for (int64_t tile = t_begin; tile < t_end; ++tile, buf ^= 1) {
+        const Tile c = nxt;
+        cp_async_wait<0>();
+        __syncthreads();                                   // tile data landed; previous tile's MMAs are done with tileG
+        // ---- im2col row of this thread's pixel q = (t, h0 + pr, w0 + pc) ----
+        {
+            const float* gh = gsh[buf];
+            const int qh = c.h0 + pr, qw = c.w0 + pc;
+            const bool in_img = qh < p.Ho && qw < p.Wo;
+            // extra (clamped) source per axis: low border feeds tap 0 from p = q, high border feeds tap 2 from p = q
+            const bool xt0 = c.t == 0, xt2 = c.t == p.To - 1, xh0 = qh == 0, xh2 = qh == p.Ho - 1, xw0 = qw == 0, xw2 = qw == p.Wo - 1;
+            uint32_t packed[16];
+            float prev = 0.f;
+#pragma unroll
+            for (int k = 0; k < 27; ++k) {
+                const int kt = k / 9, kh = (k / 3) % 3, kw = k % 3;
+                // exact pair p = q + 1 - k  ->  halo index (2 - kt, pr + 2 - kh, pc + 2 - kw)
+                float v = gh[((2 - kt) * HH + pr + 2 - kh) * HW_ + pc + 2 - kw];
+                const bool et = (kt == 0 && xt0) || (kt == 2 && xt2), eh = (kh == 0 && xh0) || (kh == 2 && xh2),
+                           ew = (kw == 0 && xw0) || (kw == 2 && xw2);
+                if (et || eh || ew) {                      // border: add the clamped combinations (center index 1 / pr+1 / pc+1)
+                    const int at[2] = {2 - kt, 1}, ah[2] = {pr + 2 - kh, pr + 1}, aw[2] = {pc + 2 - kw, pc + 1};
+                    v = 0.f;
+                    for (int i = 0; i <= (et ? 1 : 0); ++i)
+                        for (int j = 0; j <= (eh ? 1 : 0); ++j)
+                            for (int l = 0; l <= (ew ? 1 : 0); ++l) v += gh[(at[i] * HH + ah[j]) * HW_ + aw[l]];
+                }
+                if (!in_img) v = 0.f;
+                if (k & 1) packed[k >> 1] = pack_bf16(prev, v); else prev = v;
+            }
+            packed[13] = pack_bf16(prev, 0.f); packed[14] = 0u; packed[15] = 0u;
+            uint4* row = reinterpret_cast<uint4*>(tileG + tid * CPG);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) row[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+            if (in_img) gsum += gh[(1 * HH + pr + 1) * HW_ + pc + 1];
+        }
+        __syncthreads();
+        if (tile + 1 < t_end) { nxt = decode(tile + 1); issue(nxt, buf ^ 1); }
+        // ---- D[16 ch x 32 taps] += h^T G over this warp's two 16-pixel rows ----
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+            const int ks = warp * 2 + kk;
+            uint32_t a[4], b0[4], b1[4];
+            ldsm_x4_t(a, &tileA[buf][(ks * TW + a_pix) * CPA + a_coff]);
+            ldsm_x4_t(b0, tileG + (ks * TW + b_pix) * CPG + b_coff);
+            ldsm_x4_t(b1, tileG + (ks * TW + b_pix) * CPG + 16 + b_coff);
+            mma_bf16(acc[0], a, b0[0], b0[1]); mma_bf16(acc[1], a, b0[2], b0[3]);
+            mma_bf16(acc[2], a, b1[0], b1[1]); mma_bf16(acc[3], a, b1[2], b1[3]);
+        }
+    }
+    // ---- CTA reduction (4 warps hold partial sums over disjoint pixels) and partial store ----
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int tap = nt * 8 + (lane % 4) * 2 + (q & 1), ch = lane / 4 + (q >> 1) * 8;
+            if (tap < 27) atomicAdd(&red[tap * 16 + ch], acc[nt][q]);
+        }
+    gsum = warp_sum(gsum);
+    if (lane == 0) atomicAdd(&red[27 * 16], gsum);
+    __syncthreads();
+    constexpr int PS = 27 * 256 + 16;
+    float* part = p.partials + ((int64_t)wset * p.S + s) * PS;                // n_ic == n_oc16 == 1
+    for (int e = tid; e < 27 * 16; e += 128) part[(e / 16) * 256 + (e % 16) * 16] = red[e];
+    if (tid == 0) part[27 * 256] = red[27 * 16];
+}
 
 // NT taps, NTL n-tiles (8 output channels each) per CTA; cin chunk 16.  A16 / G16: the input / output-gradient tensors hold
 // bf16: their tiles are then copied by cp.async straight into the (double-buffered) MMA layout, no staging and no convert.
@@ -635,7 +880,7 @@ wgrad_tc_kernel(WP p) {
     const g_t* gout = reinterpret_cast<const g_t*>(p.gout);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int s = blockIdx.x, wset = blockIdx.y;
-    const int n_occ = (p.n_oc16 * 16 + NC - 1) / NC;          // output chunks of NC channels
+    const int n_occ = (p.FCO + NC - 1) / NC;                  // output chunks of NC channels that hold real channels
     const int ic = blockIdx.z / n_occ, occ = blockIdx.z % n_occ;
     float acc[TPW][NTL][4], accb[NTL][4];
 #pragma unroll
@@ -659,6 +904,7 @@ wgrad_tc_kernel(WP p) {
     const int b_pix = (lane & 7) + ((lane >> 3) & 1) * 8, b_coff = (lane >> 4) * 8;     // B (trans) lane address
     const int64_t coff = (ic / p.in_cpg) * p.in_sg + (ic % p.in_cpg) * 16;
     const bool g_vec = G16 || (p.FCO % 4) == 0;               // gout rows can be fetched in 16-byte pieces
+    const bool g_one = !G16 && p.FCO == 1;                    // single output channel (logit convs, folded 16 -> 1 proj conv)
     // smem offsets (halves) of this warp's taps inside the halo tile
     int a_off[TPW];
 #pragma unroll
@@ -749,7 +995,13 @@ wgrad_tc_kernel(WP p) {
                 cp_async16_u32(dstA + d, in_img + off, ok ? 16 : 0);
             }
         }
-        if (g_vec) {
+        if (g_one) {                                   // one real output channel: one 4-byte async copy per tile pixel
+            const int pr = tid / TW, pc = tid % TW;
+            const bool ok = c.h0 + pr < p.Ho && c.w0 + pc < p.Wo;
+            const float* src = reinterpret_cast<const float*>(p.gout) + c.n * p.go_sn + c.v * p.go_sv +
+                               (int64_t)(c.t * (int)p.go_st + (c.h0 + pr) * (int)p.go_sh + (c.w0 + pc) * (int)p.go_sw);
+            cp_async4_u32(smem_u32(stageG) + tid * 4, ok ? src : reinterpret_cast<const float*>(p.gout), ok ? 4 : 0);
+        } else if (g_vec) {
             const g_t* go_tile = gout + c.n * p.go_sn + c.v * p.go_sv + (int64_t)(c.t * (int)p.go_st + c.h0 * (int)p.go_sh + c.w0 * (int)p.go_sw);
             if (g_full && c.h0 + TH <= p.Ho && c.w0 + TW <= p.Wo) {
 #pragma unroll
@@ -786,7 +1038,12 @@ wgrad_tc_kernel(WP p) {
             }
         }
         if (!G16) {
-            if (g_vec) {
+            if (g_one) {
+                const float v = stageG[tid];
+                uint4 row = make_uint4(pack_bf16(v, 0.f), 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(tileG0 + tid * CPG) = row;
+                if (NC > 8) for (int c8 = 1; c8 < NC / 8; ++c8) *reinterpret_cast<uint4*>(tileG0 + tid * CPG + c8 * 8) = make_uint4(0u, 0u, 0u, 0u);
+            } else if (g_vec) {
                 for (int e = tid; e < TH * TW * (NC / 4); e += 128) {
                     const int c4 = e % (NC / 4), pix = e / (NC / 4);
                     const float4 f = ld4(stageG + e * 4);
@@ -922,6 +1179,10 @@ int launch_tc16(const P& p, int n_img_t, cudaStream_t st, const char* who) {
 template <int MODE>
 int dispatch_tc(const P& p, const Plan& pl, int n_img_t, cudaStream_t st, const char* who) {
     if (p.in16 || p.out16) {       // bf16 activation storage: 16 -> 16 proj conv (forward: any mix, data gradient: bf16 input)
+        if constexpr (MODE == PROJ_FWD) {          // 16 -> 1 (the last encoder conv folded with the quantiser's project_in)
+            if (pl.KS == 1 && p.CIr == 16 && pl.n_oc == 1 && pl.NTL == 1 && p.in16 && !p.out16)
+                return launch_tc16<MODE, 1, true, false>(p, n_img_t, st, who);
+        }
         if (pl.KS == 1 && p.CIr == 16 && pl.n_oc == 1 && pl.NTL == 2) {
             if constexpr (MODE == PROJ_FWD) {
                 if (p.in16 && p.out16) return launch_tc16<MODE, 2, true, true>(p, n_img_t, st, who);
@@ -993,6 +1254,7 @@ size_t conv_tc_fwd_workspace_bytes(const idee_conv_desc* d) {
 }
 
 size_t conv_tc_dgrad_workspace_bytes(const idee_conv_desc* d) {
+    if (d->proj && d->Cout == 1 && d->Cin == 16) return 0;           // scalar-gradient stencil: no staging
     if (conv96_umma_eligible(d)) return conv96_umma_workspace_bytes();
     if (conv_umma_eligible(d)) return conv_umma_workspace_bytes();
     size_t b = make_plan(d->proj ? PROJ_DGRAD_PAD : CLS_DGRAD, d->Cout, d->Cin, d->Vw).wfrag_bytes;
@@ -1028,6 +1290,31 @@ int conv_tc_fwd(const idee_conv_desc* d, const void* x, const float* w, const fl
 int conv_tc_dgrad(const idee_conv_desc* d, const void* gy, const float* w, const void* relu_src, void* gx, void* ws, cudaStream_t st) {
     if (conv96_umma_eligible(d)) return conv96_umma_run(d, 1, (const float*)gy, w, nullptr, (const float*)relu_src, (float*)gx, ws, st);
     if (conv_umma_eligible(d)) return conv_umma_run(d, 1, (const float*)gy, w, nullptr, (const float*)relu_src, (float*)gx, ws, st);
+    if (d->proj && d->Cout == 1 && d->Cin == 16) {            // one scalar per pixel comes in: CUDA-core stencil, exact replicate adjoint
+        IDEE_REQUIRE(d->y_dtype == 0, "conv3d_dgrad(proj 16->1): the incoming gradient must be fp32");
+        IDEE_REQUIRE(d->x_sw == 16 && d->x_sh == (int64_t)d->Wi * 16 && d->x_st == (int64_t)d->Hi * d->Wi * 16 &&
+                     d->x_sv == (int64_t)d->Ti * d->Hi * d->Wi * 16 && d->x_sn == d->x_sv * d->V,
+                     "conv3d_dgrad(proj 16->1): the input gradient must be a contiguous [N,V,T,H,W,16] tensor");
+        IDEE_REQUIRE((int64_t)d->To * d->y_st + (int64_t)d->Ho * d->y_sh + (int64_t)d->Wo * d->y_sw < (1ll << 31),
+                     "conv3d_dgrad(proj 16->1): tensor too large for 32-bit offsets");
+        const int64_t rows64 = (int64_t)d->N * d->Ti * d->Hi;
+        IDEE_REQUIRE(rows64 < (1ll << 31), "conv3d_dgrad(proj 16->1): too many rows");
+        int nb = (int)rows64;
+        const int cap = (idee_num_sms() * 8 + d->V - 1) / d->V;
+        if (nb > cap) nb = cap;
+        const FastDiv fh = make_fastdiv(d->Hi), ft = make_fastdiv(d->Ti);
+        dim3 grid(nb, d->V);
+#define IDEE_SCALAR_DGRAD(O_, R_)                                                                                           \
+        proj_dgrad_scalar_kernel<O_, R_><<<grid, 256, 0, st>>>((const float*)gy, w, relu_src, gx, d->V, d->Vw, d->Ti, d->Hi, d->Wi, \
+                                                             d->y_sn, d->y_sv, (int)d->y_st, (int)d->y_sh, (int)d->y_sw, (int)rows64, fh, ft)
+        if (d->gx_dtype && d->x_dtype) IDEE_SCALAR_DGRAD(true, true);
+        else if (d->gx_dtype) IDEE_SCALAR_DGRAD(true, false);
+        else if (d->x_dtype) IDEE_SCALAR_DGRAD(false, true);
+        else IDEE_SCALAR_DGRAD(false, false);
+#undef IDEE_SCALAR_DGRAD
+        IDEE_LAUNCH_CHECK("conv3d_dgrad(proj 16->1)");
+        return 0;
+    }
     const int mode = d->proj ? PROJ_DGRAD_PAD : CLS_DGRAD;
     const Plan pl = make_plan(mode, d->Cout, d->Cin, d->Vw);
     if (prep(d, w, (uint2*)ws, pl, 1, st)) return 2;
@@ -1081,7 +1368,7 @@ int conv_tc_wgrad_ncout(const idee_conv_desc* d) { return d->Cout >= 32 ? 32 : (
 
 int conv_tc_wgrad_splits(const idee_conv_desc* d) {
     const int n_ic = (d->Cin + 15) / 16, NC = conv_tc_wgrad_ncout(d);
-    const int n_occ = (((d->Cout + 15) / 16) * 16 + NC - 1) / NC;
+    const int n_occ = (d->Cout + NC - 1) / NC;
     int S = (idee_num_sms() * 4 + d->Vw * n_ic * n_occ - 1) / (d->Vw * n_ic * n_occ);
     if (S < 1) S = 1;
     if (S > 512) S = 512;
@@ -1110,7 +1397,7 @@ int conv_tc_wgrad_partials(const idee_conv_desc* d, const void* x, const void* g
     p.fd_ipn = make_fastdiv(d->Vw == 1 ? d->V : 1);
     IDEE_REQUIRE(p.tiles_per_set < (1ll << 31), "conv3d_wgrad(bf16): too many tiles for 32-bit tile indices");
     const int NC = conv_tc_wgrad_ncout(d);
-    const int n_occ = (p.n_oc16 * 16 + NC - 1) / NC;
+    const int n_occ = (d->Cout + NC - 1) / NC;
     // the partial buffer is only partly written when Cout is not a multiple of 16 (Cout == 1): clear it first
     if (d->Cout % 16) IDEE_CUDA(cudaMemsetAsync(partials, 0, conv_tc_wgrad_workspace_bytes(d), st), "conv3d_wgrad(bf16)");
     dim3 grid(p.S, d->Vw, p.n_ic * n_occ);
@@ -1125,8 +1412,13 @@ int conv_tc_wgrad_partials(const idee_conv_desc* d, const void* x, const void* g
         IDEE_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<NT_, NTL_, A_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "conv3d_wgrad(bf16)"); \
         wgrad_tc_kernel<NT_, NTL_, A_, G_><<<grid, 128, smem, st>>>(p);                                                    \
     } while (0)
-    if (d->proj) {
-        if (NC != 16) { idee_set_error("conv3d_wgrad(proj,bf16): Cout must be 16"); return 1; }
+    if (d->proj && NC == 8) {                      // 16 -> 1: the incoming gradient is one scalar per pixel
+        if (p.g16) { idee_set_error("conv3d_wgrad(proj 16->1,bf16): the incoming gradient must be fp32"); return 1; }
+        if (p.a16 && d->Cin == 16 && d->Cout == 1 && d->x_sw == 16 && d->y_sw == 1) {
+            proj_wgrad_scalar_kernel<<<dim3(p.S, d->Vw), 128, 0, st>>>(p);          // im2col-of-the-scalar-plane GEMM
+        } else if (p.a16) IDEE_WGRAD_LAUNCH(27, 1, true, false); else IDEE_WGRAD_LAUNCH(27, 1, false, false);
+    } else if (d->proj) {
+        if (NC != 16) { idee_set_error("conv3d_wgrad(proj,bf16): Cout must be 1 or 16"); return 1; }
         if (p.a16 && p.g16) IDEE_WGRAD_LAUNCH(27, 2, true, true);
         else if (p.a16) IDEE_WGRAD_LAUNCH(27, 2, true, false);
         else if (p.g16) IDEE_WGRAD_LAUNCH(27, 2, false, true);

@@ -46,6 +46,8 @@ __device__ __forceinline__ void block_reduce_store(double* acc, double* out) {
     }
 }
 
+// ZS: z holds the projected scalar s itself ([ntok], project_in already applied by the producer)
+template <bool ZS>
 __global__ void __launch_bounds__(LFQ_THREADS)
 lfq_fwd_kernel(const float* __restrict__ z, const float* __restrict__ w_in, const float* __restrict__ b_in,
                const float* __restrict__ w_out, const float* __restrict__ b_out, float* __restrict__ zq,
@@ -53,15 +55,19 @@ lfq_fwd_kernel(const float* __restrict__ z, const float* __restrict__ w_in, cons
                float inv_temp) {
     float wi[C], wo[C], bo[C];
 #pragma unroll
-    for (int c = 0; c < C; ++c) { wi[c] = __ldg(w_in + c); wo[c] = __ldg(w_out + c); bo[c] = __ldg(b_out + c); }
-    const float bi = __ldg(b_in);
+    for (int c = 0; c < C; ++c) { wi[c] = ZS ? 0.f : __ldg(w_in + c); wo[c] = __ldg(w_out + c); bo[c] = __ldg(b_out + c); }
+    const float bi = ZS ? 0.f : __ldg(b_in);
     double acc[4] = {0.0, 0.0, 0.0, 0.0};   // sum entropy, sum p0, sum p1, sum (s-q)^2
     for (int64_t tok = (int64_t)blockIdx.x * LFQ_THREADS + threadIdx.x; tok < ntok; tok += (int64_t)gridDim.x * LFQ_THREADS) {
-        float zr[C];
-        load16(zr, z + tok * C);
-        float s = bi;
+        float s;
+        if (ZS) s = __ldg(z + tok);
+        else {
+            float zr[C];
+            load16(zr, z + tok * C);
+            s = bi;
 #pragma unroll
-        for (int c = 0; c < C; ++c) s += wi[c] * zr[c];
+            for (int c = 0; c < C; ++c) s += wi[c] * zr[c];
+        }
         const float q = s > 0.f ? 1.f : -1.f;
         const float x = training ? s + (q - s) : q;
         indices[tok] = x > 0.f ? 1 : 0;
@@ -101,6 +107,7 @@ __global__ void lfq_finalize_kernel(const double* __restrict__ partials, int nbl
 
 constexpr int LFQ_NG = 3 * C + 1;   // g_w_in[16], g_b_in, g_w_out[16], g_b_out[16]
 
+template <bool ZS>
 __global__ void __launch_bounds__(LFQ_THREADS)
 lfq_bwd_kernel(const float* __restrict__ z, const float* __restrict__ gzq, const float* __restrict__ gxq, const float* __restrict__ g_aux,
                const float* __restrict__ stats, const float* __restrict__ w_in, const float* __restrict__ b_in,
@@ -108,8 +115,8 @@ lfq_bwd_kernel(const float* __restrict__ z, const float* __restrict__ gzq, const
                float lam_commit, float lam_ent, float gamma, float inv_temp) {
     float wi[C], wo[C];
 #pragma unroll
-    for (int c = 0; c < C; ++c) { wi[c] = __ldg(w_in + c); wo[c] = __ldg(w_out + c); }
-    const float bi = __ldg(b_in);
+    for (int c = 0; c < C; ++c) { wi[c] = ZS ? 0.f : __ldg(w_in + c); wo[c] = __ldg(w_out + c); }
+    const float bi = ZS ? 0.f : __ldg(b_in);
     const float ga = g_aux ? __ldg(g_aux) : 0.f;
     const float invn = 1.f / (float)ntok;
     const float cb_diff = ent_grad(__ldg(stats + 5)) - ent_grad(__ldg(stats + 4));   // f(pbar1) - f(pbar0)
@@ -122,11 +129,15 @@ lfq_bwd_kernel(const float* __restrict__ z, const float* __restrict__ gzq, const
     int cnt = 0;
     for (int64_t tok = (int64_t)blockIdx.x * LFQ_THREADS + threadIdx.x; tok < ntok; tok += (int64_t)gridDim.x * LFQ_THREADS) {
         float zr[C], gr[C];
-        load16(zr, z + tok * C);
         load16(gr, gzq + tok * C);
-        float s = bi;
+        float s;
+        if (ZS) s = __ldg(z + tok);
+        else {
+            load16(zr, z + tok * C);
+            s = bi;
 #pragma unroll
-        for (int c = 0; c < C; ++c) s += wi[c] * zr[c];
+            for (int c = 0; c < C; ++c) s += wi[c] * zr[c];
+        }
         const float q = s > 0.f ? 1.f : -1.f;
         const float x = s + (q - s);
         float gs = 0.f;
@@ -138,11 +149,14 @@ lfq_bwd_kernel(const float* __restrict__ z, const float* __restrict__ gzq, const
         const float dp1 = 2.f * inv_temp * 2.f * p0 * p1;     // d p1 / d s  (= 400 p0 p1 at inv_temp 100)
         const float d_ent = dp1 * (ent_grad(p1) - ent_grad(p0));
         gs += ga * invn * (lam_commit * 2.f * (s - q) + lam_ent * d_ent - gamma * dp1 * cb_diff);
-        float r[C];
+        if (ZS) gz[tok] = gs;                      // gradient w.r.t. the scalar; project_in's gradients come from the producer
+        else {
+            float r[C];
 #pragma unroll
-        for (int c = 0; c < C; ++c) { r[c] = gs * wi[c]; a_wi[c] += gs * zr[c]; }
-        a_bi += gs;
-        store16(gz + tok * C, r);
+            for (int c = 0; c < C; ++c) { r[c] = gs * wi[c]; a_wi[c] += gs * zr[c]; }
+            a_bi += gs;
+            store16(gz + tok * C, r);
+        }
         if (++cnt == 64) {   // flush fp32 running sums into double
 #pragma unroll
             for (int c = 0; c < C; ++c) { acc[c] += a_wi[c]; acc[C + 1 + c] += a_wo[c]; acc[2 * C + 1 + c] += a_bo[c]; a_wi[c] = a_wo[c] = a_bo[c] = 0.f; }
@@ -180,12 +194,14 @@ extern "C" int idee_lfq_fwd(const float* z, const float* w_in, const float* b_in
                             float* zq, int64_t* indices, float* xq, float* stats, int64_t ntok, int dim, int codebook_size, int training,
                             float inv_temperature, float lambda_commit, float lambda_entropy, float diversity_gamma,
                             void* workspace, size_t workspace_bytes, void* stream) {
-    IDEE_REQUIRE(dim == C && codebook_size == 2, "lfq_fwd: only dim=16, codebook_size=2 is built (got %d, %d)", dim, codebook_size);
+    IDEE_REQUIRE((dim == C || dim == 1) && codebook_size == 2, "lfq_fwd: only dim=16 (or 1: pre-projected scalar), codebook_size=2 is built (got %d, %d)", dim, codebook_size);
     IDEE_REQUIRE(workspace_bytes >= idee_lfq_workspace_bytes(ntok), "lfq_fwd: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     const int nb = lfq_blocks(ntok);
-    lfq_fwd_kernel<<<nb, LFQ_THREADS, 0, st>>>(z, w_in, b_in, w_out, b_out, zq, (long long*)indices, xq, (double*)workspace, ntok,
-                                                training, inv_temperature);
+    if (dim == 1) lfq_fwd_kernel<true><<<nb, LFQ_THREADS, 0, st>>>(z, w_in, b_in, w_out, b_out, zq, (long long*)indices, xq, (double*)workspace,
+                                                                  ntok, training, inv_temperature);
+    else lfq_fwd_kernel<false><<<nb, LFQ_THREADS, 0, st>>>(z, w_in, b_in, w_out, b_out, zq, (long long*)indices, xq, (double*)workspace, ntok,
+                                                            training, inv_temperature);
     IDEE_LAUNCH_CHECK("lfq_fwd");
     if (training) {
         lfq_finalize_kernel<<<1, 32, 0, st>>>((const double*)workspace, nb, ntok, lambda_commit, lambda_entropy, diversity_gamma, stats);
@@ -201,8 +217,10 @@ extern "C" int idee_lfq_bwd(const float* z, const float* gzq, const float* gxq, 
     IDEE_REQUIRE(workspace_bytes >= idee_lfq_workspace_bytes(ntok), "lfq_bwd: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     const int nb = lfq_blocks(ntok);
-    lfq_bwd_kernel<<<nb, LFQ_THREADS, 0, st>>>(z, gzq, gxq, g_aux, stats, w_in, b_in, w_out, gz, (double*)workspace, ntok, lambda_commit,
-                                                lambda_entropy, diversity_gamma, inv_temperature);
+    if (w_in == nullptr) lfq_bwd_kernel<true><<<nb, LFQ_THREADS, 0, st>>>(z, gzq, gxq, g_aux, stats, w_in, b_in, w_out, gz, (double*)workspace, ntok,
+                                                                          lambda_commit, lambda_entropy, diversity_gamma, inv_temperature);
+    else lfq_bwd_kernel<false><<<nb, LFQ_THREADS, 0, st>>>(z, gzq, gxq, g_aux, stats, w_in, b_in, w_out, gz, (double*)workspace, ntok, lambda_commit,
+                                                            lambda_entropy, diversity_gamma, inv_temperature);
     IDEE_LAUNCH_CHECK("lfq_bwd");
     lfq_bwd_finalize_kernel<<<1, 64, 0, st>>>((const double*)workspace, nb, grads);
     IDEE_LAUNCH_CHECK("lfq_bwd_finalize");

@@ -66,9 +66,18 @@ class VQ_model(nn.Module):
             self.load_state_dict(state_dict, strict=True)
 
     def forward(self, x_d):
-        tok = self.encoder.forward_tokens(x_d)                         # [N,V,T,H,W,C] channel-last
-        N, V, T, H, W, C = tok.shape
-        z_q, anomaly, loss_z_q = self.vq(tok.view(N, V * T * H * W, C))  # token order (v,t,h,w) as build.py:150
+        from .. import _lib
+        if _lib.PRECISION == "bf16" and getattr(self.encoder, "forward_tokens", None) is not None and self.vq.dim == 16:
+            # the quantiser's project_in (Linear 16 -> 1) is the only consumer of the encoder output: fold it into the encoder's
+            # last 3x3x3 conv (one 16 -> 1 conv instead of 16 -> 16 followed by a dot product; forward, data and weight gradient)
+            s = self.encoder.forward_tokens(x_d, fold_last=(self.vq.project_in.weight, self.vq.project_in.bias))   # [N,V,T,H,W]
+            N, V, T, H, W = s.shape
+            C = self.vq.dim
+            z_q, anomaly, loss_z_q = self.vq.forward_projected(s.reshape(N, V * T * H * W))
+        else:
+            tok = self.encoder.forward_tokens(x_d)                         # [N,V,T,H,W,C] channel-last
+            N, V, T, H, W, C = tok.shape
+            z_q, anomaly, loss_z_q = self.vq(tok.view(N, V * T * H * W, C))  # token order (v,t,h,w) as build.py:150
         z_q = z_q.view(N, V, T, H, W, C).permute(0, 1, 5, 2, 3, 4)      # logical [N,V,C,T,H,W]
         anomaly = anomaly.view(N, V, T, H, W)
         # the joint head consumes the rank-1 form of z_q (x * w_out + b_out): identical result, 1/6 of the conv1 work

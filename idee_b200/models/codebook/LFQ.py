@@ -74,6 +74,19 @@ class LFQ(nn.Module):
             codes = codes.movedim(-1, 1)
         return codes
 
+    def forward_projected(self, s, inv_temperature=100.):
+        """s [...] = project_in(z) already evaluated by the producer (VQ_model folds project_in into the encoder's last conv)
+        -> Return(quantized [..., dim], indices int64 [...], aux loss).  Same arithmetic as ``forward`` from s onwards."""
+        zq, idx, aux, xq = ops.LFQScalarFn.apply(s, self.project_out.weight, self.project_out.bias, self.training,
+                                                 float(inv_temperature), float(self.commitment_loss_weight),
+                                                 float(self.entropy_loss_weight), float(self.diversity_gamma), self.codebook_size)
+        self.last_scalar = xq
+        if not self.training:
+            aux = self.zero
+        if self.keep_num_codebooks_dim:
+            idx = idx.unsqueeze(-1)
+        return Return(zq, idx, aux)
+
     def forward(self, x, inv_temperature=100., return_loss_breakdown=False, mask=None):
         """x [b, n, d] (or image/video [b, d, ...]) -> Return(quantized, indices int64, aux loss)."""
         if mask is not None:

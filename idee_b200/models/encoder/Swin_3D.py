@@ -243,8 +243,13 @@ class Swin_3D(nn.Module):
         return [pk["embed_w"], pk["embed_b"]] + [p for _, _, p in pk["blocks"]] + \
             [pk["proj0_w"], pk["proj0_b"], pk["proj2_w"], pk["proj2_b"]]
 
-    def forward_tokens(self, x: torch.Tensor) -> torch.Tensor:
-        """x [N,V,C,D,H,W] -> channel-last encoder output [N,V,D,H,W,E] (contiguous)."""
+    def forward_tokens(self, x: torch.Tensor, fold_last=None) -> torch.Tensor:
+        """x [N,V,C,D,H,W] -> channel-last encoder output [N,V,D,H,W,E] (contiguous).
+
+        fold_last = (w_in [1,E], b_in [1]) (bf16 mode only): the caller applies Linear(E -> 1) to the encoder output and nothing
+        else reads it (VQ_model: LFQ.project_in), so the last proj conv and that Linear are evaluated as ONE 16 -> 1 conv with
+        weights sum_o w_in[o] W2[o, c, tap] and bias w_in . b2 + b_in; returns s [N,V,D,H,W].  The folded weights are built with
+        differentiable torch ops, so gradients reach proj_var[2].weight / bias and w_in / b_in through autograd."""
         if x.dim() == 5 and self.in_chans == 1:
             x = x.unsqueeze(2)
         if self._packs is None:
@@ -271,6 +276,12 @@ class Swin_3D(nn.Module):
         # conv -> ReLU -> conv: the second conv is the only consumer of the ReLU output, so its data-gradient epilogue applies
         # the ReLU backward mask and the first conv skips the separate pass
         tok = ops.conv3d_cl(tok, w0, b0, proj=True, relu=True, consumer_masks=True, x16=tok16, out_bf16=bf16_io)
+        if fold_last is not None and bf16_io:
+            w_in, b_in = fold_last
+            wf = torch.einsum('vocthw,o->vcthw', w2, w_in.reshape(-1)).unsqueeze(1)          # [V,1,E,3,3,3]
+            bf = (b2 @ w_in.reshape(-1) + b_in.reshape(())).unsqueeze(1)                        # [V,1]
+            s = ops.conv3d_cl(tok, wf, bf, proj=True, relu=False, input_is_relu=True)           # [N,V,D,H,W,1]
+            return s.squeeze(-1)
         tok = ops.conv3d_cl(tok, w2, b2, proj=True, relu=False, input_is_relu=True)
         return tok
 

@@ -398,6 +398,56 @@ class LFQFn(torch.autograd.Function):
                 None, None, None, None, None, None)
 
 
+class LFQScalarFn(torch.autograd.Function):
+    """Pre-projected form of LFQFn: s [...] = project_in(z) already computed by the producer (the encoder's last conv folded
+    with project_in into one 16 -> 1 conv) -> (z_q [..., 16], indices int64 [...], aux scalar, xq [...]).  The backward pass
+    returns the gradient w.r.t. s only; project_in's gradients flow through the producer's folded weights."""
+
+    @staticmethod
+    def forward(ctx, s, w_out, b_out, training, inv_temp, lam_commit, lam_ent, gamma, codebook_size):
+        L.require_cuda(s)
+        lib = L.load()
+        s = _f32c(s)
+        w_out, b_out = _f32c(w_out), _f32c(b_out)
+        ntok = s.numel()
+        zq = torch.empty(*s.shape, 16, device=s.device, dtype=torch.float32)
+        idx = torch.empty(s.shape, device=s.device, dtype=torch.int64)
+        xq = torch.empty(s.shape, device=s.device, dtype=torch.float32)
+        stats = torch.zeros(8, device=s.device, dtype=torch.float32)
+        nws = lib.idee_lfq_workspace_bytes(ntok)
+        ws = L.workspace(nws, s.device)
+        L.run("lfq_fwd" if training else "lfq_fwd_eval", lib.idee_lfq_fwd, s.data_ptr(), None, None, w_out.data_ptr(), b_out.data_ptr(),
+              zq.data_ptr(), idx.data_ptr(), xq.data_ptr(), stats.data_ptr(), ntok, 1, codebook_size, int(training), inv_temp,
+              lam_commit, lam_ent, gamma, ws.data_ptr(), nws, L.stream())
+        ctx.save_for_backward(s, w_out, stats)
+        ctx.hyper = (inv_temp, lam_commit, lam_ent, gamma)
+        ctx.training = training
+        ctx.mark_non_differentiable(idx)
+        ctx.set_materialize_grads(False)
+        return zq, idx, stats[0], xq
+
+    @staticmethod
+    def backward(ctx, gzq, _gidx, gaux, gxq):
+        lib = L.load()
+        s, w_out, stats = ctx.saved_tensors
+        inv_temp, lam_commit, lam_ent, gamma = ctx.hyper
+        ntok = s.numel()
+        gzq = torch.zeros(*s.shape, 16, device=s.device, dtype=torch.float32) if gzq is None else _f32c(gzq)
+        if not ctx.training:
+            gaux, gxq = None, None
+        gaux_t = None if gaux is None else _f32c(gaux).reshape(1)
+        gxq_t = None if gxq is None else _f32c(gxq)
+        gs = torch.empty_like(s)
+        grads = torch.empty(49, device=s.device, dtype=torch.float32)
+        nws = lib.idee_lfq_workspace_bytes(ntok)
+        ws = L.workspace(nws, s.device)
+        L.run("lfq_bwd", lib.idee_lfq_bwd, s.data_ptr(), gzq.data_ptr(), L.ptr(gxq_t), L.ptr(gaux_t), stats.data_ptr(), None, None,
+              w_out.data_ptr(), gs.data_ptr(), grads.data_ptr(), ntok, inv_temp, lam_commit, lam_ent, gamma, ws.data_ptr(), nws, L.stream())
+        if not ctx.training:
+            gs = torch.zeros_like(s)
+        return gs, grads[17:33].view(16, 1), grads[33:49], None, None, None, None, None, None
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # losses
 # ----------------------------------------------------------------------------------------------------------------

@@ -114,7 +114,9 @@ int idee_conv3d_wgrad(const idee_conv_desc* d, const void* x, const void* gy, fl
 /* ---- LFQ quantiser, dim=16, codebook_size=2                                      models/codebook/LFQ.py:183-307 ----
  * z,zq,gz,gzq: [ntok][16]; indices: int64 [ntok]; xq (optional, may be NULL): float [ntok], the quantised scalar x (+-1) with
  * z_q = x * w_out + b_out, gxq (optional): gradient w.r.t. x from consumers that use the rank-1 form of z_q; stats: float[8] = {aux, per_sample_entropy, codebook_entropy,
- * commit, mean p0, mean p1, ntok, 0} (written only when training); grads: float[49] = g_w_in[16] | g_b_in | g_w_out[16] | g_b_out[16] */
+ * commit, mean p0, mean p1, ntok, 0} (written only when training); grads: float[49] = g_w_in[16] | g_b_in | g_w_out[16] | g_b_out[16]
+ * Pre-projected form: dim == 1 (forward) / w_in == NULL (backward): z is the scalar s = project_in(z) itself ([ntok]), computed by
+ * the producer (the encoder's last conv folded with project_in into one 16 -> 1 conv); gz is then [ntok] and g_w_in / g_b_in are 0. */
 size_t idee_lfq_workspace_bytes(int64_t ntok);
 int idee_lfq_fwd(const float* z, const float* w_in, const float* b_in, const float* w_out, const float* b_out,
                  float* zq, int64_t* indices, float* xq, float* stats, int64_t ntok, int dim, int codebook_size, int training,
