@@ -726,6 +726,137 @@ struct WP {
     FastDiv fd_to, fd_tw, fd_th, fd_ipn;
 };
 
+// im2col row of the scalar gradient plane for pixel q = (qt, qh, qw) (tile-local (pr, pc)):  G[tap] = sum of gs[p] over the pixels p
+// with clamp(p + tap - 1) == q, read from the zero-filled halo gh[3][HH][HW_] around the tile; 27 taps + 5 zeros as 32 bf16.
+__device__ __forceinline__ void gcol_row(const float* gh, __nv_bfloat16* row_out, int qt, int qh, int qw, int pr, int pc, int T, int H, int W,
+                                         bool in_img) {
+    // extra (clamped) source per axis: the low border feeds tap 0 from p = q, the high border feeds tap 2 from p = q
+    const bool xt0 = qt == 0, xt2 = qt == T - 1, xh0 = qh == 0, xh2 = qh == H - 1, xw0 = qw == 0, xw2 = qw == W - 1;
+    uint32_t packed[16];
+    float prev = 0.f;
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+        const int kt = k / 9, kh = (k / 3) % 3, kw = k % 3;
+        // exact pair p = q + 1 - k  ->  halo index (2 - kt, pr + 2 - kh, pc + 2 - kw)
+        float v = gh[((2 - kt) * HH + pr + 2 - kh) * HW_ + pc + 2 - kw];
+        const bool et = (kt == 0 && xt0) || (kt == 2 && xt2), eh = (kh == 0 && xh0) || (kh == 2 && xh2),
+                   ew = (kw == 0 && xw0) || (kw == 2 && xw2);
+        if (et || eh || ew) {                      // border: add the clamped combinations (center index 1 / pr+1 / pc+1)
+            const int at[2] = {2 - kt, 1}, ah[2] = {pr + 2 - kh, pr + 1}, aw[2] = {pc + 2 - kw, pc + 1};
+            v = 0.f;
+            for (int i = 0; i <= (et ? 1 : 0); ++i)
+                for (int j = 0; j <= (eh ? 1 : 0); ++j)
+                    for (int l = 0; l <= (ew ? 1 : 0); ++l) v += gh[(at[i] * HH + ah[j]) * HW_ + aw[l]];
+        }
+        if (!in_img) v = 0.f;
+        if (k & 1) packed[k >> 1] = pack_bf16(prev, v); else prev = v;
+    }
+    packed[13] = pack_bf16(prev, 0.f); packed[14] = 0u; packed[15] = 0u;
+    uint4* row = reinterpret_cast<uint4*>(row_out);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) row[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+}
+
+// Data gradient of the 16 -> 1 proj conv on tensor cores: gx[q][c] = sum_tap G[q][tap] * W[c][tap] with the same im2col rows
+// (M = 128 tile pixels, K = 32 taps, N = 16 channels; the weights live in registers as B fragments), fused ReLU mask, bf16 or
+// fp32 output.  grid = (CTAs per variable, V); each CTA walks a contiguous range of the variable's tiles.
+template <bool OUT16, bool RS16>
+__global__ void __launch_bounds__(128)
+proj_dgrad_scalar_tc_kernel(const float* __restrict__ gs, const float* __restrict__ w, const void* __restrict__ relu_src_,
+                            void* __restrict__ gx_, int V, int Vw, int T, int H, int W, int64_t gs_sn, int64_t gs_sv, int gs_st, int gs_sh,
+                            int gs_sw, int tiles_h, int tiles_w, uint32_t tiles_per_v, FastDiv fd_tw, FastDiv fd_th, FastDiv fd_t) {
+    constexpr int CPG = 40, NHALO = 3 * HH * HW_;
+    __shared__ __align__(16) float gsh[2][NHALO];
+    __shared__ __align__(16) __nv_bfloat16 tileG[TH * TW * CPG];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, v = blockIdx.y;
+    const int pr = tid / TW, pc = tid % TW;
+    // B fragments: B[k = tap][n = c] = w[c][tap]   (k-step kk, n-tile nt)
+    const float* wv = w + (int64_t)(Vw == 1 ? 0 : v) * 16 * 27;
+    uint32_t bf[2][2][2];
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+            const int cch = nt * 8 + lane / 4, t0 = kk * 16 + 2 * (lane % 4);
+            auto wt = [&](int tap) { return tap < 27 ? __ldg(wv + cch * 27 + tap) : 0.f; };
+            bf[kk][nt][0] = pack_bf16(wt(t0), wt(t0 + 1));
+            bf[kk][nt][1] = pack_bf16(wt(t0 + 8), wt(t0 + 9));
+        }
+    const uint32_t per_cta = (tiles_per_v + gridDim.x - 1) / gridDim.x;
+    const uint32_t first = blockIdx.x * per_cta, last = min(tiles_per_v, first + per_cta);
+    struct Tile { int n, t, h0, w0; };
+    auto decode = [&](uint32_t tile) {
+        Tile c;
+        uint32_t q, r;
+        fd_tw.divmod(tile, q, r); c.w0 = (int)r * TW;
+        fd_th.divmod(q, q, r); c.h0 = (int)r * TH;
+        fd_t.divmod(q, q, r); c.t = (int)r; c.n = (int)q;
+        return c;
+    };
+    auto issue = [&](const Tile& c, int buf) {
+        const float* g_img = gs + c.n * gs_sn + v * gs_sv;
+        for (int e = tid; e < NHALO; e += 128) {
+            const int a = e / (HH * HW_), rem = e - a * (HH * HW_), b = rem / HW_, cc = rem - b * HW_;
+            const int pt = c.t - 1 + a, ph = c.h0 - 1 + b, pw = c.w0 - 1 + cc;
+            const bool ok = (unsigned)pt < (unsigned)T && (unsigned)ph < (unsigned)H && (unsigned)pw < (unsigned)W;
+            const float* src = ok ? g_img + (int64_t)(pt * gs_st + ph * gs_sh + pw * gs_sw) : gs;
+            cp_async4_u32(smem_u32(&gsh[buf][e]), src, ok ? 4 : 0);
+        }
+        cp_async_commit();
+    };
+    Tile nxt{};
+    if (first < last) { nxt = decode(first); issue(nxt, 0); }
+    const int a_pix = (lane & 7) + ((lane >> 3) & 1) * 8, a_koff = (lane >> 4) * 8;
+    int buf = 0;
+    for (uint32_t tile = first; tile < last; ++tile, buf ^= 1) {
+        const Tile c = nxt;
+        cp_async_wait<0>();
+        __syncthreads();
+        gcol_row(gsh[buf], tileG + tid * CPG, c.t, c.h0 + pr, c.w0 + pc, pr, pc, T, H, W, c.h0 + pr < H && c.w0 + pc < W);
+        __syncthreads();
+        if (tile + 1 < last) { nxt = decode(tile + 1); issue(nxt, buf ^ 1); }
+        const int64_t img_off = (((int64_t)c.n * V + v) * T + c.t) * (int64_t)H * W * 16;
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            const int ks = warp * 2 + m;                           // tile row of 16 pixels
+            float acc[2][4];
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+                uint32_t a[4];
+                ldsm_x4(a, tileG + (ks * TW + a_pix) * CPG + kk * 16 + a_koff);
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) mma_bf16(acc[nt], a, bf[kk][nt][0], bf[kk][nt][1]);
+            }
+            const int hq = c.h0 + ks;
+            if (hq >= H) continue;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int wq = c.w0 + lane / 4 + half * 8;
+                if (wq >= W) continue;
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                    const int64_t o = img_off + ((int64_t)hq * W + wq) * 16 + nt * 8 + (lane % 4) * 2;
+                    float v0 = acc[nt][half * 2], v1 = acc[nt][half * 2 + 1];
+                    if (relu_src_) {
+                        if (RS16) {
+                            const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const __nv_bfloat16*>(relu_src_) + o));
+                            if (!(__uint_as_float(u << 16) > 0.f)) v0 = 0.f;
+                            if (!(__uint_as_float(u & 0xFFFF0000u) > 0.f)) v1 = 0.f;
+                        } else {
+                            const float2 a2 = __ldg(reinterpret_cast<const float2*>(reinterpret_cast<const float*>(relu_src_) + o));
+                            if (!(a2.x > 0.f)) v0 = 0.f; if (!(a2.y > 0.f)) v1 = 0.f;
+                        }
+                    }
+                    if (OUT16) *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(gx_) + o) = __floats2bfloat162_rn(v0, v1);
+                    else *reinterpret_cast<float2*>(reinterpret_cast<float*>(gx_) + o) = make_float2(v0, v1);
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // Weight gradient of the 16 -> 1 proj conv as ONE small GEMM per tile:  dW[c][tap] = sum_q h[q][c] * G[q][tap], where
 // G[q][tap] = sum of gs[p] over the pixels p with clamp(p + tap - 1) == q is the im2col of the SCALAR gradient plane (27 values
@@ -797,35 +928,9 @@ proj_wgrad_scalar_kernel(WP p) {
         __syncthreads();                                   // tile data landed; previous tile's MMAs are done with tileG
         // ---- im2col row of this thread's pixel q = (t, h0 + pr, w0 + pc) ----
         {
-            const float* gh = gsh[buf];
-            const int qh = c.h0 + pr, qw = c.w0 + pc;
-            const bool in_img = qh < p.Ho && qw < p.Wo;
-            // extra (clamped) source per axis: low border feeds tap 0 from p = q, high border feeds tap 2 from p = q
-            const bool xt0 = c.t == 0, xt2 = c.t == p.To - 1, xh0 = qh == 0, xh2 = qh == p.Ho - 1, xw0 = qw == 0, xw2 = qw == p.Wo - 1;
-            uint32_t packed[16];
-            float prev = 0.f;
-#pragma unroll
-            for (int k = 0; k < 27; ++k) {
-                const int kt = k / 9, kh = (k / 3) % 3, kw = k % 3;
-                // exact pair p = q + 1 - k  ->  halo index (2 - kt, pr + 2 - kh, pc + 2 - kw)
-                float v = gh[((2 - kt) * HH + pr + 2 - kh) * HW_ + pc + 2 - kw];
-                const bool et = (kt == 0 && xt0) || (kt == 2 && xt2), eh = (kh == 0 && xh0) || (kh == 2 && xh2),
-                           ew = (kw == 0 && xw0) || (kw == 2 && xw2);
-                if (et || eh || ew) {                      // border: add the clamped combinations (center index 1 / pr+1 / pc+1)
-                    const int at[2] = {2 - kt, 1}, ah[2] = {pr + 2 - kh, pr + 1}, aw[2] = {pc + 2 - kw, pc + 1};
-                    v = 0.f;
-                    for (int i = 0; i <= (et ? 1 : 0); ++i)
-                        for (int j = 0; j <= (eh ? 1 : 0); ++j)
-                            for (int l = 0; l <= (ew ? 1 : 0); ++l) v += gh[(at[i] * HH + ah[j]) * HW_ + aw[l]];
-                }
-                if (!in_img) v = 0.f;
-                if (k & 1) packed[k >> 1] = pack_bf16(prev, v); else prev = v;
-            }
-            packed[13] = pack_bf16(prev, 0.f); packed[14] = 0u; packed[15] = 0u;
-            uint4* row = reinterpret_cast<uint4*>(tileG + tid * CPG);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) row[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
-            if (in_img) gsum += gh[(1 * HH + pr + 1) * HW_ + pc + 1];
+            const bool in_img = c.h0 + pr < p.Ho && c.w0 + pc < p.Wo;
+            gcol_row(gsh[buf], tileG + tid * 40, c.t, c.h0 + pr, c.w0 + pc, pr, pc, p.To, p.Ho, p.Wo, in_img);
+            if (in_img) gsum += gsh[buf][(1 * HH + pr + 1) * HW_ + pc + 1];
         }
         __syncthreads();
         if (tile + 1 < t_end) { nxt = decode(tile + 1); issue(nxt, buf ^ 1); }
@@ -1299,14 +1404,18 @@ int conv_tc_dgrad(const idee_conv_desc* d, const void* gy, const float* w, const
                      "conv3d_dgrad(proj 16->1): tensor too large for 32-bit offsets");
         const int64_t rows64 = (int64_t)d->N * d->Ti * d->Hi;
         IDEE_REQUIRE(rows64 < (1ll << 31), "conv3d_dgrad(proj 16->1): too many rows");
-        int nb = (int)rows64;
-        const int cap = (idee_num_sms() * 8 + d->V - 1) / d->V;
-        if (nb > cap) nb = cap;
-        const FastDiv fh = make_fastdiv(d->Hi), ft = make_fastdiv(d->Ti);
+        (void)rows64;
+        // same bf16 operands as the forward 16 -> 1 conv: im2col of the scalar plane x weights on the tensor cores
+        const int tiles_h = (d->Hi + TH - 1) / TH, tiles_w = (d->Wi + TW - 1) / TW;
+        const int64_t tpv = (int64_t)d->N * d->Ti * tiles_h * tiles_w;
+        IDEE_REQUIRE(tpv < (1ll << 31), "conv3d_dgrad(proj 16->1): too many tiles");
+        int nb = (idee_num_sms() * 8 + d->V - 1) / d->V;
+        if (nb > tpv) nb = (int)tpv;
         dim3 grid(nb, d->V);
 #define IDEE_SCALAR_DGRAD(O_, R_)                                                                                           \
-        proj_dgrad_scalar_kernel<O_, R_><<<grid, 256, 0, st>>>((const float*)gy, w, relu_src, gx, d->V, d->Vw, d->Ti, d->Hi, d->Wi, \
-                                                             d->y_sn, d->y_sv, (int)d->y_st, (int)d->y_sh, (int)d->y_sw, (int)rows64, fh, ft)
+        proj_dgrad_scalar_tc_kernel<O_, R_><<<grid, 128, 0, st>>>((const float*)gy, w, relu_src, gx, d->V, d->Vw, d->Ti, d->Hi, d->Wi, \
+            d->y_sn, d->y_sv, (int)d->y_st, (int)d->y_sh, (int)d->y_sw, tiles_h, tiles_w, (uint32_t)tpv, make_fastdiv(tiles_w),       \
+            make_fastdiv(tiles_h), make_fastdiv(d->Ti))
         if (d->gx_dtype && d->x_dtype) IDEE_SCALAR_DGRAD(true, true);
         else if (d->gx_dtype) IDEE_SCALAR_DGRAD(true, false);
         else if (d->x_dtype) IDEE_SCALAR_DGRAD(false, true);
