@@ -44,6 +44,19 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
+// 256-bit global accesses (sm_100: LDG/STG.256): one full 32-byte sector per thread and instruction; p must be 32-byte aligned
+__device__ __forceinline__ void st8u(void* p, const uint32_t (&r)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]),
+                 "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void st8f(float* p, const float* r) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]),
+                 "f"(r[5]), "f"(r[6]), "f"(r[7]) : "memory");
+}
+__device__ __forceinline__ void ldg8f(float* r, const float* p) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]),
+                 "=f"(r[5]), "=f"(r[6]), "=f"(r[7]) : "l"(p));
+}
 __device__ __forceinline__ void load16(float* r, const float* p) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -54,6 +67,24 @@ __device__ __forceinline__ void load16(float* r, const float* p) {
 __device__ __forceinline__ void store16(float* p, const float* r) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) st4(p + 4 * i, make_float4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]));
+}
+// Coalesced variant for a warp whose lanes hold 16 consecutive floats of 32 CONSECUTIVE rows (64 B each): the rows are staged
+// in the warp's 2 KB shared-memory region (XOR-swizzled 16-byte chunks, conflict free both ways) and written back as four
+// fully coalesced 512-byte stores instead of four stores that each touch 32 half-filled sectors.
+// gwarp: address of lane 0's row; nrows: rows of this warp that exist (rows >= nrows are not written).
+__device__ __forceinline__ void store16_warp(float* gwarp, const float* r, float* smw, int lane, int nrows) {
+    const int sw = (lane >> 1) & 3;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        *reinterpret_cast<float4*>(smw + lane * 16 + ((k ^ sw) << 2)) = make_float4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int row = j * 8 + (lane >> 2), part = lane & 3;
+        const float4 v = *reinterpret_cast<const float4*>(smw + row * 16 + ((part ^ ((row >> 1) & 3)) << 2));
+        if (row < nrows) st4(gwarp + (j * 32 + lane) * 4, v);
+    }
+    __syncwarp();
 }
 __device__ __forceinline__ void zero16(float* r) {
 #pragma unroll

@@ -225,14 +225,13 @@ conv16_umma_kernel(UP16 p) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
             }
-            if (OUT16) {
-                uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o);
-                dst[0] = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
-                dst[1] = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
+            if (OUT16) {                               // 16 bf16 = one 32-byte sector in a single 256-bit store
+                const uint32_t pk[8] = {pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]),
+                                        pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15])};
+                st8u(reinterpret_cast<__nv_bfloat16*>(p.out) + o, pk);
             } else {
-                float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                float* dst = reinterpret_cast<float*>(p.out) + o;
+                st8f(dst, v); st8f(dst + 8, v + 8);
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

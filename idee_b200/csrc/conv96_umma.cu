@@ -267,14 +267,14 @@ conv96_umma_kernel(UP p) {
             bool pix_ok;
             const int64_t o = out_offset(c, pix_ok);
             if (!pix_ok) return;
-            float4 a[12];
+            float a[48];
 #pragma unroll
-            for (int i = 0; i < 12; ++i) a[i] = ldg4(p.relu_src + o + 4 * i);
+            for (int i = 0; i < 6; ++i) ldg8f(a + 8 * i, p.relu_src + o + 8 * i);
             uint32_t b0 = 0u, b1 = 0u;
 #pragma unroll
-            for (int i = 0; i < 12; ++i) {
-                const uint32_t m = (a[i].x > 0.f ? 1u : 0u) | (a[i].y > 0.f ? 2u : 0u) | (a[i].z > 0.f ? 4u : 0u) | (a[i].w > 0.f ? 8u : 0u);
-                if (i < 8) b0 |= m << (4 * i); else b1 |= m << (4 * (i - 8));
+            for (int i = 0; i < 48; ++i) {
+                const uint32_t m = a[i] > 0.f ? 1u : 0u;
+                if (i < 32) b0 |= m << i; else b1 |= m << (i - 32);
             }
             bits[0] = b0; bits[1] = b1;
         };
@@ -288,15 +288,14 @@ conv96_umma_kernel(UP p) {
                 tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * CO + chalf * 48 + 16 * k, v);
                 if (pix_ok) {
 #pragma unroll
-                    for (int i = 0; i < 16; i += 4) {
-                        float4 ov = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                        { const float4 bb = ld4(bias_s + chalf * 48 + 16 * k + i); ov.x += bb.x; ov.y += bb.y; ov.z += bb.z; ov.w += bb.w; }
-                        if (p.relu) { ov.x = fmaxf(ov.x, 0.f); ov.y = fmaxf(ov.y, 0.f); ov.z = fmaxf(ov.z, 0.f); ov.w = fmaxf(ov.w, 0.f); }
+                    for (int i = 0; i < 16; ++i) {
                         const int ch = 16 * k + i;                               // channel inside this warp's 48
-                        const uint32_t m = (ch < 32 ? bits[0] >> ch : bits[1] >> (ch - 32)) & 15u;
-                        if (!(m & 1u)) ov.x = 0.f; if (!(m & 2u)) ov.y = 0.f; if (!(m & 4u)) ov.z = 0.f; if (!(m & 8u)) ov.w = 0.f;
-                        st4(orow + ch, ov);
+                        float ov = v[i] + bias_s[chalf * 48 + ch];
+                        if (p.relu) ov = fmaxf(ov, 0.f);
+                        if (!((ch < 32 ? bits[0] >> ch : bits[1] >> (ch - 32)) & 1u)) ov = 0.f;
+                        v[i] = ov;
                     }
+                    st8f(orow + 16 * k, v); st8f(orow + 16 * k + 8, v + 8);
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

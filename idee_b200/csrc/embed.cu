@@ -41,11 +41,21 @@ embed_ln_fwd_kernel(EmbP p, float* __restrict__ y) {
     const bool dense = x_dense(p);
     const float* ximg = p.x + n * p.xs_n + v * p.xs_v;
     float* yimg = y + ((int64_t)n * p.V + v) * thw * C;
-    for (uint32_t r = blockIdx.x * EMB_THREADS + threadIdx.x; r < thw; r += gridDim.x * EMB_THREADS) {
-        const int64_t xo = x_offset(p, r, dense);
+    __shared__ __align__(16) float y_stage[EMB_THREADS / 32][512];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // whole warps iterate together: the 32 consecutive token rows of a warp are written with coalesced 512-byte stores
+    for (uint32_t r0 = blockIdx.x * EMB_THREADS + warp * 32; r0 < thw; r0 += gridDim.x * EMB_THREADS) {
+        const uint32_t r = r0 + lane;
+        const bool live = r < thw;
         float xin[MAXCIN];
+        if (live) {
+            const int64_t xo = x_offset(p, r, dense);
 #pragma unroll
-        for (int ci = 0; ci < MAXCIN; ++ci) xin[ci] = ci < p.Cin ? __ldg(ximg + xo + ci * p.xs_c) : 0.f;
+            for (int ci = 0; ci < MAXCIN; ++ci) xin[ci] = ci < p.Cin ? __ldg(ximg + xo + ci * p.xs_c) : 0.f;
+        } else {
+#pragma unroll
+            for (int ci = 0; ci < MAXCIN; ++ci) xin[ci] = 0.f;
+        }
         float e[C], en[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) {
@@ -55,7 +65,7 @@ embed_ln_fwd_kernel(EmbP p, float* __restrict__ y) {
             e[c] = a;
         }
         ln16(e, en);
-        store16(yimg + (int64_t)r * C, en);
+        store16_warp(yimg + (int64_t)r0 * C, en, y_stage[warp], lane, (int)min(32u, thw - r0));
     }
 }
 

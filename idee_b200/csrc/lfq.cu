@@ -58,9 +58,15 @@ lfq_fwd_kernel(const float* __restrict__ z, const float* __restrict__ w_in, cons
     for (int c = 0; c < C; ++c) { wi[c] = ZS ? 0.f : __ldg(w_in + c); wo[c] = __ldg(w_out + c); bo[c] = __ldg(b_out + c); }
     const float bi = ZS ? 0.f : __ldg(b_in);
     double acc[4] = {0.0, 0.0, 0.0, 0.0};   // sum entropy, sum p0, sum p1, sum (s-q)^2
-    for (int64_t tok = (int64_t)blockIdx.x * LFQ_THREADS + threadIdx.x; tok < ntok; tok += (int64_t)gridDim.x * LFQ_THREADS) {
-        float s;
-        if (ZS) s = __ldg(z + tok);
+    __shared__ __align__(16) float zq_stage[LFQ_THREADS / 32][512];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // whole warps stay in the loop together (the z_q rows of a warp are written cooperatively); lanes past the end are masked
+    for (int64_t tok0 = (int64_t)blockIdx.x * LFQ_THREADS + warp * 32; tok0 < ntok; tok0 += (int64_t)gridDim.x * LFQ_THREADS) {
+        const int64_t tok = tok0 + lane;
+        const bool live = tok < ntok;
+        float s = 0.f;
+        if (!live) {}
+        else if (ZS) s = __ldg(z + tok);
         else {
             float zr[C];
             load16(zr, z + tok * C);
@@ -70,13 +76,12 @@ lfq_fwd_kernel(const float* __restrict__ z, const float* __restrict__ w_in, cons
         }
         const float q = s > 0.f ? 1.f : -1.f;
         const float x = training ? s + (q - s) : q;
-        indices[tok] = x > 0.f ? 1 : 0;
-        if (xq) xq[tok] = x;
+        if (live) { indices[tok] = x > 0.f ? 1 : 0; if (xq) xq[tok] = x; }
         float r[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) r[c] = x * wo[c] + bo[c];
-        store16(zq + tok * C, r);
-        if (training) {
+        store16_warp(zq + tok0 * C, r, zq_stage[warp], lane, (int)min((int64_t)32, ntok - tok0));
+        if (training && live) {
             float p0, p1;
             probs(s, inv_temp, p0, p1);
             acc[0] += (double)(ent_term(p0) + ent_term(p1));
