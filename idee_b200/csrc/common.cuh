@@ -64,6 +64,10 @@ __device__ __forceinline__ void load16(float* r, const float* p) {
         r[4 * i + 0] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
     }
 }
+// same with two 256-bit loads when the row is 32-byte aligned (a32 is uniform: derived from the base pointer)
+__device__ __forceinline__ void load16_a(float* r, const float* p, bool a32) {
+    if (a32) { ldg8f(r, p); ldg8f(r + 8, p + 8); } else load16(r, p);
+}
 __device__ __forceinline__ void store16(float* p, const float* r) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) st4(p + 4 * i, make_float4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]));

@@ -107,7 +107,7 @@ embed_ln_bwd_kernel(EmbP p, const float* __restrict__ gy, float* __restrict__ pa
             e[c] = a;
         }
         const float rstd = ln16(e, en);
-        load16(g, gy + (((int64_t)n * p.V + v) * thw + r) * C);
+        load16_a(g, gy + (((int64_t)n * p.V + v) * thw + r) * C, (reinterpret_cast<uintptr_t>(gy) & 31) == 0);
         ln16_bwd(g, en, rstd, ge);
 #pragma unroll
         for (int c = 0; c < C; ++c) {

@@ -123,6 +123,7 @@ lfq_bwd_kernel(const float* __restrict__ z, const float* __restrict__ gzq, const
     for (int c = 0; c < C; ++c) { wi[c] = ZS ? 0.f : __ldg(w_in + c); wo[c] = __ldg(w_out + c); }
     const float bi = ZS ? 0.f : __ldg(b_in);
     const float ga = g_aux ? __ldg(g_aux) : 0.f;
+    const bool gzq_a32 = (reinterpret_cast<uintptr_t>(gzq) & 31) == 0;
     const float invn = 1.f / (float)ntok;
     const float cb_diff = ent_grad(__ldg(stats + 5)) - ent_grad(__ldg(stats + 4));   // f(pbar1) - f(pbar0)
     float a_wi[C], a_wo[C], a_bo[C], a_bi = 0.f;
@@ -134,7 +135,7 @@ lfq_bwd_kernel(const float* __restrict__ z, const float* __restrict__ gzq, const
     int cnt = 0;
     for (int64_t tok = (int64_t)blockIdx.x * LFQ_THREADS + threadIdx.x; tok < ntok; tok += (int64_t)gridDim.x * LFQ_THREADS) {
         float zr[C], gr[C];
-        load16(gr, gzq + tok * C);
+        load16_a(gr, gzq + tok * C, gzq_a32);
         float s;
         if (ZS) s = __ldg(z + tok);
         else {
