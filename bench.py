@@ -149,6 +149,21 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------------
 # algorithmic work of the entry points (for the roofline of the dominant kernel)
 # ------------------------------------------------------------------------------------------------------------------
+# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the entry points captured with `ncu --set full` at
+# the benchmark shape; source: profiles/r01_ncu/prof_sw_raw.csv.gz (Swin backward = MLP half + attention half)
+NCU_TRAFFIC = {
+    "swin_block_bwd[w(2, 4, 4)": (1.9669 + 0.970349 + 1.96789 + 1.214569) * 1e9,
+    "swin_block_fwd[w(2, 4, 4)": (0.983186 + 1.913179) * 1e9,
+}
+
+
+def ncu_traffic(name):
+    for k, v in NCU_TRAFFIC.items():
+        if name.startswith(k):
+            return v
+    return None
+
+
 def op_flops(name, B, V, T, H, W):
     """Algorithmic FLOPs (2*MAC, no recompute / padding credit) of ONE call of an entry point; None if not FLOP-shaped."""
     tok = B * V * T * H * W
@@ -302,7 +317,9 @@ def main():
                 avg_ms = t / c
                 ach = fl / (avg_ms * 1e-3) / 1e12
                 roofline = {"kernel": k, "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                            "traffic": None, "avg_ms_per_launch": avg_ms, "flops_per_launch": fl, "share_of_step": t / tot,
+                            "traffic": ncu_traffic(k) if (B, HW) == (8, 200) else None,
+                            "traffic_source": "profiles/r01_ncu/prof_sw_raw.csv.gz (ncu --set full, same shape)" if ncu_traffic(k) and (B, HW) == (8, 200) else None,
+                            "avg_ms_per_launch": avg_ms, "flops_per_launch": fl, "share_of_step": t / tot,
                             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s (of fallback)",
                             "note": "algorithmic FLOPs (2*MAC, no recompute/padding credit) against the dense bf16 tensor-core peak"}
                 break
@@ -324,7 +341,8 @@ def main():
                 "model_tflops_per_gpu": whole_model_tf, "loss": loss_val,
                 "inference": {"value": n_gpus * B / (ms_infer / 1e3), "unit": UNIT, "ms_per_step": ms_infer,
                               "what": "eval forward (logits + driver masks), no_grad, device-resident inputs"},
-                "algorithmic_shortcuts": "joint classifier conv1 evaluated on the rank-1 form of z_q (exact; 1/6 of its MACs); "
+                "algorithmic_shortcuts": "exact algebraic rewrites, all parity-tested: joint classifier conv1 and the anomaly loss evaluated "
+                                         "on the rank-1 form of z_q; LFQ.project_in folded into the encoder's last conv (16->1); "
                                          "model_tflops_per_gpu still counts the reference's 571.98 GFLOP/sample",
                 "breakdown": breakdown}
         print(json.dumps(line), flush=True)

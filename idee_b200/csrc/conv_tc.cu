@@ -600,116 +600,6 @@ fold_pad_kernel(const float* __restrict__ gpad, void* __restrict__ gin_, const v
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Data gradient of the 16 -> 1 proj conv (the encoder's last conv folded with the quantiser's project_in): the incoming
-// gradient is ONE scalar per pixel, so gx[r][c] = sum over the (<= 27) pairs (p, tap) with clamp(p + tap - 1) == r of
-// W[c][tap] * gs[p] is a 27-point scalar stencil with 16 outputs -- 432 fp32 FMAs per pixel on the CUDA cores, no padded
-// domain and no fold pass (each axis contributes at most three (p, tap) pairs, also on the replicate border).
-// ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int axis_pairs(int r, int S, int (&pp)[4], int (&kk)[4]) {
-    int n = 0;
-#pragma unroll
-    for (int off = -1; off <= 1; ++off) {
-        const int q = r - off;                                   // p + off == r
-        if (q >= 0 && q < S) { pp[n] = q; kk[n] = off + 1; ++n; }
-    }
-    if (r == 0) { pp[n] = 0; kk[n] = 0; ++n; }                   // p + off == -1 clamps to 0
-    if (r == S - 1) { pp[n] = S - 1; kk[n] = 2; ++n; }           // p + off == S clamps to S - 1
-    return n;
-}
-
-template <bool OUT16, bool RS16>
-__global__ void __launch_bounds__(256)
-proj_dgrad_scalar_kernel(const float* __restrict__ gs, const float* __restrict__ w, const void* __restrict__ relu_src_,
-                         void* __restrict__ gx_, int V, int Vw, int T, int H, int W, int64_t gs_sn, int64_t gs_sv, int gs_st, int gs_sh,
-                         int gs_sw, int rows_per_v, FastDiv fd_h, FastDiv fd_t) {
-    __shared__ __align__(16) float Ws[27][16];                    // [tap][c] of this variable's weight set
-    const int v = blockIdx.y;
-    const float* wv = w + (int64_t)(Vw == 1 ? 0 : v) * 16 * 27;   // [1][16][27]
-    for (int e = threadIdx.x; e < 27 * 16; e += 256) Ws[e / 16][e % 16] = wv[(e % 16) * 27 + e / 16];
-    __syncthreads();
-    for (int row = blockIdx.x; row < rows_per_v; row += gridDim.x) {       // row = (n, t, h) of variable v
-        uint32_t q, r;
-        fd_h.divmod((uint32_t)row, q, r); const int h = (int)r;
-        fd_t.divmod(q, q, r); const int t = (int)r;
-        const int n = (int)q;
-        int pt[4], kt[4], ph[4], kh[4];
-        const int nt = axis_pairs(t, T, pt, kt), nh = axis_pairs(h, H, ph, kh);
-        const float* gimg = gs + n * gs_sn + v * gs_sv;
-        const int64_t orow = ((((int64_t)n * V + v) * T + t) * H + h) * (int64_t)W * 16;
-        for (int x = threadIdx.x; x < W; x += 256) {
-            int pw[4], kw[4];
-            const int nw = axis_pairs(x, W, pw, kw);
-            float acc[16];
-#pragma unroll
-            for (int c = 0; c < 16; ++c) acc[c] = 0.f;
-            if (t > 0 && t < T - 1 && h > 0 && h < H - 1 && x > 0 && x < W - 1) {
-                // interior pixel: exactly the 27 pairs (p = r + 1 - k, k); all loads are issued before the FMAs
-                float g[27];
-                const float* g0 = gimg + (t + 1) * gs_st + (h + 1) * gs_sh + (x + 1) * gs_sw;
-#pragma unroll
-                for (int k = 0; k < 27; ++k) g[k] = __ldg(g0 - (k / 9) * gs_st - ((k / 3) % 3) * gs_sh - (k % 3) * gs_sw);
-#pragma unroll
-                for (int k = 0; k < 27; ++k) {
-                    const float4* wr = reinterpret_cast<const float4*>(Ws[k]);
-#pragma unroll
-                    for (int c4 = 0; c4 < 4; ++c4) {
-                        const float4 ww = wr[c4];
-                        acc[4 * c4] += ww.x * g[k]; acc[4 * c4 + 1] += ww.y * g[k]; acc[4 * c4 + 2] += ww.z * g[k]; acc[4 * c4 + 3] += ww.w * g[k];
-                    }
-                }
-            } else
-            for (int a = 0; a < nt; ++a)
-                for (int b = 0; b < nh; ++b) {
-                    const float* grow = gimg + pt[a] * gs_st + ph[b] * gs_sh;
-                    const int tap0 = (kt[a] * 3 + kh[b]) * 3;
-                    for (int cidx = 0; cidx < nw; ++cidx) {
-                        const float g = __ldg(grow + pw[cidx] * gs_sw);
-                        const float4* wr = reinterpret_cast<const float4*>(Ws[tap0 + kw[cidx]]);
-#pragma unroll
-                        for (int c4 = 0; c4 < 4; ++c4) {
-                            const float4 ww = wr[c4];
-                            acc[4 * c4] += ww.x * g; acc[4 * c4 + 1] += ww.y * g; acc[4 * c4 + 2] += ww.z * g; acc[4 * c4 + 3] += ww.w * g;
-                        }
-                    }
-                }
-            const int64_t o = orow + (int64_t)x * 16;
-            if (relu_src_) {
-                if (RS16) {
-                    const uint4* rs = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(relu_src_) + o);
-#pragma unroll
-                    for (int hf = 0; hf < 2; ++hf) {
-                        const uint4 u = __ldg(rs + hf);
-                        const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            if (!(__uint_as_float(uu[k] << 16) > 0.f)) acc[8 * hf + 2 * k] = 0.f;
-                            if (!(__uint_as_float(uu[k] & 0xFFFF0000u) > 0.f)) acc[8 * hf + 2 * k + 1] = 0.f;
-                        }
-                    }
-                } else {
-                    const float* rs = reinterpret_cast<const float*>(relu_src_) + o;
-#pragma unroll
-                    for (int c4 = 0; c4 < 4; ++c4) {
-                        const float4 a4 = ldg4(rs + 4 * c4);
-                        if (!(a4.x > 0.f)) acc[4 * c4] = 0.f; if (!(a4.y > 0.f)) acc[4 * c4 + 1] = 0.f;
-                        if (!(a4.z > 0.f)) acc[4 * c4 + 2] = 0.f; if (!(a4.w > 0.f)) acc[4 * c4 + 3] = 0.f;
-                    }
-                }
-            }
-            if (OUT16) {
-                uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(gx_) + o);
-                dst[0] = make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]), pack_bf16(acc[6], acc[7]));
-                dst[1] = make_uint4(pack_bf16(acc[8], acc[9]), pack_bf16(acc[10], acc[11]), pack_bf16(acc[12], acc[13]), pack_bf16(acc[14], acc[15]));
-            } else {
-                float* dst = reinterpret_cast<float*>(gx_) + o;
-#pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) st4(dst + 4 * c4, make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]));
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------------------
 // weight gradient
 // ------------------------------------------------------------------------------------------------------------------
 struct WP {

@@ -230,3 +230,36 @@ def test_tcgen05_proj_conv_matches_mma_sync(shape):
     assert float((y0 != y1).float().mean()) < 1e-3                                # ... and only where the fp32 sums straddle a tie
     assert rel_l2(gx1, gx0) < 1e-6
     assert torch.equal(gw0, gw1) and torch.equal(gb0, gb1)                        # weight gradient kernel is shared
+
+
+def test_folded_last_conv_matches_conv_then_project_in():
+    """VQ_model's bf16 path evaluates proj_var[2] followed by LFQ.project_in as ONE 16 -> 1 conv (Swin_3D.forward_tokens(fold_last=...)):
+    the scalar it feeds to the quantiser must equal project_in(encoder output), and so must the gradients that reach the last
+    conv's weights, project_in and the encoder input."""
+    from idee_b200.config import default_config
+    from idee_b200.models.build import VQ_model
+    cfg = default_config()
+    torch.manual_seed(2)
+    model = VQ_model(cfg).cuda().train()
+    with torch.no_grad():                                  # spread the quantiser input around 0 so both signs occur
+        model.vq.project_in.bias.fill_(-0.35)
+    x = torch.randn(2, cfg.in_channels_dynamic, cfg.in_channels, 8, 24, 40, device="cuda")
+    w_in, b_in = model.vq.project_in.weight, model.vq.project_in.bias
+    gs = torch.randn(2, cfg.in_channels_dynamic, 8, 24, 40, device="cuda")
+
+    def grads():
+        ps = [model.encoder.proj_var[0][2].weight, w_in, b_in, model.encoder.layers_var[0][0].blocks[0].attn.qkv.weight]
+        out = [p.grad.clone() for p in ps]
+        model.zero_grad(set_to_none=True)
+        return out
+
+    s_fold = model.encoder.forward_tokens(x, fold_last=(w_in, b_in))
+    (s_fold * gs).sum().backward()
+    g_fold = grads()
+    z = model.encoder.forward_tokens(x)
+    s_ref = z @ w_in.reshape(-1) + b_in
+    (s_ref * gs).sum().backward()
+    g_ref = grads()
+    assert rel_l2(s_fold, s_ref) < 5e-3
+    for a, b in zip(g_fold, g_ref):
+        assert rel_l2(a, b) < TOL
