@@ -155,9 +155,9 @@ conv96_umma_kernel(UP p) {
     auto decode = [&](uint32_t tile) {
         Tile c;
         uint32_t r = tile;
-        c.w0 = (int)(r % (uint32_t)p.tiles_w) * TC; r /= (uint32_t)p.tiles_w;
-        c.h0 = (int)(r % (uint32_t)p.tiles_h) * TR; r /= (uint32_t)p.tiles_h;
-        c.t = (int)(r % (uint32_t)p.To); c.n = (int)(r / (uint32_t)p.To);
+        c.t = (int)(r % (uint32_t)p.To); r /= (uint32_t)p.To;      // t fastest: the forward kernel's tiles at t, t+1 are disjoint in
+        c.w0 = (int)(r % (uint32_t)p.tiles_w) * TC; r /= (uint32_t)p.tiles_w;   // input, the data gradient's share their slice
+        c.h0 = (int)(r % (uint32_t)p.tiles_h) * TR; c.n = (int)(r / (uint32_t)p.tiles_h);
         return c;
     };
 

@@ -354,12 +354,20 @@ conv_tc16_kernel(P p, int64_t total_tiles64, FastDiv fd_tw, FastDiv fd_th, FastD
         for (int hf = 0; hf < 2; ++hf) rel_out[m][hf] = (int)((warp * MT + m) * p.out_sh + (lane / 4 + hf * 8) * p.out_sw) + (lane % 4) * 2;
 
     struct Tile { int n, v, t, h0, w0; };
-    auto decode = [&](uint32_t tile) {                           // tw fastest, then th, t, v, n (multiply-high divisions)
+    // proj convs: t fastest, then tw, th, v, n (multiply-high divisions): consecutive tiles of a CTA share two of their three
+    // input time slices, so the re-reads hit L2 (with t slowest ncu showed every slice fetched from DRAM three times)
+    auto decode = [&](uint32_t tile) {
         Tile c;
         uint32_t q, r;
-        fd_tw.divmod(tile, q, r); c.w0 = (int)r * TW;
-        fd_th.divmod(q, q, r); c.h0 = (int)r * TH;
-        fd_to.divmod(q, q, r); c.t = (int)r;
+        if (MODE == PROJ_FWD || MODE == PROJ_DGRAD_PAD) {
+            fd_to.divmod(tile, q, r); c.t = (int)r;
+            fd_tw.divmod(q, q, r); c.w0 = (int)r * TW;
+            fd_th.divmod(q, q, r); c.h0 = (int)r * TH;
+        } else {                                   // strided classifier convs: no shared slices, keep the image-plane order
+            fd_tw.divmod(tile, q, r); c.w0 = (int)r * TW;
+            fd_th.divmod(q, q, r); c.h0 = (int)r * TH;
+            fd_to.divmod(q, q, r); c.t = (int)r;
+        }
         fd_v.divmod(q, q, r); c.v = (int)r; c.n = (int)q;
         return c;
     };
