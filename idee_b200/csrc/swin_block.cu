@@ -47,6 +47,7 @@ struct Geom {
     float scale;
     int thwc;     // T*H*W*C (elements of one (n, v) image; < 2^31)
     void* out16;  // forward, bf16 path: optional bf16 copy of the block output (for the proj conv that consumes it)
+    const float* emb_x; const float* emb_w; const float* emb_b;   // bf16 path: fused patch embedding (see idee_swin_desc)
 };
 
 __device__ __forceinline__ int region_id(int p, int S, int ws, int ss) {
@@ -637,6 +638,9 @@ int make_geom(Geom& g, const idee_swin_desc* d, const char* who) {
     IDEE_REQUIRE((int64_t)d->T * d->H * d->W * C < (1ll << 31), "%s: one (n, v) volume must hold fewer than 2^31 elements", who);
     g.thwc = d->T * d->H * d->W * C;
     g.out16 = nullptr;
+    IDEE_REQUIRE(d->embed_x == nullptr || (d->precision == 1 && d->embed_w && d->embed_b),
+                 "%s: the fused patch embedding needs precision 1 and embed_w / embed_b", who);
+    g.emb_x = d->embed_x; g.emb_w = d->embed_w; g.emb_b = d->embed_b;
     return 0;
 }
 
@@ -656,14 +660,17 @@ int launch_fwd(const idee_swin_desc* d, const Geom& g, const float* x, float* ou
     if (d->precision == 1) {
         if (G < 8) { idee_set_error("swin_block_fwd(bf16): windows with fewer than 8 tokens are only built for the fp32 path"); return 1; }
         // persistent grid of exactly one resident wave (a partial second wave would run at a fraction of the occupancy)
+        const bool emb = g.emb_x != nullptr;
         int per_sm = 1;
-        IDEE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, swin_fwd_tc_kernel<WD, WH, WW>, TCW * 32, 0), "swin_block_fwd(bf16)");
+        if (emb) IDEE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, swin_fwd_tc_kernel<WD, WH, WW, true>, TCW * 32, 0), "swin_block_fwd(bf16)");
+        else IDEE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, swin_fwd_tc_kernel<WD, WH, WW, false>, TCW * 32, 0), "swin_block_fwd(bf16)");
         if (per_sm < 1) per_sm = 1;
         int per_v = (g.n_wg + TCW - 1) / TCW;
         const int cap = idee_num_sms() * per_sm / d->V;
         if (per_v > cap) per_v = cap;
         if (per_v < 1) per_v = 1;
-        swin_fwd_tc_kernel<WD, WH, WW><<<dim3(per_v, d->V), TCW * 32, 0, st>>>(x, out, ymid, params, d->param_stride, rel_index, g);
+        if (emb) swin_fwd_tc_kernel<WD, WH, WW, true><<<dim3(per_v, d->V), TCW * 32, 0, st>>>(x, out, ymid, params, d->param_stride, rel_index, g);
+        else swin_fwd_tc_kernel<WD, WH, WW, false><<<dim3(per_v, d->V), TCW * 32, 0, st>>>(x, out, ymid, params, d->param_stride, rel_index, g);
         IDEE_LAUNCH_CHECK("swin_block_fwd(bf16)");
         return 0;
     }

@@ -151,6 +151,22 @@ __device__ __forceinline__ void ln_tile(const float (&x)[4][4], float (&xn)[4][4
         for (int q = 0; q < 4; ++q) xn[r][q] = (valid == nullptr || valid[r]) ? d[q] * rs : 0.f;
     }
 }
+// Block input tile: either the stored tokens, or (fused patch embedding, in_chans == 1) LayerNorm(w[c] * x + b[c]) evaluated from
+// the raw scalar input -- 4 bytes instead of 64 per token, and the embedded tokens never exist in HBM.
+__device__ __forceinline__ void load_x_tile(float (&t)[4][4], const float* x, const TokRows& tr, int c0, const Geom& g, int v) {
+    if (g.emb_x == nullptr) { load_tile(t, x, tr, c0); return; }
+    const float* w = g.emb_w + v * C;
+    const float* b = g.emb_b + v * C;
+    const float w0 = __ldg(w + c0), w1 = __ldg(w + c0 + 1), w2 = __ldg(w + c0 + 8), w3 = __ldg(w + c0 + 9);
+    const float b0 = __ldg(b + c0), b1 = __ldg(b + c0 + 1), b2 = __ldg(b + c0 + 8), b3 = __ldg(b + c0 + 9);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const float xin = tr.valid[r] ? __ldg(g.emb_x + (tr.off[r] >> 4)) : 0.f;     // raw index = token index (C == 16)
+        t[r][0] = w0 * xin + b0; t[r][1] = w1 * xin + b1; t[r][2] = w2 * xin + b2; t[r][3] = w3 * xin + b3;
+    }
+    float rs[4];
+    ln_tile(t, t, rs, tr.valid);
+}
 // g_x = rstd * (g - mean(g) - xn * mean(g * xn))
 __device__ __forceinline__ void ln_bwd_tile(const float (&g)[4][4], const float (&xn)[4][4], const float (&rstd)[4], float (&gx)[4][4]) {
 #pragma unroll
@@ -317,7 +333,7 @@ constexpr int TCW = 4;   // warps per CTA
 // fragment table (uint2[32] each): qkv^T 6 | proj^T 2 | fc1^T 8 | fc2^T (4 k-steps x 2 n-tiles) 8
 constexpr int FW_FRAGS = 24;
 
-template <int WD, int WH, int WW>
+template <int WD, int WH, int WW, bool EMB>
 __global__ void __launch_bounds__(TCW * 32)
 swin_fwd_tc_kernel(const float* __restrict__ x, float* __restrict__ out, float* __restrict__ ymid, const float* __restrict__ params,
                    int64_t pstride, const int* __restrict__ rel_index, Geom g) {
@@ -345,7 +361,7 @@ swin_fwd_tc_kernel(const float* __restrict__ x, float* __restrict__ out, float* 
         TokRows tr;
         map_rows<WD, WH, WW>(tr, g, v, wg, true, lane);
         float xt[4][4], y[4][4];
-        load_tile(xt, x, tr, c0);
+        if (EMB) load_x_tile(xt, x, tr, c0, g, v); else load_tile(xt, x, tr, c0);
         {
             float xn[4][4], rstd[4], q[4][4], k[4][4], vv[4][4], o[4][4];
             ln_tile(xt, xn, rstd, tr.valid);
@@ -588,7 +604,7 @@ swin_attn_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ g
         TokRows tr;
         map_rows<WD, WH, WW>(tr, g, v, wg_ok ? wg : 0, wg_ok, lane);
         float xt[4][4], xn[4][4], rstd[4], ga[4][4];
-        load_tile(xt, x, tr, c0);
+        load_x_tile(xt, x, tr, c0, g, v);
         load_tile(ga, gy, tr, c0);
         ln_tile(xt, xn, rstd, tr.valid);
         float q[4][4], k[4][4], vv[4][4];

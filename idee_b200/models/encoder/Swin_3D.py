@@ -258,7 +258,9 @@ class Swin_3D(nn.Module):
         assert V == self.in_vars and Cin == self.in_chans, "input must be [N, in_vars, in_chans, D, H, W]"
         pk = self._packs
         E = self.embed_dim[-1]
-        tok = ops.embed_ln(x, pk["embed_w"], pk["embed_b"])
+        # bf16 mode, in_chans == 1: the patch embedding (1x1x1 conv + LayerNorm) is evaluated inside the first block's kernels
+        fuse_embed = _lib.PRECISION == "bf16" and Cin == 1 and E == 16 and len(pk["blocks"]) > 1
+        tok = None if fuse_embed else ops.embed_ln(x, pk["embed_w"], pk["embed_b"])
         # bf16 mode: the tensor-core proj convs round their operands to bf16 when they load them, so the tensors only they
         # consume (the last block's output and the hidden ReLU activation, plus the hidden gradient in backward) are kept in
         # HBM as bf16 -- bit-identical results, half the traffic, and no conversion pass in the conv kernels.
@@ -267,7 +269,10 @@ class Swin_3D(nn.Module):
         for i, (l, b, pack) in enumerate(pk["blocks"]):
             blk = self.layers_var[0][l].blocks[b]
             ws, ss, idx, rows, scale, heads, hidden = blk.kernel_args(D, H, W)
-            if bf16_io and i == len(pk["blocks"]) - 1:
+            if fuse_embed and i == 0:
+                xin = x if (x.dtype == torch.float32 and x.is_contiguous()) else x.float().contiguous()
+                tok = ops.swin_block_embed(xin, pk["embed_w"], pk["embed_b"], pack, idx, ws, ss, rows, scale, heads, hidden)
+            elif bf16_io and i == len(pk["blocks"]) - 1:
                 tok, tok16 = ops.swin_block(tok, pack, idx, ws, ss, rows, scale, heads, hidden, want_bf16=True)
             else:
                 tok = ops.swin_block(tok, pack, idx, ws, ss, rows, scale, heads, hidden)

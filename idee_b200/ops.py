@@ -190,6 +190,66 @@ class SwinBlock(torch.autograd.Function):
         return (gx, None, None, None, None, None, None, None, None, None, *pack.split_grad(gflat))
 
 
+class SwinBlockEmbed(torch.autograd.Function):
+    """First Swin block with the patch embedding fused in (bf16 mode, in_chans == 1): raw input x [N,V,1,T,H,W] (contiguous) ->
+    block output tokens [N,V,T,H,W,16].  The kernels evaluate LayerNorm(w * x + b) on the fly wherever the block reads its input
+    (forward and the recompute of the attention backward), so the embedded tokens are never written to or read from HBM;
+    the token gradient of the block goes straight into the embedding's backward kernel.  Swin_3D.py:473-491 + 224-287."""
+
+    @staticmethod
+    def forward(ctx, x, wpack: ParamPack, bpack: ParamPack, pack: ParamPack, rel_index, window, shift, rpb_rows, scale, heads, hidden,
+                *params):
+        L.require_cuda(x)
+        lib = L.load()
+        assert x.dtype == torch.float32 and x.is_contiguous() and x.shape[2] == 1
+        N, V, _, T, H, W = x.shape
+        flat, w, b = pack.tensor(), wpack.tensor(), bpack.tensor()
+        if lib.idee_swin_block_packed_floats(rpb_rows) != pack.P:
+            raise RuntimeError("swin_block: packed parameter size mismatch")
+        out = torch.empty(N, V, T, H, W, 16, device=x.device, dtype=torch.float32)
+        d = _swin_desc(out, window, shift, rpb_rows, scale, pack, heads, hidden)
+        d.embed_x, d.embed_w, d.embed_b = x.data_ptr(), w.data_ptr(), b.data_ptr()
+        need_bwd = any(ctx.needs_input_grad)
+        ymid = torch.empty_like(out) if need_bwd else None
+        L.run("swin_block_fwd", lib.idee_swin_block_fwd, C.byref(d), None, out.data_ptr(), L.ptr(ymid), None, flat.data_ptr(),
+              rel_index.data_ptr(), L.stream(), tag=f"w{window} s{shift} +embed")
+        if need_bwd:
+            ctx.save_for_backward(x, ymid, rel_index)
+            ctx.packs, ctx.args = (pack, wpack, bpack), (window, shift, rpb_rows, scale, heads, hidden)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        lib = L.load()
+        x, ymid, rel_index = ctx.saved_tensors
+        pack, wpack, bpack = ctx.packs
+        window, shift, rpb_rows, scale, heads, hidden = ctx.args
+        N, V, _, T, H, W = x.shape
+        flat, w, b = pack.tensor(), wpack.tensor(), bpack.tensor()
+        d = _swin_desc(ymid, window, shift, rpb_rows, scale, pack, heads, hidden)
+        d.embed_x, d.embed_w, d.embed_b = x.data_ptr(), w.data_ptr(), b.data_ptr()
+        gout = _f32c(gout)
+        gtok = torch.empty_like(ymid)                      # gradient w.r.t. the (virtual) embedded tokens
+        gflat = pack.grad_out(flat)
+        nws = lib.idee_swin_block_bwd_workspace_bytes(C.byref(d))
+        ws = L.workspace(nws, x.device)
+        L.run("swin_block_bwd", lib.idee_swin_block_bwd, C.byref(d), None, ymid.data_ptr(), gout.data_ptr(), gtok.data_ptr(), flat.data_ptr(),
+              rel_index.data_ptr(), gflat.data_ptr(), ws.data_ptr(), nws, L.stream(), tag=f"w{window} s{shift} +embed")
+        gw, gb = wpack.grad_out(w), bpack.grad_out(b)
+        nws = lib.idee_embed_ln_bwd_workspace_bytes(V)
+        ws = L.workspace(nws, x.device)
+        xs = (C.c_int64 * 6)(*x.stride())
+        L.run("embed_ln_bwd", lib.idee_embed_ln_bwd, x.data_ptr(), C.cast(xs, C.c_void_p), w.data_ptr(), b.data_ptr(), gtok.data_ptr(),
+              gw.data_ptr(), gb.data_ptr(), N, V, 1, T, H, W, 16, ws.data_ptr(), nws, L.stream())
+        return (None, None, None, None, None, None, None, None, None, None, None,
+                *pack.split_grad(gflat), *wpack.split_grad(gw), *bpack.split_grad(gb))
+
+
+def swin_block_embed(x, wpack: ParamPack, bpack: ParamPack, pack: ParamPack, rel_index, window, shift, rpb_rows, scale, heads, hidden):
+    return SwinBlockEmbed.apply(x, wpack, bpack, pack, rel_index, tuple(window), tuple(shift), rpb_rows, float(scale), heads, hidden,
+                                *pack.params(), *wpack.params(), *bpack.params())
+
+
 def swin_block(x, pack: ParamPack, rel_index, window, shift, rpb_rows, scale, heads, hidden, want_bf16: bool = False):
     """-> out, or (out, out_bf16) when want_bf16 (bf16 mode; the copy feeds a bf16-storage conv, see Conv3dCL)."""
     return SwinBlock.apply(x, pack, rel_index, tuple(window), tuple(shift), rpb_rows, float(scale), heads, hidden,

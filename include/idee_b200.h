@@ -55,6 +55,12 @@ typedef struct {
     float scale;            /* qk scale, head_dim^-0.5 unless overridden */
     int64_t param_stride;   /* floats between consecutive variables' packed parameter blocks */
     int precision;          /* 0: fp32 CUDA-core exact path; 1: bf16 tensor-core operands, fp32 accumulate / softmax / LayerNorm */
+    /* Fused patch embedding (optional, precision 1, in_chans == 1): when embed_x != NULL the block's input tokens are
+     * LayerNorm(embed_w[v][c] * embed_x[n,v,t,h,w] + embed_b[v][c]) (PatchEmbed3D, Swin_3D.py:473-491) evaluated on the fly from
+     * the contiguous raw input embed_x [N,V,1,T,H,W]; the token tensor `x` of idee_swin_block_fwd/bwd is then not read (may be
+     * NULL) and never has to exist in HBM.  gx of idee_swin_block_bwd is still the gradient w.r.t. those tokens
+     * (feed it to idee_embed_ln_bwd). */
+    const float* embed_x; const float* embed_w; const float* embed_b;
 } idee_swin_desc;
 
 int idee_swin_block_packed_floats(int rpb_rows);
