@@ -90,31 +90,47 @@ embed_ln_bwd_kernel(EmbP p, const float* __restrict__ gy, float* __restrict__ pa
     const uint32_t thw = (uint32_t)(p.T * p.H * p.W);
     const bool dense = x_dense(p);
     const uint32_t per_img = (thw + EMB_THREADS - 1) / EMB_THREADS;            // chunks of EMB_THREADS tokens per image
-    for (uint32_t chunk = blockIdx.x; chunk < per_img * (uint32_t)p.N; chunk += gridDim.x) {
+    // software pipeline: the loads of the next chunk (4 B of x, 64 B of gy per thread) are in flight while this one is reduced
+    const bool gy_a32 = (reinterpret_cast<uintptr_t>(gy) & 31) == 0;
+    const uint32_t nchunk = per_img * (uint32_t)p.N;
+    auto fetch = [&](uint32_t chunk, float (&xin)[CIN], float (&g)[C]) -> bool {
         const uint32_t n = chunk / per_img, r = (chunk - n * per_img) * EMB_THREADS + threadIdx.x;
-        if (r >= thw) continue;
+        if (chunk >= nchunk || r >= thw) return false;
         const float* ximg = p.x + n * p.xs_n + v * p.xs_v;
         const int64_t xo = x_offset(p, r, dense);
-        float xin[CIN];
 #pragma unroll
         for (int ci = 0; ci < CIN; ++ci) xin[ci] = __ldg(ximg + xo + ci * p.xs_c);
-        float e[C], en[C], g[C], ge[C];
+        load16_a(g, gy + (((int64_t)n * p.V + v) * thw + r) * C, gy_a32);
+        return true;
+    };
+    float xin[CIN], g[C];
+    bool have = fetch(blockIdx.x, xin, g);
+    for (uint32_t chunk = blockIdx.x; chunk < nchunk; chunk += gridDim.x) {
+        float xin_n[CIN], g_n[C];
+        const bool have_n = fetch(chunk + gridDim.x, xin_n, g_n);
+        if (have) {
+            float e[C], en[C], ge[C];
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-            float a = br[c];
+            for (int c = 0; c < C; ++c) {
+                float a = br[c];
 #pragma unroll
-            for (int ci = 0; ci < CIN; ++ci) a += wr[c][ci] * xin[ci];
-            e[c] = a;
+                for (int ci = 0; ci < CIN; ++ci) a += wr[c][ci] * xin[ci];
+                e[c] = a;
+            }
+            const float rstd = ln16(e, en);
+            ln16_bwd(g, en, rstd, ge);
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+#pragma unroll
+                for (int ci = 0; ci < CIN; ++ci) acc[c * CIN + ci] += ge[c] * xin[ci];
+                acc[C * CIN + c] += ge[c];
+            }
         }
-        const float rstd = ln16(e, en);
-        load16_a(g, gy + (((int64_t)n * p.V + v) * thw + r) * C, (reinterpret_cast<uintptr_t>(gy) & 31) == 0);
-        ln16_bwd(g, en, rstd, ge);
+        have = have_n;
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
+        for (int ci = 0; ci < CIN; ++ci) xin[ci] = xin_n[ci];
 #pragma unroll
-            for (int ci = 0; ci < CIN; ++ci) acc[c * CIN + ci] += ge[c] * xin[ci];
-            acc[C * CIN + c] += ge[c];
-        }
+        for (int c = 0; c < C; ++c) g[c] = g_n[c];
     }
     __shared__ float red[EMB_THREADS / 32][NG];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -48,6 +48,7 @@ struct Geom {
     int thwc;     // T*H*W*C (elements of one (n, v) image; < 2^31)
     void* out16;  // forward, bf16 path: optional bf16 copy of the block output (for the proj conv that consumes it)
     const float* emb_x; const float* emb_w; const float* emb_b;   // bf16 path: fused patch embedding (see idee_swin_desc)
+    float* emb_gpart;                                             // backward: per-CTA partials [V][CTAs][32] of the embedding gradients
 };
 
 __device__ __forceinline__ int region_id(int p, int S, int ws, int ss) {
@@ -640,7 +641,9 @@ int make_geom(Geom& g, const idee_swin_desc* d, const char* who) {
     g.out16 = nullptr;
     IDEE_REQUIRE(d->embed_x == nullptr || (d->precision == 1 && d->embed_w && d->embed_b),
                  "%s: the fused patch embedding needs precision 1 and embed_w / embed_b", who);
-    g.emb_x = d->embed_x; g.emb_w = d->embed_w; g.emb_b = d->embed_b;
+    g.emb_x = d->embed_x; g.emb_w = d->embed_w; g.emb_b = d->embed_b; g.emb_gpart = nullptr;
+    IDEE_REQUIRE((d->embed_gw == nullptr) == (d->embed_gb == nullptr) && (d->embed_gw == nullptr || d->embed_x != nullptr),
+                 "%s: embed_gw / embed_gb come together and need the fused patch embedding", who);
     return 0;
 }
 
@@ -697,19 +700,32 @@ int launch_bwd(const idee_swin_desc* d, const Geom& g, const float* x, const flo
     constexpr int G = WD * WH * WW;
     const int per_v = bwd_ctas_per_var(d->V);
     const int APS = ATT_PART_W + NH * G * G;
-    const size_t need = sizeof(float) * (size_t)d->V * per_v * (APS + MLP_PART);
+    const size_t need = sizeof(float) * (size_t)d->V * per_v * (APS + MLP_PART + (d->embed_gw ? 32 : 0));
     IDEE_REQUIRE(ws_bytes >= need, "swin_block_bwd: workspace too small (%zu < %zu)", ws_bytes, need);
     float* part_attn = ws;
     float* part_mlp = ws + (size_t)d->V * per_v * APS;
+    float* part_emb = part_mlp + (size_t)d->V * per_v * MLP_PART;
     const int64_t thw = (int64_t)d->T * d->H * d->W;
     if (d->precision == 1) {
         if (G < 8) { idee_set_error("swin_block_bwd(bf16): windows with fewer than 8 tokens are only built for the fp32 path"); return 1; }
         swin_mlp_bwd_tc_kernel<<<dim3(per_v, d->V), TCW * 32, 0, st>>>(ymid, gout, gx, params, d->param_stride, g.tbl, part_mlp, d->N, d->V, thw);
         IDEE_LAUNCH_CHECK("swin_mlp_bwd(bf16)");
         const size_t dyn = sizeof(float) * TCW * NH * G * dbs(G);
-        IDEE_CUDA(cudaFuncSetAttribute(swin_attn_bwd_tc_kernel<WD, WH, WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn), "swin_attn_bwd(bf16)");
-        swin_attn_bwd_tc_kernel<WD, WH, WW><<<dim3(per_v, d->V), TCW * 32, dyn, st>>>(x, gx, gx, params, d->param_stride, rel_index, part_attn, g);
-        IDEE_LAUNCH_CHECK("swin_attn_bwd(bf16)");
+        if (g.emb_x) {
+            Geom ge = g;
+            ge.emb_gpart = d->embed_gw ? part_emb : nullptr;
+            IDEE_CUDA(cudaFuncSetAttribute(swin_attn_bwd_tc_kernel<WD, WH, WW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn), "swin_attn_bwd(bf16)");
+            swin_attn_bwd_tc_kernel<WD, WH, WW, true><<<dim3(per_v, d->V), TCW * 32, dyn, st>>>(x, gx, gx, params, d->param_stride, rel_index, part_attn, ge);
+            IDEE_LAUNCH_CHECK("swin_attn_bwd(bf16,embed)");
+            if (d->embed_gw) {
+                embed_grad_finalize_kernel<<<d->V, 32, 0, st>>>(part_emb, per_v, d->embed_gw, d->embed_gb);
+                IDEE_LAUNCH_CHECK("embed_grad_finalize");
+            }
+        } else {
+            IDEE_CUDA(cudaFuncSetAttribute(swin_attn_bwd_tc_kernel<WD, WH, WW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn), "swin_attn_bwd(bf16)");
+            swin_attn_bwd_tc_kernel<WD, WH, WW, false><<<dim3(per_v, d->V), TCW * 32, dyn, st>>>(x, gx, gx, params, d->param_stride, rel_index, part_attn, g);
+            IDEE_LAUNCH_CHECK("swin_attn_bwd(bf16)");
+        }
         swin_grad_finalize_kernel<G><<<d->V, 1024, 0, st>>>(part_attn, part_mlp, per_v, per_v, rel_index, gparams, d->param_stride, g.tbl);
         IDEE_LAUNCH_CHECK("swin_grad_finalize");
         return 0;
@@ -744,7 +760,7 @@ extern "C" int idee_swin_block_packed_floats(int rpb_rows) { return POff(rpb_row
 extern "C" size_t idee_swin_block_bwd_workspace_bytes(const idee_swin_desc* d) {
     const int Gt = d->wd * d->wh * d->ww;
     const int per_v = bwd_ctas_per_var(d->V);
-    return sizeof(float) * (size_t)d->V * per_v * (ATT_PART_W + NH * Gt * Gt + MLP_PART);
+    return sizeof(float) * (size_t)d->V * per_v * (ATT_PART_W + NH * Gt * Gt + MLP_PART + (d->embed_gw ? 32 : 0));
 }
 
 extern "C" int idee_swin_block_fwd(const idee_swin_desc* d, const float* x, float* out, float* ymid, void* out_bf16,

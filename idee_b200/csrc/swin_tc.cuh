@@ -557,7 +557,15 @@ constexpr int AB_FRAGS = 14;
 // row stride of the warp-private bias-gradient table: conflict-free 8-byte read-modify-write per half warp
 __host__ __device__ constexpr int dbs(int G) { return G == 8 ? 8 : G + 8; }
 
-template <int WD, int WH, int WW>
+// sums the per-CTA partials [V][nblocks][32] = (g_w[16] | g_b[16]) of the fused embedding backward
+__global__ void embed_grad_finalize_kernel(const float* __restrict__ part, int nblocks, float* __restrict__ gw, float* __restrict__ gb) {
+    const int v = blockIdx.x, k = threadIdx.x;
+    double a = 0.0;
+    for (int b = 0; b < nblocks; ++b) a += part[((int64_t)v * nblocks + b) * 32 + k];
+    if (k < 16) gw[v * 16 + k] = (float)a; else gb[v * 16 + k - 16] = (float)a;
+}
+
+template <int WD, int WH, int WW, bool EMB>
 __global__ void __launch_bounds__(TCW * 32, 3)
 swin_attn_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gx,
                         const float* __restrict__ params, int64_t pstride, const int* __restrict__ rel_index,
@@ -596,6 +604,8 @@ swin_attn_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ g
     for (int b = 0; b < 2; ++b) aWp[b][0] = aWp[b][1] = aWp[b][2] = aWp[b][3] = 0.f;
 #pragma unroll
     for (int a = 0; a < 4; ++a) { abp[a] = 0.f; abq[0][a] = abq[1][a] = abq[2][a] = 0.f; }
+    float aew[4] = {0.f, 0.f, 0.f, 0.f}, aeb[4] = {0.f, 0.f, 0.f, 0.f};     // fused embedding backward (EMB with emb_gpart)
+    const bool emb_bwd = EMB && g.emb_gpart != nullptr;
 
     const int n_iter = (g.n_wg + gridDim.x * TCW - 1) / (gridDim.x * TCW);
     for (int it = 0; it < n_iter; ++it) {
@@ -604,7 +614,7 @@ swin_attn_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ g
         TokRows tr;
         map_rows<WD, WH, WW>(tr, g, v, wg_ok ? wg : 0, wg_ok, lane);
         float xt[4][4], xn[4][4], rstd[4], ga[4][4];
-        load_x_tile(xt, x, tr, c0, g, v);
+        if (EMB) load_x_tile(xt, x, tr, c0, g, v); else load_tile(xt, x, tr, c0);
         load_tile(ga, gy, tr, c0);
         ln_tile(xt, xn, rstd, tr.valid);
         float q[4][4], k[4][4], vv[4][4];
@@ -710,7 +720,29 @@ swin_attn_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ g
         for (int r = 0; r < 4; ++r)
 #pragma unroll
             for (int qd = 0; qd < 4; ++qd) gxt[r][qd] += ga[r][qd];
-        store_tile(gx, gxt, tr, c0);
+        if (emb_bwd) {
+            // the block input IS the embedding output: run its backward here (LN backward, then d/dw = sum ge * x, d/db = sum ge)
+            // instead of writing the token gradient and reading it back in a separate kernel
+            const float* w = g.emb_w + v * C;
+            const float* b = g.emb_b + v * C;
+            const float wq[4] = {__ldg(w + c0), __ldg(w + c0 + 1), __ldg(w + c0 + 8), __ldg(w + c0 + 9)};
+            const float bq[4] = {__ldg(b + c0), __ldg(b + c0 + 1), __ldg(b + c0 + 8), __ldg(b + c0 + 9)};
+            float xin[4], e[4][4], en[4][4], rs[4], ge[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                xin[r] = tr.valid[r] ? __ldg(g.emb_x + (tr.off[r] >> 4)) : 0.f;
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) e[r][qd] = wq[qd] * xin[r] + bq[qd];
+            }
+            ln_tile(e, en, rs, nullptr);
+            ln_bwd_tile(gxt, en, rs, ge);
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (tr.valid[r]) {
+#pragma unroll
+                    for (int qd = 0; qd < 4; ++qd) { aew[qd] += ge[r][qd] * xin[r]; aeb[qd] += ge[r][qd]; }
+                }
+        } else store_tile(gx, gxt, tr, c0);
         // weight gradients (K = the 32 tokens of this warp)
         uint32_t xnT[4][2], oT[4][2];
 #pragma unroll
@@ -754,6 +786,23 @@ swin_attn_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ g
 #pragma unroll
         for (int w3 = 0; w3 < 3; ++w3) atomicAdd(&red[3 * C * C + 16 * w3 + col], abq[w3][qd]);
         atomicAdd(&red[3 * C * C + 3 * C + C * C + col], abp[qd]);
+    }
+    if (emb_bwd) {                                        // rows live in lanes with equal lane % 4: reduce over lane / 4, then over the warps
+        __shared__ float red_e[32];
+        if (tid < 32) red_e[tid] = 0.f;
+        __syncthreads();
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+            float sw_ = aew[qd], sb_ = aeb[qd];
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) { sw_ += __shfl_xor_sync(0xffffffffu, sw_, o); sb_ += __shfl_xor_sync(0xffffffffu, sb_, o); }
+            if (lane < 4) {
+                const int col = c0 + (qd & 1) + 8 * (qd >> 1);
+                atomicAdd(&red_e[col], sw_); atomicAdd(&red_e[16 + col], sb_);
+            }
+        }
+        __syncthreads();
+        if (tid < 32) g.emb_gpart[((int64_t)v * gridDim.x + blockIdx.x) * 32 + tid] = red_e[tid];
     }
     __syncthreads();
     float* part = partials + ((int64_t)v * gridDim.x + blockIdx.x) * PART;

@@ -229,18 +229,14 @@ class SwinBlockEmbed(torch.autograd.Function):
         d = _swin_desc(ymid, window, shift, rpb_rows, scale, pack, heads, hidden)
         d.embed_x, d.embed_w, d.embed_b = x.data_ptr(), w.data_ptr(), b.data_ptr()
         gout = _f32c(gout)
-        gtok = torch.empty_like(ymid)                      # gradient w.r.t. the (virtual) embedded tokens
+        gtok = torch.empty_like(ymid)                      # scratch between the MLP and attention halves of the backward
         gflat = pack.grad_out(flat)
+        gw, gb = wpack.grad_out(w), bpack.grad_out(b)
+        d.embed_gw, d.embed_gb = gw.data_ptr(), gb.data_ptr()  # the attention half also runs the embedding's backward
         nws = lib.idee_swin_block_bwd_workspace_bytes(C.byref(d))
         ws = L.workspace(nws, x.device)
         L.run("swin_block_bwd", lib.idee_swin_block_bwd, C.byref(d), None, ymid.data_ptr(), gout.data_ptr(), gtok.data_ptr(), flat.data_ptr(),
               rel_index.data_ptr(), gflat.data_ptr(), ws.data_ptr(), nws, L.stream(), tag=f"w{window} s{shift} +embed")
-        gw, gb = wpack.grad_out(w), bpack.grad_out(b)
-        nws = lib.idee_embed_ln_bwd_workspace_bytes(V)
-        ws = L.workspace(nws, x.device)
-        xs = (C.c_int64 * 6)(*x.stride())
-        L.run("embed_ln_bwd", lib.idee_embed_ln_bwd, x.data_ptr(), C.cast(xs, C.c_void_p), w.data_ptr(), b.data_ptr(), gtok.data_ptr(),
-              gw.data_ptr(), gb.data_ptr(), N, V, 1, T, H, W, 16, ws.data_ptr(), nws, L.stream())
         return (None, None, None, None, None, None, None, None, None, None, None,
                 *pack.split_grad(gflat), *wpack.split_grad(gw), *bpack.split_grad(gb))
 

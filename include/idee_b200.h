@@ -61,6 +61,10 @@ typedef struct {
      * NULL) and never has to exist in HBM.  gx of idee_swin_block_bwd is still the gradient w.r.t. those tokens
      * (feed it to idee_embed_ln_bwd). */
     const float* embed_x; const float* embed_w; const float* embed_b;
+    /* backward, optional: when embed_gw / embed_gb ([V][16] each) are given, the attention half also runs the embedding's
+     * backward (LayerNorm backward + weight / bias reduction) on the token gradient it holds in registers and writes the two
+     * gradients here; gx is then only used as the scratch between the two halves and its final content is unspecified. */
+    float* embed_gw; float* embed_gb;
 } idee_swin_desc;
 
 int idee_swin_block_packed_floats(int rpb_rows);
