@@ -39,6 +39,24 @@ void idee_set_error(const char* fmt, ...);
 
 int idee_num_sms();  // cached SM count of the current device
 
+// n / d and n % d for n < 2^31 by multiply-high with m = ceil(2^32 / d) (0xFFFFFFFF for d == 1) and one correction step each way
+struct FastDiv {
+    uint32_t d, m;
+    __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const {
+        uint32_t qq = __umulhi(n, m);
+        int rr = (int)(n - qq * d);
+        if (rr < 0) { --qq; rr += (int)d; }
+        if (rr >= (int)d) { ++qq; rr -= (int)d; }
+        q = qq; r = (uint32_t)rr;
+    }
+};
+inline FastDiv make_fastdiv(int d) {
+    FastDiv f;
+    f.d = (uint32_t)d;
+    f.m = d > 1 ? (uint32_t)(((1ull << 32) + (uint64_t)d - 1) / (uint64_t)d) : 0xFFFFFFFFu;
+    return f;
+}
+
 // ---- device helpers ----
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }

@@ -34,22 +34,6 @@ constexpr int TMEM_COLS = 32;
 constexpr int NBUF = IDEE_U16_NBUF;             // halo buffers / accumulators per CTA (1: overlap comes from co-resident CTAs)
 enum { U16_FWD = 0, U16_DGRAD_PAD = 1 };
 
-struct FastDiv {
-    uint32_t d, m;
-    __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const {
-        uint32_t qq = __umulhi(n, m);
-        int rr = (int)(n - qq * d);
-        if (rr < 0) { --qq; rr += (int)d; }
-        if (rr >= (int)d) { ++qq; rr -= (int)d; }
-        q = qq; r = (uint32_t)rr;
-    }
-};
-inline FastDiv make_fastdiv(int d) {
-    FastDiv f;
-    f.d = (uint32_t)d;
-    f.m = d > 1 ? (uint32_t)(((1ull << 32) + (uint64_t)d - 1) / (uint64_t)d) : 0xFFFFFFFFu;
-    return f;
-}
 
 struct UP16 {
     const __nv_bfloat16* in; void* out; const float* bias; const __nv_bfloat16* wB;   // wB: [wset][tap][512 B]

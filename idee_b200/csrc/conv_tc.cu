@@ -59,23 +59,6 @@ __device__ __forceinline__ void cp_async4_u32(uint32_t smem, const void* gmem, i
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
-// n / d and n % d for n < 2^31 by multiply-high with m = ceil(2^32 / d) (0xFFFFFFFF for d == 1) and one correction step
-struct FastDiv {
-    uint32_t d, m;
-    __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const {
-        uint32_t qq = __umulhi(n, m);
-        int rr = (int)(n - qq * d);
-        if (rr < 0) { --qq; rr += (int)d; }
-        if (rr >= (int)d) { ++qq; rr -= (int)d; }
-        q = qq; r = (uint32_t)rr;
-    }
-};
-inline FastDiv make_fastdiv(int d) {
-    FastDiv f;
-    f.d = (uint32_t)d;
-    f.m = d > 1 ? (uint32_t)(((1ull << 32) + (uint64_t)d - 1) / (uint64_t)d) : 0xFFFFFFFFu;
-    return f;
-}
 
 struct P {
     const float* in; float* out; const float* bias; const float* relu_src;

@@ -768,6 +768,7 @@ extern "C" int idee_swin_block_fwd(const idee_swin_desc* d, const float* x, floa
     Geom g;
     if (make_geom(g, d, "swin_block_fwd")) return 1;
     IDEE_REQUIRE(out_bf16 == nullptr || d->precision == 1, "swin_block_fwd: the bf16 output copy is only produced by the bf16 path");
+    IDEE_REQUIRE(out != nullptr || out_bf16 != nullptr, "swin_block_fwd: out may only be NULL when the bf16 copy is requested");
     g.out16 = out_bf16;
     cudaStream_t st = (cudaStream_t)stream;
     SWIN_DISPATCH(launch_fwd, d, g, x, out, ymid, params, rel_index, st)

@@ -273,7 +273,8 @@ class Swin_3D(nn.Module):
                 xin = x if (x.dtype == torch.float32 and x.is_contiguous()) else x.float().contiguous()
                 tok = ops.swin_block_embed(xin, pk["embed_w"], pk["embed_b"], pack, idx, ws, ss, rows, scale, heads, hidden)
             elif bf16_io and i == len(pk["blocks"]) - 1:
-                tok, tok16 = ops.swin_block(tok, pack, idx, ws, ss, rows, scale, heads, hidden, want_bf16=True)
+                # the proj conv reads only the bf16 copy: the fp32 tokens of the last block are never written
+                tok, tok16 = ops.swin_block(tok, pack, idx, ws, ss, rows, scale, heads, hidden, want_bf16="only")
             else:
                 tok = ops.swin_block(tok, pack, idx, ws, ss, rows, scale, heads, hidden)
         w0, b0 = ops.packed(pk["proj0_w"], (V, E, E, 3, 3, 3)), ops.packed(pk["proj0_b"], (V, E))

@@ -158,11 +158,14 @@ class SwinBlock(torch.autograd.Function):
         if lib.idee_swin_block_packed_floats(rpb_rows) != pack.P:
             raise RuntimeError("swin_block: packed parameter size mismatch")
         d = _swin_desc(x, window, shift, rpb_rows, scale, pack, heads, hidden)
+        # want_bf16 == "only": the caller reads nothing but the bf16 copy, so the fp32 result is not written (the returned fp32
+        # tensor only routes the gradient and is left uninitialised)
         out = torch.empty_like(x)
         need_bwd = any(ctx.needs_input_grad)
         ymid = torch.empty_like(x) if need_bwd else None
         out16 = torch.empty_like(x, dtype=torch.bfloat16) if want_bf16 else None
-        L.run("swin_block_fwd", lib.idee_swin_block_fwd, C.byref(d), x.data_ptr(), out.data_ptr(), L.ptr(ymid), L.ptr(out16),
+        L.run("swin_block_fwd", lib.idee_swin_block_fwd, C.byref(d), x.data_ptr(), None if want_bf16 == "only" else out.data_ptr(),
+              L.ptr(ymid), L.ptr(out16),
               flat.data_ptr(), rel_index.data_ptr(), L.stream(), tag=f"w{window} s{shift}")
         if need_bwd:
             ctx.save_for_backward(x, ymid, rel_index)
@@ -249,7 +252,7 @@ def swin_block_embed(x, wpack: ParamPack, bpack: ParamPack, pack: ParamPack, rel
 def swin_block(x, pack: ParamPack, rel_index, window, shift, rpb_rows, scale, heads, hidden, want_bf16: bool = False):
     """-> out, or (out, out_bf16) when want_bf16 (bf16 mode; the copy feeds a bf16-storage conv, see Conv3dCL)."""
     return SwinBlock.apply(x, pack, rel_index, tuple(window), tuple(shift), rpb_rows, float(scale), heads, hidden,
-                           bool(want_bf16), *pack.params())
+                           want_bf16 if want_bf16 == "only" else bool(want_bf16), *pack.params())
 
 
 # ----------------------------------------------------------------------------------------------------------------

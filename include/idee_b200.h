@@ -70,7 +70,8 @@ typedef struct {
 int idee_swin_block_packed_floats(int rpb_rows);
 /* ymid (optional, may be NULL): the mid-block residual x + attn(...) saved for the backward pass.
  * out_bf16 (optional, may be NULL; precision 1 only): a bf16 copy of `out` in the same layout, written by the same kernel for a
- * consumer that rounds its input to bf16 anyway (the proj_var conv, see idee_conv_desc.x_dtype) */
+ * consumer that rounds its input to bf16 anyway (the proj_var conv, see idee_conv_desc.x_dtype); `out` may then be NULL
+ * (the fp32 tensor is not written at all) */
 int idee_swin_block_fwd(const idee_swin_desc* d, const float* x, float* out, float* ymid, void* out_bf16, const float* params,
                         const int32_t* rel_index, void* stream);
 size_t idee_swin_block_bwd_workspace_bytes(const idee_swin_desc* d);
