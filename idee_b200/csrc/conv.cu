@@ -332,8 +332,8 @@ int check_desc(const idee_conv_desc* d, const char* who) {
     else IDEE_REQUIRE(d->To == (d->Ti - 2) / 2 + 1 && d->Ti >= 2 && d->Ho == d->Hi && d->Wo == d->Wi, "%s: cls conv output shape mismatch", who);
     IDEE_REQUIRE((unsigned)d->x_dtype <= 1u && (unsigned)d->y_dtype <= 1u && (unsigned)d->gx_dtype <= 1u, "%s: dtype fields must be 0 (float) or 1 (bf16)", who);
     if (d->x_dtype || d->y_dtype || d->gx_dtype)
-        IDEE_REQUIRE(d->precision >= 1 && d->proj && d->Cin == 16 && (d->Cout == 16 || d->Cout == 1) && d->in_cpg == 1 && d->out_cpg == 1,
-                     "%s: bf16 activation storage is only built for the precision >= 1 16 -> 16 / 16 -> 1 proj conv", who);
+        IDEE_REQUIRE(d->precision >= 1 && d->Cin == 16 && (d->Cout == 16 || (d->proj && d->Cout == 1)) && d->in_cpg == 1 && d->out_cpg == 1,
+                     "%s: bf16 activation storage is only built for the precision >= 1 16 -> 16 convs and the 16 -> 1 proj conv", who);
     return 0;
 }
 

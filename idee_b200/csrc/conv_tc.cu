@@ -532,7 +532,12 @@ conv_tc16_kernel(P p, int64_t total_tiles64, FastDiv fd_tw, FastDiv fd_th, FastD
                     const int o = rel_out[m][half] + nt * 8;
                     float v0 = acc[m][nt][half * 2] + bias0[nt], v1 = acc[m][nt][half * 2 + 1] + bias1[nt];
                     if (p.relu && MODE <= PROJ_FWD) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-                    if (OUT16) {                           // host guarantees an even channel count
+                    if (OUT16) {                           // host guarantees an even channel count; a ReLU mask has the output's dtype
+                        if (p.relu_src) {
+                            const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const __nv_bfloat16*>(p.relu_src) + tile_off + o));
+                            if (!(__uint_as_float(u << 16) > 0.f)) v0 = 0.f;
+                            if (!(__uint_as_float(u & 0xFFFF0000u) > 0.f)) v1 = 0.f;
+                        }
                         *reinterpret_cast<__nv_bfloat162*>(out_tile16 + o) = __floats2bfloat162_rn(v0, v1);
                     } else {
                         if (rs_tile) { if (!(rs_tile[o] > 0.f)) v0 = 0.f; if (co + 1 < p.CO && !(rs_tile[o + 1] > 0.f)) v1 = 0.f; }
@@ -1150,7 +1155,7 @@ int launch_tc16(const P& p, int n_img_t, cudaStream_t st, const char* who) {
     IDEE_REQUIRE(total < (1ll << 31) && (p.Ti + 3) * p.in_st + (p.Hi + HH) * p.in_sh + (p.Wi + HW_) * p.in_sw < (1ll << 31) &&
                  (p.To + 1) * p.out_st + (p.Ho + TH) * p.out_sh + (p.Wo + TW) * p.out_sw < (1ll << 31),
                  "%s: tensor too large for 32-bit image-relative offsets", who);
-    IDEE_REQUIRE(!OUT16 || (p.CO % 2 == 0 && p.relu_src == nullptr), "%s: bf16 output needs an even channel count and no mask", who);
+    IDEE_REQUIRE(!OUT16 || p.CO % 2 == 0, "%s: bf16 output needs an even channel count", who);
     int per_sm = 1;
     IDEE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C16_THREADS, smem), who);
     if (per_sm < 1) per_sm = 1;
@@ -1170,6 +1175,10 @@ int dispatch_tc(const P& p, const Plan& pl, int n_img_t, cudaStream_t st, const 
                 return launch_tc16<MODE, 1, true, false>(p, n_img_t, st, who);
         }
         if (pl.KS == 1 && p.CIr == 16 && pl.n_oc == 1 && pl.NTL == 2) {
+            if constexpr (MODE == CLS_FWD || MODE == CLS_DGRAD) {     // per-variable classifier heads: one side of the conv in bf16
+                if (p.in16 && !p.out16) return launch_tc16<MODE, 2, true, false>(p, n_img_t, st, who);
+                if (!p.in16 && p.out16) return launch_tc16<MODE, 2, false, true>(p, n_img_t, st, who);
+            }
             if constexpr (MODE == PROJ_FWD) {
                 if (p.in16 && p.out16) return launch_tc16<MODE, 2, true, true>(p, n_img_t, st, who);
                 if (p.in16) return launch_tc16<MODE, 2, true, false>(p, n_img_t, st, who);
@@ -1317,6 +1326,8 @@ int conv_tc_dgrad(const idee_conv_desc* d, const void* gy, const float* w, const
     p.CO = d->Cin; p.CIr = d->Cout; p.NTf = pl.NTf; p.relu = 0;
     if (!d->proj) {
         p.out = (float*)gx; p.relu_src = (const float*)relu_src;
+        p.out16 = d->gx_dtype;
+        IDEE_REQUIRE(relu_src == nullptr || d->x_dtype == d->gx_dtype, "conv3d_dgrad(cls,bf16): the ReLU mask must have gx's element type");
         p.To = d->Ti; p.Ho = d->Hi; p.Wo = d->Wi;
         p.out_sn = d->x_sn; p.out_sv = d->x_sv; p.out_st = d->x_st; p.out_sh = d->x_sh; p.out_sw = d->x_sw; p.out_sg = d->x_sg; p.out_cpg = d->in_cpg;
         p.tiles_w = (p.Wo + TW - 1) / TW;
@@ -1414,7 +1425,11 @@ int conv_tc_wgrad_partials(const idee_conv_desc* d, const void* x, const void* g
         else if (p.g16) IDEE_WGRAD_LAUNCH(27, 2, false, true);
         else IDEE_WGRAD_LAUNCH(27, 2, false, false);
     }
-    else if (p.a16 || p.g16) { idee_set_error("conv3d_wgrad(cls,bf16): bf16 activation storage is not built"); return 1; }
+    else if (p.a16 || p.g16) {
+        if (NC == 16 && p.a16 && !p.g16) IDEE_WGRAD_LAUNCH(18, 2, true, false);
+        else if (NC == 16 && !p.a16 && p.g16) IDEE_WGRAD_LAUNCH(18, 2, false, true);
+        else { idee_set_error("conv3d_wgrad(cls,bf16): this bf16 activation storage combination is not built"); return 1; }
+    }
     else if (NC == 32) IDEE_WGRAD_LAUNCH(18, 4, false, false);
     else if (NC == 16) IDEE_WGRAD_LAUNCH(18, 2, false, false);
     else IDEE_WGRAD_LAUNCH(18, 1, false, false);

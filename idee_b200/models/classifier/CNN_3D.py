@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from ... import ops
+from ... import _lib, ops
 
 
 def _conv():
@@ -48,7 +48,11 @@ def _head(tok, wb, drop, groups, first=None, fuse1=True):
     """conv1 -> ReLU -> Dropout -> conv2 -> ReLU -> conv3.  Each ReLU output has exactly one consumer, so the ReLU backward
     masks are applied in the consumers' data-gradient epilogues (fuse1 is False when an active Dropout sits in between)."""
     (w1, b1), (w2, b2), (w3, b3) = wb
-    h = first if first is not None else ops.conv3d_cl(tok, w1, b1, proj=False, relu=True, groups=groups, consumer_masks=fuse1)
+    # bf16 mode, 16 -> 16 heads: the first ReLU activation (and its gradient) is only ever read by tensor-core kernels that round
+    # it to bf16 as they load it, so it is stored as bf16 (bit-identical, see Conv3dCL)
+    y1_bf16 = first is None and groups == 1 and fuse1 and _lib.PRECISION == "bf16" and w1.shape[1] == 16 and w1.shape[2] == 16
+    h = first if first is not None else ops.conv3d_cl(tok, w1, b1, proj=False, relu=True, groups=groups, consumer_masks=fuse1,
+                                                      out_bf16=y1_bf16)
     h = drop(h)
     h = ops.conv3d_cl(h, w2, b2, proj=False, relu=True, input_is_relu=fuse1, consumer_masks=True)
     return ops.conv3d_cl(h, w3, b3, proj=False, relu=False, input_is_relu=True)
