@@ -172,6 +172,7 @@ class SwinBlock(torch.autograd.Function):
             ctx.pack, ctx.args = pack, (window, shift, rpb_rows, scale, heads, hidden)
         if want_bf16:
             ctx.mark_non_differentiable(out16)
+            ctx.set_materialize_grads(False)     # no 0.5 GB zero tensor for the non-differentiable bf16 copy in every backward
             return out, out16
         return out
 
@@ -179,6 +180,8 @@ class SwinBlock(torch.autograd.Function):
     def backward(ctx, gout, *_unused):
         lib = L.load()
         x, ymid, rel_index = ctx.saved_tensors
+        if gout is None:
+            gout = torch.zeros_like(x)
         pack = ctx.pack
         window, shift, rpb_rows, scale, heads, hidden = ctx.args
         flat = pack.tensor()
