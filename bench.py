@@ -149,19 +149,21 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------------
 # algorithmic work of the entry points (for the roofline of the dominant kernel)
 # ------------------------------------------------------------------------------------------------------------------
-# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the entry points captured with `ncu --set full` at
-# the benchmark shape; source: profiles/r01_ncu/prof_sw_raw.csv.gz (Swin backward = MLP half + attention half)
+# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the Swin entry points, captured with `ncu --set full`
+# inside this very command at the benchmark shape; source: profiles/r01_ncu/prof_final_v57_swin_raw.csv.gz
+# (backward = MLP half + attention half; "+embed" = first block with the patch embedding fused in)
 NCU_TRAFFIC = {
-    "swin_block_bwd[w(2, 4, 4)": (1.9669 + 0.970349 + 1.96789 + 1.214569) * 1e9,
-    "swin_block_fwd[w(2, 4, 4)": (0.983186 + 1.913179) * 1e9,
+    "swin_block_bwd[w(2, 4, 4) s(0, 0, 0) +embed]": (1.967 + 0.977 + 1.045 + 0.046) * 1e9,
+    "swin_block_bwd[w(2, 4, 4) s(1, 2, 2)]": (1.967 + 0.977 + 1.967 + 1.213) * 1e9,
+    "swin_block_bwd[w(8, 1, 1) s(0, 0, 0)]": (1.967 + 0.977 + 1.978 + 0.995) * 1e9,
+    "swin_block_fwd[w(2, 4, 4) s(0, 0, 0) +embed]": (0.065 + 1.907) * 1e9,
+    "swin_block_fwd[w(2, 4, 4) s(1, 2, 2)]": (0.984 + 1.911) * 1e9,
+    "swin_block_fwd[w(8, 1, 1) s(0, 0, 0)]": (0.983 + 1.426) * 1e9,
 }
 
 
 def ncu_traffic(name):
-    for k, v in NCU_TRAFFIC.items():
-        if name.startswith(k):
-            return v
-    return None
+    return NCU_TRAFFIC.get(name)
 
 
 def op_flops(name, B, V, T, H, W):
@@ -318,7 +320,7 @@ def main():
                 ach = fl / (avg_ms * 1e-3) / 1e12
                 roofline = {"kernel": k, "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                             "traffic": ncu_traffic(k) if (B, HW) == (8, 200) else None,
-                            "traffic_source": "profiles/r01_ncu/prof_sw_raw.csv.gz (ncu --set full, same shape)" if ncu_traffic(k) and (B, HW) == (8, 200) else None,
+                            "traffic_source": "profiles/r01_ncu/prof_final_v57_swin_raw.csv.gz (ncu --set full of this command)" if ncu_traffic(k) and (B, HW) == (8, 200) else None,
                             "avg_ms_per_launch": avg_ms, "flops_per_launch": fl, "share_of_step": t / tot,
                             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s (of fallback)",
                             "note": "algorithmic FLOPs (2*MAC, no recompute/padding credit) against the dense bf16 tensor-core peak"}
