@@ -614,6 +614,8 @@ struct WP {
 
 // im2col row of the scalar gradient plane for pixel q = (qt, qh, qw) (tile-local (pr, pc)):  G[tap] = sum of gs[p] over the pixels p
 // with clamp(p + tap - 1) == q, read from the zero-filled halo gh[3][HH][HW_] around the tile; 27 taps + 5 zeros as 32 bf16.
+// BORDER = false: the whole tile lies strictly inside the image (CTA-uniform), so every tap has exactly its one exact source.
+template <bool BORDER>
 __device__ __forceinline__ void gcol_row(const float* gh, __nv_bfloat16* row_out, int qt, int qh, int qw, int pr, int pc, int T, int H, int W,
                                          bool in_img) {
     // extra (clamped) source per axis: the low border feeds tap 0 from p = q, the high border feeds tap 2 from p = q
@@ -625,22 +627,30 @@ __device__ __forceinline__ void gcol_row(const float* gh, __nv_bfloat16* row_out
         const int kt = k / 9, kh = (k / 3) % 3, kw = k % 3;
         // exact pair p = q + 1 - k  ->  halo index (2 - kt, pr + 2 - kh, pc + 2 - kw)
         float v = gh[((2 - kt) * HH + pr + 2 - kh) * HW_ + pc + 2 - kw];
-        const bool et = (kt == 0 && xt0) || (kt == 2 && xt2), eh = (kh == 0 && xh0) || (kh == 2 && xh2),
-                   ew = (kw == 0 && xw0) || (kw == 2 && xw2);
-        if (et || eh || ew) {                      // border: add the clamped combinations (center index 1 / pr+1 / pc+1)
-            const int at[2] = {2 - kt, 1}, ah[2] = {pr + 2 - kh, pr + 1}, aw[2] = {pc + 2 - kw, pc + 1};
-            v = 0.f;
-            for (int i = 0; i <= (et ? 1 : 0); ++i)
-                for (int j = 0; j <= (eh ? 1 : 0); ++j)
-                    for (int l = 0; l <= (ew ? 1 : 0); ++l) v += gh[(at[i] * HH + ah[j]) * HW_ + aw[l]];
+        if (BORDER) {
+            const bool et = (kt == 0 && xt0) || (kt == 2 && xt2), eh = (kh == 0 && xh0) || (kh == 2 && xh2),
+                       ew = (kw == 0 && xw0) || (kw == 2 && xw2);
+            if (et || eh || ew) {                  // border: add the clamped combinations (center index 1 / pr+1 / pc+1)
+                const int at[2] = {2 - kt, 1}, ah[2] = {pr + 2 - kh, pr + 1}, aw[2] = {pc + 2 - kw, pc + 1};
+                v = 0.f;
+                for (int i = 0; i <= (et ? 1 : 0); ++i)
+                    for (int j = 0; j <= (eh ? 1 : 0); ++j)
+                        for (int l = 0; l <= (ew ? 1 : 0); ++l) v += gh[(at[i] * HH + ah[j]) * HW_ + aw[l]];
+            }
+            if (!in_img) v = 0.f;
         }
-        if (!in_img) v = 0.f;
         if (k & 1) packed[k >> 1] = pack_bf16(prev, v); else prev = v;
     }
     packed[13] = pack_bf16(prev, 0.f); packed[14] = 0u; packed[15] = 0u;
     uint4* row = reinterpret_cast<uint4*>(row_out);
 #pragma unroll
     for (int i = 0; i < 4; ++i) row[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+}
+// tile-uniform dispatch: tiles that touch no image border (and lie fully inside) take the branch-free builder
+__device__ __forceinline__ void gcol_row_tile(const float* gh, __nv_bfloat16* row_out, int t, int h0, int w0, int pr, int pc, int T, int H, int W) {
+    const bool inner = t > 0 && t < T - 1 && h0 > 0 && h0 + TH < H && w0 > 0 && w0 + TW < W;
+    if (inner) gcol_row<false>(gh, row_out, t, h0 + pr, w0 + pc, pr, pc, T, H, W, true);
+    else gcol_row<true>(gh, row_out, t, h0 + pr, w0 + pc, pr, pc, T, H, W, h0 + pr < H && w0 + pc < W);
 }
 
 // Data gradient of the 16 -> 1 proj conv on tensor cores: gx[q][c] = sum_tap G[q][tap] * W[c][tap] with the same im2col rows
@@ -698,7 +708,7 @@ proj_dgrad_scalar_tc_kernel(const float* __restrict__ gs, const float* __restric
         const Tile c = nxt;
         cp_async_wait<0>();
         __syncthreads();
-        gcol_row(gsh[buf], tileG + tid * CPG, c.t, c.h0 + pr, c.w0 + pc, pr, pc, T, H, W, c.h0 + pr < H && c.w0 + pc < W);
+        gcol_row_tile(gsh[buf], tileG + tid * CPG, c.t, c.h0, c.w0, pr, pc, T, H, W);
         __syncthreads();
         if (tile + 1 < last) { nxt = decode(tile + 1); issue(nxt, buf ^ 1); }
         const int64_t img_off = (((int64_t)c.n * V + v) * T + c.t) * (int64_t)H * W * 16;
@@ -815,7 +825,7 @@ proj_wgrad_scalar_kernel(WP p) {
         // ---- im2col row of this thread's pixel q = (t, h0 + pr, w0 + pc) ----
         {
             const bool in_img = c.h0 + pr < p.Ho && c.w0 + pc < p.Wo;
-            gcol_row(gsh[buf], tileG + tid * 40, c.t, c.h0 + pr, c.w0 + pc, pr, pc, p.To, p.Ho, p.Wo, in_img);
+            gcol_row_tile(gsh[buf], tileG + tid * 40, c.t, c.h0, c.w0, pr, pc, p.To, p.Ho, p.Wo);
             if (in_img) gsum += gsh[buf][(1 * HH + pr + 1) * HW_ + pc + 1];
         }
         __syncthreads();
