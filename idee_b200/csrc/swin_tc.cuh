@@ -604,8 +604,11 @@ swin_attn_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ g
     for (int b = 0; b < 2; ++b) aWp[b][0] = aWp[b][1] = aWp[b][2] = aWp[b][3] = 0.f;
 #pragma unroll
     for (int a = 0; a < 4; ++a) { abp[a] = 0.f; abq[0][a] = abq[1][a] = abq[2][a] = 0.f; }
-    float aew[4] = {0.f, 0.f, 0.f, 0.f}, aeb[4] = {0.f, 0.f, 0.f, 0.f};     // fused embedding backward (EMB with emb_gpart)
+    // fused embedding backward (EMB with emb_gpart): its 8 running sums per lane live in shared memory (two float4 per lane and
+    // tile), not in registers -- this kernel already spills
+    __shared__ __align__(16) float4 emb_acc[EMB ? TCW * 2 * 32 : 1];
     const bool emb_bwd = EMB && g.emb_gpart != nullptr;
+    if (EMB) { emb_acc[(warp * 2) * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f); emb_acc[(warp * 2 + 1) * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f); }
 
     const int n_iter = (g.n_wg + gridDim.x * TCW - 1) / (gridDim.x * TCW);
     for (int it = 0; it < n_iter; ++it) {
@@ -736,12 +739,14 @@ swin_attn_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ g
             }
             ln_tile(e, en, rs, nullptr);
             ln_bwd_tile(gxt, en, rs, ge);
+            float4 sw4 = emb_acc[(warp * 2) * 32 + lane], sb4 = emb_acc[(warp * 2 + 1) * 32 + lane];
 #pragma unroll
             for (int r = 0; r < 4; ++r)
                 if (tr.valid[r]) {
-#pragma unroll
-                    for (int qd = 0; qd < 4; ++qd) { aew[qd] += ge[r][qd] * xin[r]; aeb[qd] += ge[r][qd]; }
+                    sw4.x += ge[r][0] * xin[r]; sw4.y += ge[r][1] * xin[r]; sw4.z += ge[r][2] * xin[r]; sw4.w += ge[r][3] * xin[r];
+                    sb4.x += ge[r][0]; sb4.y += ge[r][1]; sb4.z += ge[r][2]; sb4.w += ge[r][3];
                 }
+            emb_acc[(warp * 2) * 32 + lane] = sw4; emb_acc[(warp * 2 + 1) * 32 + lane] = sb4;
         } else store_tile(gx, gxt, tr, c0);
         // weight gradients (K = the 32 tokens of this warp)
         uint32_t xnT[4][2], oT[4][2];
@@ -793,7 +798,9 @@ swin_attn_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ g
         __syncthreads();
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
-            float sw_ = aew[qd], sb_ = aeb[qd];
+            const float4 sw4 = emb_acc[(warp * 2) * 32 + lane], sb4 = emb_acc[(warp * 2 + 1) * 32 + lane];
+            float sw_ = qd == 0 ? sw4.x : (qd == 1 ? sw4.y : (qd == 2 ? sw4.z : sw4.w));
+            float sb_ = qd == 0 ? sb4.x : (qd == 1 ? sb4.y : (qd == 2 ? sb4.z : sb4.w));
 #pragma unroll
             for (int o = 4; o < 32; o <<= 1) { sw_ += __shfl_xor_sync(0xffffffffu, sw_, o); sb_ += __shfl_xor_sync(0xffffffffu, sb_, o); }
             if (lane < 4) {
