@@ -595,7 +595,12 @@ swin_attn_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ g
     float* dB = dBw_all + warp * DBW;
 
     // persistent accumulators: dWqkv[o][c] 3 m-tiles x 2 n-tiles ; dWproj[c][e] 1 x 2 ; biases per-lane column sums
-    float aWq[3][2][4], aWp[2][4], abq[3][4], abp[4];
+    // bias-gradient column sums (4 float4 per lane) live in shared memory: 8 128-bit accesses per tile instead of 16 registers
+    // held across the whole loop of a kernel that already spills
+    __shared__ __align__(16) float4 bias_acc[TCW * 4 * 32];
+    float aWq[3][2][4], aWp[2][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) bias_acc[(warp * 4 + a) * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int a = 0; a < 3; ++a)
 #pragma unroll
@@ -603,7 +608,6 @@ swin_attn_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ g
 #pragma unroll
     for (int b = 0; b < 2; ++b) aWp[b][0] = aWp[b][1] = aWp[b][2] = aWp[b][3] = 0.f;
 #pragma unroll
-    for (int a = 0; a < 4; ++a) { abp[a] = 0.f; abq[0][a] = abq[1][a] = abq[2][a] = 0.f; }
     // fused embedding backward (EMB with emb_gpart): its 8 running sums per lane live in shared memory (two float4 per lane and
     // tile), not in registers -- this kernel already spills
     __shared__ __align__(16) float4 emb_acc[EMB ? TCW * 2 * 32 : 1];
@@ -769,10 +773,20 @@ swin_attn_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ g
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) mma16816(aWp[nt], a0, a1, a2, a3, oT[2 * ik][nt], oT[2 * ik + 1][nt]);
         }
+        {
+            float4 b4[4];
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
+            for (int a = 0; a < 4; ++a) b4[a] = bias_acc[(warp * 4 + a) * 32 + lane];
 #pragma unroll
-            for (int qd = 0; qd < 4; ++qd) { abq[0][qd] += dq[r][qd]; abq[1][qd] += dk[r][qd]; abq[2][qd] += dv[r][qd]; abp[qd] += ga[r][qd]; }
+            for (int r = 0; r < 4; ++r) {
+                b4[0].x += dq[r][0]; b4[0].y += dq[r][1]; b4[0].z += dq[r][2]; b4[0].w += dq[r][3];
+                b4[1].x += dk[r][0]; b4[1].y += dk[r][1]; b4[1].z += dk[r][2]; b4[1].w += dk[r][3];
+                b4[2].x += dv[r][0]; b4[2].y += dv[r][1]; b4[2].z += dv[r][2]; b4[2].w += dv[r][3];
+                b4[3].x += ga[r][0]; b4[3].y += ga[r][1]; b4[3].z += ga[r][2]; b4[3].w += ga[r][3];
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a) bias_acc[(warp * 4 + a) * 32 + lane] = b4[a];
+        }
     }
     // CTA reduction, layout: qkv_w[48*16] | qkv_b[48] | proj_w[16*16] | proj_b[16] | dB
 #pragma unroll
@@ -786,11 +800,14 @@ swin_attn_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ g
                 atomicAdd(&red[3 * C * C + 3 * C + (gq + 8 * hf) * C + 8 * nt + c0 + b], aWp[nt][2 * hf + b]);
             }
 #pragma unroll
-    for (int qd = 0; qd < 4; ++qd) {
-        const int col = c0 + (qd & 1) + 8 * (qd >> 1);
+    for (int a = 0; a < 4; ++a) {
+        const float4 b4 = bias_acc[(warp * 4 + a) * 32 + lane];
+        const float vals[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-        for (int w3 = 0; w3 < 3; ++w3) atomicAdd(&red[3 * C * C + 16 * w3 + col], abq[w3][qd]);
-        atomicAdd(&red[3 * C * C + 3 * C + C * C + col], abp[qd]);
+        for (int qd = 0; qd < 4; ++qd) {
+            const int col = c0 + (qd & 1) + 8 * (qd >> 1);
+            atomicAdd(&red[a < 3 ? 3 * C * C + 16 * a + col : 3 * C * C + 3 * C + C * C + col], vals[qd]);
+        }
     }
     if (emb_bwd) {                                        // rows live in lanes with equal lane % 4: reduce over lane / 4, then over the warps
         __shared__ float red_e[32];
