@@ -753,6 +753,104 @@ proj_dgrad_scalar_tc_kernel(const float* __restrict__ gs, const float* __restric
     }
 }
 
+// Data gradient of the classifier's logit convs (NCH -> 1, kernel (2,3,3), stride (2,1,1), zero padding): the incoming gradient is
+// one scalar per output pixel and input slice t only receives the kt = t & 1 taps of output slice t >> 1, so
+// gx[(t,h,w)][c] = sum_{kh,kw} W[c][t & 1][kh][kw] * gs[(t >> 1, h + 1 - kh, w + 1 - kw)] is a 9-tap 2-D stencil: im2col of the
+// scalar plane (9 of 16 bf16 per pixel) x weights (register B fragments for both time parities), one HMMA k-step per n-tile,
+// fused ReLU mask, fp32 stores.  grid = (CTAs per image set, Vimg).
+template <int NCH>
+__global__ void __launch_bounds__(128)
+cls_dgrad_scalar_tc_kernel(const float* __restrict__ gs, const float* __restrict__ w, const float* __restrict__ relu_src,
+                           float* __restrict__ gx, int Vw, int Ti, int To, int H, int W, int64_t gs_sn, int64_t gs_sv, int gs_st, int gs_sh, int gs_sw,
+                           int64_t x_sn, int64_t x_sv, int x_st, int x_sh, int x_sw, uint32_t tiles_per_v, FastDiv fd_tw, FastDiv fd_th,
+                           FastDiv fd_t) {
+    constexpr int CPG = 24, NHALO = HH * HW_, NTN = NCH / 8;
+    __shared__ __align__(16) float gsh[2][NHALO];
+    __shared__ __align__(16) __nv_bfloat16 tileG[TH * TW * CPG];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, v = blockIdx.y;
+    const int pr = tid / TW, pc = tid % TW;
+    // B fragments for both time parities: B[k = kh*3+kw (< 9)][n = c] = w[c][kt][kh][kw];  w: [Vw][1][NCH][2][3][3]
+    const float* wv = w + (int64_t)(Vw == 1 ? 0 : v) * NCH * 18;
+    uint32_t bf[2][NTN][2];
+#pragma unroll
+    for (int kt = 0; kt < 2; ++kt)
+#pragma unroll
+        for (int nt = 0; nt < NTN; ++nt) {
+            const int cch = nt * 8 + lane / 4, t0 = 2 * (lane % 4);
+            auto wt = [&](int tap) { return tap < 9 ? __ldg(wv + cch * 18 + kt * 9 + tap) : 0.f; };
+            bf[kt][nt][0] = pack_bf16(wt(t0), wt(t0 + 1));
+            bf[kt][nt][1] = pack_bf16(wt(t0 + 8), wt(t0 + 9));
+        }
+    const uint32_t per_cta = (tiles_per_v + gridDim.x - 1) / gridDim.x;
+    const uint32_t first = blockIdx.x * per_cta, last = min(tiles_per_v, first + per_cta);
+    struct Tile { int n, t, h0, w0; };
+    auto decode = [&](uint32_t tile) {
+        Tile c;
+        uint32_t q, r;
+        fd_tw.divmod(tile, q, r); c.w0 = (int)r * TW;
+        fd_th.divmod(q, q, r); c.h0 = (int)r * TH;
+        fd_t.divmod(q, q, r); c.t = (int)r; c.n = (int)q;
+        return c;
+    };
+    auto issue = [&](const Tile& c, int buf) {
+        const float* g_img = gs + c.n * gs_sn + v * gs_sv + (int64_t)(c.t >> 1) * gs_st;
+        for (int e = tid; e < NHALO; e += 128) {
+            const int b = e / HW_, cc = e - b * HW_;
+            const int ph = c.h0 - 1 + b, pw = c.w0 - 1 + cc;
+            const bool ok = (c.t >> 1) < To && (unsigned)ph < (unsigned)H && (unsigned)pw < (unsigned)W;   // odd Ti: last slice unused
+            cp_async4_u32(smem_u32(&gsh[buf][e]), ok ? g_img + (int64_t)(ph * gs_sh + pw * gs_sw) : gs, ok ? 4 : 0);
+        }
+        cp_async_commit();
+    };
+    Tile nxt{};
+    if (first < last) { nxt = decode(first); issue(nxt, 0); }
+    const int a_pix = (lane & 7) + ((lane >> 3) & 1) * 8, a_koff = (lane >> 4) * 8;
+    int buf = 0;
+    for (uint32_t tile = first; tile < last; ++tile, buf ^= 1) {
+        const Tile c = nxt;
+        cp_async_wait<0>();
+        __syncthreads();
+        {                                                  // im2col row: G[q][kh*3+kw] = gs[h + 1 - kh, w + 1 - kw]
+            const float* gh = gsh[buf];
+            float g9[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) g9[k] = gh[(pr + 2 - k / 3) * HW_ + pc + 2 - k % 3];
+            uint4* row = reinterpret_cast<uint4*>(tileG + tid * CPG);
+            row[0] = make_uint4(pack_bf16(g9[0], g9[1]), pack_bf16(g9[2], g9[3]), pack_bf16(g9[4], g9[5]), pack_bf16(g9[6], g9[7]));
+            row[1] = make_uint4(pack_bf16(g9[8], 0.f), 0u, 0u, 0u);
+        }
+        __syncthreads();
+        if (tile + 1 < last) { nxt = decode(tile + 1); issue(nxt, buf ^ 1); }
+        const int kt = c.t & 1;
+        const int64_t img_off = c.n * x_sn + v * x_sv + (int64_t)c.t * x_st;
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            const int ks = warp * 2 + m;                   // tile row of 16 pixels
+            uint32_t a[4];
+            ldsm_x4(a, tileG + (ks * TW + a_pix) * CPG + a_koff);
+            const int hq = c.h0 + ks;
+            if (hq >= H) continue;
+#pragma unroll
+            for (int nt = 0; nt < NTN; ++nt) {
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                mma_bf16(acc, a, kt ? bf[1][nt][0] : bf[0][nt][0], kt ? bf[1][nt][1] : bf[0][nt][1]);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int wq = c.w0 + lane / 4 + half * 8;
+                    if (wq >= W) continue;
+                    const int64_t o = img_off + (int64_t)(hq * x_sh + wq * x_sw) + nt * 8 + (lane % 4) * 2;
+                    float v0 = acc[half * 2], v1 = acc[half * 2 + 1];
+                    if (relu_src) {
+                        const float2 a2 = __ldg(reinterpret_cast<const float2*>(relu_src + o));
+                        if (!(a2.x > 0.f)) v0 = 0.f; if (!(a2.y > 0.f)) v1 = 0.f;
+                    }
+                    *reinterpret_cast<float2*>(gx + o) = make_float2(v0, v1);
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // Weight gradient of the 16 -> 1 proj conv as ONE small GEMM per tile:  dW[c][tap] = sum_q h[q][c] * G[q][tap], where
 // G[q][tap] = sum of gs[p] over the pixels p with clamp(p + tap - 1) == q is the im2col of the SCALAR gradient plane (27 values
@@ -1259,7 +1357,9 @@ size_t conv_tc_fwd_workspace_bytes(const idee_conv_desc* d) {
 }
 
 size_t conv_tc_dgrad_workspace_bytes(const idee_conv_desc* d) {
-    if (d->proj && d->Cout == 1 && d->Cin == 16) return 0;           // scalar-gradient stencil: no staging
+    if (d->proj && d->Cout == 1 && d->Cin == 16) return 0;           // scalar-gradient kernels: no staging
+    if (!d->proj && d->Cout == 1 && (d->Cin == 16 || d->Cin == 96) && !d->x_dtype && !d->y_dtype && !d->gx_dtype &&
+        d->x_sw == d->Cin && d->in_cpg * 16 == d->Cin && d->y_sw == 1) return 0;
     if (conv96_umma_eligible(d)) return conv96_umma_workspace_bytes();
     if (conv_umma_eligible(d)) return conv_umma_workspace_bytes();
     size_t b = make_plan(d->proj ? PROJ_DGRAD_PAD : CLS_DGRAD, d->Cout, d->Cin, d->Vw).wfrag_bytes;
@@ -1295,6 +1395,27 @@ int conv_tc_fwd(const idee_conv_desc* d, const void* x, const float* w, const fl
 int conv_tc_dgrad(const idee_conv_desc* d, const void* gy, const float* w, const void* relu_src, void* gx, void* ws, cudaStream_t st) {
     if (conv96_umma_eligible(d)) return conv96_umma_run(d, 1, (const float*)gy, w, nullptr, (const float*)relu_src, (float*)gx, ws, st);
     if (conv_umma_eligible(d)) return conv_umma_run(d, 1, (const float*)gy, w, nullptr, (const float*)relu_src, (float*)gx, ws, st);
+    if (!d->proj && d->Cout == 1 && (d->Cin == 16 || d->Cin == 96) && !d->x_dtype && !d->y_dtype && !d->gx_dtype &&
+        d->x_sw == d->Cin && d->in_cpg * 16 == d->Cin && d->y_sw == 1) {
+        // logit conv: scalar gradient plane in, 9-tap stencil per input slice on the tensor cores
+        IDEE_REQUIRE((int64_t)d->Ti * d->x_st + (int64_t)d->Hi * d->x_sh + (int64_t)d->Wi * d->x_sw < (1ll << 31) &&
+                     (int64_t)d->To * d->y_st + (int64_t)d->Ho * d->y_sh + (int64_t)d->Wo * d->y_sw < (1ll << 31),
+                     "conv3d_dgrad(cls ->1): tensor too large for 32-bit offsets");
+        const int tiles_h = (d->Hi + TH - 1) / TH, tiles_w = (d->Wi + TW - 1) / TW;
+        const int64_t tpv = (int64_t)d->N * d->Ti * tiles_h * tiles_w;
+        IDEE_REQUIRE(tpv < (1ll << 31), "conv3d_dgrad(cls ->1): too many tiles");
+        int nb = (idee_num_sms() * 8 + d->V - 1) / d->V;
+        if (nb > tpv) nb = (int)tpv;
+        dim3 grid(nb, d->V);
+#define IDEE_CLS_SCALAR_DGRAD(N_)                                                                                                  \
+        cls_dgrad_scalar_tc_kernel<N_><<<grid, 128, 0, st>>>((const float*)gy, w, (const float*)relu_src, (float*)gx, d->Vw, d->Ti, d->To, d->Hi,   \
+            d->Wi, d->y_sn, d->y_sv, (int)d->y_st, (int)d->y_sh, (int)d->y_sw, d->x_sn, d->x_sv, (int)d->x_st, (int)d->x_sh, (int)d->x_sw,   \
+            (uint32_t)tpv, make_fastdiv(tiles_w), make_fastdiv(tiles_h), make_fastdiv(d->Ti))
+        if (d->Cin == 16) IDEE_CLS_SCALAR_DGRAD(16); else IDEE_CLS_SCALAR_DGRAD(96);
+#undef IDEE_CLS_SCALAR_DGRAD
+        IDEE_LAUNCH_CHECK("conv3d_dgrad(cls ->1)");
+        return 0;
+    }
     if (d->proj && d->Cout == 1 && d->Cin == 16) {            // one scalar per pixel comes in: CUDA-core stencil, exact replicate adjoint
         IDEE_REQUIRE(d->y_dtype == 0, "conv3d_dgrad(proj 16->1): the incoming gradient must be fp32");
         IDEE_REQUIRE(d->x_sw == 16 && d->x_sh == (int64_t)d->Wi * 16 && d->x_st == (int64_t)d->Hi * d->Wi * 16 &&
