@@ -25,7 +25,7 @@ class ConvDesc(C.Structure):
     _fields_ = [(n, c_int) for n in ("N", "V", "Vw", "Cin", "Cout", "Ti", "Hi", "Wi", "To", "Ho", "Wo", "proj", "relu", "precision")] + \
                [(n, c_i64) for n in ("x_sn", "x_sv", "x_st", "x_sh", "x_sw", "x_sg")] + [("in_cpg", c_int)] + \
                [(n, c_i64) for n in ("y_sn", "y_sv", "y_st", "y_sh", "y_sw", "y_sg")] + [("out_cpg", c_int)] + \
-               [(n, c_int) for n in ("x_dtype", "y_dtype", "gx_dtype", "umma16", "umma96")]
+               [(n, c_int) for n in ("x_dtype", "y_dtype", "gx_dtype", "umma16", "umma96", "cin_real")]
 
 
 _SIGS = {

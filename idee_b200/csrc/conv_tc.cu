@@ -1446,7 +1446,9 @@ int conv_tc_dgrad(const idee_conv_desc* d, const void* gy, const float* w, const
         return 0;
     }
     const int mode = d->proj ? PROJ_DGRAD_PAD : CLS_DGRAD;
-    const Plan pl = make_plan(mode, d->Cout, d->Cin, d->Vw);
+    // structurally zero input channels (cin_real): their gradient is neither needed nor computed
+    const int go = (!d->proj && d->cin_real > 0 && d->cin_real <= 8 && d->Cin == 16) ? 8 : d->Cin;
+    const Plan pl = make_plan(mode, d->Cout, go, d->Vw);
     if (prep(d, w, (uint2*)ws, pl, 1, st)) return 2;
     P p{};
     p.in = (const float*)gy; p.bias = nullptr; p.wfrag = (const uint2*)ws;
@@ -1454,7 +1456,7 @@ int conv_tc_dgrad(const idee_conv_desc* d, const void* gy, const float* w, const
     p.N = d->N; p.V = d->V; p.Vw = d->Vw;
     p.Ti = d->To; p.Hi = d->Ho; p.Wi = d->Wo;
     p.in_sn = d->y_sn; p.in_sv = d->y_sv; p.in_st = d->y_st; p.in_sh = d->y_sh; p.in_sw = d->y_sw; p.in_sg = d->y_sg; p.in_cpg = d->out_cpg;
-    p.CO = d->Cin; p.CIr = d->Cout; p.NTf = pl.NTf; p.relu = 0;
+    p.CO = go; p.CIr = d->Cout; p.NTf = pl.NTf; p.relu = 0;
     if (!d->proj) {
         p.out = (float*)gx; p.relu_src = (const float*)relu_src;
         p.out16 = d->gx_dtype;

@@ -113,8 +113,9 @@ class CNN_3D(nn.Module):
         Wq = torch.einsum('ovcthw,c->ovthw', W5, w_out.reshape(-1))
         Wb = torch.einsum('ovcthw,c->othw', W5, b_out.reshape(-1))
         W16 = torch.cat([Wq, Wb.unsqueeze(1), Wq.new_zeros(Co, 15 - V, 2, 3, 3)], dim=1)
+        # only the V scalar planes need a gradient (ones / zero planes are constants): cin_real lets the data gradient skip the rest
         return ops.conv3d_cl(planes.unsqueeze(1), W16.unsqueeze(0), self.conv1.bias.unsqueeze(0), proj=False, relu=True,
-                             consumer_masks=self._fuse1())
+                             consumer_masks=self._fuse1(), cin_real=V + 1)
 
     def _fuse1(self) -> bool:
         """conv2 may apply conv1's ReLU mask only when the Dropout between them is the identity."""

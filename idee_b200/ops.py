@@ -291,7 +291,7 @@ class Conv3dCL(torch.autograd.Function):
       * ``out_bf16`` stores the output as bf16 (and its incoming gradient is then bf16)."""
 
     @staticmethod
-    def forward(ctx, x, w, b, proj, relu, groups, input_is_relu=False, consumer_masks=False, x16=None, out_bf16=False):
+    def forward(ctx, x, w, b, proj, relu, groups, input_is_relu=False, consumer_masks=False, x16=None, out_bf16=False, cin_real=0):
         """input_is_relu: x is the fused-ReLU output of a conv whose ONLY consumer is this op -> this op's data gradient is
         multiplied by (x > 0) in the kernel epilogue.  consumer_masks: the (only) consumer of this op's ReLU output does
         exactly that, so the incoming gradient is already masked and no separate ReLU-backward pass is needed."""
@@ -322,6 +322,7 @@ class Conv3dCL(torch.autograd.Function):
                        (y.stride(0), y.stride(1), y.stride(2), y.stride(3), y.stride(4)), Vw, Cin, Cout, proj, relu,
                        in_cpg, max(Cout // 16, 1), x_sg, 0)
         d.x_dtype, d.y_dtype, d.gx_dtype = int(xin.dtype == torch.bfloat16), int(out_bf16), int(gx_dtype == torch.bfloat16)
+        d.cin_real = int(cin_real)       # leading input channels that carry data; the gradient of the rest is left unwritten
         nws = lib.idee_conv3d_fwd_workspace_bytes(C.byref(d))
         ws = L.workspace(nws, xin.device)
         L.run("conv3d_fwd_bf16" if d.precision else "conv3d_fwd", lib.idee_conv3d_fwd, C.byref(d), xin.data_ptr(), w.data_ptr(),
@@ -358,7 +359,7 @@ class Conv3dCL(torch.autograd.Function):
             relu_src = x.data_ptr() if ctx.input_is_relu else None       # dL/d(pre-activation) = dL/dx * (x > 0), fused
             L.run("conv3d_dgrad_bf16" if d.precision else "conv3d_dgrad", lib.idee_conv3d_dgrad, C.byref(d), gy.data_ptr(),
                   w.data_ptr(), relu_src, gx.data_ptr(), ws.data_ptr(), nws, L.stream(), tag=_conv_tag(d))
-        return gx, gw, gb, None, None, None, None, None, None, None
+        return gx, gw, gb, None, None, None, None, None, None, None, None
 
 
 def _conv_tag(d) -> str:
@@ -377,9 +378,9 @@ def _dense(t: torch.Tensor) -> bool:
 
 
 def conv3d_cl(x, w, b, proj: bool, relu: bool, groups: int = 1, input_is_relu: bool = False, consumer_masks: bool = False,
-              x16=None, out_bf16: bool = False):
+              x16=None, out_bf16: bool = False, cin_real: int = 0):
     return Conv3dCL.apply(x, w, b, bool(proj), bool(relu), int(groups), bool(input_is_relu), bool(consumer_masks), x16,
-                          bool(out_bf16))
+                          bool(out_bf16), int(cin_real))
 
 
 class PackedWB(torch.autograd.Function):

@@ -108,6 +108,9 @@ typedef struct {
     /* 1: run the 96 -> 96 classifier conv (forward and data gradient, fp32 I/O) on the warp-specialised tcgen05 + TMEM kernel
      * (conv96_umma.cu) instead of mma.sync */
     int umma96;
+    /* > 0: only the first cin_real input channels carry data (the rest are structurally zero, e.g. the padded plane image of the
+     * rank-1 joint conv); the data gradient then computes and writes only those channels (rounded up to 8) */
+    int cin_real;
 } idee_conv_desc;
 
 size_t idee_conv3d_fwd_workspace_bytes(const idee_conv_desc* d);
