@@ -75,6 +75,7 @@ struct P {
     int tiles_w;
     int KS;                      // k-steps (gather-in channels / 16) for the generic (template KS == 0) kernels
     int in16, out16;             // input / output tensors hold bf16 instead of fp32 (16-channel proj kernels only)
+    int pair;                    // forward, <= 8 real input channels: two taps share one k16 step (8 channels each)
 };
 
 // fp32 PyTorch weights [FCO][FCI][NTf] -> bf16 mma B fragments.  B(k, n) = W[o=n][c=k] (forward) or W[o=k][c=n] (dgrad).
@@ -135,7 +136,14 @@ conv_tc_kernel(P p) {
         if (MODE == CLS_DGRAD) return (t & 1) * 9 + (2 - j / 3) * 3 + (2 - j % 3);
         return (2 - j / 9) * 9 + (2 - (j / 3) % 3) * 3 + (2 - j % 3);
     };
-    if (!STREAM) {
+    const bool pair = !STREAM && KS_T == 1 && MODE == CLS_FWD && p.pair;
+    if (pair) {
+        // taps (2q, 2q+1) packed into one k16 step: k 0-7 = channels 0-7 of tap 2q, k 8-15 = channels 0-7 of tap 2q+1
+        for (int e = tid; e < (NJ / 2) * WTAP; e += 128) {
+            const int q = e / WTAP, r = e - q * WTAP;
+            wsm[e] = make_uint2(wf[(int64_t)(2 * q) * WTAP + r].x, wf[(int64_t)(2 * q + 1) * WTAP + r].x);
+        }
+    } else if (!STREAM) {
         for (int e = tid; e < NJ * WTAP; e += 128) wsm[e] = wf[(int64_t)ftap_of(e / WTAP) * WTAP + e % WTAP];
     } else {
         for (int e = tid; e < WTAP / 2; e += 128) cp_async16(&wsm[2 * e], &wf[(int64_t)ftap_of(0) * WTAP + 2 * e]);
@@ -204,6 +212,26 @@ conv_tc_kernel(P p) {
 
     // ldmatrix row address of this lane inside an m-tile (16 consecutive w of one tile row)
     const int a_pix = (lane & 7) + ((lane >> 3) & 1) * 8, a_koff = (lane >> 4) * 8;
+    if (pair) {
+        // lanes 0-15 address the rows of tap 2q, lanes 16-31 those of tap 2q+1 (both at channel offset 0): one ldmatrix.x4
+        // yields the k16 A fragment [8 channels of tap 2q | 8 channels of tap 2q+1]
+#pragma unroll
+        for (int q = 0; q < NJ / 2; ++q) {
+            const int j = 2 * q + (lane >> 4);
+            const int kt = j / 9, kh = (j / 3) % 3, kw = j % 3;
+            uint32_t a[2][4];
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+                ldsm_x4(a[m], halo + ((size_t)(kt * HH + warp * 2 + m + kh) * HW_ + kw + a_pix) * CP);
+            const uint2* wt = wsm + q * WTAP;
+#pragma unroll
+            for (int nt = 0; nt < NTL; ++nt) {
+                const uint2 b = wt[nt * 32 + lane];
+                mma_bf16(acc[0][nt], a[0], b.x, b.y);
+                mma_bf16(acc[1][nt], a[1], b.x, b.y);
+            }
+        }
+    } else
     for (int j = 0; j < NJ; ++j) {
         const uint2* wt;
         if (STREAM) {
@@ -1388,6 +1416,7 @@ int conv_tc_fwd(const idee_conv_desc* d, const void* x, const float* w, const fl
     p.in_sn = d->x_sn; p.in_sv = d->x_sv; p.in_st = d->x_st; p.in_sh = d->x_sh; p.in_sw = d->x_sw; p.in_sg = d->x_sg; p.in_cpg = d->in_cpg;
     p.out_sn = d->y_sn; p.out_sv = d->y_sv; p.out_st = d->y_st; p.out_sh = d->y_sh; p.out_sw = d->y_sw; p.out_sg = d->y_sg; p.out_cpg = d->out_cpg;
     p.CO = d->Cout; p.CIr = d->Cin; p.NTf = pl.NTf; p.relu = d->relu; p.tiles_w = (p.Wo + TW - 1) / TW;
+    p.pair = (!d->proj && d->cin_real > 0 && d->cin_real <= 8 && d->Cin == 16) ? 1 : 0;
     const int nit = d->N * d->V * d->To;
     return d->proj ? dispatch_tc<PROJ_FWD>(p, pl, nit, st, "conv3d_fwd(proj,bf16)") : dispatch_tc<CLS_FWD>(p, pl, nit, st, "conv3d_fwd(cls,bf16)");
 }
