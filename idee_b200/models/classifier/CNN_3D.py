@@ -38,6 +38,12 @@ class Layer_v(nn.Module):
         return out[:, 0].permute(0, 4, 1, 2, 3).squeeze(2)
 
 
+class HeadLogits(list):
+    """The reference's list of per-variable logit maps [y_v [N,1,H,W]] * V (classifier/CNN_3D.py:139); ``stacked`` [N,V,H,W] is
+    the one tensor they are views of, so a loss over all heads can run as a single batched launch."""
+    stacked = None
+
+
 def _channel_last(x: torch.Tensor) -> torch.Tensor:
     """logical [N,V,C,T,H,W] -> token view [N,V,T,H,W,C] with C contiguous (copy only if the storage is not channel-last)."""
     tok = x.permute(0, 1, 3, 4, 5, 2)
@@ -128,7 +134,9 @@ class CNN_3D(nn.Module):
         tok = _channel_last(x)
         # multi-head classifier: all V heads per launch
         yh = _head(tok, self._head_params(), self.drop, groups=1, fuse1=self._fuse1())   # [N,V,T',H,W,1]
-        y = [yh[:, i].permute(0, 4, 1, 2, 3).squeeze(2) for i in range(self.in_var)]
+        y = HeadLogits(yh[:, i].permute(0, 4, 1, 2, 3).squeeze(2) for i in range(self.in_var))
+        if yh.shape[2] == 1:
+            y.stacked = yh[:, :, 0, :, :, 0]                                              # [N,V,H,W] view
         # joint head over the V*C channels
         first = None
         if rank1 is not None and V + 1 <= 16 and C == self.var_embed_dim:

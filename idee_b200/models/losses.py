@@ -42,9 +42,14 @@ def train_step_loss(model, data_d, mask_extreme, mask_extreme_loss, lambda_anoma
     vq = model.module.vq if hasattr(model, "module") else model.vq
     vq0 = vq.indices_to_codes(torch.zeros(1, dtype=torch.long, device=data_d.device)).clone().detach()
     loss_anomaly = crit_an(z_q, mask_extreme_loss.float(), vq0)
-    loss_var = 0
-    for y in pred_y:
-        loss_var = loss_var + crit(y, tgt)
+    stacked = getattr(pred_y, "stacked", None)
+    if stacked is not None and stacked.dtype == torch.float32:
+        # the V per-variable maps are views of one [N,V,H,W] tensor: same V losses (train_synthetic.py:196-198), one launch set
+        loss_var = ops.bce_loss_maps(stacked, tgt).sum()
+    else:
+        loss_var = 0
+        for y in pred_y:
+            loss_var = loss_var + crit(y, tgt)
     total = loss + loss_anomaly * lambda_anomaly + loss_var + loss_z_q
     return total, dict(pred=pred, pred_y=pred_y, anomaly=anomaly, z_q=z_q, loss_z_q=loss_z_q, loss_bce=loss,
                        loss_anomaly=loss_anomaly, loss_var=loss_var)

@@ -519,7 +519,7 @@ class BCEWeighted(torch.autograd.Function):
     pred: [K?, N, 1, H, W]-like storage addressed as k*sk + n*sn + i."""
 
     @staticmethod
-    def forward(ctx, pred, target, K, sk, sn, N, HW):
+    def forward(ctx, pred, target, K, sk, sn, N, HW, kdim=0):
         L.require_cuda(pred, target)
         lib = L.load()
         target = _f32c(target)
@@ -531,16 +531,17 @@ class BCEWeighted(torch.autograd.Function):
         L.run("bce_loss_fwd", lib.idee_bce_loss_fwd, pred.data_ptr(), sk, sn, K, N, HW, target.data_ptr(), wts.data_ptr(), loss.data_ptr(),
               dpred.data_ptr(), ws.data_ptr(), nws, L.stream())
         ctx.save_for_backward(dpred)
-        ctx.K = K
+        ctx.K, ctx.kdim = K, kdim
         return loss
 
     @staticmethod
     def backward(ctx, gloss):
         (dpred,) = ctx.saved_tensors
         if ctx.K == 1:
-            return dpred * gloss.reshape(()), None, None, None, None, None, None
-        shape = [ctx.K] + [1] * (dpred.dim() - 1)
-        return dpred * gloss.view(shape), None, None, None, None, None, None
+            return dpred * gloss.reshape(()), None, None, None, None, None, None, None
+        shape = [1] * dpred.dim()
+        shape[ctx.kdim] = ctx.K
+        return dpred * gloss.view(shape), None, None, None, None, None, None, None
 
 
 def bce_loss_map(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
@@ -553,6 +554,14 @@ def bce_loss_map(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
     if not inner_ok:
         pred = pred.contiguous()
     return BCEWeighted.apply(pred, target, 1, 0, pred.stride(0), N, HW)[0]
+
+
+def bce_loss_maps(stacked: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """K logit maps sharing one target in ONE launch set: stacked [N,K,H,W]-like storage (contiguous H,W), target [N,1,H,W]
+    -> losses [K] (the same values as K bce_loss_map calls)."""
+    assert stacked.dtype == torch.float32 and stacked.dim() == 4 and stacked[0, 0].is_contiguous()
+    N, K, H, W = stacked.shape
+    return BCEWeighted.apply(stacked, target, K, stacked.stride(1), stacked.stride(0), N, H * W, 1)
 
 
 class AnomalyL1(torch.autograd.Function):
