@@ -129,10 +129,8 @@ lfq_bwd_kernel(const float* __restrict__ z, const float* __restrict__ gzq, const
     float a_wi[C], a_wo[C], a_bo[C], a_bi = 0.f;
 #pragma unroll
     for (int c = 0; c < C; ++c) { a_wi[c] = 0.f; a_wo[c] = 0.f; a_bo[c] = 0.f; }
-    double acc[LFQ_NG];
-#pragma unroll
-    for (int k = 0; k < LFQ_NG; ++k) acc[k] = 0.0;
-    int cnt = 0;
+    // a thread sees at most 64 tokens (lfq_blocks sizes the grid accordingly), so plain fp32 running sums are exact enough;
+    // they are widened to double only for the block / grid reduction (98 fewer live registers than double accumulators)
     for (int64_t tok = (int64_t)blockIdx.x * LFQ_THREADS + threadIdx.x; tok < ntok; tok += (int64_t)gridDim.x * LFQ_THREADS) {
         float zr[C], gr[C];
         load16_a(gr, gzq + tok * C, gzq_a32);
@@ -163,15 +161,11 @@ lfq_bwd_kernel(const float* __restrict__ z, const float* __restrict__ gzq, const
             a_bi += gs;
             store16(gz + tok * C, r);
         }
-        if (++cnt == 64) {   // flush fp32 running sums into double
-#pragma unroll
-            for (int c = 0; c < C; ++c) { acc[c] += a_wi[c]; acc[C + 1 + c] += a_wo[c]; acc[2 * C + 1 + c] += a_bo[c]; a_wi[c] = a_wo[c] = a_bo[c] = 0.f; }
-            acc[C] += a_bi; a_bi = 0.f; cnt = 0;
-        }
     }
+    double acc[LFQ_NG];
 #pragma unroll
-    for (int c = 0; c < C; ++c) { acc[c] += a_wi[c]; acc[C + 1 + c] += a_wo[c]; acc[2 * C + 1 + c] += a_bo[c]; }
-    acc[C] += a_bi;
+    for (int c = 0; c < C; ++c) { acc[c] = a_wi[c]; acc[C + 1 + c] = a_wo[c]; acc[2 * C + 1 + c] = a_bo[c]; }
+    acc[C] = a_bi;
     block_reduce_store<LFQ_NG>(acc, partials + (int64_t)blockIdx.x * LFQ_NG);
 }
 
@@ -186,7 +180,9 @@ __global__ void lfq_bwd_finalize_kernel(const double* __restrict__ partials, int
 
 int lfq_blocks(int64_t ntok) {
     int64_t nb = (ntok + LFQ_THREADS - 1) / LFQ_THREADS;
-    const int cap = idee_num_sms() * 8;
+    int64_t cap = idee_num_sms() * 8;
+    const int64_t per64 = (ntok + (int64_t)LFQ_THREADS * 64 - 1) / ((int64_t)LFQ_THREADS * 64);   // <= 64 tokens per thread
+    if (cap < per64) cap = per64;
     if (nb > cap) nb = cap;
     if (nb < 1) nb = 1;
     return (int)nb;
