@@ -46,7 +46,7 @@ _SIGS = {
     "idee_conv3d_wgrad_workspace_bytes": (c_sz, [C.POINTER(ConvDesc)]),
     "idee_conv3d_wgrad": (c_int, [C.POINTER(ConvDesc)] + [c_vp] * 5 + [c_sz, c_vp]),
     "idee_lfq_workspace_bytes": (c_sz, [c_i64]),
-    "idee_lfq_fwd": (c_int, [c_vp] * 9 + [c_i64, c_int, c_int, c_int] + [c_f32] * 4 + [c_vp, c_sz, c_vp]),
+    "idee_lfq_fwd": (c_int, [c_vp] * 9 + [c_i64, c_int, c_int, c_int] + [c_f32] * 4 + [c_vp, c_sz, c_vp, c_vp]),
     "idee_lfq_bwd": (c_int, [c_vp] * 10 + [c_i64] + [c_f32] * 4 + [c_vp, c_sz, c_vp]),
     "idee_bce_loss_workspace_bytes": (c_sz, [c_int]),
     "idee_bce_loss_fwd": (c_int, [c_vp, c_i64, c_i64, c_int, c_int, c_i64] + [c_vp] * 5 + [c_sz, c_vp]),

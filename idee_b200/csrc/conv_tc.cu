@@ -1314,6 +1314,7 @@ int dispatch_tc(const P& p, const Plan& pl, int n_img_t, cudaStream_t st, const 
             if constexpr (MODE == CLS_FWD || MODE == CLS_DGRAD) {     // per-variable classifier heads: one side of the conv in bf16
                 if (p.in16 && !p.out16) return launch_tc16<MODE, 2, true, false>(p, n_img_t, st, who);
                 if (!p.in16 && p.out16) return launch_tc16<MODE, 2, false, true>(p, n_img_t, st, who);
+                if constexpr (MODE == CLS_FWD) return launch_tc16<MODE, 2, true, true>(p, n_img_t, st, who);
             }
             if constexpr (MODE == PROJ_FWD) {
                 if (p.in16 && p.out16) return launch_tc16<MODE, 2, true, true>(p, n_img_t, st, who);
@@ -1588,7 +1589,8 @@ int conv_tc_wgrad_partials(const idee_conv_desc* d, const void* x, const void* g
         else IDEE_WGRAD_LAUNCH(27, 2, false, false);
     }
     else if (p.a16 || p.g16) {
-        if (NC == 16 && p.a16 && !p.g16) IDEE_WGRAD_LAUNCH(18, 2, true, false);
+        if (NC == 16 && p.a16 && p.g16) IDEE_WGRAD_LAUNCH(18, 2, true, true);
+        else if (NC == 16 && p.a16 && !p.g16) IDEE_WGRAD_LAUNCH(18, 2, true, false);
         else if (NC == 16 && !p.a16 && p.g16) IDEE_WGRAD_LAUNCH(18, 2, false, true);
         else { idee_set_error("conv3d_wgrad(cls,bf16): this bf16 activation storage combination is not built"); return 1; }
     }

@@ -8,6 +8,8 @@
 //   index = x>0 ; z_q = x*w_out + b_out ; train: p = softmax([-200 s, +200 s]), sums of per-token entropy,
 //   of p (for the codebook entropy) and of (s-q)^2, reduced in double per CTA then by a 1-thread finalize.
 // backward: single pass, g_s = <w_out, g_zq> (straight-through) + g_aux * d(aux)/ds, using the saved mean prob.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "idee_b200.h"
 
@@ -52,7 +54,7 @@ __global__ void __launch_bounds__(LFQ_THREADS)
 lfq_fwd_kernel(const float* __restrict__ z, const float* __restrict__ w_in, const float* __restrict__ b_in,
                const float* __restrict__ w_out, const float* __restrict__ b_out, float* __restrict__ zq,
                long long* __restrict__ indices, float* __restrict__ xq, double* __restrict__ partials, int64_t ntok, int training,
-               float inv_temp) {
+               float inv_temp, __nv_bfloat16* __restrict__ zq16) {
     float wi[C], wo[C], bo[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) { wi[c] = ZS ? 0.f : __ldg(w_in + c); wo[c] = __ldg(w_out + c); bo[c] = __ldg(b_out + c); }
@@ -81,6 +83,23 @@ lfq_fwd_kernel(const float* __restrict__ z, const float* __restrict__ w_in, cons
 #pragma unroll
         for (int c = 0; c < C; ++c) r[c] = x * wo[c] + bo[c];
         store16_warp(zq + tok0 * C, r, zq_stage[warp], lane, (int)min((int64_t)32, ntok - tok0));
+        if (zq16) {        // bf16 copy for consumers that round to bf16 anyway: re-read the staged rows, two coalesced 512-byte stores
+            const int nrows = (int)min((int64_t)32, ntok - tok0);
+            const float* smw = zq_stage[warp];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int f = j * 32 + lane, row = f >> 1, half = f & 1, sw = (row >> 1) & 3;
+                const float4 a = *reinterpret_cast<const float4*>(smw + row * 16 + (((2 * half) ^ sw) << 2));
+                const float4 b = *reinterpret_cast<const float4*>(smw + row * 16 + (((2 * half + 1) ^ sw) << 2));
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(b.x, b.y), h3 = __floats2bfloat162_rn(b.z, b.w);
+                if (row < nrows)
+                    *reinterpret_cast<uint4*>(zq16 + (tok0 + row) * C + half * 8) =
+                        make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1), *reinterpret_cast<uint32_t*>(&h2),
+                                   *reinterpret_cast<uint32_t*>(&h3));
+            }
+            __syncwarp();
+        }
         if (training && live) {
             float p0, p1;
             probs(s, inv_temp, p0, p1);
@@ -195,15 +214,15 @@ extern "C" size_t idee_lfq_workspace_bytes(int64_t ntok) { return sizeof(double)
 extern "C" int idee_lfq_fwd(const float* z, const float* w_in, const float* b_in, const float* w_out, const float* b_out,
                             float* zq, int64_t* indices, float* xq, float* stats, int64_t ntok, int dim, int codebook_size, int training,
                             float inv_temperature, float lambda_commit, float lambda_entropy, float diversity_gamma,
-                            void* workspace, size_t workspace_bytes, void* stream) {
+                            void* workspace, size_t workspace_bytes, void* zq_bf16, void* stream) {
     IDEE_REQUIRE((dim == C || dim == 1) && codebook_size == 2, "lfq_fwd: only dim=16 (or 1: pre-projected scalar), codebook_size=2 is built (got %d, %d)", dim, codebook_size);
     IDEE_REQUIRE(workspace_bytes >= idee_lfq_workspace_bytes(ntok), "lfq_fwd: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     const int nb = lfq_blocks(ntok);
     if (dim == 1) lfq_fwd_kernel<true><<<nb, LFQ_THREADS, 0, st>>>(z, w_in, b_in, w_out, b_out, zq, (long long*)indices, xq, (double*)workspace,
-                                                                  ntok, training, inv_temperature);
+                                                                  ntok, training, inv_temperature, (__nv_bfloat16*)zq_bf16);
     else lfq_fwd_kernel<false><<<nb, LFQ_THREADS, 0, st>>>(z, w_in, b_in, w_out, b_out, zq, (long long*)indices, xq, (double*)workspace, ntok,
-                                                            training, inv_temperature);
+                                                            training, inv_temperature, (__nv_bfloat16*)zq_bf16);
     IDEE_LAUNCH_CHECK("lfq_fwd");
     if (training) {
         lfq_finalize_kernel<<<1, 32, 0, st>>>((const double*)workspace, nb, ntok, lambda_commit, lambda_entropy, diversity_gamma, stats);

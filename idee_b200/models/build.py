@@ -73,7 +73,7 @@ class VQ_model(nn.Module):
             s = self.encoder.forward_tokens(x_d, fold_last=(self.vq.project_in.weight, self.vq.project_in.bias))   # [N,V,T,H,W]
             N, V, T, H, W = s.shape
             C = self.vq.dim
-            z_q, anomaly, loss_z_q = self.vq.forward_projected(s.reshape(N, V * T * H * W))
+            z_q, anomaly, loss_z_q = self.vq.forward_projected(s.reshape(N, V * T * H * W), want_bf16=True)
         else:
             tok = self.encoder.forward_tokens(x_d)                         # [N,V,T,H,W,C] channel-last
             N, V, T, H, W, C = tok.shape
@@ -82,6 +82,10 @@ class VQ_model(nn.Module):
         anomaly = anomaly.view(N, V, T, H, W)
         # the joint head consumes the rank-1 form of z_q (x * w_out + b_out): identical result, 1/6 of the conv1 work
         rank1 = (self.vq.last_scalar.view(N, V, T, H, W), self.vq.project_out.weight, self.vq.project_out.bias)
+        zq16 = getattr(self.vq, "last_zq_bf16", None)
+        if zq16 is not None:               # bf16 copy written by the quantiser kernel: input of the per-variable heads' first conv
+            z_q._idee_bf16 = zq16.view(N, V, T, H, W, C)
+            self.vq.last_zq_bf16 = None
         z, y = self.cls(z_q, rank1=rank1)
         z_q._idee_rank1 = rank1            # lets Anomaly_L1_loss_synthetic evaluate the same loss on the scalar plane
         return z, y, anomaly, z_q, loss_z_q.unsqueeze(0)

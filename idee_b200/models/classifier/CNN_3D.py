@@ -50,7 +50,7 @@ def _channel_last(x: torch.Tensor) -> torch.Tensor:
     return tok if tok.stride(5) == 1 and ops._dense(tok) else tok.contiguous()
 
 
-def _head(tok, wb, drop, groups, first=None, fuse1=True):
+def _head(tok, wb, drop, groups, first=None, fuse1=True, tok16=None):
     """conv1 -> ReLU -> Dropout -> conv2 -> ReLU -> conv3.  Each ReLU output has exactly one consumer, so the ReLU backward
     masks are applied in the consumers' data-gradient epilogues (fuse1 is False when an active Dropout sits in between)."""
     (w1, b1), (w2, b2), (w3, b3) = wb
@@ -58,7 +58,7 @@ def _head(tok, wb, drop, groups, first=None, fuse1=True):
     # it to bf16 as they load it, so it is stored as bf16 (bit-identical, see Conv3dCL)
     y1_bf16 = first is None and groups == 1 and fuse1 and _lib.PRECISION == "bf16" and w1.shape[1] == 16 and w1.shape[2] == 16
     h = first if first is not None else ops.conv3d_cl(tok, w1, b1, proj=False, relu=True, groups=groups, consumer_masks=fuse1,
-                                                      out_bf16=y1_bf16)
+                                                      x16=tok16 if y1_bf16 else None, out_bf16=y1_bf16)
     h = drop(h)
     h = ops.conv3d_cl(h, w2, b2, proj=False, relu=True, input_is_relu=fuse1, consumer_masks=True)
     return ops.conv3d_cl(h, w3, b3, proj=False, relu=False, input_is_relu=True)
@@ -133,7 +133,10 @@ class CNN_3D(nn.Module):
         N, V, C, T, H, W = x.shape
         tok = _channel_last(x)
         # multi-head classifier: all V heads per launch
-        yh = _head(tok, self._head_params(), self.drop, groups=1, fuse1=self._fuse1())   # [N,V,T',H,W,1]
+        tok16 = getattr(x, "_idee_bf16", None)                # bf16 copy of z_q written by the quantiser kernel (VQ_model)
+        if tok16 is not None and (tok16.shape != tok.shape or tok16.stride() != tok.stride()):
+            tok16 = None
+        yh = _head(tok, self._head_params(), self.drop, groups=1, fuse1=self._fuse1(), tok16=tok16)   # [N,V,T',H,W,1]
         y = HeadLogits(yh[:, i].permute(0, 4, 1, 2, 3).squeeze(2) for i in range(self.in_var))
         if yh.shape[2] == 1:
             y.stacked = yh[:, :, 0, :, :, 0]                                              # [N,V,H,W] view

@@ -74,12 +74,15 @@ class LFQ(nn.Module):
             codes = codes.movedim(-1, 1)
         return codes
 
-    def forward_projected(self, s, inv_temperature=100.):
+    def forward_projected(self, s, inv_temperature=100., want_bf16=False):
         """s [...] = project_in(z) already evaluated by the producer (VQ_model folds project_in into the encoder's last conv)
-        -> Return(quantized [..., dim], indices int64 [...], aux loss).  Same arithmetic as ``forward`` from s onwards."""
-        zq, idx, aux, xq = ops.LFQScalarFn.apply(s, self.project_out.weight, self.project_out.bias, self.training,
-                                                 float(inv_temperature), float(self.commitment_loss_weight),
-                                                 float(self.entropy_loss_weight), float(self.diversity_gamma), self.codebook_size)
+        -> Return(quantized [..., dim], indices int64 [...], aux loss).  Same arithmetic as ``forward`` from s onwards.
+        want_bf16: the kernel also writes a bf16 copy of the quantized tensor (``self.last_zq_bf16``)."""
+        out = ops.LFQScalarFn.apply(s, self.project_out.weight, self.project_out.bias, self.training,
+                                    float(inv_temperature), float(self.commitment_loss_weight),
+                                    float(self.entropy_loss_weight), float(self.diversity_gamma), self.codebook_size, bool(want_bf16))
+        zq, idx, aux, xq = out[:4]
+        self.last_zq_bf16 = out[4] if want_bf16 else None
         self.last_scalar = xq
         if not self.training:
             aux = self.zero

@@ -427,7 +427,7 @@ class LFQFn(torch.autograd.Function):
         ws = L.workspace(nws, z.device)
         L.run("lfq_fwd" if training else "lfq_fwd_eval", lib.idee_lfq_fwd, z.data_ptr(), w_in.data_ptr(), b_in.data_ptr(),
               w_out.data_ptr(), b_out.data_ptr(), zq.data_ptr(), idx.data_ptr(), xq.data_ptr(), stats.data_ptr(), ntok, dim,
-              codebook_size, int(training), inv_temp, lam_commit, lam_ent, gamma, ws.data_ptr(), nws, L.stream())
+              codebook_size, int(training), inv_temp, lam_commit, lam_ent, gamma, ws.data_ptr(), nws, None, L.stream())
         ctx.save_for_backward(z, w_in, b_in, w_out, stats)
         ctx.hyper = (inv_temp, lam_commit, lam_ent, gamma)
         ctx.training = training
@@ -467,7 +467,8 @@ class LFQScalarFn(torch.autograd.Function):
     returns the gradient w.r.t. s only; project_in's gradients flow through the producer's folded weights."""
 
     @staticmethod
-    def forward(ctx, s, w_out, b_out, training, inv_temp, lam_commit, lam_ent, gamma, codebook_size):
+    def forward(ctx, s, w_out, b_out, training, inv_temp, lam_commit, lam_ent, gamma, codebook_size, want_bf16=False):
+        """want_bf16: also return a non-differentiable bf16 copy of z_q (for consumers that round it to bf16 anyway)."""
         L.require_cuda(s)
         lib = L.load()
         s = _f32c(s)
@@ -477,20 +478,24 @@ class LFQScalarFn(torch.autograd.Function):
         idx = torch.empty(s.shape, device=s.device, dtype=torch.int64)
         xq = torch.empty(s.shape, device=s.device, dtype=torch.float32)
         stats = torch.zeros(8, device=s.device, dtype=torch.float32)
+        zq16 = torch.empty(*s.shape, 16, device=s.device, dtype=torch.bfloat16) if want_bf16 else None
         nws = lib.idee_lfq_workspace_bytes(ntok)
         ws = L.workspace(nws, s.device)
         L.run("lfq_fwd" if training else "lfq_fwd_eval", lib.idee_lfq_fwd, s.data_ptr(), None, None, w_out.data_ptr(), b_out.data_ptr(),
               zq.data_ptr(), idx.data_ptr(), xq.data_ptr(), stats.data_ptr(), ntok, 1, codebook_size, int(training), inv_temp,
-              lam_commit, lam_ent, gamma, ws.data_ptr(), nws, L.stream())
+              lam_commit, lam_ent, gamma, ws.data_ptr(), nws, L.ptr(zq16), L.stream())
         ctx.save_for_backward(s, w_out, stats)
         ctx.hyper = (inv_temp, lam_commit, lam_ent, gamma)
         ctx.training = training
-        ctx.mark_non_differentiable(idx)
         ctx.set_materialize_grads(False)
+        if want_bf16:
+            ctx.mark_non_differentiable(idx, zq16)
+            return zq, idx, stats[0], xq, zq16
+        ctx.mark_non_differentiable(idx)
         return zq, idx, stats[0], xq
 
     @staticmethod
-    def backward(ctx, gzq, _gidx, gaux, gxq):
+    def backward(ctx, gzq, _gidx, gaux, gxq, *_unused):
         lib = L.load()
         s, w_out, stats = ctx.saved_tensors
         inv_temp, lam_commit, lam_ent, gamma = ctx.hyper
@@ -508,7 +513,7 @@ class LFQScalarFn(torch.autograd.Function):
               w_out.data_ptr(), gs.data_ptr(), grads.data_ptr(), ntok, inv_temp, lam_commit, lam_ent, gamma, ws.data_ptr(), nws, L.stream())
         if not ctx.training:
             gs = torch.zeros_like(s)
-        return gs, grads[17:33].view(16, 1), grads[33:49], None, None, None, None, None, None
+        return gs, grads[17:33].view(16, 1), grads[33:49], None, None, None, None, None, None, None
 
 
 # ----------------------------------------------------------------------------------------------------------------

@@ -135,7 +135,7 @@ size_t idee_lfq_workspace_bytes(int64_t ntok);
 int idee_lfq_fwd(const float* z, const float* w_in, const float* b_in, const float* w_out, const float* b_out,
                  float* zq, int64_t* indices, float* xq, float* stats, int64_t ntok, int dim, int codebook_size, int training,
                  float inv_temperature, float lambda_commit, float lambda_entropy, float diversity_gamma,
-                 void* workspace, size_t workspace_bytes, void* stream);
+                 void* workspace, size_t workspace_bytes, void* zq_bf16 /* optional bf16 copy of zq, may be NULL */, void* stream);
 int idee_lfq_bwd(const float* z, const float* gzq, const float* gxq, const float* g_aux, const float* stats, const float* w_in,
                  const float* b_in, const float* w_out, float* gz, float* grads, int64_t ntok, float inv_temperature,
                  float lambda_commit, float lambda_entropy, float diversity_gamma,
