@@ -168,18 +168,22 @@ anomaly_l1_bwd_kernel(AnomP p, const float* __restrict__ out, const float* __res
 __global__ void __launch_bounds__(AT)
 anomaly_rank1_fwd_kernel(const float* __restrict__ xq, const float* __restrict__ mask, int N, int V, int T, int64_t HW,
                          double* __restrict__ partials) {
+    // grid = (blocks, N): a block strides over the V*T*HW tokens of one sample with 32-bit indices (no 64-bit divisions)
     __shared__ double red[32];
-    const int64_t per_n = (int64_t)V * T * HW, ntok = (int64_t)N * per_n;
+    const int n = blockIdx.y;
+    const uint32_t hw = (uint32_t)HW, per_n = (uint32_t)(V * T) * hw;
+    const float* xn = xq + (int64_t)n * per_n;
+    const float* mn = mask + (int64_t)n * HW;
     double cp = 0.0, cm = 0.0, wsum = 0.0;
-    for (int64_t tok = (int64_t)blockIdx.x * AT + threadIdx.x; tok < ntok; tok += (int64_t)gridDim.x * AT) {
-        const int64_t n = tok / per_n, r = tok - n * per_n, hw = r % HW;
-        const float m = __ldg(mask + n * HW + hw);
-        if (r < HW) wsum += (double)(1.f - m);
+    for (uint32_t r = blockIdx.x * AT + threadIdx.x; r < per_n; r += gridDim.x * AT) {
+        const float m = __ldg(mn + r % hw);
+        if (r < hw) wsum += (double)(1.f - m);
         if (m == 1.f) continue;
-        if (__ldg(xq + tok) > 0.f) cp += (double)(1.f - m); else cm += (double)(1.f - m);
+        if (__ldg(xn + r) > 0.f) cp += (double)(1.f - m); else cm += (double)(1.f - m);
     }
     cp = block_sum_d(cp, red); cm = block_sum_d(cm, red); wsum = block_sum_d(wsum, red);
-    if (threadIdx.x == 0) { partials[3 * blockIdx.x] = cp; partials[3 * blockIdx.x + 1] = cm; partials[3 * blockIdx.x + 2] = wsum; }
+    const int b = blockIdx.y * gridDim.x + blockIdx.x;
+    if (threadIdx.x == 0) { partials[3 * b] = cp; partials[3 * b + 1] = cm; partials[3 * b + 2] = wsum; }
 }
 // out: {loss, total weight = sum(1-m) * V*C*T, count(+1), count(-1)}
 __global__ void anomaly_rank1_finalize_kernel(const double* __restrict__ partials, int nblocks, int V, int T, const float* __restrict__ w_out,
@@ -209,7 +213,7 @@ anomaly_rank1_bwd_kernel(const float* __restrict__ xq, const float* __restrict__
         gp += dp > 0.f ? w : (dp < 0.f ? -w : 0.f);
         gm += dm > 0.f ? w : (dm < 0.f ? -w : 0.f);
     }
-    if (blockIdx.x == 0 && threadIdx.x < 16) {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 16) {
         const int c = threadIdx.x;
         const float w = w_out[c], b = b_out[c], v = vq0[c], cp = out[2], cm = out[3];
         const float dp = (w + b) - v, dm = (-w + b) - v;
@@ -217,11 +221,14 @@ anomaly_rank1_bwd_kernel(const float* __restrict__ xq, const float* __restrict__
         gw[c] = scale * (cp * sp - cm * sm);            // d z_q[c] / d w_out[c] = x
         gb[c] = scale * (cp * sp + cm * sm);
     }
-    const int64_t per_n = (int64_t)V * T * HW, ntok = (int64_t)N * per_n;
-    for (int64_t tok = (int64_t)blockIdx.x * AT + threadIdx.x; tok < ntok; tok += (int64_t)gridDim.x * AT) {
-        const int64_t n = tok / per_n, r = tok - n * per_n, hw = r % HW;
-        const float m = __ldg(mask + n * HW + hw);
-        gxq[tok] = m == 1.f ? 0.f : scale * (1.f - m) * (__ldg(xq + tok) > 0.f ? gp : gm);
+    const int n = blockIdx.y;
+    const uint32_t hw = (uint32_t)HW, per_n = (uint32_t)(V * T) * hw;
+    const float* xn = xq + (int64_t)n * per_n;
+    const float* mn = mask + (int64_t)n * HW;
+    float* gn = gxq + (int64_t)n * per_n;
+    for (uint32_t r = blockIdx.x * AT + threadIdx.x; r < per_n; r += gridDim.x * AT) {
+        const float m = __ldg(mn + r % hw);
+        gn[r] = m == 1.f ? 0.f : scale * (1.f - m) * (__ldg(xn + r) > 0.f ? gp : gm);
     }
 }
 
@@ -291,17 +298,21 @@ extern "C" int idee_anomaly_l1_bwd(const float* zq, const float* mask, const flo
     return 0;
 }
 
-extern "C" size_t idee_anomaly_rank1_workspace_bytes(int64_t ntok) { return sizeof(double) * 3 * (size_t)anom_blocks(ntok); }
+// one partial triple per (block, sample); a few thousand spare slots cover tiny inputs whose sample count exceeds the block cap
+extern "C" size_t idee_anomaly_rank1_workspace_bytes(int64_t ntok) { return sizeof(double) * 3 * ((size_t)anom_blocks(ntok) + 4096); }
 
 extern "C" int idee_anomaly_rank1_fwd(const float* xq, const float* mask, const float* w_out, const float* b_out, const float* vq0, int N,
                                       int V, int T, int64_t HW, int C, float* out, void* workspace, size_t workspace_bytes, void* stream) {
     IDEE_REQUIRE(C == 16, "anomaly_rank1: only C=16 is built (got %d)", C);
     const int64_t ntok = (int64_t)N * V * T * HW;
     IDEE_REQUIRE(workspace_bytes >= idee_anomaly_rank1_workspace_bytes(ntok), "anomaly_rank1_fwd: workspace too small");
-    const int nb = anom_blocks(ntok);
-    anomaly_rank1_fwd_kernel<<<nb, AT, 0, (cudaStream_t)stream>>>(xq, mask, N, V, T, HW, (double*)workspace);
+    IDEE_REQUIRE((int64_t)V * T * HW < (1ll << 31) && N <= 65535, "anomaly_rank1: sample too large for 32-bit token indices");
+    int bx = anom_blocks(ntok) / N;
+    if (bx < 1) bx = 1;
+    IDEE_REQUIRE((size_t)bx * N <= (size_t)anom_blocks(ntok) + 4096, "anomaly_rank1_fwd: too many samples for the partial buffer");
+    anomaly_rank1_fwd_kernel<<<dim3(bx, N), AT, 0, (cudaStream_t)stream>>>(xq, mask, N, V, T, HW, (double*)workspace);
     IDEE_LAUNCH_CHECK("anomaly_rank1_fwd");
-    anomaly_rank1_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const double*)workspace, nb, V, T, w_out, b_out, vq0, out);
+    anomaly_rank1_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const double*)workspace, bx * N, V, T, w_out, b_out, vq0, out);
     IDEE_LAUNCH_CHECK("anomaly_rank1_finalize");
     return 0;
 }
@@ -311,8 +322,11 @@ extern "C" int idee_anomaly_rank1_bwd(const float* xq, const float* mask, const 
                                       float* gb, void* stream) {
     IDEE_REQUIRE(C == 16, "anomaly_rank1: only C=16 is built (got %d)", C);
     const int64_t ntok = (int64_t)N * V * T * HW;
-    anomaly_rank1_bwd_kernel<<<anom_blocks(ntok), AT, 0, (cudaStream_t)stream>>>(xq, mask, N, V, T, HW, w_out, b_out, vq0, out, g_loss, gxq,
-                                                                              gw, gb);
+    IDEE_REQUIRE((int64_t)V * T * HW < (1ll << 31) && N <= 65535, "anomaly_rank1: sample too large for 32-bit token indices");
+    int bx = anom_blocks(ntok) / N;
+    if (bx < 1) bx = 1;
+    anomaly_rank1_bwd_kernel<<<dim3(bx, N), AT, 0, (cudaStream_t)stream>>>(xq, mask, N, V, T, HW, w_out, b_out, vq0, out, g_loss, gxq,
+                                                                        gw, gb);
     IDEE_LAUNCH_CHECK("anomaly_rank1_bwd");
     return 0;
 }
