@@ -247,3 +247,43 @@ extern "C" int idee_lfq_bwd(const float* z, const float* gzq, const float* gxq, 
     IDEE_LAUNCH_CHECK("lfq_bwd_finalize");
     return 0;
 }
+
+// ---- scalar planes of the rank-1 form -> one 16-channel channel-last image (input of the joint head's folded first conv) ----
+// planes[n, p, c] = xq[n, c, p] for c < V, 1 for c == V, 0 above: one pixel (64 B, two 256-bit stores) per thread, the V scalar reads
+// are coalesced across the warp.  The backward gathers the first V channels of the image gradient back into scalar planes.
+__global__ void __launch_bounds__(256) rank1_planes_fwd_kernel(const float* __restrict__ xq, float* __restrict__ planes, int V, uint32_t THW) {
+    const uint32_t p = blockIdx.x * 256u + threadIdx.x;
+    if (p >= THW) return;
+    const float* src = xq + (size_t)blockIdx.y * V * THW + p;
+    float r[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) r[c] = c < V ? __ldg(src + (size_t)c * THW) : (c == V ? 1.f : 0.f);
+    float* dst = planes + ((size_t)blockIdx.y * THW + p) * 16;
+    st8f(dst, r);
+    st8f(dst + 8, r + 8);
+}
+__global__ void __launch_bounds__(256) rank1_planes_bwd_kernel(const float* __restrict__ gplanes, float* __restrict__ gxq, int V, uint32_t THW) {
+    const uint32_t p = blockIdx.x * 256u + threadIdx.x;
+    if (p >= THW) return;
+    const float* src = gplanes + ((size_t)blockIdx.y * THW + p) * 16;
+    float r[16];
+    ldg8f(r, src);
+    if (V > 8) ldg8f(r + 8, src + 8);
+    float* dst = gxq + (size_t)blockIdx.y * V * THW + p;
+#pragma unroll
+    for (int c = 0; c < 15; ++c)
+        if (c < V) dst[(size_t)c * THW] = r[c];
+}
+
+extern "C" int idee_rank1_planes_fwd(const float* xq, float* planes, int N, int V, int64_t THW, void* stream) {
+    IDEE_REQUIRE(V >= 1 && V <= 15 && THW > 0 && THW < (1ll << 31) && N >= 1 && N <= 65535, "rank1_planes_fwd: need 1 <= V <= 15, THW < 2^31, N <= 65535");
+    rank1_planes_fwd_kernel<<<dim3((unsigned)((THW + 255) / 256), N), 256, 0, (cudaStream_t)stream>>>(xq, planes, V, (uint32_t)THW);
+    IDEE_LAUNCH_CHECK("rank1_planes_fwd");
+    return 0;
+}
+extern "C" int idee_rank1_planes_bwd(const float* gplanes, float* gxq, int N, int V, int64_t THW, void* stream) {
+    IDEE_REQUIRE(V >= 1 && V <= 15 && THW > 0 && THW < (1ll << 31) && N >= 1 && N <= 65535, "rank1_planes_bwd: need 1 <= V <= 15, THW < 2^31, N <= 65535");
+    rank1_planes_bwd_kernel<<<dim3((unsigned)((THW + 255) / 256), N), 256, 0, (cudaStream_t)stream>>>(gplanes, gxq, V, (uint32_t)THW);
+    IDEE_LAUNCH_CHECK("rank1_planes_bwd");
+    return 0;
+}

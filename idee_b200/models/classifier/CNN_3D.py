@@ -114,7 +114,7 @@ class CNN_3D(nn.Module):
         differentiable torch ops, so gradients reach conv1.weight, project_out.weight and project_out.bias through autograd."""
         N, V, T, H, W = xq.shape
         Co, C = self.dim, self.var_embed_dim
-        planes = torch.cat([xq.permute(0, 2, 3, 4, 1), xq.new_ones(N, T, H, W, 1), xq.new_zeros(N, T, H, W, 15 - V)], dim=-1)
+        planes = ops.Rank1Planes.apply(xq)                    # [N,T,H,W,16]: V scalar planes | ones | zeros
         W5 = self.conv1.weight.view(Co, V, C, 2, 3, 3)
         Wq = torch.einsum('ovcthw,c->ovthw', W5, w_out.reshape(-1))
         Wb = torch.einsum('ovcthw,c->othw', W5, b_out.reshape(-1))

@@ -634,6 +634,31 @@ class AnomalyRank1(torch.autograd.Function):
         return gxq, gw.view(ctx.shapes[0]), gb.view(ctx.shapes[1]), None, None
 
 
+class Rank1Planes(torch.autograd.Function):
+    """xq [N,V,T,H,W] -> planes [N,T,H,W,16] (channel v < V = xq_v, channel V = 1, rest 0): the image the joint classifier's folded
+    first conv reads (CNN_3D._joint_conv1_rank1).  One pass each way instead of a cat of three strided copies."""
+
+    @staticmethod
+    def forward(ctx, xq):
+        L.require_cuda(xq)
+        lib = L.load()
+        xq = _f32c(xq)
+        N, V, T, H, W = xq.shape
+        planes = torch.empty(N, T, H, W, 16, device=xq.device, dtype=torch.float32)
+        L.run("rank1_planes_fwd", lib.idee_rank1_planes_fwd, xq.data_ptr(), planes.data_ptr(), N, V, T * H * W, L.stream())
+        ctx.shape = xq.shape
+        return planes
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = L.load()
+        N, V, T, H, W = ctx.shape
+        g = _f32c(g)
+        gxq = torch.empty(ctx.shape, device=g.device, dtype=torch.float32)
+        L.run("rank1_planes_bwd", lib.idee_rank1_planes_bwd, g.data_ptr(), gxq.data_ptr(), N, V, T * H * W, L.stream())
+        return gxq
+
+
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step):
     lib = L.load()
     L.run("adam_step", lib.idee_adam_step, p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2, eps,

@@ -164,6 +164,13 @@ int idee_anomaly_rank1_bwd(const float* xq, const float* mask, const float* w_ou
                            int T, int64_t HW, int C, const float* out, const float* g_loss, float* gxq, float* gw, float* gb,
                            void* stream);
 
+/* The V scalar planes xq [N,V,THW] of the rank-1 form as one 16-channel channel-last image planes [N,THW,16]: channel v < V = xq_v,
+ * channel V = 1 (carries the project_out bias through the zero-padded border), channels above = 0 -- the input of the joint
+ * classifier's first conv (classifier/CNN_3D.py:77,118) once project_out (LFQ.py:284) is folded into its weights.
+ * The backward gathers channels 0..V-1 of the image gradient into gxq [N,V,THW].  1 <= V <= 15. */
+int idee_rank1_planes_fwd(const float* xq, float* planes, int N, int V, int64_t THW, void* stream);
+int idee_rank1_planes_bwd(const float* gplanes, float* gxq, int N, int V, int64_t THW, void* stream);
+
 /* ---- optimiser: torch.optim.Adam(lr, betas, eps, weight_decay) on one flat buffer        train_synthetic.py:127-129 ---- */
 int idee_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                    float weight_decay, int step, void* stream);

@@ -133,3 +133,18 @@ def test_anomaly_rank1_matches_full_loss():
     assert abs(float(loss1) - float(want)) <= 1e-6 * abs(float(want)) and abs(float(loss1) - float(loss2)) <= 1e-6 * abs(float(loss2))
     for a, b in zip(g1, (xq.grad, w_out.grad, b_out.grad)):
         assert rel_err(a, b) < 1e-5
+
+
+@pytest.mark.parametrize("V", [1, 6, 11, 15])
+def test_rank1_planes_layout_and_gradient(V):
+    """idee_rank1_planes_fwd / _bwd against the torch statement of the same layout (bit-exact: pure data movement), ragged THW."""
+    from idee_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(V)
+    N, T, H, W = 3, 2, 7, 37
+    xq = torch.where(torch.rand(N, V, T, H, W, device="cuda", generator=g) > 0.5, 1.0, -1.0).requires_grad_(True)
+    planes = ops.Rank1Planes.apply(xq)
+    want = torch.cat([xq.detach().permute(0, 2, 3, 4, 1), xq.new_ones(N, T, H, W, 1), xq.new_zeros(N, T, H, W, 15 - V)], dim=-1)
+    assert planes.shape == (N, T, H, W, 16) and torch.equal(planes, want)
+    gp = torch.randn(N, T, H, W, 16, device="cuda", generator=g)
+    planes.backward(gp)
+    assert torch.equal(xq.grad, gp[..., :V].permute(0, 4, 1, 2, 3))
