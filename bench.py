@@ -105,13 +105,18 @@ class ClockSampler:
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, device_index):
-        self.idx, self.proc, self.lines = device_index, None, []
+    def __init__(self, device_indices):
+        """device_indices: the GPUs of the whole job (one nvidia-smi process on rank 0 polls them all: a poller per rank makes N
+        processes contend for the driver with the N launching threads), or None on the other ranks."""
+        self.idx = None if device_indices is None else ",".join(str(i) for i in device_indices)
+        self.proc, self.lines = None, []
 
     def start(self):
+        if self.idx is None:
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-i", self.idx], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
@@ -239,28 +244,33 @@ def main():
     for _ in range(args.warmup):
         trainer.step(x, me, ml)
     barrier()
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(list(range(world)) if (rank == 0 and world > 1) else [local] if rank == 0 else None)
     clocks.start()
     _lib.Profile.reset(events=False)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t_host = time.perf_counter()
     for _ in range(args.steps):
         loss, _ = trainer.step(x, me, ml)
+    host_ms = (time.perf_counter() - t_host) * 1e3 / args.steps      # host time to ENQUEUE one step (no synchronisation inside)
     e1.record()
     barrier()
     ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    host_ms = max_over_ranks(host_ms)
     launches = _lib.Profile.launches
     value = n_gpus * B / (ms_step / 1e3)
     loss_val = float(loss)
 
     # ---- end to end through the public API: pinned host inputs -> device, step, loss + logits back to the host ----
-    pred_h = torch.empty(B, 1, HW, HW, dtype=torch.float32).pin_memory()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     # every step's inputs are copied from pinned host memory inside the timed region; the copy of step i+1 runs on a side
-    # stream while step i computes (idee_b200.trainer.HostPrefetcher), the logits and the loss come back every step
-    from idee_b200.trainer import HostPrefetcher
+    # stream while step i computes (idee_b200.trainer.HostPrefetcher); every step's logits and loss come back to pinned host
+    # memory inside the timed region too, read by the host one step later so the launch queue never drains (HostResults)
+    from idee_b200.trainer import HostPrefetcher, HostResults
     pf = HostPrefetcher(dev, (x_h, me_h, ml_h))
+    res = HostResults(dev, (torch.empty(B, 1, HW, HW), torch.empty(1)))
+    host_losses = []
     e0.record()
     pf.stage(0, (x_h, me_h, ml_h))
     for i in range(args.steps):
@@ -269,10 +279,14 @@ def main():
             pf.stage((i + 1) & 1, (x_h, me_h, ml_h))
         loss, out = trainer.step(xd, med, mld)
         pf.release(i & 1)
-        pred_h.copy_(out["pred"].detach(), non_blocking=True)
-        _ = loss.item()
+        res.put(i & 1, (out["pred"], loss))
+        if i > 0:
+            host_losses.append(float(res.get((i - 1) & 1)[1]))
+    pred_h, loss_h = res.get((args.steps - 1) & 1)
+    host_losses.append(float(loss_h))
     e1.record()
     barrier()
+    assert len(host_losses) == args.steps and all(l == l for l in host_losses)
     ms_e2e = max_over_ranks(e0.elapsed_time(e1) / args.steps)
     clock_info = clocks.stop()      # sampled over both timed regions (device-resident and end-to-end), every 100 ms
     h2d = x_h.numel() * 4 + me_h.numel() * 4 + ml_h.numel() * 4
@@ -339,7 +353,7 @@ def main():
                 "data": "synthetic", "config": workload_config(args, n_gpus), "impl": "idee_b200",
                 "e2e": {"value": n_gpus * B / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e},
-                "gpu_launches": launches, "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms, "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "model_tflops_per_gpu": whole_model_tf, "loss": loss_val,
                 "inference": {"value": n_gpus * B / (ms_infer / 1e3), "unit": UNIT, "ms_per_step": ms_infer,
                               "what": "eval forward (logits + driver masks), no_grad, device-resident inputs"},

@@ -156,3 +156,28 @@ class HostPrefetcher:
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.device))
         self.free[slot] = ev
+
+
+class HostResults:
+    """Double-buffered device -> host return of a step's results (logits, loss) without draining the launch queue.
+
+    The reference reads ``loss.item()`` right after every step (train_synthetic.py:176-186), which leaves the GPU idle while the
+    host enqueues the next step.  Here step i's results are copied into pinned host slot i & 1 behind the step on the compute
+    stream (``put``), and the host reads them (``get``) one step later, after step i+1 has been enqueued: every step's results
+    still reach the host, the copies just overlap the next step's launches."""
+
+    def __init__(self, device, example_results):
+        self.device = torch.device(device)
+        self.slots = [[torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in example_results] for _ in range(2)]
+        self.done = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def put(self, slot: int, results):
+        """Enqueue the device -> host copies of ``results`` into ``slot`` on the current stream; returns immediately."""
+        for dst, src in zip(self.slots[slot], results):
+            dst.copy_(src.detach().reshape(dst.shape), non_blocking=True)
+        self.done[slot].record(torch.cuda.current_stream(self.device))
+
+    def get(self, slot: int):
+        """Pinned host tensors of ``slot`` (blocks until its copies have landed)."""
+        self.done[slot].synchronize()
+        return self.slots[slot]

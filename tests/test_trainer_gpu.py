@@ -88,3 +88,23 @@ def test_host_prefetcher_delivers_every_batch_in_order():
         pf.release(i & 1)
     torch.cuda.synchronize()
     assert [float(s) for s in sums] == [2.0 * i for i in range(len(batches))]
+
+
+def test_host_results_return_every_step_one_step_late():
+    """Pipelined device -> host results: step i's values are read after step i+1 has been enqueued and are never overwritten early."""
+    from idee_b200.trainer import HostResults
+    dev = torch.device("cuda", 0)
+    res = HostResults(dev, (torch.empty(1 << 18), torch.empty(1)))
+    got, steps = [], 7
+    for i in range(steps):
+        big = torch.full((1 << 18,), float(i), device=dev)
+        for _ in range(10):
+            big = big * 1.0 + 0.0
+        res.put(i & 1, (big, big.sum().reshape(1) / big.numel()))
+        if i > 0:
+            a, b = res.get((i - 1) & 1)
+            got.append((float(a[0]), float(a[-1]), float(b)))
+    a, b = res.get((steps - 1) & 1)
+    got.append((float(a[0]), float(a[-1]), float(b)))
+    assert got == [(float(i),) * 3 for i in range(steps)]
+    assert a.is_pinned()
