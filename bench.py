@@ -156,11 +156,13 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------------
 # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the Swin entry points, captured with `ncu --set full`
 # inside this very command at the benchmark shape; source: profiles/r01_ncu/prof_final_v57_swin_raw.csv.gz
-# (backward = MLP half + attention half; "+embed" = first block with the patch embedding fused in)
+# (backward = MLP half + attention half; "+embed" = first block with the patch embedding fused in); re-captured at HEAD in
+# profiles/r01_ncu/prof_final_v75_swin_raw.csv.gz (first ten Swin launches of a step: same bytes, shifted-window attention backward
+# 1.101 GB written instead of 1.213)
 NCU_TRAFFIC = {
     "swin_block_bwd[w(2, 4, 4) s(0, 0, 0) +embed]": (1.967 + 0.977 + 1.045 + 0.046) * 1e9,
-    "swin_block_bwd[w(2, 4, 4) s(1, 2, 2)]": (1.967 + 0.977 + 1.967 + 1.213) * 1e9,
-    "swin_block_bwd[w(8, 1, 1) s(0, 0, 0)]": (1.967 + 0.977 + 1.978 + 0.995) * 1e9,
+    "swin_block_bwd[w(2, 4, 4) s(1, 2, 2)]": (1.967 + 0.975 + 1.967 + 1.101) * 1e9,
+    "swin_block_bwd[w(8, 1, 1) s(0, 0, 0)]": (1.967 + 0.977 + 1.974 + 0.978) * 1e9,
     "swin_block_fwd[w(2, 4, 4) s(0, 0, 0) +embed]": (0.065 + 1.907) * 1e9,
     "swin_block_fwd[w(2, 4, 4) s(1, 2, 2)]": (0.984 + 1.911) * 1e9,
     "swin_block_fwd[w(8, 1, 1) s(0, 0, 0)]": (0.983 + 1.426) * 1e9,
