@@ -40,6 +40,7 @@ def parse_args():
                     help="bf16: tensor-core operands + fp32 accumulate for the GEMM-shaped kernels; fp32: exact CUDA-core path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
     return ap.parse_args()
 
 
@@ -83,6 +84,59 @@ def cpu_model_name():
     return "unknown"
 
 
+def gpu_reference_baseline(dev, hw, batches=(8, 4, 2, 1), steps=3, warmup=1):
+    """The incumbent on the SAME box: the reference algorithm as stock PyTorch ops
+    (ATen / cuDNN / cuBLAS kernels; the oracle port moved to the GPU) -- fp32 with TF32 off, and torch.autocast(bf16).  Forward +
+    losses + backward, CUDA-event timed, largest batch of `batches` that fits.  A reported baseline: none of this repo's kernels
+    run here."""
+    from oracle import idee_oracle as O
+    cfg = O.OracleConfig()
+    out = {}
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        for mode in ("fp32", "bf16_autocast"):
+            res = None
+            for B in batches:
+                try:
+                    sd = {k: v.to(dev).requires_grad_(True) for k, v in O.make_state_dict(cfg, seed=0, kind="reference").items()}
+                    x, me, ml = (t.to(dev) for t in O.make_inputs(cfg, B, 8, hw, hw, seed=0))
+                    times = []
+                    for it in range(warmup + steps):
+                        for p_ in sd.values():
+                            p_.grad = None
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode != "fp32")):
+                            total, _ = O.train_step_loss(sd, x, me, ml, cfg)
+                        total.backward()
+                        e1.record()
+                        torch.cuda.synchronize()
+                        times.append(e0.elapsed_time(e1))
+                    ms = statistics.median(times[warmup:])
+                    res = {"value": B / (ms / 1e3), "unit": UNIT, "batch": B, "ms_per_step": ms, "loss": float(total.detach()),
+                           "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9}
+                    break
+                except torch.cuda.OutOfMemoryError:
+                    res = {"error": f"out of memory at batch {B}"}
+                except Exception as e:                                    # never take the benchmark line down with the baseline
+                    res = {"error": f"{type(e).__name__}: {e}"[:300]}
+                    break
+                finally:
+                    sd = x = me = ml = total = None
+                    import gc
+                    gc.collect()
+                    torch.cuda.empty_cache()
+                    torch.cuda.reset_peak_memory_stats(dev)
+            out[mode] = res
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+    out["what"] = ("reference algorithm as stock PyTorch ops on this GPU (oracle port on cuda: ATen/cuDNN/cuBLAS kernels), "
+                   "fwd + losses + bwd, no optimiser; fp32 = TF32 off")
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -93,6 +147,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp32", "data": "synthetic", "config": workload_config(args, args.gpus),
+            "reference": {"batch_per_step": 1, "optimizer_in_step": False,
+                          "note": "the CPU arm times B=1 samples of the config's workload (fwd + losses + bwd); samples/s is batch-independent here"},
             "cpu_baseline": {"value": sps, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
             "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -154,23 +210,45 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------------
 # algorithmic work of the entry points (for the roofline of the dominant kernel)
 # ------------------------------------------------------------------------------------------------------------------
-# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the Swin entry points, captured with `ncu --set full`
-# inside this very command at the benchmark shape; source: profiles/r01_ncu/prof_final_v57_swin_raw.csv.gz
-# (backward = MLP half + attention half; "+embed" = first block with the patch embedding fused in); re-captured at HEAD in
-# profiles/r01_ncu/prof_final_v75_swin_raw.csv.gz (first ten Swin launches of a step: same bytes, shifted-window attention backward
-# 1.101 GB written instead of 1.213)
-NCU_TRAFFIC = {
-    "swin_block_bwd[w(2, 4, 4) s(0, 0, 0) +embed]": (1.967 + 0.977 + 1.045 + 0.046) * 1e9,
-    "swin_block_bwd[w(2, 4, 4) s(1, 2, 2)]": (1.967 + 0.975 + 1.967 + 1.101) * 1e9,
-    "swin_block_bwd[w(8, 1, 1) s(0, 0, 0)]": (1.967 + 0.977 + 1.974 + 0.978) * 1e9,
-    "swin_block_fwd[w(2, 4, 4) s(0, 0, 0) +embed]": (0.065 + 1.907) * 1e9,
-    "swin_block_fwd[w(2, 4, 4) s(1, 2, 2)]": (0.984 + 1.911) * 1e9,
-    "swin_block_fwd[w(8, 1, 1) s(0, 0, 0)]": (0.983 + 1.426) * 1e9,
-}
+# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernels behind an entry point, from the newest
+# profiles/r*_ncu_traffic.json -- a summary generated by tools/ncu_traffic.py from the committed `ncu --set full` capture of this
+# very command at the benchmark shape (the file names its source CSV and commit).
+def _load_traffic():
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_traffic.json")))
+    if not files:
+        return None, None
+    try:
+        return json.load(open(files[-1])), os.path.relpath(files[-1], ROOT)
+    except (OSError, ValueError):
+        return None, None
+
+
+def entry_kernels(name):
+    """Kernel (short) names launched by a Swin entry point label such as 'swin_block_bwd[w(2, 4, 4) s(1, 2, 2) +embed]'."""
+    import re
+    m = re.search(r"w\((\d+), (\d+), (\d+)\)", name)
+    if not m or not name.startswith("swin_block"):
+        return []
+    w = ",".join(m.groups())
+    emb = "1" if "+embed" in name else "0"
+    G = int(m.group(1)) * int(m.group(2)) * int(m.group(3))
+    if "fwd" in name:
+        return [f"swin_fwd_tc_kernel<{w},{emb}>", f"swin_fwd_umma_kernel<{w},{emb}>"]
+    return ["swin_mlp_bwd_tc_kernel", f"swin_attn_bwd_tc_kernel<{w},{emb}>", f"swin_grad_finalize_kernel<{G}>",
+            f"swin_bwd_umma_kernel<{w},{emb}>"]
 
 
 def ncu_traffic(name):
-    return NCU_TRAFFIC.get(name)
+    """(bytes per call of the entry point, source file) or (None, None) when no capture covers it."""
+    data, src = _load_traffic()
+    if not data:
+        return None, None
+    ks = data.get("kernels", {})
+    found = [ks[k]["dram_bytes"] for k in entry_kernels(name) if k in ks and "dram_bytes" in ks[k]]
+    if not found:
+        return None, None
+    return float(sum(found)), f"{src} <- {data.get('source')} @ {data.get('commit')}"
 
 
 def op_flops(name, B, V, T, H, W):
@@ -271,7 +349,9 @@ def main():
     # memory inside the timed region too, read by the host one step later so the launch queue never drains (HostResults)
     from idee_b200.trainer import HostPrefetcher, HostResults
     pf = HostPrefetcher(dev, (x_h, me_h, ml_h))
-    res = HostResults(dev, (torch.empty(B, 1, HW, HW), torch.empty(1)))
+    # ... together with the driver mask `anomaly` (train_synthetic.py:215 pulls it every step), as uint8 instead of the reference's
+    # int64 (values are 0/1; 15 MB instead of 123 MB over PCIe)
+    res = HostResults(dev, (torch.empty(B, 1, HW, HW), torch.empty(1), torch.empty(B, 6, 8, HW, HW, dtype=torch.uint8)))
     host_losses = []
     e0.record()
     pf.stage(0, (x_h, me_h, ml_h))
@@ -281,10 +361,10 @@ def main():
             pf.stage((i + 1) & 1, (x_h, me_h, ml_h))
         loss, out = trainer.step(xd, med, mld)
         pf.release(i & 1)
-        res.put(i & 1, (out["pred"], loss))
+        res.put(i & 1, (out["pred"], loss, out["anomaly"]))
         if i > 0:
             host_losses.append(float(res.get((i - 1) & 1)[1]))
-    pred_h, loss_h = res.get((args.steps - 1) & 1)
+    pred_h, loss_h, anomaly_h = res.get((args.steps - 1) & 1)
     host_losses.append(float(loss_h))
     e1.record()
     barrier()
@@ -292,7 +372,7 @@ def main():
     ms_e2e = max_over_ranks(e0.elapsed_time(e1) / args.steps)
     clock_info = clocks.stop()      # sampled over both timed regions (device-resident and end-to-end), every 100 ms
     h2d = x_h.numel() * 4 + me_h.numel() * 4 + ml_h.numel() * 4
-    d2h = pred_h.numel() * 4 + 4
+    d2h = pred_h.numel() * 4 + 4 + anomaly_h.numel()
 
     # ---- inference throughput (eval mode, no_grad), same inputs, device resident ----
     model.eval()
@@ -310,7 +390,7 @@ def main():
     model.train()
 
     # ---- per-entry-point CUDA-event profile (same workload, same stream) for the roofline of the dominant kernel ----
-    roofline, breakdown = None, None
+    roofline, breakdown, executed_gflop = None, None, None
     if not args.no_profile:
         prof_steps = max(2, min(args.steps, 5))
         barrier()
@@ -323,6 +403,9 @@ def main():
         tot = sum(t for _, t in summ.values())
         top = sorted(summ.items(), key=lambda kv: -kv[1][1])
         breakdown = [{"op": k, "calls_per_step": c / prof_steps, "ms_per_step": t / prof_steps, "share": t / tot} for k, (c, t) in top[:40]]
+        # FLOPs the launched kernels actually execute per sample (the rank-1 joint conv1 and the folded 16->1 conv delete work the
+        # reference performs; the 571.98 GFLOP figure above counts the reference's)
+        executed_gflop = sum((op_flops(k, B, 6, 8, HW, HW) or 0) * c / prof_steps for k, (c, t) in summ.items()) / B / 1e9
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -334,9 +417,9 @@ def main():
             if fl is not None:
                 avg_ms = t / c
                 ach = fl / (avg_ms * 1e-3) / 1e12
+                traffic, traffic_src = ncu_traffic(k) if (B, HW) == (8, 200) else (None, None)
                 roofline = {"kernel": k, "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                            "traffic": ncu_traffic(k) if (B, HW) == (8, 200) else None,
-                            "traffic_source": "profiles/r01_ncu/prof_final_v57_swin_raw.csv.gz (ncu --set full of this command)" if ncu_traffic(k) and (B, HW) == (8, 200) else None,
+                            "traffic": traffic, "traffic_source": traffic_src,
                             "avg_ms_per_launch": avg_ms, "flops_per_launch": fl, "share_of_step": t / tot,
                             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s (of fallback)",
                             "note": "algorithmic FLOPs (2*MAC, no recompute/padding credit) against the dense bf16 tensor-core peak"}
@@ -349,6 +432,11 @@ def main():
             cpu_baseline = {"value": sps, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                             "sample": f"B=1 sample of the same workload, fwd+losses+bwd fp32, median of 2 steps after 1 warm-up "
                                       f"({sec:.2f} s/step), {cpu_model_name()}"}
+        gpu_baseline = None
+        if n_gpus == 1 and not args.no_gpu_baseline:
+            del trainer, model
+            torch.cuda.empty_cache()
+            gpu_baseline = gpu_reference_baseline(dev, HW)
         whole_model_tf = value / n_gpus * FLOP_FWD_BWD_PER_SAMPLE / 1e12
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision,
@@ -356,7 +444,8 @@ def main():
                 "e2e": {"value": n_gpus * B / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e},
                 "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms, "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "model_tflops_per_gpu": whole_model_tf, "loss": loss_val,
+                "gpu_baseline": gpu_baseline,
+                "model_tflops_per_gpu": whole_model_tf, "executed_gflop_per_sample": executed_gflop, "loss": loss_val,
                 "inference": {"value": n_gpus * B / (ms_infer / 1e3), "unit": UNIT, "ms_per_step": ms_infer,
                               "what": "eval forward (logits + driver masks), no_grad, device-resident inputs"},
                 "algorithmic_shortcuts": "exact algebraic rewrites, all parity-tested: joint classifier conv1 and the anomaly loss evaluated "

@@ -70,8 +70,22 @@ def library_path() -> str:
     return _build.LIB
 
 
+def header_version() -> int:
+    """IDEE_B200_VERSION of include/idee_b200.h: bumped on every ABI change (argument lists, descriptor structs)."""
+    import re
+    with open(os.path.join(_build.INCLUDE, "idee_b200.h")) as fh:
+        m = re.search(r"#define\s+IDEE_B200_VERSION\s+(\d+)", fh.read())
+    if m is None:
+        raise RuntimeError("include/idee_b200.h does not define IDEE_B200_VERSION")
+    return int(m.group(1))
+
+
 def load(build_if_missing: bool = True):
-    """Load (building in-tree with nvcc if needed) libidee_b200.so and declare every prototype."""
+    """Load (building in-tree with nvcc if needed) libidee_b200.so and declare every prototype.
+
+    A stale library is never bound to the current prototypes: if the sources changed and the rebuild fails, the error is
+    raised (the old binary is only used when its build stamp matches the sources), and the library's idee_version() must
+    equal the header's IDEE_B200_VERSION."""
     global _lib
     with _lock:
         if _lib is not None:
@@ -83,12 +97,19 @@ def load(build_if_missing: bool = True):
             except Exception as e:
                 if not os.path.exists(path):
                     raise RuntimeError(f"{path} is missing and could not be built ({e}); there is no fallback path") from e
+                if not _build.up_to_date():
+                    raise RuntimeError(f"{path} is older than its sources and could not be rebuilt ({e}); refusing to bind the "
+                                       f"current prototypes to a stale binary") from e
         if not os.path.exists(path):
             raise RuntimeError(f"{path} is missing: run `python -m idee_b200.build` (needs nvcc); there is no fallback path")
         lib = C.CDLL(path)
         for name, (res, args) in _SIGS.items():
             fn = getattr(lib, name)   # AttributeError if the symbol is not exported
             fn.restype, fn.argtypes = res, args
+        want = header_version()
+        if lib.idee_version() != want:
+            raise RuntimeError(f"{path} reports ABI version {lib.idee_version()}, include/idee_b200.h declares {want}: rebuild with "
+                               f"`python -m idee_b200.build --force`")
         _lib = lib
         return lib
 
@@ -107,16 +128,9 @@ if PRECISION not in ("fp32", "bf16"):
     raise ValueError("IDEE_B200_PRECISION must be fp32 or bf16")
 
 
-# route the dense 96->96 classifier convs through the tcgen05/TMEM kernel (bf16 mode only)
-UMMA = os.environ.get("IDEE_B200_UMMA", "0") == "1"
 # tcgen05 + TMEM kernel for the bf16-storage 16 -> 16 proj conv (forward + data gradient), bf16 mode only; on by default
 # (measured 9 % faster than the mma.sync kernel on the forward conv), IDEE_B200_UMMA16=0 selects the mma.sync kernel
 UMMA16 = os.environ.get("IDEE_B200_UMMA16", "1") == "1"
-
-
-def set_umma(on: bool) -> None:
-    global UMMA
-    UMMA = bool(on)
 
 
 # warp-specialised tcgen05 + TMEM kernel for the dense 96 -> 96 classifier conv (forward + data gradient), bf16 mode only;
@@ -169,7 +183,8 @@ class Profile:
 
 
 def run(what: str, fn, *args, tag=None):
-    """Call one C-ABI entry point on the current stream; raise on a non-zero return code."""
+    """Call one C-ABI entry point on the current stream of the CURRENT device; raise on a non-zero return code.
+    Callers pass ``stream()`` and tensors validated by ``require_cuda`` (all on the current device)."""
     Profile.launches += LAUNCHES[what]
     if Profile.events:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -191,9 +206,18 @@ def ptr(t):
 
 
 def require_cuda(*tensors):
+    """Every tensor of a call must live on the CURRENT CUDA device: the kernels launch on the current device's stream with raw
+    pointers, so a tensor on another GPU (model.to('cuda:1') without torch.cuda.set_device(1), nn.DataParallel replicas that
+    share the packed parameters of device 0) would be dereferenced on the wrong device."""
+    cur = torch.cuda.current_device() if torch.cuda.is_available() else -1
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("idee_b200 kernels run on CUDA tensors only (there is no CPU path); got a %s tensor" % t.device)
+        if t.device.index != cur:
+            raise RuntimeError(f"idee_b200: tensor on {t.device} but the current device is cuda:{cur}; call torch.cuda.set_device() "
+                               f"(one process per GPU, see idee_b200.trainer). nn.DataParallel is not supported: use Trainer/torchrun")
 
 
 def workspace(nbytes: int, device) -> torch.Tensor:

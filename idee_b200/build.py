@@ -20,7 +20,7 @@ LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "libidee_b200.so")
 INCLUDE = os.path.join(ROOT, "include")
 
-SOURCES = ["api.cu", "embed.cu", "swin_block.cu", "conv.cu", "conv_tc.cu", "conv_umma.cu", "conv16_umma.cu", "conv96_umma.cu", "lfq.cu", "losses.cu"]
+SOURCES = ["api.cu", "embed.cu", "swin_block.cu", "conv.cu", "conv_tc.cu", "conv16_umma.cu", "conv96_umma.cu", "lfq.cu", "losses.cu"]
 BASE_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr"]
 NVCC_FLAGS = BASE_FLAGS + ["-I", INCLUDE, "-I", CSRC]
@@ -48,6 +48,11 @@ def _fingerprint() -> str:
 def _up_to_date(fp: str) -> bool:
     stamp = os.path.join(LIBDIR, "build.stamp")
     return os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == fp
+
+
+def up_to_date() -> bool:
+    """True when the in-tree library was built from the current sources and flags."""
+    return _up_to_date(_fingerprint())
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

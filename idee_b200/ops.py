@@ -102,6 +102,7 @@ class EmbedLN(torch.autograd.Function):
         x = x if x.dtype == torch.float32 else x.float()
         N, V, Cin, T, H, W = x.shape
         w, b = wpack.tensor(), bpack.tensor()
+        L.require_cuda(w, b)
         y = torch.empty(N, V, T, H, W, 16, device=x.device, dtype=torch.float32)
         xs = (C.c_int64 * 6)(*x.stride())
         L.run("embed_ln_fwd", lib.idee_embed_ln_fwd, x.data_ptr(), C.cast(xs, C.c_void_p), w.data_ptr(), b.data_ptr(), y.data_ptr(),
@@ -155,6 +156,7 @@ class SwinBlock(torch.autograd.Function):
         lib = L.load()
         x = _f32c(x)
         flat = pack.tensor()
+        L.require_cuda(flat, rel_index)
         if lib.idee_swin_block_packed_floats(rpb_rows) != pack.P:
             raise RuntimeError("swin_block: packed parameter size mismatch")
         d = _swin_desc(x, window, shift, rpb_rows, scale, pack, heads, hidden)
@@ -210,6 +212,7 @@ class SwinBlockEmbed(torch.autograd.Function):
         assert x.dtype == torch.float32 and x.is_contiguous() and x.shape[2] == 1
         N, V, _, T, H, W = x.shape
         flat, w, b = pack.tensor(), wpack.tensor(), bpack.tensor()
+        L.require_cuda(flat, w, b, rel_index)
         if lib.idee_swin_block_packed_floats(rpb_rows) != pack.P:
             raise RuntimeError("swin_block: packed parameter size mismatch")
         out = torch.empty(N, V, T, H, W, 16, device=x.device, dtype=torch.float32)
@@ -273,7 +276,7 @@ def _conv_desc(x_dims, x_strides, y_strides, Vw, Cin, Cout, proj, relu, in_cpg, 
     d.x_sn, d.x_sv, d.x_st, d.x_sh, d.x_sw = x_strides
     d.y_sn, d.y_sv, d.y_st, d.y_sh, d.y_sw = y_strides
     d.x_sg, d.y_sg, d.in_cpg, d.out_cpg = x_sg, y_sg, in_cpg, out_cpg
-    d.precision = (2 if L.UMMA else 1) if L.PRECISION == "bf16" else 0
+    d.precision = 1 if L.PRECISION == "bf16" else 0
     d.umma16 = int(L.UMMA16 and L.PRECISION == "bf16")
     d.umma96 = int(L.UMMA96 and L.PRECISION == "bf16")
     return d
@@ -295,7 +298,7 @@ class Conv3dCL(torch.autograd.Function):
         """input_is_relu: x is the fused-ReLU output of a conv whose ONLY consumer is this op -> this op's data gradient is
         multiplied by (x > 0) in the kernel epilogue.  consumer_masks: the (only) consumer of this op's ReLU output does
         exactly that, so the incoming gradient is already masked and no separate ReLU-backward pass is needed."""
-        L.require_cuda(x, w)
+        L.require_cuda(x, w, b, x16)
         lib = L.load()
         gx_dtype = torch.bfloat16 if (x.dtype == torch.bfloat16 and x16 is None) else torch.float32
         xin = x16 if x16 is not None else x

@@ -136,7 +136,7 @@ def window_attention(sd: Dict[str, Tensor], p: str, xw: Tensor, mask, num_heads:
     qkv = qkv.reshape(B_, N, 3, num_heads, hd).permute(2, 0, 3, 1, 4)
     q, k, v = qkv[0] * scale, qkv[1], qkv[2]
     attn = q @ k.transpose(-2, -1)
-    idx = relative_position_index(cfg_ws)[:N, :N].reshape(-1)               # :158-160 (slice of configured window)
+    idx = relative_position_index(cfg_ws)[:N, :N].reshape(-1).to(xw.device)  # :158-160 (slice of configured window)
     bias = sd[p + "relative_position_bias_table"][idx].reshape(N, N, -1).permute(2, 0, 1)
     attn = attn + bias.unsqueeze(0)
     if mask is not None:
@@ -163,7 +163,7 @@ def swin_block(sd, p, x: Tensor, cfg_ws, cfg_ss, num_heads, qk_scale, layer_ss) 
     if any(s > 0 for s in ss):
         xs = torch.roll(xn, shifts=(-ss[0], -ss[1], -ss[2]), dims=(1, 2, 3))
         _, mss = get_window_size((D, H, W), cfg_ws, layer_ss)
-        mask = compute_mask(Dp, Hp, Wp, ws, mss)
+        mask = compute_mask(Dp, Hp, Wp, ws, mss).to(x.device)
     else:
         xs, mask = xn, None
     aw = window_attention(sd, p + "attn.", window_partition(xs, ws), mask, num_heads, cfg_ws, qk_scale)
@@ -240,11 +240,11 @@ def lfq_forward(sd, z: Tensor, cfg: OracleConfig, training: bool, prefix: str = 
     s = z @ sd[prefix + "project_in.weight"].t() + sd[prefix + "project_in.bias"] if has_proj else z
     q = torch.where(s > 0, torch.ones_like(s), -torch.ones_like(s))         # :221-222 (s==0 -> -1)
     x = s + (q - s).detach() if training else q                              # :226-230
-    bitmask = 2 ** torch.arange(kbits - 1, -1, -1)                           # :134
+    bitmask = 2 ** torch.arange(kbits - 1, -1, -1, device=z.device)          # :134
     indices = ((x > 0).int() * bitmask.int()).sum(-1).long()                 # :234
-    zero = torch.zeros(())
+    zero = torch.zeros((), device=z.device)
     if training:
-        codes = torch.arange(cfg.codebook_size)
+        codes = torch.arange(cfg.codebook_size, device=z.device)
         codebook = ((codes[:, None].int() & bitmask.int()) != 0).float() * 2 - 1   # :139-146
         dist = -2 * torch.einsum("bnd,jd->bnj", s, codebook)                 # :239
         prob = (-dist * inv_temperature).softmax(-1).reshape(-1, cfg.codebook_size)  # :240,246
@@ -262,7 +262,7 @@ def lfq_forward(sd, z: Tensor, cfg: OracleConfig, training: bool, prefix: str = 
 def lfq_indices_to_codes(sd, indices: Tensor, cfg: OracleConfig, prefix: str = "vq.") -> Tensor:
     """LFQ.indices_to_codes(project_out=True) for <3-D indices, LFQ.py:152-181."""
     kbits = int(math.log2(cfg.codebook_size))
-    bitmask = 2 ** torch.arange(kbits - 1, -1, -1)
+    bitmask = 2 ** torch.arange(kbits - 1, -1, -1, device=indices.device)
     bits = ((indices[..., None].int() & bitmask.int()) != 0).float()
     codes = bits * 2 - 1
     return codes @ sd[prefix + "project_out.weight"].t() + sd[prefix + "project_out.bias"]
@@ -320,7 +320,7 @@ def anomaly_l1_loss_synthetic(zq: Tensor, mask_extreme: Tensor, vq0: Tensor) -> 
     N, V, C, T, H, W = zq.shape
     m = mask_extreme.view(N, 1, 1, 1, H, W)
     tgt = vq0.reshape(1, 1, C, 1, 1, 1)
-    diff = torch.where(m == 1, torch.zeros((), dtype=zq.dtype), (zq - tgt).abs())
+    diff = torch.where(m == 1, torch.zeros((), dtype=zq.dtype, device=zq.device), (zq - tgt).abs())
     wsum = (1 - mask_extreme).sum() * (V * C * T)
     return (diff * (1 - m)).sum() / wsum
 
@@ -330,7 +330,7 @@ def train_step_loss(sd, x, mask_extreme, mask_extreme_loss, cfg: OracleConfig):
     zc, ys, anomaly, zq, aux, z_enc = vq_model_forward(sd, x, cfg, training=True)
     tgt = mask_extreme.unsqueeze(1).float()
     loss = bce_loss_synthetic(zc, tgt)
-    vq0 = lfq_indices_to_codes(sd, torch.tensor([0]), cfg).detach()                     # :188-194
+    vq0 = lfq_indices_to_codes(sd, torch.tensor([0], device=x.device), cfg).detach()                     # :188-194
     loss_anom = anomaly_l1_loss_synthetic(zq, mask_extreme_loss.float(), vq0)
     loss_var = sum(bce_loss_synthetic(y, tgt) for y in ys)
     total = loss + loss_anom * cfg.lambda_anomaly + loss_var + aux

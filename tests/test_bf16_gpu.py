@@ -109,12 +109,10 @@ def test_bf16_medium_mask_flips_are_near_ties():
     assert ties_ok and frac >= 0.98, frac
 
 
-@pytest.mark.parametrize("kernel", ["umma96", "umma"])
 @pytest.mark.parametrize("dims", [(2, 4, 20, 28), (1, 8, 37, 19)])
-def test_tcgen05_classifier_conv_matches_mma_sync_and_oracle(kernel, dims):
-    """The tcgen05 / TMEM kernels for the 96->96 classifier conv (forward + data gradient incl. the fused ReLU mask) against the
-    mma.sync kernel and the fp32 oracle (torch conv3d on CPU).  umma96: warp-specialised kernel (conv96_umma.cu, default);
-    umma: the earlier single-role kernel (conv_umma.cu, opt-in)."""
+def test_tcgen05_classifier_conv_matches_mma_sync_and_oracle(dims):
+    """The warp-specialised tcgen05 / TMEM kernel for the 96->96 classifier conv (conv96_umma.cu: forward + data gradient incl.
+    the fused ReLU mask) against the mma.sync kernel and the fp32 oracle (torch conv3d on CPU)."""
     import torch.nn.functional as F
     from idee_b200 import _lib, ops
     N, T, H, W = dims
@@ -128,19 +126,17 @@ def test_tcgen05_classifier_conv_matches_mma_sync_and_oracle(kernel, dims):
     want = F.conv3d(xr[:, 0].permute(0, 4, 1, 2, 3), w[0], b[0], stride=(2, 1, 1), padding=(0, 1, 1)).permute(0, 2, 3, 4, 1).unsqueeze(1)
     (want * g).sum().backward()
     want_gx = xr.grad * (x > 0)                                    # input_is_relu: the data gradient carries the ReLU mask
-    setter = _lib.set_umma96 if kernel == "umma96" else _lib.set_umma
-    old96, old = _lib.UMMA96, _lib.UMMA
+    old96 = _lib.UMMA96
     outs = {}
     try:
-        _lib.set_umma96(False); _lib.set_umma(False)
         for on in (False, True):
-            setter(on)
+            _lib.set_umma96(on)
             xc = x.cuda().requires_grad_(True)
             y = ops.conv3d_cl(xc, w.cuda(), b.cuda(), False, False, input_is_relu=True)
             (y * g.cuda()).sum().backward()
             outs[on] = (y.detach().cpu(), xc.grad.cpu())
     finally:
-        _lib.set_umma96(old96); _lib.set_umma(old)
+        _lib.set_umma96(old96)
     for on in (False, True):
         assert rel_err(outs[on][0], want) < TOL
         assert rel_err(outs[on][1], want_gx) < TOL

@@ -27,7 +27,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/idee_b200.h but not exported"
     assert set(syms) == set(_lib.EXPORTS), set(syms) ^ set(_lib.EXPORTS)
-    assert lib.idee_version() == 100
+    assert lib.idee_version() == _lib.header_version()
     assert lib.idee_swin_block_packed_floats(147) == 147 * 2 + 3216
 
 
@@ -60,6 +60,51 @@ def test_initialisation_is_bit_identical_to_reference():
     for k in rsd:
         assert torch.equal(rsd[k], osd[k]), k
     sys.modules.pop("models", None)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (GPU box)")
+def test_install_as_reference_modules_routes_the_reference_build():
+    """idee_b200.install_as_reference_modules(): the reference's OWN models/build.py (import_class -> importlib, build.py:17-20)
+    then constructs the idee_b200 encoder / quantiser / classifier with the reference's parameter inventory and bit-identical
+    initialisation, and the assembled model refuses CPU tensors (no silent fallback to the reference's PyTorch code)."""
+    import importlib
+    from tests.golden.make_golden import install_timm_shim, reference_config
+    import idee_b200
+    from idee_b200.models.encoder.Swin_3D import Swin_3D
+    from idee_b200.models.codebook.LFQ import LFQ
+    from idee_b200.models.classifier.CNN_3D import CNN_3D
+    saved = {k: v for k, v in sys.modules.items() if k == "models" or k.startswith("models.")}
+    for k in saved:
+        del sys.modules[k]
+    try:
+        install_timm_shim()
+        if REF not in sys.path:
+            sys.path.insert(0, REF)
+        idee_b200.install_as_reference_modules()
+        # the reference's own build.py, loaded from its file so that its import_class goes through importlib -> sys.modules
+        spec = importlib.util.spec_from_file_location("ref_build_under_test", os.path.join(REF, "models", "build.py"))
+        ref_build = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref_build)
+        config_mod = importlib.import_module("config")
+        cfg = reference_config(config_mod, in_channels_dynamic=6, in_channels=1)
+        torch.manual_seed(0)
+        model = ref_build.VQ_model(cfg)
+        assert type(model.encoder) is Swin_3D and type(model.vq) is LFQ and type(model.cls) is CNN_3D
+        assert sum(p.numel() for p in model.parameters()) == 535892
+        got = {k: tuple(v.shape) for k, v in model.named_parameters()}
+        assert got == O.param_shapes(O.OracleConfig(in_vars=6, in_chans=1))
+        from idee_b200.config import default_config
+        from idee_b200.models.build import VQ_model
+        torch.manual_seed(0)
+        ours = VQ_model(default_config())
+        for (ka, a), (kb, b) in zip(model.state_dict().items(), ours.state_dict().items()):
+            assert ka == kb and torch.equal(a, b), ka
+        with pytest.raises(RuntimeError):
+            model(torch.randn(1, 6, 1, 8, 8, 8))
+    finally:
+        for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
 
 
 def test_window_clamp_and_relative_index():

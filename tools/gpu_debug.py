@@ -1,7 +1,7 @@
 """Per-op GPU diagnostics against the CPU oracle (development aid; the formal tests are tests/test_*_gpu.py).
 
-    python tests/gpu_debug.py            # runs every stage, each in its own process (a CUDA fault poisons a context)
-    python tests/gpu_debug.py <stage>    # one stage in-process
+    python tools/gpu_debug.py            # runs every stage, each in its own process (a CUDA fault poisons a context)
+    python tools/gpu_debug.py <stage>    # one stage in-process
 """
 import os
 import subprocess
@@ -158,18 +158,6 @@ def stage_conv_b():
     _conv_case(False, 96, 96, 1, 1, (4, 9, 7), True)
     _conv_case(False, 96, 1, 1, 1, (3, 9, 7), False)
     _conv_case(True, 16, 16, 2, 2, (8, 40, 52), True, N=1)
-
-
-def stage_conv_umma():
-    """96 -> 96 classifier conv on the tcgen05 / TMEM kernel (bf16 operands) against the oracle."""
-    from idee_b200 import _lib
-    _lib.set_precision("bf16")
-    _lib.set_umma(True)
-    global BF16
-    BF16 = True
-    _conv_case(False, 96, 96, 1, 1, (4, 9, 7), True)
-    _conv_case(False, 96, 96, 1, 1, (4, 40, 52), True, N=2)
-    _conv_case(False, 96, 96, 1, 1, (8, 24, 20), False, N=1)
 
 
 def stage_lfq():
