@@ -18,7 +18,7 @@ c_i64, c_int, c_f32, c_vp, c_sz = C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c
 class SwinDesc(C.Structure):
     _fields_ = [(n, c_int) for n in ("N", "V", "T", "H", "W", "C", "heads", "hidden", "wd", "wh", "ww", "st", "sh", "sw", "rpb_rows")] + \
                [("scale", c_f32), ("param_stride", c_i64), ("precision", c_int)] + \
-               [(n, c_vp) for n in ("embed_x", "embed_w", "embed_b", "embed_gw", "embed_gb")]
+               [(n, c_vp) for n in ("embed_x", "embed_w", "embed_b", "embed_gw", "embed_gb")] + [("act_dtype", c_int)]
 
 
 class ConvDesc(C.Structure):
@@ -136,6 +136,20 @@ UMMA16 = os.environ.get("IDEE_B200_UMMA16", "1") == "1"
 # warp-specialised tcgen05 + TMEM kernel for the dense 96 -> 96 classifier conv (forward + data gradient), bf16 mode only;
 # on by default (measured 1.9x / 1.5x faster than the mma.sync kernel), IDEE_B200_UMMA96=0 selects the mma.sync kernel
 UMMA96 = os.environ.get("IDEE_B200_UMMA96", "1") == "1"
+
+
+# tcgen05 / TMEM Swin block kernels on bf16 token storage (swin_umma.cuh), bf16 mode only; IDEE_B200_SWIN_UMMA=0 selects the
+# mma.sync kernels on fp32 token storage (swin_tc.cuh)
+SWIN_UMMA = os.environ.get("IDEE_B200_SWIN_UMMA", "1") == "1"
+
+
+def set_swin_umma(on: bool) -> None:
+    global SWIN_UMMA
+    SWIN_UMMA = bool(on)
+
+
+def swin_umma() -> bool:
+    return SWIN_UMMA and PRECISION == "bf16"
 
 
 def set_umma96(on: bool) -> None:

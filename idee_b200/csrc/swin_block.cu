@@ -617,6 +617,7 @@ swin_grad_finalize_kernel(const float* __restrict__ part_attn, const float* __re
 }
 
 #include "swin_tc.cuh"
+#include "swin_umma.cuh"
 
 // ---- host side -----------------------------------------------------------------------------------------
 int make_geom(Geom& g, const idee_swin_desc* d, const char* who) {
@@ -660,6 +661,27 @@ template <int WD, int WH, int WW>
 int launch_fwd(const idee_swin_desc* d, const Geom& g, const float* x, float* out, float* ymid, const float* params,
                const int* rel_index, cudaStream_t st) {
     constexpr int G = WD * WH * WW;
+    if (d->precision == 1 && d->act_dtype == 1) {
+        if (G < 8) { idee_set_error("swin_block_fwd(bf16 tokens): windows with fewer than 8 tokens are only built for the fp32 path"); return 1; }
+        const bool emb = g.emb_x != nullptr;
+        const size_t smem = sizeof(swu::FwdSm) + sizeof(float) * bsz(G);
+        const int n_tiles = (g.n_wg + 3) / 4;
+        int per_v = idee_num_sms() * 4 / d->V;
+        if (per_v > n_tiles) per_v = n_tiles;
+        if (per_v < 1) per_v = 1;
+        auto bx = reinterpret_cast<const __nv_bfloat16*>(x);
+        auto bo = reinterpret_cast<__nv_bfloat16*>(out);
+        auto by = reinterpret_cast<__nv_bfloat16*>(ymid);
+        if (emb) {
+            IDEE_CUDA(cudaFuncSetAttribute(swu::swin_fwd_umma_kernel<WD, WH, WW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "swin_block_fwd(umma)");
+            swu::swin_fwd_umma_kernel<WD, WH, WW, true><<<dim3(per_v, d->V), swu::NT, smem, st>>>(bx, bo, by, params, d->param_stride, rel_index, g);
+        } else {
+            IDEE_CUDA(cudaFuncSetAttribute(swu::swin_fwd_umma_kernel<WD, WH, WW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "swin_block_fwd(umma)");
+            swu::swin_fwd_umma_kernel<WD, WH, WW, false><<<dim3(per_v, d->V), swu::NT, smem, st>>>(bx, bo, by, params, d->param_stride, rel_index, g);
+        }
+        IDEE_LAUNCH_CHECK("swin_block_fwd(umma)");
+        return 0;
+    }
     if (d->precision == 1) {
         if (G < 8) { idee_set_error("swin_block_fwd(bf16): windows with fewer than 8 tokens are only built for the fp32 path"); return 1; }
         // persistent grid of exactly one resident wave (a partial second wave would run at a fraction of the occupancy)
@@ -768,6 +790,8 @@ extern "C" int idee_swin_block_fwd(const idee_swin_desc* d, const float* x, floa
     Geom g;
     if (make_geom(g, d, "swin_block_fwd")) return 1;
     IDEE_REQUIRE(out_bf16 == nullptr || d->precision == 1, "swin_block_fwd: the bf16 output copy is only produced by the bf16 path");
+    IDEE_REQUIRE(d->act_dtype == 0 || (d->act_dtype == 1 && d->precision == 1 && out_bf16 == nullptr && out != nullptr),
+                 "swin_block_fwd: bf16 tokens (act_dtype 1) need precision 1, out != NULL and out_bf16 == NULL");
     IDEE_REQUIRE(out != nullptr || out_bf16 != nullptr, "swin_block_fwd: out may only be NULL when the bf16 copy is requested");
     g.out16 = out_bf16;
     cudaStream_t st = (cudaStream_t)stream;

@@ -117,7 +117,7 @@ class SwinTransformerBlock3D(nn.Module):
         B, D, H, W, C = x.shape
         ws, ss, idx, rows, scale, heads, hidden = self.kernel_args(D, H, W)
         y = ops.swin_block(x.unsqueeze(1), self._pack1, idx, ws, ss, rows, scale, heads, hidden)
-        return y.squeeze(1)
+        return y.squeeze(1).to(x.dtype)      # the tcgen05 kernels keep tokens in bf16; the module contract returns x's dtype
 
 
 class PatchEmbed3D(nn.Module):
@@ -272,7 +272,7 @@ class Swin_3D(nn.Module):
             if fuse_embed and i == 0:
                 xin = x if (x.dtype == torch.float32 and x.is_contiguous()) else x.float().contiguous()
                 tok = ops.swin_block_embed(xin, pk["embed_w"], pk["embed_b"], pack, idx, ws, ss, rows, scale, heads, hidden)
-            elif bf16_io and i == len(pk["blocks"]) - 1:
+            elif bf16_io and i == len(pk["blocks"]) - 1 and not _lib.swin_umma():
                 # the proj conv reads only the bf16 copy: the fp32 tokens of the last block are never written
                 tok, tok16 = ops.swin_block(tok, pack, idx, ws, ss, rows, scale, heads, hidden, want_bf16="only")
             else:
@@ -281,6 +281,8 @@ class Swin_3D(nn.Module):
         w2, b2 = ops.packed(pk["proj2_w"], (V, E, E, 3, 3, 3)), ops.packed(pk["proj2_b"], (V, E))
         # conv -> ReLU -> conv: the second conv is the only consumer of the ReLU output, so its data-gradient epilogue applies
         # the ReLU backward mask and the first conv skips the separate pass
+        if tok.dtype == torch.bfloat16 and not bf16_io:
+            tok = tok.float()
         tok = ops.conv3d_cl(tok, w0, b0, proj=True, relu=True, consumer_masks=True, x16=tok16, out_bf16=bf16_io)
         if fold_last is not None and bf16_io:
             w_in, b_in = fold_last

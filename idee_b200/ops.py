@@ -143,6 +143,7 @@ def _swin_desc(x, window, shift, rpb_rows, scale, pack: ParamPack, heads, hidden
     d.st, d.sh, d.sw = shift
     d.rpb_rows, d.scale, d.param_stride = rpb_rows, scale, pack.P
     d.precision = 1 if L.PRECISION == "bf16" else 0
+    d.act_dtype = 1 if x.dtype == torch.bfloat16 else 0
     return d
 
 
@@ -154,11 +155,24 @@ class SwinBlock(torch.autograd.Function):
         """want_bf16 (bf16 mode only): also return a non-differentiable bf16 copy of the output, written by the same kernel."""
         L.require_cuda(x)
         lib = L.load()
-        x = _f32c(x)
         flat = pack.tensor()
         L.require_cuda(flat, rel_index)
         if lib.idee_swin_block_packed_floats(rpb_rows) != pack.P:
             raise RuntimeError("swin_block: packed parameter size mismatch")
+        if L.swin_umma() and window[0] * window[1] * window[2] >= 8:
+            # tcgen05 / TMEM kernels: bf16 tokens in, bf16 tokens out (the residual stream lives in HBM as bf16)
+            x = x.contiguous() if x.dtype == torch.bfloat16 else x.to(torch.bfloat16).contiguous()
+            d = _swin_desc(x, window, shift, rpb_rows, scale, pack, heads, hidden)
+            out = torch.empty_like(x)
+            need_bwd = any(ctx.needs_input_grad)
+            ymid = torch.empty_like(x) if need_bwd else None
+            L.run("swin_block_fwd", lib.idee_swin_block_fwd, C.byref(d), x.data_ptr(), out.data_ptr(), L.ptr(ymid), None,
+                  flat.data_ptr(), rel_index.data_ptr(), L.stream(), tag=f"w{window} s{shift}")
+            if need_bwd:
+                ctx.save_for_backward(x, ymid, rel_index)
+                ctx.pack, ctx.args = pack, (window, shift, rpb_rows, scale, heads, hidden)
+            return out
+        x = _f32c(x)
         d = _swin_desc(x, window, shift, rpb_rows, scale, pack, heads, hidden)
         # want_bf16 == "only": the caller reads nothing but the bf16 copy, so the fp32 result is not written (the returned fp32
         # tensor only routes the gradient and is left uninitialised)
@@ -215,7 +229,7 @@ class SwinBlockEmbed(torch.autograd.Function):
         L.require_cuda(flat, w, b, rel_index)
         if lib.idee_swin_block_packed_floats(rpb_rows) != pack.P:
             raise RuntimeError("swin_block: packed parameter size mismatch")
-        out = torch.empty(N, V, T, H, W, 16, device=x.device, dtype=torch.float32)
+        out = torch.empty(N, V, T, H, W, 16, device=x.device, dtype=torch.bfloat16 if L.swin_umma() else torch.float32)
         d = _swin_desc(out, window, shift, rpb_rows, scale, pack, heads, hidden)
         d.embed_x, d.embed_w, d.embed_b = x.data_ptr(), w.data_ptr(), b.data_ptr()
         need_bwd = any(ctx.needs_input_grad)
@@ -256,7 +270,11 @@ def swin_block_embed(x, wpack: ParamPack, bpack: ParamPack, pack: ParamPack, rel
 
 
 def swin_block(x, pack: ParamPack, rel_index, window, shift, rpb_rows, scale, heads, hidden, want_bf16: bool = False):
-    """-> out, or (out, out_bf16) when want_bf16 (bf16 mode; the copy feeds a bf16-storage conv, see Conv3dCL)."""
+    """-> out, or (out, out_bf16) when want_bf16 (bf16 mode; the copy feeds a bf16-storage conv, see Conv3dCL).
+    With the tcgen05 kernels (L.swin_umma()) the tokens themselves are bf16: out is bf16 and doubles as the copy."""
+    if L.swin_umma() and window[0] * window[1] * window[2] >= 8:
+        out = SwinBlock.apply(x, pack, rel_index, tuple(window), tuple(shift), rpb_rows, float(scale), heads, hidden, False, *pack.params())
+        return (out, out) if want_bf16 else out
     return SwinBlock.apply(x, pack, rel_index, tuple(window), tuple(shift), rpb_rows, float(scale), heads, hidden,
                            want_bf16 if want_bf16 == "only" else bool(want_bf16), *pack.params())
 
