@@ -664,7 +664,7 @@ int launch_fwd(const idee_swin_desc* d, const Geom& g, const float* x, float* ou
     if (d->precision == 1 && d->act_dtype == 1) {
         if (G < 8) { idee_set_error("swin_block_fwd(bf16 tokens): windows with fewer than 8 tokens are only built for the fp32 path"); return 1; }
         const bool emb = g.emb_x != nullptr;
-        const size_t smem = sizeof(swu::FwdSm) + sizeof(float) * bsz(G);
+        const size_t smem = sizeof(swu::FwdSm) + sizeof(float) * NH * G * swu::bns(G);
         const int n_tiles = (g.n_wg + 3) / 4;
         int per_v = idee_num_sms() * 4 / d->V;
         if (per_v > n_tiles) per_v = n_tiles;
@@ -711,8 +711,8 @@ int launch_fwd(const idee_swin_desc* d, const Geom& g, const float* x, float* ou
     return 0;
 }
 
-int bwd_ctas_per_var(int V) {
-    int per_v = (idee_num_sms() * 3 + V - 1) / V;
+int bwd_ctas_per_var(int V, int per_sm = 3) {
+    int per_v = (idee_num_sms() * per_sm + V - 1) / V;
     return per_v < 1 ? 1 : per_v;
 }
 
@@ -720,7 +720,7 @@ template <int WD, int WH, int WW>
 int launch_bwd(const idee_swin_desc* d, const Geom& g, const float* x, const float* ymid, const float* gout, float* gx,
                const float* params, const int* rel_index, float* gparams, float* ws, size_t ws_bytes, cudaStream_t st) {
     constexpr int G = WD * WH * WW;
-    const int per_v = bwd_ctas_per_var(d->V);
+    const int per_v = bwd_ctas_per_var(d->V, d->act_dtype == 1 ? 4 : 3);
     const int APS = ATT_PART_W + NH * G * G;
     const size_t need = sizeof(float) * (size_t)d->V * per_v * (APS + MLP_PART + (d->embed_gw ? 32 : 0));
     IDEE_REQUIRE(ws_bytes >= need, "swin_block_bwd: workspace too small (%zu < %zu)", ws_bytes, need);
@@ -728,6 +728,31 @@ int launch_bwd(const idee_swin_desc* d, const Geom& g, const float* x, const flo
     float* part_mlp = ws + (size_t)d->V * per_v * APS;
     float* part_emb = part_mlp + (size_t)d->V * per_v * MLP_PART;
     const int64_t thw = (int64_t)d->T * d->H * d->W;
+    if (d->precision == 1 && d->act_dtype == 1) {
+        if (G < 8) { idee_set_error("swin_block_bwd(bf16 tokens): windows with fewer than 8 tokens are only built for the fp32 path"); return 1; }
+        IDEE_REQUIRE((int64_t)d->N * thw < (1ll << 31), "swin_block_bwd(umma): N*T*H*W must be below 2^31");
+        IDEE_REQUIRE(g.emb_x == nullptr || d->embed_gw != nullptr, "swin_block_bwd(umma): the fused embedding needs embed_gw / embed_gb");
+        IDEE_REQUIRE(gx != gout, "swin_block_bwd(umma): gx must not alias gout");
+        // persistent grids of one resident wave: 4 CTAs / SM (MLP half), 2 CTAs / SM (attention half: 85 KB of shared memory)
+        int pv_mlp = idee_num_sms() * 4 / d->V, pv_att = idee_num_sms() * 2 / d->V;
+        if (pv_mlp < 1) pv_mlp = 1;
+        if (pv_att < 1) pv_att = 1;
+        float* u_attn = ws;
+        float* u_mlp = u_attn + (size_t)d->V * pv_att * APS;
+        float* u_emb = u_mlp + (size_t)d->V * pv_mlp * MLP_PART;
+        auto bx = reinterpret_cast<const __nv_bfloat16*>(x);
+        auto bym = reinterpret_cast<const __nv_bfloat16*>(ymid);
+        auto bgo = reinterpret_cast<const __nv_bfloat16*>(gout);
+        auto bgx = reinterpret_cast<__nv_bfloat16*>(gx);
+        {
+            const size_t smem = sizeof(swu::MlpBwdSm);
+            IDEE_CUDA(cudaFuncSetAttribute(swu::swin_mlp_bwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "swin_mlp_bwd(umma)");
+            swu::swin_mlp_bwd_umma_kernel<<<dim3(pv_mlp, d->V), swu::NT, smem, st>>>(bym, bgo, bgx, params, d->param_stride, g.tbl, u_mlp, d->N, d->V,
+                                                                                     (int)thw, make_fastdiv((int)thw));
+            IDEE_LAUNCH_CHECK("swin_mlp_bwd(umma)");
+        }
+        return swu::launch_attn_bwd<WD, WH, WW>(d, g, bx, bgx, params, rel_index, gparams, u_attn, u_mlp, u_emb, pv_att, pv_mlp, st);
+    }
     if (d->precision == 1) {
         if (G < 8) { idee_set_error("swin_block_bwd(bf16): windows with fewer than 8 tokens are only built for the fp32 path"); return 1; }
         swin_mlp_bwd_tc_kernel<<<dim3(per_v, d->V), TCW * 32, 0, st>>>(ymid, gout, gx, params, d->param_stride, g.tbl, part_mlp, d->N, d->V, thw);
@@ -781,7 +806,7 @@ extern "C" int idee_swin_block_packed_floats(int rpb_rows) { return POff(rpb_row
 
 extern "C" size_t idee_swin_block_bwd_workspace_bytes(const idee_swin_desc* d) {
     const int Gt = d->wd * d->wh * d->ww;
-    const int per_v = bwd_ctas_per_var(d->V);
+    const int per_v = bwd_ctas_per_var(d->V, d->act_dtype == 1 ? 4 : 3);     // upper bound of either kernel's CTAs per variable
     return sizeof(float) * (size_t)d->V * per_v * (ATT_PART_W + NH * Gt * Gt + MLP_PART + (d->embed_gw ? 32 : 0));
 }
 

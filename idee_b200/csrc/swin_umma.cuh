@@ -178,6 +178,17 @@ __device__ __forceinline__ Tok map_token(const Geom& g, int v, int wg, int lane)
     return t;
 }
 
+// row stride (floats) of the staged relative-position-bias table Bn[h][i][.]: lanes g = 0..3 of a half warp read rows 8 r + g
+// as float2 -> the four row offsets must fall into different 32-byte bank groups: stride * 4 mod 128 in {32, 96}
+__host__ __device__ constexpr int bns(int G) { return G == 32 ? 40 : (G == 16 ? 24 : G); }
+template <int G>
+__device__ __forceinline__ void stage_bias_pad(float* Bn, const float* tbl, const int* __restrict__ rel_index) {
+    for (int e = threadIdx.x; e < NH * G * G; e += blockDim.x) {
+        const int h = e / (G * G), ij = e % (G * G);
+        Bn[(h * G + ij / G) * bns(G) + ij % G] = tbl[rel_index[ij] * NH + h] * LOG2E;      // log2 domain
+    }
+}
+
 // attention core of one warp (32 tokens = 32 / G windows) on mma.sync fragments, operands from the warp's staging tile
 template <int G>
 struct AttnU {
@@ -226,7 +237,7 @@ struct AttnU {
             for (int nj = 0; nj < 4; ++nj) {
                 if (tile_needed(r, nj)) {
                     const int jl = (8 * nj + c0) % G;
-                    const float2 b = *reinterpret_cast<const float2*>(Bn + (h * G + il) * G + jl);
+                    const float2 b = *reinterpret_cast<const float2*>(Bn + (h * G + il) * bns(G) + jl);
                     p[mi][nj][2 * hf] += b.x; p[mi][nj][2 * hf + 1] += b.y;
                 }
             }
@@ -314,7 +325,7 @@ swin_fwd_umma_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restr
     constexpr int G = WD * WH * WW;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FwdSm& S = *reinterpret_cast<FwdSm*>(smem_raw);
-    float* Bn = reinterpret_cast<float*>(smem_raw + sizeof(FwdSm));          // [NH][G][G], log2 domain
+    float* Bn = reinterpret_cast<float*>(smem_raw + sizeof(FwdSm));          // [NH][G][bns(G)], log2 domain
     const int v = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* P = params + (int64_t)v * pstride;
     const POff po(g.tbl);
@@ -339,7 +350,7 @@ swin_fwd_umma_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restr
     for (int e = tid; e < 48; e += NT) S.bqkv[e] = P[po.qkv_b + e] * (e < 16 ? qs : 1.f);
     for (int e = tid; e < 16; e += NT) { S.bproj[e] = P[po.proj_b + e]; S.b2[e] = P[po.fc2_b + e]; }
     for (int e = tid; e < 64; e += NT) S.b1[e] = P[po.fc1_b + e];
-    stage_bias_n<G>(Bn, P, rel_index);
+    stage_bias_pad<G>(Bn, P, rel_index);
     proxy_fence();
     tc_fence_before();
     __syncthreads();
@@ -522,6 +533,696 @@ swin_fwd_umma_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restr
     }
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(F_COLS) : "memory");
+}
+
+
+// =====================================================================================================
+// backward, MLP half (tcgen05):  out = y + fc2(gelu(fc1(LN(y))))
+//   inputs y, g_out (bf16 tokens);  outputs g_y (bf16), per-CTA partial d{fc1_w, fc1_b, fc2_w, fc2_b} (MLP_PART layout)
+// =====================================================================================================
+// GELU (tanh form, the forward's gelu_fast) and ITS derivative: y = 0.5 x (1 + t), t = tanh(u), u = x (a + b x^2);
+// dy/dx = 0.5 (1 + t) + 0.5 x (1 - t^2) (a + 3 b x^2)
+__device__ __forceinline__ void gelu_tanh_grad(float x, float& y, float& dy) {
+    const float x2 = x * x;
+    const float t = tanh_approx(x * (0.7978845608028654f + 0.0356774081363001f * x2));
+    const float cdf = 0.5f + 0.5f * t;
+    y = x * cdf;
+    dy = (0.5f * x) * (1.f - t * t) * (0.7978845608028654f + 0.1070322244089003f * x2) + cdf;
+}
+
+// TMEM column map of the MLP backward kernel (128 columns): pre-activation and hidden gradient of one 32-unit half, the token
+// gradient, and the persistent weight-gradient accumulator D[128 x 48] = [g_pre | gelu(h)]^T [yn | g_out | 1 | 0]
+constexpr int M_PRE = 0, M_DH = 32, M_DYN = 64, M_WACC = 80, M_COLS = 128;
+
+struct MlpBwdSm {
+    unsigned char pa[16 * PLANE];        // chunk planes: g_pre (8 chunks of 8 hidden units) | gelu(h) (8 chunks)
+    unsigned char ones0[PLANE];          // A operand of the bias GEMM step, chunk 0: elements 0 and 1 of every row = 1 (chunk 1 = pb[5])
+    unsigned char b1[64 * 16];           // B(n = hidden, k) chunk 0 of the bias step: k = 0 -> hi(b1[n]), k = 1 -> lo(b1[n]) (chunk 1 = pb[5])
+    unsigned char w1[64 * 32];           // B(n = hidden, k = c) = fc1.weight[n][k]            (pre = yn W1^T)
+    unsigned char w2t[64 * 32];          // B(n = hidden, k = c) = fc2.weight[k][n]            (g_h = g_out W2)
+    unsigned char w1t[16 * 128];         // B(n = c, k = hidden) = fc1.weight[k][n]            (g_yn = g_pre W1)
+    unsigned char pb[6 * PLANE];         // chunk planes: yn (2) | g_out (2) | ones (1) | zeros (1); after ones0 / b1: their LBO > 0
+    float red[16];
+    uint64_t mma_bar;
+    uint32_t tmem_slot;
+};
+
+__global__ void __launch_bounds__(NT, 4)
+swin_mlp_bwd_umma_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ gout, __nv_bfloat16* __restrict__ gy,
+                         const float* __restrict__ params, int64_t pstride, int tbl, float* __restrict__ partials,
+                         int N, int V, int thw, FastDiv fd_thw) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    MlpBwdSm& S = *reinterpret_cast<MlpBwdSm*>(smem_raw);
+    const int v = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* P = params + (int64_t)v * pstride;
+    const POff po(tbl);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_slot)), "n"(M_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) { mbar_init(smem_u32(&S.mma_bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    stage_b_kmajor(S.w1, P + po.fc1_w, C, 64, 16, 0, 1.f);
+    stage_b_kmajor_t(S.w2t, P + po.fc2_w, HID, 64, 16);
+    stage_b_kmajor_t(S.w1t, P + po.fc1_w, C, 16, 64);
+    for (int e = tid; e < 64 * 8; e += NT) {                       // bias rows: hi + lo bf16 split keeps the fp32 bias to 2^-17
+        const int n = e >> 3, k = e & 7;
+        const float b = P[po.fc1_b + n];
+        const __nv_bfloat16 hi = __float2bfloat16(b);
+        const __nv_bfloat16 lo = __float2bfloat16(b - __bfloat162float(hi));
+        reinterpret_cast<__nv_bfloat16*>(S.b1)[e] = k == 0 ? hi : (k == 1 ? lo : __float2bfloat16(0.f));
+    }
+    // constant planes: ones (B operand column block of the bias-gradient sums), zeros, and the A operand of the bias step
+    sts128(smem_u32(S.pb) + 4 * PLANE + tid * 16, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    sts128(smem_u32(S.pb) + 5 * PLANE + tid * 16, 0u, 0u, 0u, 0u);
+    sts128(smem_u32(S.ones0) + tid * 16, 0x3F803F80u, 0u, 0u, 0u);
+    if (tid < 16) S.red[tid] = 0.f;
+    proxy_fence();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = S.tmem_slot;
+    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t mma_bar = smem_u32(&S.mma_bar);
+    const uint32_t pa = smem_u32(S.pa), pb = smem_u32(S.pb);
+    uint32_t n_commit = 0;
+    float db2[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) db2[c] = 0.f;
+
+    const int64_t ntok = (int64_t)N * thw;
+    const int n_tiles = (int)((ntok + NT - 1) / NT);
+    bool first = true;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t tok = (uint32_t)tile * NT + tid;
+        const bool valid = tok < ntok;
+        uint32_t n, rem;
+        fd_thw.divmod(valid ? tok : 0u, n, rem);
+        const int64_t off = ((int64_t)(n * V + v) * thw + rem) * C;
+        // ---- R0: rows -> LN -> planes yn | g_out -> GEMMs of half 0 ----
+        uint32_t pg[8];
+        float yn[16], rstd;
+        {
+            uint32_t py[8];
+            if (valid) { ldg_row16(y + off, py); ldg_row16(gout + off, pg); }
+            else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { py[i] = 0u; pg[i] = 0u; }
+            }
+            float yr[16];
+            unpack16(py, yr);
+            rstd = ln_row(yr, yn);
+            uint32_t pn[8];
+            pack16(yn, pn);
+            sts128(pb + tid * 16, pn[0], pn[1], pn[2], pn[3]);
+            sts128(pb + PLANE + tid * 16, pn[4], pn[5], pn[6], pn[7]);
+            sts128(pb + 2 * PLANE + tid * 16, pg[0], pg[1], pg[2], pg[3]);
+            sts128(pb + 3 * PLANE + tid * 16, pg[4], pg[5], pg[6], pg[7]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { db2[2 * i] += bf_lo(pg[i]); db2[2 * i + 1] += bf_hi(pg[i]); }
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            proxy_fence();
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                // pre = yn W1^T + b1 (bias as a second K step against the constant ones operand);  g_h = g_out W2
+                umma_ss(tmem + M_PRE, make_desc(pb, PLANE, 128), make_desc(smem_u32(S.w1) + half * 512, 64 * 16, 128), idesc(128, 32), 0);
+                umma_ss(tmem + M_PRE, make_desc(smem_u32(S.ones0), pb + 5 * PLANE - smem_u32(S.ones0), 128),
+                        make_desc(smem_u32(S.b1) + half * 512, pb + 5 * PLANE - (smem_u32(S.b1) + half * 512), 128), idesc(128, 32), 1);
+                umma_ss(tmem + M_DH, make_desc(pb + 2 * PLANE, PLANE, 128), make_desc(smem_u32(S.w2t) + half * 512, 64 * 16, 128), idesc(128, 32), 0);
+                umma_commit(mma_bar);
+            }
+            mbar_wait(mma_bar, n_commit++ & 1u);
+            tc_fence_after();
+            // ---- R1 / R2: GELU and its derivative on this half's 32 hidden units -> planes g_pre | gelu(h) ----
+            float pre[32], dh[32];
+            tmem_ld32(tlane + M_PRE, pre);
+            tmem_ld32(tlane + M_DH, dh);
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                uint32_t pp[4], ph[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float h0, d0, h1, d1;
+                    gelu_tanh_grad(pre[8 * c4 + 2 * j], h0, d0);
+                    gelu_tanh_grad(pre[8 * c4 + 2 * j + 1], h1, d1);
+                    pp[j] = pk(dh[8 * c4 + 2 * j] * d0, dh[8 * c4 + 2 * j + 1] * d1);
+                    ph[j] = pk(h0, h1);
+                }
+                sts128(pa + (4 * half + c4) * PLANE + tid * 16, pp[0], pp[1], pp[2], pp[3]);
+                sts128(pa + (8 + 4 * half + c4) * PLANE + tid * 16, ph[0], ph[1], ph[2], ph[3]);
+            }
+        }
+        proxy_fence();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            // weight gradients: D[128 x 48] += [g_pre | gelu(h)]^T [yn | g_out | 1 | 0], K = the tile's 128 tokens in 8 steps;
+            // both operands are MN-major views of the token-major chunk planes (LBO = 8-token group, SBO = chunk plane)
+#pragma unroll
+            for (int s = 0; s < 8; ++s)
+                umma_ss(tmem + M_WACC, make_desc(pa + s * 256, 128, PLANE), make_desc(pb + s * 256, 128, PLANE), idesc(128, 48, 1, 1),
+                        (first && s == 0) ? 0u : 1u);
+            // g_yn = g_pre W1  (K = 64 hidden units in four steps)
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+                umma_ss(tmem + M_DYN, make_desc(pa + 2 * s * PLANE, PLANE, 128), make_desc(smem_u32(S.w1t) + s * 512, 16 * 16, 128), idesc(128, 16), s > 0 ? 1u : 0u);
+            umma_commit(mma_bar);
+        }
+        first = false;
+        mbar_wait(mma_bar, n_commit++ & 1u);
+        tc_fence_after();
+        // ---- R3: LayerNorm backward + residual -> g_y ----
+        {
+            float d[16];
+            tmem_ld16(tlane + M_DYN, d);
+            float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) { m1 += d[c]; m2 += d[c] * yn[c]; }
+            m1 *= (1.f / 16.f); m2 *= (1.f / 16.f);
+            float go[16];
+            unpack16(pg, go);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) d[c] = go[c] + rstd * (d[c] - m1 - yn[c] * m2);
+            if (valid) {
+                uint32_t po_[8];
+                pack16(d, po_);
+                st8u(gy + off, po_);
+            }
+        }
+        tc_fence_before();
+    }
+    // ---- per-CTA partials: fc1_w[k][c] | fc1_b[k] | fc2_w[c][k] | fc2_b[c] ----
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+        float s = db2[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) atomicAdd(&S.red[c], s);
+    }
+    __syncthreads();
+    tc_fence_after();
+    float* part = partials + ((int64_t)v * gridDim.x + blockIdx.x) * MLP_PART;
+    const bool any = (int)blockIdx.x < n_tiles;                     // a CTA without tiles never wrote its accumulator
+    if (tid < 64) {                                                 // rows 0..63 of D: g_pre units
+        float w[16], b[16];
+        tmem_ld16(tlane + M_WACC, w);
+        tmem_ld16(tlane + M_WACC + 32, b);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) part[tid * C + c] = any ? w[c] : 0.f;
+        part[HID * C + tid] = any ? b[0] : 0.f;
+    } else {                                                        // rows 64..127: gelu(h) units against g_out
+        float w[16];
+        tmem_ld16(tlane + M_WACC + 16, w);
+        const int k = tid - 64;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) part[HID * C + HID + c * HID + k] = any ? w[c] : 0.f;
+    }
+    if (tid < 16) part[HID * C + HID + C * HID + tid] = S.red[tid];
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(M_COLS) : "memory");
+}
+
+
+// =====================================================================================================
+// backward, attention half (tcgen05):  y = x + proj(attn(LN(x)))
+//   inputs x (or the raw embedding input), g_y (bf16);  outputs g_x (bf16, may alias g_y), per-CTA partial
+//   d{qkv_w, qkv_b, proj_w, proj_b, bias[h][i][j]} (ATT_PART_W + NH*G*G layout) and, with the fused embedding, d{embed w, b}
+// =====================================================================================================
+// chunk planes [plane][token][16 B] of a tile (see the file header):
+//   0-1 q -> dq | 2-3 k -> dk | 4-5 v -> dv | 6-7 g_y | 8-9 g_embed (fused embedding only) | 10-11 xn | 12-13 dO -> o | 14 ones | 15 (x, 1, 0..)
+// weight gradients: D[M x 48] += [dq | dk | dv | g_y (| g_e | ...)]^T [xn | o | 1 | (x, 1)], M = 64 (128 with the fused embedding)
+constexpr int A_Q = 0, A_K = 2, A_V = 4, A_GY = 6, A_GE = 8, A_XN = 10, A_DO = 12, A_ONE = 14, A_X1 = 15, A_PLANES = 16;
+constexpr int B_QKV = 0, B_DO = 48, B_DXN = 64, B_WACC = 80, B_COLS = 128;       // TMEM columns
+
+struct AttnBwdSm {
+    unsigned char pl[A_PLANES * PLANE];
+    unsigned char ones0[PLANE];          // A operand of the bias GEMM step (chunk 1 = the zero chunk zq)
+    unsigned char bq[48 * 16];           // B(n, k) chunk 0 of the bias step: k = 0 -> hi(bqkv[n]), k = 1 -> lo (q rows pre-scaled)
+    unsigned char wqkv[48 * 32];         // B(n = o, k = c) = qkv.weight[n][k] (q rows pre-scaled)       qkv = xn Wqkv^T
+    unsigned char wpt[16 * 32];          // B(n = e, k = c) = proj.weight[k][n]                          dO = g_y Wproj
+    unsigned char wqt[16 * 96];          // B(n = c, k = o) = qkv.weight[k][n]                           dxn = [dq|dk|dv] Wqkv
+    unsigned char zq[PLANE];             // zeros: chunk 1 of both bias-step operands, 128 rows for the A side (after ones0 / bq: LBO > 0)
+    uint64_t mma_bar;
+    uint32_t tmem_slot;
+};
+
+template <int WD, int WH, int WW, bool EMB>
+__global__ void __launch_bounds__(NT, 2)
+swin_attn_bwd_umma_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gy, __nv_bfloat16* __restrict__ gx,
+                          const float* __restrict__ params, int64_t pstride, const int* __restrict__ rel_index,
+                          float* __restrict__ partials, Geom g) {
+    constexpr int G = WD * WH * WW;
+    constexpr int PART = ATT_PART_W + NH * G * G;
+    constexpr int DBS = dbs(G), DBW = NH * G * DBS;            // per-warp bias-gradient table (conflict-free 8-byte RMW)
+    constexpr int WM = EMB ? 128 : 64;                         // rows of the weight-gradient GEMM
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    AttnBwdSm& S = *reinterpret_cast<AttnBwdSm*>(smem_raw);
+    float* Bn = reinterpret_cast<float*>(smem_raw + sizeof(AttnBwdSm));      // [NH][G][bns(G)]
+    float* dBw_all = Bn + NH * G * bns(G);                                  // [4 warps][DBW]
+    const int v = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* P = params + (int64_t)v * pstride;
+    const POff po(g.tbl);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_slot)), "n"(B_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) { mbar_init(smem_u32(&S.mma_bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    const float qs = g.scale * LOG2E;
+    stage_b_kmajor(S.wqkv, P + po.qkv_w, C, 48, 16, 16, qs);
+    stage_b_kmajor_t(S.wpt, P + po.proj_w, C, 16, 16);
+    stage_b_kmajor_t(S.wqt, P + po.qkv_w, C, 16, 48);
+    for (int e = tid; e < 48 * 8; e += NT) {
+        const int n = e >> 3, k = e & 7;
+        const float b = P[po.qkv_b + n] * (n < 16 ? qs : 1.f);
+        const __nv_bfloat16 hi = __float2bfloat16(b);
+        const __nv_bfloat16 lo = __float2bfloat16(b - __bfloat162float(hi));
+        reinterpret_cast<__nv_bfloat16*>(S.bq)[e] = k == 0 ? hi : (k == 1 ? lo : __float2bfloat16(0.f));
+    }
+    const uint32_t pl = smem_u32(S.pl);
+    sts128(pl + A_ONE * PLANE + tid * 16, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    sts128(pl + A_X1 * PLANE + tid * 16, 0u, 0u, 0u, 0u);
+    sts128(pl + A_GE * PLANE + tid * 16, 0u, 0u, 0u, 0u);
+    sts128(pl + (A_GE + 1) * PLANE + tid * 16, 0u, 0u, 0u, 0u);
+    sts128(smem_u32(S.ones0) + tid * 16, 0x3F803F80u, 0u, 0u, 0u);
+    sts128(smem_u32(S.zq) + tid * 16, 0u, 0u, 0u, 0u);
+    for (int e = tid; e < 4 * DBW; e += NT) dBw_all[e] = 0.f;
+    stage_bias_pad<G>(Bn, P, rel_index);
+    proxy_fence();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = S.tmem_slot;
+    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t mma_bar = smem_u32(&S.mma_bar);
+    uint32_t n_commit = 0;
+    float* dB = dBw_all + warp * DBW;
+    const int gq = lane / 4, c0 = 2 * (lane % 4);
+    const uint32_t my_row = (uint32_t)(tid * 16);                                            // this token's 16 bytes inside a plane
+    // fragment-layout store address (row g, column pair c0 of chunk h): + h * PLANE + r * 128
+    const uint32_t fr = (uint32_t)((warp * 32 + gq) * 16 + (lane % 4) * 4);
+    const float* ew = g.emb_w + v * C;
+    const float* eb = g.emb_b + v * C;
+
+    const int n_tiles = (g.n_wg + 3) / 4;
+    bool first = true;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const Tok tk = map_token<WD, WH, WW>(g, v, tile * 4 + warp, lane);
+        const bool masked = __any_sync(0xffffffffu, tk.border);
+        // ---- R0: rows -> LN1 -> planes xn | g_y -> qkv and dO GEMMs ----
+        float rstd, xin = 0.f;
+        {
+            float xr[16];
+            if (EMB) {
+                xin = tk.valid ? __ldg(g.emb_x + (tk.off >> 4)) : 0.f;
+                float e[16];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) e[c] = __ldg(ew + c) * xin + __ldg(eb + c);
+                ln_row(e, xr);
+            } else {
+                uint32_t px[8];
+                if (tk.valid) ldg_row16(x + tk.off, px);
+                else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) px[i] = 0u;
+                }
+                unpack16(px, xr);
+            }
+            uint32_t pg[8];
+            if (tk.valid) ldg_row16(gy + tk.off, pg);
+            else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) pg[i] = 0u;
+            }
+            float xn[16];
+            rstd = ln_row(xr, xn);
+            uint32_t pn[8];
+            if (tk.valid) pack16(xn, pn);
+            else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) pn[i] = 0u;
+            }
+            sts128(pl + A_XN * PLANE + my_row, pn[0], pn[1], pn[2], pn[3]);
+            sts128(pl + (A_XN + 1) * PLANE + my_row, pn[4], pn[5], pn[6], pn[7]);
+            sts128(pl + A_GY * PLANE + my_row, pg[0], pg[1], pg[2], pg[3]);
+            sts128(pl + (A_GY + 1) * PLANE + my_row, pg[4], pg[5], pg[6], pg[7]);
+            if (EMB) sts128(pl + A_X1 * PLANE + my_row, pk(xin, 1.f), 0u, 0u, 0u);
+        }
+        proxy_fence();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            umma_ss(tmem + B_QKV, make_desc(pl + A_XN * PLANE, PLANE, 128), make_desc(smem_u32(S.wqkv), 48 * 16, 128), idesc(128, 48), 0);
+            umma_ss(tmem + B_QKV, make_desc(smem_u32(S.ones0), smem_u32(S.zq) - smem_u32(S.ones0), 128),
+                    make_desc(smem_u32(S.bq), smem_u32(S.zq) - smem_u32(S.bq), 128), idesc(128, 48), 1);
+            umma_ss(tmem + B_DO, make_desc(pl + A_GY * PLANE, PLANE, 128), make_desc(smem_u32(S.wpt), 16 * 16, 128), idesc(128, 16), 0);
+            umma_commit(mma_bar);
+        }
+        mbar_wait(mma_bar, n_commit++ & 1u);
+        tc_fence_after();
+        // ---- R1: q | k | v | dO rows -> bf16 planes (ldmatrix sources of the warp's attention core) ----
+        {
+            float t16[16];
+            uint32_t pq[8];
+#pragma unroll
+            for (int part = 0; part < 4; ++part) {
+                tmem_ld16(tlane + B_QKV + 16 * part, t16);
+                pack16(t16, pq);
+                const uint32_t dst = pl + (part < 3 ? 2 * part : A_DO) * PLANE + my_row;
+                sts128(dst, pq[0], pq[1], pq[2], pq[3]);
+                sts128(dst + PLANE, pq[4], pq[5], pq[6], pq[7]);
+            }
+        }
+        __syncwarp();
+        // ---- attention forward recompute + backward, one head at a time; results go back into the planes ----
+        uint32_t st_dq[2][4], st_dk[2][4], st_dv[2][4], st_o[2][4];          // packed bf16 pairs [h][r] awaiting the plane stores
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+            // fragments of head h (chunk h of each plane pair): plain and transposed 8x8 blocks of q, k, v, dO (row groups 0..3)
+            uint32_t qa[4], qt[4], kb[4], kt[4], vb[4], vt[4], da[4], dt[4];
+            {
+                const uint32_t a0 = pl + (uint32_t)(h * PLANE + (warp * 32 + (lane & 7) + 8 * (lane >> 3)) * 16);   // matrices = row groups 0..3
+                ldsm_x4(a0 + A_Q * PLANE, qa[0], qa[1], qa[2], qa[3]);
+                ldsm_x4_t(a0 + A_Q * PLANE, qt[0], qt[1], qt[2], qt[3]);
+                ldsm_x4(a0 + A_K * PLANE, kb[0], kb[1], kb[2], kb[3]);
+                ldsm_x4_t(a0 + A_K * PLANE, kt[0], kt[1], kt[2], kt[3]);
+                ldsm_x4(a0 + A_V * PLANE, vb[0], vb[1], vb[2], vb[3]);
+                ldsm_x4_t(a0 + A_V * PLANE, vt[0], vt[1], vt[2], vt[3]);
+                ldsm_x4(a0 + A_DO * PLANE, da[0], da[1], da[2], da[3]);
+                ldsm_x4_t(a0 + A_DO * PLANE, dt[0], dt[1], dt[2], dt[3]);
+            }
+            // scores (log2 domain) + bias + mask + softmax (normalised)
+            float p[2][4][4];
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int nj = 0; nj < 4; ++nj) {
+                    p[mi][nj][0] = p[mi][nj][1] = p[mi][nj][2] = p[mi][nj][3] = 0.f;
+                    if (AttnU<G>::tile_needed(2 * mi, nj) || AttnU<G>::tile_needed(2 * mi + 1, nj)) mma1688(p[mi][nj], qa[2 * mi], qa[2 * mi + 1], kb[nj]);
+                }
+            int cj[4][2], cr[4];
+            if (masked) {
+#pragma unroll
+                for (int nj = 0; nj < 4; ++nj) {
+                    cj[nj][0] = __shfl_sync(0xffffffffu, tk.code, 8 * nj + c0);
+                    cj[nj][1] = __shfl_sync(0xffffffffu, tk.code, 8 * nj + c0 + 1);
+                    cr[nj] = __shfl_sync(0xffffffffu, tk.code, gq + 8 * nj);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int mi = r / 2, hf = r % 2;
+                const int il = (gq + 8 * r) % G;
+                float mx = -INFINITY;
+#pragma unroll
+                for (int nj = 0; nj < 4; ++nj) {
+                    if (AttnU<G>::tile_needed(r, nj)) {
+                        const int jl = (8 * nj + c0) % G;
+                        const float2 b = *reinterpret_cast<const float2*>(Bn + (h * G + il) * bns(G) + jl);
+                        p[mi][nj][2 * hf] += b.x; p[mi][nj][2 * hf + 1] += b.y;
+                        if (masked) {
+                            if (cj[nj][0] != cr[r]) p[mi][nj][2 * hf] += -100.0f * LOG2E;
+                            if (cj[nj][1] != cr[r]) p[mi][nj][2 * hf + 1] += -100.0f * LOG2E;
+                        }
+                        mx = fmaxf(mx, fmaxf(p[mi][nj][2 * hf], p[mi][nj][2 * hf + 1]));
+                    }
+                }
+                mx = quad_max(mx);
+                float sum = 0.f;
+#pragma unroll
+                for (int nj = 0; nj < 4; ++nj) {
+                    if (AttnU<G>::tile_needed(r, nj)) {
+                        const float e0 = ex2_approx(p[mi][nj][2 * hf] - mx), e1 = ex2_approx(p[mi][nj][2 * hf + 1] - mx);
+                        p[mi][nj][2 * hf] = e0; p[mi][nj][2 * hf + 1] = e1; sum += e0 + e1;
+                    } else { p[mi][nj][2 * hf] = 0.f; p[mi][nj][2 * hf + 1] = 0.f; }
+                }
+                const float inv = __fdividef(1.f, quad_sum(sum));
+#pragma unroll
+                for (int nj = 0; nj < 4; ++nj) { p[mi][nj][2 * hf] *= inv; p[mi][nj][2 * hf + 1] *= inv; }
+            }
+            // packed P blocks pb[ib][jb] (row group ib, key group jb); o_h = P V_h
+            uint32_t pb[4][4];
+#pragma unroll
+            for (int ib = 0; ib < 4; ++ib)
+#pragma unroll
+                for (int jb = 0; jb < 4; ++jb) pb[ib][jb] = pk(p[ib / 2][jb][2 * (ib % 2)], p[ib / 2][jb][2 * (ib % 2) + 1]);
+            float oh[2][4];                                                   // [mi][c-fragment]: rows g + 8(2mi), g + 8(2mi+1)
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi) {
+                oh[mi][0] = oh[mi][1] = oh[mi][2] = oh[mi][3] = 0.f;
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk) {
+                    if (!(AttnU<G>::tile_needed(2 * mi, 2 * kk) || AttnU<G>::tile_needed(2 * mi, 2 * kk + 1) || AttnU<G>::tile_needed(2 * mi + 1, 2 * kk) ||
+                          AttnU<G>::tile_needed(2 * mi + 1, 2 * kk + 1))) continue;
+                    mma16816(oh[mi], pb[2 * mi][2 * kk], pb[2 * mi + 1][2 * kk], pb[2 * mi][2 * kk + 1], pb[2 * mi + 1][2 * kk + 1], vt[2 * kk], vt[2 * kk + 1]);
+                }
+            }
+            // D_r = <dO_r, O_r> over the 8 dims of head h;  dP = dO_h V_h^T;  dS = P o (dP - D)
+            float Dr[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                Dr[r] = quad_sum(bf_lo(da[r]) * oh[r / 2][2 * (r % 2)] + bf_hi(da[r]) * oh[r / 2][2 * (r % 2) + 1]);
+            float ds[2][4][4];
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int nj = 0; nj < 4; ++nj) {
+                    ds[mi][nj][0] = ds[mi][nj][1] = ds[mi][nj][2] = ds[mi][nj][3] = 0.f;
+                    if (AttnU<G>::tile_needed(2 * mi, nj) || AttnU<G>::tile_needed(2 * mi + 1, nj)) {
+                        mma1688(ds[mi][nj], da[2 * mi], da[2 * mi + 1], vb[nj]);
+#pragma unroll
+                        for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+                            for (int b = 0; b < 2; ++b) ds[mi][nj][2 * hf + b] = p[mi][nj][2 * hf + b] * (ds[mi][nj][2 * hf + b] - Dr[2 * mi + hf]);
+                    }
+                }
+            // relative-position-bias gradient: warp-private table, every (i, j) pair owned by exactly one lane
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int nj = 0; nj < 4; ++nj)
+                    if (AttnU<G>::tile_needed(r, nj)) {
+                        const int il = (gq + 8 * r) % G, jl = (8 * nj + c0) % G;
+                        float2* pd = reinterpret_cast<float2*>(&dB[(h * G + il) * DBS + jl]);
+                        float2 acc2 = *pd;
+                        acc2.x += ds[r / 2][nj][2 * (r % 2)]; acc2.y += ds[r / 2][nj][2 * (r % 2) + 1];
+                        *pd = acc2;
+                    }
+            uint32_t dsb[4][4];
+#pragma unroll
+            for (int ib = 0; ib < 4; ++ib)
+#pragma unroll
+                for (int jb = 0; jb < 4; ++jb) dsb[ib][jb] = pk(ds[ib / 2][jb][2 * (ib % 2)], ds[ib / 2][jb][2 * (ib % 2) + 1]);
+            // dQ_h = dS K_h (K = keys j);  dK_h = dS^T Q_h, dV_h = P^T dO_h (rows j, K = queries i)
+            float dq[2][4], dk[2][4], dv[2][4];
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi) {
+                dq[mi][0] = dq[mi][1] = dq[mi][2] = dq[mi][3] = 0.f;
+                dk[mi][0] = dk[mi][1] = dk[mi][2] = dk[mi][3] = 0.f;
+                dv[mi][0] = dv[mi][1] = dv[mi][2] = dv[mi][3] = 0.f;
+            }
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi)
+                    mma16816(dq[mi], dsb[2 * mi][2 * kk], dsb[2 * mi + 1][2 * kk], dsb[2 * mi][2 * kk + 1], dsb[2 * mi + 1][2 * kk + 1], kt[2 * kk], kt[2 * kk + 1]);
+#pragma unroll
+            for (int ik = 0; ik < 2; ++ik)
+#pragma unroll
+                for (int jm = 0; jm < 2; ++jm) {
+                    mma16816(dk[jm], movm(dsb[2 * ik][2 * jm]), movm(dsb[2 * ik][2 * jm + 1]), movm(dsb[2 * ik + 1][2 * jm]), movm(dsb[2 * ik + 1][2 * jm + 1]),
+                             qt[2 * ik], qt[2 * ik + 1]);
+                    mma16816(dv[jm], movm(pb[2 * ik][2 * jm]), movm(pb[2 * ik][2 * jm + 1]), movm(pb[2 * ik + 1][2 * jm]), movm(pb[2 * ik + 1][2 * jm + 1]),
+                             dt[2 * ik], dt[2 * ik + 1]);
+                }
+            // gradient w.r.t. the unscaled projections: dq carries `scale`; dK was formed with q * scale * log2(e)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                st_dq[h][r] = pk(dq[r / 2][2 * (r % 2)] * g.scale, dq[r / 2][2 * (r % 2) + 1] * g.scale);
+                st_dk[h][r] = pk(dk[r / 2][2 * (r % 2)] * (1.f / LOG2E), dk[r / 2][2 * (r % 2) + 1] * (1.f / LOG2E));
+                st_dv[h][r] = pk(dv[r / 2][2 * (r % 2)], dv[r / 2][2 * (r % 2) + 1]);
+                st_o[h][r] = pk(oh[r / 2][2 * (r % 2)], oh[r / 2][2 * (r % 2) + 1]);
+            }
+        }
+        __syncwarp();                 // every lane of the warp has read its q / k / v / dO fragments: the rows can be overwritten
+#pragma unroll
+        for (int h = 0; h < NH; ++h)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const uint32_t a = pl + fr + h * PLANE + r * 128;
+                sts32(a + A_Q * PLANE, st_dq[h][r]);
+                sts32(a + A_K * PLANE, st_dk[h][r]);
+                sts32(a + A_V * PLANE, st_dv[h][r]);
+                sts32(a + A_DO * PLANE, st_o[h][r]);
+            }
+        proxy_fence();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            // dxn = [dq | dk | dv] Wqkv  (K = 48 in three steps)
+#pragma unroll
+            for (int s3 = 0; s3 < 3; ++s3)
+                umma_ss(tmem + B_DXN, make_desc(pl + 2 * s3 * PLANE, PLANE, 128), make_desc(smem_u32(S.wqt) + s3 * 512, 16 * 16, 128), idesc(128, 16), s3 > 0 ? 1u : 0u);
+            if (!EMB) {
+                // weight gradients: D[64 x 48] += [dq | dk | dv | g_y]^T [xn | o | 1 | 0] over the tile's 128 tokens (MN-major views)
+#pragma unroll
+                for (int s8 = 0; s8 < 8; ++s8)
+                    umma_ss(tmem + B_WACC, make_desc(pl + s8 * 256, 128, PLANE), make_desc(pl + A_XN * PLANE + s8 * 256, 128, PLANE),
+                            idesc(WM, 48, 1, 1), (first && s8 == 0) ? 0u : 1u);
+            }
+            umma_commit(mma_bar);
+        }
+        mbar_wait(mma_bar, n_commit++ & 1u);
+        tc_fence_after();
+        // ---- R2: LayerNorm backward + residual -> g_x (or the fused embedding backward) ----
+        {
+            float d[16], xn[16], gyr[16];
+            tmem_ld16(tlane + B_DXN, d);
+            {
+                const uint4 a = lds128(pl + A_XN * PLANE + my_row), b = lds128(pl + (A_XN + 1) * PLANE + my_row);
+                const uint32_t pn[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                unpack16(pn, xn);
+                const uint4 c = lds128(pl + A_GY * PLANE + my_row), e = lds128(pl + (A_GY + 1) * PLANE + my_row);
+                const uint32_t pg[8] = {c.x, c.y, c.z, c.w, e.x, e.y, e.z, e.w};
+                unpack16(pg, gyr);
+            }
+            float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) { m1 += d[c]; m2 += d[c] * xn[c]; }
+            m1 *= (1.f / 16.f); m2 *= (1.f / 16.f);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) d[c] = gyr[c] + rstd * (d[c] - m1 - xn[c] * m2);
+            if (EMB) {
+                // the block input IS the embedding output: LayerNorm backward of the embedding here; its weight / bias sums
+                // (sum_t ge x, sum_t ge) come out of the weight-gradient GEMM below (rows 64..79 against the (x, 1) columns)
+                float e[16], en[16];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) e[c] = __ldg(ew + c) * xin + __ldg(eb + c);
+                const float rs = ln_row(e, en);
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) { s1 += d[c]; s2 += d[c] * en[c]; }
+                s1 *= (1.f / 16.f); s2 *= (1.f / 16.f);
+                uint32_t pe[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float g0 = tk.valid ? rs * (d[2 * i] - s1 - en[2 * i] * s2) : 0.f;
+                    const float g1 = tk.valid ? rs * (d[2 * i + 1] - s1 - en[2 * i + 1] * s2) : 0.f;
+                    pe[i] = pk(g0, g1);
+                }
+                sts128(pl + A_GE * PLANE + my_row, pe[0], pe[1], pe[2], pe[3]);
+                sts128(pl + (A_GE + 1) * PLANE + my_row, pe[4], pe[5], pe[6], pe[7]);
+            } else if (tk.valid) {
+                uint32_t po_[8];
+                pack16(d, po_);
+                st8u(gx + tk.off, po_);
+            }
+        }
+        if (EMB) {
+            // with the fused embedding the weight-gradient GEMM also needs g_e (written above): D[128 x 48] += [dq | dk | dv | g_y | g_e | ..]^T
+            // [xn | o | 1 | (x, 1)], one more round
+            proxy_fence();
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+#pragma unroll
+                for (int s8 = 0; s8 < 8; ++s8)
+                    umma_ss(tmem + B_WACC, make_desc(pl + s8 * 256, 128, PLANE), make_desc(pl + A_XN * PLANE + s8 * 256, 128, PLANE),
+                            idesc(WM, 48, 1, 1), (first && s8 == 0) ? 0u : 1u);
+                umma_commit(mma_bar);
+            }
+            mbar_wait(mma_bar, n_commit++ & 1u);        // the planes are rewritten by the next tile
+            tc_fence_after();
+        }
+        first = false;
+        tc_fence_before();
+    }
+    // ---- per-CTA partials: qkv_w[48*16] | qkv_b[48] | proj_w[16*16] | proj_b[16] | dB[h][i][j] ----
+    __syncthreads();
+    tc_fence_after();
+    float* part = partials + ((int64_t)v * gridDim.x + blockIdx.x) * PART;
+    const bool any = (int)blockIdx.x < n_tiles;
+    if (EMB) {
+        // M = 128: row m in lane m.  rows 0..47 = dq | dk | dv, 48..63 = g_y, 64..79 = g_e
+        float w[16], o2[16], b[16];
+        tmem_ld16(tlane + B_WACC, w);
+        tmem_ld16(tlane + B_WACC + 16, o2);
+        tmem_ld16(tlane + B_WACC + 32, b);
+        if (tid < 48) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) part[tid * C + c] = any ? w[c] : 0.f;
+            part[3 * C * C + tid] = any ? b[0] : 0.f;
+        } else if (tid < 64) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) part[3 * C * C + 3 * C + (tid - 48) * C + c] = any ? o2[c] : 0.f;
+            part[3 * C * C + 3 * C + C * C + tid - 48] = any ? b[0] : 0.f;
+        } else if (tid < 80 && g.emb_gpart != nullptr) {
+            float* pe = g.emb_gpart + ((int64_t)v * gridDim.x + blockIdx.x) * 32;
+            pe[tid - 64] = any ? b[8] : 0.f;            // column 40: sum_t g_e[c] x
+            pe[16 + tid - 64] = any ? b[9] : 0.f;       // column 41: sum_t g_e[c]
+        }
+    } else {
+        // M = 64: row m in lane (m % 16) + 32 (m / 16): warp w holds rows 16 w .. 16 w + 15 in its lanes 0..15
+        float w[16], o2[16], b[16];
+        tmem_ld16(tlane + B_WACC, w);
+        tmem_ld16(tlane + B_WACC + 16, o2);
+        tmem_ld16(tlane + B_WACC + 32, b);
+        if (lane < 16) {
+            const int m = 16 * warp + lane;
+            if (m < 48) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) part[m * C + c] = any ? w[c] : 0.f;
+                part[3 * C * C + m] = any ? b[0] : 0.f;
+            } else {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) part[3 * C * C + 3 * C + (m - 48) * C + c] = any ? o2[c] : 0.f;
+                part[3 * C * C + 3 * C + C * C + m - 48] = any ? b[0] : 0.f;
+            }
+        }
+    }
+    for (int e = tid; e < NH * G * G; e += NT) {
+        const int hi = e / G, jl = e % G;     // hi = h * G + i_local
+        float sum = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) sum += dBw_all[w * DBW + hi * DBS + jl];
+        part[ATT_PART_W + e] = sum;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(B_COLS) : "memory");
+}
+
+template <int WD, int WH, int WW>
+int launch_attn_bwd(const idee_swin_desc* d, const Geom& g, const __nv_bfloat16* x, __nv_bfloat16* gx, const float* params,
+                    const int* rel_index, float* gparams, float* part_attn, float* part_mlp, float* part_emb, int per_v, int per_v_mlp,
+                    cudaStream_t st) {
+    constexpr int G = WD * WH * WW;
+    const size_t smem = sizeof(AttnBwdSm) + sizeof(float) * (NH * G * bns(G) + 4 * NH * G * dbs(G));
+    if (g.emb_x) {
+        Geom ge = g;
+        ge.emb_gpart = d->embed_gw ? part_emb : nullptr;
+        IDEE_CUDA(cudaFuncSetAttribute(swin_attn_bwd_umma_kernel<WD, WH, WW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "swin_attn_bwd(umma)");
+        swin_attn_bwd_umma_kernel<WD, WH, WW, true><<<dim3(per_v, d->V), NT, smem, st>>>(x, gx, gx, params, d->param_stride, rel_index, part_attn, ge);
+        IDEE_LAUNCH_CHECK("swin_attn_bwd(umma,embed)");
+        if (d->embed_gw) {
+            embed_grad_finalize_kernel<<<d->V, 32, 0, st>>>(part_emb, per_v, d->embed_gw, d->embed_gb);
+            IDEE_LAUNCH_CHECK("embed_grad_finalize");
+        }
+    } else {
+        IDEE_CUDA(cudaFuncSetAttribute(swin_attn_bwd_umma_kernel<WD, WH, WW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "swin_attn_bwd(umma)");
+        swin_attn_bwd_umma_kernel<WD, WH, WW, false><<<dim3(per_v, d->V), NT, smem, st>>>(x, gx, gx, params, d->param_stride, rel_index, part_attn, g);
+        IDEE_LAUNCH_CHECK("swin_attn_bwd(umma)");
+    }
+    swin_grad_finalize_kernel<G><<<d->V, 1024, 0, st>>>(part_attn, part_mlp, per_v, per_v_mlp, rel_index, gparams, d->param_stride, g.tbl);
+    IDEE_LAUNCH_CHECK("swin_grad_finalize");
+    return 0;
 }
 
 }  // namespace swu

@@ -161,6 +161,7 @@ class SwinBlock(torch.autograd.Function):
             raise RuntimeError("swin_block: packed parameter size mismatch")
         if L.swin_umma() and window[0] * window[1] * window[2] >= 8:
             # tcgen05 / TMEM kernels: bf16 tokens in, bf16 tokens out (the residual stream lives in HBM as bf16)
+            in_dtype = x.dtype
             x = x.contiguous() if x.dtype == torch.bfloat16 else x.to(torch.bfloat16).contiguous()
             d = _swin_desc(x, window, shift, rpb_rows, scale, pack, heads, hidden)
             out = torch.empty_like(x)
@@ -171,6 +172,7 @@ class SwinBlock(torch.autograd.Function):
             if need_bwd:
                 ctx.save_for_backward(x, ymid, rel_index)
                 ctx.pack, ctx.args = pack, (window, shift, rpb_rows, scale, heads, hidden)
+                ctx.in_dtype = in_dtype
             return out
         x = _f32c(x)
         d = _swin_desc(x, window, shift, rpb_rows, scale, pack, heads, hidden)
@@ -202,6 +204,17 @@ class SwinBlock(torch.autograd.Function):
         window, shift, rpb_rows, scale, heads, hidden = ctx.args
         flat = pack.tensor()
         d = _swin_desc(x, window, shift, rpb_rows, scale, pack, heads, hidden)
+        if x.dtype == torch.bfloat16:          # tcgen05 kernels: bf16 token gradients in and out
+            gout = gout.contiguous() if gout.dtype == torch.bfloat16 else gout.to(torch.bfloat16).contiguous()
+            gx = torch.empty_like(x)
+            gflat = pack.grad_out(flat)
+            nws = lib.idee_swin_block_bwd_workspace_bytes(C.byref(d))
+            ws = L.workspace(nws, x.device)
+            L.run("swin_block_bwd", lib.idee_swin_block_bwd, C.byref(d), x.data_ptr(), ymid.data_ptr(), gout.data_ptr(), gx.data_ptr(),
+                  flat.data_ptr(), rel_index.data_ptr(), gflat.data_ptr(), ws.data_ptr(), nws, L.stream(), tag=f"w{window} s{shift}")
+            if ctx.in_dtype != torch.bfloat16:
+                gx = gx.to(ctx.in_dtype)
+            return (gx, None, None, None, None, None, None, None, None, None, *pack.split_grad(gflat))
         gout = _f32c(gout)
         gx = torch.empty_like(x)
         gflat = pack.grad_out(flat)
@@ -251,7 +264,10 @@ class SwinBlockEmbed(torch.autograd.Function):
         flat, w, b = pack.tensor(), wpack.tensor(), bpack.tensor()
         d = _swin_desc(ymid, window, shift, rpb_rows, scale, pack, heads, hidden)
         d.embed_x, d.embed_w, d.embed_b = x.data_ptr(), w.data_ptr(), b.data_ptr()
-        gout = _f32c(gout)
+        if ymid.dtype == torch.bfloat16:
+            gout = gout.contiguous() if gout.dtype == torch.bfloat16 else gout.to(torch.bfloat16).contiguous()
+        else:
+            gout = _f32c(gout)
         gtok = torch.empty_like(ymid)                      # scratch between the MLP and attention halves of the backward
         gflat = pack.grad_out(flat)
         gw, gb = wpack.grad_out(w), bpack.grad_out(b)
