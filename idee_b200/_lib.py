@@ -18,7 +18,7 @@ c_i64, c_int, c_f32, c_vp, c_sz = C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c
 class SwinDesc(C.Structure):
     _fields_ = [(n, c_int) for n in ("N", "V", "T", "H", "W", "C", "heads", "hidden", "wd", "wh", "ww", "st", "sh", "sw", "rpb_rows")] + \
                [("scale", c_f32), ("param_stride", c_i64), ("precision", c_int)] + \
-               [(n, c_vp) for n in ("embed_x", "embed_w", "embed_b", "embed_gw", "embed_gb")] + [("act_dtype", c_int)]
+               [(n, c_vp) for n in ("embed_x", "embed_w", "embed_b", "embed_gw", "embed_gb")] + [("act_dtype", c_int), ("x_dtype", c_int), ("out_dtype", c_int)]
 
 
 class ConvDesc(C.Structure):

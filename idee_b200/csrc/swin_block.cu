@@ -49,6 +49,7 @@ struct Geom {
     void* out16;  // forward, bf16 path: optional bf16 copy of the block output (for the proj conv that consumes it)
     const float* emb_x; const float* emb_w; const float* emb_b;   // bf16 path: fused patch embedding (see idee_swin_desc)
     float* emb_gpart;                                             // backward: per-CTA partials [V][CTAs][32] of the embedding gradients
+    int x32, out32;                                               // tcgen05 path: the block input / output tokens are fp32 (else bf16)
 };
 
 __device__ __forceinline__ int region_id(int p, int S, int ws, int ss) {
@@ -643,6 +644,7 @@ int make_geom(Geom& g, const idee_swin_desc* d, const char* who) {
     IDEE_REQUIRE(d->embed_x == nullptr || (d->precision == 1 && d->embed_w && d->embed_b),
                  "%s: the fused patch embedding needs precision 1 and embed_w / embed_b", who);
     g.emb_x = d->embed_x; g.emb_w = d->embed_w; g.emb_b = d->embed_b; g.emb_gpart = nullptr;
+    g.x32 = d->x_dtype == 0; g.out32 = d->out_dtype == 0;
     IDEE_REQUIRE((d->embed_gw == nullptr) == (d->embed_gb == nullptr) && (d->embed_gw == nullptr || d->embed_x != nullptr),
                  "%s: embed_gw / embed_gb come together and need the fused patch embedding", who);
     return 0;
@@ -669,8 +671,8 @@ int launch_fwd(const idee_swin_desc* d, const Geom& g, const float* x, float* ou
         int per_v = idee_num_sms() * 4 / d->V;
         if (per_v > n_tiles) per_v = n_tiles;
         if (per_v < 1) per_v = 1;
-        auto bx = reinterpret_cast<const __nv_bfloat16*>(x);
-        auto bo = reinterpret_cast<__nv_bfloat16*>(out);
+        const void* bx = x;
+        void* bo = out;
         auto by = reinterpret_cast<__nv_bfloat16*>(ymid);
         if (emb) {
             IDEE_CUDA(cudaFuncSetAttribute(swu::swin_fwd_umma_kernel<WD, WH, WW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "swin_block_fwd(umma)");
@@ -740,7 +742,7 @@ int launch_bwd(const idee_swin_desc* d, const Geom& g, const float* x, const flo
         float* u_attn = ws;
         float* u_mlp = u_attn + (size_t)d->V * pv_att * APS;
         float* u_emb = u_mlp + (size_t)d->V * pv_mlp * MLP_PART;
-        auto bx = reinterpret_cast<const __nv_bfloat16*>(x);
+        const void* bx = x;
         auto bym = reinterpret_cast<const __nv_bfloat16*>(ymid);
         auto bgo = reinterpret_cast<const __nv_bfloat16*>(gout);
         auto bgx = reinterpret_cast<__nv_bfloat16*>(gx);

@@ -308,7 +308,7 @@ __device__ __forceinline__ void stage_b_kmajor_t(unsigned char* dst, const float
 constexpr int F_DQKV = 0, F_DH = 0, F_DP = 64, F_DO = 64, F_AX = 80, F_AH = 96, F_COLS = 128;
 
 struct FwdSm {          // dynamic shared memory of the forward kernel
-    unsigned char xbuf[2][NT * 32];                  // bf16 token tiles (TMA bulk destination), double buffered
+    unsigned char xbuf[2][NT * 64];                  // token tiles (TMA bulk destination; 32 B bf16 or 64 B fp32 rows), double buffered
     unsigned char stg[4][32 * STG];                  // per-warp q | k | v staging
     unsigned char a2[2 * PLANE];                     // attention output as the proj GEMM's A operand
     unsigned char wqkv[48 * 32], wproj[16 * 32], w1[64 * 32], w2[16 * 128];
@@ -320,7 +320,7 @@ struct FwdSm {          // dynamic shared memory of the forward kernel
 
 template <int WD, int WH, int WW, bool EMB>
 __global__ void __launch_bounds__(NT, 4)
-swin_fwd_umma_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ ymid,
+swin_fwd_umma_kernel(const void* __restrict__ x, void* __restrict__ out, __nv_bfloat16* __restrict__ ymid,
                      const float* __restrict__ params, int64_t pstride, const int* __restrict__ rel_index, Geom g) {
     constexpr int G = WD * WH * WW;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -361,18 +361,19 @@ swin_fwd_umma_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restr
     uint32_t n_commit = 0;                                                   // commits so far -> wait parity
 
     const int n_tiles = (g.n_wg + 3) / 4;
-    const uint32_t my_slot = (uint32_t)(tid * 32);
+    const uint32_t my_slot = (uint32_t)(tid * 64);
+    const uint32_t row_bytes = g.x32 ? 64u : 32u;
     // token tile prefetch (TMA bulk copy of this thread's 32-byte token row into its slot of the double buffer)
     auto prefetch = [&](int tile, int buf) {
         if (EMB) return;
         const Tok t = map_token<WD, WH, WW>(g, v, tile * 4 + warp, lane);
         const uint32_t bar = smem_u32(&S.load_bar[buf][warp]);
         const unsigned m = __ballot_sync(0xffffffffu, t.valid);
-        if (lane == 0) mbar_expect_tx(bar, 32u * __popc(m));
+        if (lane == 0) mbar_expect_tx(bar, row_bytes * __popc(m));
         __syncwarp();
         const uint32_t dst = smem_u32(S.xbuf[buf]) + my_slot;
-        if (t.valid) bulk_g2s(dst, x + t.off, 32, bar);
-        else { sts128(dst, 0, 0, 0, 0); sts128(dst + 16, 0, 0, 0, 0); }
+        if (t.valid) bulk_g2s(dst, reinterpret_cast<const unsigned char*>(x) + t.off * (g.x32 ? 4 : 2), row_bytes, bar);
+        else { sts128(dst, 0, 0, 0, 0); sts128(dst + 16, 0, 0, 0, 0); sts128(dst + 32, 0, 0, 0, 0); sts128(dst + 48, 0, 0, 0, 0); }
     };
     if ((int)blockIdx.x < n_tiles) prefetch(blockIdx.x, 0);
 
@@ -394,9 +395,17 @@ swin_fwd_umma_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restr
         } else {
             mbar_wait(smem_u32(&S.load_bar[buf][warp]), (uint32_t)(it >> 1) & 1u);
             const uint32_t src = smem_u32(S.xbuf[buf]) + my_slot;
-            const uint4 lo = lds128(src), hi = lds128(src + 16);
-            const uint32_t pr[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-            unpack16(pr, xr);
+            if (g.x32) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint4 q4 = lds128(src + 16 * i);
+                    xr[4 * i] = __uint_as_float(q4.x); xr[4 * i + 1] = __uint_as_float(q4.y); xr[4 * i + 2] = __uint_as_float(q4.z); xr[4 * i + 3] = __uint_as_float(q4.w);
+                }
+            } else {
+                const uint4 lo = lds128(src), hi = lds128(src + 16);
+                const uint32_t pr[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+                unpack16(pr, xr);
+            }
         }
         if (tile + (int)gridDim.x < n_tiles) prefetch(tile + gridDim.x, buf ^ 1);
         {
@@ -524,9 +533,12 @@ swin_fwd_umma_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restr
 #pragma unroll
             for (int c = 0; c < 16; ++c) d[c] += y[c] + S.b2[c];
             if (tk.valid) {
-                uint32_t po_[8];
-                pack16(d, po_);
-                st8u(out + tk.off, po_);
+                if (g.out32) { float* o32 = reinterpret_cast<float*>(out) + tk.off; st8f(o32, d); st8f(o32 + 8, d + 8); }
+                else {
+                    uint32_t po_[8];
+                    pack16(d, po_);
+                    st8u(reinterpret_cast<__nv_bfloat16*>(out) + tk.off, po_);
+                }
             }
         }
         tc_fence_before();      // the next tile's first MMA overwrites columns read above: ordered by its __syncthreads
@@ -773,7 +785,7 @@ struct AttnBwdSm {
 
 template <int WD, int WH, int WW, bool EMB>
 __global__ void __launch_bounds__(NT, 2)
-swin_attn_bwd_umma_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gy, __nv_bfloat16* __restrict__ gx,
+swin_attn_bwd_umma_kernel(const void* __restrict__ x, const __nv_bfloat16* __restrict__ gy, __nv_bfloat16* __restrict__ gx,
                           const float* __restrict__ params, int64_t pstride, const int* __restrict__ rel_index,
                           float* __restrict__ partials, Geom g) {
     constexpr int G = WD * WH * WW;
@@ -843,9 +855,15 @@ swin_attn_bwd_umma_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat
 #pragma unroll
                 for (int c = 0; c < 16; ++c) e[c] = __ldg(ew + c) * xin + __ldg(eb + c);
                 ln_row(e, xr);
+            } else if (g.x32) {
+                if (tk.valid) { const float* xp = reinterpret_cast<const float*>(x) + tk.off; ldg8f(xr, xp); ldg8f(xr + 8, xp + 8); }
+                else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) xr[i] = 0.f;
+                }
             } else {
                 uint32_t px[8];
-                if (tk.valid) ldg_row16(x + tk.off, px);
+                if (tk.valid) ldg_row16(reinterpret_cast<const __nv_bfloat16*>(x) + tk.off, px);
                 else {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) px[i] = 0u;
@@ -1200,7 +1218,7 @@ swin_attn_bwd_umma_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat
 }
 
 template <int WD, int WH, int WW>
-int launch_attn_bwd(const idee_swin_desc* d, const Geom& g, const __nv_bfloat16* x, __nv_bfloat16* gx, const float* params,
+int launch_attn_bwd(const idee_swin_desc* d, const Geom& g, const void* x, __nv_bfloat16* gx, const float* params,
                     const int* rel_index, float* gparams, float* part_attn, float* part_mlp, float* part_emb, int per_v, int per_v_mlp,
                     cudaStream_t st) {
     constexpr int G = WD * WH * WW;

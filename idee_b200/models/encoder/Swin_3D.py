@@ -28,6 +28,11 @@ def get_window_size(x_size, window_size, shift_size=None):
     return tuple(ws), tuple(ss)
 
 
+def _win_tokens(blk, D, H, W) -> int:
+    ws = get_window_size((D, H, W), blk.window_size)
+    return ws[0] * ws[1] * ws[2]
+
+
 def _relative_position_index(ws) -> torch.Tensor:
     """Pairwise relative-position index of the tokens of one window (Swin_3D.py:121-135)."""
     grid = torch.stack(torch.meshgrid(*[torch.arange(w) for w in ws], indexing="ij")).flatten(1)   # 3, N
@@ -266,17 +271,33 @@ class Swin_3D(nn.Module):
         # HBM as bf16 -- bit-identical results, half the traffic, and no conversion pass in the conv kernels.
         bf16_io = _lib.PRECISION == "bf16" and E == 16
         tok16 = None
+        if _lib.swin_umma() and bf16_io and all(_win_tokens(self.layers_var[0][l].blocks[b], D, H, W) >= 8 for l, b, _ in pk["blocks"]):
+            # tcgen05 / TMEM kernels: every block in one autograd node (fp32 residual stream, bf16 saved activations / gradients)
+            specs = []
+            for l, b, pack in pk["blocks"]:
+                ws, ss, idx, rows, scale, heads, hidden = self.layers_var[0][l].blocks[b].kernel_args(D, H, W)
+                specs.append((pack, idx, tuple(ws), tuple(ss), rows, float(scale), heads, hidden))
+            if fuse_embed:
+                xin = x if (x.dtype == torch.float32 and x.is_contiguous()) else x.float().contiguous()
+                tok = ops.swin_stack(xin, specs, embed=(pk["embed_w"], pk["embed_b"]))
+            else:
+                tok = ops.swin_stack(tok, specs)
+            return self._proj(tok, None, pk, V, E, bf16_io, fold_last)
         for i, (l, b, pack) in enumerate(pk["blocks"]):
             blk = self.layers_var[0][l].blocks[b]
             ws, ss, idx, rows, scale, heads, hidden = blk.kernel_args(D, H, W)
             if fuse_embed and i == 0:
                 xin = x if (x.dtype == torch.float32 and x.is_contiguous()) else x.float().contiguous()
                 tok = ops.swin_block_embed(xin, pk["embed_w"], pk["embed_b"], pack, idx, ws, ss, rows, scale, heads, hidden)
-            elif bf16_io and i == len(pk["blocks"]) - 1 and not _lib.swin_umma():
+            elif bf16_io and i == len(pk["blocks"]) - 1:
                 # the proj conv reads only the bf16 copy: the fp32 tokens of the last block are never written
                 tok, tok16 = ops.swin_block(tok, pack, idx, ws, ss, rows, scale, heads, hidden, want_bf16="only")
             else:
                 tok = ops.swin_block(tok, pack, idx, ws, ss, rows, scale, heads, hidden)
+        return self._proj(tok, tok16, pk, V, E, bf16_io, fold_last)
+
+    def _proj(self, tok, tok16, pk, V, E, bf16_io, fold_last):
+        """proj_var: conv3^3(replicate) + ReLU + conv3^3(replicate) on the channel-last tokens (Swin_3D.py:586-592, 631)."""
         w0, b0 = ops.packed(pk["proj0_w"], (V, E, E, 3, 3, 3)), ops.packed(pk["proj0_b"], (V, E))
         w2, b2 = ops.packed(pk["proj2_w"], (V, E, E, 3, 3, 3)), ops.packed(pk["proj2_b"], (V, E))
         # conv -> ReLU -> conv: the second conv is the only consumer of the ReLU output, so its data-gradient epilogue applies

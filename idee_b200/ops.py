@@ -143,8 +143,20 @@ def _swin_desc(x, window, shift, rpb_rows, scale, pack: ParamPack, heads, hidden
     d.st, d.sh, d.sw = shift
     d.rpb_rows, d.scale, d.param_stride = rpb_rows, scale, pack.P
     d.precision = 1 if L.PRECISION == "bf16" else 0
-    d.act_dtype = 1 if x.dtype == torch.bfloat16 else 0
+    d.act_dtype, d.x_dtype, d.out_dtype = 0, 0, 0
     return d
+
+
+def _umma_desc(shape_like, x_dtype, out_dtype, window, shift, rpb_rows, scale, pack, heads, hidden):
+    """descriptor of the tcgen05 kernels: bf16 saved activation / gradients, block input / output fp32 or bf16"""
+    d = _swin_desc(shape_like, window, shift, rpb_rows, scale, pack, heads, hidden)
+    d.precision, d.act_dtype = 1, 1
+    d.x_dtype, d.out_dtype = int(x_dtype == torch.bfloat16), int(out_dtype == torch.bfloat16)
+    return d
+
+
+def _bf16c(t):
+    return t.contiguous() if t.dtype == torch.bfloat16 else t.to(torch.bfloat16).contiguous()
 
 
 class SwinBlock(torch.autograd.Function):
@@ -160,19 +172,21 @@ class SwinBlock(torch.autograd.Function):
         if lib.idee_swin_block_packed_floats(rpb_rows) != pack.P:
             raise RuntimeError("swin_block: packed parameter size mismatch")
         if L.swin_umma() and window[0] * window[1] * window[2] >= 8:
-            # tcgen05 / TMEM kernels: bf16 tokens in, bf16 tokens out (the residual stream lives in HBM as bf16)
+            # tcgen05 / TMEM kernels: the residual stream stays in the caller's dtype (fp32, or bf16 with L.STREAM_BF16 / for the
+            # last block whose only consumer rounds to bf16 anyway); the saved mid residual and all token gradients are bf16
             in_dtype = x.dtype
-            x = x.contiguous() if x.dtype == torch.bfloat16 else x.to(torch.bfloat16).contiguous()
-            d = _swin_desc(x, window, shift, rpb_rows, scale, pack, heads, hidden)
-            out = torch.empty_like(x)
+            x = x.contiguous() if x.dtype in (torch.float32, torch.bfloat16) else x.float().contiguous()
+            out_dtype = torch.bfloat16 if (want_bf16 == "only" or x.dtype == torch.bfloat16) else torch.float32
+            d = _umma_desc(x, x.dtype, out_dtype, window, shift, rpb_rows, scale, pack, heads, hidden)
+            out = torch.empty(x.shape, device=x.device, dtype=out_dtype)
             need_bwd = any(ctx.needs_input_grad)
-            ymid = torch.empty_like(x) if need_bwd else None
+            ymid = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if need_bwd else None
             L.run("swin_block_fwd", lib.idee_swin_block_fwd, C.byref(d), x.data_ptr(), out.data_ptr(), L.ptr(ymid), None,
                   flat.data_ptr(), rel_index.data_ptr(), L.stream(), tag=f"w{window} s{shift}")
             if need_bwd:
                 ctx.save_for_backward(x, ymid, rel_index)
                 ctx.pack, ctx.args = pack, (window, shift, rpb_rows, scale, heads, hidden)
-                ctx.in_dtype = in_dtype
+                ctx.in_dtype, ctx.umma = in_dtype, True
             return out
         x = _f32c(x)
         d = _swin_desc(x, window, shift, rpb_rows, scale, pack, heads, hidden)
@@ -204,9 +218,10 @@ class SwinBlock(torch.autograd.Function):
         window, shift, rpb_rows, scale, heads, hidden = ctx.args
         flat = pack.tensor()
         d = _swin_desc(x, window, shift, rpb_rows, scale, pack, heads, hidden)
-        if x.dtype == torch.bfloat16:          # tcgen05 kernels: bf16 token gradients in and out
-            gout = gout.contiguous() if gout.dtype == torch.bfloat16 else gout.to(torch.bfloat16).contiguous()
-            gx = torch.empty_like(x)
+        if getattr(ctx, "umma", False):        # tcgen05 kernels: bf16 token gradients in and out
+            d = _umma_desc(x, x.dtype, x.dtype, window, shift, rpb_rows, scale, pack, heads, hidden)
+            gout = _bf16c(gout)
+            gx = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
             gflat = pack.grad_out(flat)
             nws = lib.idee_swin_block_bwd_workspace_bytes(C.byref(d))
             ws = L.workspace(nws, x.device)
@@ -242,11 +257,13 @@ class SwinBlockEmbed(torch.autograd.Function):
         L.require_cuda(flat, w, b, rel_index)
         if lib.idee_swin_block_packed_floats(rpb_rows) != pack.P:
             raise RuntimeError("swin_block: packed parameter size mismatch")
-        out = torch.empty(N, V, T, H, W, 16, device=x.device, dtype=torch.bfloat16 if L.swin_umma() else torch.float32)
-        d = _swin_desc(out, window, shift, rpb_rows, scale, pack, heads, hidden)
+        out = torch.empty(N, V, T, H, W, 16, device=x.device, dtype=torch.float32)
+        umma = L.swin_umma()
+        d = _umma_desc(out, torch.float32, torch.float32, window, shift, rpb_rows, scale, pack, heads, hidden) if umma else \
+            _swin_desc(out, window, shift, rpb_rows, scale, pack, heads, hidden)
         d.embed_x, d.embed_w, d.embed_b = x.data_ptr(), w.data_ptr(), b.data_ptr()
         need_bwd = any(ctx.needs_input_grad)
-        ymid = torch.empty_like(out) if need_bwd else None
+        ymid = torch.empty(out.shape, device=x.device, dtype=torch.bfloat16 if umma else torch.float32) if need_bwd else None
         L.run("swin_block_fwd", lib.idee_swin_block_fwd, C.byref(d), None, out.data_ptr(), L.ptr(ymid), None, flat.data_ptr(),
               rel_index.data_ptr(), L.stream(), tag=f"w{window} s{shift} +embed")
         if need_bwd:
@@ -262,12 +279,13 @@ class SwinBlockEmbed(torch.autograd.Function):
         window, shift, rpb_rows, scale, heads, hidden = ctx.args
         N, V, _, T, H, W = x.shape
         flat, w, b = pack.tensor(), wpack.tensor(), bpack.tensor()
-        d = _swin_desc(ymid, window, shift, rpb_rows, scale, pack, heads, hidden)
-        d.embed_x, d.embed_w, d.embed_b = x.data_ptr(), w.data_ptr(), b.data_ptr()
         if ymid.dtype == torch.bfloat16:
-            gout = gout.contiguous() if gout.dtype == torch.bfloat16 else gout.to(torch.bfloat16).contiguous()
+            d = _umma_desc(ymid, torch.float32, torch.float32, window, shift, rpb_rows, scale, pack, heads, hidden)
+            gout = _bf16c(gout)
         else:
+            d = _swin_desc(ymid, window, shift, rpb_rows, scale, pack, heads, hidden)
             gout = _f32c(gout)
+        d.embed_x, d.embed_w, d.embed_b = x.data_ptr(), w.data_ptr(), b.data_ptr()
         gtok = torch.empty_like(ymid)                      # scratch between the MLP and attention halves of the backward
         gflat = pack.grad_out(flat)
         gw, gb = wpack.grad_out(w), bpack.grad_out(b)
@@ -289,10 +307,102 @@ def swin_block(x, pack: ParamPack, rel_index, window, shift, rpb_rows, scale, he
     """-> out, or (out, out_bf16) when want_bf16 (bf16 mode; the copy feeds a bf16-storage conv, see Conv3dCL).
     With the tcgen05 kernels (L.swin_umma()) the tokens themselves are bf16: out is bf16 and doubles as the copy."""
     if L.swin_umma() and window[0] * window[1] * window[2] >= 8:
-        out = SwinBlock.apply(x, pack, rel_index, tuple(window), tuple(shift), rpb_rows, float(scale), heads, hidden, False, *pack.params())
-        return (out, out) if want_bf16 else out
+        out = SwinBlock.apply(x, pack, rel_index, tuple(window), tuple(shift), rpb_rows, float(scale), heads, hidden,
+                              "only" if want_bf16 == "only" else False, *pack.params())
+        if want_bf16 == "only":
+            return out, out
+        return (out, out.detach().to(torch.bfloat16)) if want_bf16 else out
     return SwinBlock.apply(x, pack, rel_index, tuple(window), tuple(shift), rpb_rows, float(scale), heads, hidden,
                            want_bf16 if want_bf16 == "only" else bool(want_bf16), *pack.params())
+
+
+class SwinStack(torch.autograd.Function):
+    """All Swin blocks of the encoder as ONE autograd node on the tcgen05 kernels (bf16 mode): raw input x [N,V,1,T,H,W] (patch
+    embedding fused into the first block) or fp32 tokens [N,V,T,H,W,16] -> bf16 tokens of the last block (the proj conv rounds
+    its input to bf16 anyway).  Between blocks the residual stream is fp32 in HBM; the saved mid residuals and every token
+    gradient are bf16 and are handed from block to block without passing through autograd (no dtype casts, one node instead of
+    three).  Swin_3D.py:224-287, 422-446, 473-491."""
+
+    @staticmethod
+    def forward(ctx, x, blocks, embed, *params):
+        """blocks: list of (pack, rel_index, window, shift, rpb_rows, scale, heads, hidden); embed: (wpack, bpack) or None."""
+        L.require_cuda(x)
+        lib = L.load()
+        need_bwd = any(ctx.needs_input_grad)
+        if embed is not None:
+            assert x.dtype == torch.float32 and x.is_contiguous() and x.shape[2] == 1
+            N, V, _, T, H, W = x.shape
+            ew, eb = embed[0].tensor(), embed[1].tensor()
+            L.require_cuda(ew, eb)
+        else:
+            x = _f32c(x)
+            N, V, T, H, W, _ = x.shape
+        shape = (N, V, T, H, W, 16)
+        cur, ins, ymids = (None if embed is not None else x), [], []
+        for i, (pack, rel_index, window, shift, rpb_rows, scale, heads, hidden) in enumerate(blocks):
+            flat = pack.tensor()
+            L.require_cuda(flat, rel_index)
+            last = i == len(blocks) - 1
+            out_dtype = torch.bfloat16 if last else torch.float32
+            out = torch.empty(shape, device=x.device, dtype=out_dtype)
+            d = _umma_desc(out, torch.float32, out_dtype, window, shift, rpb_rows, scale, pack, heads, hidden)
+            tag = f"w{window} s{shift}"
+            if i == 0 and embed is not None:
+                d.embed_x, d.embed_w, d.embed_b = x.data_ptr(), ew.data_ptr(), eb.data_ptr()
+                tag += " +embed"
+            ymid = torch.empty(shape, device=x.device, dtype=torch.bfloat16) if need_bwd else None
+            L.run("swin_block_fwd", lib.idee_swin_block_fwd, C.byref(d), L.ptr(cur), out.data_ptr(), L.ptr(ymid), None, flat.data_ptr(),
+                  rel_index.data_ptr(), L.stream(), tag=tag)
+            ins.append(cur)
+            ymids.append(ymid)
+            cur = out
+        if need_bwd:
+            ctx.blocks, ctx.embed, ctx.x = blocks, embed, x
+            ctx.ins, ctx.ymids = ins, ymids              # plain attributes: intermediate tensors that never leave this node
+        return cur
+
+    @staticmethod
+    def backward(ctx, gout):
+        lib = L.load()
+        blocks, embed, x = ctx.blocks, ctx.embed, ctx.x
+        g = _bf16c(gout)
+        grads = []
+        for i in range(len(blocks) - 1, -1, -1):
+            pack, rel_index, window, shift, rpb_rows, scale, heads, hidden = blocks[i]
+            flat = pack.tensor()
+            ymid, xin = ctx.ymids[i], ctx.ins[i]
+            d = _umma_desc(ymid, torch.float32, torch.float32, window, shift, rpb_rows, scale, pack, heads, hidden)
+            gflat = pack.grad_out(flat)
+            tag = f"w{window} s{shift}"
+            gx = torch.empty(ymid.shape, device=ymid.device, dtype=torch.bfloat16)
+            if i == 0 and embed is not None:
+                ew, eb = embed[0].tensor(), embed[1].tensor()
+                gw, gb = embed[0].grad_out(ew), embed[1].grad_out(eb)
+                d.embed_x, d.embed_w, d.embed_b = x.data_ptr(), ew.data_ptr(), eb.data_ptr()
+                d.embed_gw, d.embed_gb = gw.data_ptr(), gb.data_ptr()
+                tag += " +embed"
+            nws = lib.idee_swin_block_bwd_workspace_bytes(C.byref(d))
+            ws = L.workspace(nws, ymid.device)
+            L.run("swin_block_bwd", lib.idee_swin_block_bwd, C.byref(d), L.ptr(xin), ymid.data_ptr(), g.data_ptr(), gx.data_ptr(),
+                  flat.data_ptr(), rel_index.data_ptr(), gflat.data_ptr(), ws.data_ptr(), nws, L.stream(), tag=tag)
+            grads.append(pack.split_grad(gflat))
+            g = gx
+        ctx.ins, ctx.ymids = None, None
+        out = []
+        for gs in reversed(grads):
+            out.extend(gs)
+        if embed is not None:
+            out.extend(embed[0].split_grad(gw))
+            out.extend(embed[1].split_grad(gb))
+            return (None, None, None, *out)
+        return (g.float(), None, None, *out)
+
+
+def swin_stack(x, blocks, embed=None):
+    params = [p for b in blocks for p in b[0].params()]
+    if embed is not None:
+        params += embed[0].params() + embed[1].params()
+    return SwinStack.apply(x, blocks, embed, *params)
 
 
 # ----------------------------------------------------------------------------------------------------------------

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define IDEE_B200_VERSION 200
+#define IDEE_B200_VERSION 201
 
 const char* idee_last_error(void);
 int idee_version(void);
@@ -65,10 +65,11 @@ typedef struct {
      * backward (LayerNorm backward + weight / bias reduction) on the token gradient it holds in registers and writes the two
      * gradients here; gx is then only used as the scratch between the two halves and its final content is unspecified. */
     float* embed_gw; float* embed_gb;
-    /* element type of the token tensors x / out / ymid / gout / gx: 0 = float, 1 = bf16 (precision 1 only).  With bf16 tokens
-     * the block runs on the tcgen05 / TMEM kernels (swin_umma.cuh): the pointers of idee_swin_block_fwd / _bwd are then
-     * __nv_bfloat16* (passed through the float* parameters), out_bf16 must be NULL, and gx must not alias gout. */
-    int act_dtype;
+    /* act_dtype 1 (precision 1 only) selects the tcgen05 / TMEM kernels (swin_umma.cuh): the saved activation ymid and the token
+     * gradients gout / gx are then bf16 (__nv_bfloat16* passed through the float* parameters), out_bf16 must be NULL, gx must not
+     * alias gout, and the block input x / output out are float (x_dtype / out_dtype 0) or bf16 (1).  act_dtype 0: every token
+     * tensor is float and x_dtype / out_dtype must be 0. */
+    int act_dtype, x_dtype, out_dtype;
 } idee_swin_desc;
 
 int idee_swin_block_packed_floats(int rpb_rows);

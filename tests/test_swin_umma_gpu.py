@@ -54,14 +54,17 @@ def test_umma_forward_matches_mma_sync_and_fp32(window, shift, dims):
             ytc = ops.swin_block(x.float(), pack, idx, ws, ss, rows, scale, heads, hidden)
         _lib.set_swin_umma(True)
         with torch.no_grad():
-            yu = ops.swin_block(x, pack, idx, ws, ss, rows, scale, heads, hidden)
+            yu = ops.swin_block(x, pack, idx, ws, ss, rows, scale, heads, hidden)                 # bf16 stream
+            yu32 = ops.swin_block(x.float(), pack, idx, ws, ss, rows, scale, heads, hidden)       # fp32 stream (the encoder's default)
     finally:
         _lib.set_precision(old[0]); _lib.set_swin_umma(old[1])
     assert yu.dtype == torch.bfloat16 and yu.shape == x.shape
     assert torch.isfinite(yu.float()).all()
-    e_tc, e_u = _rel(ytc, y32), _rel(yu.float(), y32)
-    print(f"window {window} shift {shift} dims {dims}: mma.sync vs fp32 {e_tc:.3e}, tcgen05 vs fp32 {e_u:.3e}")
+    assert yu32.dtype == torch.float32
+    e_tc, e_u, e_u32 = _rel(ytc, y32), _rel(yu.float(), y32), _rel(yu32, y32)
+    print(f"window {window} shift {shift} dims {dims}: mma.sync vs fp32 {e_tc:.3e}, tcgen05 vs fp32 {e_u:.3e} (bf16 out) {e_u32:.3e} (fp32 out)")
     assert e_u < 2e-2 and e_u < 3 * e_tc + 8e-3, (e_tc, e_u)     # bf16 output rounding (2^-8) on top of the bf16-operand error
+    assert e_u32 < 2 * e_tc + 1e-3, (e_tc, e_u32)                # same operand rounding as the mma.sync kernels
 
 
 def _rel_l2(a, b):
