@@ -16,6 +16,7 @@
 // Weight gradients are accumulated in registers across the CTA's persistent loop via a shared-memory
 // transposed outer-product phase, written as per-CTA partials and summed by a deterministic second stage.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "idee_b200.h"
@@ -50,6 +51,7 @@ struct Geom {
     const float* emb_x; const float* emb_w; const float* emb_b;   // bf16 path: fused patch embedding (see idee_swin_desc)
     float* emb_gpart;                                             // backward: per-CTA partials [V][CTAs][32] of the embedding gradients
     int x32, out32;                                               // tcgen05 path: the block input / output tokens are fp32 (else bf16)
+    FastDiv fd_img, fd_hw, fd_w;                                  // tcgen05 path: window index -> (n, dw, hw, ww) without integer division
 };
 
 __device__ __forceinline__ int region_id(int p, int S, int ws, int ss) {
@@ -645,6 +647,8 @@ int make_geom(Geom& g, const idee_swin_desc* d, const char* who) {
                  "%s: the fused patch embedding needs precision 1 and embed_w / embed_b", who);
     g.emb_x = d->embed_x; g.emb_w = d->embed_w; g.emb_b = d->embed_b; g.emb_gpart = nullptr;
     g.x32 = d->x_dtype == 0; g.out32 = d->out_dtype == 0;
+    IDEE_REQUIRE(nwin < (1ll << 31), "%s: too many windows", who);
+    g.fd_img = make_fastdiv(g.nwin_img); g.fd_hw = make_fastdiv(g.nwh * g.nww); g.fd_w = make_fastdiv(g.nww);
     IDEE_REQUIRE((d->embed_gw == nullptr) == (d->embed_gb == nullptr) && (d->embed_gw == nullptr || d->embed_x != nullptr),
                  "%s: embed_gw / embed_gb come together and need the fused patch embedding", who);
     return 0;
@@ -735,8 +739,9 @@ int launch_bwd(const idee_swin_desc* d, const Geom& g, const float* x, const flo
         IDEE_REQUIRE((int64_t)d->N * thw < (1ll << 31), "swin_block_bwd(umma): N*T*H*W must be below 2^31");
         IDEE_REQUIRE(g.emb_x == nullptr || d->embed_gw != nullptr, "swin_block_bwd(umma): the fused embedding needs embed_gw / embed_gb");
         IDEE_REQUIRE(gx != gout, "swin_block_bwd(umma): gx must not alias gout");
-        // persistent grids of one resident wave: 4 CTAs / SM (MLP half), 2 CTAs / SM (attention half: 85 KB of shared memory)
-        int pv_mlp = idee_num_sms() * 4 / d->V, pv_att = idee_num_sms() * 2 / d->V;
+        // persistent grids of one resident wave: 4 CTAs / SM (MLP half), 3 CTAs / SM (attention half; 2 with the fused embedding:
+        // 16 planes and 232 registers)
+        int pv_mlp = idee_num_sms() * 4 / d->V, pv_att = idee_num_sms() * (g.emb_x ? 2 : 3) / d->V;
         if (pv_mlp < 1) pv_mlp = 1;
         if (pv_att < 1) pv_att = 1;
         float* u_attn = ws;

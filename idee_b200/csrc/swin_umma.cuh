@@ -29,6 +29,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
+// D = F32, A = B = F16 (the fc2 GEMM of the forward kernel: its A operand is the packed-f16 GELU output)
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
 // D = F32, A = B = BF16; a_mn / b_mn: operand is MN-major (transposed view)
 __host__ __device__ constexpr uint32_t idesc(int M, int N, int a_mn = 0, int b_mn = 0) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
@@ -132,6 +134,22 @@ __device__ __forceinline__ void ldg_row16(const __nv_bfloat16* p, uint32_t* r) {
                  "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
 }
 
+// GELU (tanh form) on two values packed as f16x2: six packed instructions and ONE MUFU for the pair.  The result feeds the fc2
+// GEMM as an f16 operand (11 mantissa bits; the bf16 operand it replaces has 8).  y = 0.5 x (1 + tanh(x (a + b x^2)))
+__device__ __forceinline__ uint32_t gelu_f16x2(float x0, float x1) {
+    const __half2 x = __floats2half2_rn(x0, x1);
+    const __half2 x2 = __hmul2(x, x);
+    const __half2 u = __hmul2(x, __hfma2(x2, __float2half2_rn(0.0356774081363001f), __float2half2_rn(0.7978845608028654f)));
+    uint32_t ub = *reinterpret_cast<const uint32_t*>(&u), tb;
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(tb) : "r"(ub));
+    const __half2 t = *reinterpret_cast<const __half2*>(&tb);
+    const __half2 hx = __hmul2(x, __float2half2_rn(0.5f));
+    const __half2 y = __hfma2(hx, t, hx);
+    return *reinterpret_cast<const uint32_t*>(&y);
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // LayerNorm(16, eps 1e-5, no affine) of one token held by the thread; returns rstd
 __device__ __forceinline__ float ln_row(const float* x, float* xn) {
     float mu = 0.f;
@@ -161,11 +179,11 @@ __device__ __forceinline__ Tok map_token(const Geom& g, int v, int wg, int lane)
     const int win = wg * (32 / G) + lane / G;
     const int i = lane % G;
     const bool active = wg < g.n_wg && win < g.N * g.nwin_img;
-    const int n = win / g.nwin_img;
-    int r = win - n * g.nwin_img;
-    const int dw = r / (g.nwh * g.nww);
-    r -= dw * g.nwh * g.nww;
-    const int hw = r / g.nww, ww = r - hw * g.nww;
+    uint32_t un, ur, udw, uhw, uww;
+    g.fd_img.divmod(active ? (uint32_t)win : 0u, un, ur);
+    g.fd_hw.divmod(ur, udw, ur);
+    g.fd_w.divmod(ur, uhw, uww);
+    const int n = (int)un, dw = (int)udw, hw = (int)uhw, ww = (int)uww;
     const int dl = i / (WH * WW), hl = (i / WW) % WH, wl = i % WW;
     const int pt = dw * WD + dl, ph = hw * WH + hl, pw = ww * WW + wl;   // rolled frame
     int s_t = pt + g.st; if (s_t >= g.Tp) s_t -= g.Tp;                   // torch.roll(x, -shift)
@@ -178,14 +196,18 @@ __device__ __forceinline__ Tok map_token(const Geom& g, int v, int wg, int lane)
     return t;
 }
 
-// row stride (floats) of the staged relative-position-bias table Bn[h][i][.]: lanes g = 0..3 of a half warp read rows 8 r + g
-// as float2 -> the four row offsets must fall into different 32-byte bank groups: stride * 4 mod 128 in {32, 96}
-__host__ __device__ constexpr int bns(int G) { return G == 32 ? 40 : (G == 16 ? 24 : G); }
+// [h][i][j] float tables in shared memory (the staged relative-position bias Bn and the per-warp bias-gradient tables), accessed
+// as float2 by lane (g = lane / 4 -> row i = g + 8 r, c0 = 2 (lane % 4) -> columns 8 nj + c0): the four rows a half warp touches
+// must land in four different 32-byte bank groups.  G = 32: row stride 32 with the 8-column group index XOR-ed by (row & 3);
+// G = 16: padded stride 24; G = 8: stride 8.
+__host__ __device__ constexpr int bns(int G) { return G == 32 ? 32 : (G == 16 ? 24 : G); }
+template <int G>
+__device__ __forceinline__ int tcol(int row, int col) { return G == 32 ? (col ^ ((row & 3) << 3)) : col; }
 template <int G>
 __device__ __forceinline__ void stage_bias_pad(float* Bn, const float* tbl, const int* __restrict__ rel_index) {
     for (int e = threadIdx.x; e < NH * G * G; e += blockDim.x) {
-        const int h = e / (G * G), ij = e % (G * G);
-        Bn[(h * G + ij / G) * bns(G) + ij % G] = tbl[rel_index[ij] * NH + h] * LOG2E;      // log2 domain
+        const int h = e / (G * G), ij = e % (G * G), i = ij / G, j = ij % G;
+        Bn[(h * G + i) * bns(G) + tcol<G>(i, j)] = tbl[rel_index[ij] * NH + h] * LOG2E;      // log2 domain
     }
 }
 
@@ -212,11 +234,19 @@ struct AttnU {
     template <bool NORMALISE>
     __device__ __forceinline__ void probs(int h, float (&p)[2][4][4], float (&rinv)[4], const float* Bn, int code, bool masked, int lane) {
         const int g = lane / 4, c0 = 2 * (lane % 4);
+        // the accumulators start from the relative-position bias (log2 domain): s = q k^T + B comes out of the MMA
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
             for (int nj = 0; nj < 4; ++nj) {
                 p[mi][nj][0] = p[mi][nj][1] = p[mi][nj][2] = p[mi][nj][3] = 0.f;
+                const int jl = (8 * nj + c0) % G;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf)
+                    if (tile_needed(2 * mi + hf, nj)) {
+                        const float2 b = *reinterpret_cast<const float2*>(Bn + (h * G + (g + 8 * (2 * mi + hf)) % G) * bns(G) + tcol<G>(g, jl));
+                        p[mi][nj][2 * hf] = b.x; p[mi][nj][2 * hf + 1] = b.y;
+                    }
                 if (tile_needed(2 * mi, nj) || tile_needed(2 * mi + 1, nj)) mma1688(p[mi][nj], qa[mi][h][0], qa[mi][h][1], kb[h][nj]);
             }
         int cj[4][2], cr[4];
@@ -231,16 +261,7 @@ struct AttnU {
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const int mi = r / 2, hf = r % 2;
-            const int il = (g + 8 * r) % G;
             float mx = -INFINITY;
-#pragma unroll
-            for (int nj = 0; nj < 4; ++nj) {
-                if (tile_needed(r, nj)) {
-                    const int jl = (8 * nj + c0) % G;
-                    const float2 b = *reinterpret_cast<const float2*>(Bn + (h * G + il) * bns(G) + jl);
-                    p[mi][nj][2 * hf] += b.x; p[mi][nj][2 * hf + 1] += b.y;
-                }
-            }
             if (masked) {
 #pragma unroll
                 for (int nj = 0; nj < 4; ++nj) {
@@ -312,7 +333,11 @@ struct FwdSm {          // dynamic shared memory of the forward kernel
     unsigned char stg[4][32 * STG];                  // per-warp q | k | v staging
     unsigned char a2[2 * PLANE];                     // attention output as the proj GEMM's A operand
     unsigned char wqkv[48 * 32], wproj[16 * 32], w1[64 * 32], w2[16 * 128];
-    float bqkv[48], bproj[16], b1[64], b2[16];
+    // biases ride on the tensor core: one more K step against a constant A operand whose elements 0 and 1 are 1 (chunk 0 = ones0,
+    // chunk 1 = zero) and B rows (hi(b[n]), lo(b[n]), 0, ...) -- the bf16 hi + lo split keeps the fp32 bias to 2^-17
+    unsigned char ones0[128];                         // one 8-row core matrix, shared by all 16 row groups (SBO = 0)
+    unsigned char bias_c[(48 + 16 + 64 + 16) * 16];   // chunk 0 of the bias operands: qkv | proj | fc1 | fc2
+    unsigned char zero[128];                          // chunk 1 of every bias-step operand: one zero core matrix (SBO = 0; after them: LBO > 0)
     uint64_t mma_bar;
     uint64_t load_bar[2][4];
     uint32_t tmem_slot;
@@ -346,10 +371,18 @@ swin_fwd_umma_kernel(const void* __restrict__ x, void* __restrict__ out, __nv_bf
     stage_b_kmajor(S.wqkv, P + po.qkv_w, C, 48, 16, 16, qs);
     stage_b_kmajor(S.wproj, P + po.proj_w, C, 16, 16, 0, 1.f);
     stage_b_kmajor(S.w1, P + po.fc1_w, C, 64, 16, 0, 1.f);
-    stage_b_kmajor(S.w2, P + po.fc2_w, HID, 16, 64, 0, 1.f);
-    for (int e = tid; e < 48; e += NT) S.bqkv[e] = P[po.qkv_b + e] * (e < 16 ? qs : 1.f);
-    for (int e = tid; e < 16; e += NT) { S.bproj[e] = P[po.proj_b + e]; S.b2[e] = P[po.fc2_b + e]; }
-    for (int e = tid; e < 64; e += NT) S.b1[e] = P[po.fc1_b + e];
+    for (int e = tid; e < 16 * 64; e += NT) {                                // fc2.weight as an f16 operand (see gelu_f16x2)
+        const int n = e / 64, k = e % 64;
+        *reinterpret_cast<__half*>(S.w2 + (k >> 3) * 16 * 16 + n * 16 + (k & 7) * 2) = __float2half_rn(P[po.fc2_w + n * HID + k]);
+    }
+    for (int e = tid; e < 144 * 8; e += NT) {
+        const int n = e >> 3, k = e & 7;
+        const float b = n < 48 ? P[po.qkv_b + n] * (n < 16 ? qs : 1.f) : (n < 64 ? P[po.proj_b + n - 48] : (n < 128 ? P[po.fc1_b + n - 64] : P[po.fc2_b + n - 128]));
+        const __nv_bfloat16 hi = __float2bfloat16(b);
+        const __nv_bfloat16 lo = __float2bfloat16(b - __bfloat162float(hi));
+        reinterpret_cast<__nv_bfloat16*>(S.bias_c)[e] = k == 0 ? hi : (k == 1 ? lo : __float2bfloat16(0.f));
+    }
+    if (tid < 8) { sts128(smem_u32(S.ones0) + tid * 16, 0x3F803F80u, 0u, 0u, 0u); sts128(smem_u32(S.zero) + tid * 16, 0u, 0u, 0u, 0u); }
     stage_bias_pad<G>(Bn, P, rel_index);
     proxy_fence();
     tc_fence_before();
@@ -359,14 +392,25 @@ swin_fwd_umma_kernel(const void* __restrict__ x, void* __restrict__ out, __nv_bf
     const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);             // this warp's lane quadrant
     const uint32_t mma_bar = smem_u32(&S.mma_bar);
     uint32_t n_commit = 0;                                                   // commits so far -> wait parity
+    // D[128 x N] += 1 * bias^T: A = (ones0, zero), B = (bias_c rows n0 .. n0 + N, zero)
+    auto bias_step = [&](uint32_t dcol, int n0, int N) {
+        const uint32_t a0 = smem_u32(S.ones0), b0 = smem_u32(S.bias_c) + n0 * 16, z = smem_u32(S.zero);
+        // K-major operands as (chunk 0, chunk 1) pairs: A = (ones0, zero) with SBO = 0 (every 8-row group reads the same core
+        // matrix); B chunk 0 = the bias rows (SBO = 128), chunk 1 = zero -- the B descriptor's SBO also applies to chunk 1, so
+        // the zero chunk is read at z + 128 * group: `zero` is followed by >= 1 KB of bytes whose value times A's zero chunk
+        // cannot matter only if they are finite; therefore B's chunk 1 points at the bias rows themselves (finite) and it is A's
+        // chunk 1 (exact zeros) that cancels the second half of the K step
+        umma_ss(tmem + dcol, make_desc(a0, z - a0, 0), make_desc(b0, 0, 128), idesc(128, N), 1);
+    };
 
     const int n_tiles = (g.n_wg + 3) / 4;
     const uint32_t my_slot = (uint32_t)(tid * 64);
     const uint32_t row_bytes = g.x32 ? 64u : 32u;
-    // token tile prefetch (TMA bulk copy of this thread's 32-byte token row into its slot of the double buffer)
-    auto prefetch = [&](int tile, int buf) {
-        if (EMB) return;
-        const Tok t = map_token<WD, WH, WW>(g, v, tile * 4 + warp, lane);
+    // token tile prefetch: TMA bulk copy of this thread's token row into its slot of the double buffer (fused embedding: the
+    // raw scalar into a register).  The token map of a tile is computed once, here, and carried into the tile's iteration.
+    float xin_next = 0.f;
+    auto prefetch = [&](const Tok& t, int buf) {
+        if (EMB) { xin_next = t.valid ? __ldg(g.emb_x + (t.off >> 4)) : 0.f; return; }
         const uint32_t bar = smem_u32(&S.load_bar[buf][warp]);
         const unsigned m = __ballot_sync(0xffffffffu, t.valid);
         if (lane == 0) mbar_expect_tx(bar, row_bytes * __popc(m));
@@ -375,17 +419,18 @@ swin_fwd_umma_kernel(const void* __restrict__ x, void* __restrict__ out, __nv_bf
         if (t.valid) bulk_g2s(dst, reinterpret_cast<const unsigned char*>(x) + t.off * (g.x32 ? 4 : 2), row_bytes, bar);
         else { sts128(dst, 0, 0, 0, 0); sts128(dst + 16, 0, 0, 0, 0); sts128(dst + 32, 0, 0, 0, 0); sts128(dst + 48, 0, 0, 0, 0); }
     };
-    if ((int)blockIdx.x < n_tiles) prefetch(blockIdx.x, 0);
+    Tok tk_next = map_token<WD, WH, WW>(g, v, (int)blockIdx.x * 4 + warp, lane);
+    if ((int)blockIdx.x < n_tiles) prefetch(tk_next, 0);
 
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const int buf = it & 1;
-        const Tok tk = map_token<WD, WH, WW>(g, v, tile * 4 + warp, lane);
+        const Tok tk = tk_next;
+        const float xin = xin_next;
         const bool masked = __any_sync(0xffffffffu, tk.border);
         // ---- P0: token row -> LN1 -> A operand (TMEM) -> QKV GEMM ----
         float xr[16];
         if (EMB) {
-            const float xin = tk.valid ? __ldg(g.emb_x + (tk.off >> 4)) : 0.f;
             const float* w = g.emb_w + v * C;
             const float* b = g.emb_b + v * C;
             float e[16];
@@ -407,7 +452,10 @@ swin_fwd_umma_kernel(const void* __restrict__ x, void* __restrict__ out, __nv_bf
                 unpack16(pr, xr);
             }
         }
-        if (tile + (int)gridDim.x < n_tiles) prefetch(tile + gridDim.x, buf ^ 1);
+        if (tile + (int)gridDim.x < n_tiles) {
+            tk_next = map_token<WD, WH, WW>(g, v, (tile + (int)gridDim.x) * 4 + warp, lane);
+            prefetch(tk_next, buf ^ 1);
+        }
         {
             float xn[16];
             ln_row(xr, xn);
@@ -418,6 +466,12 @@ swin_fwd_umma_kernel(const void* __restrict__ x, void* __restrict__ out, __nv_bf
                 for (int i = 0; i < 8; ++i) pa[i] = 0u;                      // zero padding AFTER LN1 (Swin_3D.py:233-238)
             }
             tmem_st8(tlane + F_AX, pa);
+            // the residual rides in the accumulator: x goes into the columns the proj GEMM accumulates onto (y = x + proj(o) + b), and
+            // the fc2 GEMM accumulates onto y in the same columns (out = y + fc2(h) + b)
+            uint32_t px[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) px[c] = __float_as_uint(xr[c]);
+            tmem_st16(tlane + F_DP, px);
             tmem_st_wait();
         }
         tc_fence_before();
@@ -425,6 +479,7 @@ swin_fwd_umma_kernel(const void* __restrict__ x, void* __restrict__ out, __nv_bf
         if (tid == 0) {
             tc_fence_after();
             umma_ts(tmem + F_DQKV, tmem + F_AX, make_desc(smem_u32(S.wqkv), 48 * 16, 128), idesc(128, 48), 0);
+            bias_step(F_DQKV, 0, 48);
             umma_commit(mma_bar);
         }
         // ---- P1: q | k | v rows (+ bias) -> bf16 staging tile of the warp ----
@@ -436,8 +491,6 @@ swin_fwd_umma_kernel(const void* __restrict__ x, void* __restrict__ out, __nv_bf
 #pragma unroll
             for (int part = 0; part < 3; ++part) {
                 tmem_ld16(tlane + F_DQKV + 16 * part, qkv);
-#pragma unroll
-                for (int c = 0; c < 16; ++c) qkv[c] += S.bqkv[16 * part + c];
                 uint32_t pq[8];
                 pack16(qkv, pq);
                 sts128(stg + lane * STG + 32 * part, pq[0], pq[1], pq[2], pq[3]);
@@ -471,17 +524,16 @@ swin_fwd_umma_kernel(const void* __restrict__ x, void* __restrict__ out, __nv_bf
         __syncthreads();
         if (tid == 0) {
             tc_fence_after();
-            umma_ss(tmem + F_DP, make_desc(smem_u32(S.a2), PLANE, 128), make_desc(smem_u32(S.wproj), 16 * 16, 128), idesc(128, 16), 0);
+            umma_ss(tmem + F_DP, make_desc(smem_u32(S.a2), PLANE, 128), make_desc(smem_u32(S.wproj), 16 * 16, 128), idesc(128, 16), 1);
+            bias_step(F_DP, 48, 16);
             umma_commit(mma_bar);
         }
         // ---- P3: y = x + proj(o) + b -> (ymid) -> LN2 -> A operand -> fc1 GEMM ----
         mbar_wait(mma_bar, n_commit++ & 1u);
         tc_fence_after();
-        float y[16];
         {
+            float y[16];
             tmem_ld16(tlane + F_DP, y);
-#pragma unroll
-            for (int c = 0; c < 16; ++c) y[c] += xr[c] + S.bproj[c];
             if (ymid != nullptr && tk.valid) {
                 uint32_t py[8];
                 pack16(y, py);
@@ -499,6 +551,7 @@ swin_fwd_umma_kernel(const void* __restrict__ x, void* __restrict__ out, __nv_bf
         if (tid == 0) {
             tc_fence_after();
             umma_ts(tmem + F_DH, tmem + F_AX, make_desc(smem_u32(S.w1), 64 * 16, 128), idesc(128, 64), 0);
+            bias_step(F_DH, 64, 64);
             umma_commit(mma_bar);
         }
         // ---- P4: hidden = GELU(fc1 + b1) -> A operand (TMEM, 32 columns) -> fc2 GEMM in four K steps ----
@@ -511,7 +564,7 @@ swin_fwd_umma_kernel(const void* __restrict__ x, void* __restrict__ out, __nv_bf
             uint32_t ph[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c)
-                ph[c] = pk(gelu_fast(hd[2 * c] + S.b1[32 * half + 2 * c]), gelu_fast(hd[2 * c + 1] + S.b1[32 * half + 2 * c + 1]));
+                ph[c] = gelu_f16x2(hd[2 * c], hd[2 * c + 1]);
             tmem_st16(tlane + F_AH + 16 * half, ph);
         }
         tmem_st_wait();
@@ -521,7 +574,8 @@ swin_fwd_umma_kernel(const void* __restrict__ x, void* __restrict__ out, __nv_bf
             tc_fence_after();
 #pragma unroll
             for (int s = 0; s < 4; ++s)
-                umma_ts(tmem + F_DO, tmem + F_AH + 8 * s, make_desc(smem_u32(S.w2) + s * 512, 16 * 16, 128), idesc(128, 16), s > 0 ? 1u : 0u);
+                umma_ts(tmem + F_DO, tmem + F_AH + 8 * s, make_desc(smem_u32(S.w2) + s * 512, 16 * 16, 128), idesc_f16(128, 16), 1);
+            bias_step(F_DO, 128, 16);
             umma_commit(mma_bar);
         }
         // ---- P5: out = y + fc2(hidden) + b2 ----
@@ -530,8 +584,6 @@ swin_fwd_umma_kernel(const void* __restrict__ x, void* __restrict__ out, __nv_bf
         {
             float d[16];
             tmem_ld16(tlane + F_DO, d);
-#pragma unroll
-            for (int c = 0; c < 16; ++c) d[c] += y[c] + S.b2[c];
             if (tk.valid) {
                 if (g.out32) { float* o32 = reinterpret_cast<float*>(out) + tk.off; st8f(o32, d); st8f(o32 + 8, d + 8); }
                 else {
@@ -630,6 +682,15 @@ swin_mlp_bwd_umma_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat1
         uint32_t n, rem;
         fd_thw.divmod(valid ? tok : 0u, n, rem);
         const int64_t off = ((int64_t)(n * V + v) * thw + rem) * C;
+        {   // next tile's rows towards L2 while this tile computes
+            const uint32_t tok2 = tok + gridDim.x * NT;
+            if (tok2 < ntok) {
+                uint32_t n2, rem2;
+                fd_thw.divmod(tok2, n2, rem2);
+                const int64_t off2 = ((int64_t)(n2 * V + v) * thw + rem2) * C;
+                prefetch_l2(y + off2); prefetch_l2(gout + off2);
+            }
+        }
         // ---- R0: rows -> LN -> planes yn | g_out -> GEMMs of half 0 ----
         uint32_t pg[8];
         float yn[16], rstd;
@@ -768,33 +829,38 @@ swin_mlp_bwd_umma_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat1
 // chunk planes [plane][token][16 B] of a tile (see the file header):
 //   0-1 q -> dq | 2-3 k -> dk | 4-5 v -> dv | 6-7 g_y | 8-9 g_embed (fused embedding only) | 10-11 xn | 12-13 dO -> o | 14 ones | 15 (x, 1, 0..)
 // weight gradients: D[M x 48] += [dq | dk | dv | g_y (| g_e | ...)]^T [xn | o | 1 | (x, 1)], M = 64 (128 with the fused embedding)
-constexpr int A_Q = 0, A_K = 2, A_V = 4, A_GY = 6, A_GE = 8, A_XN = 10, A_DO = 12, A_ONE = 14, A_X1 = 15, A_PLANES = 16;
+constexpr int A_Q = 0, A_K = 2, A_V = 4, A_GY = 6, A_GE = 8;
+template <bool EMB> struct APl {          // without the fused embedding the two g_embed planes do not exist
+    static constexpr int XN = EMB ? 10 : 8, DO = XN + 2, ONE = XN + 4, X1 = XN + 5, PLANES = XN + 6;
+};
 constexpr int B_QKV = 0, B_DO = 48, B_DXN = 64, B_WACC = 80, B_COLS = 128;       // TMEM columns
 
+template <bool EMB>
 struct AttnBwdSm {
-    unsigned char pl[A_PLANES * PLANE];
-    unsigned char ones0[PLANE];          // A operand of the bias GEMM step (chunk 1 = the zero chunk zq)
+    unsigned char pl[APl<EMB>::PLANES * PLANE];
+    unsigned char ones0[128];            // A operand of the bias GEMM step: one core matrix (1, 1, 0, ...) for every row group (SBO = 0)
     unsigned char bq[48 * 16];           // B(n, k) chunk 0 of the bias step: k = 0 -> hi(bqkv[n]), k = 1 -> lo (q rows pre-scaled)
     unsigned char wqkv[48 * 32];         // B(n = o, k = c) = qkv.weight[n][k] (q rows pre-scaled)       qkv = xn Wqkv^T
     unsigned char wpt[16 * 32];          // B(n = e, k = c) = proj.weight[k][n]                          dO = g_y Wproj
     unsigned char wqt[16 * 96];          // B(n = c, k = o) = qkv.weight[k][n]                           dxn = [dq|dk|dv] Wqkv
-    unsigned char zq[PLANE];             // zeros: chunk 1 of both bias-step operands, 128 rows for the A side (after ones0 / bq: LBO > 0)
+    unsigned char zq[128];               // zeros: chunk 1 of the bias step's A operand (after ones0: LBO > 0)
     uint64_t mma_bar;
     uint32_t tmem_slot;
 };
 
 template <int WD, int WH, int WW, bool EMB>
-__global__ void __launch_bounds__(NT, 2)
+__global__ void __launch_bounds__(NT, EMB ? 2 : 3)
 swin_attn_bwd_umma_kernel(const void* __restrict__ x, const __nv_bfloat16* __restrict__ gy, __nv_bfloat16* __restrict__ gx,
                           const float* __restrict__ params, int64_t pstride, const int* __restrict__ rel_index,
                           float* __restrict__ partials, Geom g) {
     constexpr int G = WD * WH * WW;
     constexpr int PART = ATT_PART_W + NH * G * G;
-    constexpr int DBS = dbs(G), DBW = NH * G * DBS;            // per-warp bias-gradient table (conflict-free 8-byte RMW)
+    constexpr int DBS = bns(G), DBW = NH * G * DBS;            // per-warp bias-gradient table (conflict-free 8-byte RMW, see bns / tcol)
     constexpr int WM = EMB ? 128 : 64;                         // rows of the weight-gradient GEMM
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    AttnBwdSm& S = *reinterpret_cast<AttnBwdSm*>(smem_raw);
-    float* Bn = reinterpret_cast<float*>(smem_raw + sizeof(AttnBwdSm));      // [NH][G][bns(G)]
+    constexpr int A_XN = APl<EMB>::XN, A_DO = APl<EMB>::DO, A_ONE = APl<EMB>::ONE, A_X1 = APl<EMB>::X1;
+    AttnBwdSm<EMB>& S = *reinterpret_cast<AttnBwdSm<EMB>*>(smem_raw);
+    float* Bn = reinterpret_cast<float*>(smem_raw + sizeof(AttnBwdSm<EMB>));  // [NH][G][bns(G)]
     float* dBw_all = Bn + NH * G * bns(G);                                  // [4 warps][DBW]
     const int v = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* P = params + (int64_t)v * pstride;
@@ -818,10 +884,8 @@ swin_attn_bwd_umma_kernel(const void* __restrict__ x, const __nv_bfloat16* __res
     const uint32_t pl = smem_u32(S.pl);
     sts128(pl + A_ONE * PLANE + tid * 16, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
     sts128(pl + A_X1 * PLANE + tid * 16, 0u, 0u, 0u, 0u);
-    sts128(pl + A_GE * PLANE + tid * 16, 0u, 0u, 0u, 0u);
-    sts128(pl + (A_GE + 1) * PLANE + tid * 16, 0u, 0u, 0u, 0u);
-    sts128(smem_u32(S.ones0) + tid * 16, 0x3F803F80u, 0u, 0u, 0u);
-    sts128(smem_u32(S.zq) + tid * 16, 0u, 0u, 0u, 0u);
+    if (EMB) { sts128(pl + A_GE * PLANE + tid * 16, 0u, 0u, 0u, 0u); sts128(pl + (A_GE + 1) * PLANE + tid * 16, 0u, 0u, 0u, 0u); }
+    if (tid < 8) { sts128(smem_u32(S.ones0) + tid * 16, 0x3F803F80u, 0u, 0u, 0u); sts128(smem_u32(S.zq) + tid * 16, 0u, 0u, 0u, 0u); }
     for (int e = tid; e < 4 * DBW; e += NT) dBw_all[e] = 0.f;
     stage_bias_pad<G>(Bn, P, rel_index);
     proxy_fence();
@@ -842,9 +906,18 @@ swin_attn_bwd_umma_kernel(const void* __restrict__ x, const __nv_bfloat16* __res
 
     const int n_tiles = (g.n_wg + 3) / 4;
     bool first = true;
+    Tok tk_next = map_token<WD, WH, WW>(g, v, (int)blockIdx.x * 4 + warp, lane);
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const Tok tk = map_token<WD, WH, WW>(g, v, tile * 4 + warp, lane);
+        const Tok tk = tk_next;
         const bool masked = __any_sync(0xffffffffu, tk.border);
+        if (tile + (int)gridDim.x < n_tiles) {                 // next tile's token map, and its rows towards L2 while this tile computes
+            tk_next = map_token<WD, WH, WW>(g, v, (tile + (int)gridDim.x) * 4 + warp, lane);
+            if (tk_next.valid) {
+                prefetch_l2(gy + tk_next.off);
+                if (EMB) prefetch_l2(g.emb_x + (tk_next.off >> 4));
+                else prefetch_l2(reinterpret_cast<const unsigned char*>(x) + tk_next.off * (g.x32 ? 4 : 2));
+            }
+        }
         // ---- R0: rows -> LN1 -> planes xn | g_y -> qkv and dO GEMMs ----
         float rstd, xin = 0.f;
         {
@@ -896,8 +969,8 @@ swin_attn_bwd_umma_kernel(const void* __restrict__ x, const __nv_bfloat16* __res
         if (tid == 0) {
             tc_fence_after();
             umma_ss(tmem + B_QKV, make_desc(pl + A_XN * PLANE, PLANE, 128), make_desc(smem_u32(S.wqkv), 48 * 16, 128), idesc(128, 48), 0);
-            umma_ss(tmem + B_QKV, make_desc(smem_u32(S.ones0), smem_u32(S.zq) - smem_u32(S.ones0), 128),
-                    make_desc(smem_u32(S.bq), smem_u32(S.zq) - smem_u32(S.bq), 128), idesc(128, 48), 1);
+            // bias step: A = (ones0, zq) with SBO = 0; B chunk 1 = chunk 0 (finite values against A's exact zeros)
+            umma_ss(tmem + B_QKV, make_desc(smem_u32(S.ones0), smem_u32(S.zq) - smem_u32(S.ones0), 0), make_desc(smem_u32(S.bq), 0, 128), idesc(128, 48), 1);
             umma_ss(tmem + B_DO, make_desc(pl + A_GY * PLANE, PLANE, 128), make_desc(smem_u32(S.wpt), 16 * 16, 128), idesc(128, 16), 0);
             umma_commit(mma_bar);
         }
@@ -941,6 +1014,13 @@ swin_attn_bwd_umma_kernel(const void* __restrict__ x, const __nv_bfloat16* __res
 #pragma unroll
                 for (int nj = 0; nj < 4; ++nj) {
                     p[mi][nj][0] = p[mi][nj][1] = p[mi][nj][2] = p[mi][nj][3] = 0.f;
+                    const int jl = (8 * nj + c0) % G;
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf)
+                        if (AttnU<G>::tile_needed(2 * mi + hf, nj)) {
+                            const float2 b = *reinterpret_cast<const float2*>(Bn + (h * G + (gq + 8 * (2 * mi + hf)) % G) * bns(G) + tcol<G>(gq, jl));
+                            p[mi][nj][2 * hf] = b.x; p[mi][nj][2 * hf + 1] = b.y;
+                        }
                     if (AttnU<G>::tile_needed(2 * mi, nj) || AttnU<G>::tile_needed(2 * mi + 1, nj)) mma1688(p[mi][nj], qa[2 * mi], qa[2 * mi + 1], kb[nj]);
                 }
             int cj[4][2], cr[4];
@@ -955,14 +1035,10 @@ swin_attn_bwd_umma_kernel(const void* __restrict__ x, const __nv_bfloat16* __res
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 const int mi = r / 2, hf = r % 2;
-                const int il = (gq + 8 * r) % G;
                 float mx = -INFINITY;
 #pragma unroll
                 for (int nj = 0; nj < 4; ++nj) {
                     if (AttnU<G>::tile_needed(r, nj)) {
-                        const int jl = (8 * nj + c0) % G;
-                        const float2 b = *reinterpret_cast<const float2*>(Bn + (h * G + il) * bns(G) + jl);
-                        p[mi][nj][2 * hf] += b.x; p[mi][nj][2 * hf + 1] += b.y;
                         if (masked) {
                             if (cj[nj][0] != cr[r]) p[mi][nj][2 * hf] += -100.0f * LOG2E;
                             if (cj[nj][1] != cr[r]) p[mi][nj][2 * hf + 1] += -100.0f * LOG2E;
@@ -1026,7 +1102,7 @@ swin_attn_bwd_umma_kernel(const void* __restrict__ x, const __nv_bfloat16* __res
                 for (int nj = 0; nj < 4; ++nj)
                     if (AttnU<G>::tile_needed(r, nj)) {
                         const int il = (gq + 8 * r) % G, jl = (8 * nj + c0) % G;
-                        float2* pd = reinterpret_cast<float2*>(&dB[(h * G + il) * DBS + jl]);
+                        float2* pd = reinterpret_cast<float2*>(&dB[(h * G + il) * DBS + tcol<G>(gq, jl)]);
                         float2 acc2 = *pd;
                         acc2.x += ds[r / 2][nj][2 * (r % 2)]; acc2.y += ds[r / 2][nj][2 * (r % 2) + 1];
                         *pd = acc2;
@@ -1209,7 +1285,7 @@ swin_attn_bwd_umma_kernel(const void* __restrict__ x, const __nv_bfloat16* __res
         const int hi = e / G, jl = e % G;     // hi = h * G + i_local
         float sum = 0.f;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) sum += dBw_all[w * DBW + hi * DBS + jl];
+        for (int w = 0; w < 4; ++w) sum += dBw_all[w * DBW + hi * DBS + tcol<G>(hi % G, jl)];
         part[ATT_PART_W + e] = sum;
     }
     tc_fence_before();
@@ -1222,12 +1298,13 @@ int launch_attn_bwd(const idee_swin_desc* d, const Geom& g, const void* x, __nv_
                     const int* rel_index, float* gparams, float* part_attn, float* part_mlp, float* part_emb, int per_v, int per_v_mlp,
                     cudaStream_t st) {
     constexpr int G = WD * WH * WW;
-    const size_t smem = sizeof(AttnBwdSm) + sizeof(float) * (NH * G * bns(G) + 4 * NH * G * dbs(G));
+    const size_t smem_e = sizeof(AttnBwdSm<true>) + sizeof(float) * 5 * NH * G * bns(G);
+    const size_t smem = sizeof(AttnBwdSm<false>) + sizeof(float) * 5 * NH * G * bns(G);
     if (g.emb_x) {
         Geom ge = g;
         ge.emb_gpart = d->embed_gw ? part_emb : nullptr;
-        IDEE_CUDA(cudaFuncSetAttribute(swin_attn_bwd_umma_kernel<WD, WH, WW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "swin_attn_bwd(umma)");
-        swin_attn_bwd_umma_kernel<WD, WH, WW, true><<<dim3(per_v, d->V), NT, smem, st>>>(x, gx, gx, params, d->param_stride, rel_index, part_attn, ge);
+        IDEE_CUDA(cudaFuncSetAttribute(swin_attn_bwd_umma_kernel<WD, WH, WW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e), "swin_attn_bwd(umma)");
+        swin_attn_bwd_umma_kernel<WD, WH, WW, true><<<dim3(per_v, d->V), NT, smem_e, st>>>(x, gx, gx, params, d->param_stride, rel_index, part_attn, ge);
         IDEE_LAUNCH_CHECK("swin_attn_bwd(umma,embed)");
         if (d->embed_gw) {
             embed_grad_finalize_kernel<<<d->V, 32, 0, st>>>(part_emb, per_v, d->embed_gw, d->embed_gb);
