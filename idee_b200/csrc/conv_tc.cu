@@ -892,12 +892,11 @@ proj_wgrad_scalar_kernel(WP p) {
     __shared__ __align__(16) __nv_bfloat16 tileA[2][TH * TW * CPA];    // h tile, double buffered (cp.async)
     __shared__ __align__(16) float gsh[2][NHALO];                      // scalar-gradient halo, double buffered
     __shared__ __align__(16) __nv_bfloat16 tileG[TH * TW * CPG];       // im2col of the scalar plane, 32 columns (27 taps + 5 zeros)
-    __shared__ float red[27 * 16 + 1];
+    __shared__ float red[4][27 * 16 + 1];        // one slot per warp, summed in a fixed order: bit-identical from run to run
     const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(p.in);
     const float* gout = reinterpret_cast<const float*>(p.gout);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int s = blockIdx.x, wset = blockIdx.y;
-    for (int e = tid; e < 27 * 16 + 1; e += 128) red[e] = 0.f;
     float acc[4][4];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
@@ -974,15 +973,15 @@ proj_wgrad_scalar_kernel(WP p) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int tap = nt * 8 + (lane % 4) * 2 + (q & 1), ch = lane / 4 + (q >> 1) * 8;
-            if (tap < 27) atomicAdd(&red[tap * 16 + ch], acc[nt][q]);
+            if (tap < 27) red[warp][tap * 16 + ch] = acc[nt][q];
         }
     gsum = warp_sum(gsum);
-    if (lane == 0) atomicAdd(&red[27 * 16], gsum);
+    if (lane == 0) red[warp][27 * 16] = gsum;
     __syncthreads();
     constexpr int PS = 27 * 256 + 16;
     float* part = p.partials + ((int64_t)wset * p.S + s) * PS;                // n_ic == n_oc16 == 1
-    for (int e = tid; e < 27 * 16; e += 128) part[(e / 16) * 256 + (e % 16) * 16] = red[e];
-    if (tid == 0) part[27 * 256] = red[27 * 16];
+    for (int e = tid; e < 27 * 16; e += 128) part[(e / 16) * 256 + (e % 16) * 16] = (red[0][e] + red[1][e]) + (red[2][e] + red[3][e]);
+    if (tid == 0) part[27 * 256] = (red[0][27 * 16] + red[1][27 * 16]) + (red[2][27 * 16] + red[3][27 * 16]);
 }
 
 // NT taps, NTL n-tiles (8 output channels each) per CTA; cin chunk 16.  A16 / G16: the input / output-gradient tensors hold

@@ -250,6 +250,22 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     }
 }
 
+// CUDA-graph form: the step counter and the learning rate live in device memory (state[0] = step as float, state[1] = lr), so one
+// captured launch sequence serves every replay; the first kernel advances the counter, the second reads it
+__global__ void adam_tick_kernel(float* state) { state[0] += 1.f; }
+__global__ void adam_state_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                  const float* __restrict__ state, float b1, float b2, float eps, float wd) {
+    const float step = state[0], lr = state[1];
+    const float bc1 = 1.f - powf(b1, step), bc2_sqrt = sqrtf(1.f - powf(b2, step));
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float gi = g[i] + wd * p[i];
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        p[i] -= (lr / bc1) * mi / (sqrtf(vi) / bc2_sqrt + eps);
+    }
+}
+
 }  // namespace
 
 extern "C" size_t idee_bce_loss_workspace_bytes(int K) { return sizeof(double) * (size_t)(3 + K) * BNB; }
@@ -340,5 +356,18 @@ extern "C" int idee_adam_step(float* p, const float* g, float* m, float* v, int6
     if (nb > cap) nb = cap;
     adam_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2);
     IDEE_LAUNCH_CHECK("adam_step");
+    return 0;
+}
+
+extern "C" int idee_adam_step_state(float* p, const float* g, float* m, float* v, int64_t n, float* state, float beta1, float beta2,
+                                    float eps, float weight_decay, void* stream) {
+    IDEE_REQUIRE(state != nullptr, "adam_step_state: state (step, lr) must be a device pointer");
+    int nb = (int)((n + 255) / 256);
+    const int cap = idee_num_sms() * 8;
+    if (nb > cap) nb = cap;
+    adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state);
+    IDEE_LAUNCH_CHECK("adam_tick");
+    adam_state_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, state, beta1, beta2, eps, weight_decay);
+    IDEE_LAUNCH_CHECK("adam_step_state");
     return 0;
 }

@@ -626,7 +626,7 @@ struct MlpBwdSm {
     unsigned char w2t[64 * 32];          // B(n = hidden, k = c) = fc2.weight[k][n]            (g_h = g_out W2)
     unsigned char w1t[16 * 128];         // B(n = c, k = hidden) = fc1.weight[k][n]            (g_yn = g_pre W1)
     unsigned char pb[6 * PLANE];         // chunk planes: yn (2) | g_out (2) | ones (1) | zeros (1); after ones0 / b1: their LBO > 0
-    float red[16];
+    float red[4][16];
     uint64_t mma_bar;
     uint32_t tmem_slot;
 };
@@ -659,7 +659,6 @@ swin_mlp_bwd_umma_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat1
     sts128(smem_u32(S.pb) + 4 * PLANE + tid * 16, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
     sts128(smem_u32(S.pb) + 5 * PLANE + tid * 16, 0u, 0u, 0u, 0u);
     sts128(smem_u32(S.ones0) + tid * 16, 0x3F803F80u, 0u, 0u, 0u);
-    if (tid < 16) S.red[tid] = 0.f;
     proxy_fence();
     tc_fence_before();
     __syncthreads();
@@ -794,7 +793,7 @@ swin_mlp_bwd_umma_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat1
         float s = db2[c];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) atomicAdd(&S.red[c], s);
+        if (lane == 0) S.red[warp][c] = s;          // fixed summation order: bit-identical from run to run
     }
     __syncthreads();
     tc_fence_after();
@@ -814,7 +813,7 @@ swin_mlp_bwd_umma_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat1
 #pragma unroll
         for (int c = 0; c < 16; ++c) part[HID * C + HID + c * HID + k] = any ? w[c] : 0.f;
     }
-    if (tid < 16) part[HID * C + HID + C * HID + tid] = S.red[tid];
+    if (tid < 16) part[HID * C + HID + C * HID + tid] = (S.red[0][tid] + S.red[1][tid]) + (S.red[2][tid] + S.red[3][tid]);
     tc_fence_before();
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(M_COLS) : "memory");

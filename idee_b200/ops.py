@@ -810,3 +810,10 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step):
     lib = L.load()
     L.run("adam_step", lib.idee_adam_step, p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2, eps,
                                weight_decay, step, L.stream())
+
+
+def adam_step_state(p, g, m, v, state, beta1, beta2, eps, weight_decay):
+    """Adam with (step, lr) in the 2-float device tensor ``state``: CUDA-graph capturable."""
+    lib = L.load()
+    L.run("adam_step_state", lib.idee_adam_step_state, p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), state.data_ptr(),
+          beta1, beta2, eps, weight_decay, L.stream())

@@ -40,6 +40,9 @@ class Trainer:
         self._flatten()
         self.exp_avg = torch.zeros_like(self.flat_params)
         self.exp_avg_sq = torch.zeros_like(self.flat_params)
+        # (steps taken, lr) in device memory: the fused Adam reads them there, so one captured CUDA graph serves every step
+        self.adam_state = torch.tensor([0.0, float(lr)], device=self.flat_params.device, dtype=torch.float32)
+        self._graph = None
         if self.distributed and self.world > 1:
             dist.broadcast(self.flat_params, src=0, group=self.group)   # same weights on every rank
 
@@ -112,14 +115,74 @@ class Trainer:
     def optimizer_step(self):
         self.reduce_gradients()
         self.step_count += 1
-        ops.adam_step(self.flat_params, self.flat_grads, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1],
-                      self.eps, self.weight_decay, self.step_count)
+        ops.adam_step_state(self.flat_params, self.flat_grads, self.exp_avg, self.exp_avg_sq, self.adam_state, self.betas[0],
+                            self.betas[1], self.eps, self.weight_decay)
 
     def step(self, x, mask_extreme, mask_extreme_loss):
         """forward + losses + backward + gradient all-reduce + Adam; returns (loss[1] tensor on device, outputs)."""
         total, out = self.forward_backward(x, mask_extreme, mask_extreme_loss)
         self.optimizer_step()
         return total.detach(), out
+
+    # ---- learning-rate schedule / checkpointing (train_synthetic.py:127-131, utils_train.py:576-582) ----
+    def set_lr(self, lr: float):
+        """Schedulers (the reference steps a warm-up + cosine / step schedule every iteration) write the device-side lr."""
+        self.lr = float(lr)
+        self.adam_state[1] = self.lr
+
+    def state_dict(self):
+        """Optimiser state in the shape of torch.optim.Adam's essentials: flat first / second moments, step count, lr."""
+        return {"step": self.step_count, "lr": self.lr, "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone()}
+
+    def load_state_dict(self, sd):
+        self.step_count = int(sd["step"])
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.lr = float(sd["lr"])
+        self.adam_state.copy_(torch.tensor([float(self.step_count), self.lr]))
+
+    # ---- the whole step as ONE CUDA graph launch ----
+    def capture(self, x, mask_extreme, mask_extreme_loss, warmup: int = 3):
+        """Capture zero-grad + forward + losses + backward + all-reduce + Adam into a CUDA graph (static input buffers).
+
+        The warm-up steps PyTorch needs before a capture run on copies of the training state, which is restored afterwards, so
+        capturing does not advance training.  Returns self; use ``step_graph`` afterwards."""
+        dev = self.flat_params.device
+        self._static_in = tuple(torch.empty_like(t, device=dev) for t in (x, mask_extreme, mask_extreme_loss))
+        for dst, src in zip(self._static_in, (x, mask_extreme, mask_extreme_loss)):
+            dst.copy_(src)
+        saved = (self.flat_params.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone(), self.adam_state.clone(), self.step_count)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.step(*self._static_in)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        from . import _lib
+        before = _lib.Profile.launches
+        with torch.cuda.graph(graph):
+            total, out = self.step(*self._static_in)
+        self.graph_launches = _lib.Profile.launches - before           # kernels of one replay (counted while capturing)
+        self._static_out = (total, out)
+        self.flat_params.copy_(saved[0]); self.exp_avg.copy_(saved[1]); self.exp_avg_sq.copy_(saved[2]); self.adam_state.copy_(saved[3])
+        self.step_count = saved[4]
+        self._graph = graph
+        return self
+
+    def step_graph(self, x, mask_extreme, mask_extreme_loss):
+        """One replay of the captured step on new inputs; the returned tensors are the graph's static outputs (valid until the next
+        replay)."""
+        if self._graph is None:
+            raise RuntimeError("Trainer.step_graph: call capture() first")
+        for dst, src in zip(self._static_in, (x, mask_extreme, mask_extreme_loss)):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self._graph.replay()
+        self.step_count += 1
+        from . import _lib
+        _lib.Profile.launches += self.graph_launches
+        return self._static_out
 
 
 class HostPrefetcher:

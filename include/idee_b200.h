@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define IDEE_B200_VERSION 201
+#define IDEE_B200_VERSION 202
 
 const char* idee_last_error(void);
 int idee_version(void);
@@ -179,6 +179,10 @@ int idee_rank1_planes_bwd(const float* gplanes, float* gxq, int N, int V, int64_
 /* ---- optimiser: torch.optim.Adam(lr, betas, eps, weight_decay) on one flat buffer        train_synthetic.py:127-129 ---- */
 int idee_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                    float weight_decay, int step, void* stream);
+/* the same update with the step counter and the learning rate in device memory (state[0] = steps taken so far as float, advanced
+ * by the call; state[1] = lr): one captured CUDA-graph launch sequence serves every replay, schedulers write state[1] */
+int idee_adam_step_state(float* p, const float* g, float* m, float* v, int64_t n, float* state, float beta1, float beta2, float eps,
+                         float weight_decay, void* stream);
 
 #ifdef __cplusplus
 }
