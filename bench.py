@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager kernel launches instead of one CUDA graph per step")
     return ap.parse_args()
 
 
@@ -234,9 +235,9 @@ def entry_kernels(name):
     emb = "1" if "+embed" in name else "0"
     G = int(m.group(1)) * int(m.group(2)) * int(m.group(3))
     if "fwd" in name:
-        return [f"swin_fwd_tc_kernel<{w},{emb}>", f"swin_fwd_umma_kernel<{w},{emb}>"]
-    return ["swin_mlp_bwd_tc_kernel", f"swin_attn_bwd_tc_kernel<{w},{emb}>", f"swin_grad_finalize_kernel<{G}>",
-            f"swin_bwd_umma_kernel<{w},{emb}>"]
+        return [f"swin_fwd_tc_kernel<{w},{emb}>", f"swu::swin_fwd_umma_kernel<{w},{emb}>"]
+    return ["swin_mlp_bwd_tc_kernel", f"swin_attn_bwd_tc_kernel<{w},{emb}>", "swu::swin_mlp_bwd_umma_kernel",
+            f"swu::swin_attn_bwd_umma_kernel<{w},{emb}>", f"swin_grad_finalize_kernel<{G}>"]
 
 
 def ncu_traffic(name):
@@ -324,6 +325,22 @@ def main():
     for _ in range(args.warmup):
         trainer.step(x, me, ml)
     barrier()
+    # the whole step (zero-grad, forward, losses, backward, gradient all-reduce, Adam) as ONE CUDA graph launch
+    graph_info = {"enabled": False}
+    if not args.no_graph:
+        try:
+            trainer.capture(x, me, ml)
+            x, me, ml = trainer._static_in
+            graph_info = {"enabled": True, "kernels_per_replay": trainer.graph_launches}
+        except Exception as e:                                            # capture is an optimisation: fall back to eager launches
+            import traceback
+            frames = [l.strip() for l in traceback.format_exc().splitlines() if l.strip().startswith("File")]
+            graph_info = {"enabled": False, "error": f"{type(e).__name__}: {e}"[:200], "where": frames[-6:]}
+            torch.cuda.synchronize()
+    step_fn = trainer.step_graph if graph_info["enabled"] else trainer.step
+    for _ in range(2):
+        step_fn(x, me, ml)
+    barrier()
     clocks = ClockSampler(list(range(world)) if (rank == 0 and world > 1) else [local] if rank == 0 else None)
     clocks.start()
     _lib.Profile.reset(events=False)
@@ -331,7 +348,7 @@ def main():
     e0.record()
     t_host = time.perf_counter()
     for _ in range(args.steps):
-        loss, _ = trainer.step(x, me, ml)
+        loss, _ = step_fn(x, me, ml)
     host_ms = (time.perf_counter() - t_host) * 1e3 / args.steps      # host time to ENQUEUE one step (no synchronisation inside)
     e1.record()
     barrier()
@@ -359,7 +376,7 @@ def main():
         xd, med, mld = pf.take(i & 1)
         if i + 1 < args.steps:
             pf.stage((i + 1) & 1, (x_h, me_h, ml_h))
-        loss, out = trainer.step(xd, med, mld)
+        loss, out = step_fn(xd, med, mld)
         pf.release(i & 1)
         res.put(i & 1, (out["pred"], loss, out["anomaly"]))
         if i > 0:
@@ -373,6 +390,15 @@ def main():
     clock_info = clocks.stop()      # sampled over both timed regions (device-resident and end-to-end), every 100 ms
     h2d = x_h.numel() * 4 + me_h.numel() * 4 + ml_h.numel() * 4
     d2h = pred_h.numel() * 4 + 4 + anomaly_h.numel()
+
+    # ---- data-parallel consistency: after the timed steps every rank must hold bit-identical parameters ----
+    dp_check = None
+    if world > 1:
+        ref = trainer.flat_params.clone()
+        dist.broadcast(ref, src=0)
+        div = (trainer.flat_params - ref).abs().max().reshape(1).double()
+        dist.all_reduce(div, op=dist.ReduceOp.MAX)
+        dp_check = {"max_param_divergence_across_ranks": float(div.item()), "steps_taken": trainer.step_count}
 
     # ---- inference throughput (eval mode, no_grad), same inputs, device resident ----
     model.eval()
@@ -443,7 +469,7 @@ def main():
                 "data": "synthetic", "config": workload_config(args, n_gpus), "impl": "idee_b200",
                 "e2e": {"value": n_gpus * B / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e},
-                "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms, "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms, "cuda_graph": graph_info, "dp_check": dp_check, "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "gpu_baseline": gpu_baseline,
                 "model_tflops_per_gpu": whole_model_tf, "executed_gflop_per_sample": executed_gflop, "loss": loss_val,
                 "inference": {"value": n_gpus * B / (ms_infer / 1e3), "unit": UNIT, "ms_per_step": ms_infer,

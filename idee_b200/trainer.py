@@ -43,6 +43,10 @@ class Trainer:
         # (steps taken, lr) in device memory: the fused Adam reads them there, so one captured CUDA graph serves every step
         self.adam_state = torch.tensor([0.0, float(lr)], device=self.flat_params.device, dtype=torch.float32)
         self._graph = None
+        # Steps never run on the legacy default stream: autograd ties each parameter's gradient accumulator to the stream of its
+        # first backward, and an accumulator tied to the default stream (which synchronises with every other stream) invalidates a
+        # later CUDA-graph capture.  When called on the default stream the step hops onto this stream and back.
+        self.stream = torch.cuda.Stream(self.flat_params.device) if self.flat_params.is_cuda else None
         if self.distributed and self.world > 1:
             dist.broadcast(self.flat_params, src=0, group=self.group)   # same weights on every rank
 
@@ -120,6 +124,14 @@ class Trainer:
 
     def step(self, x, mask_extreme, mask_extreme_loss):
         """forward + losses + backward + gradient all-reduce + Adam; returns (loss[1] tensor on device, outputs)."""
+        dev = self.flat_params.device
+        if self.stream is not None and torch.cuda.current_stream(dev) == torch.cuda.default_stream(dev):
+            self.stream.wait_stream(torch.cuda.default_stream(dev))
+            with torch.cuda.stream(self.stream):
+                total, out = self.forward_backward(x, mask_extreme, mask_extreme_loss)
+                self.optimizer_step()
+            torch.cuda.default_stream(dev).wait_stream(self.stream)
+            return total.detach(), out
         total, out = self.forward_backward(x, mask_extreme, mask_extreme_loss)
         self.optimizer_step()
         return total.detach(), out
@@ -152,7 +164,7 @@ class Trainer:
         for dst, src in zip(self._static_in, (x, mask_extreme, mask_extreme_loss)):
             dst.copy_(src)
         saved = (self.flat_params.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone(), self.adam_state.clone(), self.step_count)
-        side = torch.cuda.Stream(dev)
+        side = self.stream
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(warmup):
@@ -161,7 +173,7 @@ class Trainer:
         graph = torch.cuda.CUDAGraph()
         from . import _lib
         before = _lib.Profile.launches
-        with torch.cuda.graph(graph):
+        with torch.cuda.graph(graph, stream=side):
             total, out = self.step(*self._static_in)
         self.graph_launches = _lib.Profile.launches - before           # kernels of one replay (counted while capturing)
         self._static_out = (total, out)
