@@ -38,6 +38,9 @@ def parse_args():
     ap.add_argument("--hw", type=int, default=200)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
                     help="bf16: tensor-core operands + fp32 accumulate for the GEMM-shaped kernels; fp32: exact CUDA-core path")
+    ap.add_argument("--encoder", default="Swin_3D", choices=["Swin_3D", "CNN_3D"], help="encoder backbone (config.py:40)")
+    ap.add_argument("--mode", default="train", choices=["train", "infer"],
+                    help="infer: eval-forward throughput sweep over B in {1,2,4,8,16,32} (BASELINE.json configs[3])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true")
@@ -272,10 +275,53 @@ def op_flops(name, B, V, T, H, W):
     return None
 
 
+def run_infer_sweep(args):
+    """BASELINE.json configs[3]: inference throughput of the IDEE model (default: 3D-CNN backbone) over batch sizes, one GPU."""
+    assert torch.cuda.is_available(), "the inference sweep needs a CUDA device"
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    from idee_b200 import _lib
+    from idee_b200.config import default_config
+    from idee_b200.models.build import VQ_model
+    from oracle import idee_oracle as O
+    _lib.set_precision(args.precision)
+    torch.manual_seed(0)
+    model = VQ_model(default_config(encoder=args.encoder)).to(dev).eval()
+    ocfg = O.OracleConfig(encoder=args.encoder)
+    sweep = []
+    for B in (1, 2, 4, 8, 16, 32):
+        x = O.make_inputs(ocfg, B, 8, args.hw, args.hw, seed=0)[0].to(dev)
+        with torch.no_grad():
+            for _ in range(max(args.warmup, 2)):
+                model(x)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                model(x)
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        sweep.append({"batch": B, "ms_per_step": ms, "samples_per_s": B / (ms / 1e3)})
+        del x
+        torch.cuda.empty_cache()
+    best = max(sweep, key=lambda r: r["samples_per_s"])
+    fwd_gflop = 252.61 if args.encoder == "CNN_3D" else 190.68          # SURVEY.md section 8d
+    line = {"metric": "inference_samples_per_sec", "value": best["samples_per_s"], "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": best["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic", "impl": "idee_b200",
+            "config": {"workload": f"IDEE VQ_model eval forward, encoder {args.encoder}, synthetic-CERRA [V=6, C=1, T=8, {args.hw}x{args.hw}], "
+                                   f"batch sweep (BASELINE.json configs[3])", "best_batch": best["batch"]},
+            "sweep": sweep, "model_tflops_per_gpu": best["samples_per_s"] * fwd_gflop / 1e3}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.mode == "infer":
+        return run_infer_sweep(args)
 
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))

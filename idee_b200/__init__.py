@@ -15,5 +15,5 @@ def install_as_reference_modules() -> None:
     """Make ``importlib.import_module('models.encoder.Swin_3D')`` etc. resolve to the idee_b200 modules, so the
     reference's ``models/build.py::import_class`` (build.py:17-20) and training scripts pick up the CUDA path."""
     import importlib
-    for name in ("encoder.Swin_3D", "codebook.LFQ", "classifier.CNN_3D", "losses", "build"):
+    for name in ("encoder.Swin_3D", "encoder.CNN_3D", "codebook.LFQ", "classifier.CNN_3D", "losses", "build"):
         sys.modules["models." + name] = importlib.import_module("idee_b200.models." + name)

@@ -58,6 +58,9 @@ _SIGS = {
     "idee_anomaly_rank1_bwd": (c_int, [c_vp] * 5 + [c_int] * 3 + [c_i64, c_int] + [c_vp] * 6),
     "idee_rank1_planes_fwd": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_vp]),
     "idee_rank1_planes_bwd": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_vp]),
+    "idee_ln_act_res_fwd": (c_int, [c_vp] * 6 + [c_int, c_int, c_i64, c_int, c_vp]),
+    "idee_ln_act_res_bwd_workspace_bytes": (c_sz, [c_int]),
+    "idee_ln_act_res_bwd": (c_int, [c_vp] * 7 + [c_int, c_int, c_i64, c_int, c_vp, c_sz, c_vp]),
     "idee_adam_step": (c_int, [c_vp] * 4 + [c_i64] + [c_f32] * 5 + [c_int, c_vp]),
     "idee_adam_step_state": (c_int, [c_vp] * 4 + [c_i64, c_vp] + [c_f32] * 4 + [c_vp]),
 }
@@ -173,7 +176,7 @@ def set_precision(mode: str) -> None:
 LAUNCHES = {"embed_ln_fwd": 1, "embed_ln_bwd": 2, "swin_block_fwd": 1, "swin_block_bwd": 3, "conv3d_fwd": 1, "conv3d_dgrad": 1,
             "conv3d_wgrad": 2, "conv3d_fwd_bf16": 2, "conv3d_dgrad_bf16": 3, "conv3d_wgrad_bf16": 2, "lfq_fwd": 2, "lfq_fwd_eval": 1, "lfq_bwd": 2, "bce_loss_fwd": 4, "anomaly_l1_fwd": 2,
             "anomaly_l1_bwd": 1, "anomaly_rank1_fwd": 2, "anomaly_rank1_bwd": 1, "rank1_planes_fwd": 1,
-            "rank1_planes_bwd": 1, "adam_step": 1, "adam_step_state": 2}
+            "rank1_planes_bwd": 1, "adam_step": 1, "adam_step_state": 2, "ln_act_res_fwd": 1, "ln_act_res_bwd": 2}
 
 
 class Profile:

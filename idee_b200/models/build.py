@@ -30,8 +30,13 @@ class VQ_model(nn.Module):
                 mlp_ratio=config.en_mlp_ratio, drop_rate=config.en_drop_rate, attn_drop_rate=config.en_attn_drop_rate,
                 drop_path_rate=config.en_drop_path_rate, qkv_bias=config.en_qkv_bias, qk_scale=config.en_qk_scale,
                 patch_size=config.en_patch_size, patch_norm=config.en_patch_norm, use_checkpoint=config.en_use_checkpoint)
+        elif config.encoder == "CNN_3D":
+            self.encoder = import_class('encoder', config.encoder)(
+                in_vars=config.in_channels_dynamic, in_channels=config.in_channels, out_channels=config.en_embed_dim,
+                drop_path_rate=config.en_drop_path_rate, drop_rate=config.en_drop_rate)
         else:
-            raise NotImplementedError(f"idee_b200: encoder {config.encoder} is not built (hot path = Swin_3D)")
+            raise NotImplementedError(f"idee_b200: encoder {config.encoder} is not built (built: Swin_3D, CNN_3D; Mamba needs the "
+                                      f"un-vendored mamba_ssm package)")
         self.cls = import_class('classifier', 'CNN_3D')(in_var=config.in_channels_dynamic, embed_dim=config.codebook_dim,
                                                         dim=config.cls_dim, drop_rate=config.cls_drop_rate)
         self.vq = import_class('codebook', 'LFQ')(dim=config.codebook_dim, codebook_size=config.codebook_size,

@@ -806,6 +806,51 @@ class Rank1Planes(torch.autograd.Function):
         return gxq
 
 
+class LnActRes(torch.autograd.Function):
+    """out = shortcut + ReLU(LayerNorm(y) * gamma + beta) on channel-last tokens [N,V,T,H,W,16]; gamma / beta packs [V][16].
+    models/encoder/CNN_3D.py:129-147.  want_bf16: also return a non-differentiable bf16 copy of out (input of the next conv)."""
+
+    @staticmethod
+    def forward(ctx, y, shortcut, gpack: ParamPack, bpack: ParamPack, want_bf16, *params):
+        L.require_cuda(y, shortcut)
+        lib = L.load()
+        y, shortcut = _f32c(y), _f32c(shortcut)
+        gamma, beta = gpack.tensor(), bpack.tensor()
+        L.require_cuda(gamma, beta)
+        N, V, T, H, W, Cc = y.shape
+        out = torch.empty_like(y)
+        out16 = torch.empty_like(y, dtype=torch.bfloat16) if want_bf16 else None
+        L.run("ln_act_res_fwd", lib.idee_ln_act_res_fwd, y.data_ptr(), shortcut.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+              out.data_ptr(), L.ptr(out16), N, V, T * H * W, Cc, L.stream())
+        ctx.save_for_backward(y)
+        ctx.packs = (gpack, bpack)
+        if want_bf16:
+            ctx.mark_non_differentiable(out16)
+            ctx.set_materialize_grads(False)
+            return out, out16
+        return out
+
+    @staticmethod
+    def backward(ctx, gout, *_unused):
+        lib = L.load()
+        (y,) = ctx.saved_tensors
+        gpack, bpack = ctx.packs
+        gamma, beta = gpack.tensor(), bpack.tensor()
+        N, V, T, H, W, Cc = y.shape
+        gout = _f32c(gout)
+        gy = torch.empty_like(y)
+        dg, db = gpack.grad_out(gamma), bpack.grad_out(beta)
+        nws = lib.idee_ln_act_res_bwd_workspace_bytes(V)
+        ws = L.workspace(nws, y.device)
+        L.run("ln_act_res_bwd", lib.idee_ln_act_res_bwd, y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), gout.data_ptr(), gy.data_ptr(),
+              dg.data_ptr(), db.data_ptr(), N, V, T * H * W, Cc, ws.data_ptr(), nws, L.stream())
+        return (gy, gout, None, None, None, *gpack.split_grad(dg), *bpack.split_grad(db))
+
+
+def ln_act_res(y, shortcut, gpack: ParamPack, bpack: ParamPack, want_bf16: bool = False):
+    return LnActRes.apply(y, shortcut, gpack, bpack, bool(want_bf16), *gpack.params(), *bpack.params())
+
+
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step):
     lib = L.load()
     L.run("adam_step", lib.idee_adam_step, p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2, eps,

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define IDEE_B200_VERSION 202
+#define IDEE_B200_VERSION 203
 
 const char* idee_last_error(void);
 int idee_version(void);
@@ -175,6 +175,16 @@ int idee_anomaly_rank1_bwd(const float* xq, const float* mask, const float* w_ou
  * The backward gathers channels 0..V-1 of the image gradient into gxq [N,V,THW].  1 <= V <= 15. */
 int idee_rank1_planes_fwd(const float* xq, float* planes, int N, int V, int64_t THW, void* stream);
 int idee_rank1_planes_bwd(const float* gplanes, float* gxq, int N, int V, int64_t THW, void* stream);
+
+/* ---- CNN_3D encoder: per-token tail of a residual conv block                     models/encoder/CNN_3D.py:74-147 ----
+ * out = shortcut + ReLU(LayerNorm_16(y) * gamma[v] + beta[v]) on channel-last tokens [N,V,THW,16] (y = conv3^3 output of
+ * idee_conv3d_fwd); gamma / beta [V][16].  out_bf16 (optional) receives a bf16 copy of out for the next conv (x_dtype 1).
+ * Backward: gy = d/dy, dgamma / dbeta [V][16]; the gradient w.r.t. the shortcut is gout itself. */
+int idee_ln_act_res_fwd(const float* y, const float* shortcut, const float* gamma, const float* beta, float* out, void* out_bf16,
+                        int N, int V, int64_t THW, int C, void* stream);
+size_t idee_ln_act_res_bwd_workspace_bytes(int V);
+int idee_ln_act_res_bwd(const float* y, const float* gamma, const float* beta, const float* gout, float* gy, float* dgamma,
+                        float* dbeta, int N, int V, int64_t THW, int C, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- optimiser: torch.optim.Adam(lr, betas, eps, weight_decay) on one flat buffer        train_synthetic.py:127-129 ---- */
 int idee_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,

@@ -32,6 +32,7 @@ Tensor = torch.Tensor
 # ----------------------------------------------------------------------------------------------
 @dataclass
 class OracleConfig:
+    encoder: str = "Swin_3D"              # config.py:40  'Swin_3D' | 'CNN_3D'
     in_vars: int = 6                      # config.py:49  in_channels_dynamic
     in_chans: int = 1                     # config.py:50  (1 synthetic, 2 real)
     embed_dim: Sequence[int] = (16, 16)   # config.py:51
@@ -223,6 +224,37 @@ def swin3d_forward(sd: Dict[str, Tensor], x: Tensor, cfg: OracleConfig, prefix: 
     return torch.cat(outs, dim=1)
 
 
+def cnn3d_forward(sd: Dict[str, Tensor], x: Tensor, cfg: OracleConfig, prefix: str = "encoder.") -> Tensor:
+    """encoder CNN_3D.forward, models/encoder/CNN_3D.py:214-237 with conv_block.forward (:119-147) and its PatchEmbed3D
+    (:44-71: conv k=1 without bias + LayerNorm without affine).  x [N,V,C,D,H,W] -> [N,V,E,D,H,W]."""
+    outs = []
+    chans = [cfg.in_chans] + list(cfg.embed_dim[:-1])
+    for v in range(cfg.in_vars):
+        xv = x[:, v]
+        for l, dim in enumerate(cfg.embed_dim):
+            p = f"{prefix}layers_var.{v}.{l}."
+            if chans[l] != dim:                                                           # :113-117
+                xv = F.conv3d(xv, sd[p + "downsample.proj.weight"])
+                B, C, D, H, W = xv.shape
+                xv = layer_norm_noaffine(xv.flatten(2).transpose(1, 2)).transpose(1, 2).reshape(B, C, D, H, W)
+            B, C, D, H, W = xv.shape
+            for conv, norm in (("conv1", "norm1"), ("conv2", "norm2")):                   # :133-145
+                y = F.conv3d(F.pad(xv, (1,) * 6, mode="replicate"), sd[p + conv + ".weight"])
+                y = y.reshape(B, C, D * H * W).permute(0, 2, 1)
+                y = F.layer_norm(y, (C,), sd[p + norm + ".weight"], sd[p + norm + ".bias"], eps=1e-5)
+                xv = xv + F.relu(y.permute(0, 2, 1).reshape(B, C, D, H, W))
+        pv = f"{prefix}proj_var.{v}."
+        xv = F.conv3d(F.pad(xv, (1,) * 6, mode="replicate"), sd[pv + "0.weight"], sd[pv + "0.bias"])
+        xv = F.relu(xv)
+        xv = F.conv3d(F.pad(xv, (1,) * 6, mode="replicate"), sd[pv + "2.weight"], sd[pv + "2.bias"])
+        outs.append(xv.unsqueeze(1))
+    return torch.cat(outs, dim=1)
+
+
+def encoder_forward(sd, x, cfg: OracleConfig) -> Tensor:
+    return cnn3d_forward(sd, x, cfg) if cfg.encoder == "CNN_3D" else swin3d_forward(sd, x, cfg)
+
+
 # ----------------------------------------------------------------------------------------------
 # LFQ (codebook_size 2^k; IDEE uses k=1)
 # ----------------------------------------------------------------------------------------------
@@ -294,7 +326,7 @@ def classifier_forward(sd, zq: Tensor, cfg: OracleConfig, prefix: str = "cls."):
 # ----------------------------------------------------------------------------------------------
 def vq_model_forward(sd, x: Tensor, cfg: OracleConfig, training: bool):
     """VQ_model.forward, build.py:130-159."""
-    z = swin3d_forward(sd, x, cfg)
+    z = encoder_forward(sd, x, cfg)
     N, V, C, T, H, W = z.shape
     zt = z.permute(0, 2, 1, 3, 4, 5).reshape(N, C, V * T * H * W).permute(0, 2, 1)      # :150
     zq, idx, aux, _ = lfq_forward(sd, zt, cfg, training)
@@ -346,7 +378,20 @@ def param_shapes(cfg: OracleConfig) -> Dict[str, Tuple[int, ...]]:
     (SURVEY.md section 9 'Shapes at defaults'; checked against the reference by make_golden.py)."""
     shp: Dict[str, Tuple[int, ...]] = {}
     hid = lambda d: int(d * cfg.mlp_ratio)
-    for v in range(cfg.in_vars):
+    if cfg.encoder == "CNN_3D":                                    # models/encoder/CNN_3D.py:97-117, 176-183 (module order)
+        chans = [cfg.in_chans] + list(cfg.embed_dim[:-1])
+        for v in range(cfg.in_vars):
+            for l, dim in enumerate(cfg.embed_dim):
+                p = f"encoder.layers_var.{v}.{l}."
+                shp[p + "conv1.weight"] = (dim, dim, 3, 3, 3)
+                shp[p + "norm1.weight"] = (dim,)
+                shp[p + "norm1.bias"] = (dim,)
+                shp[p + "conv2.weight"] = (dim, dim, 3, 3, 3)
+                shp[p + "norm2.weight"] = (dim,)
+                shp[p + "norm2.bias"] = (dim,)
+                if chans[l] != dim:
+                    shp[p + "downsample.proj.weight"] = (dim, chans[l], 1, 1, 1)
+    for v in range(cfg.in_vars if cfg.encoder != "CNN_3D" else 0):
         for l, dim in enumerate(cfg.embed_dim):
             p = f"encoder.layers_var.{v}.{l}."
             ws = cfg.window_size[l]

@@ -89,6 +89,9 @@ CASES = {
     "two_chan": (dict(in_channels_dynamic=2, in_channels=2), 1, 8, 8, 8, "random"),         # real-data C=2
     "six_vars": (dict(in_channels_dynamic=6, in_channels=1), 1, 8, 8, 8, "random"),         # full V, joint head 96ch
     "long_t": (dict(in_channels_dynamic=1, in_channels=1), 1, 12, 8, 8, "random"),          # T=12: stage-2 pad 12->16
+    # BASELINE.json configs[3]: 3D-CNN backbone (models/encoder/CNN_3D.py) instead of the Swin encoder
+    "cnn_encoder": (dict(encoder="CNN_3D", in_channels_dynamic=2, in_channels=1), 1, 8, 8, 12, "random"),
+    "cnn_encoder_2ch": (dict(encoder="CNN_3D", in_channels_dynamic=2, in_channels=2), 1, 8, 10, 14, "reference"),
 }
 
 
@@ -100,7 +103,7 @@ def run_case(name, build, losses, config_mod):
     cfg = reference_config(config_mod, **over)
     torch.manual_seed(0)
     model = build.VQ_model(cfg)
-    ocfg = O.OracleConfig(in_vars=cfg.in_channels_dynamic, in_chans=cfg.in_channels)
+    ocfg = O.OracleConfig(encoder=cfg.encoder, in_vars=cfg.in_channels_dynamic, in_chans=cfg.in_channels)
     # parameter inventory of the oracle must equal the reference's
     ref_shapes = {k: tuple(v.shape) for k, v in model.named_parameters()}
     assert ref_shapes == O.param_shapes(ocfg), "oracle param_shapes() disagrees with the reference"
@@ -111,6 +114,7 @@ def run_case(name, build, losses, config_mod):
     out = {}
     out["cfg_in_vars"] = np.int64(cfg.in_channels_dynamic)
     out["cfg_in_chans"] = np.int64(cfg.in_channels)
+    out["cfg_encoder"] = np.array(cfg.encoder)
     for k, v in model.state_dict().items():
         if k.endswith("relative_position_index") or k == "vq.mask":
             continue

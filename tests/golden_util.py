@@ -15,7 +15,8 @@ CASES = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.pa
 
 def load_case(name):
     d = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
-    cfg = O.OracleConfig(in_vars=int(d["cfg_in_vars"]), in_chans=int(d["cfg_in_chans"]))
+    enc = str(d["cfg_encoder"]) if "cfg_encoder" in d.files else "Swin_3D"
+    cfg = O.OracleConfig(encoder=enc, in_vars=int(d["cfg_in_vars"]), in_chans=int(d["cfg_in_chans"]))
     sd = {k[3:]: torch.from_numpy(d[k]) for k in d.files if k.startswith("sd/")}
     grads = {k[5:]: torch.from_numpy(d[k]) for k in d.files if k.startswith("grad/")}
     ins = {k[3:]: torch.from_numpy(d[k]) for k in d.files if k.startswith("in/")}
