@@ -72,7 +72,8 @@ class VQ_model(nn.Module):
 
     def forward(self, x_d):
         from .. import _lib
-        if _lib.PRECISION == "bf16" and getattr(self.encoder, "forward_tokens", None) is not None and self.vq.dim == 16:
+        one_bit = self.vq.codebook_dim == 1        # the IDEE configuration: rank-1 z_q, project_in folded into the encoder's last conv
+        if _lib.PRECISION == "bf16" and getattr(self.encoder, "forward_tokens", None) is not None and self.vq.dim == 16 and one_bit:
             # the quantiser's project_in (Linear 16 -> 1) is the only consumer of the encoder output: fold it into the encoder's
             # last 3x3x3 conv (one 16 -> 1 conv instead of 16 -> 16 followed by a dot product; forward, data and weight gradient)
             s = self.encoder.forward_tokens(x_d, fold_last=(self.vq.project_in.weight, self.vq.project_in.bias))   # [N,V,T,H,W]
@@ -85,6 +86,9 @@ class VQ_model(nn.Module):
             z_q, anomaly, loss_z_q = self.vq(tok.view(N, V * T * H * W, C))  # token order (v,t,h,w) as build.py:150
         z_q = z_q.view(N, V, T, H, W, C).permute(0, 1, 5, 2, 3, 4)      # logical [N,V,C,T,H,W]
         anomaly = anomaly.view(N, V, T, H, W)
+        if not one_bit:                                                     # codebook_size 2^K, K > 1: z_q has rank K, generic paths
+            z, y = self.cls(z_q)
+            return z, y, anomaly, z_q, loss_z_q.unsqueeze(0)
         # the joint head consumes the rank-1 form of z_q (x * w_out + b_out): identical result, 1/6 of the conv1 work
         rank1 = (self.vq.last_scalar.view(N, V, T, H, W), self.vq.project_out.weight, self.vq.project_out.bias)
         zq16 = getattr(self.vq, "last_zq_bf16", None)

@@ -31,10 +31,10 @@ class LFQ(nn.Module):
         codebook_dim = int(log2(codebook_size))
         codebook_dims = codebook_dim * num_codebooks
         dim = dim if dim is not None else codebook_dims
-        if not (codebook_size == 2 and num_codebooks == 1 and dim == 16 and codebook_scale == 1.
+        if not (codebook_size in (2, 4, 8, 16) and num_codebooks == 1 and dim == 16 and codebook_scale == 1.
                 and frac_per_sample_entropy == 1. and isinstance(straight_through_activation, nn.Identity)):
-            raise NotImplementedError("idee_b200: the LFQ kernel is built for dim=16, codebook_size=2, one codebook, "
-                                      "scale 1, identity activation (the IDEE configuration, build.py:87-91)")
+            raise NotImplementedError("idee_b200: the LFQ kernels are built for dim=16, codebook_size 2 (the IDEE configuration, "
+                                      "build.py:87-91), 4, 8 or 16, one codebook, scale 1, identity activation")
         has_projections = dim != codebook_dims
         self.project_in = nn.Linear(dim, codebook_dims) if has_projections else nn.Identity()
         self.project_out = nn.Linear(codebook_dims, dim) if has_projections else nn.Identity()
@@ -98,6 +98,22 @@ class LFQ(nn.Module):
         if is_img_or_video:
             x = x.movedim(1, -1)
         assert x.shape[-1] == self.dim, f'expected dimension of {self.dim} but received {x.shape[-1]}'
+        if self.codebook_dim > 1:
+            # K-bit sign codes (codebook_size 4, 8, 16): distances to the 2^K codes, argmin, STE and the loss sums in one kernel each way
+            if return_loss_breakdown:
+                raise NotImplementedError("idee_b200: return_loss_breakdown is not built (unused by IDEE, build.py:151)")
+            zq, idx, aux = ops.LFQGeneralFn.apply(x, self.project_in.weight, self.project_in.bias, self.project_out.weight,
+                                                  self.project_out.bias, self.training, float(inv_temperature),
+                                                  float(self.commitment_loss_weight), float(self.entropy_loss_weight),
+                                                  float(self.diversity_gamma), self.codebook_dim)
+            self.last_scalar = None
+            if not self.training:
+                aux = self.zero
+            if is_img_or_video:
+                zq = zq.movedim(-1, 1)
+            if self.keep_num_codebooks_dim:
+                idx = idx.unsqueeze(-1)
+            return Return(zq, idx, aux)
         zq, idx, aux, xq = ops.LFQFn.apply(x, self.project_in.weight, self.project_in.bias, self.project_out.weight,
                                            self.project_out.bias, self.training, float(inv_temperature),
                                            float(self.commitment_loss_weight), float(self.entropy_loss_weight),

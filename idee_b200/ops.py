@@ -663,6 +663,51 @@ class LFQScalarFn(torch.autograd.Function):
         return gs, grads[17:33].view(16, 1), grads[33:49], None, None, None, None, None, None, None
 
 
+class LFQGeneralFn(torch.autograd.Function):
+    """LFQ with a 2^K-entry codebook, K = 2..4: z [..., 16] -> (z_q [..., 16], indices int64 [...], aux scalar).  LFQ.py:183-307."""
+
+    @staticmethod
+    def forward(ctx, z, w_in, b_in, w_out, b_out, training, inv_temp, lam_commit, lam_ent, gamma, bits):
+        L.require_cuda(z, w_in, w_out)
+        lib = L.load()
+        z = _f32c(z)
+        w_in, b_in, w_out, b_out = _f32c(w_in), _f32c(b_in), _f32c(w_out), _f32c(b_out)
+        ntok = z.numel() // z.shape[-1]
+        zq = torch.empty_like(z)
+        idx = torch.empty(z.shape[:-1], device=z.device, dtype=torch.int64)
+        stats = torch.zeros(4 + 2 ** bits, device=z.device, dtype=torch.float32)
+        nws = lib.idee_lfqk_workspace_bytes(bits)
+        ws = L.workspace(nws, z.device)
+        L.run("lfqk_fwd" if training else "lfqk_fwd_eval", lib.idee_lfqk_fwd, z.data_ptr(), w_in.data_ptr(), b_in.data_ptr(), w_out.data_ptr(),
+              b_out.data_ptr(), zq.data_ptr(), idx.data_ptr(), stats.data_ptr(), ntok, z.shape[-1], bits, int(training), inv_temp,
+              lam_commit, lam_ent, gamma, ws.data_ptr(), nws, L.stream())
+        ctx.save_for_backward(z, w_in, b_in, w_out, stats)
+        ctx.hyper = (inv_temp, lam_commit, lam_ent, gamma, bits, training)
+        ctx.mark_non_differentiable(idx)
+        ctx.set_materialize_grads(False)
+        return zq, idx, stats[0]
+
+    @staticmethod
+    def backward(ctx, gzq, _gidx, gaux):
+        lib = L.load()
+        z, w_in, b_in, w_out, stats = ctx.saved_tensors
+        inv_temp, lam_commit, lam_ent, gamma, bits, training = ctx.hyper
+        ntok = z.numel() // z.shape[-1]
+        gzq = torch.zeros_like(z) if gzq is None else _f32c(gzq)
+        gaux_t = None if (gaux is None or not training) else _f32c(gaux).reshape(1)
+        gz = torch.empty_like(z)
+        K = bits
+        grads = torch.empty(K * 16 + K + 16 * K + 16, device=z.device, dtype=torch.float32)
+        nws = lib.idee_lfqk_workspace_bytes(bits)
+        ws = L.workspace(nws, z.device)
+        L.run("lfqk_bwd", lib.idee_lfqk_bwd, z.data_ptr(), gzq.data_ptr(), L.ptr(gaux_t), stats.data_ptr(), w_in.data_ptr(), b_in.data_ptr(),
+              w_out.data_ptr(), gz.data_ptr(), grads.data_ptr(), ntok, bits, int(training), inv_temp, lam_commit, lam_ent, gamma,
+              ws.data_ptr(), nws, L.stream())
+        o = K * 16
+        return (gz, grads[:o].view(K, 16), grads[o:o + K], grads[o + K:o + K + 16 * K].view(16, K), grads[o + K + 16 * K:],
+                None, None, None, None, None, None)
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # losses
 # ----------------------------------------------------------------------------------------------------------------

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define IDEE_B200_VERSION 203
+#define IDEE_B200_VERSION 204
 
 const char* idee_last_error(void);
 int idee_version(void);
@@ -145,6 +145,18 @@ int idee_lfq_bwd(const float* z, const float* gzq, const float* gxq, const float
                  const float* b_in, const float* w_out, float* gz, float* grads, int64_t ntok, float inv_temperature,
                  float lambda_commit, float lambda_entropy, float diversity_gamma,
                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* General LFQ, codebook_size = 2^K for K = 2..4 (K = 1 is idee_lfq_fwd): project_in Linear(16,K), K-bit sign codes (argmin of the
+ * 2^K code distances, ties -> lowest index), straight-through estimator, project_out Linear(K,16), entropy / commitment losses.
+ * w_in [K][16], b_in [K], w_out [16][K], b_out [16] (reference layouts).  stats: float[4 + 2^K] = aux | H_tok | H_cb | commit | mean p.
+ * grads (backward): g_w_in [K][16] | g_b_in [K] | g_w_out [16][K] | g_b_out [16].                       LFQ.py:92-101,134-146,183-307 */
+size_t idee_lfqk_workspace_bytes(int codebook_bits);
+int idee_lfqk_fwd(const float* z, const float* w_in, const float* b_in, const float* w_out, const float* b_out, float* zq,
+                  int64_t* indices, float* stats, int64_t ntok, int dim, int codebook_bits, int training, float inv_temperature,
+                  float lambda_commit, float lambda_entropy, float diversity_gamma, void* workspace, size_t workspace_bytes, void* stream);
+int idee_lfqk_bwd(const float* z, const float* gzq, const float* g_aux, const float* stats, const float* w_in, const float* b_in,
+                  const float* w_out, float* gz, float* grads, int64_t ntok, int codebook_bits, int training, float inv_temperature,
+                  float lambda_commit, float lambda_entropy, float diversity_gamma, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- losses                                                                         models/losses.py:98-168 ----
  * BCE_loss_synthetic over K logit maps sharing one target: element (k,n,i) of pred at k*stride_k + n*stride_n + i, i<HW;

@@ -92,6 +92,9 @@ CASES = {
     # BASELINE.json configs[3]: 3D-CNN backbone (models/encoder/CNN_3D.py) instead of the Swin encoder
     "cnn_encoder": (dict(encoder="CNN_3D", in_channels_dynamic=2, in_channels=1), 1, 8, 8, 12, "random"),
     "cnn_encoder_2ch": (dict(encoder="CNN_3D", in_channels_dynamic=2, in_channels=2), 1, 8, 10, 14, "reference"),
+    # general LFQ: 2^K-entry codebooks of K-bit sign codes (LFQ.py:92-101,134-146)
+    "lfq_4_codes": (dict(in_channels_dynamic=2, in_channels=1, codebook_size=4), 1, 8, 8, 12, "random"),
+    "lfq_16_codes": (dict(in_channels_dynamic=1, in_channels=1, codebook_size=16), 2, 8, 8, 8, "random"),
 }
 
 
@@ -103,7 +106,7 @@ def run_case(name, build, losses, config_mod):
     cfg = reference_config(config_mod, **over)
     torch.manual_seed(0)
     model = build.VQ_model(cfg)
-    ocfg = O.OracleConfig(encoder=cfg.encoder, in_vars=cfg.in_channels_dynamic, in_chans=cfg.in_channels)
+    ocfg = O.OracleConfig(encoder=cfg.encoder, in_vars=cfg.in_channels_dynamic, in_chans=cfg.in_channels, codebook_size=cfg.codebook_size)
     # parameter inventory of the oracle must equal the reference's
     ref_shapes = {k: tuple(v.shape) for k, v in model.named_parameters()}
     assert ref_shapes == O.param_shapes(ocfg), "oracle param_shapes() disagrees with the reference"
@@ -115,6 +118,7 @@ def run_case(name, build, losses, config_mod):
     out["cfg_in_vars"] = np.int64(cfg.in_channels_dynamic)
     out["cfg_in_chans"] = np.int64(cfg.in_channels)
     out["cfg_encoder"] = np.array(cfg.encoder)
+    out["cfg_codebook_size"] = np.int64(cfg.codebook_size)
     for k, v in model.state_dict().items():
         if k.endswith("relative_position_index") or k == "vq.mask":
             continue

@@ -16,7 +16,8 @@ CASES = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.pa
 def load_case(name):
     d = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     enc = str(d["cfg_encoder"]) if "cfg_encoder" in d.files else "Swin_3D"
-    cfg = O.OracleConfig(encoder=enc, in_vars=int(d["cfg_in_vars"]), in_chans=int(d["cfg_in_chans"]))
+    cbs = int(d["cfg_codebook_size"]) if "cfg_codebook_size" in d.files else 2
+    cfg = O.OracleConfig(encoder=enc, in_vars=int(d["cfg_in_vars"]), in_chans=int(d["cfg_in_chans"]), codebook_size=cbs)
     sd = {k[3:]: torch.from_numpy(d[k]) for k in d.files if k.startswith("sd/")}
     grads = {k[5:]: torch.from_numpy(d[k]) for k in d.files if k.startswith("grad/")}
     ins = {k[3:]: torch.from_numpy(d[k]) for k in d.files if k.startswith("in/")}
@@ -33,9 +34,14 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
 
 
 def lfq_scalar(sd, z_enc: torch.Tensor) -> torch.Tensor:
-    """pre-quantiser scalar s per token from an encoder output [N,V,C,T,H,W] (LFQ.py:211)."""
-    w, b = sd["vq.project_in.weight"], sd["vq.project_in.bias"]
-    return torch.einsum("nvcthw,c->nvthw", z_enc.double().cpu(), w[0].double().cpu()) + b.double().cpu()
+    """pre-quantiser scalar s per token from an encoder output [N,V,C,T,H,W] (LFQ.py:211); for a K-bit codebook the
+    projection closest to a sign change, min_i |s_i| (signed), since any bit can flip the index."""
+    w, b = sd["vq.project_in.weight"].double().cpu(), sd["vq.project_in.bias"].double().cpu()
+    s = torch.einsum("nvcthw,kc->nvthwk", z_enc.double().cpu(), w) + b
+    if s.shape[-1] == 1:
+        return s[..., 0]
+    i = s.abs().argmin(-1, keepdim=True)
+    return s.gather(-1, i)[..., 0]
 
 
 def mask_agreement(anom_a, anom_b, s: torch.Tensor, tie_tol: float):

@@ -18,7 +18,8 @@ def build_model(cfg, sd, train=True):
     from idee_b200.config import default_config
     from idee_b200.models.build import VQ_model
     torch.manual_seed(0)
-    model = VQ_model(default_config(encoder=cfg.encoder, in_channels_dynamic=cfg.in_vars, in_channels=cfg.in_chans))
+    model = VQ_model(default_config(encoder=cfg.encoder, in_channels_dynamic=cfg.in_vars, in_channels=cfg.in_chans,
+                                    codebook_size=cfg.codebook_size))
     missing, unexpected = model.load_state_dict(sd, strict=False)
     assert not unexpected
     assert all(k.endswith("relative_position_index") or k == "vq.mask" for k in missing), missing
