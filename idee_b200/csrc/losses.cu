@@ -156,7 +156,13 @@ anomaly_l1_bwd_kernel(AnomP p, const float* __restrict__ out, const float* __res
             load16(z, p.zq + tok * 16);
             const float sc = scale * (1.f - m);
 #pragma unroll
-            for (int c = 0; c < 16; ++c) { const float d = z[c] - v0[c]; g[c] = d > 0.f ? sc : (d < 0.f ? -sc : 0.f); }
+            for (int c = 0; c < 16; ++c) {
+                // sign(zq - vq0), with differences at rounding level taken as the exact zero they stand for: a token quantised to
+                // code 0 has zq == vq0 mathematically (both are project_out of the all -1 code, LFQ.py:152-181,284), but the two
+                // are evaluated by different kernels (different FMA order) and may differ in the last bit
+                const float d = z[c] - v0[c], tiny = 4e-7f * fmaxf(fabsf(z[c]), fabsf(v0[c]));
+                g[c] = d > tiny ? sc : (d < -tiny ? -sc : 0.f);
+            }
         }
         store16(gzq + tok * 16, g);
     }

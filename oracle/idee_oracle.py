@@ -50,6 +50,11 @@ class OracleConfig:
     lambda_entropy: float = 0.1           # config.py:131
     diversity_gamma: float = 0.1          # config.py:132
     delta_t: int = 8                      # config.py:101
+    # checker-only switch: evaluate the straight-through value as q + (s - s.detach()) (== q exactly) instead of the reference's
+    # s + (q - s).detach() (== q up to one ulp, LFQ.py:226).  The one-ulp residue makes z_q differ from the code of index 0 at
+    # rounding level for tokens quantised to code 0, and Anomaly_L1's |z_q - vq0| then has a +-1 gradient of arbitrary sign there
+    # (losses.py:147-168): a rounding artefact of the reference, not part of its algorithm.  See DESIGN.md section 4.
+    exact_ste: bool = False
 
 
 # ----------------------------------------------------------------------------------------------
@@ -271,7 +276,10 @@ def lfq_forward(sd, z: Tensor, cfg: OracleConfig, training: bool, prefix: str = 
     has_proj = cfg.codebook_dim != kbits                                     # LFQ.py:98
     s = z @ sd[prefix + "project_in.weight"].t() + sd[prefix + "project_in.bias"] if has_proj else z
     q = torch.where(s > 0, torch.ones_like(s), -torch.ones_like(s))         # :221-222 (s==0 -> -1)
-    x = s + (q - s).detach() if training else q                              # :226-230
+    if training:
+        x = q + (s - s.detach()) if cfg.exact_ste else s + (q - s).detach()  # :226-230
+    else:
+        x = q
     bitmask = 2 ** torch.arange(kbits - 1, -1, -1, device=z.device)          # :134
     indices = ((x > 0).int() * bitmask.int()).sum(-1).long()                 # :234
     zero = torch.zeros((), device=z.device)
