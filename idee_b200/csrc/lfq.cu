@@ -4,7 +4,7 @@
 // project_in Linear(16,1), project_out Linear(1,16), codebook {-1,+1}); always fp32 like the reference
 // (LFQ.py:183,199).  Pure HBM-bound streaming kernel: 64 B/token in, 64 B (z_q) + 8 B (int64 index) out.
 //
-// forward (per token): s = w_in.z + b_in ; q = s>0 ? +1 : -1 (tie -> -1 -> index 0) ; x = s + (q - s) (train) | q (eval)
+// forward (per token): s = w_in.z + b_in ; q = s>0 ? +1 : -1 (tie -> -1 -> index 0) ; x = q (the reference's s + (q - s).detach() equals q up to one ulp; the exact value keeps z_q of a code identical for every token)
 //   index = x>0 ; z_q = x*w_out + b_out ; train: p = softmax([-200 s, +200 s]), sums of per-token entropy,
 //   of p (for the codebook entropy) and of (s-q)^2, reduced in double per CTA then by a 1-thread finalize.
 // backward: single pass, g_s = <w_out, g_zq> (straight-through) + g_aux * d(aux)/ds, using the saved mean prob.
@@ -77,7 +77,7 @@ lfq_fwd_kernel(const float* __restrict__ z, const float* __restrict__ w_in, cons
             for (int c = 0; c < C; ++c) s += wi[c] * zr[c];
         }
         const float q = s > 0.f ? 1.f : -1.f;
-        const float x = training ? s + (q - s) : q;
+        const float x = q;     // == s + (q - s) up to one ulp (LFQ.py:226); the straight-through gradient is applied analytically in the backward pass
         if (live) { indices[tok] = x > 0.f ? 1 : 0; if (xq) xq[tok] = x; }
         float r[C];
 #pragma unroll
@@ -162,7 +162,7 @@ lfq_bwd_kernel(const float* __restrict__ z, const float* __restrict__ gzq, const
             for (int c = 0; c < C; ++c) s += wi[c] * zr[c];
         }
         const float q = s > 0.f ? 1.f : -1.f;
-        const float x = s + (q - s);
+        const float x = q;
         float gs = 0.f;
 #pragma unroll
         for (int c = 0; c < C; ++c) { gs += wo[c] * gr[c]; a_wo[c] += x * gr[c]; a_bo[c] += gr[c]; }

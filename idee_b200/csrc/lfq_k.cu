@@ -4,7 +4,7 @@
 //
 // forward, one thread per token: s = W_in z + b_in (K dot products) ; distances d_j = -2 <s, c_j> to the 2^K codes ; the code is
 //   the argmin (ties -> lowest index, i.e. bit i = [s_i > 0]: every s_i == 0 keeps bit 0, LFQ.py:221-222) ; driver index = sum of
-//   bit_i << (K-1-i) ; straight-through x = s + (q - s) (train) | q (eval) ; z_q = W_out x + b_out.
+//   bit_i << (K-1-i) ; straight-through value x = q (the reference's s + (q - s).detach(), exact here) ; z_q = b_out + sum_i W_out[:, i] x_i (FMA chain).
 //   train: p = softmax_j(-inv_temp d_j) ; sums of the per-token entropy, of p (codebook entropy) and of |s - q|^2 in double per
 //   CTA, then a one-thread finalize: aux = lambda_c commit + lambda_e H_tok - gamma H(mean p).
 // backward, one pass: g_s = W_out^T g_zq (straight-through) + g_aux d(aux)/ds from the saved mean probabilities;
@@ -83,7 +83,7 @@ lfqk_fwd_kernel(const float* __restrict__ z, const float* __restrict__ w_in, con
             for (int c = 0; c < C; ++c) a += wi[i * C + c] * zr[c];
             s[i] = a;
             const float q = a > 0.f ? 1.f : -1.f;
-            x[i] = training ? a + (q - a) : q;                                           // LFQ.py:226-230
+            x[i] = q;                    // LFQ.py:226-230: s + (q - s).detach() == q up to one ulp; the STE gradient is analytic (backward)
             idx |= (long long)(x[i] > 0.f ? 1 : 0) << (K - 1 - i);                       // :234
             if (training) acc[1] += (double)((a - q) * (a - q));
         }
@@ -156,7 +156,7 @@ lfqk_bwd_kernel(const float* __restrict__ z, const float* __restrict__ gzq, cons
             for (int c = 0; c < C; ++c) a += wi[i * C + c] * zr[c];
             s[i] = a;
             const float q = a > 0.f ? 1.f : -1.f;
-            x[i] = training ? a + (q - a) : q;
+            x[i] = q;
             float g = 0.f;
 #pragma unroll
             for (int c = 0; c < C; ++c) g += wo[c * K + i] * gq[c];                      // straight-through: d z_q / d x_i

@@ -69,7 +69,15 @@ class LFQ(nn.Module):
         bits = ((indices[..., None].int() & self.mask) != 0).to(self.dtype)
         codes = self.bits_to_codes(bits).flatten(-2)
         if project_out:
-            codes = self.project_out(codes)
+            if self.has_projections and codes.is_cuda:
+                # same arithmetic as the quantiser kernels (b + sum_i W[:, i] c_i as a chain of fused multiply-adds), so the code of an
+                # index is bit-identical to the z_q the kernels emit for it (Anomaly_L1 compares the two, losses.py:147-168)
+                w, acc = self.project_out.weight, self.project_out.bias.expand(*codes.shape[:-1], -1)
+                for i in range(w.shape[1]):
+                    acc = torch.addcmul(acc, codes[..., i:i + 1], w[:, i])
+                codes = acc
+            else:
+                codes = self.project_out(codes)
         if is_img_or_video:
             codes = codes.movedim(-1, 1)
         return codes

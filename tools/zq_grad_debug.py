@@ -5,7 +5,7 @@ from tests.golden_util import load_case, rel_err
 from tests.test_parity_gpu import build_model
 from idee_b200.models.losses import train_step_loss
 from oracle import idee_oracle as O
-cfg, sd, ins, train, ev, grads = load_case("lfq_4_codes")
+cfg, sd, ins, train, ev, grads = load_case(sys.argv[1] if len(sys.argv) > 1 else "lfq_4_codes")
 model = build_model(cfg, sd)
 for which in ("loss_bce", "loss_var", "loss_anomaly", "TOTAL"):
     sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
