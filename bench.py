@@ -238,9 +238,9 @@ def entry_kernels(name):
     emb = "1" if "+embed" in name else "0"
     G = int(m.group(1)) * int(m.group(2)) * int(m.group(3))
     if "fwd" in name:
-        return [f"swin_fwd_tc_kernel<{w},{emb}>", f"swu::swin_fwd_umma_kernel<{w},{emb}>"]
-    return ["swin_mlp_bwd_tc_kernel", f"swin_attn_bwd_tc_kernel<{w},{emb}>", "swu::swin_mlp_bwd_umma_kernel",
-            f"swu::swin_attn_bwd_umma_kernel<{w},{emb}>", f"swin_grad_finalize_kernel<{G}>"]
+        return [f"swin_fwd_tc_kernel<{w},{emb}>", f"swin_fwd_umma_kernel<{w},{emb}>"]
+    return ["swin_mlp_bwd_tc_kernel", f"swin_attn_bwd_tc_kernel<{w},{emb}>", "swin_mlp_bwd_umma_kernel",
+            f"swin_attn_bwd_umma_kernel<{w},{emb}>", f"swin_grad_finalize_kernel<{G}>"]
 
 
 def ncu_traffic(name):

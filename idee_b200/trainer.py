@@ -42,7 +42,7 @@ class Trainer:
         self.exp_avg_sq = torch.zeros_like(self.flat_params)
         # (steps taken, lr) in device memory: the fused Adam reads them there, so one captured CUDA graph serves every step
         self.adam_state = torch.tensor([0.0, float(lr)], device=self.flat_params.device, dtype=torch.float32)
-        self._graph = None
+        self._graph, self._graph2 = None, None
         # Steps never run on the legacy default stream: autograd ties each parameter's gradient accumulator to the stream of its
         # first backward, and an accumulator tied to the default stream (which synchronises with every other stream) invalidates a
         # later CUDA-graph capture.  When called on the default stream the step hops onto this stream and back.
@@ -170,13 +170,25 @@ class Trainer:
             for _ in range(warmup):
                 self.step(*self._static_in)
         torch.cuda.current_stream(dev).wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
         from . import _lib
         before = _lib.Profile.launches
+        multi = self.distributed and self.world > 1
+        graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, stream=side):
-            total, out = self.step(*self._static_in)
+            if multi:
+                # several ranks: the NCCL all-reduce stays OUTSIDE the graphs (one eager collective between two replays), so no
+                # communicator work is ever captured: graph 1 = zero-grad + forward + losses + backward, graph 2 = Adam
+                total, out = self.forward_backward(*self._static_in)
+            else:
+                total, out = self.step(*self._static_in)
+        self._graph2 = None
+        if multi:
+            self._graph2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph2, stream=side):
+                ops.adam_step_state(self.flat_params, self.flat_grads, self.exp_avg, self.exp_avg_sq, self.adam_state, self.betas[0],
+                                    self.betas[1], self.eps, self.weight_decay)
         self.graph_launches = _lib.Profile.launches - before           # kernels of one replay (counted while capturing)
-        self._static_out = (total, out)
+        self._static_out = (total.detach(), out)
         self.flat_params.copy_(saved[0]); self.exp_avg.copy_(saved[1]); self.exp_avg_sq.copy_(saved[2]); self.adam_state.copy_(saved[3])
         self.step_count = saved[4]
         self._graph = graph
@@ -191,6 +203,9 @@ class Trainer:
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
         self._graph.replay()
+        if self._graph2 is not None:
+            self.reduce_gradients()
+            self._graph2.replay()
         self.step_count += 1
         from . import _lib
         _lib.Profile.launches += self.graph_launches

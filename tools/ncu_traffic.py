@@ -19,7 +19,9 @@ UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "n
 
 
 def short_name(full: str) -> str:
-    name = full.split("(")[0].replace("void ", "").replace("<unnamed>::", "").strip()
+    name = re.sub(r"\((int|bool|unsigned|long)\)", "", full)          # the source page prints template arguments with casts
+    name = name.split("(")[0].replace("void ", "").replace("<unnamed>::", "").strip()
+    name = re.sub(r"\b\w+::", "", name)                                  # drop namespaces
     return re.sub(r"\s+", "", name)
 
 
