@@ -45,6 +45,8 @@ _SIGS = {
     "idee_conv3d_dgrad": (c_int, [C.POINTER(ConvDesc)] + [c_vp] * 5 + [c_sz, c_vp]),
     "idee_conv3d_wgrad_workspace_bytes": (c_sz, [C.POINTER(ConvDesc)]),
     "idee_conv3d_wgrad": (c_int, [C.POINTER(ConvDesc)] + [c_vp] * 5 + [c_sz, c_vp]),
+    "idee_conv3d_bwd_workspace_bytes": (c_sz, [C.POINTER(ConvDesc)]),
+    "idee_conv3d_bwd": (c_int, [C.POINTER(ConvDesc)] + [c_vp] * 8 + [c_sz, c_vp]),
     "idee_lfq_workspace_bytes": (c_sz, [c_i64]),
     "idee_lfq_fwd": (c_int, [c_vp] * 9 + [c_i64, c_int, c_int, c_int] + [c_f32] * 4 + [c_vp, c_sz, c_vp, c_vp]),
     "idee_lfq_bwd": (c_int, [c_vp] * 10 + [c_i64] + [c_f32] * 4 + [c_vp, c_sz, c_vp]),
@@ -177,7 +179,7 @@ def set_precision(mode: str) -> None:
 
 
 LAUNCHES = {"embed_ln_fwd": 1, "embed_ln_bwd": 2, "swin_block_fwd": 1, "swin_block_bwd": 3, "conv3d_fwd": 1, "conv3d_dgrad": 1,
-            "conv3d_wgrad": 2, "conv3d_fwd_bf16": 2, "conv3d_dgrad_bf16": 3, "conv3d_wgrad_bf16": 2, "lfq_fwd": 2, "lfq_fwd_eval": 1, "lfq_bwd": 2, "bce_loss_fwd": 4, "anomaly_l1_fwd": 2,
+            "conv3d_wgrad": 2, "conv3d_bwd": 3, "conv3d_bwd_bf16": 5, "conv3d_fwd_bf16": 2, "conv3d_dgrad_bf16": 3, "conv3d_wgrad_bf16": 2, "lfq_fwd": 2, "lfq_fwd_eval": 1, "lfq_bwd": 2, "bce_loss_fwd": 4, "anomaly_l1_fwd": 2,
             "anomaly_l1_bwd": 1, "anomaly_rank1_fwd": 2, "anomaly_rank1_bwd": 1, "rank1_planes_fwd": 1,
             "rank1_planes_bwd": 1, "adam_step": 1, "adam_step_state": 2, "ln_act_res_fwd": 1, "ln_act_res_bwd": 2, "lfqk_fwd": 2, "lfqk_fwd_eval": 1, "lfqk_bwd": 2}
 

@@ -22,6 +22,11 @@ int conv_tc_wgrad_splits(const idee_conv_desc* d);
 int conv_tc_fwd(const idee_conv_desc* d, const void* x, const float* w, const float* b, void* y, void* ws, cudaStream_t st);
 int conv_tc_dgrad(const idee_conv_desc* d, const void* gy, const float* w, const void* relu_src, void* gx, void* ws, cudaStream_t st);
 int conv_tc_wgrad_partials(const idee_conv_desc* d, const void* x, const void* gy, float* partials, cudaStream_t st);
+bool conv_tc_bwd_fused_eligible(const idee_conv_desc* d, const void* x, const void* relu_src);
+int conv_tc_bwd_fused_splits(const idee_conv_desc* d);
+size_t conv_tc_bwd_fused_workspace_bytes(const idee_conv_desc* d);
+int conv_tc_bwd_fused_partials(const idee_conv_desc* d, const void* x, const void* gy, const float* w, const void* relu_src, void* gx,
+                               float* partials, cudaStream_t st);
 
 namespace {
 
@@ -433,4 +438,31 @@ extern "C" int idee_conv3d_wgrad(const idee_conv_desc* d, const void* x, const v
         p.partials, gw, gb, d->Vw, d->Cin, d->Cout, NT, p.n_ic, p.n_oc, p.S, (int64_t)d->Cin * d->Cout * NT, d->Cout);
     IDEE_LAUNCH_CHECK("conv3d_wgrad_reduce");
     return 0;
+}
+
+// Whole backward of one conv in one call.  The 16 -> 1 proj conv on bf16 storage runs ONE kernel for both gradients (conv_tc.cu,
+// proj_bwd_scalar_kernel); every other geometry runs the weight-gradient and data-gradient entry points back to back on the
+// same workspace.
+extern "C" size_t idee_conv3d_bwd_workspace_bytes(const idee_conv_desc* d) {
+    size_t a = idee_conv3d_wgrad_workspace_bytes(d), b = idee_conv3d_dgrad_workspace_bytes(d);
+    if (b > a) a = b;
+    if (d->precision >= 1 && d->proj && d->Cin == 16 && d->Cout == 1) { b = conv_tc_bwd_fused_workspace_bytes(d); if (b > a) a = b; }
+    return a;
+}
+
+extern "C" int idee_conv3d_bwd(const idee_conv_desc* d, const void* x, const void* gy, const float* w, const void* relu_src, void* gx,
+                               float* gw, float* gb, void* workspace, size_t workspace_bytes, void* stream) {
+    if (check_desc(d, "conv3d_bwd")) return 1;
+    IDEE_REQUIRE(workspace_bytes >= idee_conv3d_bwd_workspace_bytes(d), "conv3d_bwd: workspace too small");
+    if (conv_tc_bwd_fused_eligible(d, x, relu_src)) {
+        cudaStream_t st = (cudaStream_t)stream;
+        if (conv_tc_bwd_fused_partials(d, x, gy, w, relu_src, gx, (float*)workspace, st)) return 2;
+        const int64_t nel = (int64_t)d->Cout * d->Cin * 27 + d->Cout;
+        conv_wgrad_reduce_kernel<<<dim3((unsigned)((nel + 255) / 256), d->Vw), 256, 0, st>>>(
+            (const float*)workspace, gw, gb, d->Vw, d->Cin, d->Cout, 27, 1, 1, conv_tc_bwd_fused_splits(d), (int64_t)d->Cin * d->Cout * 27, d->Cout);
+        IDEE_LAUNCH_CHECK("conv3d_bwd reduce");
+        return 0;
+    }
+    if (idee_conv3d_wgrad(d, x, gy, gw, gb, workspace, workspace_bytes, stream)) return 2;
+    return idee_conv3d_dgrad(d, gy, w, relu_src, gx, workspace, workspace_bytes, stream);
 }

@@ -984,6 +984,155 @@ proj_wgrad_scalar_kernel(WP p) {
     if (tid == 0) part[27 * 256] = (red[0][27 * 16] + red[1][27 * 16]) + (red[2][27 * 16] + red[3][27 * 16]);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Data gradient AND weight gradient of the 16 -> 1 proj conv in one pass (proj_wgrad_scalar_kernel + proj_dgrad_scalar_tc_kernel
+// on the same tile): the scalar-gradient halo is fetched once, its im2col G[q][tap] is built once and feeds both GEMMs,
+//   dW[c][tap] += sum_q h[q][c] G[q][tap]   (persistent register accumulators, partials in conv.cu's layout)
+//   gx[q][c]    = sum_tap G[q][tap] W[c][tap] * [h[q][c] > 0]
+// and the ReLU mask of the data gradient is the h tile already in shared memory for the weight gradient (the conv's input IS
+// the ReLU output), so h is read from HBM once for the whole backward of this conv.  The output channels of the data-gradient
+// MMAs are permuted (column n of n-tile nt <-> channel 4 (n / 2) + 2 nt + n % 2) so that a thread owns 4 consecutive channels of a
+// pixel: one 8-byte (bf16) or 16-byte (fp32) store and one 8-byte mask load per pixel row instead of two.
+// ------------------------------------------------------------------------------------------------------------------
+template <bool OUT16, bool MASK>
+__global__ void __launch_bounds__(128)
+proj_bwd_scalar_kernel(WP p, const float* __restrict__ w, void* __restrict__ gx_) {
+    constexpr int CPA = 24, CPG = 40, NHALO = 3 * HH * HW_;
+    __shared__ __align__(16) __nv_bfloat16 tileA[2][TH * TW * CPA];    // h tile, double buffered (cp.async)
+    __shared__ __align__(16) float gsh[2][NHALO];                      // scalar-gradient halo, double buffered
+    __shared__ __align__(16) __nv_bfloat16 tileG[TH * TW * CPG];       // im2col of the scalar plane, 32 columns (27 taps + 5 zeros)
+    __shared__ float red[4][27 * 16 + 1];
+    const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(p.in);
+    const float* gout = reinterpret_cast<const float*>(p.gout);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int s = blockIdx.x, wset = blockIdx.y;
+    float acc[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+    float gsum = 0.f;
+    // data-gradient B fragments: B[k = tap][n] = w[channel(nt, n)][tap]
+    uint32_t bf[2][2][2];
+    {
+        const float* wv = w + (int64_t)wset * 16 * 27;
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const int n = lane / 4, cch = 4 * (n / 2) + 2 * nt + (n & 1), t0 = kk * 16 + 2 * (lane % 4);
+                auto wt = [&](int tap) { return tap < 27 ? __ldg(wv + cch * 27 + tap) : 0.f; };
+                bf[kk][nt][0] = pack_bf16(wt(t0), wt(t0 + 1));
+                bf[kk][nt][1] = pack_bf16(wt(t0 + 8), wt(t0 + 9));
+            }
+    }
+    const int64_t t_begin = p.tiles_per_set * s / p.S, t_end = p.tiles_per_set * (s + 1) / p.S;
+    const int a_pix = (lane & 7) + (lane >> 4) * 8, a_coff = ((lane >> 3) & 1) * 8;     // A (trans) lane address, weight gradient
+    const int b_pix = (lane & 7) + ((lane >> 3) & 1) * 8, b_coff = (lane >> 4) * 8;     // B (trans) / data-gradient A lane address
+    const int pr = tid / TW, pc = tid % TW;
+    struct Tile { int n, v, t, h0, w0; };
+    auto decode = [&](int64_t tile64) {
+        Tile c;
+        uint32_t q, r;
+        p.fd_to.divmod((uint32_t)tile64, q, r); c.t = (int)r;
+        p.fd_tw.divmod(q, q, r); c.w0 = (int)r * TW;
+        p.fd_th.divmod(q, q, r); c.h0 = (int)r * TH;
+        if (p.Vw == 1) { p.fd_ipn.divmod(q, q, r); c.n = (int)q; c.v = (int)r; }
+        else { c.n = (int)q; c.v = wset; }
+        return c;
+    };
+    auto issue = [&](const Tile& c, int buf) {
+        const __nv_bfloat16* in_img = in + c.n * p.in_sn + c.v * p.in_sv;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int e = tid + i * 128, pix = e >> 1, ch = e & 1;
+            const int h = c.h0 + pix / TW, w_ = c.w0 + pix % TW;
+            const bool ok = h < p.Hi && w_ < p.Wi;
+            const __nv_bfloat16* src = ok ? in_img + (int64_t)(c.t * (int)p.in_st + h * (int)p.in_sh + w_ * (int)p.in_sw) + ch * 8 : in;
+            cp_async16_u32(smem_u32(&tileA[buf][pix * CPA + ch * 8]), src, ok ? 16 : 0);
+        }
+        const float* g_img = gout + c.n * p.go_sn + c.v * p.go_sv;
+        for (int e = tid; e < NHALO; e += 128) {
+            const int a = e / (HH * HW_), rem = e - a * (HH * HW_), b = rem / HW_, cc = rem - b * HW_;
+            const int pt = c.t - 1 + a, ph = c.h0 - 1 + b, pw = c.w0 - 1 + cc;
+            const bool ok = (unsigned)pt < (unsigned)p.To && (unsigned)ph < (unsigned)p.Ho && (unsigned)pw < (unsigned)p.Wo;
+            const float* src = ok ? g_img + (int64_t)(pt * (int)p.go_st + ph * (int)p.go_sh + pw * (int)p.go_sw) : gout;
+            cp_async4_u32(smem_u32(&gsh[buf][e]), src, ok ? 4 : 0);
+        }
+        cp_async_commit();
+    };
+    Tile nxt{};
+    if (t_begin < t_end) { nxt = decode(t_begin); issue(nxt, 0); }
+    int buf = 0;
+    for (int64_t tile = t_begin; tile < t_end; ++tile, buf ^= 1) {
+        const Tile c = nxt;
+        cp_async_wait<0>();
+        __syncthreads();                                   // tile data landed; previous tile's MMAs are done with tileG
+        {
+            const bool in_img = c.h0 + pr < p.Ho && c.w0 + pc < p.Wo;
+            gcol_row_tile(gsh[buf], tileG + tid * CPG, c.t, c.h0, c.w0, pr, pc, p.To, p.Ho, p.Wo);
+            if (in_img) gsum += gsh[buf][(1 * HH + pr + 1) * HW_ + pc + 1];
+        }
+        __syncthreads();
+        if (tile + 1 < t_end) { nxt = decode(tile + 1); issue(nxt, buf ^ 1); }
+        // gx is a contiguous [N,V,T,H,W,16] tensor (host-checked): 32-bit offsets inside the (image, t) slice
+        const int64_t img_off = (((int64_t)c.n * p.V + c.v) * p.To + c.t) * (int64_t)p.Ho * p.Wo * 16;
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+            const int ks = warp * 2 + kk;                  // tile row of 16 pixels
+            uint32_t a[4], b0[4], b1[4];
+            ldsm_x4_t(a, &tileA[buf][(ks * TW + a_pix) * CPA + a_coff]);
+            ldsm_x4_t(b0, tileG + (ks * TW + b_pix) * CPG + b_coff);
+            ldsm_x4_t(b1, tileG + (ks * TW + b_pix) * CPG + 16 + b_coff);
+            // ---- weight gradient: D[16 ch x 32 taps] += h^T G ----
+            mma_bf16(acc[0], a, b0[0], b0[1]); mma_bf16(acc[1], a, b0[2], b0[3]);
+            mma_bf16(acc[2], a, b1[0], b1[1]); mma_bf16(acc[3], a, b1[2], b1[3]);
+            // ---- data gradient: D[16 pixels x 16 ch] = G W^T ----
+            float dg[2][4];
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) dg[nt][0] = dg[nt][1] = dg[nt][2] = dg[nt][3] = 0.f;
+#pragma unroll
+            for (int k2 = 0; k2 < 2; ++k2) {
+                uint32_t ga[4];
+                ldsm_x4(ga, tileG + (ks * TW + b_pix) * CPG + k2 * 16 + b_coff);
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) mma_bf16(dg[nt], ga, bf[k2][nt][0], bf[k2][nt][1]);
+            }
+            const int hq = c.h0 + ks;
+            if (hq >= p.Ho) continue;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int pxl = lane / 4 + half * 8, wq = c.w0 + pxl;
+                if (wq >= p.Wo) continue;
+                float v0 = dg[0][half * 2], v1 = dg[0][half * 2 + 1], v2 = dg[1][half * 2], v3 = dg[1][half * 2 + 1];
+                if (MASK) {
+                    const uint2 u = *reinterpret_cast<const uint2*>(&tileA[buf][(ks * TW + pxl) * CPA + (lane % 4) * 4]);
+                    if (!(__uint_as_float(u.x << 16) > 0.f)) v0 = 0.f;
+                    if (!(__uint_as_float(u.x & 0xFFFF0000u) > 0.f)) v1 = 0.f;
+                    if (!(__uint_as_float(u.y << 16) > 0.f)) v2 = 0.f;
+                    if (!(__uint_as_float(u.y & 0xFFFF0000u) > 0.f)) v3 = 0.f;
+                }
+                const int64_t o = img_off + (int64_t)((hq * p.Wo + wq) * 16 + (lane % 4) * 4);
+                if (OUT16) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(gx_) + o) = make_uint2(pack_bf16(v0, v1), pack_bf16(v2, v3));
+                else *reinterpret_cast<float4*>(reinterpret_cast<float*>(gx_) + o) = make_float4(v0, v1, v2, v3);
+            }
+        }
+    }
+    // ---- CTA reduction of the weight-gradient partials (fixed order) ----
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int tap = nt * 8 + (lane % 4) * 2 + (q & 1), ch = lane / 4 + (q >> 1) * 8;
+            if (tap < 27) red[warp][tap * 16 + ch] = acc[nt][q];
+        }
+    gsum = warp_sum(gsum);
+    if (lane == 0) red[warp][27 * 16] = gsum;
+    __syncthreads();
+    constexpr int PS = 27 * 256 + 16;
+    float* part = p.partials + ((int64_t)wset * p.S + s) * PS;
+    for (int e = tid; e < 27 * 16; e += 128) part[(e / 16) * 256 + (e % 16) * 16] = (red[0][e] + red[1][e]) + (red[2][e] + red[3][e]);
+    if (tid == 0) part[27 * 256] = (red[0][27 * 16] + red[1][27 * 16]) + (red[2][27 * 16] + red[3][27 * 16]);
+}
+
 // NT taps, NTL n-tiles (8 output channels each) per CTA; cin chunk 16.  A16 / G16: the input / output-gradient tensors hold
 // bf16: their tiles are then copied by cp.async straight into the (double-buffered) MMA layout, no staging and no convert.
 template <int NT, int NTL, bool A16, bool G16>
@@ -1588,5 +1737,52 @@ int conv_tc_wgrad_partials(const idee_conv_desc* d, const void* x, const void* g
     else IDEE_WGRAD_LAUNCH(18, 1, false, false);
 #undef IDEE_WGRAD_LAUNCH
     IDEE_LAUNCH_CHECK("conv3d_wgrad(bf16)");
+    return 0;
+}
+
+// ---- fused backward of the 16 -> 1 proj conv (proj_bwd_scalar_kernel) ----
+bool conv_tc_bwd_fused_eligible(const idee_conv_desc* d, const void* x, const void* relu_src) {
+    return d->precision >= 1 && d->proj && d->Cin == 16 && d->Cout == 1 && d->x_dtype == 1 && d->y_dtype == 0 && d->x_sw == 16 &&
+           d->y_sw == 1 && d->x_sh == (int64_t)d->Wi * 16 && d->x_st == (int64_t)d->Hi * d->Wi * 16 &&
+           d->x_sv == (int64_t)d->Ti * d->Hi * d->Wi * 16 && d->x_sn == d->x_sv * d->V && (relu_src == nullptr || relu_src == x);
+}
+int conv_tc_bwd_fused_splits(const idee_conv_desc* d) {
+    int S = (idee_num_sms() * 6 + d->Vw - 1) / d->Vw;        // 34 KB of shared memory per CTA: six CTAs per SM
+    if (S < 1) S = 1;
+    if (S > 1024) S = 1024;
+    return S;
+}
+size_t conv_tc_bwd_fused_workspace_bytes(const idee_conv_desc* d) {
+    return sizeof(float) * (size_t)d->Vw * conv_tc_bwd_fused_splits(d) * (27 * 256 + 16);
+}
+int conv_tc_bwd_fused_partials(const idee_conv_desc* d, const void* x, const void* gy, const float* w, const void* relu_src, void* gx,
+                               float* partials, cudaStream_t st) {
+    WP p{};
+    p.in = x; p.gout = gy; p.partials = partials;
+    p.a16 = 1; p.g16 = 0;
+    p.N = d->N; p.V = d->V; p.Vw = d->Vw;
+    p.Ti = d->Ti; p.Hi = d->Hi; p.Wi = d->Wi; p.To = d->To; p.Ho = d->Ho; p.Wo = d->Wo;
+    p.in_sn = d->x_sn; p.in_sv = d->x_sv; p.in_st = d->x_st; p.in_sh = d->x_sh; p.in_sw = d->x_sw; p.in_sg = d->x_sg; p.in_cpg = d->in_cpg;
+    p.go_sn = d->y_sn; p.go_sv = d->y_sv; p.go_st = d->y_st; p.go_sh = d->y_sh; p.go_sw = d->y_sw;
+    p.FCO = d->Cout; p.proj = d->proj;
+    p.n_ic = 1; p.n_oc16 = 1; p.S = conv_tc_bwd_fused_splits(d);
+    p.tiles_h = (d->Ho + TH - 1) / TH; p.tiles_w = (d->Wo + TW - 1) / TW;
+    p.tiles_per_set = (int64_t)d->N * (d->Vw == 1 ? d->V : 1) * d->To * p.tiles_h * p.tiles_w;
+    p.fd_to = make_fastdiv(d->To); p.fd_tw = make_fastdiv(p.tiles_w); p.fd_th = make_fastdiv(p.tiles_h);
+    p.fd_ipn = make_fastdiv(d->Vw == 1 ? d->V : 1);
+    IDEE_REQUIRE(p.tiles_per_set < (1ll << 31), "conv3d_bwd(proj 16->1): too many tiles for 32-bit tile indices");
+    IDEE_REQUIRE((int64_t)(d->Ti + 3) * d->x_st + (int64_t)(d->Hi + HH) * d->x_sh + (int64_t)(d->Wi + HW_) * d->x_sw < (1ll << 31) &&
+                 (int64_t)(d->To + 1) * d->y_st + (int64_t)(d->Ho + TH) * d->y_sh + (int64_t)(d->Wo + TW) * d->y_sw < (1ll << 31),
+                 "conv3d_bwd(proj 16->1): tensor too large for 32-bit image-relative offsets");
+    // every partial entry the reduce stage reads ((tap, c, o = 0) and the bias slot) is written by every CTA: no clearing pass
+    const dim3 grid(p.S, d->Vw);
+    if (d->gx_dtype) {
+        if (relu_src) proj_bwd_scalar_kernel<true, true><<<grid, 128, 0, st>>>(p, w, gx);
+        else proj_bwd_scalar_kernel<true, false><<<grid, 128, 0, st>>>(p, w, gx);
+    } else {
+        if (relu_src) proj_bwd_scalar_kernel<false, true><<<grid, 128, 0, st>>>(p, w, gx);
+        else proj_bwd_scalar_kernel<false, false><<<grid, 128, 0, st>>>(p, w, gx);
+    }
+    IDEE_LAUNCH_CHECK("conv3d_bwd(proj 16->1)");
     return 0;
 }

@@ -492,20 +492,22 @@ class Conv3dCL(torch.autograd.Function):
         gw = gw_dst if gw_dst is not None and gw_dst.shape == w.shape else torch.empty_like(w)
         gb = gb_dst if gb_dst is not None and gb_dst.shape == (w.shape[0], w.shape[1]) else \
             torch.empty(w.shape[0], w.shape[1], device=w.device, dtype=torch.float32)
-        nws = lib.idee_conv3d_wgrad_workspace_bytes(C.byref(d))
-        ws = L.workspace(nws, x.device)
-        L.run("conv3d_wgrad_bf16" if d.precision else "conv3d_wgrad", lib.idee_conv3d_wgrad, C.byref(d), x.data_ptr(), gy.data_ptr(), gw.data_ptr(), gb.data_ptr(), ws.data_ptr(), nws,
-                                      L.stream(), tag=_conv_tag(d))
-        gx = None
         if ctx.needs_input_grad[0]:
+            # both gradients through one entry point (one fused kernel for the 16 -> 1 proj conv, two launches otherwise)
             gx = torch.empty_strided(x.shape, x.stride(), device=x.device, dtype=ctx.gx_dtype) if _dense(x) else None
             if gx is None:
-                raise RuntimeError("conv3d_dgrad: input must be a dense channel-last tensor")
-            nws = lib.idee_conv3d_dgrad_workspace_bytes(C.byref(d))
-            ws = L.workspace(nws, x.device)
+                raise RuntimeError("conv3d_bwd: input must be a dense channel-last tensor")
             relu_src = x.data_ptr() if ctx.input_is_relu else None       # dL/d(pre-activation) = dL/dx * (x > 0), fused
-            L.run("conv3d_dgrad_bf16" if d.precision else "conv3d_dgrad", lib.idee_conv3d_dgrad, C.byref(d), gy.data_ptr(),
-                  w.data_ptr(), relu_src, gx.data_ptr(), ws.data_ptr(), nws, L.stream(), tag=_conv_tag(d))
+            nws = lib.idee_conv3d_bwd_workspace_bytes(C.byref(d))
+            ws = L.workspace(nws, x.device)
+            L.run("conv3d_bwd_bf16" if d.precision else "conv3d_bwd", lib.idee_conv3d_bwd, C.byref(d), x.data_ptr(), gy.data_ptr(),
+                  w.data_ptr(), relu_src, gx.data_ptr(), gw.data_ptr(), gb.data_ptr(), ws.data_ptr(), nws, L.stream(), tag=_conv_tag(d))
+        else:
+            gx = None
+            nws = lib.idee_conv3d_wgrad_workspace_bytes(C.byref(d))
+            ws = L.workspace(nws, x.device)
+            L.run("conv3d_wgrad_bf16" if d.precision else "conv3d_wgrad", lib.idee_conv3d_wgrad, C.byref(d), x.data_ptr(), gy.data_ptr(),
+                  gw.data_ptr(), gb.data_ptr(), ws.data_ptr(), nws, L.stream(), tag=_conv_tag(d))
         return gx, gw, gb, None, None, None, None, None, None, None, None
 
 

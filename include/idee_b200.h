@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define IDEE_B200_VERSION 204
+#define IDEE_B200_VERSION 205
 
 const char* idee_last_error(void);
 int idee_version(void);
@@ -129,6 +129,12 @@ int idee_conv3d_dgrad(const idee_conv_desc* d, const void* gy, const float* w, c
 size_t idee_conv3d_wgrad_workspace_bytes(const idee_conv_desc* d);
 int idee_conv3d_wgrad(const idee_conv_desc* d, const void* x, const void* gy, float* gw, float* gb,
                       void* workspace, size_t workspace_bytes, void* stream);
+/* Both gradients of one conv (what autograd asks of torch.nn.Conv3d.backward, Swin_3D.py:586-592 / classifier/CNN_3D.py:83-85):
+ * same arguments as the two calls above.  The 16 -> 1 proj conv on bf16 storage (x_dtype 1, relu_src == x or NULL) runs ONE
+ * kernel that reads x and gy once for both results; other geometries run idee_conv3d_wgrad then idee_conv3d_dgrad. */
+size_t idee_conv3d_bwd_workspace_bytes(const idee_conv_desc* d);
+int idee_conv3d_bwd(const idee_conv_desc* d, const void* x, const void* gy, const float* w, const void* relu_src, void* gx,
+                    float* gw, float* gb, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- LFQ quantiser, dim=16, codebook_size=2                                      models/codebook/LFQ.py:183-307 ----
  * z,zq,gz,gzq: [ntok][16]; indices: int64 [ntok]; xq (optional, may be NULL): float [ntok], the quantised scalar x (+-1) with
