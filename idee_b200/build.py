@@ -20,7 +20,7 @@ LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "libidee_b200.so")
 INCLUDE = os.path.join(ROOT, "include")
 
-SOURCES = ["api.cu", "embed.cu", "swin_block.cu", "conv.cu", "conv_tc.cu", "conv16_umma.cu", "conv96_umma.cu", "lfq.cu", "lfq_k.cu", "losses.cu", "cnn_enc.cu"]
+SOURCES = ["api.cu", "embed.cu", "swin_block.cu", "conv.cu", "conv_tc.cu", "conv16_umma.cu", "conv96_umma.cu", "conv96_wgrad_umma.cu", "lfq.cu", "lfq_k.cu", "losses.cu", "cnn_enc.cu"]
 BASE_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr"]
 NVCC_FLAGS = BASE_FLAGS + ["-I", INCLUDE, "-I", CSRC]

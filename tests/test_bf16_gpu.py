@@ -123,7 +123,8 @@ def test_tcgen05_classifier_conv_matches_mma_sync_and_oracle(dims):
     b = torch.randn(1, 96)
     g = torch.randn(N, 1, To, H, W, 96)
     xr = x.clone().requires_grad_(True)
-    want = F.conv3d(xr[:, 0].permute(0, 4, 1, 2, 3), w[0], b[0], stride=(2, 1, 1), padding=(0, 1, 1)).permute(0, 2, 3, 4, 1).unsqueeze(1)
+    wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    want = F.conv3d(xr[:, 0].permute(0, 4, 1, 2, 3), wr[0], br[0], stride=(2, 1, 1), padding=(0, 1, 1)).permute(0, 2, 3, 4, 1).unsqueeze(1)
     (want * g).sum().backward()
     want_gx = xr.grad * (x > 0)                                    # input_is_relu: the data gradient carries the ReLU mask
     old96 = _lib.UMMA96
@@ -132,16 +133,19 @@ def test_tcgen05_classifier_conv_matches_mma_sync_and_oracle(dims):
         for on in (False, True):
             _lib.set_umma96(on)
             xc = x.cuda().requires_grad_(True)
-            y = ops.conv3d_cl(xc, w.cuda(), b.cuda(), False, False, input_is_relu=True)
+            wc, bc = w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+            y = ops.conv3d_cl(xc, wc, bc, False, False, input_is_relu=True)
             (y * g.cuda()).sum().backward()
-            outs[on] = (y.detach().cpu(), xc.grad.cpu())
+            outs[on] = (y.detach().cpu(), xc.grad.cpu(), wc.grad.cpu(), bc.grad.cpu())
     finally:
         _lib.set_umma96(old96)
     for on in (False, True):
-        assert rel_err(outs[on][0], want) < TOL
+        assert rel_err(outs[on][0], want.detach()) < TOL
         assert rel_err(outs[on][1], want_gx) < TOL
-    assert rel_err(outs[True][0], outs[False][0]) < 2e-3          # same bf16 operands, at most a different accumulation order
-    assert rel_err(outs[True][1], outs[False][1]) < 2e-3
+        assert rel_err(outs[on][2], wr.grad) < TOL                 # weight gradient (tcgen05: TMEM accumulation over pixels)
+        assert rel_err(outs[on][3], br.grad) < TOL
+    for i in range(4):                                             # same bf16 operands, at most a different accumulation order
+        assert rel_err(outs[True][i], outs[False][i]) < 2e-3
 
 
 @pytest.mark.parametrize("shape", [(2, 3, 4, 21, 37), (1, 6, 8, 40, 48)])
