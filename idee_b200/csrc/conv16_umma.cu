@@ -32,7 +32,10 @@ constexpr int TMEM_COLS = 32;
 #define IDEE_U16_NBUF 2
 #endif
 constexpr int NBUF = IDEE_U16_NBUF;             // halo buffers / accumulators per CTA (1: overlap comes from co-resident CTAs)
-enum { U16_FWD = 0, U16_DGRAD_PAD = 1 };
+// U16_DGRAD_T: data gradient on the domain [T][H+2][W+2] (time unpadded: the replicate adjoint along t is 9 extra MMAs on the
+// first / last slice, see the kernel; h / w padded).  Pixels that need no folding along h / w are final: ReLU mask, bf16, straight
+// into gx.  Only the two-pixel ring around the image goes to the fp32 padded buffer for fold_ring_kernel (conv_tc.cu).
+enum { U16_FWD = 0, U16_DGRAD_PAD = 1, U16_DGRAD_T = 2 };
 
 
 struct UP16 {
@@ -42,6 +45,8 @@ struct UP16 {
     int in_st, in_sh, in_sw, out_st, out_sh, out_sw;
     uint32_t total_tiles;
     FastDiv fd_tw, fd_th, fd_to, fd_v;
+    __nv_bfloat16* gx; const __nv_bfloat16* relu_src;      // U16_DGRAD_T: contiguous [N,V,T,H,W,16] gradient / ReLU source (or null)
+    int H, W;                                              // U16_DGRAD_T: unpadded image extent (Ho = H + 2, Wo = W + 2)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -106,7 +111,7 @@ __global__ void prep_umma16_weights_kernel(const float* __restrict__ w, __nv_bfl
 template <int MODE, bool OUT16>
 __global__ void __launch_bounds__(NTH)
 conv16_umma_kernel(UP16 p) {
-    constexpr int OT = MODE == U16_FWD ? -1 : -2, OHW = OT;           // halo origin relative to the tile
+    constexpr int OT = MODE == U16_DGRAD_PAD ? -2 : -1, OHW = MODE == U16_FWD ? -1 : -2;   // halo origin relative to the tile
     constexpr int TOTAL = NPX * 2, NEL = (TOTAL + NTH - 1) / NTH;      // 16-byte elements: (pixel, chunk), chunk fastest
     constexpr int PLANE = HR * HC * 2;                                 // elements per input time slice
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -199,6 +204,29 @@ conv16_umma_kernel(UP16 p) {
         float v[16];
         tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * 16, v);
         const int r = warp * 4 + (lane >> 3), cc = lane & 7;
+        if (MODE == U16_DGRAD_T) {
+            const int h = c.h0 + r - 1, w = c.w0 + cc - 1;             // unpadded pixel of this padded position
+            if (h >= 1 && h <= p.H - 2 && w >= 1 && w <= p.W - 2) {    // no folding along h / w: final value
+                const int64_t o = ((((int64_t)c.n * p.V + c.v) * p.To + c.t) * p.H + h) * (int64_t)p.W * 16 + w * 16;
+                if (p.relu_src) {
+                    uint32_t m[8];
+                    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(m[0]), "=r"(m[1]), "=r"(m[2]), "=r"(m[3]),
+                                 "=r"(m[4]), "=r"(m[5]), "=r"(m[6]), "=r"(m[7]) : "l"(p.relu_src + o));
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (!(__uint_as_float(m[i] << 16) > 0.f)) v[2 * i] = 0.f;
+                        if (!(__uint_as_float(m[i] & 0xFFFF0000u) > 0.f)) v[2 * i + 1] = 0.f;
+                    }
+                }
+                const uint32_t pk[8] = {pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]),
+                                        pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15])};
+                st8u(p.gx + o, pk);
+            } else if (c.h0 + r < p.Ho && c.w0 + cc < p.Wo) {          // ring: fp32 into the padded buffer, folded later
+                const int64_t o = c.n * p.out_sn + c.v * p.out_sv + (int64_t)(c.t * p.out_st + (c.h0 + r) * p.out_sh + (c.w0 + cc) * p.out_sw);
+                float* dst = reinterpret_cast<float*>(p.out) + o;
+                st8f(dst, v); st8f(dst + 8, v + 8);
+            }
+        } else
         if (c.h0 + r < p.Ho && c.w0 + cc < p.Wo) {
             const int64_t o = c.n * p.out_sn + c.v * p.out_sv + (int64_t)(c.t * p.out_st + (c.h0 + r) * p.out_sh + (c.w0 + cc) * p.out_sw);
 #pragma unroll
@@ -257,6 +285,19 @@ conv16_umma_kernel(UP16 p) {
                 const int kt = j / 9, kh = (j / 3) % 3, kw = j % 3;
                 umma_bf16(dcol, adesc0 + (uint64_t)((kt * HR + kh) * HC + kw), bdesc0 + (uint64_t)(j * (B_TAP / 16)), j > 0 ? 1u : 0u);
             }
+            if (MODE == U16_DGRAD_T) {
+                // adjoint of the replicate padding along t: slice 0 also receives gy[0] W[kt = 0] (the clamped read of x[-1]) and
+                // slice T-1 gy[T-1] W[kt = 2]: the centre plane of the halo against the weight tiles of the far / near time tap
+                const bool lo = cur.t == 0, hi = cur.t == p.To - 1;
+                if (lo || hi) {
+#pragma unroll
+                    for (int j9 = 0; j9 < 9; ++j9) {
+                        const uint64_t ad = adesc0 + (uint64_t)((HR + j9 / 3) * HC + j9 % 3);
+                        if (lo) umma_bf16(dcol, ad, bdesc0 + (uint64_t)((18 + j9) * (B_TAP / 16)), 1u);
+                        if (hi) umma_bf16(dcol, ad, bdesc0 + (uint64_t)(j9 * (B_TAP / 16)), 1u);
+                    }
+                }
+            }
             umma_commit(smem_u32(&bars[buf]));
         }
         if (NBUF == 2) {
@@ -288,16 +329,18 @@ using namespace conv16u;
 
 size_t conv16_umma_workspace_bytes(int Vw) { return sizeof(__nv_bfloat16) * (size_t)Vw * NTAP * 256; }
 
-// mode 0: y = conv(x) (+bias, ReLU);  mode 1: padded-domain data gradient (out = [N,V,T+2,H+2,W+2,16] fp32, no bias)
+// mode 0: y = conv(x) (+bias, ReLU);  mode 1: padded-domain data gradient (out = [N,V,T+2,H+2,W+2,16] fp32, no bias);
+// mode 2: data gradient with final pixels written to gx (bf16, optional ReLU mask) and the h / w ring to out = [N,V,T,H+2,W+2,16] fp32
 int conv16_umma_run(int mode, int out16, const void* in, const float* w, const float* bias, void* out, void* ws, int N, int V, int Vw,
                     int Ti, int Hi, int Wi, int To, int Ho, int Wo, const int64_t* in_s, const int64_t* out_s, int relu,
-                    cudaStream_t st) {
+                    cudaStream_t st, void* gx, const void* relu_src) {
     __nv_bfloat16* wB = (__nv_bfloat16*)ws;
-    prep_umma16_weights_kernel<<<(Vw * NTAP * 256 + 255) / 256, 256, 0, st>>>(w, wB, Vw, mode == U16_DGRAD_PAD);
+    prep_umma16_weights_kernel<<<(Vw * NTAP * 256 + 255) / 256, 256, 0, st>>>(w, wB, Vw, mode != U16_FWD);
     IDEE_LAUNCH_CHECK("conv3d(umma16) prep");
     UP16 p{};
     p.in = (const __nv_bfloat16*)in; p.out = out; p.bias = bias; p.wB = wB;
     p.V = V; p.Vw = Vw; p.Ti = Ti; p.Hi = Hi; p.Wi = Wi; p.To = To; p.Ho = Ho; p.Wo = Wo; p.relu = relu;
+    p.gx = (__nv_bfloat16*)gx; p.relu_src = (const __nv_bfloat16*)relu_src; p.H = Ho - 2; p.W = Wo - 2;
     p.in_sn = in_s[0]; p.in_sv = in_s[1]; p.in_st = (int)in_s[2]; p.in_sh = (int)in_s[3]; p.in_sw = (int)in_s[4];
     p.out_sn = out_s[0]; p.out_sv = out_s[1]; p.out_st = (int)out_s[2]; p.out_sh = (int)out_s[3]; p.out_sw = (int)out_s[4];
     IDEE_REQUIRE(in_s[4] == 16 && out_s[4] == 16, "conv3d(umma16): pixels must hold 16 contiguous channels");
@@ -333,6 +376,7 @@ int conv16_umma_run(int mode, int out16, const void* in, const float* w, const f
         kern<<<(unsigned)grid, NTH, smem, st>>>(p);                                                                          \
     } while (0)
     if (mode == U16_FWD) { if (out16) IDEE_U16_LAUNCH(U16_FWD, true); else IDEE_U16_LAUNCH(U16_FWD, false); }
+    else if (mode == U16_DGRAD_T) IDEE_U16_LAUNCH(U16_DGRAD_T, false);
     else IDEE_U16_LAUNCH(U16_DGRAD_PAD, false);
 #undef IDEE_U16_LAUNCH
     IDEE_LAUNCH_CHECK("conv3d(umma16)");

@@ -623,6 +623,44 @@ fold_pad_kernel(const float* __restrict__ gpad, void* __restrict__ gin_, const v
     }
 }
 
+// Border pixels only (h in {0, H-1} or w in {0, W-1}) of the [T][H+2][W+2]-domain data gradient of conv16_umma.cu (mode 2: the t
+// axis is already folded inside the GEMM, interior pixels are already final in gin): gin[r] = sum of the ring positions that clamp
+// to r along h / w, optional ReLU mask, bf16.  One CTA per (image, t) plane walks its 2 W + 2 (H - 2) border pixels.
+__global__ void __launch_bounds__(256)
+fold_ring_kernel(const float* __restrict__ gpad, __nv_bfloat16* __restrict__ gin, const __nv_bfloat16* __restrict__ relu_src,
+                 int planes, int H, int W) {
+    const int Wp = W + 2, Hp = H + 2;
+    const int nborder = 2 * W + 2 * max(H - 2, 0);
+    for (int plane = blockIdx.x; plane < planes; plane += gridDim.x) {
+        const float* pp = gpad + (int64_t)plane * Hp * Wp * 16;
+        const int64_t po = (int64_t)plane * H * W * 16;
+        for (int e = threadIdx.x; e < nborder * 4; e += 256) {
+            const int i = e >> 2, c4 = e & 3;
+            int h, w;
+            if (i < W) { h = 0; w = i; }
+            else if (i < 2 * W) { h = H - 1; w = i - W; }
+            else { const int k = i - 2 * W; h = 1 + (k >> 1); w = (k & 1) ? W - 1 : 0; }
+            const int h0 = h == 0 ? 0 : h + 1, h1 = h == H - 1 ? H + 1 : h + 1;
+            const int w0 = w == 0 ? 0 : w + 1, w1 = w == W - 1 ? W + 1 : w + 1;
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int hh = h0; hh <= h1; ++hh)
+                for (int ww = w0; ww <= w1; ++ww) {
+                    const float4 g = ldg4(pp + ((int64_t)hh * Wp + ww) * 16 + c4 * 4);
+                    s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
+                }
+            const int64_t o = po + ((int64_t)h * W + w) * 16 + c4 * 4;
+            if (relu_src) {
+                const uint2 u = __ldg(reinterpret_cast<const uint2*>(relu_src + o));
+                if (!(__uint_as_float(u.x << 16) > 0.f)) s.x = 0.f;
+                if (!(__uint_as_float(u.x & 0xFFFF0000u) > 0.f)) s.y = 0.f;
+                if (!(__uint_as_float(u.y << 16) > 0.f)) s.z = 0.f;
+                if (!(__uint_as_float(u.y & 0xFFFF0000u) > 0.f)) s.w = 0.f;
+            }
+            *reinterpret_cast<uint2*>(gin + o) = make_uint2(pack_bf16(s.x, s.y), pack_bf16(s.z, s.w));
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // weight gradient
 // ------------------------------------------------------------------------------------------------------------------
@@ -1510,7 +1548,7 @@ int conv96_umma_run(const idee_conv_desc* d, int dgrad, const float* in, const f
 size_t conv16_umma_workspace_bytes(int Vw);
 int conv16_umma_run(int mode, int out16, const void* in, const float* w, const float* bias, void* out, void* ws, int N, int V, int Vw,
                     int Ti, int Hi, int Wi, int To, int Ho, int Wo, const int64_t* in_s, const int64_t* out_s, int relu,
-                    cudaStream_t st);
+                    cudaStream_t st, void* gx = nullptr, const void* relu_src = nullptr);
 static bool umma16_fwd_eligible(const idee_conv_desc* d) {
     return d->umma16 && d->precision >= 1 && d->proj && d->Cin == 16 && d->Cout == 16 && d->x_dtype == 1 && d->x_sw == 16 && d->y_sw == 16;
 }
@@ -1647,6 +1685,20 @@ int conv_tc_dgrad(const idee_conv_desc* d, const void* gy, const float* w, const
     p.out_sw = 16; p.out_sh = (int64_t)Wp * 16; p.out_st = (int64_t)Hp * Wp * 16; p.out_sv = (int64_t)Tp * Hp * Wp * 16;
     p.out_sn = p.out_sv * d->V; p.out_sg = 0; p.out_cpg = 1;
     p.tiles_w = (p.Wo + TW - 1) / TW;
+    if (u16 && d->gx_dtype && (relu_src == nullptr || d->x_dtype)) {
+        // tcgen05 kernel on the [T][H+2][W+2] domain: interior pixels leave the kernel final (masked, bf16); only the two-pixel ring
+        // along h / w passes through the fp32 buffer and the border fold
+        const int64_t sw = 16, sh = (int64_t)Wp * 16, st_ = (int64_t)Hp * Wp * 16, sv = (int64_t)d->Ti * Hp * Wp * 16;
+        const int64_t is[5] = {d->y_sn, d->y_sv, d->y_st, d->y_sh, d->y_sw}, os[5] = {sv * d->V, sv, st_, sh, sw};
+        if (conv16_umma_run(2, 0, gy, w, nullptr, gpad, ws, d->N, d->V, d->Vw, d->To, d->Ho, d->Wo, d->Ti, Hp, Wp, is, os, 0, st, gx, relu_src)) return 2;
+        const int64_t planes64 = (int64_t)d->N * d->V * d->Ti;
+        IDEE_REQUIRE(planes64 < (1ll << 31), "conv3d_dgrad(proj,bf16): too many planes for the border fold");
+        int nbp = (int)planes64;
+        if (nbp > idee_num_sms() * 8) nbp = idee_num_sms() * 8;
+        fold_ring_kernel<<<nbp, 256, 0, st>>>(gpad, (__nv_bfloat16*)gx, (const __nv_bfloat16*)relu_src, (int)planes64, d->Hi, d->Wi);
+        IDEE_LAUNCH_CHECK("conv3d_dgrad fold ring");
+        return 0;
+    }
     if (u16) {
         const int64_t is[5] = {d->y_sn, d->y_sv, d->y_st, d->y_sh, d->y_sw}, os[5] = {p.out_sn, p.out_sv, p.out_st, p.out_sh, p.out_sw};
         if (conv16_umma_run(1, 0, gy, w, nullptr, gpad, ws, d->N, d->V, d->Vw, d->To, d->Ho, d->Wo, Tp, Hp, Wp, is, os, 0, st)) return 2;

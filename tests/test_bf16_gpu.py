@@ -232,6 +232,55 @@ def test_tcgen05_proj_conv_matches_mma_sync(shape):
     assert torch.equal(gw0, gw1) and torch.equal(gb0, gb1)                        # weight gradient kernel is shared
 
 
+@pytest.mark.parametrize("masked", [False, True])
+@pytest.mark.parametrize("shape", [(1, 2, 1, 9, 11), (1, 2, 4, 21, 37), (2, 6, 8, 40, 48)])
+def test_tcgen05_proj_dgrad_direct_matches_mma_sync(shape, masked):
+    """bf16 input gradient of the 16 -> 16 proj conv: the tcgen05 kernel on the [T][H+2][W+2] domain (replicate adjoint along t as
+    extra MMAs on the first / last slice, final pixels written straight to gx with the fused ReLU mask, only the h / w ring through
+    the fp32 buffer + fold_ring_kernel) against the mma.sync kernel on the fully padded domain + fold_pad_kernel, and against
+    autograd through torch's replicate-padded conv3d on the same bf16-rounded operands."""
+    import torch.nn.functional as F
+    from idee_b200 import _lib, ops
+    N, V, T, H, W = shape
+    g = torch.Generator(device="cuda").manual_seed(13)
+    x = torch.randn(N, V, T, H, W, 16, device="cuda", generator=g)
+    if masked:
+        x = x.relu()
+    x16 = x.to(torch.bfloat16)
+    w = torch.randn(V, 16, 16, 3, 3, 3, device="cuda", generator=g) * 0.08
+    b = torch.randn(V, 16, device="cuda", generator=g) * 0.1
+    gy = torch.randn(N, V, T, H, W, 16, device="cuda", generator=g).to(torch.bfloat16)
+
+    def run(umma):
+        old = _lib.UMMA16
+        _lib.set_umma16(umma)
+        try:
+            xx = x16.clone().requires_grad_(True)
+            y = ops.conv3d_cl(xx, w, b, proj=True, relu=True, consumer_masks=True, input_is_relu=masked, out_bf16=True)
+            y.backward(gy)
+            assert xx.grad.dtype == torch.bfloat16
+            return xx.grad.float()
+        finally:
+            _lib.set_umma16(old)
+
+    gx0, gx1 = run(False), run(True)
+    # oracle: fp32 autograd on the bf16-rounded operands
+    xr = x16.float().requires_grad_(True)
+    wr = w.to(torch.bfloat16).float()
+    want = torch.zeros_like(xr)
+    for v in range(V):
+        xi = xr[:, v].permute(0, 4, 1, 2, 3)
+        yi = F.conv3d(F.pad(xi, (1, 1, 1, 1, 1, 1), mode="replicate"), wr[v])
+        want += torch.autograd.grad(yi, xr, gy[:, v].float().permute(0, 4, 1, 2, 3), retain_graph=False)[0]
+    if masked:
+        want = want * (x16 > 0)
+    scale = float(want.abs().max())
+    for got in (gx0, gx1):
+        assert float((got - want).abs().max()) <= 2 ** -7 * scale                 # one bf16 rounding of the result
+    assert float((gx0 - gx1).abs().max()) <= 2 ** -7 * scale
+    assert float((gx0 != gx1).float().mean()) < 2e-3                              # same operands: only ties of the final rounding differ
+
+
 def test_folded_last_conv_matches_conv_then_project_in():
     """VQ_model's bf16 path evaluates proj_var[2] followed by LFQ.project_in as ONE 16 -> 1 conv (Swin_3D.forward_tokens(fold_last=...)):
     the scalar it feeds to the quantiser must equal project_in(encoder output), and so must the gradients that reach the last
