@@ -23,7 +23,8 @@ int conv_tc_fwd(const idee_conv_desc* d, const void* x, const float* w, const fl
 int conv_tc_dgrad(const idee_conv_desc* d, const void* gy, const float* w, const void* relu_src, void* gx, void* ws, cudaStream_t st);
 int conv_tc_wgrad_partials(const idee_conv_desc* d, const void* x, const void* gy, float* partials, cudaStream_t st);
 bool conv96_umma_eligible(const idee_conv_desc* d);
-size_t conv96_wgrad_umma_workspace_bytes();
+size_t conv96_wgrad_umma_workspace_bytes(int Cin);
+bool conv16to96_wgrad_umma_eligible(const idee_conv_desc* d);
 int conv96_wgrad_umma_run(const idee_conv_desc* d, const float* x, const float* gy, float* gw, float* gb, void* ws, cudaStream_t st);
 bool conv_tc_bwd_fused_eligible(const idee_conv_desc* d, const void* x, const void* relu_src);
 int conv_tc_bwd_fused_splits(const idee_conv_desc* d);
@@ -400,7 +401,7 @@ extern "C" int idee_conv3d_dgrad(const idee_conv_desc* d, const void* gy, const 
 }
 
 extern "C" size_t idee_conv3d_wgrad_workspace_bytes(const idee_conv_desc* d) {
-    if (d->precision >= 1 && conv96_umma_eligible(d)) return conv96_wgrad_umma_workspace_bytes();
+    if (d->precision >= 1 && (conv96_umma_eligible(d) || conv16to96_wgrad_umma_eligible(d))) return conv96_wgrad_umma_workspace_bytes(d->Cin);
     if (d->precision >= 1) return conv_tc_wgrad_workspace_bytes(d);
     const int n_ic = (d->Cin + 15) / 16, n_oc = (d->Cout + 15) / 16, NT = (d->proj ? 3 : 2) * 9;
     return sizeof(float) * (size_t)d->Vw * n_ic * n_oc * wgrad_splits(d) * (NT * 256 + 16);
@@ -411,7 +412,7 @@ extern "C" int idee_conv3d_wgrad(const idee_conv_desc* d, const void* x, const v
     if (check_desc(d, "conv3d_wgrad")) return 1;
     IDEE_REQUIRE(workspace_bytes >= idee_conv3d_wgrad_workspace_bytes(d), "conv3d_wgrad: workspace too small");
     IDEE_REQUIRE(d->out_cpg * 16 >= d->Cout || d->Cout == 1, "conv3d_wgrad: grouped output layout is not supported");
-    if (d->precision >= 1 && conv96_umma_eligible(d))          // 96 -> 96 classifier conv: tcgen05 / TMEM accumulation over pixels
+    if (d->precision >= 1 && (conv96_umma_eligible(d) || conv16to96_wgrad_umma_eligible(d)))   // 96 / 16 -> 96 classifier convs: tcgen05 / TMEM accumulation over pixels
         return conv96_wgrad_umma_run(d, (const float*)x, (const float*)gy, gw, gb, workspace, (cudaStream_t)stream);
     if (d->precision >= 1) {
         cudaStream_t st = (cudaStream_t)stream;

@@ -20,14 +20,23 @@
 namespace conv96w {
 
 constexpr int TR = 16, TC = 8, HR = TR + 2, HC = TC + 2;
-constexpr int CI = 96, CO = 96, KC = 12;
+constexpr int CO = 96;
 constexpr int NPX = HR * HC;                          // 180 halo pixels of one time slice
-constexpr int XCHUNK = NPX * 16 + 16;                 // halo plane stride (+16: a pixel's chunks land in different banks)
-constexpr int GCHUNK = TR * TC * 16 + 16;             // gy plane stride
-constexpr int XBUF = (KC * XCHUNK + 127) / 128 * 128, GBUF = (KC * GCHUNK + 127) / 128 * 128;
+constexpr int GCHUNK = TR * TC * 16 + 16;             // gy plane stride (+16: a pixel's chunks land in different banks)
+constexpr int GBUF = (12 * GCHUNK + 127) / 128 * 128;
 constexpr int NLOAD = 512, MMA_WARP = NLOAD / 32, NTHREADS = NLOAD + 32;
-constexpr int MAXTAPS = 5, BIAS_COL = MAXTAPS * CI, TMEM_COLS = 512;
-constexpr int PART = MAXTAPS * CO * CI + CO;          // floats per CTA: [tap slot][co][ci] | db[co]
+constexpr int TMEM_COLS = 512;
+
+// CI = 96 (the 96 -> 96 conv): four tap groups, one input time slice per CTA.  CI = 16 (the joint head's first conv on the
+// 16-channel plane image of the rank-1 form of z_q): all 18 taps (18 x 16 + 16 columns) in one CTA, both time slices in the halo.
+template <int CI_> struct Cfg {
+    static constexpr int CI = CI_, KC = CI / 8;
+    static constexpr int NGROUP = CI == 96 ? 4 : 1, MAXTAPS = CI == 96 ? 5 : 18, NPL = CI == 96 ? 1 : 2;   // halo time slices per CTA
+    static constexpr int XCHUNK = NPL * NPX * 16 + 16;                    // halo plane stride
+    static constexpr int XBUF = (KC * XCHUNK + 127) / 128 * 128;
+    static constexpr int BIAS_COL = MAXTAPS * CI;
+    static constexpr int PART = MAXTAPS * CO * CI + CO;                   // floats per CTA: [tap slot][co][ci] | db[co]
+};
 
 struct WPU {
     const float* x; const float* gy; float* partials;
@@ -89,9 +98,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// grid = 4 * S: CTA b owns tap group b & 3 (time slice kt = group >> 1; taps [0,5) or [5,9) of the 3x3) and tile slice b >> 2
+// grid = NGROUP * S: CTA b owns tap group b % NGROUP (CI = 96: time slice kt = group >> 1, taps [0,5) or [5,9) of its 3x3) and tile
+// slice b / NGROUP
+template <int CI_>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv96_wgrad_umma_kernel(WPU p) {
+    using C_ = Cfg<CI_>;
+    constexpr int CI = C_::CI, XCHUNK = C_::XCHUNK, XBUF = C_::XBUF, MAXTAPS = C_::MAXTAPS, BIAS_COL = C_::BIAS_COL,
+                  PART = C_::PART, NGROUP = C_::NGROUP, NPL = C_::NPL;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* gbuf = smem_raw;                                        // [2][KC][128 px][16 B]  gy tile planes
     unsigned char* xbuf = smem_raw + 2 * GBUF;                             // [2][KC][180 px][16 B]  halo slice planes
@@ -100,8 +114,10 @@ conv96_wgrad_umma_kernel(WPU p) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t bar_full = smem_u32(&bars[0]), bar_done = smem_u32(&bars[2]), bar_final = smem_u32(&bars[4]);
-    const int group = blockIdx.x & 3, slice = blockIdx.x >> 2;
-    const int kt = group >> 1, tap0 = (group & 1) ? 5 : 0, ntap = (group & 1) ? 4 : 5;
+    const int group = blockIdx.x % NGROUP, slice = blockIdx.x / NGROUP;
+    // taps of this CTA: CI = 96: j9 = tap0 + j of time slice kt0;  CI = 16: tap j = kt * 9 + j9 over both slices
+    const int kt0 = NGROUP == 4 ? group >> 1 : 0, tap0 = (NGROUP == 4 && (group & 1)) ? 5 : 0;
+    const int ntap = NGROUP == 4 ? ((group & 1) ? 4 : 5) : 18;
 
     if (tid < 32) reinterpret_cast<uint32_t*>(ones)[tid] = 0x3F803F80u;
     if (warp == MMA_WARP) {
@@ -148,8 +164,8 @@ conv96_wgrad_umma_kernel(WPU p) {
                     const uint64_t ad = adesc0 + (uint64_t)(ks * 2 * TC);
                     const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
                     for (int j = 0; j < ntap; ++j) {
-                        const int j9 = tap0 + j, kh = j9 / 3, kw = j9 - kh * 3;
-                        umma(tmem_base + j * CI, ad, bdesc0 + (uint64_t)((2 * ks + kh) * HC + kw), ID_W, acc);
+                        const int jj = tap0 + j, pl = jj / 9, j9 = jj - pl * 9, kh = j9 / 3, kw = j9 - kh * 3;   // pl: slice inside the halo buffer
+                        umma(tmem_base + j * CI, ad, bdesc0 + (uint64_t)((pl * HR + 2 * ks + kh) * HC + kw), ID_W, acc);
                     }
                     umma(tmem_base + BIAS_COL, ad, ones_desc, ID_B, acc);
                 }
@@ -162,19 +178,21 @@ conv96_wgrad_umma_kernel(WPU p) {
     } else {
         // ================= loaders: fp32 HBM -> bf16 chunk planes, one tile ahead of the MMAs =================
         constexpr int V4 = CI / 4;                                     // float4 units per pixel
-        constexpr int XU = NPX * V4, GU = TR * TC * V4, TOTAL = XU + GU;
+        constexpr int G4 = CO / 4;                                     // float4 units per gy pixel
+        constexpr int XU = NPL * NPX * V4, GU = TR * TC * G4, TOTAL = XU + GU;
         constexpr int DEPTH = (TOTAL + NLOAD - 1) / NLOAD;             // 15: the whole tile in ONE round of loads per thread (one memory latency per tile)
         // unit e -> (source pointer or null, destination byte offset inside the tile's x / gy planes; < 0: no such unit)
         auto unit = [&](int e, const Tile& c, bool t_ok, const float* x_n, const float* g_n, const float*& src) -> int {
             src = nullptr;
             if (e < XU) {
-                const int q = e / V4, c4 = e - q * V4, hh = q / HC, ww = q - hh * HC;
+                const int q = e / V4, c4 = e - q * V4, pl = q / NPX, q1 = q - pl * NPX, hh = q1 / HC, ww = q1 - hh * HC;
                 const int hi = c.h0 + hh - 1, wi = c.w0 + ww - 1;
-                if (t_ok && (unsigned)hi < (unsigned)p.Hi && (unsigned)wi < (unsigned)p.Wi) src = x_n + (hi * p.x_sh + wi * p.x_sw) + c4 * 4;
+                const bool ok = (NPL == 1 ? t_ok : 2 * c.t + pl < p.Ti) && (unsigned)hi < (unsigned)p.Hi && (unsigned)wi < (unsigned)p.Wi;
+                if (ok) src = x_n + (pl * p.x_st + hi * p.x_sh + wi * p.x_sw) + c4 * 4;
                 return (c4 >> 1) * XCHUNK + q * 16 + (c4 & 1) * 8;
             }
             if (e < TOTAL) {
-                const int eg = e - XU, q = eg / V4, c4 = eg - q * V4, r = q / TC, cc = q - r * TC;
+                const int eg = e - XU, q = eg / G4, c4 = eg - q * G4, r = q / TC, cc = q - r * TC;
                 const int h = c.h0 + r, w = c.w0 + cc;
                 if (h < p.Hi && w < p.Wi) src = g_n + (h * p.gy_sh + w * p.gy_sw) + c4 * 4;
                 return 2 * XBUF + (c4 >> 1) * GCHUNK + q * 16 + (c4 & 1) * 8;      // marks a gy unit: offset beyond the x buffers
@@ -186,9 +204,9 @@ conv96_wgrad_umma_kernel(WPU p) {
             const Tile c = decode(first + it);
             unsigned char* xdst = xbuf + b * XBUF;
             unsigned char* gdst = gbuf + b * GBUF;
-            const float* x_n = p.x + c.n * p.x_sn + (int64_t)(2 * c.t + kt) * p.x_st;
+            const float* x_n = p.x + c.n * p.x_sn + (int64_t)(2 * c.t + kt0) * p.x_st;
             const float* g_n = p.gy + c.n * p.gy_sn + (int64_t)c.t * p.gy_st;
-            const bool t_ok = 2 * c.t + kt < p.Ti;
+            const bool t_ok = 2 * c.t + kt0 < p.Ti;
             float4 f[DEPTH];
 #pragma unroll
             for (int u = 0; u < DEPTH; ++u) {                          // loads of tile it fly while the MMAs of tile it-2 drain
@@ -219,19 +237,18 @@ conv96_wgrad_umma_kernel(WPU p) {
         }
         const int co = warp * 32 + lane;
         const uint32_t tl = tmem_base + ((uint32_t)(warp * 32) << 16);
-        for (int j = 0; j < MAXTAPS; ++j)
 #pragma unroll 1
-            for (int k = 0; k < CI / 32; ++k) {
-                float v[32];
-                if (ntile > 0 && j < ntap) tmem_ld32(tl + j * CI + 32 * k, v);
-                else {
+        for (int col0 = 0; col0 < MAXTAPS * CI; col0 += 32) {          // 32 accumulator columns = (tap slot, ci) pairs, ci fastest
+            float v[32];
+            if (ntile > 0) tmem_ld32(tl + col0, v);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = 0.f;
-                }
-                float* dst = part + ((size_t)j * CO + co) * CI + 32 * k;
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            for (int i = 0; i < 32; i += 4) {
+                const int col = col0 + i, j = col / CI, ci = col - j * CI;
+                const bool live = ntile > 0 && j < ntap;                   // unused tap slots and CTAs without tiles contribute zeros
+                *reinterpret_cast<float4*>(part + ((size_t)j * CO + co) * CI + ci) =
+                    live ? make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+        }
         {
             float v[32];
             if (ntile > 0) tmem_ld32(tl + BIAS_COL - 16, v);           // columns BIAS_COL-16 .. BIAS_COL+15: element 16 = db[co]
@@ -244,20 +261,24 @@ conv96_wgrad_umma_kernel(WPU p) {
 }
 
 // gw[co][ci][kt][kh][kw] = sum over the S tile slices of the owning group's partial; gb[co] from the group-0 CTAs
+template <int CI_>
 __global__ void conv96_wgrad_reduce_kernel(const float* __restrict__ partials, float* __restrict__ gw, float* __restrict__ gb, int S) {
+    using C_ = Cfg<CI_>;
+    constexpr int CI = C_::CI, PART = C_::PART, NGROUP = C_::NGROUP, MAXTAPS = C_::MAXTAPS;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;                // (tap, co, ci), ci fastest: coalesced partial reads
     if (e < 18 * CO * CI) {
         const int ci = e % CI, co = (e / CI) % CO, tap = e / (CI * CO);
-        const int kt = tap / 9, j9 = tap % 9, group = kt * 2 + (j9 >= 5 ? 1 : 0), j = j9 >= 5 ? j9 - 5 : j9;
+        int group = 0, j = tap;
+        if (NGROUP == 4) { const int kt = tap / 9, j9 = tap % 9; group = kt * 2 + (j9 >= 5 ? 1 : 0); j = j9 >= 5 ? j9 - 5 : j9; }
         const float* src = partials + (size_t)group * PART + ((size_t)j * CO + co) * CI + ci;
         float acc = 0.f;
-        for (int s = 0; s < S; ++s) acc += src[(size_t)s * 4 * PART];
+        for (int s = 0; s < S; ++s) acc += src[(size_t)s * NGROUP * PART];
         gw[((size_t)co * CI + ci) * 18 + tap] = acc;
     } else if (e < 18 * CO * CI + CO && gb) {
         const int co = e - 18 * CO * CI;
         const float* src = partials + (size_t)MAXTAPS * CO * CI + co;
         float acc = 0.f;
-        for (int s = 0; s < S; ++s) acc += src[(size_t)s * 4 * PART];
+        for (int s = 0; s < S; ++s) acc += src[(size_t)s * NGROUP * PART];
         gb[co] = acc;
     }
 }
@@ -266,14 +287,23 @@ __global__ void conv96_wgrad_reduce_kernel(const float* __restrict__ partials, f
 
 using namespace conv96w;
 
-static int conv96_wgrad_slices() {
-    int S = idee_num_sms() / 4;
+template <int CI_> static int wgrad_slices() {
+    int S = idee_num_sms() / Cfg<CI_>::NGROUP;
     return S < 1 ? 1 : S;
 }
 
-size_t conv96_wgrad_umma_workspace_bytes() { return sizeof(float) * (size_t)4 * conv96_wgrad_slices() * PART; }
+bool conv16to96_wgrad_umma_eligible(const idee_conv_desc* d) {
+    return d->umma96 && d->precision >= 1 && !d->proj && d->Cin == 16 && d->Cout == 96 && d->V == 1 && d->Vw == 1 && d->in_cpg == 1 &&
+           d->out_cpg == 6 && d->x_sw == 16 && d->y_sw == 96 && !d->x_dtype && !d->y_dtype;
+}
 
-int conv96_wgrad_umma_run(const idee_conv_desc* d, const float* x, const float* gy, float* gw, float* gb, void* ws, cudaStream_t st) {
+size_t conv96_wgrad_umma_workspace_bytes(int Cin) {
+    return Cin == 96 ? sizeof(float) * (size_t)4 * wgrad_slices<96>() * Cfg<96>::PART : sizeof(float) * (size_t)wgrad_slices<16>() * Cfg<16>::PART;
+}
+
+template <int CI_>
+static int wgrad_run(const idee_conv_desc* d, const float* x, const float* gy, float* gw, float* gb, void* ws, cudaStream_t st) {
+    using C_ = Cfg<CI_>;
     WPU p{};
     p.x = x; p.gy = gy; p.partials = (float*)ws;
     p.N = d->N; p.Ti = d->Ti; p.Hi = d->Hi; p.Wi = d->Wi; p.To = d->To;
@@ -286,13 +316,17 @@ int conv96_wgrad_umma_run(const idee_conv_desc* d, const float* x, const float* 
     const int64_t total = (int64_t)d->N * d->To * p.tiles_h * p.tiles_w;
     IDEE_REQUIRE(total < (1ll << 31), "conv3d_wgrad(umma96): too many tiles");
     p.total_tiles = (uint32_t)total;
-    p.S = conv96_wgrad_slices();
-    const size_t smem = 2 * (size_t)GBUF + 2 * (size_t)XBUF + 128 + 5 * 8 + 16;
-    IDEE_CUDA(cudaFuncSetAttribute(conv96_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "conv3d_wgrad(umma96)");
-    conv96_wgrad_umma_kernel<<<4 * p.S, NTHREADS, smem, st>>>(p);
+    p.S = wgrad_slices<CI_>();
+    const size_t smem = 2 * (size_t)GBUF + 2 * (size_t)C_::XBUF + 128 + 5 * 8 + 16;
+    IDEE_CUDA(cudaFuncSetAttribute(conv96_wgrad_umma_kernel<CI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "conv3d_wgrad(umma96)");
+    conv96_wgrad_umma_kernel<CI_><<<C_::NGROUP * p.S, NTHREADS, smem, st>>>(p);
     IDEE_LAUNCH_CHECK("conv3d_wgrad(umma96)");
-    const int nel = 18 * CO * CI + CO;
-    conv96_wgrad_reduce_kernel<<<(nel + 255) / 256, 256, 0, st>>>(p.partials, gw, gb, p.S);
+    const int nel = 18 * CO * CI_ + CO;
+    conv96_wgrad_reduce_kernel<CI_><<<(nel + 255) / 256, 256, 0, st>>>(p.partials, gw, gb, p.S);
     IDEE_LAUNCH_CHECK("conv3d_wgrad(umma96) reduce");
     return 0;
+}
+
+int conv96_wgrad_umma_run(const idee_conv_desc* d, const float* x, const float* gy, float* gw, float* gb, void* ws, cudaStream_t st) {
+    return d->Cin == 96 ? wgrad_run<96>(d, x, gy, gw, gb, ws, st) : wgrad_run<16>(d, x, gy, gw, gb, ws, st);
 }
