@@ -293,24 +293,28 @@ conv_wgrad_kernel(WgradP p) {
     }
 }
 
-// second stage: one thread per dW / db element of the reference layout
+// second stage: one thread per entry of the PARTIAL layout (tap, c, o: consecutive threads read consecutive floats of every
+// partial block), summed over the S splits in a fixed order, scattered into the reference layout [o][c][tap] / [o]
 __global__ void conv_wgrad_reduce_kernel(const float* __restrict__ partials, float* __restrict__ gw, float* __restrict__ gb,
                                          int Vw, int FCI, int FCO, int NT, int n_ic, int n_oc, int S,
                                          int64_t w_set_stride, int64_t b_set_stride) {
     const int wset = blockIdx.y;
-    const int64_t nW = (int64_t)FCO * FCI * NT;
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int PS = NT * 256 + 16;
-    if (e < nW) {
-        const int ft = (int)(e % NT); const int c = (int)((e / NT) % FCI); const int o = (int)(e / ((int64_t)NT * FCI));
-        const int ic = c / 16, oc = o / 16;
-        const float* p = partials + ((((int64_t)wset * n_ic + ic) * n_oc + oc) * S) * PS + ft * 256 + (c % 16) * 16 + (o % 16);
+    const int64_t per_set = (int64_t)n_ic * n_oc * PS;
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // (ic, oc, slot)
+    if (q >= per_set) return;
+    const int slot = (int)(q % PS);
+    const int oc = (int)((q / PS) % n_oc), ic = (int)(q / ((int64_t)PS * n_oc));
+    const float* p = partials + ((((int64_t)wset * n_ic + ic) * n_oc + oc) * S) * PS + slot;
+    if (slot < NT * 256) {
+        const int ft = slot >> 8, c = ic * 16 + ((slot >> 4) & 15), o = oc * 16 + (slot & 15);
+        if (c >= FCI || o >= FCO) return;
         float acc = 0.f;
         for (int s = 0; s < S; ++s) acc += p[(int64_t)s * PS];
-        gw[wset * w_set_stride + e] = acc;
-    } else if (e < nW + FCO && gb) {
-        const int o = (int)(e - nW);
-        const float* p = partials + ((((int64_t)wset * n_ic + 0) * n_oc + o / 16) * S) * PS + NT * 256 + (o % 16);
+        gw[wset * w_set_stride + ((int64_t)o * FCI + c) * NT + ft] = acc;
+    } else if (gb && ic == 0) {
+        const int o = oc * 16 + (slot - NT * 256);
+        if (o >= FCO) return;
         float acc = 0.f;
         for (int s = 0; s < S; ++s) acc += p[(int64_t)s * PS];
         gb[wset * b_set_stride + o] = acc;
@@ -418,7 +422,7 @@ extern "C" int idee_conv3d_wgrad(const idee_conv_desc* d, const void* x, const v
         cudaStream_t st = (cudaStream_t)stream;
         if (conv_tc_wgrad_partials(d, x, gy, (float*)workspace, st)) return 2;
         const int NT = (d->proj ? 3 : 2) * 9;
-        const int64_t nel = (int64_t)d->Cout * d->Cin * NT + d->Cout;
+        const int64_t nel = (int64_t)((d->Cin + 15) / 16) * ((d->Cout + 15) / 16) * (NT * 256 + 16);
         conv_wgrad_reduce_kernel<<<dim3((unsigned)((nel + 255) / 256), d->Vw), 256, 0, st>>>(
             (const float*)workspace, gw, gb, d->Vw, d->Cin, d->Cout, NT, (d->Cin + 15) / 16, (d->Cout + 15) / 16, conv_tc_wgrad_splits(d),
             (int64_t)d->Cin * d->Cout * NT, d->Cout);
@@ -440,7 +444,7 @@ extern "C" int idee_conv3d_wgrad(const idee_conv_desc* d, const void* x, const v
     if (d->proj) conv_wgrad_kernel<27><<<grid, 27 * 16, 0, st>>>(p);
     else conv_wgrad_kernel<18><<<grid, 18 * 16, 0, st>>>(p);
     IDEE_LAUNCH_CHECK("conv3d_wgrad");
-    const int64_t nel = (int64_t)d->Cout * d->Cin * NT + d->Cout;
+    const int64_t nel = (int64_t)p.n_ic * p.n_oc * (NT * 256 + 16);
     conv_wgrad_reduce_kernel<<<dim3((unsigned)((nel + 255) / 256), d->Vw), 256, 0, st>>>(
         p.partials, gw, gb, d->Vw, d->Cin, d->Cout, NT, p.n_ic, p.n_oc, p.S, (int64_t)d->Cin * d->Cout * NT, d->Cout);
     IDEE_LAUNCH_CHECK("conv3d_wgrad_reduce");
@@ -464,7 +468,7 @@ extern "C" int idee_conv3d_bwd(const idee_conv_desc* d, const void* x, const voi
     if (conv_tc_bwd_fused_eligible(d, x, relu_src)) {
         cudaStream_t st = (cudaStream_t)stream;
         if (conv_tc_bwd_fused_partials(d, x, gy, w, relu_src, gx, (float*)workspace, st)) return 2;
-        const int64_t nel = (int64_t)d->Cout * d->Cin * 27 + d->Cout;
+        const int64_t nel = 27 * 256 + 16;
         conv_wgrad_reduce_kernel<<<dim3((unsigned)((nel + 255) / 256), d->Vw), 256, 0, st>>>(
             (const float*)workspace, gw, gb, d->Vw, d->Cin, d->Cout, 27, 1, 1, conv_tc_bwd_fused_splits(d), (int64_t)d->Cin * d->Cout * 27, d->Cout);
         IDEE_LAUNCH_CHECK("conv3d_bwd reduce");

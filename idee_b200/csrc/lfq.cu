@@ -189,12 +189,20 @@ lfq_bwd_kernel(const float* __restrict__ z, const float* __restrict__ gzq, const
 }
 
 // grads (float[49]): g_w_in[16] | g_b_in | g_w_out[16] | g_b_out[16]
-__global__ void lfq_bwd_finalize_kernel(const double* __restrict__ partials, int nblocks, float* __restrict__ grads) {
-    const int k = threadIdx.x;
-    if (k >= LFQ_NG) return;
+// one CTA per gradient element: 128 threads sum strided subsets of the per-block partials (double), fixed-order tree after
+__global__ void __launch_bounds__(128) lfq_bwd_finalize_kernel(const double* __restrict__ partials, int nblocks, float* __restrict__ grads) {
+    __shared__ double red[128];
+    const int k = blockIdx.x, t = threadIdx.x;
     double a = 0.0;
-    for (int b = 0; b < nblocks; ++b) a += partials[(int64_t)b * LFQ_NG + k];
-    grads[k] = (float)a;
+    for (int b = t; b < nblocks; b += 128) a += partials[(int64_t)b * LFQ_NG + k];
+    red[t] = a;
+    __syncthreads();
+#pragma unroll
+    for (int o = 64; o > 0; o >>= 1) {
+        if (t < o) red[t] += red[t + o];
+        __syncthreads();
+    }
+    if (t == 0) grads[k] = (float)red[0];
 }
 
 int lfq_blocks(int64_t ntok) {
@@ -243,7 +251,7 @@ extern "C" int idee_lfq_bwd(const float* z, const float* gzq, const float* gxq, 
     else lfq_bwd_kernel<false><<<nb, LFQ_THREADS, 0, st>>>(z, gzq, gxq, g_aux, stats, w_in, b_in, w_out, gz, (double*)workspace, ntok, lambda_commit,
                                                             lambda_entropy, diversity_gamma, inv_temperature);
     IDEE_LAUNCH_CHECK("lfq_bwd");
-    lfq_bwd_finalize_kernel<<<1, 64, 0, st>>>((const double*)workspace, nb, grads);
+    lfq_bwd_finalize_kernel<<<LFQ_NG, 128, 0, st>>>((const double*)workspace, nb, grads);
     IDEE_LAUNCH_CHECK("lfq_bwd_finalize");
     return 0;
 }

@@ -580,8 +580,27 @@ swin_attn_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gy, 
 }
 
 // ---- second stage: deterministic sum of per-CTA partials into the packed gradient block -------------
-// One CTA per variable: phase 1 sums every partial element over the CTAs (coalesced), phase 2 writes the packed gradient
-// and gathers the bias-table rows from the summed [h][i][j] gradient through rel_index.
+// (1) swin_grad_sum_kernel: one thread per partial element sums it over the CTAs in a fixed order (coalesced across threads) and
+//     leaves the sum in CTA 0's slot; (2) swin_grad_finalize_kernel, one CTA per variable: writes the packed gradient and gathers
+//     the bias-table rows from the summed [h][i][j] gradient through rel_index.
+template <int G>
+__global__ void __launch_bounds__(256)
+swin_grad_sum_kernel(float* __restrict__ part_attn, float* __restrict__ part_mlp, int ncta_attn, int ncta_mlp) {
+    constexpr int APS = ATT_PART_W + NH * G * G;
+    const int v = blockIdx.y, e = blockIdx.x * 256 + threadIdx.x;
+    if (e < APS) {
+        float* p = part_attn + (int64_t)v * ncta_attn * APS + e;
+        float acc = 0.f;
+        for (int c = 0; c < ncta_attn; ++c) acc += p[(int64_t)c * APS];
+        p[0] = acc;
+    } else if (e < APS + MLP_PART) {
+        float* p = part_mlp + (int64_t)v * ncta_mlp * MLP_PART + (e - APS);
+        float acc = 0.f;
+        for (int c = 0; c < ncta_mlp; ++c) acc += p[(int64_t)c * MLP_PART];
+        p[0] = acc;
+    }
+}
+
 template <int G>
 __global__ void __launch_bounds__(1024)
 swin_grad_finalize_kernel(const float* __restrict__ part_attn, const float* __restrict__ part_mlp,
@@ -592,18 +611,8 @@ swin_grad_finalize_kernel(const float* __restrict__ part_attn, const float* __re
     __shared__ float sum_mlp[MLP_PART];
     const int v = blockIdx.x;
     const POff po(tbl);
-    for (int e = threadIdx.x; e < APS; e += blockDim.x) {
-        const float* p = part_attn + (int64_t)v * ncta_attn * APS + e;
-        float acc = 0.f;
-        for (int c = 0; c < ncta_attn; ++c) acc += p[(int64_t)c * APS];
-        sum_attn[e] = acc;
-    }
-    for (int e = threadIdx.x; e < MLP_PART; e += blockDim.x) {
-        const float* p = part_mlp + (int64_t)v * ncta_mlp * MLP_PART + e;
-        float acc = 0.f;
-        for (int c = 0; c < ncta_mlp; ++c) acc += p[(int64_t)c * MLP_PART];
-        sum_mlp[e] = acc;
-    }
+    for (int e = threadIdx.x; e < APS; e += blockDim.x) sum_attn[e] = part_attn[(int64_t)v * ncta_attn * APS + e];
+    for (int e = threadIdx.x; e < MLP_PART; e += blockDim.x) sum_mlp[e] = part_mlp[(int64_t)v * ncta_mlp * MLP_PART + e];
     __syncthreads();
     float* gp = gparams + (int64_t)v * pstride;
     for (int e = threadIdx.x; e < po.total; e += blockDim.x) {
@@ -617,6 +626,17 @@ swin_grad_finalize_kernel(const float* __restrict__ part_attn, const float* __re
         else val = sum_mlp[e - po.fc1_w];
         gp[e] = val;
     }
+}
+
+template <int G>
+int launch_grad_finalize(float* part_attn, float* part_mlp, int ncta_attn, int ncta_mlp, const int* rel_index, float* gparams,
+                         int64_t pstride, int tbl, int V, cudaStream_t st) {
+    constexpr int APS = ATT_PART_W + NH * G * G;
+    swin_grad_sum_kernel<G><<<dim3((APS + MLP_PART + 255) / 256, V), 256, 0, st>>>(part_attn, part_mlp, ncta_attn, ncta_mlp);
+    IDEE_LAUNCH_CHECK("swin_grad_sum");
+    swin_grad_finalize_kernel<G><<<V, 1024, 0, st>>>(part_attn, part_mlp, ncta_attn, ncta_mlp, rel_index, gparams, pstride, tbl);
+    IDEE_LAUNCH_CHECK("swin_grad_finalize");
+    return 0;
 }
 
 #include "swin_tc.cuh"
@@ -780,8 +800,7 @@ int launch_bwd(const idee_swin_desc* d, const Geom& g, const float* x, const flo
             swin_attn_bwd_tc_kernel<WD, WH, WW, false><<<dim3(per_v, d->V), TCW * 32, dyn, st>>>(x, gx, gx, params, d->param_stride, rel_index, part_attn, g);
             IDEE_LAUNCH_CHECK("swin_attn_bwd(bf16)");
         }
-        swin_grad_finalize_kernel<G><<<d->V, 1024, 0, st>>>(part_attn, part_mlp, per_v, per_v, rel_index, gparams, d->param_stride, g.tbl);
-        IDEE_LAUNCH_CHECK("swin_grad_finalize");
+        if (launch_grad_finalize<G>(part_attn, part_mlp, per_v, per_v, rel_index, gparams, d->param_stride, g.tbl, d->V, st)) return 2;
         return 0;
     }
     IDEE_CUDA(cudaFuncSetAttribute(swin_mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MlpSmem)), "swin_mlp_bwd");
@@ -794,8 +813,7 @@ int launch_bwd(const idee_swin_desc* d, const Geom& g, const float* x, const flo
     IDEE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "swin_attn_bwd");
     kern<<<dim3(per_v, d->V), AB_WARPS * 32, smem, st>>>(x, gx, gx, params, d->param_stride, rel_index, part_attn, g);
     IDEE_LAUNCH_CHECK("swin_attn_bwd");
-    swin_grad_finalize_kernel<G><<<d->V, 1024, 0, st>>>(part_attn, part_mlp, per_v, per_v, rel_index, gparams, d->param_stride, g.tbl);
-    IDEE_LAUNCH_CHECK("swin_grad_finalize");
+    if (launch_grad_finalize<G>(part_attn, part_mlp, per_v, per_v, rel_index, gparams, d->param_stride, g.tbl, d->V, st)) return 2;
     return 0;
 }
 

@@ -1343,8 +1343,7 @@ int launch_attn_bwd(const idee_swin_desc* d, const Geom& g, const void* x, __nv_
         swin_attn_bwd_umma_kernel<WD, WH, WW, false><<<dim3(per_v, d->V), NT, smem, st>>>(x, gx, gx, params, d->param_stride, rel_index, part_attn, g);
         IDEE_LAUNCH_CHECK("swin_attn_bwd(umma)");
     }
-    swin_grad_finalize_kernel<G><<<d->V, 1024, 0, st>>>(part_attn, part_mlp, per_v, per_v_mlp, rel_index, gparams, d->param_stride, g.tbl);
-    IDEE_LAUNCH_CHECK("swin_grad_finalize");
+    if (launch_grad_finalize<G>(part_attn, part_mlp, per_v, per_v_mlp, rel_index, gparams, d->param_stride, g.tbl, d->V, st)) return 2;
     return 0;
 }
 
