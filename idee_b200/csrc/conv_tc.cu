@@ -1720,10 +1720,38 @@ int conv_tc_dgrad(const idee_conv_desc* d, const void* gy, const float* w, const
 
 int conv_tc_wgrad_ncout(const idee_conv_desc* d) { return d->Cout >= 32 ? 32 : (d->Cout >= 16 ? 16 : 8); }
 
+// resident CTAs per SM of the weight-gradient kernel this descriptor selects (registers / shared memory; -1: use the default).
+// The split count is sized so that the whole grid is ONE wave: a grid of 4 CTAs per SM on a kernel that only fits 3 runs a
+// second, one-third-full wave (the 16 -> 16 proj conv at 166 registers: 1.2 ms instead of 0.8).
+static int wgrad_ctas_per_sm(const idee_conv_desc* d) {
+    const int NC = conv_tc_wgrad_ncout(d);
+    const bool a16 = d->x_dtype, g16 = d->y_dtype;
+    const int KTIN = d->proj ? 3 : 2;
+    const size_t smem = (size_t)KTIN * HH * HW_ * (a16 ? 2 * 24 * 2 : 16 * 4 + 24 * 2) +
+                        (size_t)TH * TW * (g16 ? 2 * (NC + 8) * 2 : NC * 4 + (NC + 8) * 2);
+    const void* fn = nullptr;
+    if (d->proj && NC == 16) {
+        fn = a16 && g16 ? (const void*)wgrad_tc_kernel<27, 2, true, true> : a16 ? (const void*)wgrad_tc_kernel<27, 2, true, false>
+           : g16 ? (const void*)wgrad_tc_kernel<27, 2, false, true> : (const void*)wgrad_tc_kernel<27, 2, false, false>;
+    }
+    if (!fn) return -1;
+    static int cache[4] = {0, 0, 0, 0};
+    int& c = cache[(a16 ? 2 : 0) + (g16 ? 1 : 0)];
+    if (c == 0) {
+        int n = 0;
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, 128, smem) != cudaSuccess || n < 1) { cudaGetLastError(); n = -1; }
+        c = n;
+    }
+    return c;
+}
+
 int conv_tc_wgrad_splits(const idee_conv_desc* d) {
     const int n_ic = (d->Cin + 15) / 16, NC = conv_tc_wgrad_ncout(d);
     const int n_occ = (d->Cout + NC - 1) / NC;
-    int S = (idee_num_sms() * 4 + d->Vw * n_ic * n_occ - 1) / (d->Vw * n_ic * n_occ);
+    int per_sm = wgrad_ctas_per_sm(d);
+    if (per_sm < 1 || per_sm > 4) per_sm = 4;
+    int S = (idee_num_sms() * per_sm + d->Vw * n_ic * n_occ - 1) / (d->Vw * n_ic * n_occ);
     if (S < 1) S = 1;
     if (S > 512) S = 512;
     return S;

@@ -249,23 +249,39 @@ class HostPrefetcher:
 
 
 class HostResults:
-    """Double-buffered device -> host return of a step's results (logits, loss) without draining the launch queue.
+    """Double-buffered device -> host return of a step's results (logits, loss, driver mask) without draining the launch queue and
+    without occupying the compute stream.
 
     The reference reads ``loss.item()`` right after every step (train_synthetic.py:176-186), which leaves the GPU idle while the
-    host enqueues the next step.  Here step i's results are copied into pinned host slot i & 1 behind the step on the compute
-    stream (``put``), and the host reads them (``get``) one step later, after step i+1 has been enqueued: every step's results
-    still reach the host, the copies just overlap the next step's launches."""
+    host enqueues the next step.  Here step i's results are snapshotted into device staging slot i & 1 behind the step on the
+    compute stream (a few microseconds; this is also where a dtype change such as int64 -> uint8 happens), copied to pinned host
+    memory by a side stream (``put``), and read by the host (``get``) one step later, after step i+1 has been enqueued: every
+    step's results still reach the host, the PCIe transfer overlaps the next step's kernels."""
 
     def __init__(self, device, example_results):
         self.device = torch.device(device)
+        self.copy_stream = torch.cuda.Stream(self.device)
         self.slots = [[torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in example_results] for _ in range(2)]
+        self.stage = [[torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in example_results] for _ in range(2)]
+        self.snap = [torch.cuda.Event(), torch.cuda.Event()]
         self.done = [torch.cuda.Event(), torch.cuda.Event()]
+        self.used = [False, False]
 
     def put(self, slot: int, results):
-        """Enqueue the device -> host copies of ``results`` into ``slot`` on the current stream; returns immediately."""
-        for dst, src in zip(self.slots[slot], results):
+        """Snapshot ``results`` on the current stream and start their device -> host copies on the side stream; returns
+        immediately.  Slot reuse is safe once ``get`` of the same slot has returned (it waits for the copies)."""
+        cur = torch.cuda.current_stream(self.device)
+        if self.used[slot]:
+            cur.wait_event(self.done[slot])                       # the previous transfer out of this staging slot has finished
+        self.used[slot] = True
+        for dst, src in zip(self.stage[slot], results):
             dst.copy_(src.detach().reshape(dst.shape), non_blocking=True)
-        self.done[slot].record(torch.cuda.current_stream(self.device))
+        self.snap[slot].record(cur)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.snap[slot])
+            for dst, src in zip(self.slots[slot], self.stage[slot]):
+                dst.copy_(src, non_blocking=True)
+            self.done[slot].record(self.copy_stream)
 
     def get(self, slot: int):
         """Pinned host tensors of ``slot`` (blocks until its copies have landed)."""
