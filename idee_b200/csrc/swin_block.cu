@@ -759,9 +759,8 @@ int launch_bwd(const idee_swin_desc* d, const Geom& g, const float* x, const flo
         IDEE_REQUIRE((int64_t)d->N * thw < (1ll << 31), "swin_block_bwd(umma): N*T*H*W must be below 2^31");
         IDEE_REQUIRE(g.emb_x == nullptr || d->embed_gw != nullptr, "swin_block_bwd(umma): the fused embedding needs embed_gw / embed_gb");
         IDEE_REQUIRE(gx != gout, "swin_block_bwd(umma): gx must not alias gout");
-        // persistent grids of one resident wave: 4 CTAs / SM (MLP half), 3 CTAs / SM (attention half; 2 with the fused embedding:
-        // 16 planes and 232 registers)
-        int pv_mlp = idee_num_sms() * 4 / d->V, pv_att = idee_num_sms() * (g.emb_x ? 2 : 3) / d->V;
+        // persistent grids of one resident wave: 4 CTAs / SM (MLP half), 3 CTAs / SM (attention half)
+        int pv_mlp = idee_num_sms() * 4 / d->V, pv_att = idee_num_sms() * 3 / d->V;
         if (pv_mlp < 1) pv_mlp = 1;
         if (pv_att < 1) pv_att = 1;
         float* u_attn = ws;

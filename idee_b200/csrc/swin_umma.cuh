@@ -855,17 +855,19 @@ swin_mlp_bwd_umma_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat1
 //   d{qkv_w, qkv_b, proj_w, proj_b, bias[h][i][j]} (ATT_PART_W + NH*G*G layout) and, with the fused embedding, d{embed w, b}
 // =====================================================================================================
 // chunk planes [plane][token][16 B] of a tile (see the file header):
-//   0-1 q -> dq | 2-3 k -> dk | 4-5 v -> dv | 6-7 g_y | 8-9 g_embed (fused embedding only) | 10-11 xn | 12-13 dO -> o | 14 ones | 15 (x, 1, 0..)
-// weight gradients: D[M x 48] += [dq | dk | dv | g_y (| g_e | ...)]^T [xn | o | 1 | (x, 1)], M = 64 (128 with the fused embedding)
-constexpr int A_Q = 0, A_K = 2, A_V = 4, A_GY = 6, A_GE = 8;
-template <bool EMB> struct APl {          // without the fused embedding the two g_embed planes do not exist
-    static constexpr int XN = EMB ? 10 : 8, DO = XN + 2, ONE = XN + 4, X1 = XN + 5, PLANES = XN + 6;
+//   0-1 q -> dq | 2-3 k -> dk | 4-5 v -> dv | 6-7 g_y | 8-9 xn | 10-11 dO -> o | 12 ones | 13 zeros
+// weight gradients: D[64 x 48] += [dq | dk | dv | g_y]^T [xn | o | 1 | 0]
+// EMB: the block's input tokens are recomputed from the raw input (fused patch embedding, idee_swin_desc.embed_x); the gradient
+// w.r.t. those tokens is written to gx like for any other block and embed_bwd_tokens_kernel turns it into d{embed w, b} (the
+// LayerNorm backward of the embedding inside this kernel cost 49 registers, one CTA per SM and an extra MMA round per tile).
+constexpr int A_Q = 0, A_K = 2, A_V = 4, A_GY = 6;
+struct APl {
+    static constexpr int XN = 8, DO = XN + 2, ONE = XN + 4, X1 = XN + 5, PLANES = XN + 6;
 };
 constexpr int B_QKV = 0, B_DO = 48, B_DXN = 64, B_WACC = 80, B_COLS = 128;       // TMEM columns
 
-template <bool EMB>
 struct AttnBwdSm {
-    unsigned char pl[APl<EMB>::PLANES * PLANE];
+    unsigned char pl[APl::PLANES * PLANE];
     unsigned char ones0[128];            // A operand of the bias GEMM step: one core matrix (1, 1, 0, ...) for every row group (SBO = 0)
     unsigned char bq[48 * 16];           // B(n, k) chunk 0 of the bias step: k = 0 -> hi(bqkv[n]), k = 1 -> lo (q rows pre-scaled)
     unsigned char wqkv[48 * 32];         // B(n = o, k = c) = qkv.weight[n][k] (q rows pre-scaled)       qkv = xn Wqkv^T
@@ -877,18 +879,18 @@ struct AttnBwdSm {
 };
 
 template <int WD, int WH, int WW, bool EMB>
-__global__ void __launch_bounds__(NT, EMB ? 2 : 3)
+__global__ void __launch_bounds__(NT, 3)
 swin_attn_bwd_umma_kernel(const void* __restrict__ x, const __nv_bfloat16* __restrict__ gy, __nv_bfloat16* __restrict__ gx,
                           const float* __restrict__ params, int64_t pstride, const int* __restrict__ rel_index,
                           float* __restrict__ partials, Geom g) {
     constexpr int G = WD * WH * WW;
     constexpr int PART = ATT_PART_W + NH * G * G;
     constexpr int DBS = bns(G), DBW = NH * G * DBS;            // per-warp bias-gradient table (conflict-free 8-byte RMW, see bns / tcol)
-    constexpr int WM = EMB ? 128 : 64;                         // rows of the weight-gradient GEMM
+    constexpr int WM = 64;                                     // rows of the weight-gradient GEMM
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int A_XN = APl<EMB>::XN, A_DO = APl<EMB>::DO, A_ONE = APl<EMB>::ONE, A_X1 = APl<EMB>::X1;
-    AttnBwdSm<EMB>& S = *reinterpret_cast<AttnBwdSm<EMB>*>(smem_raw);
-    float* Bn = reinterpret_cast<float*>(smem_raw + sizeof(AttnBwdSm<EMB>));  // [NH][G][bns(G)]
+    constexpr int A_XN = APl::XN, A_DO = APl::DO, A_ONE = APl::ONE, A_X1 = APl::X1;
+    AttnBwdSm& S = *reinterpret_cast<AttnBwdSm*>(smem_raw);
+    float* Bn = reinterpret_cast<float*>(smem_raw + sizeof(AttnBwdSm));  // [NH][G][bns(G)]
     float* dBw_all = Bn + NH * G * bns(G);                                  // [4 warps][DBW]
     const int v = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* P = params + (int64_t)v * pstride;
@@ -912,7 +914,6 @@ swin_attn_bwd_umma_kernel(const void* __restrict__ x, const __nv_bfloat16* __res
     const uint32_t pl = smem_u32(S.pl);
     sts128(pl + A_ONE * PLANE + tid * 16, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
     sts128(pl + A_X1 * PLANE + tid * 16, 0u, 0u, 0u, 0u);
-    if (EMB) { sts128(pl + A_GE * PLANE + tid * 16, 0u, 0u, 0u, 0u); sts128(pl + (A_GE + 1) * PLANE + tid * 16, 0u, 0u, 0u, 0u); }
     if (tid < 8) { sts128(smem_u32(S.ones0) + tid * 16, 0x3F803F80u, 0u, 0u, 0u); sts128(smem_u32(S.zq) + tid * 16, 0u, 0u, 0u, 0u); }
     for (int e = tid; e < 4 * DBW; e += NT) dBw_all[e] = 0.f;
     stage_bias_pad<G>(Bn, P, rel_index);
@@ -989,7 +990,6 @@ swin_attn_bwd_umma_kernel(const void* __restrict__ x, const __nv_bfloat16* __res
             sts128(pl + (A_XN + 1) * PLANE + my_row, pn[4], pn[5], pn[6], pn[7]);
             sts128(pl + A_GY * PLANE + my_row, pg[0], pg[1], pg[2], pg[3]);
             sts128(pl + (A_GY + 1) * PLANE + my_row, pg[4], pg[5], pg[6], pg[7]);
-            if (EMB) sts128(pl + A_X1 * PLANE + my_row, pk(xin, 1.f), 0u, 0u, 0u);
         }
         proxy_fence();
         tc_fence_before();
@@ -1191,13 +1191,11 @@ swin_attn_bwd_umma_kernel(const void* __restrict__ x, const __nv_bfloat16* __res
 #pragma unroll
             for (int s3 = 0; s3 < 3; ++s3)
                 umma_ss(tmem + B_DXN, make_desc(pl + 2 * s3 * PLANE, PLANE, 128), make_desc(smem_u32(S.wqt) + s3 * 512, 16 * 16, 128), idesc(128, 16), s3 > 0 ? 1u : 0u);
-            if (!EMB) {
-                // weight gradients: D[64 x 48] += [dq | dk | dv | g_y]^T [xn | o | 1 | 0] over the tile's 128 tokens (MN-major views)
+            // weight gradients: D[64 x 48] += [dq | dk | dv | g_y]^T [xn | o | 1 | 0] over the tile's 128 tokens (MN-major views)
 #pragma unroll
-                for (int s8 = 0; s8 < 8; ++s8)
-                    umma_ss(tmem + B_WACC, make_desc(pl + s8 * 256, 128, PLANE), make_desc(pl + A_XN * PLANE + s8 * 256, 128, PLANE),
-                            idesc(WM, 48, 1, 1), (first && s8 == 0) ? 0u : 1u);
-            }
+            for (int s8 = 0; s8 < 8; ++s8)
+                umma_ss(tmem + B_WACC, make_desc(pl + s8 * 256, 128, PLANE), make_desc(pl + A_XN * PLANE + s8 * 256, 128, PLANE),
+                        idesc(WM, 48, 1, 1), (first && s8 == 0) ? 0u : 1u);
             umma_commit(mma_bar);
         }
         mbar_wait(mma_bar, n_commit++ & 1u);
@@ -1220,48 +1218,11 @@ swin_attn_bwd_umma_kernel(const void* __restrict__ x, const __nv_bfloat16* __res
             m1 *= (1.f / 16.f); m2 *= (1.f / 16.f);
 #pragma unroll
             for (int c = 0; c < 16; ++c) d[c] = gyr[c] + rstd * (d[c] - m1 - xn[c] * m2);
-            if (EMB) {
-                // the block input IS the embedding output: LayerNorm backward of the embedding here; its weight / bias sums
-                // (sum_t ge x, sum_t ge) come out of the weight-gradient GEMM below (rows 64..79 against the (x, 1) columns)
-                float e[16], en[16];
-#pragma unroll
-                for (int c = 0; c < 16; ++c) e[c] = __ldg(ew + c) * xin + __ldg(eb + c);
-                const float rs = ln_row(e, en);
-                float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-                for (int c = 0; c < 16; ++c) { s1 += d[c]; s2 += d[c] * en[c]; }
-                s1 *= (1.f / 16.f); s2 *= (1.f / 16.f);
-                uint32_t pe[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float g0 = tk.valid ? rs * (d[2 * i] - s1 - en[2 * i] * s2) : 0.f;
-                    const float g1 = tk.valid ? rs * (d[2 * i + 1] - s1 - en[2 * i + 1] * s2) : 0.f;
-                    pe[i] = pk(g0, g1);
-                }
-                sts128(pl + A_GE * PLANE + my_row, pe[0], pe[1], pe[2], pe[3]);
-                sts128(pl + (A_GE + 1) * PLANE + my_row, pe[4], pe[5], pe[6], pe[7]);
-            } else if (tk.valid) {
+            if (tk.valid) {
                 uint32_t po_[8];
                 pack16(d, po_);
                 st8u(gx + tk.off, po_);
             }
-        }
-        if (EMB) {
-            // with the fused embedding the weight-gradient GEMM also needs g_e (written above): D[128 x 48] += [dq | dk | dv | g_y | g_e | ..]^T
-            // [xn | o | 1 | (x, 1)], one more round
-            proxy_fence();
-            tc_fence_before();
-            __syncthreads();
-            if (tid == 0) {
-                tc_fence_after();
-#pragma unroll
-                for (int s8 = 0; s8 < 8; ++s8)
-                    umma_ss(tmem + B_WACC, make_desc(pl + s8 * 256, 128, PLANE), make_desc(pl + A_XN * PLANE + s8 * 256, 128, PLANE),
-                            idesc(WM, 48, 1, 1), (first && s8 == 0) ? 0u : 1u);
-                umma_commit(mma_bar);
-            }
-            mbar_wait(mma_bar, n_commit++ & 1u);        // the planes are rewritten by the next tile
-            tc_fence_after();
         }
         first = false;
         tc_fence_before();
@@ -1271,26 +1232,7 @@ swin_attn_bwd_umma_kernel(const void* __restrict__ x, const __nv_bfloat16* __res
     tc_fence_after();
     float* part = partials + ((int64_t)v * gridDim.x + blockIdx.x) * PART;
     const bool any = (int)blockIdx.x < n_tiles;
-    if (EMB) {
-        // M = 128: row m in lane m.  rows 0..47 = dq | dk | dv, 48..63 = g_y, 64..79 = g_e
-        float w[16], o2[16], b[16];
-        tmem_ld16(tlane + B_WACC, w);
-        tmem_ld16(tlane + B_WACC + 16, o2);
-        tmem_ld16(tlane + B_WACC + 32, b);
-        if (tid < 48) {
-#pragma unroll
-            for (int c = 0; c < 16; ++c) part[tid * C + c] = any ? w[c] : 0.f;
-            part[3 * C * C + tid] = any ? b[0] : 0.f;
-        } else if (tid < 64) {
-#pragma unroll
-            for (int c = 0; c < 16; ++c) part[3 * C * C + 3 * C + (tid - 48) * C + c] = any ? o2[c] : 0.f;
-            part[3 * C * C + 3 * C + C * C + tid - 48] = any ? b[0] : 0.f;
-        } else if (tid < 80 && g.emb_gpart != nullptr) {
-            float* pe = g.emb_gpart + ((int64_t)v * gridDim.x + blockIdx.x) * 32;
-            pe[tid - 64] = any ? b[8] : 0.f;            // column 40: sum_t g_e[c] x
-            pe[16 + tid - 64] = any ? b[9] : 0.f;       // column 41: sum_t g_e[c]
-        }
-    } else {
+    {
         // M = 64: row m in lane (m % 16) + 32 (m / 16): warp w holds rows 16 w .. 16 w + 15 in its lanes 0..15
         float w[16], o2[16], b[16];
         tmem_ld16(tlane + B_WACC, w);
@@ -1321,20 +1263,70 @@ swin_attn_bwd_umma_kernel(const void* __restrict__ x, const __nv_bfloat16* __res
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(B_COLS) : "memory");
 }
 
+// Backward of the patch embedding e[c] = w[c] x + b[c] -> LayerNorm (PatchEmbed3D, Swin_3D.py:473-491, in_chans == 1) from the bf16
+// gradient of its tokens: per token g_e = LN-backward(g_tok), then d w[c] += g_e[c] x, d b[c] += g_e[c].  One streaming pass over
+// g_tok (32 B / token) and the raw input (4 B / token); per-thread fp32 sums, fixed-order CTA reduction, partials [V][nblk][32]
+// for embed_grad_finalize_kernel.  grid = (nblk, V).
+__global__ void __launch_bounds__(256)
+embed_bwd_tokens_kernel(const __nv_bfloat16* __restrict__ gtok, const float* __restrict__ xraw, const float* __restrict__ emb_w,
+                        const float* __restrict__ emb_b, float* __restrict__ part, int N, int V, int thw) {
+    __shared__ float red[8][32];
+    const int v = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float w[16], b[16], gw[16], gb[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) { w[c] = __ldg(emb_w + v * C + c); b[c] = __ldg(emb_b + v * C + c); gw[c] = 0.f; gb[c] = 0.f; }
+    for (int n = 0; n < N; ++n) {
+        const int64_t img = (int64_t)(n * V + v) * thw;
+        for (int t = blockIdx.x * 256 + tid; t < thw; t += gridDim.x * 256) {
+            const float x = __ldg(xraw + img + t);
+            uint32_t pg[8];
+            ldg_row16(gtok + (img + t) * C, pg);
+            float d[16], e[16], en[16];
+            unpack16(pg, d);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) e[c] = w[c] * x + b[c];
+            const float rs = ln_row(e, en);
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) { s1 += d[c]; s2 += d[c] * en[c]; }
+            s1 *= (1.f / 16.f); s2 *= (1.f / 16.f);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                const float ge = rs * (d[c] - s1 - en[c] * s2);
+                gw[c] += ge * x; gb[c] += ge;
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+        float a = gw[c], q = gb[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+        if (lane == 0) { red[warp][c] = a; red[warp][16 + c] = q; }
+    }
+    __syncthreads();
+    if (tid < 32) {
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a += red[k][tid];
+        part[((int64_t)v * gridDim.x + blockIdx.x) * 32 + tid] = a;
+    }
+}
+
 template <int WD, int WH, int WW>
 int launch_attn_bwd(const idee_swin_desc* d, const Geom& g, const void* x, __nv_bfloat16* gx, const float* params,
                     const int* rel_index, float* gparams, float* part_attn, float* part_mlp, float* part_emb, int per_v, int per_v_mlp,
                     cudaStream_t st) {
     constexpr int G = WD * WH * WW;
-    const size_t smem_e = sizeof(AttnBwdSm<true>) + sizeof(float) * 5 * NH * G * bns(G);
-    const size_t smem = sizeof(AttnBwdSm<false>) + sizeof(float) * 5 * NH * G * bns(G);
+    const size_t smem = sizeof(AttnBwdSm) + sizeof(float) * 5 * NH * G * bns(G);
     if (g.emb_x) {
-        Geom ge = g;
-        ge.emb_gpart = d->embed_gw ? part_emb : nullptr;
-        IDEE_CUDA(cudaFuncSetAttribute(swin_attn_bwd_umma_kernel<WD, WH, WW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e), "swin_attn_bwd(umma)");
-        swin_attn_bwd_umma_kernel<WD, WH, WW, true><<<dim3(per_v, d->V), NT, smem_e, st>>>(x, gx, gx, params, d->param_stride, rel_index, part_attn, ge);
+        IDEE_CUDA(cudaFuncSetAttribute(swin_attn_bwd_umma_kernel<WD, WH, WW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "swin_attn_bwd(umma)");
+        swin_attn_bwd_umma_kernel<WD, WH, WW, true><<<dim3(per_v, d->V), NT, smem, st>>>(x, gx, gx, params, d->param_stride, rel_index, part_attn, g);
         IDEE_LAUNCH_CHECK("swin_attn_bwd(umma,embed)");
         if (d->embed_gw) {
+            // gx now holds the gradient w.r.t. the embedded tokens: one streaming pass turns it into d{embed w, b}
+            embed_bwd_tokens_kernel<<<dim3(per_v, d->V), 256, 0, st>>>(gx, g.emb_x, g.emb_w, g.emb_b, part_emb, d->N, d->V, d->T * d->H * d->W);
+            IDEE_LAUNCH_CHECK("embed_bwd_tokens");
             embed_grad_finalize_kernel<<<d->V, 32, 0, st>>>(part_emb, per_v, d->embed_gw, d->embed_gb);
             IDEE_LAUNCH_CHECK("embed_grad_finalize");
         }

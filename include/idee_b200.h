@@ -61,9 +61,10 @@ typedef struct {
      * NULL) and never has to exist in HBM.  gx of idee_swin_block_bwd is still the gradient w.r.t. those tokens
      * (feed it to idee_embed_ln_bwd). */
     const float* embed_x; const float* embed_w; const float* embed_b;
-    /* backward, optional: when embed_gw / embed_gb ([V][16] each) are given, the attention half also runs the embedding's
-     * backward (LayerNorm backward + weight / bias reduction) on the token gradient it holds in registers and writes the two
-     * gradients here; gx is then only used as the scratch between the two halves and its final content is unspecified. */
+    /* backward, optional: when embed_gw / embed_gb ([V][16] each) are given, the call also runs the embedding's backward
+     * (LayerNorm backward + weight / bias reduction) and writes the two gradients here.  act_dtype 1: gx receives the gradient
+     * w.r.t. the embedded tokens and one streaming pass over it produces the two gradients; act_dtype 0: the attention half does
+     * it on the token gradient in registers and the final content of gx is unspecified. */
     float* embed_gw; float* embed_gb;
     /* act_dtype 1 (precision 1 only) selects the tcgen05 / TMEM kernels (swin_umma.cuh): the saved activation ymid and the token
      * gradients gout / gx are then bf16 (__nv_bfloat16* passed through the float* parameters), out_bf16 must be NULL, gx must not
