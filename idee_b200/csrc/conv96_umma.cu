@@ -1,5 +1,7 @@
-// Warp-specialised tcgen05 / TMEM implicit-GEMM kernel for the one dense contraction of the path: the 96 -> 96 classifier
-// convolution Conv3d(96, 96, (2,3,3), stride (2,1,1), pad (0,1,1)) (classifier/CNN_3D.py:84), forward and data gradient.
+// Warp-specialised tcgen05 / TMEM implicit-GEMM kernel for the dense contractions of the joint classifier head: the 96 -> 96
+// convolution Conv3d(96, 96, (2,3,3), stride (2,1,1), pad (0,1,1)) (classifier/CNN_3D.py:84), forward and data gradient, and the
+// head's first convolution on the 16-channel plane image of the rank-1 form of z_q (16 -> 96 forward, 96 -> 16 data gradient;
+// template parameters GI / GO = gather-input / output channels; their 18 weight taps stay resident in shared memory).
 //
 // Roles (288 threads):  warps 0-7 load the halo of tile i+1 (fp32 HBM -> bf16 shared memory) and then drain the accumulator of
 // tile i (tcgen05.ld -> bias / ReLU / mask -> fp32 stores; warp w owns TMEM lanes 32 (w & 3).. and columns 48 (w >> 2)..);
@@ -20,11 +22,8 @@
 namespace conv96u {
 
 constexpr int TR = 16, TC = 8, HR = TR + 2, HC = TC + 2;
-constexpr int CI = 96, CO = 96, KC = CI / 8;
-constexpr int NB = 4;                                  // weight-tap ring depth
-constexpr int B_TAP = CO * CI * 2;                     // 18432 bytes per tap, canonical [kc][ng][8][16 B]
-constexpr int B_LBO = (CO / 8) * 128, B_SBO = 128;
-constexpr int TMEM_COLS = 256;
+constexpr int NB = 4;                                  // weight-tap ring depth (96 -> 96 only)
+constexpr int B_SBO = 128;
 constexpr int NLOAD = 256;                             // loader / epilogue threads (warps 0-7); warp 8 = weights + MMA issue
 constexpr int MMA_WARP = NLOAD / 32, NTHREADS = NLOAD + 32;
 enum { U_FWD = 0, U_DGRAD = 1 };
@@ -47,8 +46,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
-// instruction descriptor: D = F32, A = B = BF16, both K-major, N = 96, M = 128
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CO >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128
+__host__ __device__ constexpr uint32_t idesc_n(int N) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -66,9 +65,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     }
 }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -99,33 +98,43 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// fp32 reference-layout weights [Co][Ci][18] -> bf16 canonical K-major tiles, one per forward tap:
+// fp32 reference-layout weights [Co][Ci][18] -> bf16 canonical K-major tiles, one per forward tap (GI = k extent, GO = n extent):
 //   wB[ft][kc][ng][r][e] = B(n = ng*8 + r, k = kc*8 + e);  forward: B(n,k) = W[n][k][ft];  dgrad: B(n,k) = W[k][n][ft]
-__global__ void prep96_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wB, int dgrad) {
-    const int total = 18 * CO * CI;
+__global__ void prep96_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wB, int dgrad, int GI, int GO) {
+    const int total = 18 * GO * GI, KC = GI / 8, ci_ref = dgrad ? GO : GI;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
         const int el = e & 7, r = (e >> 3) & 7;
         int q = e >> 6;
-        const int ng = q % (CO / 8); q /= (CO / 8);
+        const int ng = q % (GO / 8); q /= (GO / 8);
         const int kc = q % KC;
         const int ft = q / KC;
         const int n = ng * 8 + r, k = kc * 8 + el;
         const int fo = dgrad ? k : n, fc = dgrad ? n : k;
-        wB[e] = __float2bfloat16(w[((int64_t)fo * CI + fc) * 18 + ft]);
+        wB[e] = __float2bfloat16(w[((int64_t)fo * ci_ref + fc) * 18 + ft]);
     }
 }
 
-template <int MODE>
+// GI: gather-input channels (K per tap), GO: output channels (N).  RESIDENT (GI * GO small): all 18 weight taps are copied to
+// shared memory once per CTA; otherwise they stream through an NB-deep cp.async ring.
+template <int MODE, int GI, int GO>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv96_umma_kernel(UP p) {
+    constexpr int CI = GI, CO = GO, KC = CI / 8;
+    constexpr int B_TAP = CO * CI * 2;                     // bytes per tap, canonical [kc][ng][8][16 B]
+    constexpr int B_LBO = (CO / 8) * 128;
+    constexpr bool RESIDENT = 18 * B_TAP <= 64 * 1024;
+    constexpr int B_SLOTS = RESIDENT ? 18 : NB;
+    constexpr int TMEM_COLS = 2 * CO > 128 ? 256 : (2 * CO > 64 ? 128 : (2 * CO > 32 ? 64 : 32));
+    constexpr uint32_t IDESC = idesc_n(CO);
+    constexpr int CW = CO >= 32 ? CO / 2 : CO;             // accumulator columns drained by one epilogue warp
     constexpr int KTIN = MODE == U_FWD ? 2 : 1, NT = MODE == U_FWD ? 18 : 9;
     constexpr int NPX = KTIN * HR * HC;                   // halo pixels
     constexpr int CHUNK = NPX * 16 + 16;                  // plane stride (+16: a pixel's 12 chunks land in different banks)
     constexpr int HALO = KC * CHUNK;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* halo = smem_raw;                                        // [2][KC][NPX][16 B]
-    unsigned char* Bring = smem_raw + 2 * ((HALO + 127) / 128 * 128);      // [NB][B_TAP]
-    float* bias_s = reinterpret_cast<float*>(Bring + NB * B_TAP);          // [96]
+    unsigned char* Bring = smem_raw + 2 * ((HALO + 127) / 128 * 128);      // [B_SLOTS][B_TAP]
+    float* bias_s = reinterpret_cast<float*>(Bring + B_SLOTS * B_TAP);     // [CO]
     uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + CO);             // full[2] | accdone[2] | accfree[2] | bslot[NB]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + NB);
     constexpr int HALO_PAD = (HALO + 127) / 128 * 128;
@@ -148,8 +157,12 @@ conv96_umma_kernel(UP p) {
     const uint32_t tmem_base = *tmem_slot;
 
     // contiguous tile range of this CTA
-    const uint32_t per_cta = (p.total_tiles + gridDim.x - 1) / gridDim.x;
-    const uint32_t first = blockIdx.x * per_cta, last = min(p.total_tiles, first + per_cta);
+    // data gradient with an even number of output slices: tiles 2k and 2k+1 of a CTA (t fastest) are the two time parities of one
+    // (n, t >> 1, h0, w0) and read the SAME halo -> one halo load per pair (pshift = 1), CTA ranges start on even tiles
+    const uint32_t pshift = (MODE == U_DGRAD && (p.To & 1) == 0) ? 1u : 0u;
+    uint32_t per_cta = (p.total_tiles + gridDim.x - 1) / gridDim.x;
+    if (pshift) per_cta = (per_cta + 1) & ~1u;
+    const uint32_t first = min(p.total_tiles, blockIdx.x * per_cta), last = min(p.total_tiles, first + per_cta);
     const uint32_t ntile = last > first ? last - first : 0;
     struct Tile { int n, t, h0, w0; };
     auto decode = [&](uint32_t tile) {
@@ -162,13 +175,47 @@ conv96_umma_kernel(UP p) {
     };
 
     if (warp == MMA_WARP) {
-        // ================= weight ring + MMA issue =================
-        const uint32_t total_taps = ntile * NT;
-        auto tap_ft = [&](uint32_t g) -> int {                          // forward-tap index of global tap g
-            const uint32_t it = g / NT; const int j = (int)(g - it * NT);
+        // ================= weights (resident or ring) + MMA issue =================
+        auto tile_ft = [&](uint32_t it, int j) -> int {                 // forward-tap index of tap j of this CTA's tile it
             if (MODE == U_FWD) return j;
             const Tile c = decode(first + it);
             return (c.t & 1) * 9 + (2 - j / 3) * 3 + (2 - j % 3);
+        };
+        if (RESIDENT) {
+            const uint4* src = reinterpret_cast<const uint4*>(p.wB);
+            for (int i = lane; i < 18 * B_TAP / 16; i += 32)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(Bring) + i * 16), "l"(src + i) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            for (uint32_t it = 0; it < ntile; ++it) {
+                const uint32_t b = it & 1;
+                const uint32_t q = it >> pshift, hb = q & 1;              // halo load index / buffer of this tile
+                mbar_wait(bar_full + 8 * hb, (q >> 1) & 1u);
+                if (it >= 2) mbar_wait(bar_free + 8 * b, ((it >> 1) - 1) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    const uint64_t adesc0 = make_desc(smem_u32(halo) + hb * HALO_PAD, CHUNK, HC * 16);
+                    const uint32_t dcol = tmem_base + b * CO;
+#pragma unroll 1
+                    for (int j = 0; j < NT; ++j) {
+                        const int kt = MODE == U_FWD ? j / 9 : 0, kh = (j / 3) % 3, kw = j % 3;
+                        const uint64_t ad = adesc0 + (uint64_t)((kt * HR + kh) * HC + kw);
+                        const uint64_t bd = make_desc(smem_u32(Bring) + tile_ft(it, j) * B_TAP, B_LBO, B_SBO);
+#pragma unroll
+                        for (int ks = 0; ks < CI / 16; ++ks)
+                            umma_bf16(dcol, ad + (uint64_t)(ks * 2 * (CHUNK / 16)), bd + (uint64_t)(ks * 2 * (B_LBO / 16)), IDESC, (j > 0 || ks > 0) ? 1u : 0u);
+                    }
+                    umma_commit(bar_done + 8 * b);
+                }
+                __syncwarp();
+            }
+        } else {
+        const uint32_t total_taps = ntile * NT;
+        auto tap_ft = [&](uint32_t g) -> int {                          // forward-tap index of global tap g
+            const uint32_t it = g / NT;
+            return tile_ft(it, (int)(g - it * NT));
         };
         auto load_B = [&](uint32_t g) {
             const uint4* src = reinterpret_cast<const uint4*>(p.wB + (size_t)tap_ft(g) * CO * CI);
@@ -184,10 +231,11 @@ conv96_umma_kernel(UP p) {
         uint32_t g = 0;
         for (uint32_t it = 0; it < ntile; ++it) {
             const uint32_t b = it & 1;
-            mbar_wait(bar_full + 8 * b, (it >> 1) & 1u);                                   // halo of this tile is in shared memory
+            const uint32_t q = it >> pshift, hb = q & 1;                                   // halo load index / buffer of this tile
+            mbar_wait(bar_full + 8 * hb, (q >> 1) & 1u);                                   // halo of this tile is in shared memory
             if (it >= 2) mbar_wait(bar_free + 8 * b, ((it >> 1) - 1) & 1u);                // accumulator b has been drained
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint64_t adesc0 = make_desc(smem_u32(halo) + b * HALO_PAD, CHUNK, HC * 16);
+            const uint64_t adesc0 = make_desc(smem_u32(halo) + hb * HALO_PAD, CHUNK, HC * 16);
             const uint32_t dcol = tmem_base + b * CO;
 #pragma unroll 1
             for (int j = 0; j < NT; ++j, ++g) {
@@ -201,7 +249,7 @@ conv96_umma_kernel(UP p) {
                     const uint64_t bd = make_desc(smem_u32(Bring) + (g % NB) * B_TAP, B_LBO, B_SBO);
 #pragma unroll
                     for (int ks = 0; ks < CI / 16; ++ks)
-                        umma_bf16(dcol, ad + (uint64_t)(ks * 2 * (CHUNK / 16)), bd + (uint64_t)(ks * 2 * (B_LBO / 16)), (j > 0 || ks > 0) ? 1u : 0u);
+                        umma_bf16(dcol, ad + (uint64_t)(ks * 2 * (CHUNK / 16)), bd + (uint64_t)(ks * 2 * (B_LBO / 16)), IDESC, (j > 0 || ks > 0) ? 1u : 0u);
                     umma_commit(bar_slot + 8 * (g % NB));                                   // slot is free when these MMAs have read it
                     if (j == NT - 1) umma_commit(bar_done + 8 * b);                         // ... and the accumulator is complete
                 }
@@ -216,6 +264,7 @@ conv96_umma_kernel(UP p) {
                     asm volatile("cp.async.commit_group;" ::: "memory");
                 }
             }
+        }
         }
     } else {
         // ================= halo loads (one tile ahead) + epilogue =================
@@ -252,27 +301,29 @@ conv96_umma_kernel(UP p) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core
             mbar_arrive(bar_full + 8 * buf);
         };
-        // warp w drains TMEM lanes 32 (w & 3).. (its 4 tile rows) x columns 48 (w >> 2)..  For the data gradient the ReLU mask
-        // of the 48 channels is fetched as a bit mask BEFORE waiting for the accumulator, so its latency hides behind the MMAs.
+        // warp w drains TMEM lanes 32 (w & 3).. (its 4 tile rows) x columns CW (w >> 2)..  (CO = 16: warps 0-3 take all 16 columns,
+        // warps 4-7 only load).  For the data gradient the ReLU mask of the CW channels is fetched as a bit mask BEFORE waiting
+        // for the accumulator, so its latency hides behind the MMAs.
         const int quad = warp & 3, chalf = warp >> 2;
+        const bool drains = CO >= 32 || chalf == 0;
         auto out_offset = [&](const Tile& c, bool& pix_ok) -> int64_t {
             const int r = quad * 4 + (lane >> 3), cc = lane & 7;
             const int h = c.h0 + r, w = c.w0 + cc;
             pix_ok = h < p.Ho && w < p.Wo;
-            return c.n * p.out_sn + (int64_t)(c.t * p.out_st + h * p.out_sh + w * p.out_sw) + chalf * 48;
+            return c.n * p.out_sn + (int64_t)(c.t * p.out_st + h * p.out_sh + w * p.out_sw) + chalf * CW;
         };
         auto relu_bits = [&](const Tile& c, uint32_t (&bits)[2]) {
             bits[0] = bits[1] = 0xFFFFFFFFu;
-            if (!p.relu_src) return;
+            if (!p.relu_src || !drains) return;
             bool pix_ok;
             const int64_t o = out_offset(c, pix_ok);
             if (!pix_ok) return;
-            float a[48];
+            float a[CW];
 #pragma unroll
-            for (int i = 0; i < 6; ++i) ldg8f(a + 8 * i, p.relu_src + o + 8 * i);
+            for (int i = 0; i < CW / 8; ++i) ldg8f(a + 8 * i, p.relu_src + o + 8 * i);
             uint32_t b0 = 0u, b1 = 0u;
 #pragma unroll
-            for (int i = 0; i < 48; ++i) {
+            for (int i = 0; i < CW; ++i) {
                 const uint32_t m = a[i] > 0.f ? 1u : 0u;
                 if (i < 32) b0 |= m << i; else b1 |= m << (i - 32);
             }
@@ -283,14 +334,15 @@ conv96_umma_kernel(UP p) {
             const int64_t o = out_offset(c, pix_ok);
             float* orow = p.out + o;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
+            for (int k = 0; k < CW / 16; ++k) {
+                if (!drains) break;
                 float v[16];
-                tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * CO + chalf * 48 + 16 * k, v);
+                tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * CO + chalf * CW + 16 * k, v);
                 if (pix_ok) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const int ch = 16 * k + i;                               // channel inside this warp's 48
-                        float ov = v[i] + bias_s[chalf * 48 + ch];
+                        const int ch = 16 * k + i;                               // channel inside this warp's CW
+                        float ov = v[i] + bias_s[chalf * CW + ch];
                         if (p.relu) ov = fmaxf(ov, 0.f);
                         if (!((ch < 32 ? bits[0] >> ch : bits[1] >> (ch - 32)) & 1u)) ov = 0.f;
                         v[i] = ov;
@@ -305,8 +357,12 @@ conv96_umma_kernel(UP p) {
         if (ntile > 0) { nxt = decode(first); load_halo(nxt, 0); }
         for (uint32_t it = 0; it < ntile; ++it) {
             cur = nxt;
-            // buffer (it+1)&1 was read by tile it-1, whose completion these warps waited for before its epilogue
-            if (it + 1 < ntile) { nxt = decode(first + it + 1); load_halo(nxt, (it + 1) & 1); }
+            // the halo buffer of load q+1 was last read by load q-1's tiles, whose completion these warps waited for before their
+            // epilogues; with paired tiles (pshift) only the even tile of a pair loads
+            if (it + 1 < ntile) {
+                nxt = decode(first + it + 1);
+                if (((it + 1) & pshift) == 0) load_halo(nxt, ((it + 1) >> pshift) & 1);
+            }
             uint32_t bits[2];
             relu_bits(cur, bits);
             mbar_wait(bar_done + 8 * (it & 1), (it >> 1) & 1u);
@@ -328,13 +384,40 @@ bool conv96_umma_eligible(const idee_conv_desc* d) {
            d->out_cpg == 6 && d->x_sw == 96 && d->y_sw == 96 && !d->x_dtype && !d->y_dtype && !d->gx_dtype;
 }
 
-size_t conv96_umma_workspace_bytes() { return sizeof(__nv_bfloat16) * 18 * CO * CI; }
+// the joint head's first conv on the 16-channel plane image (16 -> 96): forward and data gradient with resident weights
+bool conv16to96_umma_eligible(const idee_conv_desc* d) {
+    return d->umma96 && d->precision >= 1 && !d->proj && d->Cin == 16 && d->Cout == 96 && d->V == 1 && d->Vw == 1 && d->in_cpg == 1 &&
+           d->out_cpg == 6 && d->x_sw == 16 && d->y_sw == 96 && !d->x_dtype && !d->y_dtype && !d->gx_dtype;
+}
+
+size_t conv96_umma_workspace_bytes() { return sizeof(__nv_bfloat16) * 18 * 96 * 96; }
+
+template <int MODE, int GI, int GO>
+static int launch96(const UP& p, int64_t total, cudaStream_t st) {
+    constexpr int ktin = MODE == U_FWD ? 2 : 1;
+    constexpr size_t halo_pad = ((size_t)(GI / 8) * (ktin * HR * HC * 16 + 16) + 127) / 128 * 128;
+    constexpr size_t b_tap = (size_t)GO * GI * 2;
+    constexpr size_t slots = 18 * b_tap <= 64 * 1024 ? 18 : NB;
+    constexpr size_t smem = 2 * halo_pad + slots * b_tap + GO * 4 + (6 + NB) * 8 + 16;
+    constexpr int tmem_cols = 2 * GO > 128 ? 256 : (2 * GO > 64 ? 128 : (2 * GO > 32 ? 64 : 32));
+    auto kern = conv96_umma_kernel<MODE, GI, GO>;
+    IDEE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "conv3d(umma96)");
+    // two co-resident CTAs per SM where shared memory and TMEM columns allow it (the light 16-channel variants): one CTA's
+    // epilogue stores overlap the other's loads
+    const int per_sm = (2 * (smem + 1024) <= 227 * 1024 && 2 * tmem_cols <= 512) ? 2 : 1;
+    int64_t grid = (int64_t)idee_num_sms() * per_sm;
+    if (grid > total) grid = total;
+    kern<<<(unsigned)grid, NTHREADS, smem, st>>>(p);
+    IDEE_LAUNCH_CHECK("conv3d(umma96)");
+    return 0;
+}
 
 // dgrad == 0: y = conv(x) (+bias, ReLU);  dgrad == 1: gx = conv^T(gy) (optional ReLU mask)
 int conv96_umma_run(const idee_conv_desc* d, int dgrad, const float* in, const float* w, const float* bias, const float* relu_src,
                     float* out, void* ws, cudaStream_t st) {
     __nv_bfloat16* wB = (__nv_bfloat16*)ws;
-    prep96_weights_kernel<<<256, 256, 0, st>>>(w, wB, dgrad);
+    const int GI = dgrad ? d->Cout : d->Cin, GO = dgrad ? d->Cin : d->Cout;      // gather-input / output channels of this pass
+    prep96_weights_kernel<<<(18 * GI * GO + 255) / 256, 256, 0, st>>>(w, wB, dgrad, GI, GO);
     IDEE_LAUNCH_CHECK("conv3d(umma96) prep");
     UP p{};
     p.in = in; p.out = out; p.bias = bias; p.relu_src = relu_src; p.wB = wB; p.N = d->N;
@@ -357,18 +440,6 @@ int conv96_umma_run(const idee_conv_desc* d, int dgrad, const float* in, const f
     const int64_t total = (int64_t)d->N * p.To * p.tiles_h * p.tiles_w;
     IDEE_REQUIRE(total < (1ll << 31), "conv3d(umma96): too many tiles");
     p.total_tiles = (uint32_t)total;
-    const int ktin = dgrad ? 1 : 2;
-    const size_t halo_pad = ((size_t)KC * (ktin * HR * HC * 16 + 16) + 127) / 128 * 128;
-    const size_t smem = 2 * halo_pad + (size_t)NB * B_TAP + CO * 4 + (6 + NB) * 8 + 16;
-    int64_t grid = idee_num_sms();
-    if (grid > total) grid = total;
-    if (!dgrad) {
-        IDEE_CUDA(cudaFuncSetAttribute(conv96_umma_kernel<U_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "conv3d(umma96)");
-        conv96_umma_kernel<U_FWD><<<(unsigned)grid, NTHREADS, smem, st>>>(p);
-    } else {
-        IDEE_CUDA(cudaFuncSetAttribute(conv96_umma_kernel<U_DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "conv3d(umma96)");
-        conv96_umma_kernel<U_DGRAD><<<(unsigned)grid, NTHREADS, smem, st>>>(p);
-    }
-    IDEE_LAUNCH_CHECK("conv3d(umma96)");
-    return 0;
+    if (d->Cin == 96) return dgrad ? launch96<U_DGRAD, 96, 96>(p, total, st) : launch96<U_FWD, 96, 96>(p, total, st);
+    return dgrad ? launch96<U_DGRAD, 96, 16>(p, total, st) : launch96<U_FWD, 16, 96>(p, total, st);
 }

@@ -1541,6 +1541,7 @@ int prep(const idee_conv_desc* d, const float* w, uint2* wfrag, const Plan& pl, 
 
 // warp-specialised tcgen05 / TMEM path for the 96 -> 96 classifier conv (conv96_umma.cu)
 bool conv96_umma_eligible(const idee_conv_desc* d);
+bool conv16to96_umma_eligible(const idee_conv_desc* d);
 size_t conv96_umma_workspace_bytes();
 int conv96_umma_run(const idee_conv_desc* d, int dgrad, const float* in, const float* w, const float* bias, const float* relu_src,
                     float* out, void* ws, cudaStream_t st);
@@ -1558,7 +1559,7 @@ static bool umma16_dgrad_eligible(const idee_conv_desc* d) {
 static size_t max_sz(size_t a, size_t b) { return a > b ? a : b; }
 
 size_t conv_tc_fwd_workspace_bytes(const idee_conv_desc* d) {
-    if (conv96_umma_eligible(d)) return conv96_umma_workspace_bytes();
+    if (conv96_umma_eligible(d) || conv16to96_umma_eligible(d)) return conv96_umma_workspace_bytes();
     size_t b = make_plan(d->proj ? PROJ_FWD : CLS_FWD, d->Cin, d->Cout, d->Vw).wfrag_bytes;
     if (umma16_fwd_eligible(d)) b = max_sz(b, conv16_umma_workspace_bytes(d->Vw));
     return b;
@@ -1568,7 +1569,7 @@ size_t conv_tc_dgrad_workspace_bytes(const idee_conv_desc* d) {
     if (d->proj && d->Cout == 1 && d->Cin == 16) return 0;           // scalar-gradient kernels: no staging
     if (!d->proj && d->Cout == 1 && (d->Cin == 16 || d->Cin == 96) && !d->x_dtype && !d->y_dtype && !d->gx_dtype &&
         d->x_sw == d->Cin && d->in_cpg * 16 == d->Cin && d->y_sw == 1) return 0;
-    if (conv96_umma_eligible(d)) return conv96_umma_workspace_bytes();
+    if (conv96_umma_eligible(d) || conv16to96_umma_eligible(d)) return conv96_umma_workspace_bytes();
     size_t b = make_plan(d->proj ? PROJ_DGRAD_PAD : CLS_DGRAD, d->Cout, d->Cin, d->Vw).wfrag_bytes;
     if (umma16_dgrad_eligible(d)) b = max_sz(b, conv16_umma_workspace_bytes(d->Vw));
     b = (b + 255) / 256 * 256;
@@ -1577,7 +1578,7 @@ size_t conv_tc_dgrad_workspace_bytes(const idee_conv_desc* d) {
 }
 
 int conv_tc_fwd(const idee_conv_desc* d, const void* x, const float* w, const float* b, void* y, void* ws, cudaStream_t st) {
-    if (conv96_umma_eligible(d)) return conv96_umma_run(d, 0, (const float*)x, w, b, nullptr, (float*)y, ws, st);
+    if (conv96_umma_eligible(d) || conv16to96_umma_eligible(d)) return conv96_umma_run(d, 0, (const float*)x, w, b, nullptr, (float*)y, ws, st);
     if (umma16_fwd_eligible(d)) {
         const int64_t is[5] = {d->x_sn, d->x_sv, d->x_st, d->x_sh, d->x_sw}, os[5] = {d->y_sn, d->y_sv, d->y_st, d->y_sh, d->y_sw};
         return conv16_umma_run(0, d->y_dtype, x, w, b, y, ws, d->N, d->V, d->Vw, d->Ti, d->Hi, d->Wi, d->To, d->Ho, d->Wo, is, os,
@@ -1600,7 +1601,8 @@ int conv_tc_fwd(const idee_conv_desc* d, const void* x, const float* w, const fl
 }
 
 int conv_tc_dgrad(const idee_conv_desc* d, const void* gy, const float* w, const void* relu_src, void* gx, void* ws, cudaStream_t st) {
-    if (conv96_umma_eligible(d)) return conv96_umma_run(d, 1, (const float*)gy, w, nullptr, (const float*)relu_src, (float*)gx, ws, st);
+    if (conv96_umma_eligible(d) || conv16to96_umma_eligible(d))
+        return conv96_umma_run(d, 1, (const float*)gy, w, nullptr, (const float*)relu_src, (float*)gx, ws, st);
     if (!d->proj && d->Cout == 1 && (d->Cin == 16 || d->Cin == 96) && !d->x_dtype && !d->y_dtype && !d->gx_dtype &&
         d->x_sw == d->Cin && d->in_cpg * 16 == d->Cin && d->y_sw == 1) {
         // logit conv: scalar gradient plane in, 9-tap stencil per input slice on the tensor cores

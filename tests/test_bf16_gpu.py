@@ -149,9 +149,10 @@ def test_tcgen05_classifier_conv_matches_mma_sync_and_oracle(dims):
 
 
 @pytest.mark.parametrize("dims", [(2, 4, 20, 28), (1, 8, 37, 19), (1, 3, 9, 8)])
-def test_tcgen05_joint_conv1_weight_gradient(dims):
-    """Weight / bias gradient of the joint head's first conv on the 16-channel plane image (16 -> 96, conv96_wgrad_umma.cu with all 18
-    taps in one CTA) against the mma.sync kernel and torch autograd (fp32 conv3d on CPU)."""
+def test_tcgen05_joint_conv1(dims):
+    """The joint head's first conv on the 16-channel plane image (16 -> 96): forward and data gradient (conv96_umma.cu with resident
+    weights) and weight / bias gradient (conv96_wgrad_umma.cu, all 18 taps in one CTA) against the mma.sync kernels and torch
+    autograd (fp32 conv3d on CPU)."""
     import torch.nn.functional as F
     from idee_b200 import _lib, ops
     N, T, H, W = dims
@@ -163,8 +164,8 @@ def test_tcgen05_joint_conv1_weight_gradient(dims):
     w = torch.randn(1, 96, 16, 2, 3, 3) * 0.1
     b = torch.randn(1, 96)
     g = torch.randn(N, 1, To, H, W, 96)
-    wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
-    want = F.conv3d(x[:, 0].permute(0, 4, 1, 2, 3), wr[0], br[0], stride=(2, 1, 1), padding=(0, 1, 1)).permute(0, 2, 3, 4, 1).unsqueeze(1)
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    want = F.conv3d(xr[:, 0].permute(0, 4, 1, 2, 3), wr[0], br[0], stride=(2, 1, 1), padding=(0, 1, 1)).permute(0, 2, 3, 4, 1).unsqueeze(1)
     (want * g).sum().backward()
     old96 = _lib.UMMA96
     outs = {}
@@ -173,16 +174,18 @@ def test_tcgen05_joint_conv1_weight_gradient(dims):
             _lib.set_umma96(on)
             xc = x.cuda().requires_grad_(True)
             wc, bc = w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
-            y = ops.conv3d_cl(xc, wc, bc, False, False, cin_real=7)
+            y = ops.conv3d_cl(xc, wc, bc, False, False, cin_real=7)     # no ReLU: a sign flip of a near-zero output would move whole gradient terms
             (y * g.cuda()).sum().backward()
-            outs[on] = (wc.grad.cpu(), bc.grad.cpu())
+            outs[on] = (y.detach().cpu(), xc.grad.cpu()[..., :7], wc.grad.cpu(), bc.grad.cpu())
     finally:
         _lib.set_umma96(old96)
     for on in (False, True):
-        assert rel_err(outs[on][0][:, :, :7], wr.grad[:, :, :7]) < TOL
-        assert rel_err(outs[on][1], br.grad) < TOL
-    assert rel_err(outs[True][0], outs[False][0]) < 2e-3
-    assert rel_err(outs[True][1], outs[False][1]) < 2e-3
+        assert rel_err(outs[on][0], want.detach()) < TOL
+        assert rel_err(outs[on][1], xr.grad[..., :7]) < TOL             # channels >= cin_real carry no gradient by contract
+        assert rel_err(outs[on][2][:, :, :7], wr.grad[:, :, :7]) < TOL
+        assert rel_err(outs[on][3], br.grad) < TOL
+    for i in range(4):
+        assert rel_err(outs[True][i], outs[False][i]) < 2e-3
 
 
 @pytest.mark.parametrize("shape", [(2, 3, 4, 21, 37), (1, 6, 8, 40, 48)])
