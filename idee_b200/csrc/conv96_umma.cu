@@ -3,9 +3,9 @@
 // head's first convolution on the 16-channel plane image of the rank-1 form of z_q (16 -> 96 forward, 96 -> 16 data gradient;
 // template parameters GI / GO = gather-input / output channels; their 18 weight taps stay resident in shared memory).
 //
-// Roles (288 threads):  warps 0-7 load the halo of tile i+1 (fp32 HBM -> bf16 shared memory) and then drain the accumulator of
-// tile i (tcgen05.ld -> bias / ReLU / mask -> fp32 stores; warp w owns TMEM lanes 32 (w & 3).. and columns 48 (w >> 2)..);
-// warp 8 streams the per-tap weight matrices through a cp.async ring and issues the tcgen05.mma of tile i.
+// Roles (416 threads):  warps 0-7 load halos (fp32 HBM -> bf16 shared memory) up to two loads ahead; warps 8-11 drain the
+// accumulator of tile i (tcgen05.ld -> bias / ReLU / mask -> fp32 stores; warp w owns TMEM lanes 32 (w & 3)..); warp 12 streams
+// the per-tap weight matrices through a cp.async ring (or keeps all taps resident) and issues the tcgen05.mma of tile i.
 // Two halo buffers and two TMEM accumulators (2 x 96 columns) let the three stages run concurrently; all hand-offs are mbarriers (halo full, accumulator done via tcgen05.commit, accumulator drained, weight slot
 // free) -- there is no CTA-wide barrier in the steady state.
 //
@@ -24,8 +24,9 @@ namespace conv96u {
 constexpr int TR = 16, TC = 8, HR = TR + 2, HC = TC + 2;
 constexpr int NB = 4;                                  // weight-tap ring depth (96 -> 96 only)
 constexpr int B_SBO = 128;
-constexpr int NLOAD = 256;                             // loader / epilogue threads (warps 0-7); warp 8 = weights + MMA issue
-constexpr int MMA_WARP = NLOAD / 32, NTHREADS = NLOAD + 32;
+constexpr int NLOAD = 256;                             // loader threads (warps 0-7)
+constexpr int NEPI = 128;                              // epilogue threads (warps 8-11: warp & 3 = TMEM lane quadrant)
+constexpr int MMA_WARP = (NLOAD + NEPI) / 32, NTHREADS = NLOAD + NEPI + 32;     // warp 12 = weights + MMA issue
 enum { U_FWD = 0, U_DGRAD = 1 };
 
 struct UP {
@@ -126,7 +127,6 @@ conv96_umma_kernel(UP p) {
     constexpr int B_SLOTS = RESIDENT ? 18 : NB;
     constexpr int TMEM_COLS = 2 * CO > 128 ? 256 : (2 * CO > 64 ? 128 : (2 * CO > 32 ? 64 : 32));
     constexpr uint32_t IDESC = idesc_n(CO);
-    constexpr int CW = CO >= 32 ? CO / 2 : CO;             // accumulator columns drained by one epilogue warp
     constexpr int KTIN = MODE == U_FWD ? 2 : 1, NT = MODE == U_FWD ? 18 : 9;
     constexpr int NPX = KTIN * HR * HC;                   // halo pixels
     constexpr int CHUNK = NPX * 16 + 16;                  // plane stride (+16: a pixel's 12 chunks land in different banks)
@@ -135,11 +135,12 @@ conv96_umma_kernel(UP p) {
     unsigned char* halo = smem_raw;                                        // [2][KC][NPX][16 B]
     unsigned char* Bring = smem_raw + 2 * ((HALO + 127) / 128 * 128);      // [B_SLOTS][B_TAP]
     float* bias_s = reinterpret_cast<float*>(Bring + B_SLOTS * B_TAP);     // [CO]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + CO);             // full[2] | accdone[2] | accfree[2] | bslot[NB]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + NB);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + CO);             // full[2] | accdone[2] | accfree[2] | bslot[NB] | halofree[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + NB);
     constexpr int HALO_PAD = (HALO + 127) / 128 * 128;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t bar_full = smem_u32(&bars[0]), bar_done = smem_u32(&bars[2]), bar_free = smem_u32(&bars[4]), bar_slot = smem_u32(&bars[6]);
+    const uint32_t bar_full = smem_u32(&bars[0]), bar_done = smem_u32(&bars[2]), bar_free = smem_u32(&bars[4]), bar_slot = smem_u32(&bars[6]),
+                   bar_hfree = smem_u32(&bars[6 + NB]);
 
     if (tid < CO) bias_s[tid] = p.bias ? p.bias[tid] : 0.f;
     if (warp == MMA_WARP) {
@@ -147,7 +148,9 @@ conv96_umma_kernel(UP p) {
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(bar_full + 8 * i, NLOAD); mbar_init(bar_done + 8 * i, 1); mbar_init(bar_free + 8 * i, NLOAD); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar_full + 8 * i, NLOAD); mbar_init(bar_done + 8 * i, 1); mbar_init(bar_free + 8 * i, NEPI); mbar_init(bar_hfree + 8 * i, 1);
+        }
         for (int i = 0; i < NB; ++i) mbar_init(bar_slot + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -208,6 +211,7 @@ conv96_umma_kernel(UP p) {
                             umma_bf16(dcol, ad + (uint64_t)(ks * 2 * (CHUNK / 16)), bd + (uint64_t)(ks * 2 * (B_LBO / 16)), IDESC, (j > 0 || ks > 0) ? 1u : 0u);
                     }
                     umma_commit(bar_done + 8 * b);
+                    if (((it + 1) & pshift) == 0 || it + 1 == ntile) umma_commit(bar_hfree + 8 * hb);   // last tile that reads this halo
                 }
                 __syncwarp();
             }
@@ -251,7 +255,10 @@ conv96_umma_kernel(UP p) {
                     for (int ks = 0; ks < CI / 16; ++ks)
                         umma_bf16(dcol, ad + (uint64_t)(ks * 2 * (CHUNK / 16)), bd + (uint64_t)(ks * 2 * (B_LBO / 16)), IDESC, (j > 0 || ks > 0) ? 1u : 0u);
                     umma_commit(bar_slot + 8 * (g % NB));                                   // slot is free when these MMAs have read it
-                    if (j == NT - 1) umma_commit(bar_done + 8 * b);                         // ... and the accumulator is complete
+                    if (j == NT - 1) {
+                        umma_commit(bar_done + 8 * b);                                      // ... and the accumulator is complete
+                        if (((it + 1) & pshift) == 0 || it + 1 == ntile) umma_commit(bar_hfree + 8 * hb);   // last reader of this halo
+                    }
                 }
                 __syncwarp();
                 // refill the slot released by tap g-1 (its MMAs precede tap g's in the pipe, so this wait overlaps tap g)
@@ -266,8 +273,8 @@ conv96_umma_kernel(UP p) {
             }
         }
         }
-    } else {
-        // ================= halo loads (one tile ahead) + epilogue =================
+    } else if (warp < NLOAD / 32) {
+        // ================= halo loads: load q = tiles (q << pshift).., buffer q & 1, as soon as the MMAs of load q-2 are done =================
         auto load_halo = [&](const Tile& c, int buf) {
             unsigned char* dst = halo + buf * HALO_PAD;
             const float* in_n = p.in + c.n * p.in_sn;
@@ -301,50 +308,60 @@ conv96_umma_kernel(UP p) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core
             mbar_arrive(bar_full + 8 * buf);
         };
-        // warp w drains TMEM lanes 32 (w & 3).. (its 4 tile rows) x columns CW (w >> 2)..  (CO = 16: warps 0-3 take all 16 columns,
-        // warps 4-7 only load).  For the data gradient the ReLU mask of the CW channels is fetched as a bit mask BEFORE waiting
-        // for the accumulator, so its latency hides behind the MMAs.
-        const int quad = warp & 3, chalf = warp >> 2;
-        const bool drains = CO >= 32 || chalf == 0;
+        const uint32_t nload = (ntile + pshift) >> pshift;
+        for (uint32_t q = 0; q < nload; ++q) {
+            if (q >= 2) mbar_wait(bar_hfree + 8 * (q & 1), ((q >> 1) - 1) & 1u);     // the MMAs that read this buffer (load q-2) are done
+            load_halo(decode(first + (q << pshift)), (int)(q & 1));
+        }
+    } else {
+        // ================= epilogue: warp w drains TMEM lanes 32 (w & 3).. (its 4 tile rows) x all CO columns =================
+        // For the data gradient the ReLU mask of the pixel's channels is fetched as a bit mask BEFORE waiting for the accumulator,
+        // so its latency hides behind the MMAs.
+        const int quad = warp & 3;
         auto out_offset = [&](const Tile& c, bool& pix_ok) -> int64_t {
             const int r = quad * 4 + (lane >> 3), cc = lane & 7;
             const int h = c.h0 + r, w = c.w0 + cc;
             pix_ok = h < p.Ho && w < p.Wo;
-            return c.n * p.out_sn + (int64_t)(c.t * p.out_st + h * p.out_sh + w * p.out_sw) + chalf * CW;
+            return c.n * p.out_sn + (int64_t)(c.t * p.out_st + h * p.out_sh + w * p.out_sw);
         };
-        auto relu_bits = [&](const Tile& c, uint32_t (&bits)[2]) {
-            bits[0] = bits[1] = 0xFFFFFFFFu;
-            if (!p.relu_src || !drains) return;
+        constexpr int NW = (CO + 31) / 32;
+        auto relu_bits = [&](const Tile& c, uint32_t (&bits)[NW]) {
+#pragma unroll
+            for (int k = 0; k < NW; ++k) bits[k] = 0xFFFFFFFFu;
+            if (!p.relu_src) return;
             bool pix_ok;
             const int64_t o = out_offset(c, pix_ok);
             if (!pix_ok) return;
-            float a[CW];
 #pragma unroll
-            for (int i = 0; i < CW / 8; ++i) ldg8f(a + 8 * i, p.relu_src + o + 8 * i);
-            uint32_t b0 = 0u, b1 = 0u;
+            for (int k = 0; k < NW; ++k) {
+                constexpr int full = 32;
+                const int nch = CO - 32 * k < full ? CO - 32 * k : full;
+                float a[32];
 #pragma unroll
-            for (int i = 0; i < CW; ++i) {
-                const uint32_t m = a[i] > 0.f ? 1u : 0u;
-                if (i < 32) b0 |= m << i; else b1 |= m << (i - 32);
+                for (int i = 0; i < 4; ++i)
+                    if (8 * i < nch) ldg8f(a + 8 * i, p.relu_src + o + 32 * k + 8 * i);
+                uint32_t b0 = 0u;
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (i < nch) b0 |= (a[i] > 0.f ? 1u : 0u) << i;
+                bits[k] = b0;
             }
-            bits[0] = b0; bits[1] = b1;
         };
-        auto epilogue = [&](const Tile& c, int acc, const uint32_t (&bits)[2]) {
+        auto epilogue = [&](const Tile& c, int acc, const uint32_t (&bits)[NW]) {
             bool pix_ok;
             const int64_t o = out_offset(c, pix_ok);
             float* orow = p.out + o;
 #pragma unroll
-            for (int k = 0; k < CW / 16; ++k) {
-                if (!drains) break;
+            for (int k = 0; k < CO / 16; ++k) {
                 float v[16];
-                tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * CO + chalf * CW + 16 * k, v);
+                tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * CO + 16 * k, v);
                 if (pix_ok) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const int ch = 16 * k + i;                               // channel inside this warp's CW
-                        float ov = v[i] + bias_s[chalf * CW + ch];
+                        const int ch = 16 * k + i;
+                        float ov = v[i] + bias_s[ch];
                         if (p.relu) ov = fmaxf(ov, 0.f);
-                        if (!((ch < 32 ? bits[0] >> ch : bits[1] >> (ch - 32)) & 1u)) ov = 0.f;
+                        if (!((bits[ch >> 5] >> (ch & 31)) & 1u)) ov = 0.f;
                         v[i] = ov;
                     }
                     st8f(orow + 16 * k, v); st8f(orow + 16 * k + 8, v + 8);
@@ -353,17 +370,9 @@ conv96_umma_kernel(UP p) {
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(bar_free + 8 * acc);
         };
-        Tile cur{}, nxt{};
-        if (ntile > 0) { nxt = decode(first); load_halo(nxt, 0); }
         for (uint32_t it = 0; it < ntile; ++it) {
-            cur = nxt;
-            // the halo buffer of load q+1 was last read by load q-1's tiles, whose completion these warps waited for before their
-            // epilogues; with paired tiles (pshift) only the even tile of a pair loads
-            if (it + 1 < ntile) {
-                nxt = decode(first + it + 1);
-                if (((it + 1) & pshift) == 0) load_halo(nxt, ((it + 1) >> pshift) & 1);
-            }
-            uint32_t bits[2];
+            const Tile cur = decode(first + it);
+            uint32_t bits[NW];
             relu_bits(cur, bits);
             mbar_wait(bar_done + 8 * (it & 1), (it >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -398,14 +407,12 @@ static int launch96(const UP& p, int64_t total, cudaStream_t st) {
     constexpr size_t halo_pad = ((size_t)(GI / 8) * (ktin * HR * HC * 16 + 16) + 127) / 128 * 128;
     constexpr size_t b_tap = (size_t)GO * GI * 2;
     constexpr size_t slots = 18 * b_tap <= 64 * 1024 ? 18 : NB;
-    constexpr size_t smem = 2 * halo_pad + slots * b_tap + GO * 4 + (6 + NB) * 8 + 16;
+    constexpr size_t smem = 2 * halo_pad + slots * b_tap + GO * 4 + (8 + NB) * 8 + 16;
     constexpr int tmem_cols = 2 * GO > 128 ? 256 : (2 * GO > 64 ? 128 : (2 * GO > 32 ? 64 : 32));
     auto kern = conv96_umma_kernel<MODE, GI, GO>;
     IDEE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "conv3d(umma96)");
-    // two co-resident CTAs per SM where shared memory and TMEM columns allow it (the light 16-channel variants): one CTA's
-    // epilogue stores overlap the other's loads
-    const int per_sm = (2 * (smem + 1024) <= 227 * 1024 && 2 * tmem_cols <= 512) ? 2 : 1;
-    int64_t grid = (int64_t)idee_num_sms() * per_sm;
+    (void)tmem_cols;
+    int64_t grid = (int64_t)idee_num_sms();               // one persistent CTA per SM (416 threads x 118 registers)
     if (grid > total) grid = total;
     kern<<<(unsigned)grid, NTHREADS, smem, st>>>(p);
     IDEE_LAUNCH_CHECK("conv3d(umma96)");
