@@ -239,8 +239,11 @@ def entry_kernels(name):
     G = int(m.group(1)) * int(m.group(2)) * int(m.group(3))
     if "fwd" in name:
         return [f"swin_fwd_tc_kernel<{w},{emb}>", f"swin_fwd_umma_kernel<{w},{emb}>"]
-    return ["swin_mlp_bwd_tc_kernel", f"swin_attn_bwd_tc_kernel<{w},{emb}>", "swin_mlp_bwd_umma_kernel",
-            f"swin_attn_bwd_umma_kernel<{w},{emb}>", f"swin_grad_finalize_kernel<{G}>"]
+    ks = ["swin_mlp_bwd_tc_kernel", f"swin_attn_bwd_tc_kernel<{w},{emb}>", "swin_mlp_bwd_umma_kernel",
+          f"swin_attn_bwd_umma_kernel<{w},{emb}>", f"swin_grad_sum_kernel<{G}>", f"swin_grad_finalize_kernel<{G}>"]
+    if emb == "1":
+        ks += ["embed_bwd_tokens_kernel", "embed_grad_finalize_kernel"]
+    return ks
 
 
 def ncu_traffic(name):

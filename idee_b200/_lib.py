@@ -178,7 +178,7 @@ def set_precision(mode: str) -> None:
     PRECISION = mode
 
 
-LAUNCHES = {"embed_ln_fwd": 1, "embed_ln_bwd": 2, "swin_block_fwd": 1, "swin_block_bwd": 3, "conv3d_fwd": 1, "conv3d_dgrad": 1,
+LAUNCHES = {"embed_ln_fwd": 1, "embed_ln_bwd": 2, "swin_block_fwd": 1, "swin_block_bwd": 4, "conv3d_fwd": 1, "conv3d_dgrad": 1,
             "conv3d_wgrad": 2, "conv3d_bwd": 3, "conv3d_bwd_bf16": 5, "conv3d_fwd_bf16": 2, "conv3d_dgrad_bf16": 3, "conv3d_wgrad_bf16": 2, "lfq_fwd": 2, "lfq_fwd_eval": 1, "lfq_bwd": 2, "bce_loss_fwd": 4, "anomaly_l1_fwd": 2,
             "anomaly_l1_bwd": 1, "anomaly_rank1_fwd": 2, "anomaly_rank1_bwd": 1, "rank1_planes_fwd": 1,
             "rank1_planes_bwd": 1, "adam_step": 1, "adam_step_state": 2, "ln_act_res_fwd": 1, "ln_act_res_bwd": 2, "lfqk_fwd": 2, "lfqk_fwd_eval": 1, "lfqk_bwd": 2}

@@ -190,9 +190,9 @@ class SwinBlock(torch.autograd.Function):
             return out
         x = _f32c(x)
         d = _swin_desc(x, window, shift, rpb_rows, scale, pack, heads, hidden)
-        # want_bf16 == "only": the caller reads nothing but the bf16 copy, so the fp32 result is not written (the returned fp32
-        # tensor only routes the gradient and is left uninitialised)
-        out = torch.empty_like(x)
+        # want_bf16 == "only": the caller reads nothing but the bf16 copy, so the fp32 result is not written; the returned fp32
+        # tensor only routes the gradient and is poisoned with NaN so that an accidental consumer cannot read stale memory
+        out = torch.full_like(x, float("nan")) if want_bf16 == "only" else torch.empty_like(x)
         need_bwd = any(ctx.needs_input_grad)
         ymid = torch.empty_like(x) if need_bwd else None
         out16 = torch.empty_like(x, dtype=torch.bfloat16) if want_bf16 else None

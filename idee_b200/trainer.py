@@ -7,7 +7,10 @@ checkpoints are unchanged) and all gradients in a second flat buffer, so a step 
 
 The batch is sharded over ranks; each rank evaluates the reference loss on its local shard and gradients are averaged,
 i.e. the result equals the mean of per-shard reference steps.  Batch statistics inside the
-loss (LFQ codebook entropy, BCE class weights, anomaly normaliser) are per-shard, as they are per-replica in the reference.
+loss (LFQ codebook entropy, BCE class weights, anomaly normaliser) are per-shard.  In the reference only the LFQ entropy is per
+replica: the BCE class weights and the anomaly normaliser are computed on the gathered batch outside the DataParallel model
+(train_synthetic.py:182-201), so an N-rank step here is the mean of N single-rank reference steps on the shards, not one
+reference step on the global batch; a shard needs both classes present in its extreme mask (as the reference's full batch does).
 """
 from __future__ import annotations
 
