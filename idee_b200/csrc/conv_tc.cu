@@ -1023,6 +1023,133 @@ proj_wgrad_scalar_kernel(WP p) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Forward of the 16 -> 1 proj conv (the encoder's last conv folded with the quantiser's project_in) marching along t:
+//   s[p] = b + sum_tap sum_c h[clamp(p + tap - 1)][c] w[c][tap]
+// With ONE output channel an implicit GEMM over (pixels x taps) wastes 7 of every 8 MMA columns and re-reads the halo once per
+// tap.  Here the contraction over the 16 channels is done ONCE per input pixel for all 27 taps, Y[q][tap] = sum_c h[q][c] w[c][tap]
+// (one ldmatrix + four HMMAs per 16 pixels: M = pixels, N = 32 tap slots, K = 16), and the conv is the 27-term gather
+// s[p] = sum_tap Y[clamp(p + tap - 1)][tap] from a ring of three Y planes in shared memory (tap-major, plane stride 180: the
+// fragment stores and the gathers are bank-conflict free).  A CTA walks columns (n, v, h-tile, w-tile) and marches t: every
+// input plane is fetched once and contracted once, and serves the three outputs t-1, t, t+1 (replicate padding along t = the
+// same Y plane again; along h / w = clamped halo addresses).
+// ------------------------------------------------------------------------------------------------------------------
+struct PFS {
+    const __nv_bfloat16* in; float* out; const float* w; const float* bias;
+    int N, V, Vw, T, H, W, relu;
+    int64_t in_sn, in_sv, out_sn, out_sv;
+    int in_st, in_sh, in_sw, out_st, out_sh, out_sw;
+    int tiles_h, tiles_w;
+    uint32_t total_cols;
+    FastDiv fd_tw, fd_th, fd_v;
+};
+
+constexpr int PFS_NPX = HH * HW_, PFS_CPA = 24;
+constexpr int PFS_HALO = PFS_NPX * PFS_CPA * 2;                 // bytes of one bf16 halo plane [180][24 halves]
+constexpr int PFS_Y = 27 * PFS_NPX * 4;                         // bytes of one Y plane [27 taps][180] fp32
+constexpr int PFS_SMEM = 2 * PFS_HALO + 3 * PFS_Y + 2 * 16 * 24;    // + slack rows: the last m-tile reads 12 rows past the plane
+
+__global__ void __launch_bounds__(128)
+proj_fwd_scalar_kernel(PFS p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __nv_bfloat16* halo = reinterpret_cast<__nv_bfloat16*>(smem_raw);                       // [2][180][24]
+    float* Y = reinterpret_cast<float*>(smem_raw + 2 * PFS_HALO + 2 * 16 * 24);             // [3][27][180]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t per = (p.total_cols + gridDim.x - 1) / gridDim.x;
+    const uint32_t first = min(p.total_cols, blockIdx.x * per), last = min(p.total_cols, first + per);
+    struct Col { int n, v, h0, w0; };
+    auto decode = [&](uint32_t col) {
+        Col c;
+        uint32_t q, r;
+        p.fd_tw.divmod(col, q, r); c.w0 = (int)r * TW;
+        p.fd_th.divmod(q, q, r); c.h0 = (int)r * TH;
+        p.fd_v.divmod(q, q, r); c.v = (int)r; c.n = (int)q;
+        return c;
+    };
+    // halo plane t of column c -> buffer buf: 180 pixels x 2 chunks of 16 bytes, replicate clamp along h / w
+    auto issue = [&](const Col& c, int t, int buf) {
+        const __nv_bfloat16* img = p.in + c.n * p.in_sn + c.v * p.in_sv + (int64_t)t * p.in_st;
+        const uint32_t dst = smem_u32(halo) + buf * PFS_HALO;
+        for (int e = tid; e < PFS_NPX * 2; e += 128) {
+            const int q = e >> 1, ch = e & 1, hh = q / HW_, ww = q - hh * HW_;
+            const int hi = min(max(c.h0 - 1 + hh, 0), p.H - 1), wi = min(max(c.w0 - 1 + ww, 0), p.W - 1);
+            cp_async16_u32(dst + q * (PFS_CPA * 2) + ch * 16, img + (hi * p.in_sh + wi * p.in_sw) + ch * 8, 16);
+        }
+        cp_async_commit();
+    };
+    const int a_pix = (lane & 7) + ((lane >> 3) & 1) * 8, a_koff = (lane >> 4) * 8;
+    const int pr = tid / TW, pc = tid % TW, gbase = pr * HW_ + pc;                          // this thread's output pixel of the tile
+    int cur_wset = -1;
+    uint32_t bf[4][2];
+    float bias_v = 0.f;
+    if (first < last) issue(decode(first), 0, 0);
+    int buf = 0;
+    for (uint32_t col = first; col < last; ++col) {
+        const Col c = decode(col);
+        const int wset = p.Vw == 1 ? 0 : c.v;
+        if (wset != cur_wset) {                       // B fragments: B[k = c][n = tap] = w[wset][0][c][tap]
+            const float* wv = p.w + (int64_t)wset * 16 * 27;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const int tap = nt * 8 + lane / 4, c0 = 2 * (lane % 4);
+                auto wt = [&](int cc) { return tap < 27 ? __ldg(wv + cc * 27 + tap) : 0.f; };
+                bf[nt][0] = pack_bf16(wt(c0), wt(c0 + 1));
+                bf[nt][1] = pack_bf16(wt(c0 + 8), wt(c0 + 9));
+            }
+            bias_v = p.bias ? __ldg(p.bias + wset) : 0.f;
+            cur_wset = wset;
+        }
+        const bool pix_ok = c.h0 + pr < p.H && c.w0 + pc < p.W;
+        float* out_px = p.out + c.n * p.out_sn + c.v * p.out_sv + (int64_t)((c.h0 + pr) * p.out_sh + (c.w0 + pc) * p.out_sw);
+        for (int tp = 0; tp < p.T; ++tp, buf ^= 1) {
+            cp_async_wait<0>();
+            __syncthreads();                          // plane tp landed; the previous step's gathers are done with the ring slot
+            if (tp + 1 < p.T) issue(c, tp + 1, buf ^ 1);
+            else if (col + 1 < last) issue(decode(col + 1), 0, buf ^ 1);
+            // ---- Y(tp)[tap][q] for the 180 halo pixels: 12 m-tiles of 16 pixels, 3 per warp ----
+            const __nv_bfloat16* hp = halo + buf * (PFS_HALO / 2);
+            float* Yp = Y + (tp % 3) * (27 * PFS_NPX);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const int m0 = (warp * 3 + i) * 16;
+                uint32_t a[4];
+                ldsm_x4(a, hp + (m0 + a_pix) * PFS_CPA + a_koff);
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                    mma_bf16(acc, a, bf[nt][0], bf[nt][1]);
+                    const int tap = nt * 8 + 2 * (lane % 4), q0 = m0 + lane / 4;
+                    if (tap < 27) {
+                        if (q0 < PFS_NPX) Yp[tap * PFS_NPX + q0] = acc[0];
+                        if (q0 + 8 < PFS_NPX) Yp[tap * PFS_NPX + q0 + 8] = acc[2];
+                    }
+                    if (tap + 1 < 27) {
+                        if (q0 < PFS_NPX) Yp[(tap + 1) * PFS_NPX + q0] = acc[1];
+                        if (q0 + 8 < PFS_NPX) Yp[(tap + 1) * PFS_NPX + q0 + 8] = acc[3];
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- outputs whose three planes are complete: t = tp - 1, and t = T - 1 on the last plane ----
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                const int t = pass == 0 ? tp - 1 : tp;
+                if (pass == 0 ? tp < 1 : tp != p.T - 1) continue;
+                float s = bias_v;
+#pragma unroll
+                for (int kt = 0; kt < 3; ++kt) {
+                    const int tq = min(max(t + kt - 1, 0), p.T - 1);
+                    const float* yp = Y + (tq % 3) * (27 * PFS_NPX) + kt * 9 * PFS_NPX + gbase;
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) s += yp[k * PFS_NPX + (k / 3) * HW_ + (k % 3)];
+                }
+                if (p.relu) s = fmaxf(s, 0.f);
+                if (pix_ok) out_px[(int64_t)t * p.out_st] = s;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // Data gradient AND weight gradient of the 16 -> 1 proj conv in one pass (proj_wgrad_scalar_kernel + proj_dgrad_scalar_tc_kernel
 // on the same tile): the scalar-gradient halo is fetched once, its im2col G[q][tap] is built once and feeds both GEMMs,
 //   dW[c][tap] += sum_q h[q][c] G[q][tap]   (persistent register accumulators, partials in conv.cu's layout)
@@ -1583,6 +1710,27 @@ int conv_tc_fwd(const idee_conv_desc* d, const void* x, const float* w, const fl
         const int64_t is[5] = {d->x_sn, d->x_sv, d->x_st, d->x_sh, d->x_sw}, os[5] = {d->y_sn, d->y_sv, d->y_st, d->y_sh, d->y_sw};
         return conv16_umma_run(0, d->y_dtype, x, w, b, y, ws, d->N, d->V, d->Vw, d->Ti, d->Hi, d->Wi, d->To, d->Ho, d->Wo, is, os,
                                d->relu, st);
+    }
+    if (d->proj && d->Cin == 16 && d->Cout == 1 && d->x_dtype == 1 && d->y_dtype == 0 && d->x_sw == 16 && d->y_sw == 1 &&
+        (int64_t)d->Ti * d->x_st + (int64_t)d->Hi * d->x_sh + (int64_t)d->Wi * d->x_sw < (1ll << 31) &&
+        (int64_t)d->To * d->y_st + (int64_t)d->Ho * d->y_sh + (int64_t)d->Wo * d->y_sw < (1ll << 31)) {
+        // folded 16 -> 1 conv on bf16 storage: one channel contraction per input pixel for all 27 taps, t-marching gather
+        PFS q{};
+        q.in = (const __nv_bfloat16*)x; q.out = (float*)y; q.w = w; q.bias = b;
+        q.N = d->N; q.V = d->V; q.Vw = d->Vw; q.T = d->Ti; q.H = d->Hi; q.W = d->Wi; q.relu = d->relu;
+        q.in_sn = d->x_sn; q.in_sv = d->x_sv; q.in_st = (int)d->x_st; q.in_sh = (int)d->x_sh; q.in_sw = (int)d->x_sw;
+        q.out_sn = d->y_sn; q.out_sv = d->y_sv; q.out_st = (int)d->y_st; q.out_sh = (int)d->y_sh; q.out_sw = (int)d->y_sw;
+        q.tiles_h = (d->Hi + TH - 1) / TH; q.tiles_w = (d->Wi + TW - 1) / TW;
+        const int64_t cols = (int64_t)d->N * d->V * q.tiles_h * q.tiles_w;
+        IDEE_REQUIRE(cols < (1ll << 31), "conv3d_fwd(proj 16->1): too many tile columns");
+        q.total_cols = (uint32_t)cols;
+        q.fd_tw = make_fastdiv(q.tiles_w); q.fd_th = make_fastdiv(q.tiles_h); q.fd_v = make_fastdiv(d->V);
+        IDEE_CUDA(cudaFuncSetAttribute(proj_fwd_scalar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PFS_SMEM), "conv3d_fwd(proj 16->1)");
+        int64_t grid = (int64_t)idee_num_sms() * 3;
+        if (grid > cols) grid = cols;
+        proj_fwd_scalar_kernel<<<(unsigned)grid, 128, PFS_SMEM, st>>>(q);
+        IDEE_LAUNCH_CHECK("conv3d_fwd(proj 16->1)");
+        return 0;
     }
     const int mode = d->proj ? PROJ_FWD : CLS_FWD;
     const Plan pl = make_plan(mode, d->Cin, d->Cout, d->Vw);
