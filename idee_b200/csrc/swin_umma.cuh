@@ -151,14 +151,25 @@ __device__ __forceinline__ uint32_t gelu_f16x2(float x0, float x1) {
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // LayerNorm(16, eps 1e-5, no affine) of one token held by the thread; returns rstd
+// (sums in four interleaved partial accumulators: a 16-long dependent FADD / FFMA chain is 64 cycles of latency that four warps
+// per scheduler cannot hide)
+__device__ __forceinline__ float sum16(const float* x) {
+    float a = x[0] + x[4], b = x[1] + x[5], c = x[2] + x[6], d = x[3] + x[7];
+    a += x[8]; b += x[9]; c += x[10]; d += x[11];
+    a += x[12]; b += x[13]; c += x[14]; d += x[15];
+    return (a + b) + (c + d);
+}
+__device__ __forceinline__ float dot16(const float* x, const float* y) {
+    float a = x[0] * y[0], b = x[1] * y[1], c = x[2] * y[2], d = x[3] * y[3];
+#pragma unroll
+    for (int i = 4; i < 16; i += 4) { a = fmaf(x[i], y[i], a); b = fmaf(x[i + 1], y[i + 1], b); c = fmaf(x[i + 2], y[i + 2], c); d = fmaf(x[i + 3], y[i + 3], d); }
+    return (a + b) + (c + d);
+}
 __device__ __forceinline__ float ln_row(const float* x, float* xn) {
-    float mu = 0.f;
+    const float mu = sum16(x) * (1.f / 16.f);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) mu += x[i];
-    mu *= (1.f / 16.f);
-    float var = 0.f;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) { const float d = x[i] - mu; xn[i] = d; var += d * d; }
+    for (int i = 0; i < 16; ++i) xn[i] = x[i] - mu;
+    const float var = dot16(xn, xn);
     const float rs = rsqrtf(var * (1.f / 16.f) + 1e-5f);
 #pragma unroll
     for (int i = 0; i < 16; ++i) xn[i] *= rs;
@@ -800,10 +811,7 @@ swin_mlp_bwd_umma_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat1
         {
             float d[16];
             tmem_ld16(tlane + M_DYN, d);
-            float m1 = 0.f, m2 = 0.f;
-#pragma unroll
-            for (int c = 0; c < 16; ++c) { m1 += d[c]; m2 += d[c] * yn[c]; }
-            m1 *= (1.f / 16.f); m2 *= (1.f / 16.f);
+            const float m1 = sum16(d) * (1.f / 16.f), m2 = dot16(d, yn) * (1.f / 16.f);
             float go[16];
             unpack16(pg, go);
 #pragma unroll
@@ -1212,10 +1220,7 @@ swin_attn_bwd_umma_kernel(const void* __restrict__ x, const __nv_bfloat16* __res
                 const uint32_t pg[8] = {c.x, c.y, c.z, c.w, e.x, e.y, e.z, e.w};
                 unpack16(pg, gyr);
             }
-            float m1 = 0.f, m2 = 0.f;
-#pragma unroll
-            for (int c = 0; c < 16; ++c) { m1 += d[c]; m2 += d[c] * xn[c]; }
-            m1 *= (1.f / 16.f); m2 *= (1.f / 16.f);
+            const float m1 = sum16(d) * (1.f / 16.f), m2 = dot16(d, xn) * (1.f / 16.f);
 #pragma unroll
             for (int c = 0; c < 16; ++c) d[c] = gyr[c] + rstd * (d[c] - m1 - xn[c] * m2);
             if (tk.valid) {
@@ -1286,10 +1291,7 @@ embed_bwd_tokens_kernel(const __nv_bfloat16* __restrict__ gtok, const float* __r
 #pragma unroll
             for (int c = 0; c < 16; ++c) e[c] = w[c] * x + b[c];
             const float rs = ln_row(e, en);
-            float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-            for (int c = 0; c < 16; ++c) { s1 += d[c]; s2 += d[c] * en[c]; }
-            s1 *= (1.f / 16.f); s2 *= (1.f / 16.f);
+            const float s1 = sum16(d) * (1.f / 16.f), s2 = dot16(d, en) * (1.f / 16.f);
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
                 const float ge = rs * (d[c] - s1 - en[c] * s2);
