@@ -22,7 +22,7 @@
 namespace conv96u {
 
 constexpr int TR = 16, TC = 8, HR = TR + 2, HC = TC + 2;
-constexpr int NB = 4;                                  // weight-tap ring depth (96 -> 96 only)
+constexpr int NB_MAX = 8;                              // weight-tap ring depth (96 -> 96 only): 4 (forward, two-slice halos) or 8 (data gradient)
 constexpr int B_SBO = 128;
 constexpr int NLOAD = 256;                             // loader threads (warps 0-7)
 constexpr int NEPI = 128;                              // epilogue threads (warps 8-11: warp & 3 = TMEM lane quadrant)
@@ -65,6 +65,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     }
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// TMA bulk copy global -> shared (cp.async.bulk, SASS UBLKCP), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
@@ -124,6 +132,7 @@ conv96_umma_kernel(UP p) {
     constexpr int B_TAP = CO * CI * 2;                     // bytes per tap, canonical [kc][ng][8][16 B]
     constexpr int B_LBO = (CO / 8) * 128;
     constexpr bool RESIDENT = 18 * B_TAP <= 64 * 1024;
+    constexpr int NB = MODE == U_DGRAD ? 8 : 4;            // ring depth: the one-slice halos of the data gradient leave room for 8 taps in flight
     constexpr int B_SLOTS = RESIDENT ? 18 : NB;
     constexpr int TMEM_COLS = 2 * CO > 128 ? 256 : (2 * CO > 64 ? 128 : (2 * CO > 32 ? 64 : 32));
     constexpr uint32_t IDESC = idesc_n(CO);
@@ -135,12 +144,12 @@ conv96_umma_kernel(UP p) {
     unsigned char* halo = smem_raw;                                        // [2][KC][NPX][16 B]
     unsigned char* Bring = smem_raw + 2 * ((HALO + 127) / 128 * 128);      // [B_SLOTS][B_TAP]
     float* bias_s = reinterpret_cast<float*>(Bring + B_SLOTS * B_TAP);     // [CO]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + CO);             // full[2] | accdone[2] | accfree[2] | bslot[NB] | halofree[2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + NB);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + CO);             // full[2] | accdone[2] | accfree[2] | bslot[NB] | halofree[2] | wfull[NB]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * NB_MAX);
     constexpr int HALO_PAD = (HALO + 127) / 128 * 128;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t bar_full = smem_u32(&bars[0]), bar_done = smem_u32(&bars[2]), bar_free = smem_u32(&bars[4]), bar_slot = smem_u32(&bars[6]),
-                   bar_hfree = smem_u32(&bars[6 + NB]);
+                   bar_hfree = smem_u32(&bars[6 + NB_MAX]), bar_wfull = smem_u32(&bars[8 + NB_MAX]);
 
     if (tid < CO) bias_s[tid] = p.bias ? p.bias[tid] : 0.f;
     if (warp == MMA_WARP) {
@@ -151,7 +160,7 @@ conv96_umma_kernel(UP p) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar_full + 8 * i, NLOAD); mbar_init(bar_done + 8 * i, 1); mbar_init(bar_free + 8 * i, NEPI); mbar_init(bar_hfree + 8 * i, 1);
         }
-        for (int i = 0; i < NB; ++i) mbar_init(bar_slot + 8 * i, 1);
+        for (int i = 0; i < NB; ++i) { mbar_init(bar_slot + 8 * i, 1); mbar_init(bar_wfull + 8 * i, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -221,17 +230,16 @@ conv96_umma_kernel(UP p) {
             const uint32_t it = g / NT;
             return tile_ft(it, (int)(g - it * NT));
         };
+        // one TMA bulk copy per weight tap (18 KB), completion on the slot's mbarrier
         auto load_B = [&](uint32_t g) {
-            const uint4* src = reinterpret_cast<const uint4*>(p.wB + (size_t)tap_ft(g) * CO * CI);
-            const uint32_t dst = smem_u32(Bring) + (g % NB) * B_TAP;
-#pragma unroll 4
-            for (int i = lane; i < B_TAP / 16; i += 32)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 16), "l"(src + i) : "memory");
+            if (lane == 0) {
+                const uint32_t bar = bar_wfull + 8 * (g % NB);
+                mbar_expect_tx(bar, B_TAP);
+                bulk_g2s(smem_u32(Bring) + (g % NB) * B_TAP, p.wB + (size_t)tap_ft(g) * CO * CI, B_TAP, bar);
+            }
         };
-        for (uint32_t g = 0; g < NB; ++g) {                              // fill the ring (empty groups keep the count uniform)
+        for (uint32_t g = 0; g < NB; ++g)                                // fill the ring
             if (g < total_taps) load_B(g);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        }
         uint32_t g = 0;
         for (uint32_t it = 0; it < ntile; ++it) {
             const uint32_t b = it & 1;
@@ -243,11 +251,8 @@ conv96_umma_kernel(UP p) {
             const uint32_t dcol = tmem_base + b * CO;
 #pragma unroll 1
             for (int j = 0; j < NT; ++j, ++g) {
-                // tap g has landed once at most NB-2 younger groups are pending (group index == tap index)
-                asm volatile("cp.async.wait_group %0;" ::"n"(NB - 2) : "memory");
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
                 if (lane == 0) {
+                    mbar_wait(bar_wfull + 8 * (g % NB), (g / NB) & 1u);                     // tap g has landed in its slot
                     const int kt = MODE == U_FWD ? j / 9 : 0, kh = (j / 3) % 3, kw = j % 3;
                     const uint64_t ad = adesc0 + (uint64_t)((kt * HR + kh) * HC + kw);
                     const uint64_t bd = make_desc(smem_u32(Bring) + (g % NB) * B_TAP, B_LBO, B_SBO);
@@ -265,10 +270,9 @@ conv96_umma_kernel(UP p) {
                 if (g >= 1) {
                     const uint32_t gp = g - 1;
                     if (gp + NB < total_taps) {
-                        mbar_wait(bar_slot + 8 * (gp % NB), (gp / NB) & 1u);
+                        if (lane == 0) mbar_wait(bar_slot + 8 * (gp % NB), (gp / NB) & 1u);
                         load_B(gp + NB);
                     }
-                    asm volatile("cp.async.commit_group;" ::: "memory");
                 }
             }
         }
@@ -406,8 +410,8 @@ static int launch96(const UP& p, int64_t total, cudaStream_t st) {
     constexpr int ktin = MODE == U_FWD ? 2 : 1;
     constexpr size_t halo_pad = ((size_t)(GI / 8) * (ktin * HR * HC * 16 + 16) + 127) / 128 * 128;
     constexpr size_t b_tap = (size_t)GO * GI * 2;
-    constexpr size_t slots = 18 * b_tap <= 64 * 1024 ? 18 : NB;
-    constexpr size_t smem = 2 * halo_pad + slots * b_tap + GO * 4 + (8 + NB) * 8 + 16;
+    constexpr size_t slots = 18 * b_tap <= 64 * 1024 ? 18 : (MODE == U_DGRAD ? 8 : 4);
+    constexpr size_t smem = 2 * halo_pad + slots * b_tap + GO * 4 + (8 + 2 * NB_MAX) * 8 + 16;
     constexpr int tmem_cols = 2 * GO > 128 ? 256 : (2 * GO > 64 ? 128 : (2 * GO > 32 ? 64 : 32));
     auto kern = conv96_umma_kernel<MODE, GI, GO>;
     IDEE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "conv3d(umma96)");
