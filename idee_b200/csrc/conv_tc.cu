@@ -1760,7 +1760,16 @@ int conv_tc_dgrad(const idee_conv_desc* d, const void* gy, const float* w, const
         const int tiles_h = (d->Hi + TH - 1) / TH, tiles_w = (d->Wi + TW - 1) / TW;
         const int64_t tpv = (int64_t)d->N * d->Ti * tiles_h * tiles_w;
         IDEE_REQUIRE(tpv < (1ll << 31), "conv3d_dgrad(cls ->1): too many tiles");
-        int nb = (idee_num_sms() * 8 + d->V - 1) / d->V;
+        // persistent grid of exactly one resident wave (80 registers at 96 channels: 6 CTAs per SM, not 8)
+        int per_sm = 0;
+        if ((d->Cin == 16 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cls_dgrad_scalar_tc_kernel<16>, 128, 0)
+                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cls_dgrad_scalar_tc_kernel<96>, 128, 0)) != cudaSuccess || per_sm < 1) {
+            cudaGetLastError();
+            per_sm = 4;
+        }
+        if (per_sm > 8) per_sm = 8;
+        int nb = (idee_num_sms() * per_sm) / d->V;
+        if (nb < 1) nb = 1;
         if (nb > tpv) nb = (int)tpv;
         dim3 grid(nb, d->V);
 #define IDEE_CLS_SCALAR_DGRAD(N_)                                                                                                  \

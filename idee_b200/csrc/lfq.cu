@@ -205,11 +205,14 @@ __global__ void __launch_bounds__(128) lfq_bwd_finalize_kernel(const double* __r
     if (t == 0) grads[k] = (float)red[0];
 }
 
+// Grid-stride kernels with equal work per CTA: the grid is a whole number of resident waves (80 registers x 256 threads: 3 CTAs per
+// SM), otherwise the last, partly filled wave costs a full wave time (1184 CTAs = 2.67 waves ran as 3).
 int lfq_blocks(int64_t ntok) {
     int64_t nb = (ntok + LFQ_THREADS - 1) / LFQ_THREADS;
-    int64_t cap = idee_num_sms() * 8;
+    const int64_t wave = (int64_t)idee_num_sms() * 3;
+    int64_t cap = wave * 2;
     const int64_t per64 = (ntok + (int64_t)LFQ_THREADS * 64 - 1) / ((int64_t)LFQ_THREADS * 64);   // <= 64 tokens per thread
-    if (cap < per64) cap = per64;
+    if (cap < per64) cap = (per64 + wave - 1) / wave * wave;
     if (nb > cap) nb = cap;
     if (nb < 1) nb = 1;
     return (int)nb;

@@ -109,7 +109,7 @@ def test_bf16_medium_mask_flips_are_near_ties():
     assert ties_ok and frac >= 0.98, frac
 
 
-@pytest.mark.parametrize("dims", [(2, 4, 20, 28), (1, 8, 37, 19)])
+@pytest.mark.parametrize("dims", [(2, 4, 20, 28), (1, 8, 37, 19), (1, 5, 18, 9)])      # last: odd T (unpaired data-gradient tiles, unused last slice)
 def test_tcgen05_classifier_conv_matches_mma_sync_and_oracle(dims):
     """The warp-specialised tcgen05 / TMEM kernel for the 96->96 classifier conv (conv96_umma.cu: forward + data gradient incl.
     the fused ReLU mask) against the mma.sync kernel and the fp32 oracle (torch conv3d on CPU)."""
