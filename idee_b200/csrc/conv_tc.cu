@@ -1910,7 +1910,9 @@ int conv_tc_wgrad_splits(const idee_conv_desc* d) {
     const int n_occ = (d->Cout + NC - 1) / NC;
     int per_sm = wgrad_ctas_per_sm(d);
     if (per_sm < 1 || per_sm > 4) per_sm = 4;
-    int S = (idee_num_sms() * per_sm + d->Vw * n_ic * n_occ - 1) / (d->Vw * n_ic * n_occ);
+    // floor: the grid (S x weight sets x channel chunks) must not exceed the resident slots -- 594 persistent CTAs on 592 slots leave
+    // two CTAs to run a whole second wave alone
+    int S = (idee_num_sms() * per_sm) / (d->Vw * n_ic * n_occ);
     if (S < 1) S = 1;
     if (S > 512) S = 512;
     return S;
