@@ -1767,7 +1767,7 @@ int conv_tc_dgrad(const idee_conv_desc* d, const void* gy, const float* w, const
             cudaGetLastError();
             per_sm = 4;
         }
-        if (per_sm > 8) per_sm = 8;
+        if (per_sm > 16) per_sm = 16;
         int nb = (idee_num_sms() * per_sm) / d->V;
         if (nb < 1) nb = 1;
         if (nb > tpv) nb = (int)tpv;

@@ -1327,9 +1327,14 @@ int launch_attn_bwd(const idee_swin_desc* d, const Geom& g, const void* x, __nv_
         IDEE_LAUNCH_CHECK("swin_attn_bwd(umma,embed)");
         if (d->embed_gw) {
             // gx now holds the gradient w.r.t. the embedded tokens: one streaming pass turns it into d{embed w, b}
-            embed_bwd_tokens_kernel<<<dim3(per_v, d->V), 256, 0, st>>>(gx, g.emb_x, g.emb_w, g.emb_b, part_emb, d->N, d->V, d->T * d->H * d->W);
+            int occ = 0;                                        // one resident wave (122 registers x 256 threads: 2 CTAs per SM)
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, embed_bwd_tokens_kernel, 256, 0) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 1; }
+            int nb_e = idee_num_sms() * occ / d->V;
+            if (nb_e > per_v) nb_e = per_v;                     // part_emb holds per_v slots per variable
+            if (nb_e < 1) nb_e = 1;
+            embed_bwd_tokens_kernel<<<dim3(nb_e, d->V), 256, 0, st>>>(gx, g.emb_x, g.emb_w, g.emb_b, part_emb, d->N, d->V, d->T * d->H * d->W);
             IDEE_LAUNCH_CHECK("embed_bwd_tokens");
-            embed_grad_finalize_kernel<<<d->V, 32, 0, st>>>(part_emb, per_v, d->embed_gw, d->embed_gb);
+            embed_grad_finalize_kernel<<<d->V, 32, 0, st>>>(part_emb, nb_e, d->embed_gw, d->embed_gb);
             IDEE_LAUNCH_CHECK("embed_grad_finalize");
         }
     } else {
