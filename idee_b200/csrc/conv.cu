@@ -293,6 +293,18 @@ conv_wgrad_kernel(WgradP p) {
     }
 }
 
+// sum of n floats at stride `stride` in four interleaved accumulators (fixed order: deterministic; four loads in flight per step
+// instead of a dependent chain of n adds behind n load latencies)
+__device__ __forceinline__ float strided_sum4(const float* p, int n, int64_t stride) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int s = 0;
+    for (; s + 4 <= n; s += 4) {
+        a0 += p[(int64_t)s * stride]; a1 += p[(int64_t)(s + 1) * stride]; a2 += p[(int64_t)(s + 2) * stride]; a3 += p[(int64_t)(s + 3) * stride];
+    }
+    for (; s < n; ++s) a0 += p[(int64_t)s * stride];
+    return (a0 + a1) + (a2 + a3);
+}
+
 // second stage: one thread per entry of the PARTIAL layout (tap, c, o: consecutive threads read consecutive floats of every
 // partial block), summed over the S splits in a fixed order, scattered into the reference layout [o][c][tap] / [o]
 __global__ void conv_wgrad_reduce_kernel(const float* __restrict__ partials, float* __restrict__ gw, float* __restrict__ gb,
@@ -309,15 +321,11 @@ __global__ void conv_wgrad_reduce_kernel(const float* __restrict__ partials, flo
     if (slot < NT * 256) {
         const int ft = slot >> 8, c = ic * 16 + ((slot >> 4) & 15), o = oc * 16 + (slot & 15);
         if (c >= FCI || o >= FCO) return;
-        float acc = 0.f;
-        for (int s = 0; s < S; ++s) acc += p[(int64_t)s * PS];
-        gw[wset * w_set_stride + ((int64_t)o * FCI + c) * NT + ft] = acc;
+        gw[wset * w_set_stride + ((int64_t)o * FCI + c) * NT + ft] = strided_sum4(p, S, PS);
     } else if (gb && ic == 0) {
         const int o = oc * 16 + (slot - NT * 256);
         if (o >= FCO) return;
-        float acc = 0.f;
-        for (int s = 0; s < S; ++s) acc += p[(int64_t)s * PS];
-        gb[wset * b_set_stride + o] = acc;
+        gb[wset * b_set_stride + o] = strided_sum4(p, S, PS);
     }
 }
 

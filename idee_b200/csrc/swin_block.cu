@@ -588,16 +588,22 @@ __global__ void __launch_bounds__(256)
 swin_grad_sum_kernel(float* __restrict__ part_attn, float* __restrict__ part_mlp, int ncta_attn, int ncta_mlp) {
     constexpr int APS = ATT_PART_W + NH * G * G;
     const int v = blockIdx.y, e = blockIdx.x * 256 + threadIdx.x;
+    // four interleaved accumulators: four loads in flight per step instead of a dependent add behind every load latency
+    auto sum4 = [](const float* p, int n, int64_t stride) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int c = 0;
+        for (; c + 4 <= n; c += 4) {
+            a0 += p[(int64_t)c * stride]; a1 += p[(int64_t)(c + 1) * stride]; a2 += p[(int64_t)(c + 2) * stride]; a3 += p[(int64_t)(c + 3) * stride];
+        }
+        for (; c < n; ++c) a0 += p[(int64_t)c * stride];
+        return (a0 + a1) + (a2 + a3);
+    };
     if (e < APS) {
         float* p = part_attn + (int64_t)v * ncta_attn * APS + e;
-        float acc = 0.f;
-        for (int c = 0; c < ncta_attn; ++c) acc += p[(int64_t)c * APS];
-        p[0] = acc;
+        p[0] = sum4(p, ncta_attn, APS);
     } else if (e < APS + MLP_PART) {
         float* p = part_mlp + (int64_t)v * ncta_mlp * MLP_PART + (e - APS);
-        float acc = 0.f;
-        for (int c = 0; c < ncta_mlp; ++c) acc += p[(int64_t)c * MLP_PART];
-        p[0] = acc;
+        p[0] = sum4(p, ncta_mlp, MLP_PART);
     }
 }
 
@@ -615,17 +621,20 @@ swin_grad_finalize_kernel(const float* __restrict__ part_attn, const float* __re
     for (int e = threadIdx.x; e < MLP_PART; e += blockDim.x) sum_mlp[e] = part_mlp[(int64_t)v * ncta_mlp * MLP_PART + e];
     __syncthreads();
     float* gp = gparams + (int64_t)v * pstride;
-    for (int e = threadIdx.x; e < po.total; e += blockDim.x) {
-        float val;
-        if (e < po.qkv_w) {                       // table entry (row, head): every (i,j) that indexes it
-            const int row = e / NH, h = e % NH;
-            val = 0.f;
-            for (int ij = 0; ij < G * G; ++ij)
-                if (rel_index[ij] == row) val += sum_attn[ATT_PART_W + h * G * G + ij];
-        } else if (e < po.fc1_w) val = sum_attn[e - po.qkv_w];
-        else val = sum_mlp[e - po.fc1_w];
-        gp[e] = val;
+    // bias-table entry (row, head) = sum over every (i, j) that indexes it: one warp per entry scans the G*G pairs, fixed-order
+    // shuffle tree (the table is the reference's relative_position_index buffer, read as data)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int e = warp; e < po.qkv_w; e += nwarps) {
+        const int row = e / NH, h = e % NH;
+        float val = 0.f;
+        for (int ij = lane; ij < G * G; ij += 32)
+            if (rel_index[ij] == row) val += sum_attn[ATT_PART_W + h * G * G + ij];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+        if (lane == 0) gp[e] = val;
     }
+    for (int e = po.qkv_w + threadIdx.x; e < po.total; e += blockDim.x)
+        gp[e] = e < po.fc1_w ? sum_attn[e - po.qkv_w] : sum_mlp[e - po.fc1_w];
 }
 
 template <int G>
