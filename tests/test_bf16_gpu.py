@@ -321,6 +321,61 @@ def test_tcgen05_proj_dgrad_direct_matches_mma_sync(shape, masked):
     assert float((gx0 != gx1).float().mean()) < 2e-3                              # same operands: only ties of the final rounding differ
 
 
+@pytest.mark.parametrize("shape", [(1, 2, 1, 9, 11), (2, 6, 8, 40, 48), (1, 3, 4, 21, 37)])
+def test_fused_conv_backward_matches_separate_entry_points(shape):
+    """idee_conv3d_bwd on the folded 16 -> 1 proj conv (bf16 input, ReLU mask = the input): the ONE fused kernel must reproduce
+    idee_conv3d_wgrad + idee_conv3d_dgrad called separately (same bf16 operands; the weight gradient bit for bit per split, the
+    data gradient up to the final bf16 rounding) and torch autograd on the bf16-rounded operands."""
+    import ctypes as C
+    import torch.nn.functional as F
+    from idee_b200 import _lib as L, ops
+    N, V, T, H, W = shape
+    g = torch.Generator(device="cuda").manual_seed(17)
+    x = torch.randn(N, V, T, H, W, 16, device="cuda", generator=g).relu().to(torch.bfloat16)
+    w = (torch.randn(V, 1, 16, 3, 3, 3, device="cuda", generator=g) * 0.1).contiguous()
+    gy = torch.randn(N, V, T, H, W, 1, device="cuda", generator=g).contiguous()
+    lib = L.load()
+    old = L.PRECISION
+    L.set_precision("bf16")
+    try:
+        d = ops._conv_desc((N, V, T, H, W), (x.stride(0), x.stride(1), x.stride(2), x.stride(3), x.stride(4)),
+                           (gy.stride(0), gy.stride(1), gy.stride(2), gy.stride(3), gy.stride(4)), V, 16, 1, True, False, 1, 1, 0, 0)
+        d.x_dtype, d.y_dtype, d.gx_dtype, d.cin_real = 1, 0, 1, 0
+
+        def buffers():
+            return (torch.empty_like(x), torch.empty_like(w), torch.empty(V, 1, device="cuda"))
+
+        gx0, gw0, gb0 = buffers()
+        nws = max(lib.idee_conv3d_wgrad_workspace_bytes(C.byref(d)), lib.idee_conv3d_dgrad_workspace_bytes(C.byref(d)))
+        ws = L.workspace(nws, x.device)
+        L.check(lib.idee_conv3d_wgrad(C.byref(d), x.data_ptr(), gy.data_ptr(), gw0.data_ptr(), gb0.data_ptr(), ws.data_ptr(), nws, L.stream()), "wgrad")
+        L.check(lib.idee_conv3d_dgrad(C.byref(d), gy.data_ptr(), w.data_ptr(), x.data_ptr(), gx0.data_ptr(), ws.data_ptr(), nws, L.stream()), "dgrad")
+        gx1, gw1, gb1 = buffers()
+        nws = lib.idee_conv3d_bwd_workspace_bytes(C.byref(d))
+        ws = L.workspace(nws, x.device)
+        L.check(lib.idee_conv3d_bwd(C.byref(d), x.data_ptr(), gy.data_ptr(), w.data_ptr(), x.data_ptr(), gx1.data_ptr(), gw1.data_ptr(),
+                                    gb1.data_ptr(), ws.data_ptr(), nws, L.stream()), "bwd")
+        torch.cuda.synchronize()
+    finally:
+        L.set_precision(old)
+    # oracle: fp32 autograd on the bf16-rounded operands
+    xr = x.float().requires_grad_(True)
+    wr = w.to(torch.bfloat16).float().requires_grad_(True)
+    tot = 0
+    for v in range(V):
+        yi = F.conv3d(F.pad(xr[:, v].permute(0, 4, 1, 2, 3), (1, 1, 1, 1, 1, 1), mode="replicate"), wr[v])
+        tot = tot + (yi * gy[:, v].permute(0, 4, 1, 2, 3)).sum()
+    tot.backward()
+    want_gx = xr.grad * (x > 0)
+    scale = float(want_gx.abs().max())
+    for got in (gx0, gx1):
+        assert float((got.float() - want_gx).abs().max()) <= 2 ** -6 * scale       # bf16 operands (gy rounded) + bf16 result
+    assert float((gx0.float() - gx1.float()).abs().max()) <= 2 ** -7 * scale
+    assert rel_err(gw1, wr.grad) < TOL and rel_err(gw0, wr.grad) < TOL
+    assert rel_err(gw1, gw0) < 1e-5                                                 # same products, different split boundaries
+    assert rel_err(gb1, gy.sum(dim=(0, 2, 3, 4, 5)).reshape(V, 1)) < 1e-5 and rel_err(gb0, gb1) < 1e-5
+
+
 def test_folded_last_conv_matches_conv_then_project_in():
     """VQ_model's bf16 path evaluates proj_var[2] followed by LFQ.project_in as ONE 16 -> 1 conv (Swin_3D.forward_tokens(fold_last=...)):
     the scalar it feeds to the quantiser must equal project_in(encoder output), and so must the gradients that reach the last
