@@ -283,6 +283,187 @@ __global__ void conv96_wgrad_reduce_kernel(const float* __restrict__ partials, f
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// 16 -> 96 (the joint head's first conv on the 16-channel plane image): with N = 16 input channels per tap the kernel above re-reads
+// the 96-channel gy operand for every one of its 18 taps (85 KB of shared-memory operand reads per 16 pixels).  Here the roles are
+// swapped and the three kh taps are STACKED along M:  D_kw[(kh, ci)][co] += x[row + kh][col + kw][ci] * gy[row][col][co]
+//   A = halo slice, MN-major, M = 64 = 4 row slots x 16 ci: the slice is stored [row][chunk][col][16 B] (chunk stride 160 B, row
+//       stride 320 B), so the eight M core matrices (row slot s, chunk) sit at the uniform stride 160 B; slot 3 is idle;
+//   B = gy tile, MN-major, N = 96 co;   three MMAs (kw) + one bias MMA (A = ones) per 16 pixels: 15 KB of operand reads.
+// A CTA owns one input time slice kt (grid = 2 x S) and the 3 x 96 + 96 accumulator columns of its nine taps + bias.
+// ------------------------------------------------------------------------------------------------------------------------
+constexpr int X2ROWS = HR + 1;                                    // + one slack row read by the idle row slot
+constexpr int X2BUF = (X2ROWS * 2 * HC * 16 + 127) / 128 * 128;
+constexpr int PART2 = 9 * 16 * CO + CO;                           // floats per CTA: [kh][kw][ci][co] | db[co]
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv16_wgrad_stack_kernel(WPU p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* gbuf = smem_raw;                                        // [2][12 chunks][128 px][16 B]
+    unsigned char* xbuf = smem_raw + 2 * GBUF;                             // [2][19 rows][2 chunks][10 cols][16 B]
+    unsigned char* ones = xbuf + 2 * X2BUF;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ones + 128);              // full[2] | done[2] | final
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t bar_full = smem_u32(&bars[0]), bar_done = smem_u32(&bars[2]), bar_final = smem_u32(&bars[4]);
+    const int kt = blockIdx.x & 1, slice = blockIdx.x >> 1;
+
+    if (tid < 32) reinterpret_cast<uint32_t*>(ones)[tid] = 0x3F803F80u;
+    for (int i = tid; i < 2 * X2BUF / 16; i += NTHREADS) reinterpret_cast<uint4*>(xbuf)[i] = make_uint4(0u, 0u, 0u, 0u);   // slack rows: finite
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_full + 8 * i, NLOAD); mbar_init(bar_done + 8 * i, 1); }
+        mbar_init(bar_final, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    const uint32_t per = (p.total_tiles + p.S - 1) / p.S;
+    const uint32_t first = min(p.total_tiles, (uint32_t)slice * per), last = min(p.total_tiles, first + per);
+    const uint32_t ntile = last - first;
+    struct Tile { int n, t, h0, w0; };
+    auto decode = [&](uint32_t tile) {
+        Tile c;
+        uint32_t r = tile;
+        c.w0 = (int)(r % (uint32_t)p.tiles_w) * TC; r /= (uint32_t)p.tiles_w;
+        c.h0 = (int)(r % (uint32_t)p.tiles_h) * TR; r /= (uint32_t)p.tiles_h;
+        c.t = (int)(r % (uint32_t)p.To); c.n = (int)(r / (uint32_t)p.To);
+        return c;
+    };
+
+    if (warp == MMA_WARP) {
+        constexpr uint32_t ID = idesc_mn(64, CO);
+        const uint64_t ones_desc = make_desc(smem_u32(ones), 0, 0);
+        for (uint32_t it = 0; it < ntile; ++it) {
+            const uint32_t b = it & 1;
+            mbar_wait(bar_full + 8 * b, (it >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint64_t bdesc0 = make_desc(smem_u32(gbuf) + b * GBUF, TC * 16, GCHUNK);          // gy: K next tile row, N next chunk
+                const uint64_t adesc0 = make_desc(smem_u32(xbuf) + b * X2BUF, 2 * HC * 16, HC * 16);   // x: K next halo row, M next (slot, chunk)
+#pragma unroll 1
+                for (int ks = 0; ks < TR / 2; ++ks) {
+                    const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
+                    const uint64_t bd = bdesc0 + (uint64_t)(ks * 2 * TC);
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw)
+                        umma(tmem_base + kw * CO, adesc0 + (uint64_t)(2 * ks * 2 * HC + kw), bd, ID, acc);
+                    umma(tmem_base + 3 * CO, ones_desc, bd, ID, acc);
+                }
+                umma_commit(bar_done + 8 * b);
+            }
+            __syncwarp();
+        }
+        if (lane == 0) umma_commit(bar_final);
+        __syncwarp();
+    } else {
+        constexpr int XU = NPX * 4, G4 = CO / 4, GU = TR * TC * G4, TOTAL = XU + GU;
+        constexpr int DEPTH = (TOTAL + NLOAD - 1) / NLOAD;
+        auto unit = [&](int e, const Tile& c, bool t_ok, const float* x_n, const float* g_n, const float*& src) -> int {
+            src = nullptr;
+            if (e < XU) {
+                const int q = e >> 2, c4 = e & 3, hh = q / HC, ww = q - hh * HC;
+                const int hi = c.h0 + hh - 1, wi = c.w0 + ww - 1;
+                if (t_ok && (unsigned)hi < (unsigned)p.Hi && (unsigned)wi < (unsigned)p.Wi) src = x_n + (hi * p.x_sh + wi * p.x_sw) + c4 * 4;
+                return (hh * 2 + (c4 >> 1)) * (HC * 16) + ww * 16 + (c4 & 1) * 8;
+            }
+            if (e < TOTAL) {
+                const int eg = e - XU, q = eg / G4, c4 = eg - q * G4, r = q / TC, cc = q - r * TC;
+                const int h = c.h0 + r, w = c.w0 + cc;
+                if (h < p.Hi && w < p.Wi) src = g_n + (h * p.gy_sh + w * p.gy_sw) + c4 * 4;
+                return 2 * X2BUF + (c4 >> 1) * GCHUNK + q * 16 + (c4 & 1) * 8;             // marks a gy unit
+            }
+            return -1;
+        };
+        for (uint32_t it = 0; it < ntile; ++it) {
+            const uint32_t b = it & 1;
+            const Tile c = decode(first + it);
+            unsigned char* xdst = xbuf + b * X2BUF;
+            unsigned char* gdst = gbuf + b * GBUF;
+            const float* x_n = p.x + c.n * p.x_sn + (int64_t)(2 * c.t + kt) * p.x_st;
+            const float* g_n = p.gy + c.n * p.gy_sn + (int64_t)c.t * p.gy_st;
+            const bool t_ok = 2 * c.t + kt < p.Ti;
+            float4 f[DEPTH];
+#pragma unroll
+            for (int u = 0; u < DEPTH; ++u) {
+                const float* src;
+                unit(tid + u * NLOAD, c, t_ok, x_n, g_n, src);
+                f[u] = src ? ldg4(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (it >= 2) mbar_wait(bar_done + 8 * b, ((it >> 1) - 1) & 1u);
+#pragma unroll
+            for (int u = 0; u < DEPTH; ++u) {
+                const float* src;
+                const int o = unit(tid + u * NLOAD, c, t_ok, x_n, g_n, src);
+                if (o >= 0) {
+                    unsigned char* dst = o >= 2 * X2BUF ? gdst + (o - 2 * X2BUF) : xdst + o;
+                    *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16(f[u].x, f[u].y), pack_bf16(f[u].z, f[u].w));
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(bar_full + 8 * b);
+        }
+    }
+    // accumulators -> partials: M = 64 rows (kh slot s, ci) live in lane ci of warp s
+    float* part = p.partials + (size_t)blockIdx.x * PART2;
+    if (warp < 3) {
+        if (ntile > 0) {
+            mbar_wait(bar_final, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        const uint32_t tl = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+        for (int col0 = 0; col0 < 4 * CO; col0 += 32) {
+            float v[32];
+            if (ntile > 0) tmem_ld32(tl + col0, v);
+            else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            }
+            const int kw = col0 / CO, co0 = col0 - kw * CO;
+            if (kw < 3) {
+                if (lane < 16) {
+                    float* dst = part + ((size_t)((warp * 3 + kw) * 16 + lane)) * CO + co0;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                }
+            } else if (warp == 0 && lane == 0) {
+                float* dst = part + (size_t)9 * 16 * CO + co0;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+}
+
+// gw[co][ci][kt][kh][kw] = sum over the S tile slices of part[slice * 2 + kt][kh][kw][ci][co]; gb from the kt = 0 CTAs
+__global__ void conv16_wgrad_stack_reduce_kernel(const float* __restrict__ partials, float* __restrict__ gw, float* __restrict__ gb, int S) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;                // (kt, j9, ci, co), co fastest: coalesced partial reads
+    if (e < 18 * 16 * CO) {
+        const int co = e % CO, ci = (e / CO) % 16, j9 = (e / (CO * 16)) % 9, kt = e / (CO * 16 * 9);
+        const float* src = partials + (size_t)kt * PART2 + ((size_t)j9 * 16 + ci) * CO + co;
+        float acc = 0.f;
+        for (int s = 0; s < S; ++s) acc += src[(size_t)s * 2 * PART2];
+        gw[((size_t)co * 16 + ci) * 18 + kt * 9 + j9] = acc;
+    } else if (e < 18 * 16 * CO + CO && gb) {
+        const int co = e - 18 * 16 * CO;
+        const float* src = partials + (size_t)9 * 16 * CO + co;
+        float acc = 0.f;
+        for (int s = 0; s < S; ++s) acc += src[(size_t)s * 2 * PART2];
+        gb[co] = acc;
+    }
+}
+
 }  // namespace conv96w
 
 using namespace conv96w;
@@ -297,8 +478,10 @@ bool conv16to96_wgrad_umma_eligible(const idee_conv_desc* d) {
            d->out_cpg == 6 && d->x_sw == 16 && d->y_sw == 96 && !d->x_dtype && !d->y_dtype;
 }
 
+static int stack_slices() { const int S = idee_num_sms() / 2; return S < 1 ? 1 : S; }
+
 size_t conv96_wgrad_umma_workspace_bytes(int Cin) {
-    return Cin == 96 ? sizeof(float) * (size_t)4 * wgrad_slices<96>() * Cfg<96>::PART : sizeof(float) * (size_t)wgrad_slices<16>() * Cfg<16>::PART;
+    return Cin == 96 ? sizeof(float) * (size_t)4 * wgrad_slices<96>() * Cfg<96>::PART : sizeof(float) * (size_t)2 * stack_slices() * PART2;
 }
 
 template <int CI_>
@@ -327,6 +510,30 @@ static int wgrad_run(const idee_conv_desc* d, const float* x, const float* gy, f
     return 0;
 }
 
+static int stack_run(const idee_conv_desc* d, const float* x, const float* gy, float* gw, float* gb, void* ws, cudaStream_t st) {
+    WPU p{};
+    p.x = x; p.gy = gy; p.partials = (float*)ws;
+    p.N = d->N; p.Ti = d->Ti; p.Hi = d->Hi; p.Wi = d->Wi; p.To = d->To;
+    IDEE_REQUIRE((int64_t)(d->Ti + 1) * d->x_st + (int64_t)(d->Hi + HR) * d->x_sh + (int64_t)(d->Wi + HC) * d->x_sw < (1ll << 31) &&
+                 (int64_t)(d->To + 1) * d->y_st + (int64_t)(d->Ho + TR) * d->y_sh + (int64_t)(d->Wo + TC) * d->y_sw < (1ll << 31),
+                 "conv3d_wgrad(umma 16->96): tensor too large for 32-bit image-relative offsets");
+    p.x_sn = d->x_sn; p.x_st = (int)d->x_st; p.x_sh = (int)d->x_sh; p.x_sw = (int)d->x_sw;
+    p.gy_sn = d->y_sn; p.gy_st = (int)d->y_st; p.gy_sh = (int)d->y_sh; p.gy_sw = (int)d->y_sw;
+    p.tiles_w = (d->Wo + TC - 1) / TC; p.tiles_h = (d->Ho + TR - 1) / TR;
+    const int64_t total = (int64_t)d->N * d->To * p.tiles_h * p.tiles_w;
+    IDEE_REQUIRE(total < (1ll << 31), "conv3d_wgrad(umma 16->96): too many tiles");
+    p.total_tiles = (uint32_t)total;
+    p.S = stack_slices();
+    const size_t smem = 2 * (size_t)GBUF + 2 * (size_t)X2BUF + 128 + 5 * 8 + 16;
+    IDEE_CUDA(cudaFuncSetAttribute(conv16_wgrad_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "conv3d_wgrad(umma 16->96)");
+    conv16_wgrad_stack_kernel<<<2 * p.S, NTHREADS, smem, st>>>(p);
+    IDEE_LAUNCH_CHECK("conv3d_wgrad(umma 16->96)");
+    const int nel = 18 * 16 * CO + CO;
+    conv16_wgrad_stack_reduce_kernel<<<(nel + 255) / 256, 256, 0, st>>>(p.partials, gw, gb, p.S);
+    IDEE_LAUNCH_CHECK("conv3d_wgrad(umma 16->96) reduce");
+    return 0;
+}
+
 int conv96_wgrad_umma_run(const idee_conv_desc* d, const float* x, const float* gy, float* gw, float* gb, void* ws, cudaStream_t st) {
-    return d->Cin == 96 ? wgrad_run<96>(d, x, gy, gw, gb, ws, st) : wgrad_run<16>(d, x, gy, gw, gb, ws, st);
+    return d->Cin == 96 ? wgrad_run<96>(d, x, gy, gw, gb, ws, st) : stack_run(d, x, gy, gw, gb, ws, st);
 }
