@@ -293,39 +293,38 @@ conv_wgrad_kernel(WgradP p) {
     }
 }
 
-// sum of n floats at stride `stride` in four interleaved accumulators (fixed order: deterministic; four loads in flight per step
-// instead of a dependent chain of n adds behind n load latencies)
-__device__ __forceinline__ float strided_sum4(const float* p, int n, int64_t stride) {
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int s = 0;
-    for (; s + 4 <= n; s += 4) {
-        a0 += p[(int64_t)s * stride]; a1 += p[(int64_t)(s + 1) * stride]; a2 += p[(int64_t)(s + 2) * stride]; a3 += p[(int64_t)(s + 3) * stride];
-    }
-    for (; s < n; ++s) a0 += p[(int64_t)s * stride];
-    return (a0 + a1) + (a2 + a3);
-}
-
-// second stage: one thread per entry of the PARTIAL layout (tap, c, o: consecutive threads read consecutive floats of every
-// partial block), summed over the S splits in a fixed order, scattered into the reference layout [o][c][tap] / [o]
-__global__ void conv_wgrad_reduce_kernel(const float* __restrict__ partials, float* __restrict__ gw, float* __restrict__ gb,
-                                         int Vw, int FCI, int FCO, int NT, int n_ic, int n_oc, int S,
-                                         int64_t w_set_stride, int64_t b_set_stride) {
-    const int wset = blockIdx.y;
+// second stage: a CTA of 8 warps owns 32 consecutive entries of the PARTIAL layout (tap, c, o): lane = entry (consecutive lanes read
+// consecutive floats of every partial block), warp w sums the splits s = w, w + 8, ... in order, and the eight warp sums are added
+// in a fixed order: deterministic, and the S dependent load latencies of the one-thread-per-entry form become S / 8
+__global__ void __launch_bounds__(256)
+conv_wgrad_reduce_kernel(const float* __restrict__ partials, float* __restrict__ gw, float* __restrict__ gb,
+                         int Vw, int FCI, int FCO, int NT, int n_ic, int n_oc, int S,
+                         int64_t w_set_stride, int64_t b_set_stride) {
+    __shared__ float red[8][32];
+    const int wset = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int PS = NT * 256 + 16;
     const int64_t per_set = (int64_t)n_ic * n_oc * PS;
-    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // (ic, oc, slot)
-    if (q >= per_set) return;
-    const int slot = (int)(q % PS);
-    const int oc = (int)((q / PS) % n_oc), ic = (int)(q / ((int64_t)PS * n_oc));
-    const float* p = partials + ((((int64_t)wset * n_ic + ic) * n_oc + oc) * S) * PS + slot;
-    if (slot < NT * 256) {
-        const int ft = slot >> 8, c = ic * 16 + ((slot >> 4) & 15), o = oc * 16 + (slot & 15);
-        if (c >= FCI || o >= FCO) return;
-        gw[wset * w_set_stride + ((int64_t)o * FCI + c) * NT + ft] = strided_sum4(p, S, PS);
-    } else if (gb && ic == 0) {
-        const int o = oc * 16 + (slot - NT * 256);
-        if (o >= FCO) return;
-        gb[wset * b_set_stride + o] = strided_sum4(p, S, PS);
+    const int64_t q = (int64_t)blockIdx.x * 32 + lane;                    // (ic, oc, slot)
+    int slot = 0, oc = 0, ic = 0;
+    bool live = q < per_set;
+    int c = 0, o = 0, ft = 0;
+    bool is_bias = false;
+    if (live) {
+        slot = (int)(q % PS); oc = (int)((q / PS) % n_oc); ic = (int)(q / ((int64_t)PS * n_oc));
+        if (slot < NT * 256) { ft = slot >> 8; c = ic * 16 + ((slot >> 4) & 15); o = oc * 16 + (slot & 15); live = c < FCI && o < FCO; }
+        else { is_bias = true; o = oc * 16 + (slot - NT * 256); live = gb != nullptr && ic == 0 && o < FCO; }
+    }
+    float acc = 0.f;
+    if (live) {
+        const float* p = partials + ((((int64_t)wset * n_ic + ic) * n_oc + oc) * S) * PS + slot;
+        for (int s = warp; s < S; s += 8) acc += p[(int64_t)s * PS];
+    }
+    red[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && live) {
+        const float v = ((red[0][lane] + red[1][lane]) + (red[2][lane] + red[3][lane])) + ((red[4][lane] + red[5][lane]) + (red[6][lane] + red[7][lane]));
+        if (is_bias) gb[wset * b_set_stride + o] = v;
+        else gw[wset * w_set_stride + ((int64_t)o * FCI + c) * NT + ft] = v;
     }
 }
 
@@ -431,7 +430,7 @@ extern "C" int idee_conv3d_wgrad(const idee_conv_desc* d, const void* x, const v
         if (conv_tc_wgrad_partials(d, x, gy, (float*)workspace, st)) return 2;
         const int NT = (d->proj ? 3 : 2) * 9;
         const int64_t nel = (int64_t)((d->Cin + 15) / 16) * ((d->Cout + 15) / 16) * (NT * 256 + 16);
-        conv_wgrad_reduce_kernel<<<dim3((unsigned)((nel + 255) / 256), d->Vw), 256, 0, st>>>(
+        conv_wgrad_reduce_kernel<<<dim3((unsigned)((nel + 31) / 32), d->Vw), 256, 0, st>>>(
             (const float*)workspace, gw, gb, d->Vw, d->Cin, d->Cout, NT, (d->Cin + 15) / 16, (d->Cout + 15) / 16, conv_tc_wgrad_splits(d),
             (int64_t)d->Cin * d->Cout * NT, d->Cout);
         IDEE_LAUNCH_CHECK("conv3d_wgrad_reduce");
@@ -453,7 +452,7 @@ extern "C" int idee_conv3d_wgrad(const idee_conv_desc* d, const void* x, const v
     else conv_wgrad_kernel<18><<<grid, 18 * 16, 0, st>>>(p);
     IDEE_LAUNCH_CHECK("conv3d_wgrad");
     const int64_t nel = (int64_t)p.n_ic * p.n_oc * (NT * 256 + 16);
-    conv_wgrad_reduce_kernel<<<dim3((unsigned)((nel + 255) / 256), d->Vw), 256, 0, st>>>(
+    conv_wgrad_reduce_kernel<<<dim3((unsigned)((nel + 31) / 32), d->Vw), 256, 0, st>>>(
         p.partials, gw, gb, d->Vw, d->Cin, d->Cout, NT, p.n_ic, p.n_oc, p.S, (int64_t)d->Cin * d->Cout * NT, d->Cout);
     IDEE_LAUNCH_CHECK("conv3d_wgrad_reduce");
     return 0;
@@ -477,7 +476,7 @@ extern "C" int idee_conv3d_bwd(const idee_conv_desc* d, const void* x, const voi
         cudaStream_t st = (cudaStream_t)stream;
         if (conv_tc_bwd_fused_partials(d, x, gy, w, relu_src, gx, (float*)workspace, st)) return 2;
         const int64_t nel = 27 * 256 + 16;
-        conv_wgrad_reduce_kernel<<<dim3((unsigned)((nel + 255) / 256), d->Vw), 256, 0, st>>>(
+        conv_wgrad_reduce_kernel<<<dim3((unsigned)((nel + 31) / 32), d->Vw), 256, 0, st>>>(
             (const float*)workspace, gw, gb, d->Vw, d->Cin, d->Cout, 27, 1, 1, conv_tc_bwd_fused_splits(d), (int64_t)d->Cin * d->Cout * 27, d->Cout);
         IDEE_LAUNCH_CHECK("conv3d_bwd reduce");
         return 0;

@@ -114,13 +114,16 @@ lfq_fwd_kernel(const float* __restrict__ z, const float* __restrict__ w_in, cons
 // stats (float[8]): aux, per_sample_entropy, codebook_entropy, commit, mean p0, mean p1, ntok, 0
 __global__ void lfq_finalize_kernel(const double* __restrict__ partials, int nblocks, int64_t ntok, float lam_commit,
                                     float lam_ent, float gamma, float* __restrict__ stats) {
-    __shared__ double red[4][32];
+    __shared__ double red[8][4];
     double a[4] = {0, 0, 0, 0};
-    for (int b = threadIdx.x; b < nblocks; b += 32)
+    for (int b = threadIdx.x; b < nblocks; b += 256)
         for (int k = 0; k < 4; ++k) a[k] += partials[(int64_t)b * 4 + k];
     for (int k = 0; k < 4; ++k) a[k] = warp_sum_d(a[k]);
-    (void)red;
+    if ((threadIdx.x & 31) == 0)
+        for (int k = 0; k < 4; ++k) red[threadIdx.x >> 5][k] = a[k];
+    __syncthreads();
     if (threadIdx.x == 0) {
+        for (int k = 0; k < 4; ++k) { a[k] = 0.0; for (int w = 0; w < 8; ++w) a[k] += red[w][k]; }
         const double n = (double)ntok;
         const float h_tok = (float)(a[0] / n), p0 = (float)(a[1] / n), p1 = (float)(a[2] / n), commit = (float)(a[3] / n);
         const float h_cb = ent_term(p0) + ent_term(p1);
@@ -236,7 +239,7 @@ extern "C" int idee_lfq_fwd(const float* z, const float* w_in, const float* b_in
                                                             training, inv_temperature, (__nv_bfloat16*)zq_bf16);
     IDEE_LAUNCH_CHECK("lfq_fwd");
     if (training) {
-        lfq_finalize_kernel<<<1, 32, 0, st>>>((const double*)workspace, nb, ntok, lambda_commit, lambda_entropy, diversity_gamma, stats);
+        lfq_finalize_kernel<<<1, 256, 0, st>>>((const double*)workspace, nb, ntok, lambda_commit, lambda_entropy, diversity_gamma, stats);
         IDEE_LAUNCH_CHECK("lfq_finalize");
     }
     return 0;
