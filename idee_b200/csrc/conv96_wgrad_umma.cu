@@ -1,5 +1,5 @@
-// tcgen05 / TMEM weight gradient of the 96 -> 96 classifier convolution Conv3d(96, 96, (2,3,3), stride (2,1,1), pad (0,1,1))
-// (classifier/CNN_3D.py:84):   dW[co][ci][tap] = sum over output pixels p of gy[p][co] * x[p + tap][ci],   db[co] = sum_p gy[p][co].
+// tcgen05 / TMEM weight gradients of the joint classifier head: the 96 -> 96 convolution Conv3d(96, 96, (2,3,3), stride (2,1,1),
+// pad (0,1,1)) (classifier/CNN_3D.py:84; first kernel) and the head's first conv on the 16-channel plane image (second kernel):   dW[co][ci][tap] = sum over output pixels p of gy[p][co] * x[p + tap][ci],   db[co] = sum_p gy[p][co].
 //
 // The contraction runs over PIXELS, so both operands are read as MN-major views of channel-chunk planes (the construction of the
 // Swin weight-gradient GEMMs, swin_umma.cuh): the gy tile [128 pixels x 96] and one input time slice of the halo [18 x 10 pixels
@@ -27,8 +27,9 @@ constexpr int GBUF = (12 * GCHUNK + 127) / 128 * 128;
 constexpr int NLOAD = 512, MMA_WARP = NLOAD / 32, NTHREADS = NLOAD + 32;
 constexpr int TMEM_COLS = 512;
 
-// CI = 96 (the 96 -> 96 conv): four tap groups, one input time slice per CTA.  CI = 16 (the joint head's first conv on the
-// 16-channel plane image of the rank-1 form of z_q): all 18 taps (18 x 16 + 16 columns) in one CTA, both time slices in the halo.
+// CI = 96 (the 96 -> 96 conv, the instantiated case): four tap groups, one input time slice per CTA.  The CI = 16 parameters (all 18
+// taps as N = 16 MMAs in one CTA) describe the first tcgen05 form of the joint head's 16 -> 96 weight gradient; it re-read gy once
+// per tap and is superseded by conv16_wgrad_stack_kernel below.
 template <int CI_> struct Cfg {
     static constexpr int CI = CI_, KC = CI / 8;
     static constexpr int NGROUP = CI == 96 ? 4 : 1, MAXTAPS = CI == 96 ? 5 : 18, NPL = CI == 96 ? 1 : 2;   // halo time slices per CTA
